@@ -1,0 +1,109 @@
+/*
+ * mm2gb_chain.h -- C ABI of the B200-native anchor-chaining library (libmm2gb_chain.so).
+ *
+ * Two layers, both plain C (pointers and sizes only, no CUDA / torch types):
+ *
+ *  (1) The DROP-IN boundary: the four entry points minimap2's host driver already calls
+ *      (reference gpu/plutils.h:98-104; callers main.c:445,466 and map.c:1026,1069).  They are declared in
+ *      mm2gb_plchain.h (which needs the reference's minimap.h types) and implemented in
+ *      mm2-gb_b200/csrc/plchain_dropin.cpp on top of layer (2).
+ *
+ *  (2) The CORE chaining API below: a batch of reads' seeded anchors in, chain scores f[] and
+ *      predecessors p[] out (reference lchain.c:148-207 at max-chain-skip = infinity), plus the
+ *      backtracked chains u[] / compacted anchors (lchain.c:27-111).  It replaces what the reference
+ *      spreads over gpu/plchain.cu (orchestration), gpu/plmem.cu (buffers + H2D/D2H), gpu/plrange.cu
+ *      (window/segment kernel) and gpu/plscore.cu (score kernels).  Tests and bench.py bind it with ctypes.
+ *
+ * Every function returns 0 on success and a negative MM2GB_E* code on failure; mm2gb_last_error() gives the
+ * message.  Nothing here falls back to the CPU: without a CUDA device the calls fail.
+ */
+#ifndef MM2GB_CHAIN_H
+#define MM2GB_CHAIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM2GB_OK 0
+#define MM2GB_ECUDA (-1)    /* a CUDA runtime call failed */
+#define MM2GB_EARG (-2)     /* bad argument */
+#define MM2GB_ECAP (-3)     /* batch larger than the context capacity */
+#define MM2GB_ESTATE (-4)   /* slot busy / idle misuse */
+
+/* minimap.h:72 mm128_t.  x = rev<<63 | rid<<32 | rpos ; y = seg_id<<48 | flags<<40 | q_span<<32 | qpos */
+typedef struct { uint64_t x, y; } mm2gb_anchor_t;
+
+/* gpu/plutils.h:33-37 Misc -- identical layout (44 bytes), filled by build_misc (map.c:393-426) */
+typedef struct {
+    int max_iter, max_dist_x, max_dist_y, max_skip, bw, min_cnt, min_score, is_cdna, n_seg;
+    float chn_pen_gap, chn_pen_skip;
+} mm2gb_misc_t;
+
+typedef struct mm2gb_ctx mm2gb_ctx_t;
+
+/* per-batch counters filled by the device (for the pairs/s metric: pairs = sum_i (i - st_i), lchain.c:177) */
+typedef struct {
+    int64_t n_anchors;
+    int64_t n_pairs;       /* evaluated anchor pairs, equal to the reference's n_iter at max_skip = inf */
+    int32_t n_units;       /* independent work units the range kernel cut the batch into */
+    int32_t n_units_exact; /* units with a max_iter-clipped window, scored by the exact max_ii path (lchain.c:189-205) */
+    int32_t n_long;        /* units scored by the block-cooperative long kernel */
+    int32_t general_path;  /* 1 if the float-penalty / multi-segment score path was used for this batch */
+} mm2gb_stats_t;
+
+const char *mm2gb_last_error(void);
+int mm2gb_device_count(void);
+
+/* One context per (host thread, GPU).  `max_anchors` / `max_reads` bound one batch; `n_slots` (1..4) is the
+ * number of batches that may be in flight (each slot owns a stream, pinned staging and device buffers).
+ * Replaces plmem_stream_initialize + plrange/plscore_upload_misc (gpu/plmem.cu:558-624, plchain.cu:470-474). */
+int mm2gb_ctx_create(mm2gb_ctx_t **ctx, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc);
+void mm2gb_ctx_destroy(mm2gb_ctx_t *ctx);
+int mm2gb_ctx_set_misc(mm2gb_ctx_t *ctx, const mm2gb_misc_t *misc);
+
+/* ---- host-buffer path (what the drop-in uses; copies are part of the call) --------------------------- */
+
+/* Synchronous: chain reads r = 0..n_reads-1 whose anchors are a[off[r] .. off[r+1]) (x-sorted per read, as
+ * collect_seed_hits leaves them, map.c:329).  Outputs f[off[n_reads]] and p[off[n_reads]]; p is the index of the
+ * predecessor INSIDE the read, -1 for none (lchain.c:202).  stats may be NULL. */
+int mm2gb_chain_dp_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                        mm2gb_stats_t *stats);
+
+/* Asynchronous pair.  submit: stage anchors into the slot's pinned buffer, enqueue H2D + kernels + D2H on the slot's
+ * stream and return.  wait: block until the slot is done and expose the pinned result arrays (valid until the slot is
+ * submitted again).  gather variant takes one pointer per read (chain_read_t.a of each read, plutils.h:64). */
+int mm2gb_submit(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *a, const int64_t *off, int n_reads);
+int mm2gb_submit_gather(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads);
+int mm2gb_wait(mm2gb_ctx_t *ctx, int slot, const int32_t **f, const int32_t **p, const int64_t **off, mm2gb_stats_t *stats);
+int mm2gb_slot_busy(mm2gb_ctx_t *ctx, int slot);
+
+/* ---- device-resident path (kernel-only timing; inputs already in HBM) ---------------------------------- */
+
+/* d_a: device mm2gb_anchor_t[n_total]; d_off: device int64[n_reads+1]; d_f/d_p: device int32[n_total].
+ * Enqueues range + unit + score kernels on slot 0's stream; returns without synchronising. */
+int mm2gb_chain_dp_device(mm2gb_ctx_t *ctx, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p);
+int mm2gb_sync(mm2gb_ctx_t *ctx, int slot);
+/* the cudaStream_t of a slot, as an opaque pointer (so a caller can record its own events on it) */
+void *mm2gb_stream(mm2gb_ctx_t *ctx, int slot);
+/* stats of the last batch run through mm2gb_chain_dp_device (after mm2gb_sync) */
+int mm2gb_device_stats(mm2gb_ctx_t *ctx, mm2gb_stats_t *stats);
+
+/* Per-kernel device time of slot 0, accumulated with CUDA events while profiling is on.
+ * ms[0]=range ms[1]=unit-build ms[2]=score(short/mid) ms[3]=score(long) ms[4]=H2D ms[5]=D2H; launches[] likewise. */
+#define MM2GB_NTIMERS 6
+int mm2gb_profile(mm2gb_ctx_t *ctx, int enable);
+int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launches[MM2GB_NTIMERS]);
+
+/* ---- host stage: backtracking + compaction of one read (lchain.c:27-111) ---------------------------------
+ * u[<=n] (score<<32|count, ordered by chain start), b[<=n] compacted anchors.  Returns n_u (>=0); *n_b anchors kept.
+ * max_drop = is_cdna ? INT32_MAX : bw (lchain.c:151,162). */
+int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p, const mm2gb_anchor_t *a, int32_t min_cnt, int32_t min_sc,
+                        int32_t max_drop, uint64_t *u, mm2gb_anchor_t *b, int64_t *n_b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,476 @@
+// chain_kernels.cuh -- sm_100a device code of the anchor-chaining path.
+//
+// What is computed is minimap2-v2.24's mg_lchain_dp forward pass (reference lchain.c:148-207) at
+// max-chain-skip = infinity, bit for bit:
+//     f[i] = max( q_span(i), max_{st_i <= j < i} f[j] + comput_sc(a[i], a[j]) ),  p[i] = argmax (largest j on ties, -1 if
+//     nothing beats q_span(i)),   st_i = max( first j with same rid/strand and x_i - x_j <= max_dist_x , i - max_iter ).
+// How it is computed is NOT the reference's GPU layer (gpu/plrange.cu, gpu/plscore.cu: push DP, one barrier per anchor,
+// operands in global memory, an integer-log2 score that deviates from lchain.c).  Here:
+//   * the whole batch is one flat anchor array; k_range finds st_i by gallop + binary search, marks the independent-unit
+//     cuts (st_i == i) and the max_iter-clipped windows, and counts pairs;
+//   * units (runs between selected cuts) are scored by one warp each (k_score_units) or by a whole CTA (k_score_long),
+//     in tiles of 32 anchors: lane l owns anchor t0+l; predecessors older than the tile are swept with warp-uniform
+//     16-byte shared-memory loads (no cross-lane reduction at all), the 32x32 in-tile triangle is pre-scored in
+//     registers and resolved with one shuffle per step;
+//   * the gap penalty (int)(gap*dd + .5f*mg_log2(dd+1)) is an integer table when chn_pen_skip == 0 (all presets), and
+//     is otherwise evaluated with non-contracted fp32 ops in exactly lchain.c's order;
+//   * units that contain a clipped window run the exact max_ii state machine of lchain.c:189-205.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mm2gb {
+
+constexpr int kRangeThreads = 256;          // anchors per k_range block
+constexpr int kGroupsPerBlock = kRangeThreads / 32;
+constexpr int kNeg = -(1 << 30);            // "rejected pair" (lchain.c returns INT32_MIN); never wins a max
+constexpr int kLutMax = 4096;               // largest bw served by the integer penalty table
+
+// chaining parameters after the adjustments of lchain.c:160-161
+struct DevParams {
+    int max_iter, max_dist_x, max_dist_y, bw, is_cdna, n_seg;
+    int maxd_q;       // min(max_dist_x, max_dist_y): the dq bound when both anchors share a segment id
+    int lut_n;        // bw + 1 when the byte penalty table is valid (chn_pen_skip == 0, bw <= kLutMax, max entry <= 255), else 0
+    float pen_gap, pen_skip;
+};
+
+// device-side counters of one batch
+struct Counters {
+    int next_unit;          // work-queue cursor of k_score_units
+    int n_units;            // written by k_scan
+    int multi_sid;          // 1 if some read mixes segment ids (forces the general score path)
+    int n_exact;            // units scored by the max_ii path
+    int next_long;          // work-queue cursor of k_score_long
+    int n_long;             // units routed to k_score_long
+    int pad0, pad1;
+    unsigned long long n_pairs;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_range: window start, cuts, clipped windows, pair count            (replaces gpu/plrange.cu:38-76)
+//   one thread per anchor of the flat batch; a block first finds the read that holds its first anchor.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRangeThreads)
+k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int n_reads, int n_total, DevParams prm,
+        int *__restrict__ st, unsigned *__restrict__ selmask, unsigned *__restrict__ clipmask, int *__restrict__ block_cnt,
+        Counters *__restrict__ ctr)
+{
+    __shared__ int s_r0;
+    __shared__ int s_cnt[kGroupsPerBlock];
+    const int g0 = blockIdx.x * kRangeThreads;
+    const int g = g0 + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { // largest r with off[r] <= g0  (lands on the non-empty read that owns g0)
+        int lo = 0, hi = n_reads;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (off[mid] <= (long long)g0) lo = mid; else hi = mid;
+        }
+        s_r0 = lo;
+    }
+    __syncthreads();
+    const bool act = g < n_total;
+    bool cut = false, clipped = false, rstart = false;
+    int npair = 0;
+    if (act) {
+        int r = s_r0;
+        while (off[r + 1] <= (long long)g) ++r;
+        const int rs = (int)off[r];
+        const ulonglong2 ai = a[g];
+        const unsigned long long xi = ai.x;
+        const unsigned lo32 = (unsigned)xi, mdx = (unsigned)prm.max_dist_x;
+        // lchain.c:172: j is in the window iff same rid/strand and x_i <= x_j + max_dist_x  <=>  x_j >= lower
+        const unsigned long long lower = (xi & 0xffffffff00000000ULL) | (unsigned long long)(lo32 > mdx ? lo32 - mdx : 0u);
+        const long long lo_ll = (long long)g - (long long)prm.max_iter;   // lchain.c:173
+        const int lo0 = lo_ll > (long long)rs ? (int)lo_ll : rs;
+        int hi = g, bad = lo0 - 1, step = 1;
+        for (;;) { // gallop back from g
+            int probe = hi - step;
+            if (probe <= lo0) {
+                if (hi > lo0) { if (a[lo0].x >= lower) hi = lo0; else bad = lo0; }
+                break;
+            }
+            if (a[probe].x >= lower) { hi = probe; step <<= 1; }
+            else { bad = probe; break; }
+        }
+        while (hi - bad > 1) {
+            int mid = (hi + bad) >> 1;
+            if (a[mid].x >= lower) hi = mid; else bad = mid;
+        }
+        st[g] = hi;
+        npair = g - hi;
+        cut = hi == g;
+        rstart = g == rs;
+        clipped = lo0 > rs && hi == lo0 && a[lo0 - 1].x >= lower;
+        // lchain.c:115-116 compares the segment ids of the two anchors; one id per read is the common case
+        if ((unsigned)((ai.y >> 48) & 0xff) != (unsigned)((a[rs].y >> 48) & 0xff)) atomicOr(&ctr->multi_sid, 1);
+    }
+    const unsigned cutm = __ballot_sync(0xffffffffu, cut);
+    const unsigned rsm = __ballot_sync(0xffffffffu, rstart);
+    const unsigned clm = __ballot_sync(0xffffffffu, clipped);
+    // unit boundaries: the first cut of every 32-anchor group, plus every read start (so no unit spans two reads)
+    const unsigned sel = (cutm & (0u - cutm)) | rsm;
+    unsigned long long psum = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair);
+    if (lane == 0) {
+        const int grp = g >> 5;
+        if (g0 + wid * 32 < n_total) { selmask[grp] = sel; clipmask[grp] = clm; }
+        s_cnt[wid] = __popc(sel);
+        if (psum) atomicAdd(&ctr->n_pairs, psum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < kGroupsPerBlock; ++w) c += s_cnt[w];
+        block_cnt[blockIdx.x] = c;
+    }
+}
+
+// k_scan: exclusive prefix of the per-block unit counts (single block), total -> ctr->n_units
+__global__ void __launch_bounds__(1024)
+k_scan(const int *__restrict__ block_cnt, int n_blocks, int *__restrict__ block_base, Counters *__restrict__ ctr)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_blocks ? block_cnt[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            s_warp[lane] = w; // inclusive
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int incl = x + (wid ? s_warp[wid - 1] : 0) + carry;
+        if (i < n_blocks) block_base[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ctr->n_units = s_carry;
+}
+
+// k_units: ordered scatter of the selected cuts -> unit_start[k], unit_rbase[k] (first anchor of the owning read),
+//          sentinel unit_start[n_units] = n_total.  One thread per 32-anchor group.
+__global__ void __launch_bounds__(256)
+k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base, const long long *__restrict__ off, int n_reads,
+        int n_total, int n_groups, int *__restrict__ unit_start, int *__restrict__ unit_rbase, const Counters *__restrict__ ctr)
+{
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp == 0) unit_start[ctr->n_units] = n_total;
+    if (grp >= n_groups) return;
+    unsigned m = selmask[grp];
+    if (!m) return;
+    const int b = grp / kGroupsPerBlock;
+    int k = block_base[b];
+    for (int g2 = b * kGroupsPerBlock; g2 < grp; ++g2) k += __popc(selmask[g2]);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int g = grp * 32 + bit;
+        int lo = 0, hi = n_reads;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (off[mid] <= (long long)g) lo = mid; else hi = mid;
+        }
+        unit_start[k] = g;
+        unit_rbase[k] = (int)off[lo];
+        ++k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pair score                                                              (reference lchain.c:113-138, mmpriv.h:118-126)
+// ---------------------------------------------------------------------------------------------------------------------
+
+// shared-memory / register record of a scored anchor: x, y = low 32 bits of mm128_t.x / .y, f = chain score,
+// q = q_span | seg_id << 8
+struct __align__(16) Rec { int x, y, f, q; };
+
+__device__ __forceinline__ float mg_log2_dev(float x) // mmpriv.h:118-126, no FMA contraction
+{
+    unsigned z = __float_as_uint(x);
+    float r = (float)((int)((z >> 23) & 255u) - 128);
+    z &= ~(255u << 23);
+    z += 127u << 23;
+    const float zf = __uint_as_float(z);
+    const float poly = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(-0.34484843f, zf), 2.02466578f), zf), 0.67487759f);
+    return __fadd_rn(r, poly);
+}
+
+// every branch of comput_sc; returns kNeg for a rejected pair
+__device__ __forceinline__ int pair_general(int xi, int yi, int sidi, const Rec &r, const DevParams &P)
+{
+    const int dq = yi - r.y;
+    const int sidj = (r.q >> 8) & 0xff, qs = r.q & 0xff;
+    const bool same = sidi == sidj;
+    if (dq <= 0 || dq > P.max_dist_x) return kNeg;                                   // lchain.c:118
+    const int dr = xi - r.x;                                                          // :119
+    if (same && (dr == 0 || dq > P.max_dist_y)) return kNeg;                          // :120
+    const int dd = dr > dq ? dr - dq : dq - dr;                                       // :121
+    if (same && dd > P.bw) return kNeg;                                               // :122
+    if (P.n_seg > 1 && !P.is_cdna && same && dr > P.max_dist_y) return kNeg;          // :123
+    const int dg = dr < dq ? dr : dq;                                                 // :124
+    int sc = qs < dg ? qs : dg;                                                       // :126
+    if (dd || dg > qs) {                                                              // :127
+        const float lin = __fadd_rn(__fmul_rn(P.pen_gap, (float)dd), __fmul_rn(P.pen_skip, (float)dg));
+        const float lg = dd >= 1 ? mg_log2_dev((float)(dd + 1)) : 0.0f;
+        if (P.is_cdna || !same) {                                                     // :131
+            if (!same && dr == 0) ++sc;
+            else if (dr > dq || !same) sc -= __float2int_rz(lin < lg ? lin : lg);
+            else sc -= __float2int_rz(__fadd_rn(lin, __fmul_rn(.5f, lg)));
+        } else sc -= __float2int_rz(__fadd_rn(lin, __fmul_rn(.5f, lg)));              // :135
+    }
+    return sc;
+}
+
+// single-segment, non-cDNA, chn_pen_skip == 0: the penalty is lut[dd] (lut[0] == 0), one byte per entry in shared
+// memory (lut_s = 32-bit shared address).  Returns validity, score in sc.  `pen` is caller-owned scratch that is only
+// rewritten when dd <= bw (a rejected pair never uses it), which saves re-zeroing it for every pair.
+// In FAST kernels Rec.q holds q_span only (no segment id), so no masking is needed here.
+__device__ __forceinline__ bool pair_fast(int xi, int yi, const Rec &r, int maxd_q, unsigned bw, unsigned lut_s, int &pen, int &sc)
+{
+    const int dr = xi - r.x, dq = yi - r.y;
+    const int dg = min(dr, dq);
+    const unsigned dd = (unsigned)abs((int)((unsigned)dr - (unsigned)dq)); // abs(INT_MIN) stays 2^31 as unsigned -> rejected
+    const bool band = dd <= bw;
+    if (band) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pen) : "r"(lut_s + dd));
+    sc = min(dg, r.q) - pen;
+    bool ok = band;
+    ok = ok && dg > 0;
+    ok = ok && dq <= maxd_q;
+    return ok;
+}
+
+template <bool FAST>
+__device__ __forceinline__ bool pair_score(int xi, int yi, int sidi, const Rec &r, const DevParams &P, unsigned lut_s, int &pen, int &sc)
+{
+    if (FAST) return pair_fast(xi, yi, r, P.maxd_q, (unsigned)P.bw, lut_s, pen, sc);
+    sc = pair_general(xi, yi, sidi, r, P);
+    return sc != kNeg;
+}
+
+template <bool FAST>
+__device__ __forceinline__ Rec make_rec(const uint4 &v, int f)
+{
+    Rec r;
+    r.x = (int)v.x; r.y = (int)v.z; r.f = f;
+    r.q = FAST ? (int)(v.w & 0xffu) : (int)((v.w & 0xffu) | (((v.w >> 16) & 0xffu) << 8));
+    return r;
+}
+
+// predecessor record straight from global memory (anchors are read-only; f[] was written by this CTA)
+template <bool FAST>
+__device__ __forceinline__ Rec fetch_global(const uint4 *__restrict__ a, const int *f, int j)
+{
+    return make_rec<FAST>(__ldg(a + j), f[j]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// exact path for units with a max_iter-clipped window: lchain.c:169-207 row by row, including the max_ii fallback
+// (lchain.c:189-205).  One warp, lanes stride over the window.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ void score_unit_exact(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p,
+                                 int u0, int u1, int rbase, const DevParams &P, unsigned lut_s, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    int pen = 0;
+    const unsigned long long *ax = reinterpret_cast<const unsigned long long *>(a);
+    const unsigned long long mdx = (unsigned long long)(long long)P.max_dist_x;
+    int max_ii = -1;
+    for (int i = u0; i < u1; ++i) {
+        const uint4 ai = __ldg(a + i);
+        const int xi = (int)ai.x, yi = (int)ai.z, qsi = (int)(ai.w & 0xffu), sidi = (int)((ai.w >> 16) & 0xffu);
+        const unsigned long long x64 = ax[2 * (size_t)i];
+        const int sti = st[i];
+        int bv = kNeg, bj = -1;
+        for (int j = sti + lane; j < i; j += 32) {
+            const Rec r = fetch_global<FAST>(a, f, j);
+            int s;
+            if (pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s) && s + r.f >= bv) bv = s + r.f, bj = j;
+        }
+        const int m = __reduce_max_sync(full, bv);
+        const int jm = __reduce_max_sync(full, bv == m ? bj : -1);
+        int best = qsi, arg = -1;
+        if (m != kNeg && m > best) best = m, arg = jm;                                 // strict '>' against the init value
+        if (max_ii < 0 || x64 - ax[2 * (size_t)max_ii] > mdx) {                        // lchain.c:189-194
+            int fv = INT32_MIN, fj = -1;
+            for (int j = sti + lane; j < i; j += 32) {
+                const int fjv = f[j];
+                if (fjv >= fv) fv = fjv, fj = j;
+            }
+            const int fm = __reduce_max_sync(full, fv);
+            max_ii = __reduce_max_sync(full, (fv == fm && fj >= 0) ? fj : -1);
+        }
+        if (max_ii >= 0 && max_ii < sti - 1) {                                         // :196 (end_j = st - 1 at max_skip = inf)
+            const Rec r = fetch_global<FAST>(a, f, max_ii);
+            int s;
+            if (pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s) && best < s + r.f) best = s + r.f, arg = max_ii;
+        }
+        if (lane == 0) { f[i] = best; p[i] = arg < 0 ? -1 : arg - rbase; }
+        __syncwarp();
+        if (max_ii < 0 || (x64 - ax[2 * (size_t)max_ii] <= mdx && f[max_ii] < best)) max_ii = i; // :204
+    }
+}
+
+// does [u0,u1) contain an anchor whose window was clipped by max_iter?
+__device__ __forceinline__ bool unit_has_clip(const unsigned *__restrict__ clipmask, int u0, int u1, int lane)
+{
+    const int g0 = u0 >> 5, g1 = (u1 - 1) >> 5;
+    bool any = false;
+    for (int g = g0 + lane; g <= g1; g += 32) {
+        unsigned m = clipmask[g];
+        if (g == g0) m &= 0xffffffffu << (u0 & 31);
+        if (g == g1 && ((u1 & 31) != 0)) m &= 0xffffffffu >> (32 - (u1 & 31));
+        any |= m != 0;
+    }
+    return __any_sync(0xffffffffu, any);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tiled scoring of one unit by one warp
+//   ring: this warp's R-entry shared-memory window of Rec, indexed (i - u0) & (R-1).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int R, bool FAST>
+__device__ void score_unit_tiled(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p,
+                                 int u0, int u1, int rbase, const DevParams &P, unsigned lut_s, Rec *ring, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    int pen = 0;
+    for (int t0 = u0; t0 < u1; t0 += 32) {
+        const int i = t0 + lane;
+        const bool act = i < u1;
+        uint4 ai = make_uint4(0, 0, 0, 0);
+        int sti = INT32_MAX; // inactive lanes: empty window
+        if (act) { ai = __ldg(a + i); sti = st[i]; }
+        const int xi = (int)ai.x, yi = (int)ai.z, qsi = (int)(ai.w & 0xffu), sidi = (int)((ai.w >> 16) & 0xffu);
+        const int wmin = __shfl_sync(full, sti, 0);                       // st is non-decreasing, lane 0 is always active
+        const int wfull = min(t0, __reduce_max_sync(full, act ? sti : 0)); // from here on every active lane's window is open
+        const int jring = max(u0, t0 - R);                                 // oldest predecessor still in the ring
+        int thr = qsi + 1, bj = -1; // a candidate wins iff val >= thr: '>' against q_span(i), '>=' afterwards (ascending j)
+
+        // phase A.0: predecessors that have left the ring (window longer than R): global / L1
+        for (int j = wmin; j < min(jring, t0); ++j) {
+            const Rec r = fetch_global<FAST>(a, f, j);
+            int s;
+            const bool ok = pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s);
+            const int val = s + r.f;
+            if (ok && j >= sti && val >= thr) thr = val, bj = j;
+        }
+        // phase A.1: ring, windows still opening (needs the j >= st_i test)
+        int j = max(wmin, jring);
+        for (; j < wfull; ++j) {
+            const Rec r = ring[(j - u0) & (R - 1)];
+            int s;
+            const bool ok = pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s);
+            const int val = s + r.f;
+            if (ok && j >= sti && val >= thr) thr = val, bj = j;
+        }
+        // phase A.2: ring, all windows open.  The ring is walked in (at most two) address-contiguous runs.
+        while (j < t0) {
+            const int pos = (j - u0) & (R - 1);
+            const int len = min(t0 - j, R - pos);
+            const Rec *rp = ring + pos;
+#pragma unroll 4
+            for (int k = 0; k < len; ++k) {
+                const Rec r = rp[k];
+                int s;
+                const bool ok = pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s);
+                const int val = s + r.f;
+                if (ok && val >= thr) thr = val, bj = j + k;
+            }
+            j += len;
+        }
+        __syncwarp();
+        // publish this tile's static fields (overwrites ring entries older than t0 - R)
+        Rec *tile = ring + ((t0 - u0) & (R - 1)); // 32-aligned: a tile never wraps
+        if (act) tile[lane] = make_rec<FAST>(ai, 0);
+        __syncwarp();
+
+        // phase B: in-tile triangle.  static part first (independent of f), then the serial chain
+        const int nact = min(32, u1 - t0);
+        int w[31];
+#pragma unroll
+        for (int s = 0; s < 31; ++s) {
+            if (s >= nact - 1) break; // warp-uniform
+            int sc;
+            const bool ok = pair_score<FAST>(xi, yi, sidi, tile[s], P, lut_s, pen, sc);
+            w[s] = (ok && s < lane && t0 + s >= sti) ? sc : kNeg;
+        }
+        int fcur = bj >= 0 ? thr : qsi;
+#pragma unroll
+        for (int s = 0; s < 31; ++s) {
+            if (s >= nact - 1) break; // warp-uniform
+            const int fs = __shfl_sync(full, fcur, s);
+            const int val = fs + w[s];                  // kNeg + f stays far below any threshold
+            if (val >= thr) thr = val, fcur = val, bj = t0 + s;
+        }
+        if (act) {
+            f[i] = fcur;
+            p[i] = bj < 0 ? -1 : bj - rbase;
+            tile[lane].f = fcur;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_score_units: persistent grid, one warp per unit taken from a device-side queue
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kScoreWarps = 4;
+
+template <int R, bool FAST>
+__global__ void __launch_bounds__(kScoreWarps * 32)
+k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int *__restrict__ unit_start,
+              const int *__restrict__ unit_rbase, const unsigned *__restrict__ clipmask, int *f, int *__restrict__ p,
+              Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g, int run_mode, int long_min)
+{
+    extern __shared__ int4 smem_raw[];
+    unsigned char *lut = reinterpret_cast<unsigned char *>(smem_raw);
+    const int lut_bytes = (P.lut_n + 15) & ~15;
+    Rec *ring = reinterpret_cast<Rec *>(lut + lut_bytes) + (threadIdx.x >> 5) * R;
+    unsigned lut_s = (unsigned)__cvta_generic_to_shared(lut);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lut_s)); // opaque: keeps the table address in a register (ptxas otherwise
+                                                   // rematerialises the shared-window base before every table load)
+    const int lane = threadIdx.x & 31;
+    // run_mode 0: always; 1: only if no read mixes segment ids (FAST is valid); 2: only if some read does
+    if (run_mode == 1 && ctr->multi_sid != 0) return;
+    if (run_mode == 2 && ctr->multi_sid == 0) return;
+    for (int k = threadIdx.x; k < P.lut_n; k += blockDim.x) lut[k] = lut_g[k];
+    __syncthreads();
+    const int n_units = ctr->n_units;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&ctr->next_unit, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_units) break;
+        const int u0 = unit_start[k], u1 = unit_start[k + 1], rbase = unit_rbase[k];
+        if (u1 - u0 >= long_min) continue; // left to k_score_long
+        if (unit_has_clip(clipmask, u0, u1, lane)) {
+            if (lane == 0) atomicAdd(&ctr->n_exact, 1);
+            score_unit_exact<FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, lane);
+        } else {
+            score_unit_tiled<R, FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
+        }
+    }
+}
+
+} // namespace mm2gb
