@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- chaining anchor-pairs/s of the B200 chaining path (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ont|long|chainonly]
+
+step      = one pass of the hot path (range -> units -> score kernels) over one batch of synthetic reads.
+workload  = BASELINE.json configs[1]: 100 Mb random reference, 10k simulated ONT-like reads 10-100 kb at ~10 % error,
+            map-ont chaining parameters; anchors come from the package's own minimizer seeder (mm2-gb_b200/csrc/
+            synth_seed.cpp).  At N GPUs every rank chains its own 10k reads (same reference, different reads): weak scaling,
+            no data-path collective (reads are independent).
+value     = pairs chained per second with the anchors already resident in HBM (CUDA events on the launching stream,
+            max over ranks); pairs = sum_i (i - st_i) = the reference's n_iter (lchain.c:177), counted by the device and
+            cross-checked against the oracle in the tests.
+e2e       = the same metric through the C ABI call mm2gb_chain_host with pinned HOST buffers: upload, kernels, download of
+            f/p and the threaded host backtracking stage are all inside the timed region -- i.e. the whole mg_lchain_dp.
+roofline  = the score kernel (dominant): algorithmic HBM bytes (24 B/anchor) over its CUDA-event time vs the measured copy
+            peak, plus the issue-slot view that actually bounds it (SASS thread-instructions per pair / SM issue rate).
+cpu_baseline / --impl reference = the reference's own lchain.c (oracle/_ref/libref_lchain.so, compiled from the
+            reference sources in the build container; falls back to the oracle port) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+INSTR_PER_PAIR = 17.0      # SASS thread-instructions per anchor pair in the phase-A inner loop of k_score_units (profiles/)
+HBM_BYTES_PER_ANCHOR = 24  # read 16 B mm128_t, write 4 B f + 4 B p
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "ont": dict(name="synthetic 100 Mb random reference, 10k ONT-like reads 10-100 kb @10% error, map-ont",
+                ref_len=100_000_000, contig_len=25_000_000, n_reads=10_000, lo=10_000, hi=100_000, err=0.10),
+    # configs[2]: super-long reads, lower error + planted repeats so that reads exceed 50k anchors
+    "long": dict(name="synthetic 100 Mb reference with planted repeats, 1000 super-long reads 100-300 kb @3% error, map-ont",
+                 ref_len=100_000_000, contig_len=25_000_000, n_reads=1000, lo=100_000, hi=300_000, err=0.03,
+                 n_repeat_copies=3000, repeat_unit=3000),
+    # small variant for quick checks
+    "mini": dict(name="synthetic 5 Mb random reference, 400 ONT-like reads 10-100 kb @10% error, map-ont",
+                 ref_len=5_000_000, contig_len=0, n_reads=400, lo=10_000, hi=100_000, err=0.10),
+}
+
+
+def make_workload(w, rank):
+    from mm2gb_b200 import synth
+    kw = {k: w[k] for k in ("n_repeat_copies", "repeat_unit") if k in w}
+    return synth.seeded_workload(1, w["ref_len"], w["n_reads"], w["lo"], w["hi"], read_seed=1000 + rank, err=w["err"],
+                                 contig_len=w["contig_len"], **kw)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(a, off, budget_s=20.0):
+    """The reference's own lchain.c (whole mg_lchain_dp: DP + backtracking) on all host threads, on a bounded sample of the
+    reads of this workload.  Pairs are counted once with the oracle port."""
+    po = entry.load_oracle()
+    prm = po.map_ont_params()
+    cores = cpu_threads()
+    kind = "reference" if po.ref_available() else "port"
+    n_reads = len(off) - 1
+    # calibrate on a few reads, then size the sample for ~budget_s of CPU work (all of it if it fits)
+    probe = min(n_reads, 4 * cores)
+    t0 = time.perf_counter()
+    po.lchain_batch(prm, a, off, 0, probe, n_threads=cores, use_ref=(kind == "reference"))
+    dt = max(time.perf_counter() - t0, 1e-4)
+    per_read_cpu = dt * cores / probe
+    n_sample = int(min(n_reads, max(probe, budget_s / per_read_cpu)))
+    t0 = time.perf_counter()
+    po.lchain_batch(prm, a, off, 0, n_sample, n_threads=cores, use_ref=(kind == "reference"))
+    dt = time.perf_counter() - t0
+    pairs, _, _ = po.lchain_batch(prm, a, off, 0, n_sample, n_threads=cores)
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": f"first {n_sample} of {n_reads} reads ({int(off[n_sample])} anchors, {pairs} pairs), whole mg_lchain_dp, {dt:.2f} s wall",
+            "reads_per_s": n_sample / dt}, pairs, dt, n_sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MM2GB_BENCH_WORKLOAD", "ont"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+    pkg = entry.load_package()
+    cfg = {"workload": w["name"], "reads_per_gpu": w["n_reads"], "chaining": "map-ont: bw=500 max_dist=5000 max_iter=5000 max_skip=inf k=15",
+           "sharding": f"reads sharded by rank, {world} rank(s), no collective", "l2": "inputs_larger_than_l2"}
+
+    # ---- reference arm: the reference's CPU lchain.c on the host cores (rank 0 only) -------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        a, off = make_workload(w, 0)
+        vals = []
+        info = None
+        for i in range(args.warmup + args.steps):
+            info, pairs, dt, n_sample = cpu_baseline(a, off, budget_s=8.0)
+            if i >= args.warmup:
+                vals.append((pairs, dt, n_sample))
+        pairs = sum(v[0] for v in vals); dt = sum(v[1] for v in vals); nr = sum(v[2] for v in vals)
+        val = pairs / dt
+        info["value"] = val
+        print(json.dumps({"impl": "reference", "metric": "chaining anchor-pairs/s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                          "config": cfg, "reads_per_s": nr / dt, "cpu_baseline": info,
+                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---- our arm ----------------------------------------------------------------------------------------------------
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the chaining path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    a, off = make_workload(w, rank)
+    n, n_reads = int(off[-1]), len(off) - 1
+    misc = pkg.map_ont_misc()
+    ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=max(n, 1 << 20), max_reads=n_reads + 1, n_slots=3)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(0), device=local_rank)
+
+    # device-resident inputs
+    h_a = torch.from_numpy(a.view(np.int64)).pin_memory()
+    h_off = torch.from_numpy(off).pin_memory()
+    d_a = h_a.cuda(non_blocking=True)
+    d_off = h_off.cuda(non_blocking=True)
+    d_f = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_p = torch.empty(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.chain_dp_device(d_a, d_off, n_reads, n, d_f, d_p)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    ctx.sync()
+    st = ctx.device_stats()
+    pairs = int(st.n_pairs)
+    sampler = ClockSampler(local_rank)
+    ctx.profile(True)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+
+    # ---- end to end through the C ABI with pinned host buffers (whole mg_lchain_dp: upload, DP, download, backtracking)
+    out = {"f": torch.empty(n, dtype=torch.int32).pin_memory(), "p": torch.empty(n, dtype=torch.int32).pin_memory(),
+           "u": np.empty(n, np.uint64), "b": np.empty((n, 2), np.uint64), "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
+    host_threads = max(1, cpu_threads() // max(1, world))
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        ctx.chain(h_a, off, n_threads=host_threads, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = ctx.chain(h_a, off, n_threads=host_threads, out=out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    n_chains = int(res["n_u"].sum())
+
+    # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
+    tot = torch.tensor([float(pairs), float(n), float(n_reads)], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tot_pairs, tot_anchors, tot_reads = (float(x) for x in tot.tolist())
+    ms_max, e2e_max = (float(x) for x in tmax.tolist())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    sec = ms_max / 1e3
+    value = tot_pairs * args.steps / sec
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    score_ms, score_n = prof["score"]
+    score_avg_s = score_ms / 1e3 / max(1, score_n)
+    hbm_gbs = HBM_BYTES_PER_ANCHOR * n / score_avg_s / 1e9
+    sm_mhz = clocks["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    issue_peak = n_sm * 4 * 32 * sm_mhz * 1e6          # thread-instructions/s: 4 schedulers x 32 lanes per SM
+    issue_ach = INSTR_PER_PAIR * pairs / score_avg_s
+    roofline = {"bound": "hbm", "kernel": "k_score_units", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
+                "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms,
+                "note": "this kernel is issue-bound, not HBM-bound (~%d pairs x %.0f instr per 24 B): see issue" % (round(pairs / max(1, n)), INSTR_PER_PAIR),
+                "issue": {"bound": "int-issue", "achieved": issue_ach, "peak": issue_peak, "unit": "thread-instr/s", "frac": issue_ach / issue_peak,
+                          "instr_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": pairs / score_avg_s, "sm_mhz": sm_mhz, "n_sm": n_sm}}
+    line = {"metric": "chaining anchor-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": cfg, "reads_per_s": tot_reads * args.steps / sec, "anchors_per_s": tot_anchors * args.steps / sec,
+            "batch": {"reads": n_reads, "anchors": n, "pairs": pairs, "pairs_per_anchor": pairs / max(1, n), "units": int(st.n_units),
+                      "units_exact": int(st.n_units_exact), "chains": n_chains},
+            "kernel_ms_per_step": {k: v[0] / max(1, v[1]) for k, v in prof.items() if v[1]},
+            "roofline": roofline,
+            "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1), "d2h_bytes_per_step": 8 * n,
+                    "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps, "host_threads": host_threads,
+                    "includes": "H2D anchors, range+unit+score kernels, D2H f/p, threaded host backtracking+compaction (= whole mg_lchain_dp)"},
+            "gpu_launches": 5 * args.steps, "clocks": clocks}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(a, off)[0]
+    print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,12 @@ int mm2gb_ctx_set_misc(mm2gb_ctx_t *ctx, const mm2gb_misc_t *misc);
 int mm2gb_chain_dp_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                         mm2gb_stats_t *stats);
 
+/* The whole mg_lchain_dp (lchain.c:148-217) for a batch: device DP + host stage (backtracking, compaction) on `n_threads`
+ * host threads, pipelined chunk by chunk.  Per read r: chains u[off[r] .. off[r]+n_u[r]) (score<<32 | count, ordered by
+ * chain start) and compacted anchors b[off[r] .. off[r]+n_b[r]).  f/p (size off[n_reads]) receive the DP arrays. */
+int mm2gb_chain_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                     uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats);
+
 /* Asynchronous pair.  submit: stage anchors into the slot's pinned buffer, enqueue H2D + kernels + D2H on the slot's
  * stream and return.  wait: block until the slot is done and expose the pinned result arrays (valid until the slot is
  * submitted again).  gather variant takes one pointer per read (chain_read_t.a of each read, plutils.h:64). */

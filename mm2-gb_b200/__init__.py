@@ -83,6 +83,7 @@ def lib():
         L.mm2gb_ctx_destroy.restype = None
         L.mm2gb_ctx_set_misc.argtypes = [vp, C.POINTER(Misc)]
         L.mm2gb_chain_dp_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.POINTER(Stats)]
+        L.mm2gb_chain_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(Stats)]
         L.mm2gb_submit.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_submit_gather.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_wait.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
@@ -161,6 +162,24 @@ class ChainContext:
         st = Stats()
         _ck(lib().mm2gb_chain_dp_host(self._h, _ptr(a), _ptr(off), n_reads, _ptr(f), _ptr(p), C.byref(st)))
         return f, p, st
+
+    def chain(self, a, off, n_threads: int = 0, out=None):
+        """Whole mg_lchain_dp for a batch (device DP + threaded host backtracking).  Returns dict with f, p, u, n_u, b,
+        n_b, stats; read r's chains are u[off[r]:off[r]+n_u[r]], its compacted anchors b[off[r]:off[r]+n_b[r]].
+        `out` may carry preallocated (e.g. pinned) buffers under the same keys."""
+        n_reads = len(off) - 1
+        n = int(off[-1])
+        out = dict(out or {})
+        out.setdefault("f", np.empty(n, np.int32)); out.setdefault("p", np.empty(n, np.int32))
+        out.setdefault("u", np.empty(n, np.uint64)); out.setdefault("b", np.empty((n, 2), np.uint64))
+        out.setdefault("n_u", np.zeros(n_reads, np.int32)); out.setdefault("n_b", np.zeros(n_reads, np.int64))
+        st = Stats()
+        if n_threads <= 0:
+            n_threads = min(32, os.cpu_count() or 1)
+        _ck(lib().mm2gb_chain_host(self._h, _ptr(a), _ptr(off), n_reads, _ptr(out["f"]), _ptr(out["p"]), _ptr(out["u"]),
+                                   _ptr(out["n_u"]), _ptr(out["b"]), _ptr(out["n_b"]), n_threads, C.byref(st)))
+        out["stats"] = st
+        return out
 
     def submit(self, slot: int, a, off):
         _ck(lib().mm2gb_submit(self._h, slot, _ptr(a), _ptr(off), len(off) - 1))

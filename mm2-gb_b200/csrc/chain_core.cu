@@ -16,6 +16,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace mm2gb;
@@ -471,16 +475,15 @@ extern "C" int mm2gb_slot_busy(mm2gb_ctx_t *c, int slot)
     return c->slot[slot].busy ? 1 : 0;
 }
 
-extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
-                                   mm2gb_stats_t *stats)
+// Shared driver of the host-buffer entry points: split the reads into chunks, run them round-robin through the slots
+// (upload / kernels / download of consecutive chunks overlap) and call on_done(r0, r1) as each chunk's f/p land.
+template <class Done>
+static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                       mm2gb_stats_t *stats, Done on_done)
 {
-    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || ((!f || !p) && off[n_reads] > 0)) return fail(MM2GB_EARG, "bad argument");
-    if (stats) memset(stats, 0, sizeof(*stats));
-    if (n_reads == 0) return MM2GB_OK;
     for (int i = 0; i < c->n_slots; ++i)
         if (c->slot[i].busy) return fail(MM2GB_ESTATE, "slot %d is busy", i);
     const bool in_pinned = a && is_pinned(a), out_pinned = is_pinned(f) && is_pinned(p);
-    // split the reads into chunks so that upload / kernels / download of consecutive chunks overlap across slots
     const long long total = off[n_reads] - off[0];
     long long target = std::max<long long>(1 << 20, total / (4LL * c->n_slots) + 1);
     target = std::min<long long>(target, (long long)c->max_anchors);
@@ -488,6 +491,7 @@ extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, cons
     mm2gb_stats_t acc;
     memset(&acc, 0, sizeof(acc));
     std::vector<long long> rel;
+    int slot_r0[4] = {0, 0, 0, 0}, slot_r1[4] = {0, 0, 0, 0};
     int r0 = 0, chunk = 0, rc = MM2GB_OK;
     auto reap = [&](int si) -> int {
         int rc2 = wait_impl(c, si);
@@ -496,6 +500,7 @@ extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, cons
         fill_stats(c, *c->slot[si].h_ctr, c->slot[si].n_total, &st);
         acc.n_anchors += st.n_anchors; acc.n_pairs += st.n_pairs; acc.n_units += st.n_units;
         acc.n_units_exact += st.n_units_exact; acc.n_long += st.n_long; acc.general_path |= st.general_path;
+        on_done(slot_r0[si], slot_r1[si]);
         return MM2GB_OK;
     };
     while (r0 < n_reads) {
@@ -513,12 +518,75 @@ extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, cons
         for (int r = r0; r <= r1; ++r) rel[(size_t)(r - r0)] = off[r] - off[r0];
         rc = submit_impl(c, si, a + off[r0], in_pinned, rel.data(), r1 - r0, cnt, f + off[r0], p + off[r0], out_pinned);
         if (rc) return rc;
+        slot_r0[si] = r0; slot_r1[si] = r1;
         r0 = r1; ++chunk;
     }
-    for (int i = 0; i < c->n_slots; ++i)
-        if (c->slot[i].busy && (rc = reap(i))) return rc;
+    // drain in submission order
+    for (int k = 0; k < c->n_slots; ++k) {
+        const int si = (chunk + k) % c->n_slots;
+        if (c->slot[si].busy && (rc = reap(si))) return rc;
+    }
     if (stats) *stats = acc;
     return MM2GB_OK;
+}
+
+extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                                   mm2gb_stats_t *stats)
+{
+    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || ((!f || !p) && off[n_reads] > 0)) return fail(MM2GB_EARG, "bad argument");
+    if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_reads == 0) return MM2GB_OK;
+    return run_chunked(c, a, off, n_reads, f, p, stats, [](int, int) {});
+}
+
+// Whole mg_lchain_dp (lchain.c:148-217) for a batch: device DP, then the host stage (backtracking + compaction) on
+// `n_threads` worker threads that start on a chunk's reads as soon as its f/p have landed, while later chunks are
+// still on the GPU.  Outputs per read r: u[off[r] .. off[r]+n_u[r]), b[off[r] .. off[r]+n_b[r]).
+extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                                uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats)
+{
+    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || !n_u || !n_b) return fail(MM2GB_EARG, "bad argument");
+    if (off[n_reads] > 0 && (!f || !p || !u || !b)) return fail(MM2GB_EARG, "bad argument");
+    if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_reads == 0) return MM2GB_OK;
+    if (n_threads < 1) n_threads = 1;
+    const mm2gb_misc_t m = c->misc;
+    const int32_t max_drop = m.is_cdna ? INT32_MAX : m.bw; // lchain.c:151,162
+    std::mutex mu;
+    std::condition_variable cv;
+    int ready = 0;          // reads [0, ready) have f/p on the host
+    bool abort_all = false;
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const int r = next.fetch_add(1);
+                if (r >= n_reads) return;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return ready > r || abort_all; });
+                    if (abort_all) return;
+                }
+                const int64_t s = off[r], n = off[r + 1] - s;
+                int64_t nb = 0;
+                n_u[r] = mm2gb_backtrack(n, f + s, p + s, a + s, m.min_cnt, m.min_score, max_drop, u + s, b + s, &nb);
+                n_b[r] = nb;
+            }
+        });
+    int rc = run_chunked(c, a, off, n_reads, f, p, stats, [&](int, int r1) {
+        { std::lock_guard<std::mutex> lk(mu); ready = r1; }
+        cv.notify_all();
+    });
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc) abort_all = true; else ready = n_reads;
+    }
+    cv.notify_all();
+    for (auto &t : pool) t.join();
+    return rc;
 }
 
 extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p)
