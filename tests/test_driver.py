@@ -1,0 +1,77 @@
+"""End-to-end through the reference's UNMODIFIED host driver (main.c / map.c, --gpu-chain, PAF output) linked against the
+drop-in: oracle/_ref/minimap2_b200 (built by `make -C oracle ref` in the build container; the binary travels to the GPU
+box) against the CPU ground truth oracle/_ref/minimap2_ref --max-chain-skip=2147483647 (SURVEY.md trap T1) and the
+committed golden PAFs.  Bar: empty diff."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+B200 = os.path.join(REF, "minimap2_b200")
+CPU = os.path.join(REF, "minimap2_ref")
+FIX = os.path.join(REF, "fixtures")
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (os.path.exists(B200) and os.path.exists(CPU)),
+                                                  reason="oracle/_ref binaries not built (needs /root/reference at build time)")]
+
+
+def run(binary, args, cwd):
+    out = subprocess.run([binary] + args, capture_output=True, cwd=cwd, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    return out.stdout.decode()
+
+
+def write_cfg(path, max_total_n=2_000_000, max_read=2000):
+    with open(path, "w") as fh:
+        fh.write('{"max_total_n": %d, "max_read": %d, "host_threads": 4}' % (max_total_n, max_read))
+
+
+@pytest.mark.parametrize("tag,t,q", [("MT", "MT-human.fa", "MT-orang.fa"), ("inv", "t-inv.fa", "q-inv.fa"), ("t2", "t2.fa", "q2.fa")])
+def test_reference_fixtures_paf(tmp_path, golden_dir, tag, t, q):
+    """the reference's own accuracy recipe (README.md:85-96) on its own test FASTA"""
+    write_cfg(tmp_path / "gpu_config.json")
+    gpu = run(B200, ["-t", "1", "--gpu-chain", "--gpu-cfg", str(tmp_path / "gpu_config.json"), os.path.join(FIX, t), os.path.join(FIX, q)], tmp_path)
+    cpu = run(CPU, ["-t", "1", "--max-chain-skip=2147483647", os.path.join(FIX, t), os.path.join(FIX, q)], tmp_path)
+    assert gpu == cpu
+    assert gpu == open(os.path.join(golden_dir, tag + ".paf")).read()
+
+
+def _synth_fasta(synth, tmp_path, ref_len, n_reads, lo, hi, repeats=0, seed=1):
+    ref = synth.simulate_reference(ref_len, seed=seed, n_repeat_copies=repeats, repeat_unit=2000)
+    rds = synth.simulate_reads(ref, n_reads, lo, hi, seed=seed + 1)
+    synth.write_fasta(str(tmp_path / "ref.fa"), [ref], prefix="ref")
+    synth.write_fasta(str(tmp_path / "reads.fa"), rds, prefix="read")
+    return str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+
+
+def test_golden_synthetic_reads_paf(synth, tmp_path, golden_dir):
+    """the 8 simulated reads of tests/golden/synth.paf (regenerated from their seeds)"""
+    ref, reads = _synth_fasta(synth, tmp_path, 600_000, 8, 4000, 16000, repeats=40)
+    write_cfg(tmp_path / "cfg.json")
+    gpu = run(B200, ["-t", "1", "-x", "map-ont", "--gpu-chain", "--gpu-cfg", str(tmp_path / "cfg.json"), ref, reads], tmp_path)
+    assert gpu == open(os.path.join(golden_dir, "synth.paf")).read()
+
+
+@pytest.mark.parametrize("threads,max_total_n", [(1, 2_000_000), (4, 150_000), (3, 40_000)])
+def test_ont_like_reads_paf_multithread_small_batches(synth, tmp_path, threads, max_total_n):
+    """120 ONT-like reads on a 3 Mb reference with repeats; several driver threads and batch limits small enough that
+    batches rotate many times (and some single reads exceed the limit)"""
+    ref, reads = _synth_fasta(synth, tmp_path, 3_000_000, 120, 5000, 40000, repeats=150, seed=11)
+    write_cfg(tmp_path / "cfg.json", max_total_n=max_total_n, max_read=64)
+    gpu = run(B200, ["-t", str(threads), "-x", "map-ont", "--gpu-chain", "--gpu-cfg", str(tmp_path / "cfg.json"), ref, reads], tmp_path)
+    cpu = run(CPU, ["-t", "4", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)
+    assert len(cpu.splitlines()) >= 120
+    assert gpu == cpu
+
+
+def test_max_chain_skip_spelling_is_ignored_by_gpu_path(synth, tmp_path):
+    """trap T1: `--max-chain-skip=infinity` parses to 0 on the CPU path; the GPU path is true infinity whatever the flag"""
+    ref, reads = _synth_fasta(synth, tmp_path, 1_000_000, 30, 5000, 30000, repeats=60, seed=21)
+    write_cfg(tmp_path / "cfg.json")
+    base = ["-t", "2", "-x", "map-ont", "--gpu-chain", "--gpu-cfg", str(tmp_path / "cfg.json")]
+    a = run(B200, base + ["--max-chain-skip=infinity", ref, reads], tmp_path)
+    b = run(B200, base + [ref, reads], tmp_path)
+    cpu = run(CPU, ["-t", "2", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)
+    assert a == b == cpu
