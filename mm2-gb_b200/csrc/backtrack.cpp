@@ -64,10 +64,20 @@ void flag_pass(Key *beg, Key *end, int shift)
     }
 }
 
-void sort_by_key(Key *beg, Key *end) // ksort.h:146-150
+// ksort.h:146-150.  The reference always starts at the top byte (shift 56).  A pass in which every key has the same
+// digit is the identity (one bucket, nothing is displaced, and the recursion then continues on the whole range with the
+// next digit), so starting at the highest digit in which the keys actually differ yields the same permutation while
+// skipping the 5-6 no-op passes that 64-bit keys holding 17-bit scores would otherwise pay for.
+void sort_by_key(Key *beg, Key *end)
 {
-    if (end - beg <= 64) insertion_by_key(beg, end);
-    else flag_pass(beg, end, 56);
+    if (end - beg <= 64) { insertion_by_key(beg, end); return; }
+    uint64_t all_or = 0, all_and = ~0ULL;
+    for (Key *it = beg; it != end; ++it) all_or |= it->key, all_and &= it->key;
+    const uint64_t diff = all_or ^ all_and;
+    if (!diff) return; // all keys equal: every pass is the identity
+    int shift = 56;
+    while (((diff >> shift) & 255) == 0) shift -= 8;
+    flag_pass(beg, end, shift);
 }
 
 // lchain.c:9-25: from chain end z, walk predecessors until a used anchor, the root, or a drop > max_drop;
@@ -95,17 +105,21 @@ extern "C" int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p
 {
     if (n_b) *n_b = 0;
     if (n <= 0) return 0;
+    // per-thread scratch, reused across reads (a fresh 24 B/anchor allocation per read costs more than the walk itself)
+    static thread_local std::vector<Key> z, w;
+    static thread_local std::vector<int32_t> t, v;
+    static thread_local std::vector<uint64_t> uu;
+    static thread_local std::vector<int64_t> start;
     // chain ends: every anchor scoring >= min_sc, visited from the highest score down (lchain.c:33-41)
-    std::vector<Key> z;
-    z.reserve((size_t)n);
+    z.clear();
     for (int64_t i = 0; i < n; ++i)
         if (f[i] >= min_sc) z.push_back({(uint64_t)(int64_t)f[i], (uint64_t)i});
     if (z.empty()) return 0;
     sort_by_key(z.data(), z.data() + z.size());
 
-    std::vector<int32_t> t((size_t)n, 0), v;
-    std::vector<uint64_t> uu;
-    v.reserve((size_t)n);
+    t.assign((size_t)n, 0);
+    v.clear();
+    uu.clear();
     for (int64_t k = (int64_t)z.size() - 1; k >= 0; --k) { // lchain.c:58-72
         if (t[z[k].val] != 0) continue;
         const size_t v0 = v.size();
@@ -122,8 +136,8 @@ extern "C" int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p
 
     // lchain.c:78-111: each chain was collected end-first; flip it, then order chains by the x of their first anchor
     // with the same unstable sort (ties between chains starting at the same x follow it too).
-    std::vector<Key> w((size_t)n_u);
-    std::vector<int64_t> start((size_t)n_u);
+    w.resize((size_t)n_u);
+    start.resize((size_t)n_u);
     int64_t k = 0;
     for (int32_t c = 0; c < n_u; ++c) {
         const int32_t cnt = (int32_t)uu[(size_t)c];

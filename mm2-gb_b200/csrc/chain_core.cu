@@ -62,7 +62,8 @@ struct Slot {
     long long *d_off = nullptr;
     int *d_st = nullptr, *d_f = nullptr, *d_p = nullptr;
     unsigned *d_selmask = nullptr, *d_clipmask = nullptr;
-    int *d_block_cnt = nullptr, *d_block_base = nullptr, *d_unit_start = nullptr, *d_unit_rbase = nullptr;
+    int *d_block_cnt = nullptr, *d_block_base = nullptr, *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
+    int big_cap = 0;
     Counters *d_ctr = nullptr;
     // pinned host
     mm2gb_anchor_t *h_a = nullptr;
@@ -136,7 +137,7 @@ static int setup_params(mm2gb_ctx *c, const mm2gb_misc_t *m)
     P.pen_skip = m->chn_pen_skip;
     c->fast = !m->is_cdna && m->n_seg <= 1 && m->chn_pen_skip == 0.0f && m->bw <= kLutMax;
     if (c->fast) {
-        std::vector<unsigned char> lut((size_t)m->bw + 1);
+        std::vector<unsigned char> lut((size_t)2 * m->bw + 1); // symmetric: entry k = pen(|k - bw|)
         for (int dd = 0; dd <= m->bw && c->fast; ++dd) { // lchain.c:128-135 with dg * 0.0f == 0
             volatile float lin = m->chn_pen_gap * (float)dd;
             float lg = dd >= 1 ? host_log2((float)(dd + 1)) : 0.0f;
@@ -144,11 +145,11 @@ static int setup_params(mm2gb_ctx *c, const mm2gb_misc_t *m)
             volatile float sum = lin + half;
             const int pen = (int)sum;
             if (pen < 0 || pen > 255) c->fast = false; // does not fit a byte table: use the arithmetic path
-            lut[(size_t)dd] = (unsigned char)pen;
+            lut[(size_t)(m->bw + dd)] = lut[(size_t)(m->bw - dd)] = (unsigned char)pen;
         }
         if (c->fast) CK(cudaMemcpy(c->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
     }
-    P.lut_n = c->fast ? m->bw + 1 : 0;
+    P.lut_n = c->fast ? 2 * m->bw + 1 : 0;
     return MM2GB_OK;
 }
 
@@ -178,21 +179,21 @@ static int config_ring(mm2gb_ctx *c)
 
 template <int R, bool FAST>
 static void launch_score(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int *st, const int *us, const int *ur,
-                         const unsigned *clip, int *f, int *p, Counters *ctr, int run_mode)
+                         const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode)
 {
     const size_t smem = (size_t)((c->prm.lut_n + 15) & ~15) + (size_t)kScoreWarps * R * sizeof(Rec);
-    k_score_units<R, FAST><<<c->score_blocks, kScoreWarps * 32, smem, s>>>(a, st, us, ur, clip, f, p, ctr, c->prm, c->d_lut,
-                                                                          run_mode, c->long_min);
+    k_score_units<R, FAST><<<c->score_blocks, kScoreWarps * 32, smem, s>>>(a, st, us, ur, clip, f, p, big, big_cap, ctr, c->prm,
+                                                                          c->d_lut, run_mode, c->long_min);
 }
 
 template <bool FAST>
 static void launch_score_ring(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int *st, const int *us, const int *ur,
-                              const unsigned *clip, int *f, int *p, Counters *ctr, int run_mode)
+                              const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode)
 {
     switch (c->ring) {
-    case 256: launch_score<256, FAST>(c, s, a, st, us, ur, clip, f, p, ctr, run_mode); break;
-    case 1024: launch_score<1024, FAST>(c, s, a, st, us, ur, clip, f, p, ctr, run_mode); break;
-    default: launch_score<512, FAST>(c, s, a, st, us, ur, clip, f, p, ctr, run_mode); break;
+    case 256: launch_score<256, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
+    case 1024: launch_score<1024, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
+    default: launch_score<512, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
     }
 }
 
@@ -245,14 +246,15 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
         k_scan<<<1, 1024, 0, s>>>(sl.d_block_cnt, n_blocks, sl.d_block_base, sl.d_ctr);
         k_units<<<(n_groups + 255) / 256, 256, 0, s>>>(sl.d_selmask, sl.d_block_base, d_off, n_reads, n, n_groups, sl.d_unit_start,
                                                       sl.d_unit_rbase, sl.d_ctr);
+        k_order<<<(n_groups + n_reads + 256) / 256, 256, 0, s>>>(sl.d_unit_start, sl.d_big_order, sl.big_cap, sl.d_ctr);
     }
     {
         ProfScope ps(c, T_SCORE, s, prof);
         if (c->fast) {
-            launch_score_ring<true>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_ctr, 1);
-            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_ctr, 2);
+            launch_score_ring<true>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 1);
+            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 2);
         } else {
-            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_ctr, 0);
+            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 0);
         }
     }
     CK(cudaGetLastError());
@@ -275,7 +277,7 @@ static void free_slot(Slot &s)
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
     cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base);
-    cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_ctr);
+    cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
     cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -317,7 +319,7 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
         }                                                                                                          \
     } while (0)
     {
-        CKC(cudaMalloc(&c->d_lut, (size_t)kLutMax + 16));
+        CKC(cudaMalloc(&c->d_lut, (size_t)2 * kLutMax + 16));
         rc = setup_params(c, misc);
         if (rc) goto bad;
         rc = c->ring == 256 ? config_ring<256>(c) : c->ring == 1024 ? config_ring<1024>(c) : config_ring<512>(c);
@@ -339,6 +341,8 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaMalloc(&s.d_block_base, n_blocks * sizeof(int)));
             CKC(cudaMalloc(&s.d_unit_start, n_units_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_unit_rbase, n_units_cap * sizeof(int)));
+            s.big_cap = (int)(n / kBigMin) + 2;
+            CKC(cudaMalloc(&s.d_big_order, (size_t)4 * s.big_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_ctr, sizeof(Counters)));
             CKC(cudaMallocHost(&s.h_a, n * sizeof(mm2gb_anchor_t)));
             CKC(cudaMallocHost(&s.h_off, ((size_t)max_reads + 1) * sizeof(long long)));

@@ -31,7 +31,7 @@ constexpr int kLutMax = 4096;               // largest bw served by the integer 
 struct DevParams {
     int max_iter, max_dist_x, max_dist_y, bw, is_cdna, n_seg;
     int maxd_q;       // min(max_dist_x, max_dist_y): the dq bound when both anchors share a segment id
-    int lut_n;        // bw + 1 when the byte penalty table is valid (chn_pen_skip == 0, bw <= kLutMax, max entry <= 255), else 0
+    int lut_n;        // 2*bw + 1 when the byte penalty table is valid (chn_pen_skip == 0, bw <= kLutMax, max entry <= 255), else 0
     float pen_gap, pen_skip;
 };
 
@@ -39,13 +39,18 @@ struct DevParams {
 struct Counters {
     int next_unit;          // work-queue cursor of k_score_units
     int n_units;            // written by k_scan
-    int multi_sid;          // 1 if some read mixes segment ids (forces the general score path)
+    int multi_sid;          // 1 if some read mixes segment ids or has a zero q_span (forces the general score path)
     int n_exact;            // units scored by the max_ii path
     int next_long;          // work-queue cursor of k_score_long
     int n_long;             // units routed to k_score_long
-    int pad0, pad1;
+    int big_cnt[4];         // units of >= 4096 / 2048 / 1024 / 512 anchors, queued first (longest-first scheduling)
+    int qs_max;             // largest q_span in the batch (bounds the chain scores: f <= unit length * qs_max)
+    int pad1;
     unsigned long long n_pairs;
 };
+
+constexpr int kBigMin = 512;                // smallest unit that goes through the longest-first lists
+__device__ __forceinline__ int big_class(int len) { return len >= 4096 ? 0 : len >= 2048 ? 1 : len >= 1024 ? 2 : 3; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_range: window start, cuts, clipped windows, pair count            (replaces gpu/plrange.cu:38-76)
@@ -72,7 +77,7 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int
     __syncthreads();
     const bool act = g < n_total;
     bool cut = false, clipped = false, rstart = false;
-    int npair = 0;
+    int npair = 0, qspan = 0;
     if (act) {
         int r = s_r0;
         while (off[r + 1] <= (long long)g) ++r;
@@ -104,7 +109,9 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int
         rstart = g == rs;
         clipped = lo0 > rs && hi == lo0 && a[lo0 - 1].x >= lower;
         // lchain.c:115-116 compares the segment ids of the two anchors; one id per read is the common case
-        if ((unsigned)((ai.y >> 48) & 0xff) != (unsigned)((a[rs].y >> 48) & 0xff)) atomicOr(&ctr->multi_sid, 1);
+        qspan = (int)((ai.y >> 32) & 0xff);
+        // (the table path also assumes q_span > 0, which every real seed satisfies)
+        if ((unsigned)((ai.y >> 48) & 0xff) != (unsigned)((a[rs].y >> 48) & 0xff) || ((ai.y >> 32) & 0xff) == 0) atomicOr(&ctr->multi_sid, 1);
     }
     const unsigned cutm = __ballot_sync(0xffffffffu, cut);
     const unsigned rsm = __ballot_sync(0xffffffffu, rstart);
@@ -112,7 +119,9 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int
     // unit boundaries: the first cut of every 32-anchor group, plus every read start (so no unit spans two reads)
     const unsigned sel = (cutm & (0u - cutm)) | rsm;
     unsigned long long psum = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair);
+    const int qmax = __reduce_max_sync(0xffffffffu, qspan);
     if (lane == 0) {
+        if (qmax > ctr->qs_max) atomicMax(&ctr->qs_max, qmax);
         const int grp = g >> 5;
         if (g0 + wid * 32 < n_total) { selmask[grp] = sel; clipmask[grp] = clm; }
         s_cnt[wid] = __popc(sel);
@@ -196,6 +205,20 @@ k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base
     }
 }
 
+// k_order: units of >= kBigMin anchors are listed per size class so that the score kernel starts the longest units first
+// (a 5000-anchor unit is ~1 ms of one warp's time: started last it would be the tail of the launch).
+__global__ void __launch_bounds__(256)
+k_order(const int *__restrict__ unit_start, int *__restrict__ big_order, int big_cap, Counters *__restrict__ ctr)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ctr->n_units) return;
+    const int len = unit_start[k + 1] - unit_start[k];
+    if (len < kBigMin) return;
+    const int c = big_class(len);
+    const int pos = atomicAdd(&ctr->big_cnt[c], 1);
+    if (pos < big_cap) big_order[c * big_cap + pos] = k;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // pair score                                                              (reference lchain.c:113-138, mmpriv.h:118-126)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -241,20 +264,22 @@ __device__ __forceinline__ int pair_general(int xi, int yi, int sidi, const Rec 
     return sc;
 }
 
-// single-segment, non-cDNA, chn_pen_skip == 0: the penalty is lut[dd] (lut[0] == 0), one byte per entry in shared
-// memory (lut_s = 32-bit shared address).  Returns validity, score in sc.  `pen` is caller-owned scratch that is only
-// rewritten when dd <= bw (a rejected pair never uses it), which saves re-zeroing it for every pair.
-// In FAST kernels Rec.q holds q_span only (no segment id), so no masking is needed here.
+// single-segment, non-cDNA, chn_pen_skip == 0, every q_span > 0: the penalty is a byte table in shared memory, stored
+// symmetrically around bw (entry k holds pen(|k - bw|), k = dr - dq + bw in [0, 2bw]) so neither |.| nor an index clamp is
+// needed: one unsigned compare gives the band test (lchain.c:121-122) and the load predicate.  lut_s = 32-bit shared address
+// of entry 0.  Returns validity, score in sc.  `pen` is caller-owned scratch, rewritten only inside the band (a rejected
+// pair never uses it).  dr >= 0 always (x-sorted, same rid/strand inside a window), so min(dr,dq,q_span) > 0 <=> dq > 0 &&
+// dr != 0 (lchain.c:118,120).  In FAST kernels Rec.q holds q_span only.
 __device__ __forceinline__ bool pair_fast(int xi, int yi, const Rec &r, int maxd_q, unsigned bw, unsigned lut_s, int &pen, int &sc)
 {
     const int dr = xi - r.x, dq = yi - r.y;
-    const int dg = min(dr, dq);
-    const unsigned dd = (unsigned)abs((int)((unsigned)dr - (unsigned)dq)); // abs(INT_MIN) stays 2^31 as unsigned -> rejected
-    const bool band = dd <= bw;
-    if (band) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pen) : "r"(lut_s + dd));
-    sc = min(dg, r.q) - pen;
+    const unsigned tb = (unsigned)dr - (unsigned)dq + bw;
+    const bool band = tb <= 2u * bw;
+    if (band) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pen) : "r"(lut_s + tb));
+    const int m = min(min(dr, dq), r.q);
+    sc = m - pen;
     bool ok = band;
-    ok = ok && dg > 0;
+    ok = ok && m > 0;
     ok = ok && dq <= maxd_q;
     return ok;
 }
@@ -375,16 +400,23 @@ __device__ void score_unit_tiled(const uint4 *__restrict__ a, const int *__restr
             const int val = s + r.f;
             if (ok && j >= sti && val >= thr) thr = val, bj = j;
         }
-        // phase A.1: ring, windows still opening (needs the j >= st_i test)
+        // phase A.1 / A.2: the ring, walked in address-contiguous runs (a run never wraps, so loads are [base + imm]).
+        // A.1 = windows still opening (needs the j >= st_i test), A.2 = every active lane's window is open.
         int j = max(wmin, jring);
-        for (; j < wfull; ++j) {
-            const Rec r = ring[(j - u0) & (R - 1)];
-            int s;
-            const bool ok = pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s);
-            const int val = s + r.f;
-            if (ok && j >= sti && val >= thr) thr = val, bj = j;
+        while (j < wfull) {
+            const int pos = (j - u0) & (R - 1);
+            const int len = min(wfull - j, R - pos);
+            const Rec *rp = ring + pos;
+#pragma unroll 4
+            for (int k = 0; k < len; ++k) {
+                const Rec r = rp[k];
+                int s;
+                const bool ok = pair_score<FAST>(xi, yi, sidi, r, P, lut_s, pen, s);
+                const int val = s + r.f;
+                if (ok && j + k >= sti && val >= thr) thr = val, bj = j + k;
+            }
+            j += len;
         }
-        // phase A.2: ring, all windows open.  The ring is walked in (at most two) address-contiguous runs.
         while (j < t0) {
             const int pos = (j - u0) & (R - 1);
             const int len = min(t0 - j, R - pos);
@@ -407,21 +439,29 @@ __device__ void score_unit_tiled(const uint4 *__restrict__ a, const int *__restr
 
         // phase B: in-tile triangle.  static part first (independent of f), then the serial chain
         const int nact = min(32, u1 - t0);
-        int w[31];
-#pragma unroll
-        for (int s = 0; s < 31; ++s) {
-            if (s >= nact - 1) break; // warp-uniform
-            int sc;
-            const bool ok = pair_score<FAST>(xi, yi, sidi, tile[s], P, lut_s, pen, sc);
-            w[s] = (ok && s < lane && t0 + s >= sti) ? sc : kNeg;
-        }
         int fcur = bj >= 0 ? thr : qsi;
 #pragma unroll
-        for (int s = 0; s < 31; ++s) {
-            if (s >= nact - 1) break; // warp-uniform
-            const int fs = __shfl_sync(full, fcur, s);
-            const int val = fs + w[s];                  // kNeg + f stays far below any threshold
-            if (val >= thr) thr = val, fcur = val, bj = t0 + s;
+        for (int h = 0; h < 2; ++h) { // two halves keep the pre-scored set at 16 registers
+            if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
+            int w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int s = h * 16 + q;
+                if (s < 31) {
+                    int sc;
+                    const bool ok = pair_score<FAST>(xi, yi, sidi, tile[s], P, lut_s, pen, sc);
+                    w[q] = (ok && s < lane && t0 + s >= sti) ? sc : kNeg;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int s = h * 16 + q;
+                if (s < 31) {
+                    const int fs = __shfl_sync(full, fcur, s);
+                    const int val = fs + w[q];                  // kNeg + f stays far below any threshold
+                    if (val >= thr) thr = val, fcur = val, bj = t0 + s;
+                }
+            }
         }
         if (act) {
             f[i] = fcur;
@@ -437,11 +477,175 @@ __device__ void score_unit_tiled(const uint4 *__restrict__ a, const int *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kScoreWarps = 4;
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// packed-key variant of the tiled scoring (table path only).  For a unit of at most 8192 anchors whose scores fit 18 bits
+// (length * max q_span < 2^18 -- every 10-100 kb ONT read), score and predecessor travel in ONE register:
+//     key = f << 13 | (j - u0)
+// The ring stores F_j = f_j << 13 | slot_j, a candidate is key = F_j + ((min(dr,dq,q) - pen) << 13), and the running best
+// is thr = max(thr, key): the max picks the best score and, among equal scores, the largest j (lchain.c:174-181 scans j
+// downward with a strict '>').  thr starts at q_span << 13 | 8191, so a candidate that merely equals q_span(i) loses
+// (max_j stays -1).  This replaces compare + two selects + index bookkeeping per pair by one predicated max.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSlotBits = 13, kSlotMask = (1 << kSlotBits) - 1;
+constexpr int kNegKey = -(1 << 30);
+
+
+// One candidate of the packed-key path, written in PTX so that the validity tests stay ONE predicate chain and the update
+// is a single predicated max (nvcc otherwise expands the chain into a select per condition):
+//   p = (dr - dq + bw <=u 2bw) ; pen = lut[..] if p ; m = min(dr, dq, q) ; p &= m > 0 ; p &= dq <= maxd [; p &= j >= st_i]
+//   if (p) thr = max(thr, F_j + ((m - pen) << 13))
+template <bool CHECK>
+__device__ __forceinline__ void packed_update(int &thr, int &pen, int xi, int yi, const Rec &r, int maxd_q, unsigned bw, unsigned bw2,
+                                              unsigned lut_s, int j, int sti)
+{
+    asm volatile("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .s32 dr, dq, m, d, key;\n\t"
+        ".reg .u32 tb, ad;\n\t"
+        "sub.s32 dr, %2, %4;\n\t"
+        "sub.s32 dq, %3, %5;\n\t"
+        "sub.s32 d, dr, dq;\n\t"
+        "add.s32 d, d, %8;\n\t"
+        "mov.b32 tb, d;\n\t"
+        "setp.le.u32 p, tb, %9;\n\t"
+        "add.u32 ad, tb, %10;\n\t"
+        "@p ld.shared.u8 %1, [ad];\n\t"
+        "min.s32 m, dr, dq;\n\t"
+        "min.s32 m, m, %7;\n\t"
+        "setp.gt.and.s32 p, m, 0, p;\n\t"
+        "setp.le.and.s32 p, dq, %11, p;\n\t"
+        "setp.ge.and.s32 p, %12, %13, p;\n\t"
+        "sub.s32 d, m, %1;\n\t"
+        "mad.lo.s32 key, d, 8192, %6;\n\t"
+        "@p max.s32 %0, %0, key;\n\t"
+        "}"
+        : "+r"(thr), "+r"(pen)
+        : "r"(xi), "r"(yi), "r"(r.x), "r"(r.y), "r"(r.f), "r"(r.q), "r"(bw), "r"(bw2), "r"(lut_s), "r"(maxd_q),
+          "r"(CHECK ? j : 1), "r"(CHECK ? sti : 0));
+}
+
+// in-tile candidate, f-independent part: (m - pen) << 13 if the pair is valid and (extra) holds, else kNegKey
+__device__ __forceinline__ int packed_static(int &pen, int xi, int yi, const Rec &r, int maxd_q, unsigned bw, unsigned bw2, unsigned lut_s, int extra)
+{
+    int w;
+    asm volatile("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .s32 dr, dq, m, d;\n\t"
+        ".reg .u32 tb, ad;\n\t"
+        "sub.s32 dr, %2, %4;\n\t"
+        "sub.s32 dq, %3, %5;\n\t"
+        "sub.s32 d, dr, dq;\n\t"
+        "add.s32 d, d, %7;\n\t"
+        "mov.b32 tb, d;\n\t"
+        "setp.le.u32 p, tb, %8;\n\t"
+        "add.u32 ad, tb, %9;\n\t"
+        "@p ld.shared.u8 %1, [ad];\n\t"
+        "min.s32 m, dr, dq;\n\t"
+        "min.s32 m, m, %6;\n\t"
+        "setp.gt.and.s32 p, m, 0, p;\n\t"
+        "setp.le.and.s32 p, dq, %10, p;\n\t"
+        "setp.ne.and.s32 p, %11, 0, p;\n\t"
+        "sub.s32 d, m, %1;\n\t"
+        "shl.b32 d, d, 13;\n\t"
+        "selp.s32 %0, d, -1073741824, p;\n\t"
+        "}"
+        : "=r"(w), "+r"(pen)
+        : "r"(xi), "r"(yi), "r"(r.x), "r"(r.y), "r"(r.q), "r"(bw), "r"(bw2), "r"(lut_s), "r"(maxd_q), "r"(extra));
+    return w;
+}
+
+template <int R>
+__device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p,
+                                  int u0, int u1, int rbase, const DevParams &P, unsigned lut_s, Rec *ring, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned bw = (unsigned)P.bw, bw2 = 2u * (unsigned)P.bw;
+    int pen = 0; // scratch of the table load, only rewritten inside the band
+    for (int t0 = u0; t0 < u1; t0 += 32) {
+        const int i = t0 + lane;
+        const bool act = i < u1;
+        uint4 ai = make_uint4(0, 0, 0, 0);
+        int sti = INT32_MAX; // inactive lanes: empty window
+        if (act) { ai = __ldg(a + i); sti = st[i]; }
+        const int xi = (int)ai.x, yi = (int)ai.z, qsi = (int)(ai.w & 0xffu);
+        const int wmin = __shfl_sync(full, sti, 0);
+        const int wfull = min(t0, __reduce_max_sync(full, act ? sti : 0));
+        const int jring = max(u0, t0 - R);
+        const int thr0 = (qsi << kSlotBits) | kSlotMask;
+        int thr = thr0;
+
+        for (int j = wmin; j < min(jring, t0); ++j) { // window longer than the ring: global / L1
+            Rec r = fetch_global<true>(a, f, j);
+            r.f = (r.f << kSlotBits) | (j - u0);
+            packed_update<true>(thr, pen, xi, yi, r, P.maxd_q, bw, bw2, lut_s, j, sti);
+        }
+        int j = max(wmin, jring);
+        while (j < wfull) { // windows still opening
+            const int pos = (j - u0) & (R - 1);
+            const int len = min(wfull - j, R - pos);
+            const Rec *rp = ring + pos;
+#pragma unroll 4
+            for (int k = 0; k < len; ++k) {
+                const Rec r = rp[k];
+                packed_update<true>(thr, pen, xi, yi, r, P.maxd_q, bw, bw2, lut_s, j + k, sti);
+            }
+            j += len;
+        }
+        while (j < t0) { // every active lane's window is open
+            const int pos = (j - u0) & (R - 1);
+            const int len = min(t0 - j, R - pos);
+            const Rec *rp = ring + pos;
+#pragma unroll 4
+            for (int k = 0; k < len; ++k) {
+                const Rec r = rp[k];
+                packed_update<false>(thr, pen, xi, yi, r, P.maxd_q, bw, bw2, lut_s, 0, 0);
+            }
+            j += len;
+        }
+        __syncwarp();
+        Rec *tile = ring + ((t0 - u0) & (R - 1));
+        if (act) tile[lane] = make_rec<true>(ai, 0);
+        __syncwarp();
+
+        // phase B in two halves (s = 0..15, 16..30): the f-independent parts of 16 in-tile candidates are pre-scored into
+        // registers, then resolved by the serial chain; halving keeps the live set at 16 values instead of 31.
+        const int nact = min(32, u1 - t0);
+        const int slot = i - u0;
+        int fown = (thr & ~kSlotMask) | slot; // this anchor as a predecessor: current score, own slot
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
+            int w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int s = h * 16 + q;
+                if (s < 31) w[q] = packed_static(pen, xi, yi, tile[s], P.maxd_q, bw, bw2, lut_s, (s < lane && t0 + s >= sti) ? 1 : 0);
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int s = h * 16 + q;
+                if (s < 31) {
+                    const int fs = __shfl_sync(full, fown, s);
+                    thr = max(thr, fs + w[q]);
+                    fown = (thr & ~kSlotMask) | slot;
+                }
+            }
+        }
+        if (act) {
+            f[i] = thr >> kSlotBits;
+            p[i] = thr == thr0 ? -1 : u0 + (thr & kSlotMask) - rbase;
+            tile[lane].f = fown;
+        }
+        __syncwarp();
+    }
+}
 template <int R, bool FAST>
-__global__ void __launch_bounds__(kScoreWarps * 32)
+__global__ void __launch_bounds__(kScoreWarps * 32, 6) // 6 CTAs/SM = what the 512-entry rings allow; caps registers at 80
 k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int *__restrict__ unit_start,
               const int *__restrict__ unit_rbase, const unsigned *__restrict__ clipmask, int *f, int *__restrict__ p,
-              Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g, int run_mode, int long_min)
+              const int *__restrict__ big_order, int big_cap, Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g,
+              int run_mode, int long_min)
 {
     extern __shared__ int4 smem_raw[];
     unsigned char *lut = reinterpret_cast<unsigned char *>(smem_raw);
@@ -457,16 +661,30 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
     for (int k = threadIdx.x; k < P.lut_n; k += blockDim.x) lut[k] = lut_g[k];
     __syncthreads();
     const int n_units = ctr->n_units;
+    const int qs_max = max(ctr->qs_max, 1);
+    const int bb1 = min(ctr->big_cnt[0], big_cap), bb2 = bb1 + min(ctr->big_cnt[1], big_cap);
+    const int bb3 = bb2 + min(ctr->big_cnt[2], big_cap), n_big = bb3 + min(ctr->big_cnt[3], big_cap);
     for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&ctr->next_unit, 1);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= n_units) break;
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&ctr->next_unit, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        int k;
+        if (w < n_big) { // longest-first lists
+            const int c = w >= bb3 ? 3 : w >= bb2 ? 2 : w >= bb1 ? 1 : 0;
+            const int base = w >= bb3 ? bb3 : w >= bb2 ? bb2 : w >= bb1 ? bb1 : 0;
+            k = big_order[c * big_cap + (w - base)];
+        } else {
+            k = w - n_big;
+            if (k >= n_units) break;
+        }
         const int u0 = unit_start[k], u1 = unit_start[k + 1], rbase = unit_rbase[k];
+        if (w >= n_big && u1 - u0 >= kBigMin) continue; // already taken from a list
         if (u1 - u0 >= long_min) continue; // left to k_score_long
         if (unit_has_clip(clipmask, u0, u1, lane)) {
             if (lane == 0) atomicAdd(&ctr->n_exact, 1);
             score_unit_exact<FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, lane);
+        } else if (FAST && u1 - u0 <= (1 << kSlotBits) && (u1 - u0) * qs_max < (1 << 18)) {
+            score_unit_packed<R>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
         } else {
             score_unit_tiled<R, FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
         }
