@@ -121,6 +121,27 @@ def cpu_baseline(a, off, budget_s=20.0):
             "reads_per_s": n_sample / dt}, pairs, dt, n_sample
 
 
+def host_stage_alone(pkg, misc, a, off, f, p, n_threads):
+    """Wall time of the threaded host stage (backtracking + compaction) alone, f/p already on the host."""
+    import ctypes as C
+    L = pkg.lib()
+    n_reads = len(off) - 1
+    n = int(off[-1])
+    u = np.empty(max(n, 1), np.uint64)
+    b = np.empty((max(n, 1), 2), np.uint64)
+    n_u = np.zeros(n_reads, np.int32)
+    n_b = np.zeros(n_reads, np.int64)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rc = L.mm2gb_backtrack_batch(C.byref(misc), a.ctypes.data, off.ctypes.data, n_reads, f.ctypes.data, p.ctypes.data, u.ctypes.data,
+                                     n_u.ctypes.data, b.ctypes.data, n_b.ctypes.data, n_threads)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,6 +248,12 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     n_chains = int(res["n_u"].sum())
+    # where the end-to-end time goes: the same call without the host stage, and the host stage alone on resident f/p
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.chain_dp(h_a, off, f=out["f"], p=out["p"])
+    dp_only_s = (time.perf_counter() - t0) / e2e_steps
+    host_only_s = host_stage_alone(pkg, misc, a, off, out["f"].numpy(), out["p"].numpy(), host_threads)
 
     # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
     tot = torch.tensor([float(pairs), float(n), float(n_reads)], dtype=torch.float64, device="cuda")
@@ -272,7 +299,8 @@ def main():
             "roofline": roofline,
             "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1), "d2h_bytes_per_step": 8 * n,
                     "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps, "host_threads": host_threads,
-                    "includes": "H2D anchors, range+unit+score kernels, D2H f/p, threaded host backtracking+compaction (= whole mg_lchain_dp)"},
+                    "includes": "H2D anchors, range+unit+score kernels, D2H f/p, threaded host backtracking+compaction (= whole mg_lchain_dp)",
+                    "breakdown_ms": {"upload_kernels_download_only": 1e3 * dp_only_s, "host_stage_alone": 1e3 * host_only_s}},
             "gpu_launches": 5 * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]

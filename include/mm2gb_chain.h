@@ -109,6 +109,10 @@ int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launch
 int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p, const mm2gb_anchor_t *a, int32_t min_cnt, int32_t min_sc,
                         int32_t max_drop, uint64_t *u, mm2gb_anchor_t *b, int64_t *n_b);
 
+/* The same for a batch on `n_threads` host threads (layout of u/b/n_u/n_b as in mm2gb_chain_host). */
+int mm2gb_backtrack_batch(const mm2gb_misc_t *misc, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
+                          const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,7 @@ def lib():
         L.mm2gb_device_stats.argtypes = [vp, C.POINTER(Stats)]
         L.mm2gb_profile.argtypes = [vp, C.c_int]
         L.mm2gb_profile_read.argtypes = [vp, C.POINTER(C.c_float), i64p]
+        L.mm2gb_backtrack_batch.argtypes = [C.POINTER(Misc), vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
         L.mm2gb_backtrack.restype = C.c_int32
         L.mm2gb_backtrack.argtypes = [C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, i64p]
         _lib = L

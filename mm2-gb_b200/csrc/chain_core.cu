@@ -593,6 +593,32 @@ extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
     return rc;
 }
 
+// The host stage alone for a batch whose f/p are already in host memory (what mm2gb_chain_host runs behind the device).
+extern "C" int mm2gb_backtrack_batch(const mm2gb_misc_t *m, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
+                                     const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads)
+{
+    if (!m || !off || n_reads < 0 || !n_u || !n_b) return fail(MM2GB_EARG, "bad argument");
+    if (n_reads && off[n_reads] > 0 && (!a || !f || !p || !u || !b)) return fail(MM2GB_EARG, "bad argument");
+    if (n_threads < 1) n_threads = 1;
+    const int32_t max_drop = m->is_cdna ? INT32_MAX : m->bw; // lchain.c:151,162
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int r = next.fetch_add(1);
+            if (r >= n_reads) return;
+            const int64_t s = off[r], n = off[r + 1] - s;
+            int64_t nb = 0;
+            n_u[r] = mm2gb_backtrack(n, f + s, p + s, a + s, m->min_cnt, m->min_score, max_drop, u + s, b + s, &nb);
+            n_b[r] = nb;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return MM2GB_OK;
+}
+
 extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p)
 {
     if (!c || n_reads < 0 || n_total < 0 || !d_off) return fail(MM2GB_EARG, "bad argument");
