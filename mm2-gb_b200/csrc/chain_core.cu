@@ -62,7 +62,7 @@ struct Slot {
     long long *d_off = nullptr;
     int *d_st = nullptr, *d_f = nullptr, *d_p = nullptr;
     unsigned *d_selmask = nullptr, *d_clipmask = nullptr;
-    int *d_block_cnt = nullptr, *d_block_base = nullptr, *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
+    int *d_block_cnt = nullptr, *d_block_base = nullptr; unsigned long long *d_block_pairs = nullptr; int *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
     int big_cap = 0;
     Counters *d_ctr = nullptr;
     // pinned host
@@ -169,7 +169,7 @@ static int config_score(mm2gb_ctx *c, size_t smem)
 template <int R>
 static int config_ring(mm2gb_ctx *c)
 {
-    const size_t smem = (size_t)((c->prm.lut_n + 15) & ~15) + (size_t)kScoreWarps * R * sizeof(Rec);
+    const size_t smem = (size_t)kScoreWarps * R * sizeof(Rec);
     c->score_smem = smem;
     c->score_blocks = 0;
     int rc = config_score<R, true>(c, smem);
@@ -181,7 +181,7 @@ template <int R, bool FAST>
 static void launch_score(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int *st, const int *us, const int *ur,
                          const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode)
 {
-    const size_t smem = (size_t)((c->prm.lut_n + 15) & ~15) + (size_t)kScoreWarps * R * sizeof(Rec);
+    const size_t smem = (size_t)kScoreWarps * R * sizeof(Rec);
     k_score_units<R, FAST><<<c->score_blocks, kScoreWarps * 32, smem, s>>>(a, st, us, ur, clip, f, p, big, big_cap, ctr, c->prm,
                                                                           c->d_lut, run_mode, c->long_min);
 }
@@ -238,12 +238,13 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
     const int n_groups = (n + 31) / 32;
     {
         ProfScope ps(c, T_RANGE, s, prof);
-        k_range<<<n_blocks, kRangeThreads, 0, s>>>(reinterpret_cast<const ulonglong2 *>(d_a), d_off, n_reads, n, c->prm, sl.d_st,
-                                                  sl.d_selmask, sl.d_clipmask, sl.d_block_cnt, sl.d_ctr);
+        k_block_reads<<<(n_blocks + 255) / 256, 256, 0, s>>>(d_off, n_reads, n_blocks, sl.d_block_base);   // d_block_base doubles as block_read until k_scan
+        k_range<<<n_blocks, kRangeThreads, 0, s>>>(reinterpret_cast<const ulonglong2 *>(d_a), d_off, sl.d_block_base, n, c->prm, sl.d_st,
+                                                  sl.d_selmask, sl.d_clipmask, sl.d_block_cnt, sl.d_block_pairs, sl.d_ctr);
     }
     {
         ProfScope ps(c, T_UNITS, s, prof);
-        k_scan<<<1, 1024, 0, s>>>(sl.d_block_cnt, n_blocks, sl.d_block_base, sl.d_ctr);
+        k_scan<<<1, 1024, 0, s>>>(sl.d_block_cnt, sl.d_block_pairs, n_blocks, sl.d_block_base, sl.d_ctr);
         k_units<<<(n_groups + 255) / 256, 256, 0, s>>>(sl.d_selmask, sl.d_block_base, d_off, n_reads, n, n_groups, sl.d_unit_start,
                                                       sl.d_unit_rbase, sl.d_ctr);
         k_order<<<(n_groups + n_reads + 256) / 256, 256, 0, s>>>(sl.d_unit_start, sl.d_big_order, sl.big_cap, sl.d_ctr);
@@ -276,7 +277,7 @@ static void free_slot(Slot &s)
 {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
-    cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base);
+    cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
     cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
     cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
     if (s.done) cudaEventDestroy(s.done);
@@ -339,6 +340,7 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaMalloc(&s.d_clipmask, n_groups * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_block_cnt, n_blocks * sizeof(int)));
             CKC(cudaMalloc(&s.d_block_base, n_blocks * sizeof(int)));
+            CKC(cudaMalloc(&s.d_block_pairs, n_blocks * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_unit_start, n_units_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_unit_rbase, n_units_cap * sizeof(int)));
             s.big_cap = (int)(n / kBigMin) + 2;

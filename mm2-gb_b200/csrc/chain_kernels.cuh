@@ -25,7 +25,7 @@ namespace mm2gb {
 constexpr int kRangeThreads = 256;          // anchors per k_range block
 constexpr int kGroupsPerBlock = kRangeThreads / 32;
 constexpr int kNeg = -(1 << 30);            // "rejected pair" (lchain.c returns INT32_MIN); never wins a max
-constexpr int kLutMax = 4096;               // largest bw served by the integer penalty table
+constexpr int kLutMax = 1024;               // largest bw served by the integer penalty table (static shared: 2*bw+1 bytes)
 
 // chaining parameters after the adjustments of lchain.c:160-161
 struct DevParams {
@@ -56,52 +56,119 @@ __device__ __forceinline__ int big_class(int len) { return len >= 4096 ? 0 : len
 // k_range: window start, cuts, clipped windows, pair count            (replaces gpu/plrange.cu:38-76)
 //   one thread per anchor of the flat batch; a block first finds the read that holds its first anchor.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRangeThreads)
-k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int n_reads, int n_total, DevParams prm,
-        int *__restrict__ st, unsigned *__restrict__ selmask, unsigned *__restrict__ clipmask, int *__restrict__ block_cnt,
-        Counters *__restrict__ ctr)
+// window start of anchor g by gallop + binary search in global memory (any window length): first index in [lo0, g] whose
+// x is >= lower
+__device__ __forceinline__ int window_start_global(const ulonglong2 *__restrict__ a, int g, int lo0, unsigned long long lower)
 {
-    __shared__ int s_r0;
+    int hi = g, bad = lo0 - 1, step = 1;
+    for (;;) { // gallop back from g
+        int probe = hi - step;
+        if (probe <= lo0) {
+            if (hi > lo0) { if (a[lo0].x >= lower) hi = lo0; else bad = lo0; }
+            break;
+        }
+        if (a[probe].x >= lower) { hi = probe; step <<= 1; }
+        else { bad = probe; break; }
+    }
+    while (hi - bad > 1) {
+        int mid = (hi + bad) >> 1;
+        if (a[mid].x >= lower) hi = mid; else bad = mid;
+    }
+    return hi;
+}
+
+constexpr int kRangeHist = 1024;            // most x history (anchors before the block) staged in shared memory
+
+// block_read[b] = the read that owns the first anchor of k_range block b (largest r with off[r] <= 256 b): one thread per
+// block here, so that k_range itself starts without a 14-step dependent binary search in front of every block
+__global__ void __launch_bounds__(256)
+k_block_reads(const long long *__restrict__ off, int n_reads, int n_blocks, int *__restrict__ block_read)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const long long g0 = (long long)b * kRangeThreads;
+    int lo = 0, hi = n_reads;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= g0) lo = mid; else hi = mid;
+    }
+    block_read[b] = lo;
+}
+
+__global__ void __launch_bounds__(kRangeThreads)
+k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, const int *__restrict__ block_read, int n_total, DevParams prm,
+        int *__restrict__ st, unsigned *__restrict__ selmask, unsigned *__restrict__ clipmask, int *__restrict__ block_cnt,
+        unsigned long long *__restrict__ block_pairs, Counters *__restrict__ ctr)
+{
+    // x of the anchors [g0 - hist, g0 + 256): the block's own anchors plus as much history as the first anchor's window
+    // needs (grown 256 at a time, coalesced), so the per-anchor binary search runs on shared memory
+    __shared__ unsigned long long s_x[kRangeHist + kRangeThreads];
+    __shared__ int s_more;
     __shared__ int s_cnt[kGroupsPerBlock];
+    __shared__ unsigned long long s_pairs[kGroupsPerBlock];
     const int g0 = blockIdx.x * kRangeThreads;
     const int g = g0 + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { // largest r with off[r] <= g0  (lands on the non-empty read that owns g0)
-        int lo = 0, hi = n_reads;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (off[mid] <= (long long)g0) lo = mid; else hi = mid;
-        }
-        s_r0 = lo;
-    }
-    __syncthreads();
+    const int r0 = block_read[blockIdx.x];
     const bool act = g < n_total;
+    ulonglong2 ai = make_ulonglong2(0, 0);
+    if (act) ai = a[g];
+    // y of the previous anchor (lane 0 fetches it, the others get it by shuffle): segment ids are compared between neighbours
+    unsigned long long yprev = (lane == 0 && act && g > 0) ? a[g - 1].y : 0ULL;
+    {
+        const unsigned long long yup = __shfl_up_sync(0xffffffffu, ai.y, 1);
+        if (lane) yprev = yup;
+    }
+    s_x[kRangeHist + threadIdx.x] = ai.x;
+    __syncthreads();
+    // history: stop once the oldest staged x is outside the first anchor's window (x sorted => outside everyone's), or the
+    // read of the first anchor starts inside the staged part (a later read starts later still)
+    const unsigned mdx = (unsigned)prm.max_dist_x;
+    int hist = 0;
+    {
+        const unsigned long long x0 = s_x[kRangeHist];
+        const unsigned x0lo = (unsigned)x0;
+        const unsigned long long lower0 = (x0 & 0xffffffff00000000ULL) | (unsigned long long)(x0lo > mdx ? x0lo - mdx : 0u);
+        const long long rs0 = off[r0];
+        while (hist < kRangeHist) {
+            const int base = g0 - hist - kRangeThreads;    // next chunk [base, base + 256)
+            const int gi = base + (int)threadIdx.x;
+            const unsigned long long xv = gi >= 0 ? a[gi].x : 0ULL;
+            s_x[kRangeHist - hist - kRangeThreads + threadIdx.x] = xv;
+            if (threadIdx.x == 0) s_more = (gi > rs0 && xv >= lower0) ? 1 : 0;   // oldest of the chunk still inside the window
+            hist += kRangeThreads;
+            __syncthreads();
+            const int more = s_more;
+            __syncthreads();
+            if (!more) break;
+        }
+    }
+    const int h0 = g0 - hist;   // s_x[kRangeHist + (j - g0)] is valid for j in [max(h0, 0), g0 + 256)
     bool cut = false, clipped = false, rstart = false;
     int npair = 0, qspan = 0;
     if (act) {
-        int r = s_r0;
+        int r = r0;
         while (off[r + 1] <= (long long)g) ++r;
         const int rs = (int)off[r];
-        const ulonglong2 ai = a[g];
         const unsigned long long xi = ai.x;
-        const unsigned lo32 = (unsigned)xi, mdx = (unsigned)prm.max_dist_x;
+        const unsigned lo32 = (unsigned)xi;
         // lchain.c:172: j is in the window iff same rid/strand and x_i <= x_j + max_dist_x  <=>  x_j >= lower
         const unsigned long long lower = (xi & 0xffffffff00000000ULL) | (unsigned long long)(lo32 > mdx ? lo32 - mdx : 0u);
         const long long lo_ll = (long long)g - (long long)prm.max_iter;   // lchain.c:173
         const int lo0 = lo_ll > (long long)rs ? (int)lo_ll : rs;
-        int hi = g, bad = lo0 - 1, step = 1;
-        for (;;) { // gallop back from g
-            int probe = hi - step;
-            if (probe <= lo0) {
-                if (hi > lo0) { if (a[lo0].x >= lower) hi = lo0; else bad = lo0; }
-                break;
+        int hi;
+        const int lo_s = max(lo0, max(h0, 0));   // oldest candidate available in shared memory
+        const int sb = kRangeHist - g0;   // s_x[sb + j] = x of anchor j
+        if (lo_s > lo0 && s_x[sb + lo_s] >= lower) {
+            hi = window_start_global(a, g, lo0, lower);   // window reaches beyond the staged history (rare)
+        } else {
+            // first index in [lo_s, g] with x >= lower; x[g] itself qualifies
+            int bad = lo_s - 1;
+            hi = g;
+            while (hi - bad > 1) {
+                const int mid = (hi + bad) >> 1;
+                if (s_x[sb + mid] >= lower) hi = mid; else bad = mid;
             }
-            if (a[probe].x >= lower) { hi = probe; step <<= 1; }
-            else { bad = probe; break; }
-        }
-        while (hi - bad > 1) {
-            int mid = (hi + bad) >> 1;
-            if (a[mid].x >= lower) hi = mid; else bad = mid;
         }
         st[g] = hi;
         npair = g - hi;
@@ -111,43 +178,52 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int
         // lchain.c:115-116 compares the segment ids of the two anchors; one id per read is the common case
         qspan = (int)((ai.y >> 32) & 0xff);
         // (the table path also assumes q_span > 0, which every real seed satisfies)
-        if ((unsigned)((ai.y >> 48) & 0xff) != (unsigned)((a[rs].y >> 48) & 0xff) || ((ai.y >> 32) & 0xff) == 0) atomicOr(&ctr->multi_sid, 1);
+        if ((g > rs && (unsigned)((ai.y >> 48) & 0xff) != (unsigned)((yprev >> 48) & 0xff)) || ((ai.y >> 32) & 0xff) == 0) atomicOr(&ctr->multi_sid, 1);
     }
     const unsigned cutm = __ballot_sync(0xffffffffu, cut);
     const unsigned rsm = __ballot_sync(0xffffffffu, rstart);
     const unsigned clm = __ballot_sync(0xffffffffu, clipped);
     // unit boundaries: the first cut of every 32-anchor group, plus every read start (so no unit spans two reads)
     const unsigned sel = (cutm & (0u - cutm)) | rsm;
-    unsigned long long psum = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair);
+    // pairs of this block: summed by k_scan, not by a million same-address atomics.  npair < 2^31, so the warp sum is
+    // taken in two 16-bit halves to stay inside 32-bit redux
+    const unsigned long long psum = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair & 0xffffu) +
+                                    ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair >> 16) << 16);
     const int qmax = __reduce_max_sync(0xffffffffu, qspan);
     if (lane == 0) {
         if (qmax > ctr->qs_max) atomicMax(&ctr->qs_max, qmax);
         const int grp = g >> 5;
         if (g0 + wid * 32 < n_total) { selmask[grp] = sel; clipmask[grp] = clm; }
         s_cnt[wid] = __popc(sel);
-        if (psum) atomicAdd(&ctr->n_pairs, psum);
+        s_pairs[wid] = psum;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int c = 0;
+        unsigned long long ps = 0;
 #pragma unroll
-        for (int w = 0; w < kGroupsPerBlock; ++w) c += s_cnt[w];
+        for (int w = 0; w < kGroupsPerBlock; ++w) c += s_cnt[w], ps += s_pairs[w];
         block_cnt[blockIdx.x] = c;
+        block_pairs[blockIdx.x] = ps;
     }
 }
 
 // k_scan: exclusive prefix of the per-block unit counts (single block), total -> ctr->n_units
 __global__ void __launch_bounds__(1024)
-k_scan(const int *__restrict__ block_cnt, int n_blocks, int *__restrict__ block_base, Counters *__restrict__ ctr)
+k_scan(const int *__restrict__ block_cnt, const unsigned long long *__restrict__ block_pairs, int n_blocks, int *__restrict__ block_base,
+       Counters *__restrict__ ctr)
 {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
+    __shared__ unsigned long long s_pw[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
+    unsigned long long pairs = 0;
     for (int base = 0; base < n_blocks; base += 1024) {
         const int i = base + threadIdx.x;
         const int v = i < n_blocks ? block_cnt[i] : 0;
+        if (i < n_blocks) pairs += block_pairs[i];
         int x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -173,7 +249,17 @@ k_scan(const int *__restrict__ block_cnt, int n_blocks, int *__restrict__ block_
         if (threadIdx.x == 1023) s_carry = incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) ctr->n_units = s_carry;
+    // total pair count = sum_i (i - st_i)  (the reference's n_iter, lchain.c:177)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+    if (lane == 0) s_pw[wid] = pairs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 32; ++w) t += s_pw[w];
+        ctr->n_pairs = t;
+        ctr->n_units = s_carry;
+    }
 }
 
 // k_units: ordered scatter of the selected cuts -> unit_start[k], unit_rbase[k] (first anchor of the owning read),
@@ -482,86 +568,177 @@ constexpr int kScoreWarps = 4;
 // packed-key variant of the tiled scoring (table path only).  For a unit of at most 8192 anchors whose scores fit 18 bits
 // (length * max q_span < 2^18 -- every 10-100 kb ONT read), score and predecessor travel in ONE register:
 //     key = f << 13 | (j - u0)
-// The ring stores F_j = f_j << 13 | slot_j, a candidate is key = F_j + ((min(dr,dq,q) - pen) << 13), and the running best
-// is thr = max(thr, key): the max picks the best score and, among equal scores, the largest j (lchain.c:174-181 scans j
-// downward with a strict '>').  thr starts at q_span << 13 | 8191, so a candidate that merely equals q_span(i) loses
-// (max_j stays -1).  This replaces compare + two selects + index bookkeeping per pair by one predicated max.
+// A candidate is key = F_j + (sc << 13) with F_j = f_j << 13 | slot_j, and the running best is thr = max(thr, key): the max
+// picks the best score and, among equal scores, the largest j (lchain.c:174-181 scans j downward with a strict '>').  thr
+// starts at q_span << 13 | 8191, so a candidate that merely equals q_span(i) loses (max_j stays -1).
+//
+// The ring record is laid out for the common case:  e = x - y (the diagonal),  g = F_j + (q_span_j << 13),  y,  q.
+// With D_i = x_i - y_i + bw, one subtraction gives tb = D_i - e_j = dr - dq + bw, the band test (lchain.c:121-122) is the
+// unsigned compare tb <= 2bw and tb is also the index into the symmetric penalty table.  Predecessors are then split, per
+// tile and warp-uniformly, by how far back they are (x is sorted inside a window):
+//   MID   dr > bw + max q_span for every lane of the tile  =>  inside the band dq >= dr - bw > q_span_j, so
+//         min(dr, dq, q_span_j) = q_span_j > 0 and sc = q_span_j - pen: already folded into g.  If also dr <= maxd_q - bw for
+//         every lane, dq <= dr + bw <= maxd_q holds too and the whole pair is  sub, setp, ld.u8, mad, max  (+ one 8-byte
+//         warp-uniform record load).
+//   FAR   as MID but dr may exceed maxd_q - bw (or the window of some lanes is still opening): adds the dq <= maxd_q test
+//         (and j >= st_i while the windows open).
+//   GEN   the near predecessors (dr <= bw + max q_span): the full min(dr, dq, q_span) of lchain.c:124-126.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kSlotBits = 13, kSlotMask = (1 << kSlotBits) - 1;
 constexpr int kNegKey = -(1 << 30);
 
+struct __align__(16) RecP { int e, g, y, q; };
 
-// One candidate of the packed-key path, written in PTX so that the validity tests stay ONE predicate chain and the update
-// is a single predicated max (nvcc otherwise expands the chain into a select per condition):
-//   p = (dr - dq + bw <=u 2bw) ; pen = lut[..] if p ; m = min(dr, dq, q) ; p &= m > 0 ; p &= dq <= maxd [; p &= j >= st_i]
-//   if (p) thr = max(thr, F_j + ((m - pen) << 13))
-template <bool CHECK>
-__device__ __forceinline__ void packed_update(int &thr, int &pen, int xi, int yi, const Rec &r, int maxd_q, unsigned bw, unsigned bw2,
-                                              unsigned lut_s, int j, int sti)
+enum { MODE_MID = 0, MODE_FAR = 1, MODE_GEN = 2 };
+
+// One candidate.  The validity tests stay ONE predicate chain and the update is a single predicated max.
+// D = x_i - y_i + bw; jk / sti only used when CHECK (window still opening for some lane).
+template <int MODE, bool CHECK>
+__device__ __forceinline__ void packed_upd(int &thr, int &pen, int D, int yi, int re, int rg, int ry, int rq, int maxd_q, unsigned bw,
+                                           unsigned bw2, unsigned lut_s, int jk, int sti)
 {
-    asm volatile("{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .s32 dr, dq, m, d, key;\n\t"
-        ".reg .u32 tb, ad;\n\t"
-        "sub.s32 dr, %2, %4;\n\t"
-        "sub.s32 dq, %3, %5;\n\t"
-        "sub.s32 d, dr, dq;\n\t"
-        "add.s32 d, d, %8;\n\t"
-        "mov.b32 tb, d;\n\t"
-        "setp.le.u32 p, tb, %9;\n\t"
-        "add.u32 ad, tb, %10;\n\t"
-        "@p ld.shared.u8 %1, [ad];\n\t"
-        "min.s32 m, dr, dq;\n\t"
-        "min.s32 m, m, %7;\n\t"
-        "setp.gt.and.s32 p, m, 0, p;\n\t"
-        "setp.le.and.s32 p, dq, %11, p;\n\t"
-        "setp.ge.and.s32 p, %12, %13, p;\n\t"
-        "sub.s32 d, m, %1;\n\t"
-        "mad.lo.s32 key, d, 8192, %6;\n\t"
-        "@p max.s32 %0, %0, key;\n\t"
-        "}"
-        : "+r"(thr), "+r"(pen)
-        : "r"(xi), "r"(yi), "r"(r.x), "r"(r.y), "r"(r.f), "r"(r.q), "r"(bw), "r"(bw2), "r"(lut_s), "r"(maxd_q),
-          "r"(CHECK ? j : 1), "r"(CHECK ? sti : 0));
+    if (MODE == MODE_MID) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .s32 key;\n\t"
+            ".reg .u32 tb, ad;\n\t"
+            "sub.s32 tb, %2, %3;\n\t"
+            "setp.le.u32 p, tb, %5;\n\t"
+            "add.u32 ad, tb, %6;\n\t"
+            "@p ld.shared.u8 %1, [ad];\n\t"
+            "mad.lo.s32 key, %1, -8192, %4;\n\t"
+            "@p max.s32 %0, %0, key;\n\t"
+            "}"
+            : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s));
+    } else if (MODE == MODE_FAR) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .s32 key, dq;\n\t"
+            ".reg .u32 tb, ad;\n\t"
+            "sub.s32 tb, %2, %3;\n\t"
+            "setp.le.u32 p, tb, %5;\n\t"
+            "add.u32 ad, tb, %6;\n\t"
+            "@p ld.shared.u8 %1, [ad];\n\t"
+            "sub.s32 dq, %7, %8;\n\t"
+            "setp.le.and.s32 p, dq, %9, p;\n\t"
+            "setp.ge.and.s32 p, %10, %11, p;\n\t"
+            "mad.lo.s32 key, %1, -8192, %4;\n\t"
+            "@p max.s32 %0, %0, key;\n\t"
+            "}"
+            : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q),
+              "r"(CHECK ? jk : 1), "r"(CHECK ? sti : 0));
+    } else {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .s32 key, dq, dr, m, d;\n\t"
+            ".reg .u32 tb, ad;\n\t"
+            "sub.s32 tb, %2, %3;\n\t"
+            "setp.le.u32 p, tb, %5;\n\t"
+            "add.u32 ad, tb, %6;\n\t"
+            "@p ld.shared.u8 %1, [ad];\n\t"
+            "sub.s32 dq, %7, %8;\n\t"
+            "add.s32 dr, dq, tb;\n\t"
+            "sub.s32 dr, dr, %12;\n\t"
+            "min.s32 m, dr, dq;\n\t"
+            "min.s32 m, m, %13;\n\t"
+            "setp.gt.and.s32 p, m, 0, p;\n\t"
+            "setp.le.and.s32 p, dq, %9, p;\n\t"
+            "setp.ge.and.s32 p, %10, %11, p;\n\t"
+            "sub.s32 d, %13, m;\n\t"
+            "add.s32 d, d, %1;\n\t"
+            "mad.lo.s32 key, d, -8192, %4;\n\t"
+            "@p max.s32 %0, %0, key;\n\t"
+            "}"
+            : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q),
+              "r"(CHECK ? jk : 1), "r"(CHECK ? sti : 0), "r"(bw), "r"(rq));
+    }
 }
 
-// in-tile candidate, f-independent part: (m - pen) << 13 if the pair is valid and (extra) holds, else kNegKey
-__device__ __forceinline__ int packed_static(int &pen, int xi, int yi, const Rec &r, int maxd_q, unsigned bw, unsigned bw2, unsigned lut_s, int extra)
+// predecessors [j0, j1) of the ring, walked in address-contiguous runs (a run never wraps, so loads are [base + imm])
+template <int R, int MODE, bool CHECK>
+__device__ __forceinline__ void packed_walk(int &thr, int &pen, int j0, int j1, int u0, const RecP *ring, int D, int yi, int maxd_q,
+                                            unsigned bw, unsigned bw2, unsigned lut_s, int sti)
+{
+    int j = j0;
+    while (j < j1) {
+        const int pos = (j - u0) & (R - 1);
+        const int len = min(j1 - j, R - pos);
+        const RecP *rp = ring + pos;
+#pragma unroll(MODE == MODE_MID ? 8 : 4)
+        for (int k = 0; k < len; ++k) {
+            if (MODE == MODE_MID) {
+                const int2 r = *reinterpret_cast<const int2 *>(rp + k);
+                packed_upd<MODE, CHECK>(thr, pen, D, yi, r.x, r.y, 0, 0, maxd_q, bw, bw2, lut_s, j + k, sti);
+            } else {
+                const int4 r = *reinterpret_cast<const int4 *>(rp + k);
+                packed_upd<MODE, CHECK>(thr, pen, D, yi, r.x, r.y, r.z, r.w, maxd_q, bw, bw2, lut_s, j + k, sti);
+            }
+        }
+        j += len;
+    }
+}
+
+// in-tile candidate, f-independent part: -(q_j - m + pen) << 13 if the pair is valid and (extra) holds, else kNegKey
+__device__ __forceinline__ int packed_static(int &pen, int D, int yi, int re, int ry, int rq, int maxd_q, unsigned bw, unsigned bw2,
+                                             unsigned lut_s, int extra)
 {
     int w;
     asm volatile("{\n\t"
         ".reg .pred p;\n\t"
-        ".reg .s32 dr, dq, m, d;\n\t"
+        ".reg .s32 dq, dr, m, d;\n\t"
         ".reg .u32 tb, ad;\n\t"
-        "sub.s32 dr, %2, %4;\n\t"
-        "sub.s32 dq, %3, %5;\n\t"
-        "sub.s32 d, dr, dq;\n\t"
-        "add.s32 d, d, %7;\n\t"
-        "mov.b32 tb, d;\n\t"
-        "setp.le.u32 p, tb, %8;\n\t"
-        "add.u32 ad, tb, %9;\n\t"
+        "sub.s32 tb, %2, %3;\n\t"
+        "setp.le.u32 p, tb, %4;\n\t"
+        "add.u32 ad, tb, %5;\n\t"
         "@p ld.shared.u8 %1, [ad];\n\t"
+        "sub.s32 dq, %6, %7;\n\t"
+        "add.s32 dr, dq, tb;\n\t"
+        "sub.s32 dr, dr, %10;\n\t"
         "min.s32 m, dr, dq;\n\t"
-        "min.s32 m, m, %6;\n\t"
+        "min.s32 m, m, %11;\n\t"
         "setp.gt.and.s32 p, m, 0, p;\n\t"
-        "setp.le.and.s32 p, dq, %10, p;\n\t"
-        "setp.ne.and.s32 p, %11, 0, p;\n\t"
-        "sub.s32 d, m, %1;\n\t"
+        "setp.le.and.s32 p, dq, %8, p;\n\t"
+        "setp.ne.and.s32 p, %9, 0, p;\n\t"
+        "sub.s32 d, m, %11;\n\t"
+        "sub.s32 d, d, %1;\n\t"
         "shl.b32 d, d, 13;\n\t"
         "selp.s32 %0, d, -1073741824, p;\n\t"
         "}"
         : "=r"(w), "+r"(pen)
-        : "r"(xi), "r"(yi), "r"(r.x), "r"(r.y), "r"(r.q), "r"(bw), "r"(bw2), "r"(lut_s), "r"(maxd_q), "r"(extra));
+        : "r"(D), "r"(re), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q), "r"(extra), "r"(bw), "r"(rq));
     return w;
+}
+
+// first c in [from, t0) whose ring x (= e + y) is >= X (signed; x is sorted over [from, t0)), t0 if none
+template <int R>
+__device__ __forceinline__ int ring_lower_bound(const RecP *ring, int u0, int from, int t0, int X, int lane)
+{
+    int j = from;
+    while (j < t0) {
+        const int c = j + lane;
+        bool ge = true;
+        if (c < t0) {
+            const RecP &r = ring[(c - u0) & (R - 1)];
+            ge = r.e + r.y >= X;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ge);
+        if (b) return min(t0, j + __ffs(b) - 1);
+        j += 32;
+    }
+    return t0;
 }
 
 template <int R>
 __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p,
-                                  int u0, int u1, int rbase, const DevParams &P, unsigned lut_s, Rec *ring, int lane)
+                                  int u0, int u1, int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecP *ring, int lane)
 {
     const unsigned full = 0xffffffffu;
     const unsigned bw = (unsigned)P.bw, bw2 = 2u * (unsigned)P.bw;
+    const int maxd_q = P.maxd_q;
+    const int near_d = P.bw + qs_max;       // dr >  near_d  =>  min(dr, dq, q_span_j) = q_span_j inside the band
+    const int far_d = maxd_q - P.bw;        // dr <= far_d   =>  dq <= maxd_q inside the band
     int pen = 0; // scratch of the table load, only rewritten inside the band
+    int jA = u0, jB = u0; // first predecessor with x >= x_last - far_d / x >= x_first - near_d (monotone inside a rid/strand run)
     for (int t0 = u0; t0 < u1; t0 += 32) {
         const int i = t0 + lane;
         const bool act = i < u1;
@@ -569,6 +746,8 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
         int sti = INT32_MAX; // inactive lanes: empty window
         if (act) { ai = __ldg(a + i); sti = st[i]; }
         const int xi = (int)ai.x, yi = (int)ai.z, qsi = (int)(ai.w & 0xffu);
+        const int D = xi - yi + (int)bw;
+        const int nact = min(32, u1 - t0);
         const int wmin = __shfl_sync(full, sti, 0);
         const int wfull = min(t0, __reduce_max_sync(full, act ? sti : 0));
         const int jring = max(u0, t0 - R);
@@ -576,43 +755,41 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
         int thr = thr0;
 
         for (int j = wmin; j < min(jring, t0); ++j) { // window longer than the ring: global / L1
-            Rec r = fetch_global<true>(a, f, j);
-            r.f = (r.f << kSlotBits) | (j - u0);
-            packed_update<true>(thr, pen, xi, yi, r, P.maxd_q, bw, bw2, lut_s, j, sti);
+            const uint4 v = __ldg(a + j);
+            const int fj = f[j];
+            const int rq = (int)(v.w & 0xffu);
+            packed_upd<MODE_GEN, true>(thr, pen, D, yi, (int)v.x - (int)v.z, ((fj + rq) << kSlotBits) | (j - u0), (int)v.z, rq, maxd_q, bw, bw2,
+                                       lut_s, j, sti);
         }
-        int j = max(wmin, jring);
-        while (j < wfull) { // windows still opening
-            const int pos = (j - u0) & (R - 1);
-            const int len = min(wfull - j, R - pos);
-            const Rec *rp = ring + pos;
-#pragma unroll 4
-            for (int k = 0; k < len; ++k) {
-                const Rec r = rp[k];
-                packed_update<true>(thr, pen, xi, yi, r, P.maxd_q, bw, bw2, lut_s, j + k, sti);
-            }
-            j += len;
+        const int lo = max(wmin, jring);        // first predecessor taken from the ring
+        const int open = min(t0, max(wfull, lo)); // from here on every active lane's window is open
+        // region boundaries (warp-uniform).  Everything in [open, t0) shares rid/strand with the whole tile, x ascending.
+        jA = jB = t0;
+        if (open < t0) {
+            const int x_first = __shfl_sync(full, xi, 0), x_last = __shfl_sync(full, xi, nact - 1);
+            jA = ring_lower_bound<R>(ring, u0, open, t0, x_last - far_d, lane);
+            jB = ring_lower_bound<R>(ring, u0, open, t0, x_first - near_d, lane);
         }
-        while (j < t0) { // every active lane's window is open
-            const int pos = (j - u0) & (R - 1);
-            const int len = min(t0 - j, R - pos);
-            const Rec *rp = ring + pos;
-#pragma unroll 4
-            for (int k = 0; k < len; ++k) {
-                const Rec r = rp[k];
-                packed_update<false>(thr, pen, xi, yi, r, P.maxd_q, bw, bw2, lut_s, 0, 0);
-            }
-            j += len;
-        }
+        // windows still opening: [lo, open).  If the near region starts after `open` (jB > open), x_open < x_first - near_d
+        // and x is ascending inside a lane's window, so every predecessor older than `open` is far for every lane that
+        // has it in its window; otherwise (young unit, or a tile that straddles rid/strand runs) score them in full.
+        if (jB > open) packed_walk<R, MODE_FAR, true>(thr, pen, lo, open, u0, ring, D, yi, maxd_q, bw, bw2, lut_s, sti);
+        else packed_walk<R, MODE_GEN, true>(thr, pen, lo, open, u0, ring, D, yi, maxd_q, bw, bw2, lut_s, sti);
+        // open windows: [open, t0) = FAR [open, min(jA, jB)) | MID [jA, jB) (if jA < jB) | GEN [jB, t0)
+        const int e1 = min(jA, jB);
+        packed_walk<R, MODE_FAR, false>(thr, pen, open, e1, u0, ring, D, yi, maxd_q, bw, bw2, lut_s, sti);
+        packed_walk<R, MODE_MID, false>(thr, pen, jA, jB, u0, ring, D, yi, maxd_q, bw, bw2, lut_s, sti);
+        packed_walk<R, MODE_GEN, false>(thr, pen, jB, t0, u0, ring, D, yi, maxd_q, bw, bw2, lut_s, sti);
         __syncwarp();
-        Rec *tile = ring + ((t0 - u0) & (R - 1));
-        if (act) tile[lane] = make_rec<true>(ai, 0);
+        RecP *tile = ring + ((t0 - u0) & (R - 1));
+        if (act) { RecP r; r.e = xi - yi; r.g = 0; r.y = yi; r.q = qsi; tile[lane] = r; }
         __syncwarp();
 
         // phase B in two halves (s = 0..15, 16..30): the f-independent parts of 16 in-tile candidates are pre-scored into
         // registers, then resolved by the serial chain; halving keeps the live set at 16 values instead of 31.
-        const int nact = min(32, u1 - t0);
         const int slot = i - u0;
-        int fown = (thr & ~kSlotMask) | slot; // this anchor as a predecessor: current score, own slot
+        const int qk = qsi << kSlotBits;
+        int gown = ((thr & ~kSlotMask) | slot) + qk; // this anchor as a predecessor: current score (+ own q_span), own slot
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
@@ -620,22 +797,25 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int s = h * 16 + q;
-                if (s < 31) w[q] = packed_static(pen, xi, yi, tile[s], P.maxd_q, bw, bw2, lut_s, (s < lane && t0 + s >= sti) ? 1 : 0);
+                if (s < 31) {
+                    const int4 r = *reinterpret_cast<const int4 *>(tile + s);
+                    w[q] = packed_static(pen, D, yi, r.x, r.z, r.w, maxd_q, bw, bw2, lut_s, (s < lane && t0 + s >= sti) ? 1 : 0);
+                }
             }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int s = h * 16 + q;
                 if (s < 31) {
-                    const int fs = __shfl_sync(full, fown, s);
-                    thr = max(thr, fs + w[q]);
-                    fown = (thr & ~kSlotMask) | slot;
+                    const int gs = __shfl_sync(full, gown, s);
+                    thr = max(thr, gs + w[q]);
+                    gown = ((thr & ~kSlotMask) | slot) + qk;
                 }
             }
         }
         if (act) {
             f[i] = thr >> kSlotBits;
             p[i] = thr == thr0 ? -1 : u0 + (thr & kSlotMask) - rbase;
-            tile[lane].f = fown;
+            tile[lane].g = gown;
         }
         __syncwarp();
     }
@@ -647,13 +827,12 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
               const int *__restrict__ big_order, int big_cap, Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g,
               int run_mode, int long_min)
 {
+    // the penalty table sits in STATIC shared memory so that its address is a compile-time constant: table loads are
+    // LDS.U8 [tb + const] with no address arithmetic
+    __shared__ __align__(16) unsigned char lut[2 * kLutMax + 16];
     extern __shared__ int4 smem_raw[];
-    unsigned char *lut = reinterpret_cast<unsigned char *>(smem_raw);
-    const int lut_bytes = (P.lut_n + 15) & ~15;
-    Rec *ring = reinterpret_cast<Rec *>(lut + lut_bytes) + (threadIdx.x >> 5) * R;
-    unsigned lut_s = (unsigned)__cvta_generic_to_shared(lut);
-    asm volatile("mov.u32 %0, %0;" : "+r"(lut_s)); // opaque: keeps the table address in a register (ptxas otherwise
-                                                   // rematerialises the shared-window base before every table load)
+    Rec *ring = reinterpret_cast<Rec *>(smem_raw) + (threadIdx.x >> 5) * R;
+    const unsigned lut_s = (unsigned)__cvta_generic_to_shared(lut);
     const int lane = threadIdx.x & 31;
     // run_mode 0: always; 1: only if no read mixes segment ids (FAST is valid); 2: only if some read does
     if (run_mode == 1 && ctr->multi_sid != 0) return;
@@ -683,8 +862,8 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
         if (unit_has_clip(clipmask, u0, u1, lane)) {
             if (lane == 0) atomicAdd(&ctr->n_exact, 1);
             score_unit_exact<FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, lane);
-        } else if (FAST && u1 - u0 <= (1 << kSlotBits) && (u1 - u0) * qs_max < (1 << 18)) {
-            score_unit_packed<R>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
+        } else if (FAST && u1 - u0 <= (1 << kSlotBits) && (u1 - u0 + 1) * qs_max < (1 << 18)) {
+            score_unit_packed<R>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, reinterpret_cast<RecP *>(ring), lane);
         } else {
             score_unit_tiled<R, FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
         }
