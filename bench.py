@@ -192,7 +192,10 @@ def main():
     a, off = make_workload(w, rank)
     n, n_reads = int(off[-1]), len(off) - 1
     misc = pkg.map_ont_misc()
-    ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=max(n, 1 << 20), max_reads=n_reads + 1, n_slots=3)
+    ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=max(n, 1 << 20), max_reads=n_reads + 1, n_slots=1)   # whole batch resident
+    # the end-to-end path streams the batch through 6 slots of one eighth of it each
+    e2e_cap = max(1 << 20, n // 8 + int(np.diff(off).max()) + 1)
+    ctx_e2e = pkg.ChainContext(misc, device=local_rank, max_anchors=e2e_cap, max_reads=n_reads + 1, n_slots=6)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(0), device=local_rank)
 
     # device-resident inputs
@@ -233,27 +236,39 @@ def main():
     prof = ctx.profile_read()
     ctx.profile(False)
 
-    # ---- end to end through the C ABI with pinned host buffers (whole mg_lchain_dp: upload, DP, download, backtracking)
-    out = {"f": torch.empty(n, dtype=torch.int32).pin_memory(), "p": torch.empty(n, dtype=torch.int32).pin_memory(),
-           "u": np.empty(n, np.uint64), "b": np.empty((n, 2), np.uint64), "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
+    # ---- end to end through the C ABI with pinned host buffers: the whole mg_lchain_dp (upload of the anchors, DP kernels,
+    #      chain extraction + compaction on the device, download of chains and compacted anchors)
+    out = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
+           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
     host_threads = max(1, cpu_threads() // max(1, world))
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(2):
-        ctx.chain(h_a, off, n_threads=host_threads, out=out)
+        ctx_e2e.chain(h_a, off, out=out, want_fp=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = ctx.chain(h_a, off, n_threads=host_threads, out=out)
+        res = ctx_e2e.chain(h_a, off, out=out, want_fp=False)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     n_chains = int(res["n_u"].sum())
-    # where the end-to-end time goes: the same call without the host stage, and the host stage alone on resident f/p
+    n_chain_anchors = int(res["n_b"].sum())
+    # where the end-to-end time goes: DP only (upload, kernels, f/p download), the host-stage variant of the same call
+    # (f/p downloaded, chain extraction on host threads -- the reference's arrangement), and that host stage alone
+    outh = {"f": torch.empty(n, dtype=torch.int32).pin_memory(), "p": torch.empty(n, dtype=torch.int32).pin_memory(),
+            "u": out["u"], "b": np.empty((n, 2), np.uint64), "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
+    ctx_e2e.chain_dp(h_a, off, f=outh["f"], p=outh["p"])
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.chain_dp(h_a, off, f=out["f"], p=out["p"])
+        ctx_e2e.chain_dp(h_a, off, f=outh["f"], p=outh["p"])
     dp_only_s = (time.perf_counter() - t0) / e2e_steps
-    host_only_s = host_stage_alone(pkg, misc, a, off, out["f"].numpy(), out["p"].numpy(), host_threads)
+    ctx_e2e.chain(h_a, off, n_threads=host_threads, out=outh)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        resh = ctx_e2e.chain(h_a, off, n_threads=host_threads, out=outh)
+    hostvar_s = (time.perf_counter() - t0) / e2e_steps
+    assert np.array_equal(resh["n_u"], res["n_u"]) and np.array_equal(resh["n_b"], res["n_b"]), "device and host chain extraction disagree"
+    host_only_s = host_stage_alone(pkg, misc, a, off, outh["f"].numpy(), outh["p"].numpy(), host_threads)
 
     # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
     tot = torch.tensor([float(pairs), float(n), float(n_reads)], dtype=torch.float64, device="cuda")
@@ -297,15 +312,20 @@ def main():
                       "units_exact": int(st.n_units_exact), "chains": n_chains},
             "kernel_ms_per_step": {k: v[0] / max(1, v[1]) for k, v in prof.items() if v[1]},
             "roofline": roofline,
-            "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1), "d2h_bytes_per_step": 8 * n,
-                    "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps, "host_threads": host_threads,
-                    "includes": "H2D anchors, range+unit+score kernels, D2H f/p, threaded host backtracking+compaction (= whole mg_lchain_dp)",
-                    "breakdown_ms": {"upload_kernels_download_only": 1e3 * dp_only_s, "host_stage_alone": 1e3 * host_only_s}},
-            "gpu_launches": 5 * args.steps, "clocks": clocks}
+            "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1),
+                    "d2h_bytes_per_step": 16 * n + 8 * (n // 8 + 8 * n_reads) + 12 * n_reads,
+                    "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps,
+                    "includes": "H2D anchors, range+unit+score kernels, device chain extraction + compaction (k_backtrack), D2H chains + compacted anchors (= whole mg_lchain_dp)",
+                    "chain_anchors": n_chain_anchors,
+                    "slots": 6, "chunk_anchors": e2e_cap,
+                    "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
+                                     "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
+            "gpu_launches": 7 * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
     print(json.dumps(line))
     ctx.close()
+    ctx_e2e.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -72,9 +72,15 @@ int mm2gb_ctx_set_misc(mm2gb_ctx_t *ctx, const mm2gb_misc_t *misc);
 int mm2gb_chain_dp_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                         mm2gb_stats_t *stats);
 
-/* The whole mg_lchain_dp (lchain.c:148-217) for a batch: device DP + host stage (backtracking, compaction) on `n_threads`
- * host threads, pipelined chunk by chunk.  Per read r: chains u[off[r] .. off[r]+n_u[r]) (score<<32 | count, ordered by
- * chain start) and compacted anchors b[off[r] .. off[r]+n_b[r]).  f/p (size off[n_reads]) receive the DP arrays. */
+/* The whole mg_lchain_dp (lchain.c:148-217) for a batch, pipelined chunk by chunk through the slots.  Per read r: chains
+ * u[off[r] .. off[r]+n_u[r]) (score<<32 | count, ordered by chain start) and compacted anchors b[off[r] .. off[r]+n_b[r]);
+ * the rest of b[off[r] .. off[r+1]) is scratch.  f/p (size off[n_reads]) receive the DP arrays; they may be NULL when
+ * n_threads <= 0.
+ *   n_threads <= 0 : chain extraction + compaction (lchain.c:27-111) run on the DEVICE right behind the DP kernels and only
+ *                    their result is downloaded (straight into `b` when it is pinned).  Reads the device kernel declines
+ *                    (more than 8192 anchors, scores >= 2^19) are finished by the host implementation.
+ *   n_threads >= 1 : f/p are downloaded and that stage runs on n_threads host threads (what the reference does on one
+ *                    thread, gpu/plchain.cu:99-150). */
 int mm2gb_chain_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                      uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats);
 
@@ -84,6 +90,12 @@ int mm2gb_chain_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *o
 int mm2gb_submit(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *a, const int64_t *off, int n_reads);
 int mm2gb_submit_gather(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads);
 int mm2gb_wait(mm2gb_ctx_t *ctx, int slot, const int32_t **f, const int32_t **p, const int64_t **off, mm2gb_stats_t *stats);
+/* The same pair with chain extraction on the device (what the drop-in uses; replaces the host loop of
+ * gpu/plchain.cu:99-150).  wait_chains: per read r  n_u[r] chains at u[r][0 .. n_u[r]) and n_b[r] compacted anchors at
+ * b[off[r] ..]; everything lives in the slot's pinned memory until the slot is submitted again. */
+int mm2gb_submit_gather_chains(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads);
+int mm2gb_wait_chains(mm2gb_ctx_t *ctx, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t **b,
+                      const int32_t **n_b, const int64_t **off, mm2gb_stats_t *stats);
 int mm2gb_slot_busy(mm2gb_ctx_t *ctx, int slot);
 
 /* ---- device-resident path (kernel-only timing; inputs already in HBM) ---------------------------------- */
@@ -91,6 +103,10 @@ int mm2gb_slot_busy(mm2gb_ctx_t *ctx, int slot);
 /* d_a: device mm2gb_anchor_t[n_total]; d_off: device int64[n_reads+1]; d_f/d_p: device int32[n_total].
  * Enqueues range + unit + score kernels on slot 0's stream; returns without synchronising. */
 int mm2gb_chain_dp_device(mm2gb_ctx_t *ctx, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p);
+/* The same followed by chain extraction + compaction on the device (results stay in the slot's device buffers; used to time
+ * the whole device side of mg_lchain_dp).  `off` = host copy of d_off. */
+int mm2gb_chain_device(mm2gb_ctx_t *ctx, const void *d_a, const void *d_off, const int64_t *off, int n_reads, int64_t n_total,
+                       void *d_f, void *d_p);
 int mm2gb_sync(mm2gb_ctx_t *ctx, int slot);
 /* the cudaStream_t of a slot, as an opaque pointer (so a caller can record its own events on it) */
 void *mm2gb_stream(mm2gb_ctx_t *ctx, int slot);
@@ -98,7 +114,7 @@ void *mm2gb_stream(mm2gb_ctx_t *ctx, int slot);
 int mm2gb_device_stats(mm2gb_ctx_t *ctx, mm2gb_stats_t *stats);
 
 /* Per-kernel device time of slot 0, accumulated with CUDA events while profiling is on.
- * ms[0]=range ms[1]=unit-build ms[2]=score(short/mid) ms[3]=score(long) ms[4]=H2D ms[5]=D2H; launches[] likewise. */
+ * ms[0]=range ms[1]=unit-build ms[2]=score ms[3]=chain extraction (k_backtrack) ms[4]=H2D ms[5]=D2H; launches[] likewise. */
 #define MM2GB_NTIMERS 6
 int mm2gb_profile(mm2gb_ctx_t *ctx, int enable);
 int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launches[MM2GB_NTIMERS]);
@@ -108,6 +124,12 @@ int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launch
  * max_drop = is_cdna ? INT32_MAX : bw (lchain.c:151,162). */
 int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p, const mm2gb_anchor_t *a, int32_t min_cnt, int32_t min_sc,
                         int32_t max_drop, uint64_t *u, mm2gb_anchor_t *b, int64_t *n_b);
+
+/* The device version of that stage (k_backtrack; what mm2gb_chain_host with n_threads <= 0 and the drop-in run behind the DP
+ * kernels) on caller-supplied f / p: same outputs, layout as in mm2gb_chain_host.  *n_declined = reads the kernel handed
+ * to the host implementation (more than 8192 anchors, scores >= 2^19, chain buffer full).  Synchronous; uses slot 0. */
+int mm2gb_backtrack_device(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
+                           const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int32_t *n_declined);
 
 /* The same for a batch on `n_threads` host threads (layout of u/b/n_u/n_b as in mm2gb_chain_host). */
 int mm2gb_backtrack_batch(const mm2gb_misc_t *misc, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,

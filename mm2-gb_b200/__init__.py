@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmm2gb_chain.so")
 INT32_MAX = 2**31 - 1
 N_TIMERS = 6
-TIMER_NAMES = ("range", "units", "score", "score_long", "h2d", "d2h")
+TIMER_NAMES = ("range", "units", "score", "backtrack", "h2d", "d2h")
 
 
 class Mm2gbError(RuntimeError):
@@ -87,8 +87,11 @@ def lib():
         L.mm2gb_submit.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_submit_gather.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_wait.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
+        L.mm2gb_submit_gather_chains.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+        L.mm2gb_wait_chains.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
         L.mm2gb_slot_busy.argtypes = [vp, C.c_int]
         L.mm2gb_chain_dp_device.argtypes = [vp, vp, vp, C.c_int, C.c_int64, vp, vp]
+        L.mm2gb_chain_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
         L.mm2gb_sync.argtypes = [vp, C.c_int]
         L.mm2gb_stream.argtypes = [vp, C.c_int]
         L.mm2gb_stream.restype = vp
@@ -96,6 +99,7 @@ def lib():
         L.mm2gb_profile.argtypes = [vp, C.c_int]
         L.mm2gb_profile_read.argtypes = [vp, C.POINTER(C.c_float), i64p]
         L.mm2gb_backtrack_batch.argtypes = [C.POINTER(Misc), vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
+        L.mm2gb_backtrack_device.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32)]
         L.mm2gb_backtrack.restype = C.c_int32
         L.mm2gb_backtrack.argtypes = [C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, i64p]
         _lib = L
@@ -164,19 +168,21 @@ class ChainContext:
         _ck(lib().mm2gb_chain_dp_host(self._h, _ptr(a), _ptr(off), n_reads, _ptr(f), _ptr(p), C.byref(st)))
         return f, p, st
 
-    def chain(self, a, off, n_threads: int = 0, out=None):
-        """Whole mg_lchain_dp for a batch (device DP + threaded host backtracking).  Returns dict with f, p, u, n_u, b,
+    def chain(self, a, off, n_threads: int = 0, out=None, want_fp: bool = True):
+        """Whole mg_lchain_dp for a batch.  n_threads <= 0: chain extraction + compaction on the device (k_backtrack);
+        n_threads >= 1: that stage on n_threads host threads.  Returns dict with f, p (None unless want_fp), u, n_u, b,
         n_b, stats; read r's chains are u[off[r]:off[r]+n_u[r]], its compacted anchors b[off[r]:off[r]+n_b[r]].
         `out` may carry preallocated (e.g. pinned) buffers under the same keys."""
         n_reads = len(off) - 1
         n = int(off[-1])
         out = dict(out or {})
-        out.setdefault("f", np.empty(n, np.int32)); out.setdefault("p", np.empty(n, np.int32))
+        if want_fp or n_threads >= 1:
+            out.setdefault("f", np.empty(n, np.int32)); out.setdefault("p", np.empty(n, np.int32))
+        else:
+            out["f"] = out["p"] = None
         out.setdefault("u", np.empty(n, np.uint64)); out.setdefault("b", np.empty((n, 2), np.uint64))
         out.setdefault("n_u", np.zeros(n_reads, np.int32)); out.setdefault("n_b", np.zeros(n_reads, np.int64))
         st = Stats()
-        if n_threads <= 0:
-            n_threads = min(32, os.cpu_count() or 1)
         _ck(lib().mm2gb_chain_host(self._h, _ptr(a), _ptr(off), n_reads, _ptr(out["f"]), _ptr(out["p"]), _ptr(out["u"]),
                                    _ptr(out["n_u"]), _ptr(out["b"]), _ptr(out["n_b"]), n_threads, C.byref(st)))
         out["stats"] = st
@@ -194,10 +200,26 @@ class ChainContext:
         pa = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), (n,)) if n else np.zeros(0, np.int32)
         return fa, pa, st
 
+    def backtrack_device(self, a, off, f, p):
+        """Chain extraction + compaction on the device for given f / p.  Returns (u, n_u, b, n_b, n_declined) in the layout
+        of chain()."""
+        a = np.ascontiguousarray(a, np.uint64); off = np.ascontiguousarray(off, np.int64)
+        f = np.ascontiguousarray(f, np.int32); p = np.ascontiguousarray(p, np.int32)
+        n_reads, n = len(off) - 1, int(off[-1])
+        u = np.zeros(max(n, 1), np.uint64); b = np.zeros((max(n, 1), 2), np.uint64)
+        n_u = np.zeros(max(n_reads, 1), np.int32); n_b = np.zeros(max(n_reads, 1), np.int64)
+        nd = C.c_int32(0)
+        _ck(lib().mm2gb_backtrack_device(self._h, _ptr(a), _ptr(off), n_reads, _ptr(f), _ptr(p), _ptr(u), _ptr(n_u), _ptr(b), _ptr(n_b), C.byref(nd)))
+        return u, n_u[:n_reads], b, n_b[:n_reads], nd.value
+
     # ---- device-resident path ------------------------------------------------------------------------------
     def chain_dp_device(self, d_a, d_off, n_reads: int, n_total: int, d_f, d_p):
         """Enqueue the kernels on slot 0's stream; all arguments are device tensors/pointers.  Asynchronous."""
         _ck(lib().mm2gb_chain_dp_device(self._h, _ptr(d_a), _ptr(d_off), n_reads, n_total, _ptr(d_f), _ptr(d_p)))
+
+    def chain_device(self, d_a, d_off, off, n_reads: int, n_total: int, d_f, d_p):
+        """chain_dp_device + chain extraction on the device (off = host copy of the offsets).  Asynchronous."""
+        _ck(lib().mm2gb_chain_device(self._h, _ptr(d_a), _ptr(d_off), _ptr(off), n_reads, n_total, _ptr(d_f), _ptr(d_p)))
 
     def sync(self, slot: int = 0):
         _ck(lib().mm2gb_sync(self._h, slot))

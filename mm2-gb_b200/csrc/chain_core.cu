@@ -8,6 +8,7 @@
 //   * one flat batch, no micro-batches, no host sync between "short" and "long" phases (plchain.cu:426-452 is gone);
 //   * n_slots independent slots per context so upload, kernels and download of consecutive batches overlap.
 #include "chain_kernels.cuh"
+#include "backtrack_kernels.cuh"
 #include "../../include/mm2gb_chain.h"
 
 #include <algorithm>
@@ -52,7 +53,7 @@ extern "C" int mm2gb_device_count(void)
 
 namespace {
 
-enum { T_RANGE = 0, T_UNITS, T_SCORE, T_LONG, T_H2D, T_D2H };
+enum { T_RANGE = 0, T_UNITS, T_SCORE, T_BACKTRACK, T_H2D, T_D2H };
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -65,11 +66,23 @@ struct Slot {
     int *d_block_cnt = nullptr, *d_block_base = nullptr; unsigned long long *d_block_pairs = nullptr; int *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
     int big_cap = 0;
     Counters *d_ctr = nullptr;
+    // device chain extraction (k_backtrack): compacted anchors (+ chains in the tail of every read's region), scratch, lists
+    uint4 *d_b = nullptr;
+    unsigned long long *d_uscr = nullptr;
+    int *d_vs = nullptr, *d_nu = nullptr, *d_nb = nullptr, *d_list = nullptr, *d_upos = nullptr, *d_ucur = nullptr;
+    unsigned long long *d_upack = nullptr;
+    size_t u_cap = 0;      // entries of d_upack / h_upack
+    cudaStream_t bt_stream[7] = {nullptr};   // the size classes of k_backtrack run side by side (each is a partial wave)
+    cudaEvent_t bt_fork = nullptr, bt_join[7] = {nullptr};
+    int u_cap_batch = 0;   // entries a batch may use (= what is downloaded)
     // pinned host
     mm2gb_anchor_t *h_a = nullptr;
     long long *h_off = nullptr;
     int *h_f = nullptr, *h_p = nullptr;
     Counters *h_ctr = nullptr;
+    mm2gb_anchor_t *h_b = nullptr;
+    int *h_nu = nullptr, *h_nb = nullptr, *h_list = nullptr, *h_upos = nullptr;
+    unsigned long long *h_upack = nullptr;
     // state
     bool busy = false;
     int n_reads = 0;
@@ -77,9 +90,17 @@ struct Slot {
     // where results of a synchronous chunk go (mm2gb_chain_dp_host)
     int *user_f = nullptr, *user_p = nullptr;
     bool direct_out = false;
+    // chains requested for this batch (device backtracking); where the compacted anchors land
+    bool chains = false, want_fp = true, direct_b = false;
+    mm2gb_anchor_t *user_b = nullptr;
+    const mm2gb_anchor_t *src_a = nullptr;   // host anchors of the batch (for reads the device declines)
+    std::vector<const uint64_t *> u_ptr;     // per read: its chains (in h_upack, or in `spill` for reads finished on the host)
+    std::vector<std::vector<uint64_t>> spill;
 };
 
 } // namespace
+
+constexpr int kMaxSlots = 8;
 
 struct mm2gb_ctx {
     int device = 0, n_sm = 0;
@@ -93,7 +114,7 @@ struct mm2gb_ctx {
     int score_blocks = 0;
     size_t score_smem = 0;
     int long_min = INT32_MAX;
-    Slot slot[4];
+    Slot slot[kMaxSlots];
     // profiling (slot 0 only)
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -262,6 +283,82 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
     return MM2GB_OK;
 }
 
+
+// ---- device chain extraction ------------------------------------------------------------------------------------------
+
+#define MM2GB_BT_CLASSES(X) X(1024) X(1536) X(2048) X(3072) X(4096) X(6144) X(8192)
+
+static int config_backtrack()
+{
+#define X(CAP) CK(cudaFuncSetAttribute(k_backtrack<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtSmem<CAP>)));
+    MM2GB_BT_CLASSES(X)
+#undef X
+    return MM2GB_OK;
+}
+
+template <int CAP>
+static void launch_backtrack(cudaStream_t s, const uint4 *d_a, const int *d_f, const int *d_p, const long long *d_off, const int *list, int n_list,
+                             const BtParams &bp, Slot &sl)
+{
+    if (n_list <= 0) return;
+    k_backtrack<CAP><<<n_list, 32, sizeof(BtSmem<CAP>), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_st /* dead after scoring: v scratch */,
+                                                             sl.d_uscr, sl.d_vs, sl.d_b, sl.d_nu, sl.d_nb, sl.d_upack, sl.u_cap_batch,
+                                                             sl.d_ucur, sl.d_upos);
+}
+
+// Reads are binned by anchor count into the shared-memory classes of k_backtrack (off_rel is the host copy of the
+// offsets); reads above kBtMaxAnchors keep n_u = -1 and are finished by the host implementation.
+static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *d_a, const long long *d_off, const long long *off_rel,
+                             int n_reads, const int *d_f, const int *d_p, bool prof)
+{
+    static const int caps[7] = {1024, 1536, 2048, 3072, 4096, 6144, 8192};
+    int cnt[7] = {0, 0, 0, 0, 0, 0, 0}, base[8], fill[7];
+    for (int r = 0; r < n_reads; ++r) {
+        const long long n = off_rel[r + 1] - off_rel[r];
+        for (int k = 0; k < 7; ++k) if (n <= caps[k]) { ++cnt[k]; break; }
+    }
+    base[0] = 0;
+    for (int k = 0; k < 7; ++k) { base[k + 1] = base[k] + cnt[k]; fill[k] = base[k]; }
+    for (int r = 0; r < n_reads; ++r) {
+        const long long n = off_rel[r + 1] - off_rel[r];
+        for (int k = 0; k < 7; ++k) if (n <= caps[k]) { sl.h_list[fill[k]++] = r; break; }
+    }
+    CK(cudaMemsetAsync(sl.d_nu, 0xff, ((size_t)n_reads + 1) * sizeof(int), s));   // -1 = not done by the device
+    CK(cudaMemsetAsync(sl.d_nb, 0, ((size_t)n_reads + 1) * sizeof(int), s));
+    CK(cudaMemsetAsync(sl.d_ucur, 0, sizeof(int), s));
+    // chains of the whole batch are packed into one array; a batch may use (and the host downloads) this many entries
+    sl.u_cap_batch = (int)std::min<size_t>(sl.u_cap, (size_t)(off_rel[n_reads] / 8) + (size_t)8 * n_reads + 64);
+    if (base[7]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[7] * sizeof(int), cudaMemcpyHostToDevice, s));
+    BtParams bp;
+    bp.min_cnt = c->misc.min_cnt;
+    bp.min_sc = c->misc.min_score;
+    bp.max_drop = c->misc.is_cdna ? INT32_MAX : c->misc.bw;   // lchain.c:151,162
+    {
+        // fork: one auxiliary stream per non-empty size class, joined back into the slot's stream
+        ProfScope ps(c, T_BACKTRACK, s, prof);
+        CK(cudaEventRecord(sl.bt_fork, s));
+        for (int k = 6; k >= 0; --k) { // longest first
+            if (!cnt[k]) continue;
+            cudaStream_t bs = sl.bt_stream[k];
+            CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
+            const int *list = sl.d_list + base[k];
+            switch (k) {
+            case 6: launch_backtrack<8192>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            case 5: launch_backtrack<6144>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            case 4: launch_backtrack<4096>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            case 3: launch_backtrack<3072>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            case 2: launch_backtrack<2048>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            case 1: launch_backtrack<1536>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            default: launch_backtrack<1024>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
+            }
+            CK(cudaEventRecord(sl.bt_join[k], bs));
+            CK(cudaStreamWaitEvent(s, sl.bt_join[k], 0));
+        }
+    }
+    CK(cudaGetLastError());
+    return MM2GB_OK;
+}
+
 static void fill_stats(const mm2gb_ctx *c, const Counters &k, long long n_total, mm2gb_stats_t *st)
 {
     if (!st) return;
@@ -279,8 +376,12 @@ static void free_slot(Slot &s)
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
     cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
     cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
+    cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_nu); cudaFree(s.d_nb); cudaFree(s.d_list); cudaFree(s.d_upos); cudaFree(s.d_ucur); cudaFree(s.d_upack);
     cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
+    cudaFreeHost(s.h_b); cudaFreeHost(s.h_nu); cudaFreeHost(s.h_nb); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upos); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.bt_fork) cudaEventDestroy(s.bt_fork);
+    for (int k = 0; k < 7; ++k) { if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]); if (s.bt_stream[k]) cudaStreamDestroy(s.bt_stream[k]); }
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -291,7 +392,7 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
 {
     if (!out || !misc) return fail(MM2GB_EARG, "null argument");
     *out = nullptr;
-    if (n_slots < 1 || n_slots > 4) return fail(MM2GB_EARG, "n_slots must be 1..4");
+    if (n_slots < 1 || n_slots > kMaxSlots) return fail(MM2GB_EARG, "n_slots must be 1..%d", kMaxSlots);
     if (max_anchors == 0 || max_anchors > (size_t)INT32_MAX - 1024) return fail(MM2GB_EARG, "max_anchors must be in (0, 2^31)");
     if (max_reads < 1) return fail(MM2GB_EARG, "max_reads must be positive");
     int ndev = 0;
@@ -325,12 +426,19 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
         if (rc) goto bad;
         rc = c->ring == 256 ? config_ring<256>(c) : c->ring == 1024 ? config_ring<1024>(c) : config_ring<512>(c);
         if (rc) goto bad;
+        rc = config_backtrack();
+        if (rc) goto bad;
         const size_t n = max_anchors, n_groups = (n + 31) / 32, n_blocks = (n + kRangeThreads - 1) / kRangeThreads;
         const size_t n_units_cap = n_groups + (size_t)max_reads + 2;
         for (int i = 0; i < n_slots; ++i) {
             Slot &s = c->slot[i];
             CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&s.bt_fork, cudaEventDisableTiming));
+            for (int k = 0; k < 7; ++k) {
+                CKC(cudaStreamCreateWithFlags(&s.bt_stream[k], cudaStreamNonBlocking));
+                CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
+            }
             CKC(cudaMalloc(&s.d_a, n * sizeof(uint4)));
             CKC(cudaMalloc(&s.d_off, ((size_t)max_reads + 1) * sizeof(long long)));
             CKC(cudaMalloc(&s.d_st, n * sizeof(int)));
@@ -351,6 +459,22 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaMallocHost(&s.h_f, n * sizeof(int)));
             CKC(cudaMallocHost(&s.h_p, n * sizeof(int)));
             CKC(cudaMallocHost(&s.h_ctr, sizeof(Counters)));
+            CKC(cudaMalloc(&s.d_b, n * sizeof(uint4)));
+            CKC(cudaMalloc(&s.d_uscr, n * sizeof(unsigned long long)));
+            CKC(cudaMalloc(&s.d_vs, n * sizeof(int)));
+            CKC(cudaMalloc(&s.d_nu, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_nb, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_list, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMallocHost(&s.h_b, n * sizeof(mm2gb_anchor_t)));
+            CKC(cudaMallocHost(&s.h_nu, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMallocHost(&s.h_nb, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMallocHost(&s.h_list, ((size_t)max_reads + 1) * sizeof(int)));
+            s.u_cap = n / 8 + (size_t)8 * max_reads + 64;
+            CKC(cudaMalloc(&s.d_upack, s.u_cap * sizeof(unsigned long long)));
+            CKC(cudaMalloc(&s.d_upos, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_ucur, sizeof(int)));
+            CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
+            CKC(cudaMallocHost(&s.h_upos, ((size_t)max_reads + 1) * sizeof(int)));
         }
     }
     *out = c;
@@ -365,7 +489,7 @@ extern "C" void mm2gb_ctx_destroy(mm2gb_ctx_t *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 4; ++i) free_slot(c->slot[i]);
+    for (int i = 0; i < kMaxSlots; ++i) free_slot(c->slot[i]);
     prof_collect(c);
     cudaFree(c->d_lut);
     delete c;
@@ -388,9 +512,19 @@ static bool is_pinned(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
+// what a batch should produce
+struct Want {
+    bool fp = true;                 // download f / p
+    int *dst_f = nullptr, *dst_p = nullptr;
+    bool dst_pinned = false;
+    bool chains = false;            // run chain extraction + compaction on the device and download the result
+    mm2gb_anchor_t *dst_b = nullptr;
+    bool dst_b_pinned = false;
+};
+
 // enqueue one batch whose anchors already sit in host memory `src` (pinned: direct DMA; else staged through h_a)
 static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src_pinned, const long long *off_rel, int n_reads,
-                       long long n_total, int *dst_f, int *dst_p, bool dst_pinned)
+                       long long n_total, const Want &w)
 {
     Slot &s = c->slot[si];
     if (s.busy) return fail(MM2GB_ESTATE, "slot %d is busy", si);
@@ -408,13 +542,29 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
     }
     int rc = enqueue_kernels(c, s, s.stream, s.d_a, s.d_off, n_reads, n_total, s.d_f, s.d_p, prof);
     if (rc) return rc;
-    s.direct_out = dst_pinned && dst_f && dst_p;
-    s.user_f = dst_f; s.user_p = dst_p;
+    s.chains = w.chains;
+    s.want_fp = w.fp;
+    s.src_a = h_src;
+    if (w.chains && n_total) {
+        rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, s.h_off, n_reads, s.d_f, s.d_p, prof);
+        if (rc) return rc;
+    }
+    s.direct_out = w.fp && w.dst_pinned && w.dst_f && w.dst_p;
+    s.user_f = w.dst_f; s.user_p = w.dst_p;
+    s.direct_b = w.chains && w.dst_b_pinned && w.dst_b;
+    s.user_b = w.dst_b;
     {
         ProfScope ps(c, T_D2H, s.stream, prof);
-        if (n_total) {
-            CK(cudaMemcpyAsync(s.direct_out ? dst_f : s.h_f, s.d_f, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(s.direct_out ? dst_p : s.h_p, s.d_p, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        if (n_total && w.fp) {
+            CK(cudaMemcpyAsync(s.direct_out ? w.dst_f : s.h_f, s.d_f, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(s.direct_out ? w.dst_p : s.h_p, s.d_p, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (n_total && w.chains) {
+            CK(cudaMemcpyAsync(s.h_nu, s.d_nu, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(s.h_nb, s.d_nb, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(s.h_upos, s.d_upos, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(s.h_upack, s.d_upack, (size_t)s.u_cap_batch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(s.direct_b ? w.dst_b : s.h_b, s.d_b, (size_t)n_total * sizeof(uint4), cudaMemcpyDeviceToHost, s.stream));
         }
         CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
     }
@@ -432,10 +582,22 @@ static int wait_impl(mm2gb_ctx *c, int si)
     CK(cudaEventSynchronize(s.done));
     s.busy = false;
     if (c->profile && si == 0) prof_collect(c);
-    if (!s.direct_out && s.user_f && s.user_p && s.n_total) {
+    if (s.want_fp && !s.direct_out && s.user_f && s.user_p && s.n_total) {
         memcpy(s.user_f, s.h_f, (size_t)s.n_total * sizeof(int));
         memcpy(s.user_p, s.h_p, (size_t)s.n_total * sizeof(int));
     }
+    return MM2GB_OK;
+}
+
+// f / p of one read of a finished batch, fetched on demand (reads the device declined to backtrack)
+static int fetch_fp(mm2gb_ctx *c, Slot &s, int r, int32_t *f, int32_t *p)
+{
+    const long long o = s.h_off[r], n = s.h_off[r + 1] - o;
+    if (n <= 0) return MM2GB_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(f, s.d_f + o, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(p, s.d_p + o, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
     return MM2GB_OK;
 }
 
@@ -443,10 +605,10 @@ extern "C" int mm2gb_submit(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_t *a, c
 {
     if (!c || slot < 0 || slot >= c->n_slots || n_reads < 0 || !off) return fail(MM2GB_EARG, "bad argument");
     if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
-    return submit_impl(c, slot, a, is_pinned(a), (const long long *)off, n_reads, off[n_reads], nullptr, nullptr, false);
+    return submit_impl(c, slot, a, is_pinned(a), (const long long *)off, n_reads, off[n_reads], Want());
 }
 
-extern "C" int mm2gb_submit_gather(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads)
+static int gather_impl(mm2gb_ctx *c, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads, const Want &w)
 {
     if (!c || slot < 0 || slot >= c->n_slots || n_reads < 0) return fail(MM2GB_EARG, "bad argument");
     Slot &s = c->slot[slot];
@@ -459,17 +621,84 @@ extern "C" int mm2gb_submit_gather(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_
     if ((size_t)tot > c->max_anchors) return fail(MM2GB_ECAP, "batch of %lld anchors exceeds capacity %zu", tot, c->max_anchors);
     for (int r = 0; r < n_reads; ++r)
         if (read_n[r] > 0) memcpy(s.h_a + off[(size_t)r], read_a[r], (size_t)read_n[r] * sizeof(mm2gb_anchor_t));
-    return submit_impl(c, slot, s.h_a, true, off.data(), n_reads, tot, nullptr, nullptr, false);
+    return submit_impl(c, slot, s.h_a, true, off.data(), n_reads, tot, w);
+}
+
+extern "C" int mm2gb_submit_gather(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads)
+{
+    return gather_impl(c, slot, read_a, read_n, n_reads, Want());
+}
+
+extern "C" int mm2gb_submit_gather_chains(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads)
+{
+    Want w;
+    w.fp = false;
+    w.chains = true;
+    return gather_impl(c, slot, read_a, read_n, n_reads, w);
 }
 
 extern "C" int mm2gb_wait(mm2gb_ctx_t *c, int slot, const int32_t **f, const int32_t **p, const int64_t **off, mm2gb_stats_t *stats)
 {
     if (!c || slot < 0 || slot >= c->n_slots) return fail(MM2GB_EARG, "bad argument");
+    if (c->slot[slot].busy && !c->slot[slot].want_fp) return fail(MM2GB_ESTATE, "slot %d was submitted for chains: use mm2gb_wait_chains", slot);
     int rc = wait_impl(c, slot);
     if (rc) return rc;
     Slot &s = c->slot[slot];
     if (f) *f = s.h_f;
     if (p) *p = s.h_p;
+    if (off) *off = (const int64_t *)s.h_off;
+    fill_stats(c, *s.h_ctr, s.n_total, stats);
+    return MM2GB_OK;
+}
+
+// Chains of a finished batch: device results are used as they are; reads the device declined (n_u = -1: more than 8192
+// anchors, scores that do not pack) are finished here with the host implementation, f/p fetched on demand.
+// After the call  s.h_nu / s.h_nb  hold the counts,  `b` (the slot's or the caller's buffer) the compacted anchors at the read
+// offsets and  s.u_ptr[r]  points at the read's chains (in the packed download, or in `spill` for host-finished reads).
+static int finish_chains(mm2gb_ctx *c, Slot &s, mm2gb_anchor_t *b)
+{
+    const int n_reads = s.n_reads;
+    s.u_ptr.assign((size_t)n_reads, nullptr);
+    s.spill.clear();
+    if (!s.n_total) { for (int r = 0; r < n_reads; ++r) s.h_nu[r] = s.h_nb[r] = 0; return MM2GB_OK; }
+    const int32_t max_drop = c->misc.is_cdna ? INT32_MAX : c->misc.bw;
+    std::vector<int32_t> f, p;
+    std::vector<uint64_t> u;
+    std::vector<mm2gb_anchor_t> bb;
+    for (int r = 0; r < n_reads; ++r) {
+        const long long o = s.h_off[r], n = s.h_off[r + 1] - o;
+        if (s.h_nu[r] >= 0) {
+            s.u_ptr[(size_t)r] = reinterpret_cast<const uint64_t *>(s.h_upack) + s.h_upos[r];
+            continue;
+        }
+        f.resize((size_t)n); p.resize((size_t)n); u.resize((size_t)n); bb.resize((size_t)n);
+        int rc = fetch_fp(c, s, r, f.data(), p.data());
+        if (rc) return rc;
+        int64_t nb = 0;
+        const int32_t nu = mm2gb_backtrack(n, f.data(), p.data(), s.src_a + o, c->misc.min_cnt, c->misc.min_score, max_drop, u.data(), bb.data(), &nb);
+        s.h_nu[r] = nu;
+        s.h_nb[r] = (int)nb;
+        memcpy(b + o, bb.data(), (size_t)nb * sizeof(mm2gb_anchor_t));
+        s.spill.emplace_back(u.begin(), u.begin() + nu);
+        s.u_ptr[(size_t)r] = s.spill.back().data();
+    }
+    return MM2GB_OK;
+}
+
+extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t **b,
+                                 const int32_t **n_b, const int64_t **off, mm2gb_stats_t *stats)
+{
+    if (!c || slot < 0 || slot >= c->n_slots) return fail(MM2GB_EARG, "bad argument");
+    if (c->slot[slot].busy && !c->slot[slot].chains) return fail(MM2GB_ESTATE, "slot %d was not submitted for chains", slot);
+    int rc = wait_impl(c, slot);
+    if (rc) return rc;
+    Slot &s = c->slot[slot];
+    rc = finish_chains(c, s, s.h_b);
+    if (rc) return rc;
+    if (u) *u = s.u_ptr.data();
+    if (n_u) *n_u = s.h_nu;
+    if (b) *b = s.h_b;
+    if (n_b) *n_b = s.h_nb;
     if (off) *off = (const int64_t *)s.h_off;
     fill_stats(c, *s.h_ctr, s.n_total, stats);
     return MM2GB_OK;
@@ -482,22 +711,28 @@ extern "C" int mm2gb_slot_busy(mm2gb_ctx_t *c, int slot)
 }
 
 // Shared driver of the host-buffer entry points: split the reads into chunks, run them round-robin through the slots
-// (upload / kernels / download of consecutive chunks overlap) and call on_done(r0, r1) as each chunk's f/p land.
+// (upload / kernels / download of consecutive chunks overlap) and call on_done(slot, r0, r1) as each chunk's results land.
 template <class Done>
-static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
-                       mm2gb_stats_t *stats, Done on_done)
+static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p, mm2gb_anchor_t *b,
+                       bool chains, mm2gb_stats_t *stats, Done on_done)
 {
     for (int i = 0; i < c->n_slots; ++i)
         if (c->slot[i].busy) return fail(MM2GB_ESTATE, "slot %d is busy", i);
-    const bool in_pinned = a && is_pinned(a), out_pinned = is_pinned(f) && is_pinned(p);
+    const bool in_pinned = a && is_pinned(a);
+    Want w;
+    w.fp = f && p;
+    w.dst_pinned = w.fp && is_pinned(f) && is_pinned(p);
+    w.chains = chains;
+    w.dst_b_pinned = chains && b && is_pinned(b);
     const long long total = off[n_reads] - off[0];
-    long long target = std::max<long long>(1 << 20, total / (4LL * c->n_slots) + 1);
+    // chunks: enough of them to overlap upload / kernels / download, few enough that a chunk still fills the GPU
+    long long target = std::max<long long>(1 << 20, total / std::max(8, c->n_slots + 2) + 1);
     target = std::min<long long>(target, (long long)c->max_anchors);
     if (const char *e = getenv("MM2GB_CHUNK")) target = std::min<long long>(std::max(1LL, atoll(e)), (long long)c->max_anchors);
     mm2gb_stats_t acc;
     memset(&acc, 0, sizeof(acc));
     std::vector<long long> rel;
-    int slot_r0[4] = {0, 0, 0, 0}, slot_r1[4] = {0, 0, 0, 0};
+    int slot_r0[kMaxSlots] = {0}, slot_r1[kMaxSlots] = {0};
     int r0 = 0, chunk = 0, rc = MM2GB_OK;
     auto reap = [&](int si) -> int {
         int rc2 = wait_impl(c, si);
@@ -506,8 +741,7 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
         fill_stats(c, *c->slot[si].h_ctr, c->slot[si].n_total, &st);
         acc.n_anchors += st.n_anchors; acc.n_pairs += st.n_pairs; acc.n_units += st.n_units;
         acc.n_units_exact += st.n_units_exact; acc.n_long += st.n_long; acc.general_path |= st.general_path;
-        on_done(slot_r0[si], slot_r1[si]);
-        return MM2GB_OK;
+        return on_done(si, slot_r0[si], slot_r1[si]);
     };
     while (r0 < n_reads) {
         int r1 = r0;
@@ -522,7 +756,10 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
         if (c->slot[si].busy && (rc = reap(si))) return rc;
         rel.resize((size_t)(r1 - r0) + 1);
         for (int r = r0; r <= r1; ++r) rel[(size_t)(r - r0)] = off[r] - off[r0];
-        rc = submit_impl(c, si, a + off[r0], in_pinned, rel.data(), r1 - r0, cnt, f + off[r0], p + off[r0], out_pinned);
+        w.dst_f = w.fp ? f + off[r0] : nullptr;
+        w.dst_p = w.fp ? p + off[r0] : nullptr;
+        w.dst_b = b ? b + off[r0] : nullptr;
+        rc = submit_impl(c, si, a + off[r0], in_pinned, rel.data(), r1 - r0, cnt, w);
         if (rc) return rc;
         slot_r0[si] = r0; slot_r1[si] = r1;
         r0 = r1; ++chunk;
@@ -543,21 +780,15 @@ extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, cons
     if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
     if (stats) memset(stats, 0, sizeof(*stats));
     if (n_reads == 0) return MM2GB_OK;
-    return run_chunked(c, a, off, n_reads, f, p, stats, [](int, int) {});
+    return run_chunked(c, a, off, n_reads, f, p, nullptr, false, stats, [](int, int, int) { return MM2GB_OK; });
 }
 
-// Whole mg_lchain_dp (lchain.c:148-217) for a batch: device DP, then the host stage (backtracking + compaction) on
-// `n_threads` worker threads that start on a chunk's reads as soon as its f/p have landed, while later chunks are
+// Whole mg_lchain_dp (lchain.c:148-217) for a batch, host-stage variant: device DP, then backtracking + compaction on
+// `n_threads` host worker threads that start on a chunk's reads as soon as its f/p have landed, while later chunks are
 // still on the GPU.  Outputs per read r: u[off[r] .. off[r]+n_u[r]), b[off[r] .. off[r]+n_b[r]).
-extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+static int chain_host_hoststage(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                                 uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats)
 {
-    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || !n_u || !n_b) return fail(MM2GB_EARG, "bad argument");
-    if (off[n_reads] > 0 && (!f || !p || !u || !b)) return fail(MM2GB_EARG, "bad argument");
-    if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
-    if (stats) memset(stats, 0, sizeof(*stats));
-    if (n_reads == 0) return MM2GB_OK;
-    if (n_threads < 1) n_threads = 1;
     const mm2gb_misc_t m = c->misc;
     const int32_t max_drop = m.is_cdna ? INT32_MAX : m.bw; // lchain.c:151,162
     std::mutex mu;
@@ -582,9 +813,10 @@ extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
                 n_b[r] = nb;
             }
         });
-    int rc = run_chunked(c, a, off, n_reads, f, p, stats, [&](int, int r1) {
+    int rc = run_chunked(c, a, off, n_reads, f, p, nullptr, false, stats, [&](int, int, int r1) {
         { std::lock_guard<std::mutex> lk(mu); ready = r1; }
         cv.notify_all();
+        return MM2GB_OK;
     });
     {
         std::lock_guard<std::mutex> lk(mu);
@@ -593,6 +825,45 @@ extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
     cv.notify_all();
     for (auto &t : pool) t.join();
     return rc;
+}
+
+// Device variant (default): chain extraction + compaction run on the GPU right behind the DP kernels (k_backtrack); the
+// compacted anchors are downloaded straight into `b` (when it is pinned) and only the reads the device declines take the
+// host implementation.  f / p are downloaded only if the caller passes buffers for them.
+static int chain_host_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                             uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, mm2gb_stats_t *stats)
+{
+    return run_chunked(c, a, off, n_reads, f, p, b, true, stats, [&](int si, int r0, int r1) {
+        Slot &s = c->slot[si];
+        mm2gb_anchor_t *dst = b + off[r0];
+        mm2gb_anchor_t *land = s.direct_b ? dst : s.h_b;     // where the device results of this chunk are
+        int rc = finish_chains(c, s, land);
+        if (rc) return rc;
+        for (int r = r0; r < r1; ++r) {
+            const int k = r - r0;
+            const int64_t o = off[r] - off[r0];
+            n_u[r] = s.h_nu[k];
+            n_b[r] = s.h_nb[k];
+            if (s.h_nu[k] > 0) memcpy(u + off[r], s.u_ptr[(size_t)k], (size_t)s.h_nu[k] * sizeof(uint64_t));
+            if (!s.direct_b && s.h_nb[k] > 0) memcpy(dst + o, s.h_b + o, (size_t)s.h_nb[k] * sizeof(mm2gb_anchor_t));
+        }
+        return MM2GB_OK;
+    });
+}
+
+extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
+                                uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats)
+{
+    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || !n_u || !n_b) return fail(MM2GB_EARG, "bad argument");
+    if (off[n_reads] > 0 && (!u || !b)) return fail(MM2GB_EARG, "bad argument");
+    if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_reads == 0) return MM2GB_OK;
+    if (n_threads >= 1) { // host-stage variant needs f / p
+        if (off[n_reads] > 0 && (!f || !p)) return fail(MM2GB_EARG, "the host-stage variant needs f and p buffers");
+        return chain_host_hoststage(c, a, off, n_reads, f, p, u, n_u, b, n_b, n_threads, stats);
+    }
+    return chain_host_device(c, a, off, n_reads, f, p, u, n_u, b, n_b, stats);
 }
 
 // The host stage alone for a batch whose f/p are already in host memory (what mm2gb_chain_host runs behind the device).
@@ -621,6 +892,54 @@ extern "C" int mm2gb_backtrack_batch(const mm2gb_misc_t *m, const mm2gb_anchor_t
     return MM2GB_OK;
 }
 
+// Chain extraction + compaction on the device for caller-supplied f / p (same kernel mm2gb_chain_host runs behind the DP):
+// lets the stage be checked on arbitrary score / predecessor arrays.  Synchronous, uses slot 0.
+extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
+                                      const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int32_t *n_declined)
+{
+    if (!c || !off || n_reads < 0 || !n_u || !n_b) return fail(MM2GB_EARG, "bad argument");
+    if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
+    const long long n_total = off[n_reads];
+    if (n_total > 0 && (!a || !f || !p || !u || !b)) return fail(MM2GB_EARG, "bad argument");
+    if ((size_t)n_total > c->max_anchors) return fail(MM2GB_ECAP, "batch of %lld anchors exceeds capacity %zu", n_total, c->max_anchors);
+    if (n_reads > c->max_reads) return fail(MM2GB_ECAP, "batch of %d reads exceeds capacity %d", n_reads, c->max_reads);
+    Slot &s = c->slot[0];
+    if (s.busy) return fail(MM2GB_ESTATE, "slot 0 is busy");
+    CK(cudaSetDevice(c->device));
+    if (n_declined) *n_declined = 0;
+    memcpy(s.h_off, off, ((size_t)n_reads + 1) * sizeof(long long));
+    s.n_reads = n_reads;
+    s.n_total = n_total;
+    s.src_a = s.h_a;
+    if (n_total) {
+        memcpy(s.h_a, a, (size_t)n_total * sizeof(mm2gb_anchor_t));
+        memcpy(s.h_f, f, (size_t)n_total * sizeof(int));
+        memcpy(s.h_p, p, (size_t)n_total * sizeof(int));
+        CK(cudaMemcpyAsync(s.d_off, s.h_off, ((size_t)n_reads + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_a, s.h_a, (size_t)n_total * sizeof(uint4), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_f, s.h_f, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_p, s.h_p, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        int rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, s.h_off, n_reads, s.d_f, s.d_p, false);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.h_nu, s.d_nu, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_nb, s.d_nb, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_upos, s.d_upos, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_upack, s.d_upack, (size_t)s.u_cap_batch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_b, s.d_b, (size_t)n_total * sizeof(uint4), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        if (n_declined) for (int r = 0; r < n_reads; ++r) *n_declined += s.h_nu[r] < 0 ? 1 : 0;
+    }
+    int rc = finish_chains(c, s, s.h_b);
+    if (rc) return rc;
+    for (int r = 0; r < n_reads; ++r) {
+        n_u[r] = s.h_nu[r];
+        n_b[r] = s.h_nb[r];
+        if (s.h_nu[r] > 0) memcpy(u + off[r], s.u_ptr[(size_t)r], (size_t)s.h_nu[r] * sizeof(uint64_t));
+        if (s.h_nb[r] > 0) memcpy(b + off[r], s.h_b + off[r], (size_t)s.h_nb[r] * sizeof(mm2gb_anchor_t));
+    }
+    return MM2GB_OK;
+}
+
 extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p)
 {
     if (!c || n_reads < 0 || n_total < 0 || !d_off) return fail(MM2GB_EARG, "bad argument");
@@ -633,6 +952,19 @@ extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void
     CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
     s.n_total = n_total;
     return MM2GB_OK;
+}
+
+// device-resident DP + chain extraction: as mm2gb_chain_dp_device, then k_backtrack into slot 0's output buffers
+// (`off` = host copy of the offsets, needed to bin the reads by size)
+extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, const int64_t *off, int n_reads, int64_t n_total,
+                                  void *d_f, void *d_p)
+{
+    if (!off) return fail(MM2GB_EARG, "bad argument");
+    int rc = mm2gb_chain_dp_device(c, d_a, d_off, n_reads, n_total, d_f, d_p);
+    if (rc || n_total == 0) return rc;
+    Slot &s = c->slot[0];
+    return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, (const long long *)off, n_reads, (const int *)d_f,
+                             (const int *)d_p, c->profile);
 }
 
 extern "C" int mm2gb_sync(mm2gb_ctx_t *c, int slot)

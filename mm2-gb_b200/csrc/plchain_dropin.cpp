@@ -14,8 +14,9 @@
 //   * anchors are gathered straight from chain_read_t.a into pinned memory -- no AoS->SoA repack (plmem.cu:154-198);
 //   * no read is ever handed back for CPU chaining (plchain.cu:421-423): oversized batches grow the context instead;
 //   * --max-chain-skip is ignored, i.e. true infinity (SURVEY.md trap T1), as in the reference's kernels;
-//   * host backtracking (lchain.c:27-111 semantics, csrc/backtrack.cpp) runs on a small thread pool into scratch, then the
-//     calling thread copies the results into the kalloc arena (kalloc is not thread-safe).
+//   * chain extraction + compaction (lchain.c:27-111) run on the device behind the DP kernels (k_backtrack); the calling
+//     thread only copies the results into the kalloc arena (kalloc is not thread-safe).  "host_backtrack": 1 in the config
+//     (or MM2GB_HOST_BACKTRACK=1) moves that stage to a small host thread pool instead (csrc/backtrack.cpp).
 #include "../../include/mm2gb_plchain.h"
 
 #include <atomic>
@@ -38,6 +39,7 @@ struct Config {
     int n_gpus = 0;                 // 0 = all visible
     int n_slots = 2;
     int host_threads = 8;
+    int host_backtrack = 0;         // 1 = chain extraction on host threads instead of the device kernel
 };
 
 struct ThreadState {
@@ -113,6 +115,8 @@ void load_config(const char *path)
     if (json_number(txt, "n_gpus", &v) && v >= 0) g_cfg.n_gpus = (int)v;
     if (json_number(txt, "n_slots", &v) && v >= 2 && v <= 4) g_cfg.n_slots = (int)v;
     if (json_number(txt, "host_threads", &v) && v >= 1) g_cfg.host_threads = (int)v;
+    if (json_number(txt, "host_backtrack", &v)) g_cfg.host_backtrack = v != 0;
+    if (const char *e = getenv("MM2GB_HOST_BACKTRACK")) g_cfg.host_backtrack = atoi(e) != 0;
     if (const char *e = getenv("MM2GB_HOST_THREADS")) g_cfg.host_threads = atoi(e) > 0 ? atoi(e) : g_cfg.host_threads;
     if (const char *e = getenv("MM2GB_N_GPUS")) g_cfg.n_gpus = atoi(e) > 0 ? atoi(e) : g_cfg.n_gpus;
     if (g_cfg.max_total_n > ((size_t)1 << 31) - 2048) g_cfg.max_total_n = ((size_t)1 << 31) - 2048;
@@ -146,14 +150,21 @@ ThreadState &state_of(int tid)
     return *g_state[tid];
 }
 
-// finish the batch in flight: wait for the device, backtrack on the pool, publish into the arena, run the driver's helper
+// finish the batch in flight: wait for the device, publish the chains into the arena, run the driver's helper.
+// Chain extraction + compaction (lchain.c:27-111) ran on the device behind the DP kernels (g_cfg.host_backtrack == 0,
+// default) or runs here on a small thread pool (host_backtrack == 1: the reference's arrangement, plchain.cu:99-150).
 void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt, const Misc_abi &misc, void *km)
 {
     mm2gb_chain_read_t *reads = S.reads;
     const int n_reads = S.n_reads;
-    const int32_t *f = nullptr, *p = nullptr;
     const int64_t *off = nullptr;
-    if (S.submitted) {
+    const uint64_t *const *dev_u = nullptr;
+    const int32_t *dev_nu = nullptr, *dev_nb = nullptr;
+    const mm2gb_anchor_t *dev_b = nullptr;
+    if (S.submitted && !g_cfg.host_backtrack) {
+        if (mm2gb_wait_chains(S.ctx, S.slot, &dev_u, &dev_nu, &dev_b, &dev_nb, &off, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
+    } else if (S.submitted) {
+        const int32_t *f = nullptr, *p = nullptr;
         if (mm2gb_wait(S.ctx, S.slot, &f, &p, &off, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
         const int64_t total = off[n_reads];
         if ((int64_t)S.su.size() < total) { S.su.resize((size_t)total); S.sb.resize((size_t)total); }
@@ -179,13 +190,17 @@ void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt
     }
     for (int r = 0; r < n_reads; ++r) { // arena traffic stays on the calling thread
         mm2gb_chain_read_t &rd = reads[r];
-        const int32_t n_u = S.submitted ? S.s_nu[(size_t)r] : 0;
+        int32_t n_u = 0;
+        int64_t n_b = 0;
+        const uint64_t *src_u = nullptr;
+        const mm2gb_anchor_t *src_b = nullptr;
+        if (S.submitted && dev_nu) { n_u = dev_nu[r]; n_b = dev_nb[r]; src_u = dev_u[r]; src_b = dev_b + off[r]; }
+        else if (S.submitted) { n_u = S.s_nu[(size_t)r]; n_b = S.s_nb[(size_t)r]; src_u = S.su.data() + off[r]; src_b = S.sb.data() + off[r]; }
         if (n_u > 0) {
-            const int64_t s = off[r], n_b = S.s_nb[(size_t)r];
             uint64_t *u = (uint64_t *)kmalloc(km, (size_t)n_u * sizeof(uint64_t));
-            memcpy(u, S.su.data() + s, (size_t)n_u * sizeof(uint64_t));
+            memcpy(u, src_u, (size_t)n_u * sizeof(uint64_t));
             mm2gb_anchor_t *b = (mm2gb_anchor_t *)kmalloc(km, (size_t)n_b * sizeof(mm2gb_anchor_t));
-            memcpy(b, S.sb.data() + s, (size_t)n_b * sizeof(mm2gb_anchor_t));
+            memcpy(b, src_b, (size_t)n_b * sizeof(mm2gb_anchor_t));
             kfree(km, rd.a); // compact_a frees the oversized input array (lchain.c:107-109)
             rd.a = b; rd.u = u; rd.n_u = n_u;
         } else {             // lchain.c:212-215 / plchain.cu:135-143
@@ -247,7 +262,9 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
     const int slot = S.busy ? (S.slot + 1) % g_cfg.n_slots : 0;
     bool submitted = false;
     if (in && total > 0) {
-        if (mm2gb_submit_gather(S.ctx, slot, S.ptrs.data(), S.ns.data(), n_in) != MM2GB_OK) die("launching a chaining batch");
+        const int rc = g_cfg.host_backtrack ? mm2gb_submit_gather(S.ctx, slot, S.ptrs.data(), S.ns.data(), n_in)
+                                            : mm2gb_submit_gather_chains(S.ctx, slot, S.ptrs.data(), S.ns.data(), n_in);
+        if (rc != MM2GB_OK) die("launching a chaining batch");
         submitted = true;
     }
     if (S.busy) complete_inflight(S, mi, opt, misc, km);
