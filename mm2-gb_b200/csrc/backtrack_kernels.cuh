@@ -6,7 +6,7 @@
 // <= 64), so that permutation is reproduced here -- not approximated by a stable sort (SURVEY.md trap T4).  The
 // reference (and mm2-gb after its kernels, gpu/plchain.cu:99-150) runs this on one host thread.
 //
-// How: one warp per read, the read's working set in shared memory.
+// How: one warp per read, the read's working set in shared memory (two kernels, see below).
 //   * American-flag pass = a deterministic walk over the ORIGINAL array: every bucket is a queue of its original
 //     elements; placing an element into bucket d pops the element that sat at d's cursor, which is placed next.  Runs of
 //     elements that already sit in their own bucket are finalised (home bucket) or shifted by one (visited bucket) as a
@@ -229,95 +229,147 @@ __device__ void bt_sort(typename KO::T *A, unsigned short *pay, typename KO::T *
     }
 }
 
-// shared memory of one read of capacity CAP anchors
+// ---------------------------------------------------------------------------------------------------------------------
+// The stage is two kernels per size class, one warp (= one CTA) per read each, because the two halves want different
+// amounts of shared memory: the sort needs 8 bytes per anchor for a few microseconds, the walk only ~3.5 bytes per anchor
+// for much longer (it is a serial pointer chase) -- so three times as many walks as sorts fit on an SM.
+//   k_bt_sort : z[] = anchors scoring >= min_sc, sorted as the reference sorts them  -> zs_scr (global), nz_out
+//   k_bt_walk : chain extraction in that order + compaction                          -> n_u, n_b, b_out, u_pack
+// ---------------------------------------------------------------------------------------------------------------------
 template <int CAP>
-struct BtSmem {
-    unsigned zk[CAP];               // sorted (score << 13 | index); later the low half of the 64-bit chain-start keys
-    unsigned zk2[CAP];              // sort scratch; then f[] by anchor index; later the high half of the chain-start keys
-    unsigned short ps[CAP];         // p[] by anchor index (0xffff = none); later chain ids [0, CAP/2) + their sort scratch [CAP/2, CAP)
-    unsigned tb[CAP / 32];          // claimed bits (lchain.c: t[])
+struct BtSortSmem {
+    unsigned zk[CAP];               // (score << 13 | index), sorted in place
+    unsigned zk2[CAP];              // rank-sort scratch
     unsigned cnt[256];
-    unsigned short start[kBtLevels * kBtRow];
+    unsigned short start[3 * kBtRow];   // scores are below 2^19: at most three radix levels
 };
 
-// ---------------------------------------------------------------------------------------------------------------------
-// k_backtrack: one warp (= one CTA) per read of the list
-//   inputs : a, f, p (p = predecessor index inside the read, -1 none), off
-//   scratch: v_scr (int per anchor; the chains' anchor indices in emission order), u_scr (u64 per anchor), vs_scr (int per anchor)
-//   outputs: per read r  n_u[r] (-1 = declined), n_b[r];  b_out[off[r] .. off[r] + n_b) = compacted anchors;  the n_u chains
-//            (score << 32 | count) at u_pack[u_pos[r] ..], a packed array shared by the batch (slots handed out by an atomic
-//            cursor, so only a short prefix has to be downloaded); a read whose chains do not fit u_cap is declined
-// ---------------------------------------------------------------------------------------------------------------------
 template <int CAP>
 __global__ void __launch_bounds__(32)
-k_backtrack(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
-            const int *__restrict__ read_list, int n_list, BtParams bp, int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr,
-            int *__restrict__ vs_scr, uint4 *__restrict__ b_out, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
-            unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ u_cur, int *__restrict__ u_pos)
+k_bt_sort(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
+          unsigned *__restrict__ zs_scr, int *__restrict__ nz_out)
 {
     extern __shared__ int4 bt_raw[];
-    BtSmem<CAP> &S = *reinterpret_cast<BtSmem<CAP> *>(bt_raw);
+    BtSortSmem<CAP> &S = *reinterpret_cast<BtSortSmem<CAP> *>(bt_raw);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;
     const int r = read_list[blockIdx.x];
     const long long o0 = off[r];
     const int n = (int)(off[r + 1] - o0);
-    const int *fr = f + o0, *pr = p + o0;
-    const uint4 *ar = a + o0;
-    int *vr = v_scr + o0, *vsr = vs_scr + o0;
-    unsigned long long *ur = u_scr + o0;
-    uint4 *bo = b_out + o0;
-    if (n > CAP) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
+    const int *fr = f + o0;
+    if (n > CAP || bp.min_sc < 0) { if (lane == 0) nz_out[r] = -1; return; }
+    // z[]: anchors scoring >= min_sc, in index order (lchain.c:33-40); 4 coalesced loads per lane in flight
+    int nz = 0, fmax = 0;
+    for (int i0 = 0; i0 < n; i0 += 128) {
+        int fv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; fv[t] = i < n ? fr[i] : INT32_MIN; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int i = i0 + t * 32 + lane;
+            const bool keep = fv[t] >= bp.min_sc && i < n;
+            const unsigned m = __ballot_sync(full, keep);
+            if (keep) S.zk[nz + __popc(m & ((1u << lane) - 1u))] = ((unsigned)fv[t] << kBtIdxBits) | (unsigned)i;
+            nz += __popc(m);
+            fmax = max(fmax, keep ? fv[t] : 0);
+        }
+    }
+    fmax = __reduce_max_sync(full, fmax);
+    if (fmax >= kBtMaxScore) { if (lane == 0) nz_out[r] = -1; return; }   // does not pack into 32 bits: host path
+    __syncwarp();
     BtSortScratch sc;
     sc.cnt = S.cnt;
     sc.start = S.start;
+    bt_sort<ZKey, false>(S.zk, nullptr, S.zk2, nullptr, nz, sc, lane);
+    unsigned *zo = zs_scr + o0;
+    for (int e = lane; e < nz; e += 32) zo[e] = S.zk[e];
+    if (lane == 0) nz_out[r] = nz;
+}
 
-    // ---- z[]: anchors scoring >= min_sc, in index order (lchain.c:33-40) -------------------------------------------------
-    int nz = 0, fmax = 0;
+template <int CAP>
+struct BtWalkSmem {
+    static constexpr int WC = CAP / 16 < 64 ? 64 : CAP / 16;   // chains whose start keys can be sorted here
+    unsigned long long wk[WC], wtmp[WC];    // chain-start keys (x of the first anchor) + sort scratch
+    unsigned short ps[CAP + 2];             // p[] by anchor index; "none" is the sentinel index CAP, whose own entry is CAP
+    unsigned short path[32];                // the nodes of one chase batch
+    unsigned tb[CAP / 32 + 1];              // claimed bits (lchain.c: t[]); the sentinel's bit is never set
+    unsigned gp[CAP / 32];                  // bit i: f[i] - f[p[i]] > 0 (f[i] > 0 for a root), the sign a one-step walk needs
+    unsigned short wpay[WC], wpay2[WC];     // chain ids + sort scratch
+    unsigned cnt[256];
+    unsigned short start[kBtLevels * kBtRow];
+};
+
+// inputs : a, f, p (p = predecessor index inside the read, -1 none), off, zs_scr / nz (from k_bt_sort)
+// scratch: v_scr (int per anchor; the chains' anchor indices in emission order), u_scr (u64 per anchor), vs_scr (int per anchor)
+// outputs: per read r  n_u[r] (-1 = declined), n_b[r];  b_out[off[r] .. off[r] + n_b) = compacted anchors;  the n_u chains
+//          (score << 32 | count) at u_pack[u_pos[r] ..], a packed array shared by the batch (slots handed out by an atomic
+//          cursor, so only a short prefix has to be downloaded); a read whose chains do not fit u_cap is declined
+template <int CAP>
+__global__ void __launch_bounds__(32)
+k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
+          const int *__restrict__ read_list, int n_list, BtParams bp, const unsigned *__restrict__ zs_scr, const int *__restrict__ nz_in,
+          int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_out,
+          int *__restrict__ n_u_out, int *__restrict__ n_b_out, unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ u_cur,
+          int *__restrict__ u_pos)
+{
+    extern __shared__ int4 bt_raw[];
+    BtWalkSmem<CAP> &S = *reinterpret_cast<BtWalkSmem<CAP> *>(bt_raw);
+    constexpr int WC = BtWalkSmem<CAP>::WC;
+    constexpr int SENT = CAP;       // "no predecessor"
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_list) return;
+    const int r = read_list[blockIdx.x];
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    const int nz = nz_in[r];
+    if (nz < 0) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
+    if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; } return; }
+    const int *fr = f + o0, *pr = p + o0;
+    const uint4 *ar = a + o0;
+    const unsigned *zs = zs_scr + o0;
+    int *vr = v_scr + o0, *vsr = vs_scr + o0;
+    unsigned long long *ur = u_scr + o0;
+    uint4 *bo = b_out + o0;
+
+    // ---- p by index, sign of the link gains, cleared claim bits ------------------------------------------------------------
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
-        const int fi = i < n ? fr[i] : INT32_MIN;
-        const bool keep = i < n && fi >= bp.min_sc;
-        const unsigned m = __ballot_sync(full, keep);
-        if (keep) S.zk[nz + __popc(m & ((1u << lane) - 1u))] = ((unsigned)fi << kBtIdxBits) | (unsigned)i;
-        nz += __popc(m);
-        fmax = max(fmax, keep ? fi : 0);
+        int pi = -1, fi = 0, fp = 0;
+        if (i < n) { pi = pr[i]; fi = fr[i]; }
+        if (pi >= 0) fp = fr[pi];
+        if (i < n) S.ps[i] = pi < 0 ? (unsigned short)SENT : (unsigned short)pi;
+        const unsigned g = __ballot_sync(full, i < n && fi - fp > 0);
+        if (lane == 0) { S.gp[i0 >> 5] = g; S.tb[i0 >> 5] = 0; }
     }
-    fmax = __reduce_max_sync(full, fmax);
-    if (fmax >= kBtMaxScore || bp.min_sc < 0) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; } // does not pack: host path
-    __syncwarp();
-    if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; } return; }
-    bt_sort<ZKey, false>(S.zk, nullptr, S.zk2, nullptr, nz, sc, lane);
-
-    // ---- f, p by index; clear the claimed bits ---------------------------------------------------------------------------
-    int *fs = reinterpret_cast<int *>(S.zk2);
-    for (int i = lane; i < n; i += 32) {
-        fs[i] = fr[i];
-        const int pi = pr[i];
-        S.ps[i] = pi < 0 ? (unsigned short)0xffffu : (unsigned short)pi;
-    }
-    for (int w = lane; w < (n + 31) / 32; w += 32) S.tb[w] = 0;
+    if (lane == 0) { S.ps[SENT] = (unsigned short)SENT; S.tb[CAP / 32] = 0; }
     __syncwarp();
 
     // ---- chain extraction, best end first (lchain.c:42-72 with mg_chain_bk_end :9-25) --------------------------------------
     int n_v = 0, n_u = 0;
     int k = nz - 1;
+    bool nothing_claimed = true;    // true until the first chain is claimed: its walk needs no claim tests at all
+    unsigned znext = (k - lane >= 0) ? zs[k - lane] : 0u;   // the 32 ends below k, fetched one round ahead
+    int knext = k;
     while (k >= 0) {
         {   // next chain end that is not claimed yet.  Ends whose predecessor is already claimed (or absent) are one-step
             // walks that can only claim themselves (lchain.c:16-22 evaluates p[i] once and stops): a run of them is settled
             // here in parallel, in visiting order; the first end that needs a real walk goes through the general code below.
             const int e = k - lane;
-            bool unc = false, simple = false;
             unsigned z = 0;
-            int i0l = 0, n1 = -1;
+            if (knext == k) z = znext;                     // the prefetched group is exactly this one
+            else if (e >= 0) z = zs[e];
+            knext = k - 32;                                // prefetch the group a full step further down
+            znext = (knext - lane >= 0) ? zs[knext - lane] : 0u;
+            bool unc = false, simple = false;
+            int i0l = 0, n1 = SENT;
             if (e >= 0) {
-                z = S.zk[e];
                 i0l = (int)(z & kBtIdxMask);
                 unc = ((S.tb[i0l >> 5] >> (i0l & 31)) & 1u) == 0;
                 if (unc) {
-                    n1 = (int)(short)S.ps[i0l];
-                    simple = n1 < 0 || ((S.tb[n1 >> 5] >> (n1 & 31)) & 1u) != 0;
+                    n1 = S.ps[i0l];
+                    simple = n1 == SENT || ((S.tb[n1 >> 5] >> (n1 & 31)) & 1u) != 0;
                 }
             }
             const unsigned m = __ballot_sync(full, unc);
@@ -327,55 +379,72 @@ k_backtrack(const uint4 *__restrict__ a, const int *__restrict__ f, const int *_
             const unsigned fastm = nfast >= 32 ? m : (m & ((1u << nfast) - 1u));
             if (fastm) {
                 const bool mine_f = ((fastm >> lane) & 1u) != 0;
-                const int keyl = (int)(z >> kBtIdxBits);
-                const int s1 = mine_f ? (n1 < 0 ? keyl : keyl - fs[n1]) : 0;
-                const bool claim = mine_f && s1 > 0;                       // cut = p[i0]: the chain is {i0}
+                const bool claim = mine_f && ((S.gp[i0l >> 5] >> (i0l & 31)) & 1u) != 0;   // s_1 > 0: cut = p[i0], chain = {i0}
                 if (claim) atomicOr(&S.tb[i0l >> 5], 1u << (i0l & 31));
-                const bool acc = claim && s1 >= bp.min_sc && bp.min_cnt <= 1;
-                const unsigned am = __ballot_sync(full, acc);
-                if (am) {
-                    const int rank = __popc(am & ((1u << lane) - 1u));
-                    if (acc) {
-                        ur[n_u + rank] = ((unsigned long long)(unsigned)s1 << 32) | 1ULL;
-                        vsr[n_u + rank] = n_v + rank;
-                        vr[n_v + rank] = i0l;
+                if (__any_sync(full, claim)) nothing_claimed = false;
+                if (bp.min_cnt <= 1) { // single-anchor chains can be accepted: needs the value of s_1
+                    const int keyl = (int)(z >> kBtIdxBits);
+                    const int s1 = claim ? (n1 == SENT ? keyl : keyl - fr[n1]) : 0;
+                    const bool acc = claim && s1 >= bp.min_sc;
+                    const unsigned am = __ballot_sync(full, acc);
+                    if (am) {
+                        const int rank = __popc(am & ((1u << lane) - 1u));
+                        if (acc) {
+                            ur[n_u + rank] = ((unsigned long long)(unsigned)s1 << 32) | 1ULL;
+                            vsr[n_u + rank] = n_v + rank;
+                            vr[n_v + rank] = i0l;
+                        }
+                        n_u += __popc(am);
+                        n_v += __popc(am);
                     }
-                    n_u += __popc(am);
-                    n_v += __popc(am);
                 }
                 __syncwarp();
             }
             k -= nfast;
             if (!hard) continue;
         }
-        const unsigned zkk = S.zk[k];
+        const unsigned zkk = zs[k];
         const int i0 = (int)(zkk & kBtIdxMask), key = (int)(zkk >> kBtIdxBits);
-        // path n_0 = i0, n_1 = p[n_0], ...; node n_j (j >= 1) is "evaluated": s_j = key - f[n_j] (key if n_j < 0).
+        // path n_0 = i0, n_1 = p[n_0], ...; node n_j (j >= 1) is "evaluated": s_j = key - f[n_j] (key if n_j is the sentinel).
         // cutj = largest evaluated j whose s_j is a strict new maximum (0 if none): the chain is n_0 .. n_{cutj-1}.
+        // The predecessor chase is the serial part: 32 nodes per batch, one shared-memory load per node (the sentinel points
+        // at itself, so the chase needs no end test); where the walk ends is found afterwards for all 32 nodes at once.
         int cur = i0, max_s = 0, cutj = 0, cutnode = i0, j0 = 0;
-        int mine0 = -1; // this lane's node of the first batch (enough to mark chains of <= 32 nodes without re-reading)
+        int mine0 = SENT; // this lane's node of the first batch (enough to mark chains of <= 32 nodes without re-reading)
         for (;;) {
-            // serial part: chase up to 32 predecessors; stop right after the first node that ends the walk (root passed or a
-            // claimed anchor), so that the many 1-3 node side chains cost 1-3 steps, not 32
-            int mine = -2, nb = 0;
-            bool ended = false;
+            int nb = 32;
+            if (j0 == 0 && !nothing_claimed) {
+                // first batch of a later walk: most of them end within a few nodes (at a claimed anchor), so look as we go
+                nb = 0;
 #pragma unroll 4
-            for (int b = 0; b < 32; ++b) {
-                if (b == lane) mine = cur;
-                nb = b + 1;
-                if (cur < 0) { ended = true; break; }
-                const unsigned tw = S.tb[cur >> 5];             // both loads depend on cur only: issued together
-                const int nxt = (int)(short)S.ps[cur];          // 0xffff -> -1
-                if (((tw >> (cur & 31)) & 1u) != 0 && j0 + b >= 1) { ended = true; break; }
-                cur = nxt;
+                for (int b = 0; b < 32; ++b) {
+                    if (lane == 0) S.path[b] = (unsigned short)cur;
+                    nb = b + 1;
+                    const unsigned tw = S.tb[cur >> 5];             // both loads depend on cur only: issued together
+                    const int nxt = S.ps[cur];
+                    if (cur == SENT || (((tw >> (cur & 31)) & 1u) != 0 && b >= 1)) break;
+                    cur = nxt;
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    if (lane == 0) S.path[b] = (unsigned short)cur;
+                    cur = S.ps[cur];
+                }
             }
+            __syncwarp();
+            const int mine = lane < nb ? (int)S.path[lane] : SENT;
+            int fmine = 0;
+            if (lane < nb && mine != SENT) fmine = fr[mine];
+            __syncwarp();
             if (j0 == 0) mine0 = mine;
             const int j = j0 + lane;
             const bool ev = j >= 1 && lane < nb;
             int s = INT32_MIN;
-            const bool stop = ended && lane == nb - 1;
-            if (ev) s = mine < 0 ? key : key - fs[mine];
-            if (mine >= 0 && n_v + j < n) vr[n_v + j] = mine;   // speculative: only the first cutj entries count
+            // the walk stops after evaluating a node that is the root's "predecessor" or already claimed (lchain.c:22)
+            const bool stop = ev && (mine == SENT || ((S.tb[mine >> 5] >> (mine & 31)) & 1u) != 0);
+            if (ev) s = mine == SENT ? key : key - fmine;
+            if (lane < nb && mine != SENT && n_v + j < n) vr[n_v + j] = mine;   // speculative: only the first cutj entries count
             // prefix maxima (max_s carried in), exclusive for the tests of lchain.c:20-21
             int pm = ev ? s : INT32_MIN;
 #pragma unroll
@@ -402,6 +471,7 @@ k_backtrack(const uint4 *__restrict__ a, const int *__restrict__ f, const int *_
         }
         const int cnt = cutj;
         if (cnt > 0) { // claim n_0 .. n_{cnt-1}  (stays claimed even if the chain is rejected below, as in the reference)
+            nothing_claimed = false;
             if (cnt <= 32) {
                 if (lane < cnt) atomicOr(&S.tb[mine0 >> 5], 1u << (mine0 & 31));
             } else {
@@ -410,7 +480,7 @@ k_backtrack(const uint4 *__restrict__ a, const int *__restrict__ f, const int *_
             }
         }
         __syncwarp();
-        const int scv = cutnode < 0 ? key : key - fs[cutnode];
+        const int scv = cutnode == SENT ? key : key - fr[cutnode];
         if (scv >= bp.min_sc && cnt > 0 && cnt >= bp.min_cnt) {
             if (lane == 0) { ur[n_u] = ((unsigned long long)(unsigned)scv << 32) | (unsigned)cnt; vsr[n_u] = n_v; }
             ++n_u;
@@ -423,25 +493,26 @@ k_backtrack(const uint4 *__restrict__ a, const int *__restrict__ f, const int *_
 
     // ---- compact_a (lchain.c:78-111): chains flipped to ascending order, then ordered by the x of their first anchor with
     //      the same unstable sort (w[i].x = b[k].x, payload = chain id) --------------------------------------------------------
-    if (n_u > CAP / 2) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }   // more chains than the key buffer holds (needs min_cnt == 1)
+    if (n_u > WC) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }   // more chains than the key buffer holds: host path
     int upos = 0;
     if (lane == 0) upos = atomicAdd(u_cur, n_u);
     upos = __shfl_sync(full, upos, 0);
     if (upos + n_u > u_cap) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }   // packed chain buffer full: host path
     unsigned long long *uo = u_pack + upos;
-    unsigned long long *wk = reinterpret_cast<unsigned long long *>(S.zk);   // zk | zk2 are contiguous: CAP 64-bit keys
-    unsigned long long *wtmp = wk + CAP / 2;
     for (int c = lane; c < n_u; c += 32) {
         const int cntc = (int)(unsigned)ur[c], s0 = vsr[c];
         const uint4 av = ar[vr[s0 + cntc - 1]];
-        wk[c] = ((unsigned long long)av.y << 32) | av.x;
-        S.ps[c] = (unsigned short)c;
+        S.wk[c] = ((unsigned long long)av.y << 32) | av.x;
+        S.wpay[c] = (unsigned short)c;
     }
     __syncwarp();
-    bt_sort<WKey, true>(wk, S.ps, wtmp, S.ps + CAP / 2, n_u, sc, lane);
+    BtSortScratch sc;
+    sc.cnt = S.cnt;
+    sc.start = S.start;
+    bt_sort<WKey, true>(S.wk, S.wpay, S.wtmp, S.wpay2, n_u, sc, lane);
     int out = 0;
     for (int c = 0; c < n_u; ++c) {
-        const int src = S.ps[c];
+        const int src = S.wpay[c];
         const unsigned long long uv = ur[src];
         const int cntc = (int)(unsigned)uv, s0 = vsr[src];
         if (lane == 0) uo[c] = uv;

@@ -71,6 +71,8 @@ struct Slot {
     unsigned long long *d_uscr = nullptr;
     int *d_vs = nullptr, *d_nu = nullptr, *d_nb = nullptr, *d_list = nullptr, *d_upos = nullptr, *d_ucur = nullptr;
     unsigned long long *d_upack = nullptr;
+    unsigned *d_zs = nullptr;   // sorted (score, index) pairs of every read (k_bt_sort -> k_bt_walk)
+    int *d_nz = nullptr;
     size_t u_cap = 0;      // entries of d_upack / h_upack
     cudaStream_t bt_stream[7] = {nullptr};   // the size classes of k_backtrack run side by side (each is a partial wave)
     cudaEvent_t bt_fork = nullptr, bt_join[7] = {nullptr};
@@ -290,7 +292,9 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
 
 static int config_backtrack()
 {
-#define X(CAP) CK(cudaFuncSetAttribute(k_backtrack<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtSmem<CAP>)));
+#define X(CAP)                                                                                                                        \
+    CK(cudaFuncSetAttribute(k_bt_sort<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtSortSmem<CAP>)));            \
+    CK(cudaFuncSetAttribute(k_bt_walk<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtWalkSmem<CAP>)));
     MM2GB_BT_CLASSES(X)
 #undef X
     return MM2GB_OK;
@@ -301,9 +305,9 @@ static void launch_backtrack(cudaStream_t s, const uint4 *d_a, const int *d_f, c
                              const BtParams &bp, Slot &sl)
 {
     if (n_list <= 0) return;
-    k_backtrack<CAP><<<n_list, 32, sizeof(BtSmem<CAP>), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_st /* dead after scoring: v scratch */,
-                                                             sl.d_uscr, sl.d_vs, sl.d_b, sl.d_nu, sl.d_nb, sl.d_upack, sl.u_cap_batch,
-                                                             sl.d_ucur, sl.d_upos);
+    k_bt_sort<CAP><<<n_list, 32, sizeof(BtSortSmem<CAP>), s>>>(d_f, d_off, list, n_list, bp, sl.d_zs, sl.d_nz);
+    k_bt_walk<CAP><<<n_list, 32, sizeof(BtWalkSmem<CAP>), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zs, sl.d_nz, sl.d_st /* dead after scoring: v scratch */,
+                                                           sl.d_uscr, sl.d_vs, sl.d_b, sl.d_nu, sl.d_nb, sl.d_upack, sl.u_cap_batch, sl.d_ucur, sl.d_upos);
 }
 
 // Reads are binned by anchor count into the shared-memory classes of k_backtrack (off_rel is the host copy of the
@@ -376,7 +380,7 @@ static void free_slot(Slot &s)
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
     cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
     cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
-    cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_nu); cudaFree(s.d_nb); cudaFree(s.d_list); cudaFree(s.d_upos); cudaFree(s.d_ucur); cudaFree(s.d_upack);
+    cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_nu); cudaFree(s.d_nb); cudaFree(s.d_list); cudaFree(s.d_upos); cudaFree(s.d_ucur); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
     cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
     cudaFreeHost(s.h_b); cudaFreeHost(s.h_nu); cudaFreeHost(s.h_nb); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upos); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
@@ -473,6 +477,8 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaMalloc(&s.d_upack, s.u_cap * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_upos, ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMalloc(&s.d_ucur, sizeof(int)));
+            CKC(cudaMalloc(&s.d_zs, n * sizeof(unsigned)));
+            CKC(cudaMalloc(&s.d_nz, ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
             CKC(cudaMallocHost(&s.h_upos, ((size_t)max_reads + 1) * sizeof(int)));
         }

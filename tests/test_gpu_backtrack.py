@@ -68,8 +68,8 @@ def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score):
     _compare(pkg, misc, a, off, f, p, u, n_u, b, n_b)
     print(f"declined by the device: {nd} of {len(sizes)} reads")
     assert nd >= 2   # the two reads above 8192 anchors take the host implementation
-    if min_cnt >= 2:
-        assert nd == 2
+    if min_cnt >= 2 and kind in ("chainlike", "wide", "narrow"):
+        assert nd == 2   # (forests with thousands of chains per read exceed the chain-key buffer and go to the host too)
 
 
 def test_drop_and_negative_links(pkg, synth):
