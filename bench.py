@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ont|long|chainonly]
 
-step      = one pass of the hot path (range -> units -> score kernels) over one batch of synthetic reads.
+step      = one pass of the hot path over one batch of synthetic reads, everything on the device: range -> units -> score
+            kernels (f, p), then chain extraction + compaction (k_bt_sort / k_bt_walk: u, a') -- the whole mg_lchain_dp.
 workload  = BASELINE.json configs[1]: 100 Mb random reference, 10k simulated ONT-like reads 10-100 kb at ~10 % error,
             map-ont chaining parameters; anchors come from the package's own minimizer seeder (mm2-gb_b200/csrc/
             synth_seed.cpp).  At N GPUs every rank chains its own 10k reads (same reference, different reads): weak scaling,
@@ -11,8 +12,8 @@ workload  = BASELINE.json configs[1]: 100 Mb random reference, 10k simulated ONT
 value     = pairs chained per second with the anchors already resident in HBM (CUDA events on the launching stream,
             max over ranks); pairs = sum_i (i - st_i) = the reference's n_iter (lchain.c:177), counted by the device and
             cross-checked against the oracle in the tests.
-e2e       = the same metric through the C ABI call mm2gb_chain_host with pinned HOST buffers: upload, kernels, download of
-            f/p and the threaded host backtracking stage are all inside the timed region -- i.e. the whole mg_lchain_dp.
+e2e       = the same metric through the C ABI call mm2gb_chain_host with pinned HOST buffers: upload of the anchors, all
+            kernels, download of the chains and compacted anchors are inside the timed region.
 roofline  = the score kernel (dominant): algorithmic HBM bytes (24 B/anchor) over its CUDA-event time vs the measured copy
             peak, plus the issue-slot view that actually bounds it (SASS thread-instructions per pair / SM issue rate).
 cpu_baseline / --impl reference = the reference's own lchain.c (oracle/_ref/libref_lchain.so, compiled from the
@@ -34,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-INSTR_PER_PAIR = 17.0      # SASS thread-instructions per anchor pair in the phase-A inner loop of k_score_units (profiles/)
+INSTR_PER_PAIR = 20.0      # algorithmic integer-pipe operations per anchor pair of comput_sc + max/argmax
 HBM_BYTES_PER_ANCHOR = 24  # read 16 B mm128_t, write 4 B f + 4 B p
 
 WORKLOADS = {
@@ -208,7 +209,8 @@ def main():
     torch.cuda.synchronize()
 
     def step():
-        ctx.chain_dp_device(d_a, d_off, n_reads, n, d_f, d_p)
+        # the whole device side of mg_lchain_dp: range -> units -> score (f, p) -> chain extraction + compaction (u, a')
+        ctx.chain_device(d_a, d_off, off, n_reads, n, d_f, d_p)
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,6 +287,9 @@ def main():
 
     sec = ms_max / 1e3
     value = tot_pairs * args.steps / sec
+    rn = np.diff(off)
+    bt_classes = len({int(np.searchsorted([1024, 1536, 2048, 3072, 4096, 6144, 8192], x)) for x in rn if x <= 8192})
+    dp_ms = sum(prof[k][0] / max(1, prof[k][1]) for k in ("range", "units", "score"))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -302,15 +307,17 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_score_units", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                 "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
                 "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms,
-                "note": "this kernel is issue-bound, not HBM-bound (~%d pairs x %.0f instr per 24 B): see issue" % (round(pairs / max(1, n)), INSTR_PER_PAIR),
-                "issue": {"bound": "int-issue", "achieved": issue_ach, "peak": issue_peak, "unit": "thread-instr/s", "frac": issue_ach / issue_peak,
-                          "instr_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": pairs / score_avg_s, "sm_mhz": sm_mhz, "n_sm": n_sm}}
+                "note": "this kernel is integer-issue bound, not HBM-bound (~%d pairs x %.0f integer ops per 24 B): see issue" % (round(pairs / max(1, n)), INSTR_PER_PAIR),
+                "issue": {"bound": "int-issue", "achieved": issue_ach, "peak": issue_peak, "unit": "algorithmic int-ops/s", "frac": issue_ach / issue_peak,
+                          "int_ops_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": pairs / score_avg_s, "sm_mhz": sm_mhz, "n_sm": n_sm}}
     line = {"metric": "chaining anchor-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": cfg, "reads_per_s": tot_reads * args.steps / sec, "anchors_per_s": tot_anchors * args.steps / sec,
             "batch": {"reads": n_reads, "anchors": n, "pairs": pairs, "pairs_per_anchor": pairs / max(1, n), "units": int(st.n_units),
                       "units_exact": int(st.n_units_exact), "chains": n_chains},
             "kernel_ms_per_step": {k: v[0] / max(1, v[1]) for k, v in prof.items() if v[1]},
+            "dp_only": {"value": pairs / (dp_ms / 1e3), "unit": "pairs/s", "ms": dp_ms,
+                        "note": "range + units + score kernels only (f, p); `value` also includes the device chain extraction + compaction"},
             "roofline": roofline,
             "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1),
                     "d2h_bytes_per_step": 16 * n + 8 * (n // 8 + 8 * n_reads) + 12 * n_reads,
@@ -320,7 +327,7 @@ def main():
                     "slots": 6, "chunk_anchors": e2e_cap,
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
-            "gpu_launches": 7 * args.steps, "clocks": clocks}
+            "gpu_launches": (7 + 2 * bt_classes) * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
     print(json.dumps(line))

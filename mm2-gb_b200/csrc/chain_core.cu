@@ -752,10 +752,15 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
     while (r0 < n_reads) {
         int r1 = r0;
         long long cnt = 0;
+        // small chunks at both ends of the batch shorten the parts of the pipeline that cannot overlap (the first upload,
+        // the last kernels + download); full-size chunks in between keep the kernels efficient
+        const long long remaining = off[n_reads] - off[r0];
+        const long long ramp = (target / 4) << std::min(chunk, 2);
+        const long long this_target = std::max<long long>(1 << 18, std::min(std::min(target, ramp), std::max(target / 4, remaining * 2 / 5)));
         while (r1 < n_reads && r1 - r0 < c->max_reads) {
             const long long nr = off[r1 + 1] - off[r1];
             if (nr > (long long)c->max_anchors) return fail(MM2GB_ECAP, "read %d has %lld anchors, capacity is %zu", r1, nr, c->max_anchors);
-            if (cnt && cnt + nr > target) break;
+            if (cnt && cnt + nr > this_target) break;
             cnt += nr; ++r1;
         }
         const int si = chunk % c->n_slots;
