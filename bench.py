@@ -241,15 +241,15 @@ def main():
     # ---- end to end through the C ABI with pinned host buffers: the whole mg_lchain_dp (upload of the anchors, DP kernels,
     #      chain extraction + compaction on the device, download of chains and compacted anchors)
     out = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
-           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
+           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
     host_threads = max(1, cpu_threads() // max(1, world))
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(2):
-        ctx_e2e.chain(h_a, off, out=out, want_fp=False)
+        ctx_e2e.chain(h_a, off, out=out, packed=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = ctx_e2e.chain(h_a, off, out=out, want_fp=False)
+        res = ctx_e2e.chain(h_a, off, out=out, packed=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -273,13 +273,8 @@ def main():
     host_only_s = host_stage_alone(pkg, misc, a, off, outh["f"].numpy(), outh["p"].numpy(), host_threads)
 
     # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
-    tot = torch.tensor([float(pairs), float(n), float(n_reads)], dtype=torch.float64, device="cuda")
-    tmax = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tot_pairs, tot_anchors, tot_reads = (float(x) for x in tot.tolist())
-    ms_max, e2e_max = (float(x) for x in tmax.tolist())
+    from mm2gb_b200 import sharding
+    (tot_pairs, tot_anchors, tot_reads), (ms_max, e2e_max) = sharding.reduce_job(dist, [pairs, n, n_reads], [ms, e2e_s], device="cuda")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -288,7 +283,8 @@ def main():
     sec = ms_max / 1e3
     value = tot_pairs * args.steps / sec
     rn = np.diff(off)
-    bt_classes = len({int(np.searchsorted([1024, 1536, 2048, 3072, 4096, 6144, 8192], x)) for x in rn if x <= 8192})
+    bt_set = {int(np.searchsorted([1024, 1536, 2048, 3072, 4096, 6144, 8192], x)) for x in rn}
+    bt_classes = len(bt_set) + (1 if bt_set - {7} else 0)   # + the overflow pass behind the shared-memory classes
     dp_ms = sum(prof[k][0] / max(1, prof[k][1]) for k in ("range", "units", "score"))
     peaks = {}
     try:
@@ -320,9 +316,9 @@ def main():
                         "note": "range + units + score kernels only (f, p); `value` also includes the device chain extraction + compaction"},
             "roofline": roofline,
             "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1),
-                    "d2h_bytes_per_step": 16 * n + 8 * (n // 8 + 8 * n_reads) + 12 * n_reads,
+                    "d2h_bytes_per_step": 16 * n_chain_anchors + 8 * n_chains + 16 * (n_reads + 64),
                     "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps,
-                    "includes": "H2D anchors, range+unit+score kernels, device chain extraction + compaction (k_backtrack), D2H chains + compacted anchors (= whole mg_lchain_dp)",
+                    "includes": "H2D anchors, range+unit+score kernels, device chain extraction + compaction (k_bt_sort/k_bt_walk), packed chains + compacted anchors written to pinned host memory by k_drain (= whole mg_lchain_dp)",
                     "chain_anchors": n_chain_anchors,
                     "slots": 6, "chunk_anchors": e2e_cap,
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,

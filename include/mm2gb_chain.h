@@ -57,7 +57,7 @@ typedef struct {
 const char *mm2gb_last_error(void);
 int mm2gb_device_count(void);
 
-/* One context per (host thread, GPU).  `max_anchors` / `max_reads` bound one batch; `n_slots` (1..4) is the
+/* One context per (host thread, GPU).  `max_anchors` / `max_reads` bound one batch; `n_slots` (1..8) is the
  * number of batches that may be in flight (each slot owns a stream, pinned staging and device buffers).
  * Replaces plmem_stream_initialize + plrange/plscore_upload_misc (gpu/plmem.cu:558-624, plchain.cu:470-474). */
 int mm2gb_ctx_create(mm2gb_ctx_t **ctx, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc);
@@ -77,12 +77,18 @@ int mm2gb_chain_dp_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t
  * the rest of b[off[r] .. off[r+1]) is scratch.  f/p (size off[n_reads]) receive the DP arrays; they may be NULL when
  * n_threads <= 0.
  *   n_threads <= 0 : chain extraction + compaction (lchain.c:27-111) run on the DEVICE right behind the DP kernels and only
- *                    their result is downloaded (straight into `b` when it is pinned).  Reads the device kernel declines
- *                    (more than 8192 anchors, scores >= 2^19) are finished by the host implementation.
+ *                    their (packed) result leaves the device.  Reads of any size are handled on the device: up to 8192
+ *                    anchors in shared memory, longer ones (or scores >= 2^19) by the global-memory kernels.
  *   n_threads >= 1 : f/p are downloaded and that stage runs on n_threads host threads (what the reference does on one
  *                    thread, gpu/plchain.cu:99-150). */
 int mm2gb_chain_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                      uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats);
+
+/* The same with PACKED compacted anchors (what bench.py's end-to-end figure calls): read r's anchors are
+ * b[b_pos[r] .. b_pos[r]+n_b[r]); `b` needs room for off[n_reads] anchors.  With `b` in pinned (mapped) memory the device
+ * writes the compacted anchors there itself (k_drain) -- exactly the bytes produced, no host copy of them at all. */
+int mm2gb_chain_host_packed(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, uint64_t *u, int32_t *n_u,
+                            mm2gb_anchor_t *b, int64_t *b_pos, int64_t *n_b, mm2gb_stats_t *stats);
 
 /* Asynchronous pair.  submit: stage anchors into the slot's pinned buffer, enqueue H2D + kernels + D2H on the slot's
  * stream and return.  wait: block until the slot is done and expose the pinned result arrays (valid until the slot is
@@ -92,9 +98,9 @@ int mm2gb_submit_gather(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const 
 int mm2gb_wait(mm2gb_ctx_t *ctx, int slot, const int32_t **f, const int32_t **p, const int64_t **off, mm2gb_stats_t *stats);
 /* The same pair with chain extraction on the device (what the drop-in uses; replaces the host loop of
  * gpu/plchain.cu:99-150).  wait_chains: per read r  n_u[r] chains at u[r][0 .. n_u[r]) and n_b[r] compacted anchors at
- * b[off[r] ..]; everything lives in the slot's pinned memory until the slot is submitted again. */
+ * b[r][0 .. n_b[r]); everything lives in the slot's pinned memory until the slot is submitted again. */
 int mm2gb_submit_gather_chains(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads);
-int mm2gb_wait_chains(mm2gb_ctx_t *ctx, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t **b,
+int mm2gb_wait_chains(mm2gb_ctx_t *ctx, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t *const **b,
                       const int32_t **n_b, const int64_t **off, mm2gb_stats_t *stats);
 int mm2gb_slot_busy(mm2gb_ctx_t *ctx, int slot);
 
@@ -126,8 +132,9 @@ int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p, const mm2
                         int32_t max_drop, uint64_t *u, mm2gb_anchor_t *b, int64_t *n_b);
 
 /* The device version of that stage (k_backtrack; what mm2gb_chain_host with n_threads <= 0 and the drop-in run behind the DP
- * kernels) on caller-supplied f / p: same outputs, layout as in mm2gb_chain_host.  *n_declined = reads the kernel handed
- * to the host implementation (more than 8192 anchors, scores >= 2^19, chain buffer full).  Synchronous; uses slot 0. */
+ * kernels) on caller-supplied f / p: same outputs, layout as in mm2gb_chain_host.  *n_declined = reads handed to the host
+ * implementation (only with min_score < 0, or more than 256 reads of a batch overflowing the shared-memory kernels).
+ * Synchronous; uses slot 0. */
 int mm2gb_backtrack_device(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
                            const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int32_t *n_declined);
 

@@ -84,6 +84,7 @@ def lib():
         L.mm2gb_ctx_set_misc.argtypes = [vp, C.POINTER(Misc)]
         L.mm2gb_chain_dp_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.POINTER(Stats)]
         L.mm2gb_chain_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(Stats)]
+        L.mm2gb_chain_host_packed.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(Stats)]
         L.mm2gb_submit.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_submit_gather.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_wait.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
@@ -168,14 +169,26 @@ class ChainContext:
         _ck(lib().mm2gb_chain_dp_host(self._h, _ptr(a), _ptr(off), n_reads, _ptr(f), _ptr(p), C.byref(st)))
         return f, p, st
 
-    def chain(self, a, off, n_threads: int = 0, out=None, want_fp: bool = True):
-        """Whole mg_lchain_dp for a batch.  n_threads <= 0: chain extraction + compaction on the device (k_backtrack);
+    def chain(self, a, off, n_threads: int = 0, out=None, want_fp: bool = True, packed: bool = False):
+        """Whole mg_lchain_dp for a batch.  n_threads <= 0: chain extraction + compaction on the device (k_bt_sort/k_bt_walk);
         n_threads >= 1: that stage on n_threads host threads.  Returns dict with f, p (None unless want_fp), u, n_u, b,
         n_b, stats; read r's chains are u[off[r]:off[r]+n_u[r]], its compacted anchors b[off[r]:off[r]+n_b[r]].
+        packed=True (device stage only, no f/p): mm2gb_chain_host_packed -- read r's compacted anchors are
+        b[b_pos[r]:b_pos[r]+n_b[r]]; with a pinned `b` the device writes exactly the bytes produced straight into it.
         `out` may carry preallocated (e.g. pinned) buffers under the same keys."""
         n_reads = len(off) - 1
         n = int(off[-1])
         out = dict(out or {})
+        if packed:
+            out["f"] = out["p"] = None
+            out.setdefault("u", np.empty(n, np.uint64)); out.setdefault("b", np.empty((n, 2), np.uint64))
+            out.setdefault("n_u", np.zeros(n_reads, np.int32)); out.setdefault("n_b", np.zeros(n_reads, np.int64))
+            out.setdefault("b_pos", np.zeros(n_reads, np.int64))
+            st = Stats()
+            _ck(lib().mm2gb_chain_host_packed(self._h, _ptr(a), _ptr(off), n_reads, _ptr(out["u"]), _ptr(out["n_u"]), _ptr(out["b"]),
+                                              _ptr(out["b_pos"]), _ptr(out["n_b"]), C.byref(st)))
+            out["stats"] = st
+            return out
         if want_fp or n_threads >= 1:
             out.setdefault("f", np.empty(n, np.int32)); out.setdefault("p", np.empty(n, np.int32))
         else:

@@ -15,21 +15,27 @@
 //   * buckets of <= 64 elements: insertion sort == stable sort, done as a parallel rank sort.
 //   * chain walks: the predecessor chase is serial, everything else (claimed test, score drop test of
 //     mg_chain_bk_end, prefix maxima) is evaluated for 32 path nodes at a time.
-// Reads that do not fit (more than kBtMaxAnchors anchors, scores >= 2^19) are declined (n_u = -1) and go through the
-// host implementation (backtrack.cpp), which is the same algorithm.
+// Reads that do not fit the shared-memory kernels (more than kBtMaxAnchors anchors; scores >= 2^19; more chains than the
+// key buffer holds) run the SAME code on global-memory scratch with 64-bit keys and 32-bit indices (k_bt_sort_big /
+// k_bt_walk_big): reads above 8192 anchors are listed by the host, the others arrive through a device-side overflow list.
+// Compacted anchors and chains of the whole batch are PACKED (positions handed out by atomic cursors, recorded per read),
+// so that only what was produced is moved to the host (k_drain writes it straight into mapped pinned memory).
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "chain_kernels.cuh"
+
 namespace mm2gb {
 
-constexpr int kBtIdxBits = 13;                          // anchors per read handled on the device: 2^13
+constexpr int kBtIdxBits = 13;                          // anchors per read handled in shared memory: 2^13
 constexpr int kBtMaxAnchors = 1 << kBtIdxBits;
 constexpr unsigned kBtIdxMask = kBtMaxAnchors - 1;
 constexpr int kBtMaxScore = 1 << (32 - kBtIdxBits);     // packed key = f << 13 | i must fit 32 bits
 constexpr int kBtLevels = 8;                            // radix levels of a 64-bit key
 constexpr int kBtRow = 260;                             // per level: start[0..256], next-bucket cursor, shift
+constexpr int kBtOvfCap = 256;                          // reads per batch the shared-memory kernels may hand to the global-memory ones
 
 struct BtParams { int min_cnt, min_sc, max_drop; };
 
@@ -39,25 +45,38 @@ struct ZKey {   // (score, index) pair packed in 32 bits, ordered by score only 
     __device__ static __forceinline__ unsigned digit(T k, int shift) { return ((k >> kBtIdxBits) >> shift) & 255u; }
     __device__ static __forceinline__ bool less(T a, T b) { return (a >> kBtIdxBits) < (b >> kBtIdxBits); }
     __device__ static __forceinline__ unsigned long long key64(T k) { return (unsigned long long)(k >> kBtIdxBits); }
+    __device__ static __forceinline__ int idx(T k) { return (int)(k & kBtIdxMask); }
+    __device__ static __forceinline__ int score(T k) { return (int)(k >> kBtIdxBits); }
+    __device__ static __forceinline__ T make(int f, int i) { return ((unsigned)f << kBtIdxBits) | (unsigned)i; }
 };
-struct WKey {   // chain start position x (64 bit); the chain id travels in a separate 16-bit payload array
+struct ZKey64 { // the same pair in 64 bits (any read length, any score): score << 32 | index
+    typedef unsigned long long T;
+    __device__ static __forceinline__ unsigned digit(T k, int shift) { return ((unsigned)(k >> 32) >> shift) & 255u; }
+    __device__ static __forceinline__ bool less(T a, T b) { return (unsigned)(a >> 32) < (unsigned)(b >> 32); }
+    __device__ static __forceinline__ unsigned long long key64(T k) { return k >> 32; }
+    __device__ static __forceinline__ int idx(T k) { return (int)(unsigned)k; }
+    __device__ static __forceinline__ int score(T k) { return (int)(unsigned)(k >> 32); }
+    __device__ static __forceinline__ T make(int f, int i) { return ((unsigned long long)(unsigned)f << 32) | (unsigned)i; }
+};
+struct WKey {   // chain start position x (64 bit); the chain id travels in a separate payload array
     typedef unsigned long long T;
     __device__ static __forceinline__ unsigned digit(T k, int shift) { return (unsigned)(k >> shift) & 255u; }
     __device__ static __forceinline__ bool less(T a, T b) { return a < b; }
     __device__ static __forceinline__ unsigned long long key64(T k) { return k; }
 };
 
-// scratch shared by the sorts of one warp
+// scratch shared by the sorts of one warp; POS = type of a position inside the sorted array
+template <class POS>
 struct BtSortScratch {
-    unsigned *cnt;              // [256] histogram, then the bucket cursors of the running pass
-    unsigned short *start;      // [kBtLevels][kBtRow]
+    unsigned *cnt;      // [256] histogram, then the bucket cursors of the running pass
+    POS *start;         // [levels][kBtRow]
 };
 
 // rank sort (== the reference's insertion sort, ksort.h:105-115: stable) of every bucket of 2..64 elements of one pass;
 // start = bucket boundaries of that pass (257 entries), or nullptr to sort [lo, hi) as ONE bucket.
-template <class KO, bool PAY>
-__device__ void bt_rank_sort(typename KO::T *A, unsigned short *pay, typename KO::T *tmpA, unsigned short *tmpPay, int lo, int hi,
-                             int shift, const unsigned short *start, int lane)
+template <class KO, bool PAY, class PAYT, class POS>
+__device__ void bt_rank_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT *tmpPay, int lo, int hi,
+                             int shift, const POS *start, int lane)
 {
     typedef typename KO::T K;
     for (int e0 = lo; e0 < hi; e0 += 32) {
@@ -65,7 +84,7 @@ __device__ void bt_rank_sort(typename KO::T *A, unsigned short *pay, typename KO
         if (e < hi) {
             const K key = A[e];
             int bs = lo, be = hi;
-            if (start) { const unsigned d = KO::digit(key, shift); bs = start[d]; be = start[d + 1]; }
+            if (start) { const unsigned d = KO::digit(key, shift); bs = (int)start[d]; be = (int)start[d + 1]; }
             const int m = be - bs;
             if (m >= 2 && m <= 64) {
                 int r = 0;
@@ -90,8 +109,8 @@ __device__ void bt_rank_sort(typename KO::T *A, unsigned short *pay, typename KO
 }
 
 // One American-flag pass over A[lo, hi) on digit `shift` (ksort.h:116-139), bucket boundaries -> st[0..256].
-template <class KO, bool PAY>
-__device__ void bt_flag_pass(typename KO::T *A, unsigned short *pay, int lo, int hi, int shift, unsigned *cnt, unsigned short *st, int lane)
+template <class KO, bool PAY, class PAYT, class POS>
+__device__ void bt_flag_pass(typename KO::T *A, PAYT *pay, int lo, int hi, int shift, unsigned *cnt, POS *st, int lane)
 {
     typedef typename KO::T K;
     const unsigned full = 0xffffffffu;
@@ -113,16 +132,16 @@ __device__ void bt_flag_pass(typename KO::T *A, unsigned short *pay, int lo, int
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            st[lane * 8 + q] = (unsigned short)run;
+            st[lane * 8 + q] = (POS)run;
             cnt[lane * 8 + q] = run;        // cursor of the bucket
             run += c[q];
         }
-        if (lane == 31) st[256] = (unsigned short)hi;
+        if (lane == 31) st[256] = (POS)hi;
     }
     __syncwarp();
-    // buckets in ascending order; everything below is warp-uniform (all lanes read the same shared values)
+    // buckets in ascending order; everything below is warp-uniform (all lanes read the same values)
     for (int k = 0; k < 256; ++k) {
-        const int endk = st[k + 1];
+        const int endk = (int)st[k + 1];
         int c = (int)cnt[k];
         while (c < endk) {
             // elements that already sit in their home bucket stay where they are
@@ -132,10 +151,10 @@ __device__ void bt_flag_pass(typename KO::T *A, unsigned short *pay, int lo, int
             if (!mm) { c = min(c + 32, endk); continue; }
             c += __ffs(mm) - 1;
             K carried = A[c];
-            unsigned short cpay = PAY ? pay[c] : (unsigned short)0;
+            PAYT cpay = PAY ? pay[c] : (PAYT)0;
             unsigned d = KO::digit(carried, shift);
             do {
-                const int pos = (int)cnt[d], endd = st[d + 1];
+                const int pos = (int)cnt[d], endd = (int)st[d + 1];
                 // elements of bucket d sitting at its cursor are pushed one slot to the right (each is evicted by the
                 // arriving element and re-placed at the next slot); the first foreign element after them is evicted for good
                 int L = 0;
@@ -148,11 +167,11 @@ __device__ void bt_flag_pass(typename KO::T *A, unsigned short *pay, int lo, int
                     break;
                 }
                 const K evicted = A[pos + L];
-                const unsigned short epay = PAY ? pay[pos + L] : (unsigned short)0;
+                const PAYT epay = PAY ? pay[pos + L] : (PAYT)0;
                 for (int top = L; top > 0; top -= 32) { // shift A[pos .. pos+L) up by one, highest chunk first
                     const int base = max(0, top - 32), idx = base + lane;
                     K val = 0;
-                    unsigned short pv = 0;
+                    PAYT pv = 0;
                     if (idx < top) { val = A[pos + idx]; if (PAY) pv = pay[pos + idx]; }
                     __syncwarp();
                     if (idx < top) { A[pos + idx + 1] = val; if (PAY) pay[pos + idx + 1] = pv; }
@@ -177,12 +196,12 @@ __device__ void bt_flag_pass(typename KO::T *A, unsigned short *pay, int lo, int
 }
 
 // radix_sort_128x (ksort.h:146-150) of A[0, n) by KO's key, payload in tandem.  tmpA/tmpPay: scratch of the same size.
-template <class KO, bool PAY>
-__device__ void bt_sort(typename KO::T *A, unsigned short *pay, typename KO::T *tmpA, unsigned short *tmpPay, int n, BtSortScratch sc, int lane)
+template <class KO, bool PAY, class PAYT, class POS>
+__device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT *tmpPay, int n, BtSortScratch<POS> sc, int lane)
 {
     const unsigned full = 0xffffffffu;
     if (n <= 1) return;
-    if (n <= 64) { bt_rank_sort<KO, PAY>(A, pay, tmpA, tmpPay, 0, n, 0, nullptr, lane); return; }
+    if (n <= 64) { bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, 0, n, 0, nullptr, lane); return; }
     // Passes in which every key has the same digit are the identity (one bucket, nothing moves, recursion continues on the
     // whole range): start at the highest digit in which the keys differ (same shortcut as backtrack.cpp).
     unsigned long long o = 0, an = ~0ULL;
@@ -195,15 +214,15 @@ __device__ void bt_sort(typename KO::T *A, unsigned short *pay, typename KO::T *
     while (((diff >> shift) & 255ULL) == 0) shift -= 8;
     // depth-first over buckets of more than 64 elements; the explicit stack lives in the per-level rows of `start`
     int lv = 0;
-    unsigned short *row = sc.start;
-    bt_flag_pass<KO, PAY>(A, pay, 0, n, shift, sc.cnt, row, lane);
-    if (shift) bt_rank_sort<KO, PAY>(A, pay, tmpA, tmpPay, 0, n, shift, row, lane);
-    if (lane == 0) { row[257] = 0; row[258] = (unsigned short)shift; }
+    POS *row = sc.start;
+    bt_flag_pass<KO, PAY, PAYT, POS>(A, pay, 0, n, shift, sc.cnt, row, lane);
+    if (shift) bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, 0, n, shift, row, lane);
+    if (lane == 0) { row[257] = 0; row[258] = (POS)shift; }
     __syncwarp();
     while (lv >= 0) {
         row = sc.start + lv * kBtRow;
-        const int sh = row[258];
-        int k = row[257];
+        const int sh = (int)row[258];
+        int k = (int)row[257];
         if (sh == 0 || k >= 256) { --lv; continue; }
         // next bucket of this level with more than 64 elements
         int found = -1;
@@ -216,17 +235,24 @@ __device__ void bt_sort(typename KO::T *A, unsigned short *pay, typename KO::T *
         }
         __syncwarp();
         if (found < 0) { if (lane == 0) row[257] = 256; __syncwarp(); --lv; continue; }
-        if (lane == 0) row[257] = (unsigned short)(found + 1);
-        const int blo = row[found], bhi = row[found + 1];
+        if (lane == 0) row[257] = (POS)(found + 1);
+        const int blo = (int)row[found], bhi = (int)row[found + 1];
         const int nsh = sh > 8 ? sh - 8 : 0;
         ++lv;
-        unsigned short *crow = sc.start + lv * kBtRow;
+        POS *crow = sc.start + lv * kBtRow;
         __syncwarp();
-        bt_flag_pass<KO, PAY>(A, pay, blo, bhi, nsh, sc.cnt, crow, lane);
-        if (nsh) bt_rank_sort<KO, PAY>(A, pay, tmpA, tmpPay, blo, bhi, nsh, crow, lane);
-        if (lane == 0) { crow[257] = 0; crow[258] = (unsigned short)nsh; }
+        bt_flag_pass<KO, PAY, PAYT, POS>(A, pay, blo, bhi, nsh, sc.cnt, crow, lane);
+        if (nsh) bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, blo, bhi, nsh, crow, lane);
+        if (lane == 0) { crow[257] = 0; crow[258] = (POS)nsh; }
         __syncwarp();
     }
+}
+
+// a read the shared-memory kernels cannot finish goes to the global-memory ones through this list
+__device__ __forceinline__ void bt_overflow(int r, int *ovf_list, Counters *ctr)
+{
+    const int k = atomicAdd(&ctr->ovf_cnt, 1);
+    if (k < kBtOvfCap) ovf_list[k] = r;     // beyond the cap the read stays declined (n_u = -1: host implementation)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -234,7 +260,7 @@ __device__ void bt_sort(typename KO::T *A, unsigned short *pay, typename KO::T *
 // amounts of shared memory: the sort needs 8 bytes per anchor for a few microseconds, the walk only ~3.5 bytes per anchor
 // for much longer (it is a serial pointer chase) -- so three times as many walks as sorts fit on an SM.
 //   k_bt_sort : z[] = anchors scoring >= min_sc, sorted as the reference sorts them  -> zs_scr (global), nz_out
-//   k_bt_walk : chain extraction in that order + compaction                          -> n_u, n_b, b_out, u_pack
+//   k_bt_walk : chain extraction in that order + compaction                          -> n_u, n_b, b_pack, u_pack
 // ---------------------------------------------------------------------------------------------------------------------
 template <int CAP>
 struct BtSortSmem {
@@ -244,23 +270,14 @@ struct BtSortSmem {
     unsigned short start[3 * kBtRow];   // scores are below 2^19: at most three radix levels
 };
 
-template <int CAP>
-__global__ void __launch_bounds__(32)
-k_bt_sort(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
-          unsigned *__restrict__ zs_scr, int *__restrict__ nz_out)
+// z[]: anchors scoring >= min_sc, in index order (lchain.c:33-40); 4 coalesced loads per lane in flight.  Returns nz; the
+// largest kept score in fmax.
+template <class ZK>
+__device__ __forceinline__ int bt_collect(const int *__restrict__ fr, int n, int min_sc, typename ZK::T *zk, int lane, int &fmax)
 {
-    extern __shared__ int4 bt_raw[];
-    BtSortSmem<CAP> &S = *reinterpret_cast<BtSortSmem<CAP> *>(bt_raw);
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    if ((int)blockIdx.x >= n_list) return;
-    const int r = read_list[blockIdx.x];
-    const long long o0 = off[r];
-    const int n = (int)(off[r + 1] - o0);
-    const int *fr = f + o0;
-    if (n > CAP || bp.min_sc < 0) { if (lane == 0) nz_out[r] = -1; return; }
-    // z[]: anchors scoring >= min_sc, in index order (lchain.c:33-40); 4 coalesced loads per lane in flight
-    int nz = 0, fmax = 0;
+    int nz = 0;
+    fmax = 0;
     for (int i0 = 0; i0 < n; i0 += 128) {
         int fv[4];
 #pragma unroll
@@ -268,22 +285,77 @@ k_bt_sort(const int *__restrict__ f, const long long *__restrict__ off, const in
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int i = i0 + t * 32 + lane;
-            const bool keep = fv[t] >= bp.min_sc && i < n;
+            const bool keep = fv[t] >= min_sc && i < n;
             const unsigned m = __ballot_sync(full, keep);
-            if (keep) S.zk[nz + __popc(m & ((1u << lane) - 1u))] = ((unsigned)fv[t] << kBtIdxBits) | (unsigned)i;
+            if (keep) zk[nz + __popc(m & ((1u << lane) - 1u))] = ZK::make(fv[t], i);
             nz += __popc(m);
             fmax = max(fmax, keep ? fv[t] : 0);
         }
     }
     fmax = __reduce_max_sync(full, fmax);
-    if (fmax >= kBtMaxScore) { if (lane == 0) nz_out[r] = -1; return; }   // does not pack into 32 bits: host path
+    return nz;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(32)
+k_bt_sort(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
+          unsigned *__restrict__ zs_scr, int *__restrict__ nz_out, int *__restrict__ ovf_list, Counters *__restrict__ ctr)
+{
+    extern __shared__ int4 bt_raw[];
+    BtSortSmem<CAP> &S = *reinterpret_cast<BtSortSmem<CAP> *>(bt_raw);
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_list) return;
+    const int r = read_list[blockIdx.x];
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    const int *fr = f + o0;
+    if (n > CAP || bp.min_sc < 0) { if (lane == 0) nz_out[r] = -1; return; }
+    int fmax;
+    const int nz = bt_collect<ZKey>(fr, n, bp.min_sc, S.zk, lane, fmax);
+    if (fmax >= kBtMaxScore) { // does not pack into 32 bits: the 64-bit kernels take the read
+        if (lane == 0) { nz_out[r] = -1; bt_overflow(r, ovf_list, ctr); }
+        return;
+    }
     __syncwarp();
-    BtSortScratch sc;
+    BtSortScratch<unsigned short> sc;
     sc.cnt = S.cnt;
     sc.start = S.start;
-    bt_sort<ZKey, false>(S.zk, nullptr, S.zk2, nullptr, nz, sc, lane);
+    bt_sort<ZKey, false, unsigned short, unsigned short>(S.zk, nullptr, S.zk2, nullptr, nz, sc, lane);
     unsigned *zo = zs_scr + o0;
     for (int e = lane; e < nz; e += 32) zo[e] = S.zk[e];
+    if (lane == 0) nz_out[r] = nz;
+}
+
+// the read of CTA b: from the host's list, or (ovf != nullptr) from the device-side overflow list
+__device__ __forceinline__ int bt_big_read(const int *__restrict__ read_list, int n_list, const int *ovf_list, const Counters *ctr)
+{
+    const int b = (int)blockIdx.x;
+    if (ovf_list) return b < min(ctr->ovf_cnt, kBtOvfCap) ? ovf_list[b] : -1;
+    return b < n_list ? read_list[b] : -1;
+}
+
+// The same for reads of any size / score range: keys are 64 bit and live in global scratch (zk, zk2: one u64 per anchor each).
+__global__ void __launch_bounds__(32)
+k_bt_sort_big(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list,
+              const int *ovf_list, const Counters *ctr, BtParams bp, unsigned long long *zk_scr, unsigned long long *zk2_scr,
+              int *__restrict__ nz_out)
+{
+    __shared__ unsigned s_cnt[256];
+    __shared__ unsigned s_start[4 * kBtRow];    // scores are below 2^31: at most four radix levels
+    const int lane = threadIdx.x;
+    const int r = bt_big_read(read_list, n_list, ovf_list, ctr);
+    if (r < 0) return;
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    if (bp.min_sc < 0) { if (lane == 0) nz_out[r] = -1; return; }
+    unsigned long long *zk = zk_scr + o0, *zk2 = zk2_scr + o0;
+    int fmax;
+    const int nz = bt_collect<ZKey64>(f + o0, n, bp.min_sc, zk, lane, fmax);
+    __syncwarp();
+    BtSortScratch<unsigned> sc;
+    sc.cnt = s_cnt;
+    sc.start = s_start;
+    bt_sort<ZKey64, false, unsigned, unsigned>(zk, nullptr, zk2, nullptr, nz, sc, lane);
     if (lane == 0) nz_out[r] = nz;
 }
 
@@ -300,76 +372,132 @@ struct BtWalkSmem {
     unsigned short start[kBtLevels * kBtRow];
 };
 
-// inputs : a, f, p (p = predecessor index inside the read, -1 none), off, zs_scr / nz (from k_bt_sort)
-// scratch: v_scr (int per anchor; the chains' anchor indices in emission order), u_scr (u64 per anchor), vs_scr (int per anchor)
-// outputs: per read r  n_u[r] (-1 = declined), n_b[r];  b_out[off[r] .. off[r] + n_b) = compacted anchors;  the n_u chains
-//          (score << 32 | count) at u_pack[u_pos[r] ..], a packed array shared by the batch (slots handed out by an atomic
-//          cursor, so only a short prefix has to be downloaded); a read whose chains do not fit u_cap is declined
+// ---- where the walk keeps its state: shared memory (reads of <= CAP anchors) ...
 template <int CAP>
-__global__ void __launch_bounds__(32)
-k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
-          const int *__restrict__ read_list, int n_list, BtParams bp, const unsigned *__restrict__ zs_scr, const int *__restrict__ nz_in,
-          int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_out,
-          int *__restrict__ n_u_out, int *__restrict__ n_b_out, unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ u_cur,
-          int *__restrict__ u_pos)
-{
-    extern __shared__ int4 bt_raw[];
-    BtWalkSmem<CAP> &S = *reinterpret_cast<BtWalkSmem<CAP> *>(bt_raw);
-    constexpr int WC = BtWalkSmem<CAP>::WC;
-    constexpr int SENT = CAP;       // "no predecessor"
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    if ((int)blockIdx.x >= n_list) return;
-    const int r = read_list[blockIdx.x];
-    const long long o0 = off[r];
-    const int n = (int)(off[r + 1] - o0);
-    const int nz = nz_in[r];
-    if (nz < 0) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
-    if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; } return; }
-    const int *fr = f + o0, *pr = p + o0;
-    const uint4 *ar = a + o0;
-    const unsigned *zs = zs_scr + o0;
-    int *vr = v_scr + o0, *vsr = vs_scr + o0;
-    unsigned long long *ur = u_scr + o0;
-    uint4 *bo = b_out + o0;
-
-    // ---- p by index, sign of the link gains, cleared claim bits ------------------------------------------------------------
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        int pi = -1, fi = 0, fp = 0;
-        if (i < n) { pi = pr[i]; fi = fr[i]; }
-        if (pi >= 0) fp = fr[pi];
-        if (i < n) S.ps[i] = pi < 0 ? (unsigned short)SENT : (unsigned short)pi;
-        const unsigned g = __ballot_sync(full, i < n && fi - fp > 0);
-        if (lane == 0) { S.gp[i0 >> 5] = g; S.tb[i0 >> 5] = 0; }
+struct WalkSmall {
+    typedef ZKey ZK;
+    typedef unsigned short IDX;     // anchor index / chain id
+    typedef unsigned short POS;
+    BtWalkSmem<CAP> &S;
+    const unsigned *zs;
+    __device__ __forceinline__ WalkSmall(BtWalkSmem<CAP> &s, const unsigned *z) : S(s), zs(z) {}
+    __device__ __forceinline__ int sent() const { return CAP; }
+    __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
+    __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
+    {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            int pi = -1, fi = 0, fp = 0;
+            if (i < n) { pi = pr[i]; fi = fr[i]; }
+            if (pi >= 0) fp = fr[pi];
+            if (i < n) S.ps[i] = pi < 0 ? (unsigned short)CAP : (unsigned short)pi;
+            const unsigned g = __ballot_sync(0xffffffffu, i < n && fi - fp > 0);
+            if (lane == 0) { S.gp[i0 >> 5] = g; S.tb[i0 >> 5] = 0; }
+        }
+        if (lane == 0) { S.ps[CAP] = (unsigned short)CAP; S.tb[CAP / 32] = 0; }
     }
-    if (lane == 0) { S.ps[SENT] = (unsigned short)SENT; S.tb[CAP / 32] = 0; }
+    __device__ __forceinline__ int nextp(int cur) const { return S.ps[cur]; }
+    __device__ __forceinline__ bool claimed(int i) const { return ((S.tb[i >> 5] >> (i & 31)) & 1u) != 0; }
+    __device__ __forceinline__ void claim(int i) { atomicOr(&S.tb[i >> 5], 1u << (i & 31)); }
+    __device__ __forceinline__ bool gain(int i, const int *, const int *) const { return ((S.gp[i >> 5] >> (i & 31)) & 1u) != 0; }
+    __device__ __forceinline__ unsigned zat(int e) const { return zs[e]; }
+    __device__ __forceinline__ IDX *path() { return S.path; }
+    __device__ __forceinline__ unsigned long long *wk() { return S.wk; }
+    __device__ __forceinline__ unsigned long long *wtmp() { return S.wtmp; }
+    __device__ __forceinline__ IDX *wpay() { return S.wpay; }
+    __device__ __forceinline__ IDX *wpay2() { return S.wpay2; }
+    __device__ __forceinline__ unsigned *cnt() { return S.cnt; }
+    __device__ __forceinline__ POS *start() { return S.start; }
+};
+
+// ---- ... or global scratch (any read).  p[] is read in place, the claimed bits sit in a global bit array, the sorted z[]
+//      and (after the walks, when z[] is dead) the chain-start keys use the read's zk / zk2 scratch.
+struct WalkBig {
+    typedef ZKey64 ZK;
+    typedef int IDX;
+    typedef unsigned POS;
+    int n;
+    const int *pr;
+    unsigned *tb;
+    unsigned long long *zk, *zk2;
+    unsigned *pay, *pay2;
+    int *path_s;
+    unsigned *cnt_s, *start_s;
+    __device__ __forceinline__ int sent() const { return n; }
+    __device__ __forceinline__ int wc() const { return n; }
+    __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
+    {
+        for (int w = lane; w <= (n_ >> 5); w += 32) tb[w] = 0;
+    }
+    __device__ __forceinline__ int nextp(int cur) const
+    {
+        int nx = n;
+        if (cur < n) { const int q = pr[cur]; nx = q < 0 ? n : q; }
+        return nx;
+    }
+    __device__ __forceinline__ bool claimed(int i) const { return ((tb[i >> 5] >> (i & 31)) & 1u) != 0; }
+    __device__ __forceinline__ void claim(int i) { atomicOr(&tb[i >> 5], 1u << (i & 31)); }
+    __device__ __forceinline__ bool gain(int i, const int *fr, const int *prr) const
+    {
+        const int q = prr[i];
+        return fr[i] - (q >= 0 ? fr[q] : 0) > 0;
+    }
+    __device__ __forceinline__ unsigned long long zat(int e) const { return zk[e]; }
+    __device__ __forceinline__ IDX *path() { return path_s; }
+    __device__ __forceinline__ unsigned long long *wk() { return zk; }
+    __device__ __forceinline__ unsigned long long *wtmp() { return zk2; }
+    __device__ __forceinline__ IDX *wpay() { return reinterpret_cast<int *>(pay); }
+    __device__ __forceinline__ IDX *wpay2() { return reinterpret_cast<int *>(pay2); }
+    __device__ __forceinline__ unsigned *cnt() { return cnt_s; }
+    __device__ __forceinline__ POS *start() { return start_s; }
+};
+
+// Chain extraction + compaction of one read by one warp; W = where the state lives (above).
+// inputs : ar / fr / pr = the read's anchors, scores, predecessors (index inside the read, -1 none); nz sorted ends in W
+// scratch: vr (int per anchor; the chains' anchor indices in emission order), ur (u64 per anchor), vsr (int per anchor)
+// outputs: n_u (-1 = declined), n_b, u_pos, b_pos of read r; the n_b compacted anchors at b_pack[b_pos ..] and the n_u chains
+//          (score << 32 | count) at u_pack[u_pos ..]: packed arrays shared by the batch, slots handed out by atomic cursors,
+//          so only what was produced has to leave the device
+template <class W>
+__device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const uint4 *__restrict__ ar, const int *__restrict__ fr,
+                                             const int *__restrict__ pr, BtParams bp, int *vr, unsigned long long *ur, int *vsr,
+                                             uint4 *__restrict__ b_pack, unsigned long long *__restrict__ u_pack, int u_cap,
+                                             int *__restrict__ n_u_out, int *__restrict__ n_b_out, int *__restrict__ u_pos,
+                                             int *__restrict__ b_pos, int *ovf_list, Counters *ctr, int lane)
+{
+    typedef typename W::ZK ZK;
+    typedef typename W::IDX IDX;
+    typedef typename W::POS POS;
+    const unsigned full = 0xffffffffu;
+    const int SENT = S.sent();       // "no predecessor"
+    S.init(n, fr, pr, lane);
     __syncwarp();
 
     // ---- chain extraction, best end first (lchain.c:42-72 with mg_chain_bk_end :9-25) --------------------------------------
     int n_v = 0, n_u = 0;
     int k = nz - 1;
     bool nothing_claimed = true;    // true until the first chain is claimed: its walk needs no claim tests at all
-    unsigned znext = (k - lane >= 0) ? zs[k - lane] : 0u;   // the 32 ends below k, fetched one round ahead
+    typename ZK::T znext = (k - lane >= 0) ? S.zat(k - lane) : (typename ZK::T)0;   // the 32 ends below k, fetched one round ahead
     int knext = k;
+    IDX *path = S.path();
     while (k >= 0) {
         {   // next chain end that is not claimed yet.  Ends whose predecessor is already claimed (or absent) are one-step
             // walks that can only claim themselves (lchain.c:16-22 evaluates p[i] once and stops): a run of them is settled
             // here in parallel, in visiting order; the first end that needs a real walk goes through the general code below.
             const int e = k - lane;
-            unsigned z = 0;
+            typename ZK::T z = 0;
             if (knext == k) z = znext;                     // the prefetched group is exactly this one
-            else if (e >= 0) z = zs[e];
+            else if (e >= 0) z = S.zat(e);
             knext = k - 32;                                // prefetch the group a full step further down
-            znext = (knext - lane >= 0) ? zs[knext - lane] : 0u;
+            znext = (knext - lane >= 0) ? S.zat(knext - lane) : (typename ZK::T)0;
             bool unc = false, simple = false;
             int i0l = 0, n1 = SENT;
             if (e >= 0) {
-                i0l = (int)(z & kBtIdxMask);
-                unc = ((S.tb[i0l >> 5] >> (i0l & 31)) & 1u) == 0;
+                i0l = ZK::idx(z);
+                unc = !S.claimed(i0l);
                 if (unc) {
-                    n1 = S.ps[i0l];
-                    simple = n1 == SENT || ((S.tb[n1 >> 5] >> (n1 & 31)) & 1u) != 0;
+                    n1 = S.nextp(i0l);
+                    simple = n1 == SENT || S.claimed(n1);
                 }
             }
             const unsigned m = __ballot_sync(full, unc);
@@ -379,11 +507,11 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
             const unsigned fastm = nfast >= 32 ? m : (m & ((1u << nfast) - 1u));
             if (fastm) {
                 const bool mine_f = ((fastm >> lane) & 1u) != 0;
-                const bool claim = mine_f && ((S.gp[i0l >> 5] >> (i0l & 31)) & 1u) != 0;   // s_1 > 0: cut = p[i0], chain = {i0}
-                if (claim) atomicOr(&S.tb[i0l >> 5], 1u << (i0l & 31));
+                const bool claim = mine_f && S.gain(i0l, fr, pr);   // s_1 > 0: cut = p[i0], chain = {i0}
+                if (claim) S.claim(i0l);
                 if (__any_sync(full, claim)) nothing_claimed = false;
                 if (bp.min_cnt <= 1) { // single-anchor chains can be accepted: needs the value of s_1
-                    const int keyl = (int)(z >> kBtIdxBits);
+                    const int keyl = ZK::score(z);
                     const int s1 = claim ? (n1 == SENT ? keyl : keyl - fr[n1]) : 0;
                     const bool acc = claim && s1 >= bp.min_sc;
                     const unsigned am = __ballot_sync(full, acc);
@@ -403,12 +531,12 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
             k -= nfast;
             if (!hard) continue;
         }
-        const unsigned zkk = zs[k];
-        const int i0 = (int)(zkk & kBtIdxMask), key = (int)(zkk >> kBtIdxBits);
+        const typename ZK::T zkk = S.zat(k);
+        const int i0 = ZK::idx(zkk), key = ZK::score(zkk);
         // path n_0 = i0, n_1 = p[n_0], ...; node n_j (j >= 1) is "evaluated": s_j = key - f[n_j] (key if n_j is the sentinel).
         // cutj = largest evaluated j whose s_j is a strict new maximum (0 if none): the chain is n_0 .. n_{cutj-1}.
-        // The predecessor chase is the serial part: 32 nodes per batch, one shared-memory load per node (the sentinel points
-        // at itself, so the chase needs no end test); where the walk ends is found afterwards for all 32 nodes at once.
+        // The predecessor chase is the serial part: 32 nodes per batch, one load per node (the sentinel points at itself, so
+        // the chase needs no end test); where the walk ends is found afterwards for all 32 nodes at once.
         int cur = i0, max_s = 0, cutj = 0, cutnode = i0, j0 = 0;
         int mine0 = SENT; // this lane's node of the first batch (enough to mark chains of <= 32 nodes without re-reading)
         for (;;) {
@@ -418,22 +546,22 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
                 nb = 0;
 #pragma unroll 4
                 for (int b = 0; b < 32; ++b) {
-                    if (lane == 0) S.path[b] = (unsigned short)cur;
+                    if (lane == 0) path[b] = (IDX)cur;
                     nb = b + 1;
-                    const unsigned tw = S.tb[cur >> 5];             // both loads depend on cur only: issued together
-                    const int nxt = S.ps[cur];
-                    if (cur == SENT || (((tw >> (cur & 31)) & 1u) != 0 && b >= 1)) break;
+                    const bool cl = S.claimed(cur);                 // both loads depend on cur only: issued together
+                    const int nxt = S.nextp(cur);
+                    if (cur == SENT || (cl && b >= 1)) break;
                     cur = nxt;
                 }
             } else {
 #pragma unroll
                 for (int b = 0; b < 32; ++b) {
-                    if (lane == 0) S.path[b] = (unsigned short)cur;
-                    cur = S.ps[cur];
+                    if (lane == 0) path[b] = (IDX)cur;
+                    cur = S.nextp(cur);
                 }
             }
             __syncwarp();
-            const int mine = lane < nb ? (int)S.path[lane] : SENT;
+            const int mine = lane < nb ? (int)path[lane] : SENT;
             int fmine = 0;
             if (lane < nb && mine != SENT) fmine = fr[mine];
             __syncwarp();
@@ -442,7 +570,7 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
             const bool ev = j >= 1 && lane < nb;
             int s = INT32_MIN;
             // the walk stops after evaluating a node that is the root's "predecessor" or already claimed (lchain.c:22)
-            const bool stop = ev && (mine == SENT || ((S.tb[mine >> 5] >> (mine & 31)) & 1u) != 0);
+            const bool stop = ev && (mine == SENT || S.claimed(mine));
             if (ev) s = mine == SENT ? key : key - fmine;
             if (lane < nb && mine != SENT && n_v + j < n) vr[n_v + j] = mine;   // speculative: only the first cutj entries count
             // prefix maxima (max_s carried in), exclusive for the tests of lchain.c:20-21
@@ -473,10 +601,10 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
         if (cnt > 0) { // claim n_0 .. n_{cnt-1}  (stays claimed even if the chain is rejected below, as in the reference)
             nothing_claimed = false;
             if (cnt <= 32) {
-                if (lane < cnt) atomicOr(&S.tb[mine0 >> 5], 1u << (mine0 & 31));
+                if (lane < cnt) S.claim(mine0);
             } else {
                 __syncwarp();
-                for (int q = lane; q < cnt; q += 32) { const int nd = vr[n_v + q]; atomicOr(&S.tb[nd >> 5], 1u << (nd & 31)); }
+                for (int q = lane; q < cnt; q += 32) S.claim(vr[n_v + q]);
             }
         }
         __syncwarp();
@@ -489,30 +617,38 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
         --k;
     }
     __syncwarp();
-    if (n_u == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; } return; }
+    if (n_u == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; u_pos[r] = 0; b_pos[r] = 0; } return; }
 
     // ---- compact_a (lchain.c:78-111): chains flipped to ascending order, then ordered by the x of their first anchor with
     //      the same unstable sort (w[i].x = b[k].x, payload = chain id) --------------------------------------------------------
-    if (n_u > WC) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }   // more chains than the key buffer holds: host path
-    int upos = 0;
-    if (lane == 0) upos = atomicAdd(u_cur, n_u);
+    if (n_u > S.wc()) { // more chains than the key buffer holds: the global-memory kernels take the read
+        if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; if (ovf_list) bt_overflow(r, ovf_list, ctr); }
+        return;
+    }
+    int upos = 0, bpos = 0;
+    if (lane == 0) upos = atomicAdd(&ctr->u_cur, n_u);
     upos = __shfl_sync(full, upos, 0);
-    if (upos + n_u > u_cap) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }   // packed chain buffer full: host path
+    if (upos + n_u > u_cap) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }   // cannot happen: u_cap = anchors of the batch
+    if (lane == 0) bpos = atomicAdd(&ctr->b_cur, n_v);
+    bpos = __shfl_sync(full, bpos, 0);
     unsigned long long *uo = u_pack + upos;
+    uint4 *bo = b_pack + bpos;
+    unsigned long long *wk = S.wk();
+    IDX *wpay = S.wpay();
     for (int c = lane; c < n_u; c += 32) {
         const int cntc = (int)(unsigned)ur[c], s0 = vsr[c];
         const uint4 av = ar[vr[s0 + cntc - 1]];
-        S.wk[c] = ((unsigned long long)av.y << 32) | av.x;
-        S.wpay[c] = (unsigned short)c;
+        wk[c] = ((unsigned long long)av.y << 32) | av.x;
+        wpay[c] = (IDX)c;
     }
     __syncwarp();
-    BtSortScratch sc;
-    sc.cnt = S.cnt;
-    sc.start = S.start;
-    bt_sort<WKey, true>(S.wk, S.wpay, S.wtmp, S.wpay2, n_u, sc, lane);
+    BtSortScratch<POS> sc;
+    sc.cnt = S.cnt();
+    sc.start = S.start();
+    bt_sort<WKey, true, IDX, POS>(wk, wpay, S.wtmp(), S.wpay2(), n_u, sc, lane);
     int out = 0;
     for (int c = 0; c < n_u; ++c) {
-        const int src = S.wpay[c];
+        const int src = (int)wpay[c];
         const unsigned long long uv = ur[src];
         const int cntc = (int)(unsigned)uv, s0 = vsr[src];
         if (lane == 0) uo[c] = uv;
@@ -528,7 +664,82 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
         }
         out += cntc;
     }
-    if (lane == 0) { n_u_out[r] = n_u; n_b_out[r] = out; u_pos[r] = upos; }
+    if (lane == 0) { n_u_out[r] = n_u; n_b_out[r] = out; u_pos[r] = upos; b_pos[r] = bpos; }
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(32)
+k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
+          const int *__restrict__ read_list, int n_list, BtParams bp, const unsigned *__restrict__ zs_scr, const int *__restrict__ nz_in,
+          int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_pack,
+          unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
+          int *__restrict__ u_pos, int *__restrict__ b_pos, int *__restrict__ ovf_list, Counters *ctr)
+{
+    extern __shared__ int4 bt_raw[];
+    BtWalkSmem<CAP> &SM = *reinterpret_cast<BtWalkSmem<CAP> *>(bt_raw);
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_list) return;
+    const int r = read_list[blockIdx.x];
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    const int nz = nz_in[r];
+    if (nz < 0) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
+    if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; u_pos[r] = 0; b_pos[r] = 0; } return; }
+    WalkSmall<CAP> S(SM, zs_scr + o0);
+    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
+                 u_pos, b_pos, ovf_list, ctr, lane);
+}
+
+// tb_scr: claimed bits, read r uses the words from (off[r] >> 5) + 2 r on; pay / pay2: one unsigned per anchor each
+__global__ void __launch_bounds__(32)
+k_bt_walk_big(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
+              const int *__restrict__ read_list, int n_list, const int *ovf_list, BtParams bp, unsigned long long *zk_scr,
+              unsigned long long *zk2_scr, const int *__restrict__ nz_in, unsigned *tb_scr, unsigned *pay_scr, unsigned *pay2_scr,
+              int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_pack,
+              unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
+              int *__restrict__ u_pos, int *__restrict__ b_pos, Counters *ctr)
+{
+    __shared__ unsigned s_cnt[256];
+    __shared__ unsigned s_start[kBtLevels * kBtRow];
+    __shared__ int s_path[32];
+    const int lane = threadIdx.x;
+    const int r = bt_big_read(read_list, n_list, ovf_list, ctr);
+    if (r < 0) return;
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    const int nz = nz_in[r];
+    if (nz < 0) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
+    if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; u_pos[r] = 0; b_pos[r] = 0; } return; }
+    WalkBig S;
+    S.n = n;
+    S.pr = p + o0;
+    S.tb = tb_scr + (o0 >> 5) + 2 * (long long)r;
+    S.zk = zk_scr + o0;
+    S.zk2 = zk2_scr + o0;
+    S.pay = pay_scr + o0;
+    S.pay2 = pay2_scr + o0;
+    S.path_s = s_path;
+    S.cnt_s = s_cnt;
+    S.start_s = s_start;
+    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
+                 u_pos, b_pos, nullptr, ctr, lane);
+}
+
+// Packed results -> (mapped, pinned) host memory.  The amounts are only known on the device (the cursors), so this is a
+// kernel rather than a copy-engine transfer of the worst case: a few CTAs keep enough 16-byte stores in flight for PCIe.
+__global__ void __launch_bounds__(256)
+k_drain(const uint4 *__restrict__ src_b, uint4 *__restrict__ dst_b, const unsigned long long *__restrict__ src_u,
+        unsigned long long *__restrict__ dst_u, const Counters *__restrict__ ctr)
+{
+    const int nb = ctr->b_cur, nu = ctr->u_cur;
+    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = t;
+    for (; i + 3 * stride < nb; i += 4 * stride) {
+        const uint4 v0 = __ldg(src_b + i), v1 = __ldg(src_b + i + stride), v2 = __ldg(src_b + i + 2 * stride), v3 = __ldg(src_b + i + 3 * stride);
+        dst_b[i] = v0; dst_b[i + stride] = v1; dst_b[i + 2 * stride] = v2; dst_b[i + 3 * stride] = v3;
+    }
+    for (; i < nb; i += stride) dst_b[i] = __ldg(src_b + i);
+    for (int k = t; k < nu; k += stride) dst_u[k] = __ldg(src_u + k);
 }
 
 } // namespace mm2gb

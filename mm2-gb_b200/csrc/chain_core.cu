@@ -66,25 +66,33 @@ struct Slot {
     int *d_block_cnt = nullptr, *d_block_base = nullptr; unsigned long long *d_block_pairs = nullptr; int *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
     int big_cap = 0;
     Counters *d_ctr = nullptr;
-    // device chain extraction (k_backtrack): compacted anchors (+ chains in the tail of every read's region), scratch, lists
-    uint4 *d_b = nullptr;
+    // device chain extraction (k_bt_sort / k_bt_walk): packed compacted anchors and chains of the batch, scratch, lists
+    uint4 *d_b = nullptr;                    // packed compacted anchors (positions from Counters::b_cur)
     unsigned long long *d_uscr = nullptr;
-    int *d_vs = nullptr, *d_nu = nullptr, *d_nb = nullptr, *d_list = nullptr, *d_upos = nullptr, *d_ucur = nullptr;
-    unsigned long long *d_upack = nullptr;
-    unsigned *d_zs = nullptr;   // sorted (score, index) pairs of every read (k_bt_sort -> k_bt_walk)
+    int *d_vs = nullptr, *d_list = nullptr;
+    int *d_rinfo = nullptr;                  // per read: n_u | n_b | u_pos | b_pos, four arrays of n_reads + 1 ints
+    int *d_nu = nullptr, *d_nb = nullptr, *d_upos = nullptr, *d_bpos = nullptr;   // slices of d_rinfo for the batch in flight
+    unsigned long long *d_upack = nullptr;   // packed chains (positions from Counters::u_cur)
+    unsigned *d_zs = nullptr;   // sorted (score, index) pairs of every read (k_bt_sort -> k_bt_walk); chain ids of the big kernels
     int *d_nz = nullptr;
+    // global-memory scratch of the kernels for reads the shared-memory ones cannot take (k_bt_sort_big / k_bt_walk_big)
+    unsigned long long *d_zk = nullptr, *d_zk2 = nullptr;
+    unsigned *d_tb = nullptr, *d_pay2 = nullptr;
+    int *d_ovf = nullptr;
     size_t u_cap = 0;      // entries of d_upack / h_upack
-    cudaStream_t bt_stream[7] = {nullptr};   // the size classes of k_backtrack run side by side (each is a partial wave)
-    cudaEvent_t bt_fork = nullptr, bt_join[7] = {nullptr};
-    int u_cap_batch = 0;   // entries a batch may use (= what is downloaded)
+    cudaStream_t bt_stream[8] = {nullptr};   // the size classes run side by side (each is a partial wave); [7] = big reads
+    cudaEvent_t bt_fork = nullptr, bt_join[8] = {nullptr};
     // pinned host
     mm2gb_anchor_t *h_a = nullptr;
     long long *h_off = nullptr;
     int *h_f = nullptr, *h_p = nullptr;
     Counters *h_ctr = nullptr;
     mm2gb_anchor_t *h_b = nullptr;
-    int *h_nu = nullptr, *h_nb = nullptr, *h_list = nullptr, *h_upos = nullptr;
+    int *h_rinfo = nullptr, *h_list = nullptr;
+    int *h_nu = nullptr, *h_nb = nullptr, *h_upos = nullptr, *h_bpos = nullptr;   // slices of h_rinfo for the batch in flight
     unsigned long long *h_upack = nullptr;
+    uint4 *h_b_dev = nullptr;                // device views of the mapped pinned result buffers (k_drain writes them)
+    unsigned long long *h_upack_dev = nullptr;
     // state
     bool busy = false;
     int n_reads = 0;
@@ -93,11 +101,13 @@ struct Slot {
     int *user_f = nullptr, *user_p = nullptr;
     bool direct_out = false;
     // chains requested for this batch (device backtracking); where the compacted anchors land
-    bool chains = false, want_fp = true, direct_b = false;
-    mm2gb_anchor_t *user_b = nullptr;
+    bool chains = false, want_fp = true;
+    mm2gb_anchor_t *land_b = nullptr;        // host view of where k_drain puts the packed compacted anchors (h_b or the caller's buffer)
     const mm2gb_anchor_t *src_a = nullptr;   // host anchors of the batch (for reads the device declines)
     std::vector<const uint64_t *> u_ptr;     // per read: its chains (in h_upack, or in `spill` for reads finished on the host)
+    std::vector<const mm2gb_anchor_t *> b_ptr;   // per read: its compacted anchors (in the packed landing buffer)
     std::vector<std::vector<uint64_t>> spill;
+    long long b_total = 0;                   // anchors in the packed landing buffer after finish_chains
 };
 
 } // namespace
@@ -116,6 +126,7 @@ struct mm2gb_ctx {
     int score_blocks = 0;
     size_t score_smem = 0;
     int long_min = INT32_MAX;
+    int drain_blocks = 64;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
     Slot slot[kMaxSlots];
     // profiling (slot 0 only)
     bool profile = false;
@@ -305,34 +316,51 @@ static void launch_backtrack(cudaStream_t s, const uint4 *d_a, const int *d_f, c
                              const BtParams &bp, Slot &sl)
 {
     if (n_list <= 0) return;
-    k_bt_sort<CAP><<<n_list, 32, sizeof(BtSortSmem<CAP>), s>>>(d_f, d_off, list, n_list, bp, sl.d_zs, sl.d_nz);
+    k_bt_sort<CAP><<<n_list, 32, sizeof(BtSortSmem<CAP>), s>>>(d_f, d_off, list, n_list, bp, sl.d_zs, sl.d_nz, sl.d_ovf, sl.d_ctr);
     k_bt_walk<CAP><<<n_list, 32, sizeof(BtWalkSmem<CAP>), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zs, sl.d_nz, sl.d_st /* dead after scoring: v scratch */,
-                                                           sl.d_uscr, sl.d_vs, sl.d_b, sl.d_nu, sl.d_nb, sl.d_upack, sl.u_cap_batch, sl.d_ucur, sl.d_upos);
+                                                           sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos,
+                                                           sl.d_ovf, sl.d_ctr);
 }
 
-// Reads are binned by anchor count into the shared-memory classes of k_backtrack (off_rel is the host copy of the
-// offsets); reads above kBtMaxAnchors keep n_u = -1 and are finished by the host implementation.
+// the global-memory kernels: over the host's list of big reads (ovf == false) or over the device-side overflow list
+static void launch_backtrack_big(cudaStream_t s, const uint4 *d_a, const int *d_f, const int *d_p, const long long *d_off, const int *list, int n_list,
+                                 bool ovf, const BtParams &bp, Slot &sl)
+{
+    const int grid = ovf ? kBtOvfCap : n_list;
+    if (grid <= 0) return;
+    const int *ovf_list = ovf ? sl.d_ovf : nullptr;
+    k_bt_sort_big<<<grid, 32, 0, s>>>(d_f, d_off, list, n_list, ovf_list, sl.d_ctr, bp, sl.d_zk, sl.d_zk2, sl.d_nz);
+    k_bt_walk_big<<<grid, 32, 0, s>>>(d_a, d_f, d_p, d_off, list, n_list, ovf_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_tb, sl.d_zs, sl.d_pay2,
+                                      sl.d_st, sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos, sl.d_ctr);
+}
+
+// the four per-read result arrays of a batch of n_reads reads, device and pinned host side
+static void slice_rinfo(Slot &sl, int n_reads)
+{
+    const size_t rs = (size_t)n_reads + 1;
+    sl.d_nu = sl.d_rinfo; sl.d_nb = sl.d_rinfo + rs; sl.d_upos = sl.d_rinfo + 2 * rs; sl.d_bpos = sl.d_rinfo + 3 * rs;
+    sl.h_nu = sl.h_rinfo; sl.h_nb = sl.h_rinfo + rs; sl.h_upos = sl.h_rinfo + 2 * rs; sl.h_bpos = sl.h_rinfo + 3 * rs;
+}
+
+// Reads are binned by anchor count into the shared-memory classes of k_bt_sort / k_bt_walk (off_rel is the host copy of the
+// offsets); reads above kBtMaxAnchors go to the global-memory kernels, and so does -- through a device-side list -- any read a
+// shared-memory kernel cannot finish (scores that do not pack into 32 bits, more chains than its key buffer holds).
 static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *d_a, const long long *d_off, const long long *off_rel,
                              int n_reads, const int *d_f, const int *d_p, bool prof)
 {
     static const int caps[7] = {1024, 1536, 2048, 3072, 4096, 6144, 8192};
-    int cnt[7] = {0, 0, 0, 0, 0, 0, 0}, base[8], fill[7];
-    for (int r = 0; r < n_reads; ++r) {
-        const long long n = off_rel[r + 1] - off_rel[r];
-        for (int k = 0; k < 7; ++k) if (n <= caps[k]) { ++cnt[k]; break; }
-    }
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, base[9], fill[8];
+    auto cls = [&](long long n) { for (int k = 0; k < 7; ++k) if (n <= caps[k]) return k; return 7; };
+    for (int r = 0; r < n_reads; ++r) ++cnt[cls(off_rel[r + 1] - off_rel[r])];
     base[0] = 0;
-    for (int k = 0; k < 7; ++k) { base[k + 1] = base[k] + cnt[k]; fill[k] = base[k]; }
-    for (int r = 0; r < n_reads; ++r) {
-        const long long n = off_rel[r + 1] - off_rel[r];
-        for (int k = 0; k < 7; ++k) if (n <= caps[k]) { sl.h_list[fill[k]++] = r; break; }
-    }
-    CK(cudaMemsetAsync(sl.d_nu, 0xff, ((size_t)n_reads + 1) * sizeof(int), s));   // -1 = not done by the device
-    CK(cudaMemsetAsync(sl.d_nb, 0, ((size_t)n_reads + 1) * sizeof(int), s));
-    CK(cudaMemsetAsync(sl.d_ucur, 0, sizeof(int), s));
-    // chains of the whole batch are packed into one array; a batch may use (and the host downloads) this many entries
-    sl.u_cap_batch = (int)std::min<size_t>(sl.u_cap, (size_t)(off_rel[n_reads] / 8) + (size_t)8 * n_reads + 64);
-    if (base[7]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[7] * sizeof(int), cudaMemcpyHostToDevice, s));
+    for (int k = 0; k < 8; ++k) { base[k + 1] = base[k] + cnt[k]; fill[k] = base[k]; }
+    for (int r = 0; r < n_reads; ++r) sl.h_list[fill[cls(off_rel[r + 1] - off_rel[r])]++] = r;
+    const size_t rs = (size_t)n_reads + 1;
+    slice_rinfo(sl, n_reads);
+    CK(cudaMemsetAsync(sl.d_nu, 0xff, rs * sizeof(int), s));   // -1 = not done by the device
+    CK(cudaMemsetAsync(sl.d_nb, 0, 3 * rs * sizeof(int), s));
+    CK(cudaMemsetAsync(&sl.d_ctr->ovf_cnt, 0, 3 * sizeof(int), s));   // ovf_cnt, u_cur, b_cur
+    if (base[8]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[8] * sizeof(int), cudaMemcpyHostToDevice, s));
     BtParams bp;
     bp.min_cnt = c->misc.min_cnt;
     bp.min_sc = c->misc.min_score;
@@ -341,12 +369,13 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         // fork: one auxiliary stream per non-empty size class, joined back into the slot's stream
         ProfScope ps(c, T_BACKTRACK, s, prof);
         CK(cudaEventRecord(sl.bt_fork, s));
-        for (int k = 6; k >= 0; --k) { // longest first
+        for (int k = 7; k >= 0; --k) { // longest first
             if (!cnt[k]) continue;
             cudaStream_t bs = sl.bt_stream[k];
             CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
             const int *list = sl.d_list + base[k];
             switch (k) {
+            case 7: launch_backtrack_big(bs, d_a, d_f, d_p, d_off, list, cnt[k], false, bp, sl); break;
             case 6: launch_backtrack<8192>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             case 5: launch_backtrack<6144>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             case 4: launch_backtrack<4096>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
@@ -358,7 +387,17 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
             CK(cudaEventRecord(sl.bt_join[k], bs));
             CK(cudaStreamWaitEvent(s, sl.bt_join[k], 0));
         }
+        // whatever the shared-memory kernels handed over (normally nothing: 256 CTAs that exit at once)
+        if (base[7]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, nullptr, 0, true, bp, sl);
     }
+    CK(cudaGetLastError());
+    return MM2GB_OK;
+}
+
+// packed results of the batch -> mapped pinned host memory (dst_b: device view of where the compacted anchors land)
+static int enqueue_drain(mm2gb_ctx *c, Slot &sl, cudaStream_t s, uint4 *dst_b)
+{
+    k_drain<<<c->drain_blocks, 256, 0, s>>>(sl.d_b, dst_b, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
@@ -380,12 +419,13 @@ static void free_slot(Slot &s)
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
     cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
     cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
-    cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_nu); cudaFree(s.d_nb); cudaFree(s.d_list); cudaFree(s.d_upos); cudaFree(s.d_ucur); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
+    cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_rinfo); cudaFree(s.d_list); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
+    cudaFree(s.d_zk); cudaFree(s.d_zk2); cudaFree(s.d_tb); cudaFree(s.d_pay2); cudaFree(s.d_ovf);
     cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
-    cudaFreeHost(s.h_b); cudaFreeHost(s.h_nu); cudaFreeHost(s.h_nb); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upos); cudaFreeHost(s.h_upack);
+    cudaFreeHost(s.h_b); cudaFreeHost(s.h_rinfo); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
     if (s.bt_fork) cudaEventDestroy(s.bt_fork);
-    for (int k = 0; k < 7; ++k) { if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]); if (s.bt_stream[k]) cudaStreamDestroy(s.bt_stream[k]); }
+    for (int k = 0; k < 8; ++k) { if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]); if (s.bt_stream[k]) cudaStreamDestroy(s.bt_stream[k]); }
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -415,6 +455,10 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
         int r = atoi(e);
         if (r == 256 || r == 512 || r == 1024) c->ring = r;
     }
+    if (const char *e = getenv("MM2GB_DRAIN_BLOCKS")) {
+        int r = atoi(e);
+        if (r >= 1 && r <= 4096) c->drain_blocks = r;
+    }
     int rc = MM2GB_OK;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
@@ -439,7 +483,7 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CKC(cudaEventCreateWithFlags(&s.bt_fork, cudaEventDisableTiming));
-            for (int k = 0; k < 7; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 CKC(cudaStreamCreateWithFlags(&s.bt_stream[k], cudaStreamNonBlocking));
                 CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
             }
@@ -466,21 +510,23 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaMalloc(&s.d_b, n * sizeof(uint4)));
             CKC(cudaMalloc(&s.d_uscr, n * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_vs, n * sizeof(int)));
-            CKC(cudaMalloc(&s.d_nu, ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMalloc(&s.d_nb, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMalloc(&s.d_list, ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_b, n * sizeof(mm2gb_anchor_t)));
-            CKC(cudaMallocHost(&s.h_nu, ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_nb, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMallocHost(&s.h_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_list, ((size_t)max_reads + 1) * sizeof(int)));
-            s.u_cap = n / 8 + (size_t)8 * max_reads + 64;
+            s.u_cap = n;    // a chain has at least one anchor and every anchor is in at most one chain
             CKC(cudaMalloc(&s.d_upack, s.u_cap * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_upos, ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMalloc(&s.d_ucur, sizeof(int)));
             CKC(cudaMalloc(&s.d_zs, n * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_nz, ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
-            CKC(cudaMallocHost(&s.h_upos, ((size_t)max_reads + 1) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_zk, n * sizeof(unsigned long long)));
+            CKC(cudaMalloc(&s.d_zk2, n * sizeof(unsigned long long)));
+            CKC(cudaMalloc(&s.d_pay2, n * sizeof(unsigned)));
+            CKC(cudaMalloc(&s.d_tb, (n / 32 + 2 * (size_t)max_reads + 8) * sizeof(unsigned)));
+            CKC(cudaMalloc(&s.d_ovf, kBtOvfCap * sizeof(int)));
+            CKC(cudaHostGetDevicePointer((void **)&s.h_b_dev, s.h_b, 0));
+            CKC(cudaHostGetDevicePointer((void **)&s.h_upack_dev, s.h_upack, 0));
         }
     }
     *out = c;
@@ -524,8 +570,8 @@ struct Want {
     int *dst_f = nullptr, *dst_p = nullptr;
     bool dst_pinned = false;
     bool chains = false;            // run chain extraction + compaction on the device and download the result
-    mm2gb_anchor_t *dst_b = nullptr;
-    bool dst_b_pinned = false;
+    mm2gb_anchor_t *dst_b = nullptr; // mapped pinned landing area for the packed compacted anchors (nullptr: the slot's own) ...
+    uint4 *dst_b_dev = nullptr;      // ... and its device view
 };
 
 // enqueue one batch whose anchors already sit in host memory `src` (pinned: direct DMA; else staged through h_a)
@@ -551,14 +597,14 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
     s.chains = w.chains;
     s.want_fp = w.fp;
     s.src_a = h_src;
+    slice_rinfo(s, n_reads);
     if (w.chains && n_total) {
         rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, s.h_off, n_reads, s.d_f, s.d_p, prof);
         if (rc) return rc;
     }
     s.direct_out = w.fp && w.dst_pinned && w.dst_f && w.dst_p;
     s.user_f = w.dst_f; s.user_p = w.dst_p;
-    s.direct_b = w.chains && w.dst_b_pinned && w.dst_b;
-    s.user_b = w.dst_b;
+    s.land_b = (w.chains && w.dst_b && w.dst_b_dev) ? w.dst_b : s.h_b;
     {
         ProfScope ps(c, T_D2H, s.stream, prof);
         if (n_total && w.fp) {
@@ -566,11 +612,10 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
             CK(cudaMemcpyAsync(s.direct_out ? w.dst_p : s.h_p, s.d_p, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
         if (n_total && w.chains) {
-            CK(cudaMemcpyAsync(s.h_nu, s.d_nu, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(s.h_nb, s.d_nb, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(s.h_upos, s.d_upos, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(s.h_upack, s.d_upack, (size_t)s.u_cap_batch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(s.direct_b ? w.dst_b : s.h_b, s.d_b, (size_t)n_total * sizeof(uint4), cudaMemcpyDeviceToHost, s.stream));
+            // only what was produced leaves the device: k_drain writes the packed chains / compacted anchors into mapped memory
+            rc = enqueue_drain(c, s, s.stream, s.land_b == s.h_b ? s.h_b_dev : w.dst_b_dev);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(s.h_rinfo, s.d_rinfo, 4 * ((size_t)n_reads + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
         CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
     }
@@ -657,16 +702,19 @@ extern "C" int mm2gb_wait(mm2gb_ctx_t *c, int slot, const int32_t **f, const int
     return MM2GB_OK;
 }
 
-// Chains of a finished batch: device results are used as they are; reads the device declined (n_u = -1: more than 8192
-// anchors, scores that do not pack) are finished here with the host implementation, f/p fetched on demand.
-// After the call  s.h_nu / s.h_nb  hold the counts,  `b` (the slot's or the caller's buffer) the compacted anchors at the read
-// offsets and  s.u_ptr[r]  points at the read's chains (in the packed download, or in `spill` for host-finished reads).
-static int finish_chains(mm2gb_ctx *c, Slot &s, mm2gb_anchor_t *b)
+// Chains of a finished batch: device results are used as they are; reads the device declined (n_u = -1: only with a negative
+// min_score, or if more than kBtOvfCap reads of one batch overflow the shared-memory kernels) are finished here with the host
+// implementation, f/p fetched on demand, their compacted anchors appended to the packed landing buffer.
+// After the call  s.h_nu / s.h_nb  hold the counts,  s.b_ptr[r] / s.u_ptr[r]  point at the read's compacted anchors / chains.
+static int finish_chains(mm2gb_ctx *c, Slot &s)
 {
     const int n_reads = s.n_reads;
     s.u_ptr.assign((size_t)n_reads, nullptr);
+    s.b_ptr.assign((size_t)n_reads, nullptr);
     s.spill.clear();
-    if (!s.n_total) { for (int r = 0; r < n_reads; ++r) s.h_nu[r] = s.h_nb[r] = 0; return MM2GB_OK; }
+    s.b_total = 0;
+    if (!s.n_total) { for (int r = 0; r < n_reads; ++r) s.h_nu[r] = s.h_nb[r] = s.h_bpos[r] = 0; return MM2GB_OK; }
+    s.b_total = s.h_ctr->b_cur;
     const int32_t max_drop = c->misc.is_cdna ? INT32_MAX : c->misc.bw;
     std::vector<int32_t> f, p;
     std::vector<uint64_t> u;
@@ -675,6 +723,7 @@ static int finish_chains(mm2gb_ctx *c, Slot &s, mm2gb_anchor_t *b)
         const long long o = s.h_off[r], n = s.h_off[r + 1] - o;
         if (s.h_nu[r] >= 0) {
             s.u_ptr[(size_t)r] = reinterpret_cast<const uint64_t *>(s.h_upack) + s.h_upos[r];
+            s.b_ptr[(size_t)r] = s.land_b + s.h_bpos[r];
             continue;
         }
         f.resize((size_t)n); p.resize((size_t)n); u.resize((size_t)n); bb.resize((size_t)n);
@@ -684,14 +733,17 @@ static int finish_chains(mm2gb_ctx *c, Slot &s, mm2gb_anchor_t *b)
         const int32_t nu = mm2gb_backtrack(n, f.data(), p.data(), s.src_a + o, c->misc.min_cnt, c->misc.min_score, max_drop, u.data(), bb.data(), &nb);
         s.h_nu[r] = nu;
         s.h_nb[r] = (int)nb;
-        memcpy(b + o, bb.data(), (size_t)nb * sizeof(mm2gb_anchor_t));
+        s.h_bpos[r] = (int)s.b_total;
+        memcpy(s.land_b + s.b_total, bb.data(), (size_t)nb * sizeof(mm2gb_anchor_t));   // fits: every anchor is in at most one chain
+        s.b_ptr[(size_t)r] = s.land_b + s.b_total;
+        s.b_total += nb;
         s.spill.emplace_back(u.begin(), u.begin() + nu);
         s.u_ptr[(size_t)r] = s.spill.back().data();
     }
     return MM2GB_OK;
 }
 
-extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t **b,
+extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t *const **b,
                                  const int32_t **n_b, const int64_t **off, mm2gb_stats_t *stats)
 {
     if (!c || slot < 0 || slot >= c->n_slots) return fail(MM2GB_EARG, "bad argument");
@@ -699,11 +751,11 @@ extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const
     int rc = wait_impl(c, slot);
     if (rc) return rc;
     Slot &s = c->slot[slot];
-    rc = finish_chains(c, s, s.h_b);
+    rc = finish_chains(c, s);
     if (rc) return rc;
     if (u) *u = s.u_ptr.data();
     if (n_u) *n_u = s.h_nu;
-    if (b) *b = s.h_b;
+    if (b) *b = s.b_ptr.data();
     if (n_b) *n_b = s.h_nb;
     if (off) *off = (const int64_t *)s.h_off;
     fill_stats(c, *s.h_ctr, s.n_total, stats);
@@ -720,7 +772,7 @@ extern "C" int mm2gb_slot_busy(mm2gb_ctx_t *c, int slot)
 // (upload / kernels / download of consecutive chunks overlap) and call on_done(slot, r0, r1) as each chunk's results land.
 template <class Done>
 static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p, mm2gb_anchor_t *b,
-                       bool chains, mm2gb_stats_t *stats, Done on_done)
+                       uint4 *b_dev, bool chains, mm2gb_stats_t *stats, Done on_done)
 {
     for (int i = 0; i < c->n_slots; ++i)
         if (c->slot[i].busy) return fail(MM2GB_ESTATE, "slot %d is busy", i);
@@ -729,7 +781,6 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
     w.fp = f && p;
     w.dst_pinned = w.fp && is_pinned(f) && is_pinned(p);
     w.chains = chains;
-    w.dst_b_pinned = chains && b && is_pinned(b);
     const long long total = off[n_reads] - off[0];
     // chunks: enough of them to overlap upload / kernels / download, few enough that a chunk still fills the GPU
     long long target = std::max<long long>(1 << 20, total / std::max(8, c->n_slots + 2) + 1);
@@ -769,7 +820,8 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
         for (int r = r0; r <= r1; ++r) rel[(size_t)(r - r0)] = off[r] - off[r0];
         w.dst_f = w.fp ? f + off[r0] : nullptr;
         w.dst_p = w.fp ? p + off[r0] : nullptr;
-        w.dst_b = b ? b + off[r0] : nullptr;
+        w.dst_b = (b && b_dev) ? b + off[r0] : nullptr;      // a chunk's packed results land where its anchors start
+        w.dst_b_dev = (b && b_dev) ? b_dev + off[r0] : nullptr;
         rc = submit_impl(c, si, a + off[r0], in_pinned, rel.data(), r1 - r0, cnt, w);
         if (rc) return rc;
         slot_r0[si] = r0; slot_r1[si] = r1;
@@ -791,7 +843,7 @@ extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, cons
     if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
     if (stats) memset(stats, 0, sizeof(*stats));
     if (n_reads == 0) return MM2GB_OK;
-    return run_chunked(c, a, off, n_reads, f, p, nullptr, false, stats, [](int, int, int) { return MM2GB_OK; });
+    return run_chunked(c, a, off, n_reads, f, p, nullptr, nullptr, false, stats, [](int, int, int) { return MM2GB_OK; });
 }
 
 // Whole mg_lchain_dp (lchain.c:148-217) for a batch, host-stage variant: device DP, then backtracking + compaction on
@@ -824,7 +876,7 @@ static int chain_host_hoststage(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
                 n_b[r] = nb;
             }
         });
-    int rc = run_chunked(c, a, off, n_reads, f, p, nullptr, false, stats, [&](int, int, int r1) {
+    int rc = run_chunked(c, a, off, n_reads, f, p, nullptr, nullptr, false, stats, [&](int, int, int r1) {
         { std::lock_guard<std::mutex> lk(mu); ready = r1; }
         cv.notify_all();
         return MM2GB_OK;
@@ -838,25 +890,61 @@ static int chain_host_hoststage(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
     return rc;
 }
 
-// Device variant (default): chain extraction + compaction run on the GPU right behind the DP kernels (k_backtrack); the
-// compacted anchors are downloaded straight into `b` (when it is pinned) and only the reads the device declines take the
-// host implementation.  f / p are downloaded only if the caller passes buffers for them.
+// Device variant (default): chain extraction + compaction run on the GPU right behind the DP kernels (k_bt_sort / k_bt_walk)
+// and only their packed result leaves the device.  f / p are downloaded only if the caller passes buffers for them.
+// Output layout of mm2gb_chain_host: read r's compacted anchors at b[off[r] ..], copied there from the slot's landing buffer.
 static int chain_host_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                              uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, mm2gb_stats_t *stats)
 {
-    return run_chunked(c, a, off, n_reads, f, p, b, true, stats, [&](int si, int r0, int r1) {
+    return run_chunked(c, a, off, n_reads, f, p, nullptr, nullptr, true, stats, [&](int si, int r0, int r1) {
         Slot &s = c->slot[si];
-        mm2gb_anchor_t *dst = b + off[r0];
-        mm2gb_anchor_t *land = s.direct_b ? dst : s.h_b;     // where the device results of this chunk are
-        int rc = finish_chains(c, s, land);
+        int rc = finish_chains(c, s);
         if (rc) return rc;
         for (int r = r0; r < r1; ++r) {
             const int k = r - r0;
-            const int64_t o = off[r] - off[r0];
             n_u[r] = s.h_nu[k];
             n_b[r] = s.h_nb[k];
             if (s.h_nu[k] > 0) memcpy(u + off[r], s.u_ptr[(size_t)k], (size_t)s.h_nu[k] * sizeof(uint64_t));
-            if (!s.direct_b && s.h_nb[k] > 0) memcpy(dst + o, s.h_b + o, (size_t)s.h_nb[k] * sizeof(mm2gb_anchor_t));
+            if (s.h_nb[k] > 0) memcpy(b + off[r], s.b_ptr[(size_t)k], (size_t)s.h_nb[k] * sizeof(mm2gb_anchor_t));
+        }
+        return MM2GB_OK;
+    });
+}
+
+// device view of a caller's buffer if it is mapped pinned memory, else nullptr
+static uint4 *mapped_view(mm2gb_anchor_t *b)
+{
+    if (!b || !is_pinned(b)) return nullptr;
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, b, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return reinterpret_cast<uint4 *>(d);
+}
+
+// Packed output: the compacted anchors of read r are b[b_pos[r] .. b_pos[r] + n_b[r]); the reads of one chunk are packed
+// behind each other (in no particular order) starting where the chunk's anchors start in `a`.  With `b` in pinned memory
+// the device writes them there directly and the host only copies the (few) chains.
+extern "C" int mm2gb_chain_host_packed(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, uint64_t *u, int32_t *n_u,
+                                       mm2gb_anchor_t *b, int64_t *b_pos, int64_t *n_b, mm2gb_stats_t *stats)
+{
+    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || !n_u || !n_b || !b_pos) return fail(MM2GB_EARG, "bad argument");
+    if (off[n_reads] > 0 && (!u || !b)) return fail(MM2GB_EARG, "bad argument");
+    if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_reads == 0) return MM2GB_OK;
+    CK(cudaSetDevice(c->device));
+    uint4 *b_dev = mapped_view(b);
+    return run_chunked(c, a, off, n_reads, nullptr, nullptr, b, b_dev, true, stats, [&](int si, int r0, int r1) {
+        Slot &s = c->slot[si];
+        int rc = finish_chains(c, s);
+        if (rc) return rc;
+        mm2gb_anchor_t *dst = b + off[r0];
+        if (s.land_b != dst && s.b_total > 0) memcpy(dst, s.land_b, (size_t)s.b_total * sizeof(mm2gb_anchor_t));
+        for (int r = r0; r < r1; ++r) {
+            const int k = r - r0;
+            n_u[r] = s.h_nu[k];
+            n_b[r] = s.h_nb[k];
+            b_pos[r] = off[r0] + (s.h_nb[k] > 0 ? s.h_bpos[k] : 0);
+            if (s.h_nu[k] > 0) memcpy(u + off[r], s.u_ptr[(size_t)k], (size_t)s.h_nu[k] * sizeof(uint64_t));
         }
         return MM2GB_OK;
     });
@@ -930,23 +1018,26 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
         CK(cudaMemcpyAsync(s.d_a, s.h_a, (size_t)n_total * sizeof(uint4), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_f, s.h_f, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_p, s.h_p, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), s.stream));
         int rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, s.h_off, n_reads, s.d_f, s.d_p, false);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(s.h_nu, s.d_nu, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaMemcpyAsync(s.h_nb, s.d_nb, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaMemcpyAsync(s.h_upos, s.d_upos, (size_t)n_reads * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaMemcpyAsync(s.h_upack, s.d_upack, (size_t)s.u_cap_batch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaMemcpyAsync(s.h_b, s.d_b, (size_t)n_total * sizeof(uint4), cudaMemcpyDeviceToHost, s.stream));
+        s.land_b = s.h_b;
+        rc = enqueue_drain(c, s, s.stream, s.h_b_dev);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.h_rinfo, s.d_rinfo, 4 * ((size_t)n_reads + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
         if (n_declined) for (int r = 0; r < n_reads; ++r) *n_declined += s.h_nu[r] < 0 ? 1 : 0;
+    } else {
+        slice_rinfo(s, n_reads);
     }
-    int rc = finish_chains(c, s, s.h_b);
+    int rc = finish_chains(c, s);
     if (rc) return rc;
     for (int r = 0; r < n_reads; ++r) {
         n_u[r] = s.h_nu[r];
         n_b[r] = s.h_nb[r];
         if (s.h_nu[r] > 0) memcpy(u + off[r], s.u_ptr[(size_t)r], (size_t)s.h_nu[r] * sizeof(uint64_t));
-        if (s.h_nb[r] > 0) memcpy(b + off[r], s.h_b + off[r], (size_t)s.h_nb[r] * sizeof(mm2gb_anchor_t));
+        if (s.h_nb[r] > 0) memcpy(b + off[r], s.b_ptr[(size_t)r], (size_t)s.h_nb[r] * sizeof(mm2gb_anchor_t));
     }
     return MM2GB_OK;
 }

@@ -45,7 +45,8 @@ struct Counters {
     int n_long;             // units routed to k_score_long
     int big_cnt[4];         // units of >= 4096 / 2048 / 1024 / 512 anchors, queued first (longest-first scheduling)
     int qs_max;             // largest q_span in the batch (bounds the chain scores: f <= unit length * qs_max)
-    int pad1;
+    int ovf_cnt;            // reads the shared-memory chain-extraction kernels handed to the global-memory ones
+    int u_cur, b_cur;       // cursors of the packed chain / compacted-anchor outputs of the batch (k_bt_walk)
     unsigned long long n_pairs;
 };
 

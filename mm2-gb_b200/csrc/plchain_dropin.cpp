@@ -160,7 +160,7 @@ void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt
     const int64_t *off = nullptr;
     const uint64_t *const *dev_u = nullptr;
     const int32_t *dev_nu = nullptr, *dev_nb = nullptr;
-    const mm2gb_anchor_t *dev_b = nullptr;
+    const mm2gb_anchor_t *const *dev_b = nullptr;
     if (S.submitted && !g_cfg.host_backtrack) {
         if (mm2gb_wait_chains(S.ctx, S.slot, &dev_u, &dev_nu, &dev_b, &dev_nb, &off, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
     } else if (S.submitted) {
@@ -194,7 +194,7 @@ void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt
         int64_t n_b = 0;
         const uint64_t *src_u = nullptr;
         const mm2gb_anchor_t *src_b = nullptr;
-        if (S.submitted && dev_nu) { n_u = dev_nu[r]; n_b = dev_nb[r]; src_u = dev_u[r]; src_b = dev_b + off[r]; }
+        if (S.submitted && dev_nu) { n_u = dev_nu[r]; n_b = dev_nb[r]; src_u = dev_u[r]; src_b = dev_b[r]; }
         else if (S.submitted) { n_u = S.s_nu[(size_t)r]; n_b = S.s_nb[(size_t)r]; src_u = S.su.data() + off[r]; src_b = S.sb.data() + off[r]; }
         if (n_u > 0) {
             uint64_t *u = (uint64_t *)kmalloc(km, (size_t)n_u * sizeof(uint64_t));

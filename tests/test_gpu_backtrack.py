@@ -37,6 +37,9 @@ def _forest(rng, n, kind):
         f = rng.integers(40, 400000, n)
     elif kind == "cluster":    # large buckets at the top level, ties below
         f = rng.choice([1000, 70000, 140000], n) + rng.integers(0, 3, n) * 256 + rng.integers(0, 4, n)
+    elif kind == "huge":       # scores beyond 2^19: do not pack into the 32-bit keys, four radix levels in the 64-bit kernels
+        f = rng.integers(40, 1 << 30, n)
+        f[rng.random(n) < 0.3] = 1 << 29                      # and a big tie group
     elif kind == "chainlike":  # scores growing along the read with side branches, like real DP output
         f = 15 * (i + 1) - rng.integers(0, 40, n)
         side = rng.random(n) < 0.15
@@ -46,11 +49,11 @@ def _forest(rng, n, kind):
     return f.astype(np.int32), p
 
 
-@pytest.mark.parametrize("kind", ["few", "narrow", "wide", "cluster", "chainlike"])
+@pytest.mark.parametrize("kind", ["few", "narrow", "wide", "cluster", "chainlike", "huge"])
 @pytest.mark.parametrize("min_cnt,min_score", [(3, 40), (1, 1), (2, 60)])
 def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score):
     rng = np.random.default_rng(hash((kind, min_cnt)) % (1 << 31))
-    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 66, 200, 1000, 1024, 1025, 2048, 3000, 4096, 5000, 8192, 8193, 9000]
+    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 66, 200, 1000, 1024, 1025, 2048, 3000, 4096, 5000, 8192, 8193, 9000, 20000, 70001]
     reads, fs, ps = [], [], []
     for n in sizes:
         a = synth.ont_like_anchors(rng, max(n, 1), noise_frac=0.0)[:n]
@@ -63,11 +66,12 @@ def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score):
     off[1:] = np.cumsum(sizes)
     a, f, p = np.concatenate(reads), np.concatenate(fs), np.concatenate(ps)
     misc = pkg.map_ont_misc(min_cnt=min_cnt, min_score=min_score)
-    with pkg.ChainContext(misc, max_anchors=1 << 17, max_reads=64, n_slots=1) as c:
+    with pkg.ChainContext(misc, max_anchors=1 << 18, max_reads=64, n_slots=1) as c:
         u, n_u, b, n_b, nd = c.backtrack_device(a, off, f, p)
     _compare(pkg, misc, a, off, f, p, u, n_u, b, n_b)
-    print(f"declined by the device: {nd} of {len(sizes)} reads")
-    assert nd >= 2   # the two reads above 8192 anchors take the host implementation
+    # reads above 8192 anchors, scores >= 2^19 and reads with more chains than the shared-memory key buffer holds all stay on
+    # the device (k_bt_sort_big / k_bt_walk_big): nothing is handed to the host implementation
+    assert nd == 0
 
 
 def test_drop_and_negative_links(pkg, synth):
@@ -106,6 +110,45 @@ def test_chain_end_to_end_vs_oracle(pkg, po, synth, ctx, seed, n_reads, lo, hi):
             assert np.array_equal(rr["u"][s:s + len(uo)], uo) and np.array_equal(rr["b"][s:s + len(bo)], bo), r
 
 
+def test_more_overflowing_reads_than_the_device_list_holds(pkg, synth):
+    """300 short reads whose scores do not pack into 32 bits: 256 go through the device overflow list, the rest are
+    declined and finished by the host implementation -- results identical either way"""
+    rng = np.random.default_rng(77)
+    n_reads, n = 300, 100
+    a = np.concatenate([synth.ont_like_anchors(rng, n, noise_frac=0.0)[:n] for _ in range(n_reads)])
+    off = (np.arange(n_reads + 1) * n).astype(np.int64)
+    f, p = _forest(rng, n_reads * n, "huge")
+    for r in range(n_reads):   # predecessors must stay inside the read
+        q = p[r * n:(r + 1) * n]
+        q[:] = np.where(q >= r * n, q - r * n, -1)
+    misc = pkg.map_ont_misc()
+    with pkg.ChainContext(misc, max_anchors=1 << 16, max_reads=512, n_slots=1) as c:
+        u, n_u, b, n_b, nd = c.backtrack_device(a, off, f, p)
+    assert nd == n_reads - 256
+    _compare(pkg, misc, a, off, f, p, u, n_u, b, n_b)
+
+
+@pytest.mark.parametrize("seed,n_reads,lo,hi", [(31, 3, 9000, 30000), (32, 1, 70000, 70001)])
+def test_long_reads_end_to_end_vs_oracle(pkg, po, synth, seed, n_reads, lo, hi):
+    """reads above 8192 anchors: DP + chain extraction on the device (global-memory kernels), packed output"""
+    a, off = synth.ont_like_batch(seed, n_reads, lo, hi, repeat_copies=2, repeat_len=40)
+    with pkg.ChainContext(pkg.map_ont_misc(), max_anchors=1 << 18, max_reads=16, n_slots=2) as c:
+        res = c.chain(a, off)
+        resp = c.chain(a, off, packed=True)
+        assert c.backtrack_device(a, off, res["f"], res["p"])[4] == 0
+    prm = po.map_ont_params()
+    for r in range(n_reads):
+        s, e = int(off[r]), int(off[r + 1])
+        fo, pq, _ = po.oracle_dp(prm, a[s:e])
+        uo, bo = po.oracle_backtrack(prm, a[s:e], fo, pq)
+        assert np.array_equal(res["f"][s:e], fo)
+        assert res["n_u"][r] == len(uo) and res["n_b"][r] == len(bo), r
+        assert np.array_equal(res["u"][s:s + len(uo)], uo) and np.array_equal(res["b"][s:s + len(bo)], bo), r
+        q = int(resp["b_pos"][r])
+        assert resp["n_u"][r] == len(uo) and resp["n_b"][r] == len(bo), r
+        assert np.array_equal(resp["u"][s:s + len(uo)], uo) and np.array_equal(resp["b"][q:q + len(bo)], bo), r
+
+
 def test_chain_without_fp_and_pinned_output(pkg, po, synth):
     import torch
     a, off = synth.ont_like_batch(21, 50, 100, 3000)
@@ -118,6 +161,9 @@ def test_chain_without_fp_and_pinned_output(pkg, po, synth):
         with pkg.ChainContext(pkg.map_ont_misc(), max_anchors=1 << 18, max_reads=256, n_slots=3) as c:
             res = c.chain(h_a, off, out=out, want_fp=False)
             ref = c.chain(a, off, n_threads=4)
+            outp = {"b": torch.zeros((n, 2), dtype=torch.int64).pin_memory()}
+            resp = c.chain(h_a, off, out=outp, packed=True)       # device writes the packed anchors into the pinned buffer
+            respn = c.chain(a, off, packed=True)                 # pageable buffers: staged through the slot's pinned memory
     finally:
         del os.environ["MM2GB_CHUNK"]
     assert res["f"] is None
@@ -127,6 +173,19 @@ def test_chain_without_fp_and_pinned_output(pkg, po, synth):
         s = int(off[r])
         assert np.array_equal(res["u"][s:s + res["n_u"][r]], ref["u"][s:s + ref["n_u"][r]])
         assert np.array_equal(b[s:s + res["n_b"][r]], ref["b"][s:s + ref["n_b"][r]])
+    bp = resp["b"].numpy().view(np.uint64)
+    assert int(resp["n_b"].sum()) == int(ref["n_b"].sum())
+    for rr, bb in ((resp, bp), (respn, respn["b"])):
+        assert np.array_equal(rr["n_u"], ref["n_u"]) and np.array_equal(rr["n_b"], ref["n_b"])
+        spans = []
+        for r in range(len(off) - 1):
+            s, q = int(off[r]), int(rr["b_pos"][r])
+            assert np.array_equal(rr["u"][s:s + rr["n_u"][r]], ref["u"][s:s + ref["n_u"][r]])
+            assert np.array_equal(bb[q:q + rr["n_b"][r]], ref["b"][s:s + ref["n_b"][r]])
+            if rr["n_b"][r]:
+                spans.append((q, q + int(rr["n_b"][r])))
+        spans.sort()
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1)), "packed regions overlap"
 
 
 def test_golden_chains_on_device(pkg, ctx, golden_dir):
