@@ -31,6 +31,9 @@ import time
 
 import numpy as np
 
+# one hardware work queue per CUDA stream (the slots + the chain-extraction size classes); must be set before CUDA starts
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402

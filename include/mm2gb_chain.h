@@ -61,6 +61,13 @@ int mm2gb_device_count(void);
  * number of batches that may be in flight (each slot owns a stream, pinned staging and device buffers).
  * Replaces plmem_stream_initialize + plrange/plscore_upload_misc (gpu/plmem.cu:558-624, plchain.cu:470-474). */
 int mm2gb_ctx_create(mm2gb_ctx_t **ctx, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc);
+/* The same with flags: DEVICE_ONLY = no pinned staging and no slot-owned anchor / f / p buffers (only the device-resident
+ * entry points work; for anchor arrays that already live in HBM, e.g. the 500 M-anchor chaining-only benchmark);
+ * NO_CHAINS = no chain-extraction buffers (only the DP entry points work). */
+#define MM2GB_CTX_DEVICE_ONLY 1u
+#define MM2GB_CTX_NO_CHAINS 2u
+int mm2gb_ctx_create_ex(mm2gb_ctx_t **ctx, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc,
+                        unsigned flags);
 void mm2gb_ctx_destroy(mm2gb_ctx_t *ctx);
 int mm2gb_ctx_set_misc(mm2gb_ctx_t *ctx, const mm2gb_misc_t *misc);
 
@@ -124,6 +131,10 @@ int mm2gb_device_stats(mm2gb_ctx_t *ctx, mm2gb_stats_t *stats);
 #define MM2GB_NTIMERS 6
 int mm2gb_profile(mm2gb_ctx_t *ctx, int enable);
 int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launches[MM2GB_NTIMERS]);
+
+/* Diagnostic (tools/drain_probe.py): device -> pinned host of n anchors by k_drain with `blocks` CTAs vs the copy engine,
+ * alone and against a concurrent host -> device copy.  ms[0..4]: drain, memcpy, drain+H2D, memcpy+H2D, H2D alone. */
+int mm2gb_debug_drain(mm2gb_ctx_t *ctx, int64_t n, int blocks, float ms[5]);
 
 /* ---- host stage: backtracking + compaction of one read (lchain.c:27-111) ---------------------------------
  * u[<=n] (score<<32|count, ordered by chain start), b[<=n] compacted anchors.  Returns n_u (>=0); *n_b anchors kept.

@@ -79,6 +79,7 @@ def lib():
         L.mm2gb_last_error.restype = C.c_char_p
         L.mm2gb_device_count.restype = C.c_int
         L.mm2gb_ctx_create.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(Misc)]
+        L.mm2gb_ctx_create_ex.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(Misc), C.c_uint]
         L.mm2gb_ctx_destroy.argtypes = [vp]
         L.mm2gb_ctx_destroy.restype = None
         L.mm2gb_ctx_set_misc.argtypes = [vp, C.POINTER(Misc)]
@@ -126,12 +127,15 @@ def _ptr(x):
 class ChainContext:
     """One chaining context = (GPU, capacity, chaining parameters); mirrors mm2gb_ctx_t."""
 
-    def __init__(self, misc: Misc | None = None, device: int = 0, max_anchors: int = 1 << 22, max_reads: int = 1 << 16, n_slots: int = 2):
+    DEVICE_ONLY, NO_CHAINS = 1, 2
+
+    def __init__(self, misc: Misc | None = None, device: int = 0, max_anchors: int = 1 << 22, max_reads: int = 1 << 16, n_slots: int = 2,
+                 flags: int = 0):
         self.misc = misc if misc is not None else map_ont_misc()
         self._h = C.c_void_p()
         if lib().mm2gb_device_count() <= device:
             raise Mm2gbError(f"no CUDA device {device}: the chaining path is GPU-only (no CPU fallback)")
-        _ck(lib().mm2gb_ctx_create(C.byref(self._h), device, max_anchors, max_reads, n_slots, C.byref(self.misc)))
+        _ck(lib().mm2gb_ctx_create_ex(C.byref(self._h), device, max_anchors, max_reads, n_slots, C.byref(self.misc), flags))
         self.device, self.max_anchors, self.max_reads, self.n_slots = device, max_anchors, max_reads, n_slots
 
     def close(self):

@@ -363,6 +363,7 @@ template <int CAP>
 struct BtWalkSmem {
     static constexpr int WC = CAP / 16 < 64 ? 64 : CAP / 16;   // chains whose start keys can be sorted here
     unsigned long long wk[WC], wtmp[WC];    // chain-start keys (x of the first anchor) + sort scratch
+    int fs[CAP + 1];                        // f[] by anchor index; 0 for the sentinel, so "key - f[n_j]" needs no special case
     unsigned short ps[CAP + 2];             // p[] by anchor index; "none" is the sentinel index CAP, whose own entry is CAP
     unsigned short path[32];                // the nodes of one chase batch
     unsigned tb[CAP / 32 + 1];              // claimed bits (lchain.c: t[]); the sentinel's bit is never set
@@ -385,17 +386,25 @@ struct WalkSmall {
     __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
+        for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight
+            int pv[4], fv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; pv[t] = i < n ? pr[i] : -1; fv[t] = i < n ? fr[i] : 0; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t * 32 + lane;
+                if (i < n) { S.ps[i] = pv[t] < 0 ? (unsigned short)CAP : (unsigned short)pv[t]; S.fs[i] = fv[t]; }
+            }
+        }
+        if (lane == 0) { S.ps[CAP] = (unsigned short)CAP; S.fs[CAP] = 0; S.tb[CAP / 32] = 0; }
+        __syncwarp();
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
-            int pi = -1, fi = 0, fp = 0;
-            if (i < n) { pi = pr[i]; fi = fr[i]; }
-            if (pi >= 0) fp = fr[pi];
-            if (i < n) S.ps[i] = pi < 0 ? (unsigned short)CAP : (unsigned short)pi;
-            const unsigned g = __ballot_sync(0xffffffffu, i < n && fi - fp > 0);
+            const unsigned g = __ballot_sync(0xffffffffu, i < n && S.fs[i] - S.fs[S.ps[i]] > 0);
             if (lane == 0) { S.gp[i0 >> 5] = g; S.tb[i0 >> 5] = 0; }
         }
-        if (lane == 0) { S.ps[CAP] = (unsigned short)CAP; S.tb[CAP / 32] = 0; }
     }
+    __device__ __forceinline__ int fat(int i, const int *) const { return S.fs[i]; }
     __device__ __forceinline__ int nextp(int cur) const { return S.ps[cur]; }
     __device__ __forceinline__ bool claimed(int i) const { return ((S.tb[i >> 5] >> (i & 31)) & 1u) != 0; }
     __device__ __forceinline__ void claim(int i) { atomicOr(&S.tb[i >> 5], 1u << (i & 31)); }
@@ -435,6 +444,7 @@ struct WalkBig {
         if (cur < n) { const int q = pr[cur]; nx = q < 0 ? n : q; }
         return nx;
     }
+    __device__ __forceinline__ int fat(int i, const int *fr) const { return i < n ? fr[i] : 0; }
     __device__ __forceinline__ bool claimed(int i) const { return ((tb[i >> 5] >> (i & 31)) & 1u) != 0; }
     __device__ __forceinline__ void claim(int i) { atomicOr(&tb[i >> 5], 1u << (i & 31)); }
     __device__ __forceinline__ bool gain(int i, const int *fr, const int *prr) const
@@ -481,6 +491,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     int knext = k;
     IDX *path = S.path();
     while (k >= 0) {
+        typename ZK::T zkk;
         {   // next chain end that is not claimed yet.  Ends whose predecessor is already claimed (or absent) are one-step
             // walks that can only claim themselves (lchain.c:16-22 evaluates p[i] once and stops): a run of them is settled
             // here in parallel, in visiting order; the first end that needs a real walk goes through the general code below.
@@ -512,7 +523,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
                 if (__any_sync(full, claim)) nothing_claimed = false;
                 if (bp.min_cnt <= 1) { // single-anchor chains can be accepted: needs the value of s_1
                     const int keyl = ZK::score(z);
-                    const int s1 = claim ? (n1 == SENT ? keyl : keyl - fr[n1]) : 0;
+                    const int s1 = claim ? keyl - S.fat(n1, fr) : 0;
                     const bool acc = claim && s1 >= bp.min_sc;
                     const unsigned am = __ballot_sync(full, acc);
                     if (am) {
@@ -530,8 +541,8 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             }
             k -= nfast;
             if (!hard) continue;
+            zkk = __shfl_sync(full, z, nfast);     // the end that needs a real walk was fetched by lane nfast
         }
-        const typename ZK::T zkk = S.zat(k);
         const int i0 = ZK::idx(zkk), key = ZK::score(zkk);
         // path n_0 = i0, n_1 = p[n_0], ...; node n_j (j >= 1) is "evaluated": s_j = key - f[n_j] (key if n_j is the sentinel).
         // cutj = largest evaluated j whose s_j is a strict new maximum (0 if none): the chain is n_0 .. n_{cutj-1}.
@@ -563,7 +574,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             __syncwarp();
             const int mine = lane < nb ? (int)path[lane] : SENT;
             int fmine = 0;
-            if (lane < nb && mine != SENT) fmine = fr[mine];
+            if (lane < nb) fmine = S.fat(mine, fr);      // 0 for the sentinel
             __syncwarp();
             if (j0 == 0) mine0 = mine;
             const int j = j0 + lane;
@@ -571,7 +582,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             int s = INT32_MIN;
             // the walk stops after evaluating a node that is the root's "predecessor" or already claimed (lchain.c:22)
             const bool stop = ev && (mine == SENT || S.claimed(mine));
-            if (ev) s = mine == SENT ? key : key - fmine;
+            if (ev) s = key - fmine;
             if (lane < nb && mine != SENT && n_v + j < n) vr[n_v + j] = mine;   // speculative: only the first cutj entries count
             // prefix maxima (max_s carried in), exclusive for the tests of lchain.c:20-21
             int pm = ev ? s : INT32_MIN;
@@ -608,7 +619,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             }
         }
         __syncwarp();
-        const int scv = cutnode == SENT ? key : key - fr[cutnode];
+        const int scv = key - S.fat(cutnode, fr);
         if (scv >= bp.min_sc && cnt > 0 && cnt >= bp.min_cnt) {
             if (lane == 0) { ur[n_u] = ((unsigned long long)(unsigned)scv << 32) | (unsigned)cnt; vsr[n_u] = n_v; }
             ++n_u;
@@ -725,9 +736,11 @@ k_bt_walk_big(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
                  u_pos, b_pos, nullptr, ctr, lane);
 }
 
+constexpr int kDrainThreads = 64;   // small CTAs (2 warps x 32 registers) fit next to a resident score kernel of another slot
+
 // Packed results -> (mapped, pinned) host memory.  The amounts are only known on the device (the cursors), so this is a
 // kernel rather than a copy-engine transfer of the worst case: a few CTAs keep enough 16-byte stores in flight for PCIe.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDrainThreads)
 k_drain(const uint4 *__restrict__ src_b, uint4 *__restrict__ dst_b, const unsigned long long *__restrict__ src_u,
         unsigned long long *__restrict__ dst_u, const Counters *__restrict__ ctr)
 {

@@ -47,6 +47,7 @@ extern "C" const char *mm2gb_last_error(void) { return g_err; }
 extern "C" int mm2gb_device_count(void)
 {
     int n = 0;
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);   // see mm2gb_ctx_create_ex
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
@@ -80,8 +81,8 @@ struct Slot {
     unsigned *d_tb = nullptr, *d_pay2 = nullptr;
     int *d_ovf = nullptr;
     size_t u_cap = 0;      // entries of d_upack / h_upack
-    cudaStream_t bt_stream[8] = {nullptr};   // the size classes run side by side (each is a partial wave); [7] = big reads
     cudaEvent_t bt_fork = nullptr, bt_join[8] = {nullptr};
+    int bt_cnt[8] = {0}, bt_base[9] = {0};   // reads per size class of the batch in flight, their ranges in d_list
     // pinned host
     mm2gb_anchor_t *h_a = nullptr;
     long long *h_off = nullptr;
@@ -126,10 +127,19 @@ struct mm2gb_ctx {
     int score_blocks = 0;
     size_t score_smem = 0;
     int long_min = INT32_MAX;
-    int drain_blocks = 64;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
+    bool host_io = true;        // slots own pinned staging + device anchor/f/p buffers (false: device-resident entry points only)
+    bool chains_ok = true;      // slots own the chain-extraction buffers (false: DP entry points only)
+    // The size classes of the chain-extraction kernels run side by side (each is a partial wave) on auxiliary streams shared
+    // by all slots ([7] = big reads): with the slots' own streams that stays below the number of hardware work queues
+    // (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 below), so streams do not alias onto one queue and serialise falsely.
+    cudaStream_t bt_stream[8] = {nullptr};
+    int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
     Slot slot[kMaxSlots];
     // profiling (slot 0 only)
     bool profile = false;
+    bool timeline = false;      // MM2GB_TIMELINE=1: every slot records its stages; dumped (ms since the first event) to stderr
+    cudaEvent_t tl_t0 = nullptr;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tl_pending;   // (slot << 8 | stage, events)
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;
     float prof_ms[MM2GB_NTIMERS] = {0};
@@ -196,6 +206,7 @@ static int config_score(mm2gb_ctx *c, size_t smem)
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_score_units<R, FAST>, kScoreWarps * 32, smem));
     if (nb < 1) return fail(MM2GB_ECUDA, "score kernel does not fit on an SM (smem %zu)", smem);
+    if (const char *e = getenv("MM2GB_SCORE_CTAS")) { const int cap = atoi(e); if (cap >= 1 && cap < nb) nb = cap; }
     c->score_blocks = std::max(c->score_blocks, nb * c->n_sm);
     return MM2GB_OK;
 }
@@ -231,21 +242,44 @@ static void launch_score_ring(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, cons
     }
 }
 
+static thread_local int g_tl_slot = 0;   // slot being enqueued (timeline only)
+
 struct ProfScope {
-    mm2gb_ctx *c; int id; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
-    ProfScope(mm2gb_ctx *c_, int id_, cudaStream_t s_, bool on_) : c(c_), id(id_), s(s_), on(on_)
+    mm2gb_ctx *c; int id; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on, tl;
+    ProfScope(mm2gb_ctx *c_, int id_, cudaStream_t s_, bool on_) : c(c_), id(id_), s(s_), on(on_ && !c_->timeline), tl(c_->timeline)
     {
-        if (!on) return;
+        if (!on && !tl) return;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
+        if (tl && !c->tl_t0) { cudaEventCreate(&c->tl_t0); cudaEventRecord(c->tl_t0, s); }
         cudaEventRecord(e0, s);
     }
     ~ProfScope()
     {
-        if (!on) return;
+        if (!on && !tl) return;
         cudaEventRecord(e1, s);
-        c->ev_pending.push_back({id, {e0, e1}});
+        if (tl) c->tl_pending.push_back({(g_tl_slot << 8) | id, {e0, e1}});
+        else c->ev_pending.push_back({id, {e0, e1}});
     }
 };
+
+static void timeline_dump(mm2gb_ctx *c)
+{
+    static const char *names[] = {"range", "units", "score", "backtrack", "h2d", "d2h"};
+    if (!c->tl_t0) return;
+    cudaDeviceSynchronize();
+    for (auto &pe : c->tl_pending) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->tl_t0, pe.second.first);
+        cudaEventElapsedTime(&b, c->tl_t0, pe.second.second);
+        fprintf(stderr, "TL slot=%d stage=%s t0=%.3f t1=%.3f\n", pe.first >> 8, names[pe.first & 255], a, b);
+        cudaEventDestroy(pe.second.first);
+        cudaEventDestroy(pe.second.second);
+    }
+    c->tl_pending.clear();
+    cudaEventDestroy(c->tl_t0);
+    c->tl_t0 = nullptr;
+    fprintf(stderr, "TL end\n");
+}
 
 static void prof_collect(mm2gb_ctx *c)
 {
@@ -345,22 +379,32 @@ static void slice_rinfo(Slot &sl, int n_reads)
 // Reads are binned by anchor count into the shared-memory classes of k_bt_sort / k_bt_walk (off_rel is the host copy of the
 // offsets); reads above kBtMaxAnchors go to the global-memory kernels, and so does -- through a device-side list -- any read a
 // shared-memory kernel cannot finish (scores that do not pack into 32 bits, more chains than its key buffer holds).
-static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *d_a, const long long *d_off, const long long *off_rel,
-                             int n_reads, const int *d_f, const int *d_p, bool prof)
+// step 1 (before the anchors are uploaded, so this small copy does not queue behind them on the copy engine): bin the reads
+// by size class and upload the per-class read lists
+static int prepare_backtrack(Slot &sl, cudaStream_t s, const long long *off_rel, int n_reads)
 {
     static const int caps[7] = {1024, 1536, 2048, 3072, 4096, 6144, 8192};
-    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, base[9], fill[8];
+    int *cnt = sl.bt_cnt, *base = sl.bt_base, fill[8];
     auto cls = [&](long long n) { for (int k = 0; k < 7; ++k) if (n <= caps[k]) return k; return 7; };
+    for (int k = 0; k < 8; ++k) cnt[k] = 0;
     for (int r = 0; r < n_reads; ++r) ++cnt[cls(off_rel[r + 1] - off_rel[r])];
     base[0] = 0;
     for (int k = 0; k < 8; ++k) { base[k + 1] = base[k] + cnt[k]; fill[k] = base[k]; }
     for (int r = 0; r < n_reads; ++r) sl.h_list[fill[cls(off_rel[r + 1] - off_rel[r])]++] = r;
-    const size_t rs = (size_t)n_reads + 1;
     slice_rinfo(sl, n_reads);
+    if (base[8]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[8] * sizeof(int), cudaMemcpyHostToDevice, s));
+    return MM2GB_OK;
+}
+
+// step 2: the kernels
+static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *d_a, const long long *d_off, int n_reads, const int *d_f,
+                             const int *d_p, bool prof)
+{
+    const int *cnt = sl.bt_cnt, *base = sl.bt_base;
+    const size_t rs = (size_t)n_reads + 1;
     CK(cudaMemsetAsync(sl.d_nu, 0xff, rs * sizeof(int), s));   // -1 = not done by the device
     CK(cudaMemsetAsync(sl.d_nb, 0, 3 * rs * sizeof(int), s));
     CK(cudaMemsetAsync(&sl.d_ctr->ovf_cnt, 0, 3 * sizeof(int), s));   // ovf_cnt, u_cur, b_cur
-    if (base[8]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[8] * sizeof(int), cudaMemcpyHostToDevice, s));
     BtParams bp;
     bp.min_cnt = c->misc.min_cnt;
     bp.min_sc = c->misc.min_score;
@@ -371,7 +415,7 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         CK(cudaEventRecord(sl.bt_fork, s));
         for (int k = 7; k >= 0; --k) { // longest first
             if (!cnt[k]) continue;
-            cudaStream_t bs = sl.bt_stream[k];
+            cudaStream_t bs = c->bt_stream[k];
             CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
             const int *list = sl.d_list + base[k];
             switch (k) {
@@ -397,7 +441,7 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
 // packed results of the batch -> mapped pinned host memory (dst_b: device view of where the compacted anchors land)
 static int enqueue_drain(mm2gb_ctx *c, Slot &sl, cudaStream_t s, uint4 *dst_b)
 {
-    k_drain<<<c->drain_blocks, 256, 0, s>>>(sl.d_b, dst_b, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
+    k_drain<<<c->drain_blocks, kDrainThreads, 0, s>>>(sl.d_b, dst_b, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
@@ -425,7 +469,7 @@ static void free_slot(Slot &s)
     cudaFreeHost(s.h_b); cudaFreeHost(s.h_rinfo); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
     if (s.bt_fork) cudaEventDestroy(s.bt_fork);
-    for (int k = 0; k < 8; ++k) { if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]); if (s.bt_stream[k]) cudaStreamDestroy(s.bt_stream[k]); }
+    for (int k = 0; k < 8; ++k) if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -434,11 +478,19 @@ static void free_slot(Slot &s)
 
 extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc)
 {
+    return mm2gb_ctx_create_ex(out, device, max_anchors, max_reads, n_slots, misc, 0);
+}
+
+extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc,
+                                   unsigned flags)
+{
     if (!out || !misc) return fail(MM2GB_EARG, "null argument");
     *out = nullptr;
     if (n_slots < 1 || n_slots > kMaxSlots) return fail(MM2GB_EARG, "n_slots must be 1..%d", kMaxSlots);
     if (max_anchors == 0 || max_anchors > (size_t)INT32_MAX - 1024) return fail(MM2GB_EARG, "max_anchors must be in (0, 2^31)");
     if (max_reads < 1) return fail(MM2GB_EARG, "max_reads must be positive");
+    // one hardware work queue per stream (default is 8 for the whole process); only effective before CUDA is initialised
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
@@ -448,6 +500,8 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
     c->max_anchors = max_anchors;
     c->max_reads = max_reads;
     c->n_slots = n_slots;
+    c->host_io = !(flags & MM2GB_CTX_DEVICE_ONLY);
+    c->chains_ok = !(flags & MM2GB_CTX_NO_CHAINS);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
@@ -455,6 +509,7 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
         int r = atoi(e);
         if (r == 256 || r == 512 || r == 1024) c->ring = r;
     }
+    if (const char *e = getenv("MM2GB_TIMELINE")) c->timeline = atoi(e) != 0;
     if (const char *e = getenv("MM2GB_DRAIN_BLOCKS")) {
         int r = atoi(e);
         if (r >= 1 && r <= 4096) c->drain_blocks = r;
@@ -476,6 +531,8 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
         if (rc) goto bad;
         rc = config_backtrack();
         if (rc) goto bad;
+        if (c->chains_ok)
+            for (int k = 0; k < 8; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
         const size_t n = max_anchors, n_groups = (n + 31) / 32, n_blocks = (n + kRangeThreads - 1) / kRangeThreads;
         const size_t n_units_cap = n_groups + (size_t)max_reads + 2;
         for (int i = 0; i < n_slots; ++i) {
@@ -483,15 +540,12 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CKC(cudaEventCreateWithFlags(&s.bt_fork, cudaEventDisableTiming));
-            for (int k = 0; k < 8; ++k) {
-                CKC(cudaStreamCreateWithFlags(&s.bt_stream[k], cudaStreamNonBlocking));
-                CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
-            }
-            CKC(cudaMalloc(&s.d_a, n * sizeof(uint4)));
+            for (int k = 0; k < 8; ++k) CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
+            if (c->host_io) CKC(cudaMalloc(&s.d_a, n * sizeof(uint4)));
             CKC(cudaMalloc(&s.d_off, ((size_t)max_reads + 1) * sizeof(long long)));
             CKC(cudaMalloc(&s.d_st, n * sizeof(int)));
-            CKC(cudaMalloc(&s.d_f, n * sizeof(int)));
-            CKC(cudaMalloc(&s.d_p, n * sizeof(int)));
+            if (c->host_io) CKC(cudaMalloc(&s.d_f, n * sizeof(int)));
+            if (c->host_io) CKC(cudaMalloc(&s.d_p, n * sizeof(int)));
             CKC(cudaMalloc(&s.d_selmask, n_groups * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_clipmask, n_groups * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_block_cnt, n_blocks * sizeof(int)));
@@ -502,31 +556,32 @@ extern "C" int mm2gb_ctx_create(mm2gb_ctx_t **out, int device, size_t max_anchor
             s.big_cap = (int)(n / kBigMin) + 2;
             CKC(cudaMalloc(&s.d_big_order, (size_t)4 * s.big_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_ctr, sizeof(Counters)));
-            CKC(cudaMallocHost(&s.h_a, n * sizeof(mm2gb_anchor_t)));
+            if (c->host_io) CKC(cudaMallocHost(&s.h_a, n * sizeof(mm2gb_anchor_t)));
             CKC(cudaMallocHost(&s.h_off, ((size_t)max_reads + 1) * sizeof(long long)));
-            CKC(cudaMallocHost(&s.h_f, n * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_p, n * sizeof(int)));
+            if (c->host_io) CKC(cudaMallocHost(&s.h_f, n * sizeof(int)));
+            if (c->host_io) CKC(cudaMallocHost(&s.h_p, n * sizeof(int)));
             CKC(cudaMallocHost(&s.h_ctr, sizeof(Counters)));
+            if (!c->chains_ok) continue;
             CKC(cudaMalloc(&s.d_b, n * sizeof(uint4)));
             CKC(cudaMalloc(&s.d_uscr, n * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_vs, n * sizeof(int)));
             CKC(cudaMalloc(&s.d_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMalloc(&s.d_list, ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_b, n * sizeof(mm2gb_anchor_t)));
+            if (c->host_io) CKC(cudaMallocHost(&s.h_b, n * sizeof(mm2gb_anchor_t)));
             CKC(cudaMallocHost(&s.h_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_list, ((size_t)max_reads + 1) * sizeof(int)));
             s.u_cap = n;    // a chain has at least one anchor and every anchor is in at most one chain
             CKC(cudaMalloc(&s.d_upack, s.u_cap * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_zs, n * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_nz, ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
+            if (c->host_io) CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_zk, n * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_zk2, n * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_pay2, n * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_tb, (n / 32 + 2 * (size_t)max_reads + 8) * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_ovf, kBtOvfCap * sizeof(int)));
-            CKC(cudaHostGetDevicePointer((void **)&s.h_b_dev, s.h_b, 0));
-            CKC(cudaHostGetDevicePointer((void **)&s.h_upack_dev, s.h_upack, 0));
+            if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_b_dev, s.h_b, 0));
+            if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_upack_dev, s.h_upack, 0));
         }
     }
     *out = c;
@@ -542,6 +597,7 @@ extern "C" void mm2gb_ctx_destroy(mm2gb_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (int i = 0; i < kMaxSlots; ++i) free_slot(c->slot[i]);
+    for (int k = 0; k < 8; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
     prof_collect(c);
     cudaFree(c->d_lut);
     delete c;
@@ -580,16 +636,20 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
 {
     Slot &s = c->slot[si];
     if (s.busy) return fail(MM2GB_ESTATE, "slot %d is busy", si);
+    if (!c->host_io) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_DEVICE_ONLY: host-buffer entry points are not available");
+    if (w.chains && !c->chains_ok) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_NO_CHAINS");
     if ((size_t)n_total > c->max_anchors) return fail(MM2GB_ECAP, "batch of %lld anchors exceeds capacity %zu", n_total, c->max_anchors);
     if (n_reads > c->max_reads) return fail(MM2GB_ECAP, "batch of %d reads exceeds capacity %d", n_reads, c->max_reads);
     CK(cudaSetDevice(c->device));
     const bool prof = c->profile && si == 0;
+    g_tl_slot = si;
     memcpy(s.h_off, off_rel, ((size_t)n_reads + 1) * sizeof(long long));
     const mm2gb_anchor_t *h_src = src;
     if (!src_pinned && n_total) { memcpy(s.h_a, src, (size_t)n_total * sizeof(mm2gb_anchor_t)); h_src = s.h_a; }
     {
         ProfScope ps(c, T_H2D, s.stream, prof);
         CK(cudaMemcpyAsync(s.d_off, s.h_off, ((size_t)n_reads + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
+        if (w.chains && n_total) { int rc0 = prepare_backtrack(s, s.stream, s.h_off, n_reads); if (rc0) return rc0; }
         if (n_total) CK(cudaMemcpyAsync(s.d_a, h_src, (size_t)n_total * sizeof(uint4), cudaMemcpyHostToDevice, s.stream));
     }
     int rc = enqueue_kernels(c, s, s.stream, s.d_a, s.d_off, n_reads, n_total, s.d_f, s.d_p, prof);
@@ -599,7 +659,7 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
     s.src_a = h_src;
     slice_rinfo(s, n_reads);
     if (w.chains && n_total) {
-        rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, s.h_off, n_reads, s.d_f, s.d_p, prof);
+        rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, n_reads, s.d_f, s.d_p, prof);
         if (rc) return rc;
     }
     s.direct_out = w.fp && w.dst_pinned && w.dst_f && w.dst_p;
@@ -833,6 +893,7 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
         if (c->slot[si].busy && (rc = reap(si))) return rc;
     }
     if (stats) *stats = acc;
+    if (c->timeline) timeline_dump(c);
     return MM2GB_OK;
 }
 
@@ -1004,6 +1065,7 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
     if (n_reads > c->max_reads) return fail(MM2GB_ECAP, "batch of %d reads exceeds capacity %d", n_reads, c->max_reads);
     Slot &s = c->slot[0];
     if (s.busy) return fail(MM2GB_ESTATE, "slot 0 is busy");
+    if (!c->host_io || !c->chains_ok) return fail(MM2GB_ESTATE, "context was created without host staging / chain-extraction buffers");
     CK(cudaSetDevice(c->device));
     if (n_declined) *n_declined = 0;
     memcpy(s.h_off, off, ((size_t)n_reads + 1) * sizeof(long long));
@@ -1019,7 +1081,9 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
         CK(cudaMemcpyAsync(s.d_f, s.h_f, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_p, s.h_p, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), s.stream));
-        int rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, s.h_off, n_reads, s.d_f, s.d_p, false);
+        int rc = prepare_backtrack(s, s.stream, s.h_off, n_reads);
+        if (rc) return rc;
+        rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, n_reads, s.d_f, s.d_p, false);
         if (rc) return rc;
         s.land_b = s.h_b;
         rc = enqueue_drain(c, s, s.stream, s.h_b_dev);
@@ -1062,11 +1126,53 @@ extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d
                                   void *d_f, void *d_p)
 {
     if (!off) return fail(MM2GB_EARG, "bad argument");
+    if (c && !c->chains_ok) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_NO_CHAINS");
     int rc = mm2gb_chain_dp_device(c, d_a, d_off, n_reads, n_total, d_f, d_p);
     if (rc || n_total == 0) return rc;
     Slot &s = c->slot[0];
-    return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, (const long long *)off, n_reads, (const int *)d_f,
-                             (const int *)d_p, c->profile);
+    rc = prepare_backtrack(s, s.stream, (const long long *)off, n_reads);
+    if (rc) return rc;
+    return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, (const int *)d_f, (const int *)d_p, c->profile);
+}
+
+// Diagnostic: device -> pinned host of n anchors (16 B each) from slot 0's buffers, by k_drain with `blocks` CTAs and by the
+// copy engine, each optionally with a host -> device copy of the same size running on a second stream (PCIe is full duplex).
+// ms[0] = k_drain alone, ms[1] = cudaMemcpyAsync alone, ms[2] = k_drain + H2D, ms[3] = cudaMemcpyAsync + H2D, ms[4] = H2D alone.
+extern "C" int mm2gb_debug_drain(mm2gb_ctx_t *c, int64_t n, int blocks, float ms[5])
+{
+    if (!c || !ms || n <= 0 || (size_t)n > c->max_anchors || !c->host_io || !c->chains_ok || blocks < 1) return fail(MM2GB_EARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slot[0];
+    cudaStream_t s2;
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    Counters hc;
+    memset(&hc, 0, sizeof(hc));
+    hc.b_cur = (int)n;
+    CK(cudaMemcpy(s.d_ctr, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+    for (int mode = 0; mode < 5; ++mode) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(e0, s.stream));
+            CK(cudaStreamWaitEvent(s2, e0, 0));
+            if (mode == 0 || mode == 2) k_drain<<<blocks, kDrainThreads, 0, s.stream>>>(s.d_b, s.h_b_dev, s.d_upack, s.h_upack_dev, s.d_ctr);
+            if (mode == 1 || mode == 3) CK(cudaMemcpyAsync(s.h_b, s.d_b, (size_t)n * 16, cudaMemcpyDeviceToHost, s.stream));
+            if (mode >= 2) CK(cudaMemcpyAsync(s.d_a, s.h_a, (size_t)n * 16, cudaMemcpyHostToDevice, s2));
+            CK(cudaEventRecord(e2, s2));
+            CK(cudaStreamWaitEvent(s.stream, e2, 0));
+            CK(cudaEventRecord(e1, s.stream));
+            CK(cudaEventSynchronize(e1));
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (rep) best = std::min(best, t);
+        }
+        ms[mode] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    cudaStreamDestroy(s2);
+    return MM2GB_OK;
 }
 
 extern "C" int mm2gb_sync(mm2gb_ctx_t *c, int slot)

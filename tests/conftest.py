@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before anything starts CUDA (see csrc/chain_core.cu)
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))

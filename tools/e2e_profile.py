@@ -2,6 +2,7 @@
 """Per-stage device times of the end-to-end call (slot 0's CUDA-event timers) on a bench workload."""
 import os, sys, time, json
 import numpy as np
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry
@@ -17,14 +18,14 @@ def main():
     ctx = pkg.ChainContext(pkg.map_ont_misc(), device=0, max_anchors=cap, max_reads=n_reads + 1, n_slots=int(os.environ.get("SLOTS", "3")))
     h_a = torch.from_numpy(a.view(np.int64)).pin_memory()
     out = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
-           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
+           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
     for _ in range(2):
-        ctx.chain(h_a, off, out=out, want_fp=False)
+        ctx.chain(h_a, off, out=out, packed=True)
     ctx.profile(True)
     t0 = time.perf_counter()
     reps = 5
     for _ in range(reps):
-        ctx.chain(h_a, off, out=out, want_fp=False)
+        ctx.chain(h_a, off, out=out, packed=True)
     dt = (time.perf_counter() - t0) / reps
     prof = ctx.profile_read()
     if cap < n:
