@@ -126,7 +126,9 @@ struct mm2gb_ctx {
     int ring = 512;
     int score_blocks = 0;
     size_t score_smem = 0;
-    int long_min = INT32_MAX;
+    int long_classes = 3;       // unit size classes (>= 8192 / 4096 / 2048 anchors) scored by k_score_long; MM2GB_LONG_MIN
+    int long_blocks = 0;
+    int long_wave = 0;          // the 4096 / 2048 classes go to k_score_long only while the long units fit this many CTAs (0: always)
     bool host_io = true;        // slots own pinned staging + device anchor/f/p buffers (false: device-resident entry points only)
     bool chains_ok = true;      // slots own the chain-extraction buffers (false: DP entry points only)
     // The size classes of the chain-extraction kernels run side by side (each is a partial wave) on auxiliary streams shared
@@ -228,7 +230,7 @@ static void launch_score(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int
 {
     const size_t smem = (size_t)kScoreWarps * R * sizeof(Rec);
     k_score_units<R, FAST><<<c->score_blocks, kScoreWarps * 32, smem, s>>>(a, st, us, ur, clip, f, p, big, big_cap, ctr, c->prm,
-                                                                          c->d_lut, run_mode, c->long_min);
+                                                                          c->d_lut, run_mode, FAST ? c->long_classes : 0, c->long_wave);
 }
 
 template <bool FAST>
@@ -240,6 +242,19 @@ static void launch_score_ring(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, cons
     case 1024: launch_score<1024, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
     default: launch_score<512, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
     }
+}
+
+static int config_long(mm2gb_ctx *c)
+{
+    const size_t smem = (size_t)kLongRing * sizeof(RecL);
+    CK(cudaFuncSetAttribute(k_score_long<kLongRing, kLongWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_score_long<kLongRing, kLongWarps>, kLongWarps * 32, smem));
+    if (nb < 1) return fail(MM2GB_ECUDA, "long score kernel does not fit on an SM (smem %zu)", smem);
+    c->long_blocks = nb * c->n_sm;
+    c->long_wave = c->long_blocks;
+    if (const char *e = getenv("MM2GB_LONG_WAVE")) c->long_wave = atoi(e);
+    return MM2GB_OK;
 }
 
 static thread_local int g_tl_slot = 0;   // slot being enqueued (timeline only)
@@ -320,6 +335,10 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
     {
         ProfScope ps(c, T_SCORE, s, prof);
         if (c->fast) {
+            if (c->long_classes > 0)   // long units first: one CTA each, warps pipelined over the tiles
+                k_score_long<kLongRing, kLongWarps><<<c->long_blocks, kLongWarps * 32, (size_t)kLongRing * sizeof(RecL), s>>>(
+                    d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, c->prm, c->d_lut,
+                    c->long_classes, c->long_wave);
             launch_score_ring<true>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 1);
             launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 2);
         } else {
@@ -509,6 +528,10 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         int r = atoi(e);
         if (r == 256 || r == 512 || r == 1024) c->ring = r;
     }
+    if (const char *e = getenv("MM2GB_LONG_MIN")) { // smallest unit scored by k_score_long: 2048 / 4096 / 8192, 0 = never
+        const int v = atoi(e);
+        c->long_classes = v <= 0 ? 0 : v <= 2048 ? 3 : v <= 4096 ? 2 : 1;
+    }
     if (const char *e = getenv("MM2GB_TIMELINE")) c->timeline = atoi(e) != 0;
     if (const char *e = getenv("MM2GB_DRAIN_BLOCKS")) {
         int r = atoi(e);
@@ -528,6 +551,8 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         rc = setup_params(c, misc);
         if (rc) goto bad;
         rc = c->ring == 256 ? config_ring<256>(c) : c->ring == 1024 ? config_ring<1024>(c) : config_ring<512>(c);
+        if (rc) goto bad;
+        rc = config_long(c);
         if (rc) goto bad;
         rc = config_backtrack();
         if (rc) goto bad;
@@ -554,7 +579,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             CKC(cudaMalloc(&s.d_unit_start, n_units_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_unit_rbase, n_units_cap * sizeof(int)));
             s.big_cap = (int)(n / kBigMin) + 2;
-            CKC(cudaMalloc(&s.d_big_order, (size_t)4 * s.big_cap * sizeof(int)));
+            CKC(cudaMalloc(&s.d_big_order, (size_t)kBigClasses * s.big_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_ctr, sizeof(Counters)));
             if (c->host_io) CKC(cudaMallocHost(&s.h_a, n * sizeof(mm2gb_anchor_t)));
             CKC(cudaMallocHost(&s.h_off, ((size_t)max_reads + 1) * sizeof(long long)));

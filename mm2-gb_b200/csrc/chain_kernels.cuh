@@ -43,7 +43,7 @@ struct Counters {
     int n_exact;            // units scored by the max_ii path
     int next_long;          // work-queue cursor of k_score_long
     int n_long;             // units routed to k_score_long
-    int big_cnt[4];         // units of >= 4096 / 2048 / 1024 / 512 anchors, queued first (longest-first scheduling)
+    int big_cnt[5];         // units of >= 8192 / 4096 / 2048 / 1024 / 512 anchors, queued first (longest-first scheduling)
     int qs_max;             // largest q_span in the batch (bounds the chain scores: f <= unit length * qs_max)
     int ovf_cnt;            // reads the shared-memory chain-extraction kernels handed to the global-memory ones
     int u_cur, b_cur;       // cursors of the packed chain / compacted-anchor outputs of the batch (k_bt_walk)
@@ -51,7 +51,27 @@ struct Counters {
 };
 
 constexpr int kBigMin = 512;                // smallest unit that goes through the longest-first lists
-__device__ __forceinline__ int big_class(int len) { return len >= 4096 ? 0 : len >= 2048 ? 1 : len >= 1024 ? 2 : 3; }
+constexpr int kBigClasses = 5;
+__device__ __forceinline__ int big_class(int len) { return len >= 8192 ? 0 : len >= 4096 ? 1 : len >= 2048 ? 2 : len >= 1024 ? 3 : 4; }
+// smallest unit of the first `n` classes (the ones k_score_long takes when long_classes = n)
+__host__ __device__ __forceinline__ int big_class_min(int n) { return n <= 0 ? INT32_MAX : (8192 >> (n - 1)); }
+
+// Which size classes k_score_long takes for this batch (both score kernels evaluate the same rule on the same counters).
+// Units of >= 8192 anchors always (the packed keys of the one-warp kernel do not hold them).  The CTA-cooperative kernel
+// spends ~1.5x the instructions per pair of the packed one-warp path but finishes a unit ~2x sooner, so the 4096 and 2048
+// classes go to it only while all long units of the batch fit one wave of its CTAs (`wave`; <= 0: always) -- a batch with
+// thousands of such units keeps every warp busy in the one-warp kernel anyway.
+__device__ __forceinline__ int long_classes_eff(const Counters *ctr, int big_cap, int long_classes, int wave)
+{
+    if (long_classes <= 1 || wave <= 0) return long_classes;
+    int acc = min(ctr->big_cnt[0], big_cap), n = 1;
+    for (int c = 1; c < long_classes; ++c) {
+        acc += min(ctr->big_cnt[c], big_cap);
+        if (acc > wave) break;
+        n = c + 1;
+    }
+    return n;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_range: window start, cuts, clipped windows, pair count            (replaces gpu/plrange.cu:38-76)
@@ -826,7 +846,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32, 6) // 6 CTAs/SM = what the 5
 k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int *__restrict__ unit_start,
               const int *__restrict__ unit_rbase, const unsigned *__restrict__ clipmask, int *f, int *__restrict__ p,
               const int *__restrict__ big_order, int big_cap, Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g,
-              int run_mode, int long_min)
+              int run_mode, int long_classes, int long_wave)
 {
     // the penalty table sits in STATIC shared memory so that its address is a compile-time constant: table loads are
     // LDS.U8 [tb + const] with no address arithmetic
@@ -842,16 +862,21 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
     __syncthreads();
     const int n_units = ctr->n_units;
     const int qs_max = max(ctr->qs_max, 1);
-    const int bb1 = min(ctr->big_cnt[0], big_cap), bb2 = bb1 + min(ctr->big_cnt[1], big_cap);
-    const int bb3 = bb2 + min(ctr->big_cnt[2], big_cap), n_big = bb3 + min(ctr->big_cnt[3], big_cap);
+    int bb[kBigClasses + 1]; // list boundaries in queue order
+    bb[0] = 0;
+#pragma unroll
+    for (int c = 0; c < kBigClasses; ++c) bb[c + 1] = bb[c] + min(ctr->big_cnt[c], big_cap);
+    const int n_big = bb[kBigClasses];
+    const int long_min = big_class_min(long_classes_eff(ctr, big_cap, long_classes, long_wave));
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(&ctr->next_unit, 1);
         w = __shfl_sync(0xffffffffu, w, 0);
         int k;
         if (w < n_big) { // longest-first lists
-            const int c = w >= bb3 ? 3 : w >= bb2 ? 2 : w >= bb1 ? 1 : 0;
-            const int base = w >= bb3 ? bb3 : w >= bb2 ? bb2 : w >= bb1 ? bb1 : 0;
+            int c = 0, base = 0;
+#pragma unroll
+            for (int q = 1; q < kBigClasses; ++q) if (w >= bb[q]) c = q, base = bb[q];
             k = big_order[c * big_cap + (w - base)];
         } else {
             k = w - n_big;
@@ -859,8 +884,9 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
         }
         const int u0 = unit_start[k], u1 = unit_start[k + 1], rbase = unit_rbase[k];
         if (w >= n_big && u1 - u0 >= kBigMin) continue; // already taken from a list
-        if (u1 - u0 >= long_min) continue; // left to k_score_long
-        if (unit_has_clip(clipmask, u0, u1, lane)) {
+        const bool clip = unit_has_clip(clipmask, u0, u1, lane);
+        if (u1 - u0 >= long_min && !clip) continue; // k_score_long's
+        if (clip) {
             if (lane == 0) atomicAdd(&ctr->n_exact, 1);
             score_unit_exact<FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, lane);
         } else if (FAST && u1 - u0 <= (1 << kSlotBits) && (u1 - u0 + 1) * qs_max < (1 << 18)) {
@@ -868,6 +894,280 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
         } else {
             score_unit_tiled<R, FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_score_long: one CTA per long unit (>= long_min anchors), its warps pipelined over the unit's 32-anchor tiles
+//                                                                       (replaces gpu/plscore.cu:370-451, the long kernel)
+//
+// A long independent segment cannot be split -- f[i] needs f of the whole window before it -- and one warp walking it
+// alone leaves the unit's latency at (window x issue + in-tile chain) per tile.  Here warp w of the CTA owns tiles
+// w, w + NW, w + 2NW, ...: it sweeps the part of its window that earlier tiles have already finished while the tiles just
+// before its own are still being resolved by the other warps, and only the last step -- the newest predecessor tile and
+// the 32x32 in-tile triangle -- stays on the critical path.  Tiles finish in order; `s_done` (tiles finished, shared
+// memory, release/acquire) is the only synchronisation.  All warps share ONE ring of RL records (64 KB for 4096), so
+// windows of up to RL - 32 NW anchors are served from shared memory (the one-warp kernel has 512 per warp).
+//
+// Scores and predecessors are kept in two registers here (no f << 13 | slot packing), so neither the unit length nor
+// the chain score is bounded.  Records are in diagonal form as in score_unit_packed: e = x - y, g = f + q_span, y, q_span;
+// predecessor tiles are classified MID / FAR / GEN per (tile, predecessor tile) exactly as there.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kLongWarps = 8;
+constexpr int kLongRing = 4096;
+
+struct __align__(16) RecL { int e, g, y, q; };
+
+__device__ __forceinline__ int ld_acquire_shared(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(int *p, int v)
+{
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// one candidate j = jb + K for the anchor of this lane: (thr, bj) <- (val, j) iff the pair is valid and val >= thr.
+// As packed_upd, the validity tests stay ONE predicate chain; the update is two predicated moves.  K is an immediate so
+// that the predecessor index costs one predicated add and no register.
+template <int MODE, bool CHECK, int K>
+__device__ __forceinline__ void long_upd(int &thr, int &bj, int &pen, int D, int yi, int re, int rg, int ry, int rq, int maxd_q, unsigned bw,
+                                         unsigned bw2, unsigned lut_s, int jb, int sti)
+{
+    if (MODE == MODE_MID) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .s32 val;\n\t"
+            ".reg .u32 tb, ad;\n\t"
+            "sub.s32 tb, %3, %4;\n\t"
+            "setp.le.u32 p, tb, %6;\n\t"
+            "add.u32 ad, tb, %7;\n\t"
+            "@p ld.shared.u8 %2, [ad];\n\t"
+            "sub.s32 val, %5, %2;\n\t"
+            "setp.ge.and.s32 p, val, %0, p;\n\t"
+            "@p mov.s32 %0, val;\n\t"
+            "@p add.s32 %1, %8, %9;\n\t"
+            "}"
+            : "+r"(thr), "+r"(bj), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(jb), "n"(K));
+    } else if (MODE == MODE_FAR) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .s32 val, dq, jk;\n\t"
+            ".reg .u32 tb, ad;\n\t"
+            "sub.s32 tb, %3, %4;\n\t"
+            "setp.le.u32 p, tb, %6;\n\t"
+            "add.u32 ad, tb, %7;\n\t"
+            "@p ld.shared.u8 %2, [ad];\n\t"
+            "sub.s32 dq, %10, %11;\n\t"
+            "setp.le.and.s32 p, dq, %12, p;\n\t"
+            "add.s32 jk, %8, %9;\n\t"
+            "setp.ge.and.s32 p, jk, %13, p;\n\t"
+            "sub.s32 val, %5, %2;\n\t"
+            "setp.ge.and.s32 p, val, %0, p;\n\t"
+            "@p mov.s32 %0, val;\n\t"
+            "@p mov.s32 %1, jk;\n\t"
+            "}"
+            : "+r"(thr), "+r"(bj), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(jb), "n"(K), "r"(yi), "r"(ry), "r"(maxd_q),
+              "r"(CHECK ? sti : INT32_MIN));
+    } else {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .s32 val, dq, dr, m, d, jk;\n\t"
+            ".reg .u32 tb, ad;\n\t"
+            "sub.s32 tb, %3, %4;\n\t"
+            "setp.le.u32 p, tb, %6;\n\t"
+            "add.u32 ad, tb, %7;\n\t"
+            "@p ld.shared.u8 %2, [ad];\n\t"
+            "sub.s32 dq, %10, %11;\n\t"
+            "add.s32 dr, dq, tb;\n\t"
+            "sub.s32 dr, dr, %14;\n\t"
+            "min.s32 m, dr, dq;\n\t"
+            "min.s32 m, m, %15;\n\t"
+            "setp.gt.and.s32 p, m, 0, p;\n\t"
+            "setp.le.and.s32 p, dq, %12, p;\n\t"
+            "add.s32 jk, %8, %9;\n\t"
+            "setp.ge.and.s32 p, jk, %13, p;\n\t"
+            "sub.s32 d, m, %15;\n\t"
+            "sub.s32 d, d, %2;\n\t"
+            "add.s32 val, %5, d;\n\t"
+            "setp.ge.and.s32 p, val, %0, p;\n\t"
+            "@p mov.s32 %0, val;\n\t"
+            "@p mov.s32 %1, jk;\n\t"
+            "}"
+            : "+r"(thr), "+r"(bj), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(jb), "n"(K), "r"(yi), "r"(ry), "r"(maxd_q),
+              "r"(CHECK ? sti : INT32_MIN), "r"(bw), "r"(rq));
+    }
+}
+
+template <int MODE, bool CHECK, int K>
+__device__ __forceinline__ void long_step(int &thr, int &bj, int &pen, const RecL *rp, int jb, int D, int yi, int maxd_q, unsigned bw,
+                                          unsigned bw2, unsigned lut_s, int sti)
+{
+    if (MODE == MODE_MID) {
+        const int2 r = *reinterpret_cast<const int2 *>(rp + K);
+        long_upd<MODE, CHECK, K>(thr, bj, pen, D, yi, r.x, r.y, 0, 0, maxd_q, bw, bw2, lut_s, jb, sti);
+    } else {
+        const int4 r = *reinterpret_cast<const int4 *>(rp + K);
+        long_upd<MODE, CHECK, K>(thr, bj, pen, D, yi, r.x, r.y, r.z, r.w, maxd_q, bw, bw2, lut_s, jb, sti);
+    }
+}
+
+// the 32 records of one predecessor tile (never wraps in the ring: tiles are 32-aligned)
+template <int MODE, bool CHECK>
+__device__ __forceinline__ void long_walk32(int &thr, int &bj, int &pen, const RecL *rp, int j0, int D, int yi, int maxd_q, unsigned bw,
+                                            unsigned bw2, unsigned lut_s, int sti)
+{
+#pragma unroll 1
+    for (int kk = 0; kk < 32; kk += 8) {
+        const RecL *r8 = rp + kk;
+        const int jb = j0 + kk;
+#define MM2GB_LSTEP(K) long_step<MODE, CHECK, K>(thr, bj, pen, r8, jb, D, yi, maxd_q, bw, bw2, lut_s, sti);
+        MM2GB_LSTEP(0) MM2GB_LSTEP(1) MM2GB_LSTEP(2) MM2GB_LSTEP(3) MM2GB_LSTEP(4) MM2GB_LSTEP(5) MM2GB_LSTEP(6) MM2GB_LSTEP(7)
+#undef MM2GB_LSTEP
+    }
+}
+
+template <int RL, int NW>
+__device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p, int u0, int u1,
+                                int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecL *ring, int *s_done, int warp, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned bw = (unsigned)P.bw, bw2 = 2u * (unsigned)P.bw;
+    const int maxd_q = P.maxd_q;
+    const int near_d = P.bw + qs_max;       // dr >  near_d  =>  min(dr, dq, q_span_j) = q_span_j inside the band
+    const int far_d = maxd_q - P.bw;        // dr <= far_d   =>  dq <= maxd_q inside the band
+    const int ntiles = (u1 - u0 + 31) >> 5;
+    int pen = 0;
+    int done = 0;                           // tiles known to be finished
+    for (int t = warp; t < ntiles; t += NW) {
+        const int t0 = u0 + 32 * t;
+        const int i = t0 + lane;
+        const bool act = i < u1;
+        uint4 ai = make_uint4(0, 0, 0, 0);
+        int sti = INT32_MAX; // inactive lanes: empty window
+        if (act) { ai = __ldg(a + i); sti = st[i]; }
+        const int xi = (int)ai.x, yi = (int)ai.z, qsi = (int)(ai.w & 0xffu);
+        const int D = xi - yi + (int)bw;
+        const int nact = min(32, u1 - t0);
+        const int wmin = __shfl_sync(full, sti, 0);                        // st is non-decreasing, lane 0 is always active
+        const int wfull = min(t0, __reduce_max_sync(full, act ? sti : 0)); // from here on every active lane's window is open
+        const int x_first = __shfl_sync(full, xi, 0), x_last = __shfl_sync(full, xi, nact - 1);
+        int thr = qsi + 1, bj = -1; // a candidate wins iff val >= thr: '>' against q_span(i), '>=' afterwards (ascending j)
+        // tiles this warp may still find in the ring: the NW - 1 tiles in flight behind it may overwrite anything older
+        const int tring = max(0, t - RL / 32 + NW);
+        const int jring = u0 + 32 * tring;
+        // (rare) window older than the ring: from global memory; those tiles were finished before this warp's previous tile
+        for (int j = wmin; j < min(jring, t0); ++j) {
+            const uint4 v = __ldg(a + j);
+            const int fj = __ldcg(f + j);
+            const int rq = (int)(v.w & 0xffu);
+            long_upd<MODE_GEN, true, 0>(thr, bj, pen, D, yi, (int)v.x - (int)v.z, fj + rq, (int)v.z, rq, maxd_q, bw, bw2, lut_s, j, sti);
+        }
+        const int kfirst = max(tring, (max(wmin, u0) - u0) >> 5);
+        for (int k = kfirst; k < t; ++k) {
+            if (k >= done) { // wait for tile k (tiles finish in order)
+                for (;;) {
+                    done = ld_acquire_shared(s_done);
+                    if (k < done) break;
+                    __nanosleep(t - done > 1 ? 200 : 20);
+                }
+            }
+            const int j0 = u0 + 32 * k;
+            const RecL *rp = ring + ((32 * k) & (RL - 1));
+            if (j0 < wfull) { // some lane's window opens inside or after this tile (or the tile straddles rid/strand runs)
+                long_walk32<MODE_GEN, true>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
+            } else {          // inside every lane's window: same rid/strand as the whole tile, x ascending
+                const int xk_first = rp[0].e + rp[0].y, xk_last = rp[31].e + rp[31].y;
+                if (x_first - xk_last > near_d) {
+                    if (x_last - xk_first <= far_d) long_walk32<MODE_MID, false>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
+                    else long_walk32<MODE_FAR, false>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
+                } else long_walk32<MODE_GEN, false>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
+            }
+        }
+        // publish this tile's static fields (nobody reads them as a predecessor before s_done passes t)
+        RecL *tile = ring + ((32 * t) & (RL - 1));
+        if (act) { RecL r; r.e = xi - yi; r.g = 0; r.y = yi; r.q = qsi; tile[lane] = r; }
+        __syncwarp();
+        // phase B: the in-tile triangle, f-independent parts first, then the serial chain (one shuffle per step)
+        int fcur = bj >= 0 ? thr : qsi;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
+            int w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int s = h * 16 + q;
+                if (s < 31) {
+                    const int4 r = *reinterpret_cast<const int4 *>(tile + s);
+                    const unsigned tb = (unsigned)(D - r.x);
+                    bool ok = tb <= bw2;
+                    if (ok) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pen) : "r"(lut_s + tb));
+                    const int dq = yi - r.z;
+                    const int dr = dq + (int)tb - (int)bw;
+                    const int m = min(min(dr, dq), r.w);
+                    ok = ok && m > 0 && dq <= maxd_q && s < lane && t0 + s >= sti;
+                    w[q] = ok ? m - pen : kNeg;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int s = h * 16 + q;
+                if (s < 31) {
+                    const int fs = __shfl_sync(full, fcur, s);
+                    const int val = fs + w[q];                  // kNeg + f stays far below any threshold
+                    if (val >= thr) thr = val, fcur = val, bj = t0 + s;
+                }
+            }
+        }
+        if (act) {
+            f[i] = fcur;
+            p[i] = bj < 0 ? -1 : bj - rbase;
+            tile[lane].g = fcur + qsi;
+        }
+        // tiles finish in order: a tile whose window does not reach back into tile t - 1 (a cut inside the unit) has not
+        // waited for it yet
+        while (done < t) done = ld_acquire_shared(s_done);
+        __syncwarp();
+        if (lane == 0) st_release_shared(s_done, t + 1);
+        done = t + 1;
+    }
+}
+
+template <int RL, int NW>
+__global__ void __launch_bounds__(NW * 32, 3)
+k_score_long(const uint4 *__restrict__ a, const int *__restrict__ st, const int *__restrict__ unit_start, const int *__restrict__ unit_rbase,
+             const unsigned *__restrict__ clipmask, int *f, int *__restrict__ p, const int *__restrict__ big_order, int big_cap, Counters *ctr,
+             DevParams P, const unsigned char *__restrict__ lut_g, int long_classes_max, int long_wave)
+{
+    __shared__ __align__(16) unsigned char lut[2 * kLutMax + 16];
+    __shared__ int s_unit, s_done;
+    extern __shared__ int4 smem_raw[];
+    RecL *ring = reinterpret_cast<RecL *>(smem_raw);
+    unsigned lut_s = (unsigned)__cvta_generic_to_shared(lut);
+    asm volatile("" : "+r"(lut_s)); // keep the table address in a register (otherwise it is rematerialised per pair)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ctr->multi_sid != 0) return; // the table path is not valid for this batch: k_score_units<false> takes every unit
+    const int long_classes = long_classes_eff(ctr, big_cap, long_classes_max, long_wave);
+    int n_list = 0;
+    for (int c = 0; c < long_classes; ++c) n_list += min(ctr->big_cnt[c], big_cap);
+    if ((int)blockIdx.x >= n_list) return;
+    for (int k = threadIdx.x; k < P.lut_n; k += blockDim.x) lut[k] = lut_g[k];
+    const int qs_max = max(ctr->qs_max, 1);
+    for (;;) {
+        __syncthreads(); // everyone is done with s_unit / s_done / the ring of the previous unit
+        if (threadIdx.x == 0) { s_unit = atomicAdd(&ctr->next_long, 1); s_done = 0; }
+        __syncthreads();
+        const int w = s_unit;
+        if (w >= n_list) break;
+        int c = 0, base = 0, acc = 0;
+        for (int q = 0; q < long_classes; ++q) { if (w >= acc) c = q, base = acc; acc += min(ctr->big_cnt[q], big_cap); }
+        const int k = big_order[c * big_cap + (w - base)];
+        const int u0 = unit_start[k], u1 = unit_start[k + 1], rbase = unit_rbase[k];
+        if (unit_has_clip(clipmask, u0, u1, lane)) continue; // exact max_ii path, k_score_units
+        if (threadIdx.x == 0) atomicAdd(&ctr->n_long, 1);
+        score_unit_long<RL, NW>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane);
     }
 }
 

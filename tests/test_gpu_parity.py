@@ -87,6 +87,31 @@ def test_repeat_dense_reads(pkg, po, synth, ctx):
     _check_batch(pkg, po, ctx, np.concatenate(reads), off, po.map_ont_params())
 
 
+@pytest.mark.parametrize("long_min", [0, 2048, 8192])
+def test_long_units(pkg, po, synth, long_min):
+    """units of thousands of anchors: the CTA-cooperative pipelined kernel (k_score_long) against the one-warp kernel
+    (long_min = 0) and the oracle.  Covers chain scores beyond 2^18 (the packed keys of the one-warp kernel overflow),
+    windows longer than the shared ring (global-memory part of the window), cuts inside a long unit and a strand switch."""
+    rng = np.random.default_rng(77)
+    two_strands = np.concatenate([synth.ont_like_anchors(rng, 2600, rev=0, rpos0=5000), synth.ont_like_anchors(rng, 2600, rev=1, rpos0=5000)])
+    two_strands = two_strands[np.argsort(two_strands[:, 0], kind="stable")]
+    reads = [synth.ont_like_anchors(rng, 50000, mean_gap=9.0, noise_frac=0.2),      # ~60k anchors, one unit, f beyond 2^18
+             synth.ont_like_anchors(rng, 9000, mean_gap=1.2, noise_frac=0.05),      # ~4100 predecessors per anchor
+             synth.ont_like_anchors(rng, 2100), two_strands, synth.ont_like_anchors(rng, 300),
+             synth.chaining_only_array(5, 20000, 4500)]                              # independent segments of 4500 anchors
+    off = np.zeros(len(reads) + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    os.environ["MM2GB_LONG_MIN"] = str(long_min)
+    try:
+        with pkg.ChainContext(pkg.map_ont_misc(), max_anchors=1 << 18, max_reads=16, n_slots=1) as c:
+            st = _check_batch(pkg, po, c, np.concatenate(reads), off, po.map_ont_params(), chains=False)
+    finally:
+        del os.environ["MM2GB_LONG_MIN"]
+    assert (st.n_long > 0) == (long_min > 0), st.as_dict() if hasattr(st, "as_dict") else st.n_long
+    if long_min == 2048:
+        assert st.n_long >= 8
+
+
 @pytest.mark.parametrize("over", [dict(chn_pen_skip=0.03), dict(is_cdna=1), dict(n_seg=2), dict(bw=2000, max_dist_x=10000, max_dist_y=10000),
                                   dict(bw=100000, max_dist_x=100000, max_dist_y=100000), dict(max_dist_x=100, max_dist_y=100, bw=500)])
 def test_parameter_variants(pkg, po, synth, over):
