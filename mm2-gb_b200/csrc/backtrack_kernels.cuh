@@ -265,10 +265,12 @@ __device__ __forceinline__ void bt_overflow(int r, int *ovf_list, Counters *ctr)
 template <int CAP>
 struct BtSortSmem {
     unsigned zk[CAP];               // (score << 13 | index), sorted in place
-    unsigned zk2[CAP];              // rank-sort scratch
     unsigned cnt[256];
     unsigned short start[3 * kBtRow];   // scores are below 2^19: at most three radix levels
 };
+// The rank-sort scratch (the second key array) is NOT here: it is the read's slice of zs_scr, where the sorted keys go in
+// the end anyway.  The rank sort is the parallel part of the sort, so the global round trip costs little, and 4 instead of
+// 8 bytes per anchor doubles the reads resident on an SM -- these one-warp kernels are latency bound.
 
 // z[]: anchors scoring >= min_sc, in index order (lchain.c:33-40); 4 coalesced loads per lane in flight.  Returns nz; the
 // largest kept score in fmax.
@@ -320,8 +322,9 @@ k_bt_sort(const int *__restrict__ f, const long long *__restrict__ off, const in
     BtSortScratch<unsigned short> sc;
     sc.cnt = S.cnt;
     sc.start = S.start;
-    bt_sort<ZKey, false, unsigned short, unsigned short>(S.zk, nullptr, S.zk2, nullptr, nz, sc, lane);
     unsigned *zo = zs_scr + o0;
+    bt_sort<ZKey, false, unsigned short, unsigned short>(S.zk, nullptr, zo, nullptr, nz, sc, lane);
+    __syncwarp();
     for (int e = lane; e < nz; e += 32) zo[e] = S.zk[e];
     if (lane == 0) nz_out[r] = nz;
 }
@@ -363,7 +366,8 @@ template <int CAP>
 struct BtWalkSmem {
     static constexpr int WC = CAP / 16 < 64 ? 64 : CAP / 16;   // chains whose start keys can be sorted here
     unsigned long long wk[WC], wtmp[WC];    // chain-start keys (x of the first anchor) + sort scratch
-    int fs[CAP + 1];                        // f[] by anchor index; 0 for the sentinel, so "key - f[n_j]" needs no special case
+    // f[] is read from global memory (one 32-wide gather per chase batch): keeping it here would double the footprint and
+    // halve the reads resident on an SM, and this one-warp kernel is bound by latency, not by bandwidth
     unsigned short ps[CAP + 2];             // p[] by anchor index; "none" is the sentinel index CAP, whose own entry is CAP
     unsigned short path[32];                // the nodes of one chase batch
     unsigned tb[CAP / 32 + 1];              // claimed bits (lchain.c: t[]); the sentinel's bit is never set
@@ -386,25 +390,23 @@ struct WalkSmall {
     __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
-        for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight
-            int pv[4], fv[4];
+        for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight, then 4 gathers of f[p[i]]
+            int pv[4], fv[4], fp[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; pv[t] = i < n ? pr[i] : -1; fv[t] = i < n ? fr[i] : 0; }
 #pragma unroll
+            for (int t = 0; t < 4; ++t) fp[t] = pv[t] >= 0 ? fr[pv[t]] : 0;
+#pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int i = i0 + t * 32 + lane;
-                if (i < n) { S.ps[i] = pv[t] < 0 ? (unsigned short)CAP : (unsigned short)pv[t]; S.fs[i] = fv[t]; }
+                if (i < n) S.ps[i] = pv[t] < 0 ? (unsigned short)CAP : (unsigned short)pv[t];
+                const unsigned g = __ballot_sync(0xffffffffu, i < n && fv[t] - fp[t] > 0);
+                if (lane == 0 && i0 + t * 32 < n) { S.gp[(i0 >> 5) + t] = g; S.tb[(i0 >> 5) + t] = 0; }
             }
         }
-        if (lane == 0) { S.ps[CAP] = (unsigned short)CAP; S.fs[CAP] = 0; S.tb[CAP / 32] = 0; }
-        __syncwarp();
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const unsigned g = __ballot_sync(0xffffffffu, i < n && S.fs[i] - S.fs[S.ps[i]] > 0);
-            if (lane == 0) { S.gp[i0 >> 5] = g; S.tb[i0 >> 5] = 0; }
-        }
+        if (lane == 0) { S.ps[CAP] = (unsigned short)CAP; S.tb[CAP / 32] = 0; }
     }
-    __device__ __forceinline__ int fat(int i, const int *) const { return S.fs[i]; }
+    __device__ __forceinline__ int fat(int i, const int *__restrict__ fr) const { return i < CAP ? fr[i] : 0; }
     __device__ __forceinline__ int nextp(int cur) const { return S.ps[cur]; }
     __device__ __forceinline__ bool claimed(int i) const { return ((S.tb[i >> 5] >> (i & 31)) & 1u) != 0; }
     __device__ __forceinline__ void claim(int i) { atomicOr(&S.tb[i >> 5], 1u << (i & 31)); }

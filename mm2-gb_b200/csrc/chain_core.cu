@@ -432,13 +432,12 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         // fork: one auxiliary stream per non-empty size class, joined back into the slot's stream
         ProfScope ps(c, T_BACKTRACK, s, prof);
         CK(cudaEventRecord(sl.bt_fork, s));
-        for (int k = 7; k >= 0; --k) { // longest first
+        for (int k = 6; k >= 0; --k) { // longest first
             if (!cnt[k]) continue;
             cudaStream_t bs = c->bt_stream[k];
             CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
             const int *list = sl.d_list + base[k];
             switch (k) {
-            case 7: launch_backtrack_big(bs, d_a, d_f, d_p, d_off, list, cnt[k], false, bp, sl); break;
             case 6: launch_backtrack<8192>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             case 5: launch_backtrack<6144>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             case 4: launch_backtrack<4096>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
@@ -448,8 +447,12 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
             default: launch_backtrack<1024>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             }
             CK(cudaEventRecord(sl.bt_join[k], bs));
-            CK(cudaStreamWaitEvent(s, sl.bt_join[k], 0));
         }
+        // the big reads stay on the slot's own stream (next to the forked classes): their kernels are a few long serial warps,
+        // and on a stream shared by all slots the chunks of a batch of long reads would queue behind each other
+        if (cnt[7]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, sl.d_list + base[7], cnt[7], false, bp, sl);
+        for (int k = 6; k >= 0; --k)
+            if (cnt[k]) CK(cudaStreamWaitEvent(s, sl.bt_join[k], 0));
         // whatever the shared-memory kernels handed over (normally nothing: 256 CTAs that exit at once)
         if (base[7]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, nullptr, 0, true, bp, sl);
     }
