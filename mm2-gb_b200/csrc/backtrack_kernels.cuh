@@ -248,6 +248,197 @@ __device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT
     }
 }
 
+// ---- the same sort for reads too long for shared-memory keys ------------------------------------------------------------
+// One American-flag pass over A[lo, hi) in GLOBAL memory whose serial walk runs on a shared-memory copy of the DIGITS
+// (one byte per element, D[0 .. hi-lo)).  The pass is a deterministic walk over the original array: positions at or
+// behind a bucket's cursor still hold their original element, so the walk needs nothing but the digits and the cursors
+// and can emit, per slot, the ORIGINAL position of the element that ends up there (src[], global, write-only during the
+// walk); the keys are moved afterwards by one parallel gather.  A serial step costs a few shared-memory round trips
+// instead of an L2 round trip.  Bucket boundaries -> st[0..256] (absolute positions).
+template <class KO>
+__device__ void bt_flag_pass_dig(typename KO::T *A, typename KO::T *tmpA, unsigned *src, int lo, int hi, int shift, unsigned *cnt,
+                                 unsigned *st, unsigned char *D, int lane)
+{
+    typedef typename KO::T K;
+    const unsigned full = 0xffffffffu;
+    const int m = hi - lo;
+    K *Al = A + lo, *Tl = tmpA + lo;
+    unsigned *sl = src + lo;
+    for (int d = lane; d < 256; d += 32) cnt[d] = 0;
+    __syncwarp();
+    for (int e0 = 0; e0 < m; e0 += 128) { // 4 coalesced key loads per lane in flight
+        K kv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Al[e] : (K)0; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = e0 + t * 32 + lane;
+            if (e < m) { const unsigned d = KO::digit(kv[t], shift); D[e] = (unsigned char)d; atomicAdd(&cnt[d], 1u); }
+        }
+    }
+    __syncwarp();
+    {   // exclusive scan of 256 counts: 8 per lane (positions relative to lo)
+        unsigned c[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { c[q] = cnt[lane * 8 + q]; sum += c[q]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += y;
+        }
+        unsigned run = incl - sum;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            st[lane * 8 + q] = run;
+            cnt[lane * 8 + q] = run;        // cursor of the bucket
+            run += c[q];
+        }
+        if (lane == 31) st[256] = (unsigned)m;
+    }
+    __syncwarp();
+    bool moved = false;
+    for (int k = 0; k < 256; ++k) {
+        const int endk = (int)st[k + 1];
+        int c = (int)cnt[k];
+        while (c < endk) {
+            // elements that already sit in their home bucket stay where they are
+            const int e = c + lane;
+            const bool mis = e < endk && D[e] != (unsigned char)k;
+            const unsigned mm = __ballot_sync(full, mis);
+            const int stay = mm ? __ffs(mm) - 1 : min(32, endk - c);
+            if (lane < stay) sl[e] = (unsigned)e;
+            c += stay;
+            if (!mm) continue;
+            moved = true;
+            int s = c;                      // original position of the carried element
+            unsigned d = D[s];
+            do {
+                const int pos = (int)cnt[d], endd = (int)st[d + 1];
+                // elements of bucket d sitting at its cursor are pushed one slot to the right; the first foreign element
+                // after them is evicted and carried on
+                int L = 0;
+                unsigned dn;
+                for (;;) {
+                    const int q = pos + L + lane;
+                    const unsigned dq = q < endd ? (unsigned)D[q] : 0x100u;
+                    const unsigned nm = __ballot_sync(full, dq != d);
+                    const int t = nm ? __ffs(nm) - 1 : 32;
+                    if (lane < t) sl[q + 1] = (unsigned)q;
+                    if (nm) { dn = __shfl_sync(full, dq, t); L += t; break; }
+                    L += 32;
+                }
+                if (lane == 0) { sl[pos] = (unsigned)s; cnt[d] = (unsigned)(pos + L + 1); }
+                __syncwarp();
+                s = pos + L;
+                d = dn;
+            } while (d != (unsigned)k);
+            if (lane == 0) sl[c] = (unsigned)s;
+            ++c;
+        }
+    }
+    __syncwarp();
+    if (moved) {
+        for (int e0 = 0; e0 < m; e0 += 128) { // gather through src: 4 independent chains of two loads per lane
+            unsigned sv[4];
+            K kv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; sv[t] = e < m ? sl[e] : 0u; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Al[sv[t]] : (K)0; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Tl[e] = kv[t]; }
+        }
+        __syncwarp();
+        for (int e0 = 0; e0 < m; e0 += 128) {
+            K kv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Tl[e] : (K)0; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Al[e] = kv[t]; }
+        }
+    }
+    for (int d = lane; d <= 256; d += 32) st[d] += (unsigned)lo;
+    __syncwarp();
+}
+
+// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors: passes over more than `kcap` elements are
+// digit walks (above), any bucket of at most kcap elements is copied to shared memory (KA, which aliases D) and finished
+// there by bt_sort.  rows: 4 levels (32-bit scores) of kBtRow entries.
+template <class KO>
+__device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, unsigned *src, int n, unsigned *cnt, unsigned *rows,
+                            unsigned char *D, int kcap, int lane)
+{
+    typedef typename KO::T K;
+    const unsigned full = 0xffffffffu;
+    K *KA = reinterpret_cast<K *>(D);
+    if (n <= 1) return;
+    BtSortScratch<unsigned> sc;
+    sc.cnt = cnt;
+    sc.start = rows;
+    if (n <= kcap) {
+        for (int e = lane; e < n; e += 32) KA[e] = A[e];
+        __syncwarp();
+        bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA, nullptr, n, sc, lane);
+        __syncwarp();
+        for (int e = lane; e < n; e += 32) A[e] = KA[e];
+        __syncwarp();
+        return;
+    }
+    unsigned long long o = 0, an = ~0ULL;
+    for (int e = lane; e < n; e += 32) { const unsigned long long k = KO::key64(A[e]); o |= k; an &= k; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { o |= __shfl_xor_sync(full, o, d); an &= __shfl_xor_sync(full, an, d); }
+    const unsigned long long diff = o ^ an;
+    if (!diff) return;
+    int shift = 56;
+    while (((diff >> shift) & 255ULL) == 0) shift -= 8;
+    int lv = 0;
+    unsigned *row = rows;
+    bt_flag_pass_dig<KO>(A, tmpA, src, 0, n, shift, cnt, row, D, lane);
+    if (shift) bt_rank_sort<KO, false, unsigned, unsigned>(A, nullptr, tmpA, nullptr, 0, n, shift, row, lane);
+    if (lane == 0) { row[257] = 0; row[258] = (unsigned)shift; }
+    __syncwarp();
+    while (lv >= 0) {
+        row = rows + lv * kBtRow;
+        const int sh = (int)row[258];
+        int k = (int)row[257];
+        if (sh == 0 || k >= 256) { --lv; continue; }
+        int found = -1;
+        while (k < 256) {
+            const int kk = k + lane;
+            const bool big = kk < 256 && (int)row[kk + 1] - (int)row[kk] > 64;
+            const unsigned bm = __ballot_sync(full, big);
+            if (bm) { found = k + __ffs(bm) - 1; break; }
+            k += 32;
+        }
+        __syncwarp();
+        if (found < 0) { if (lane == 0) row[257] = 256; __syncwarp(); --lv; continue; }
+        if (lane == 0) row[257] = (unsigned)(found + 1);
+        const int blo = (int)row[found], bhi = (int)row[found + 1];
+        const int nsh = sh > 8 ? sh - 8 : 0;
+        __syncwarp();
+        if (bhi - blo <= kcap) { // the whole subtree in shared memory (identity passes are skipped by bt_sort itself)
+            const int m = bhi - blo;
+            for (int e = lane; e < m; e += 32) KA[e] = A[blo + e];
+            __syncwarp();
+            sc.start = rows + (lv + 1) * kBtRow;
+            bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA + blo, nullptr, m, sc, lane);
+            __syncwarp();
+            for (int e = lane; e < m; e += 32) A[blo + e] = KA[e];
+            __syncwarp();
+            continue;
+        }
+        ++lv;
+        unsigned *crow = rows + lv * kBtRow;
+        bt_flag_pass_dig<KO>(A, tmpA, src, blo, bhi, nsh, cnt, crow, D, lane);
+        if (nsh) bt_rank_sort<KO, false, unsigned, unsigned>(A, nullptr, tmpA, nullptr, blo, bhi, nsh, crow, lane);
+        if (lane == 0) { crow[257] = 0; crow[258] = (unsigned)nsh; }
+        __syncwarp();
+    }
+}
+
 // a read the shared-memory kernels cannot finish goes to the global-memory ones through this list
 __device__ __forceinline__ void bt_overflow(int r, int *ovf_list, Counters *ctr)
 {
@@ -362,6 +553,29 @@ k_bt_sort_big(const int *__restrict__ f, const long long *__restrict__ off, cons
     if (lane == 0) nz_out[r] = nz;
 }
 
+// Reads of 8193 .. 196608 anchors ("mid" classes): 64-bit keys in global scratch as in k_bt_sort_big, but the serial part of
+// every pass runs in shared memory (bt_sort_mid).  Dynamic shared memory: cap bytes (digits / keys of small buckets).
+__global__ void __launch_bounds__(32)
+k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
+              unsigned long long *zk_scr, unsigned long long *zk2_scr, unsigned *src_scr, int *__restrict__ nz_out, int cap)
+{
+    extern __shared__ int4 bt_raw[];
+    __shared__ unsigned s_cnt[256];
+    __shared__ unsigned s_rows[4 * kBtRow];     // scores are below 2^31: at most four radix levels
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_list) return;
+    const int r = read_list[blockIdx.x];
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    if (bp.min_sc < 0 || n > cap) { if (lane == 0) nz_out[r] = -1; return; }
+    unsigned long long *zk = zk_scr + o0, *zk2 = zk2_scr + o0;
+    int fmax;
+    const int nz = bt_collect<ZKey64>(f + o0, n, bp.min_sc, zk, lane, fmax);
+    __syncwarp();
+    bt_sort_mid<ZKey64>(zk, zk2, src_scr + o0, nz, s_cnt, s_rows, reinterpret_cast<unsigned char *>(bt_raw), cap / 8, lane);
+    if (lane == 0) nz_out[r] = nz;
+}
+
 template <int CAP>
 struct BtWalkSmem {
     static constexpr int WC = CAP / 16 < 64 ? 64 : CAP / 16;   // chains whose start keys can be sorted here
@@ -444,6 +658,65 @@ struct WalkBig {
     {
         int nx = n;
         if (cur < n) { const int q = pr[cur]; nx = q < 0 ? n : q; }
+        return nx;
+    }
+    __device__ __forceinline__ int fat(int i, const int *fr) const { return i < n ? fr[i] : 0; }
+    __device__ __forceinline__ bool claimed(int i) const { return ((tb[i >> 5] >> (i & 31)) & 1u) != 0; }
+    __device__ __forceinline__ void claim(int i) { atomicOr(&tb[i >> 5], 1u << (i & 31)); }
+    __device__ __forceinline__ bool gain(int i, const int *fr, const int *prr) const
+    {
+        const int q = prr[i];
+        return fr[i] - (q >= 0 ? fr[q] : 0) > 0;
+    }
+    __device__ __forceinline__ unsigned long long zat(int e) const { return zk[e]; }
+    __device__ __forceinline__ IDX *path() { return path_s; }
+    __device__ __forceinline__ unsigned long long *wk() { return zk; }
+    __device__ __forceinline__ unsigned long long *wtmp() { return zk2; }
+    __device__ __forceinline__ IDX *wpay() { return reinterpret_cast<int *>(pay); }
+    __device__ __forceinline__ IDX *wpay2() { return reinterpret_cast<int *>(pay2); }
+    __device__ __forceinline__ unsigned *cnt() { return cnt_s; }
+    __device__ __forceinline__ POS *start() { return start_s; }
+};
+
+// ---- ... or in between (reads of up to 196608 anchors): the predecessor links sit in shared memory as ONE BYTE per anchor,
+//      the distance i - p[i] (0 = none, 255 = "255 or more": look p[i] up in global memory), next to the claimed bits.  The
+//      pointer chase -- the serial part of every walk -- then runs at shared-memory latency; f[], the sorted z[] and the
+//      chain-start keys stay in global scratch as in WalkBig.  The sort scratch of the compaction aliases the links (dead by then).
+struct WalkMid {
+    typedef ZKey64 ZK;
+    typedef int IDX;
+    typedef unsigned POS;
+    int n;
+    const int *pr;
+    unsigned char *rel;     // [n + 1], rel[n] = 0: the sentinel points at itself
+    unsigned *tb;           // [n / 32 + 1]
+    unsigned long long *zk, *zk2;
+    unsigned *pay, *pay2;
+    int *path_s;
+    unsigned *cnt_s, *start_s;
+    __device__ __forceinline__ int sent() const { return n; }
+    __device__ __forceinline__ int wc() const { return n; }
+    __device__ __forceinline__ void init(int n_, const int *, const int *__restrict__ prr, int lane)
+    {
+        for (int i0 = 0; i0 < n_; i0 += 128) {
+            int pv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; pv[t] = i < n_ ? prr[i] : -1; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t * 32 + lane;
+                if (i < n_) rel[i] = pv[t] < 0 ? (unsigned char)0 : (unsigned char)min(i - pv[t], 255);
+            }
+        }
+        if (lane == 0) rel[n_] = 0;
+        for (int w = lane; w <= (n_ >> 5); w += 32) tb[w] = 0;
+    }
+    __device__ __forceinline__ int nextp(int cur) const
+    {
+        const unsigned d = rel[cur];
+        int nx = cur - (int)d;
+        if (d == 0u) nx = n;
+        else if (d == 255u) nx = pr[cur];
         return nx;
     }
     __device__ __forceinline__ int fat(int i, const int *fr) const { return i < n ? fr[i] : 0; }
@@ -734,6 +1007,44 @@ k_bt_walk_big(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.path_s = s_path;
     S.cnt_s = s_cnt;
     S.start_s = s_start;
+    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
+                 u_pos, b_pos, nullptr, ctr, lane);
+}
+
+// dynamic shared memory of k_bt_walk_mid for reads of up to cap anchors: links + claimed bits (the compaction's sort scratch,
+// (256 + kBtLevels * kBtRow) words, reuses the front of it: cap >= 16384)
+__host__ __device__ inline size_t bt_walk_mid_smem(int cap) { return (((size_t)cap + 1 + 15) & ~(size_t)15) + ((size_t)cap / 32 + 1) * 4 + 16; }
+
+__global__ void __launch_bounds__(32)
+k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
+              const int *__restrict__ read_list, int n_list, BtParams bp, unsigned long long *zk_scr, unsigned long long *zk2_scr,
+              const int *__restrict__ nz_in, unsigned *pay_scr, unsigned *pay2_scr, int *__restrict__ v_scr,
+              unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_pack,
+              unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
+              int *__restrict__ u_pos, int *__restrict__ b_pos, Counters *ctr, int cap)
+{
+    extern __shared__ int4 bt_raw[];
+    __shared__ int s_path[32];
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_list) return;
+    const int r = read_list[blockIdx.x];
+    const long long o0 = off[r];
+    const int n = (int)(off[r + 1] - o0);
+    const int nz = nz_in[r];
+    if (nz < 0 || n > cap) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
+    if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; u_pos[r] = 0; b_pos[r] = 0; } return; }
+    WalkMid S;
+    S.n = n;
+    S.pr = p + o0;
+    S.rel = reinterpret_cast<unsigned char *>(bt_raw);
+    S.tb = reinterpret_cast<unsigned *>(S.rel + (((size_t)cap + 1 + 15) & ~(size_t)15));
+    S.zk = zk_scr + o0;
+    S.zk2 = zk2_scr + o0;
+    S.pay = pay_scr + o0;
+    S.pay2 = pay2_scr + o0;
+    S.path_s = s_path;
+    S.cnt_s = reinterpret_cast<unsigned *>(bt_raw);
+    S.start_s = S.cnt_s + 256;
     bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);
 }

@@ -54,6 +54,20 @@ extern "C" int mm2gb_device_count(void)
 
 namespace {
 
+// size classes of the chain-extraction kernels: 0..6 shared-memory kernels (k_bt_sort<CAP> / k_bt_walk<CAP>), 7..11 "mid"
+// (k_bt_sort_mid / k_bt_walk_mid: keys in global scratch, digits / predecessor links in shared memory), 12 = any size
+constexpr int kBtClasses = 17, kBtBig = 16, kBtMid0 = 7, kBtMidStreams = 12;
+const int kBtCaps[kBtBig] = {1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608};
+// Reads of 8193 .. mid_min anchors go to the global-memory kernels, longer ones (up to 196608) to the mid kernels.  The two
+// kinds complement each other: the global-memory kernels need no shared memory, so every read of a batch is resident at once
+// but each serial step costs an L2 round trip (fine for the shorter reads); the mid kernels take ~5x less time per read but
+// an SM only holds 227 KB / (anchors of the read) of them -- they take the long reads that would otherwise be the tail.
+static int bt_mid_min()
+{
+    const char *e = getenv("MM2GB_BT_MID_MIN");   // read per batch: the tests switch it
+    return e ? std::max(8192, atoi(e)) : 32768;
+}
+
 enum { T_RANGE = 0, T_UNITS, T_SCORE, T_BACKTRACK, T_H2D, T_D2H };
 
 struct Slot {
@@ -81,8 +95,8 @@ struct Slot {
     unsigned *d_tb = nullptr, *d_pay2 = nullptr;
     int *d_ovf = nullptr;
     size_t u_cap = 0;      // entries of d_upack / h_upack
-    cudaEvent_t bt_fork = nullptr, bt_join[8] = {nullptr};
-    int bt_cnt[8] = {0}, bt_base[9] = {0};   // reads per size class of the batch in flight, their ranges in d_list
+    cudaEvent_t bt_fork = nullptr, bt_join[kBtClasses] = {nullptr};
+    int bt_cnt[kBtClasses] = {0}, bt_base[kBtClasses + 1] = {0};   // reads per size class of the batch in flight, their ranges in d_list
     // pinned host
     mm2gb_anchor_t *h_a = nullptr;
     long long *h_off = nullptr;
@@ -134,7 +148,9 @@ struct mm2gb_ctx {
     // The size classes of the chain-extraction kernels run side by side (each is a partial wave) on auxiliary streams shared
     // by all slots ([7] = big reads): with the slots' own streams that stays below the number of hardware work queues
     // (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 below), so streams do not alias onto one queue and serialise falsely.
-    cudaStream_t bt_stream[8] = {nullptr};
+    cudaStream_t bt_stream[kBtMid0] = {nullptr};
+    cudaStream_t mid_stream[kBtMidStreams] = {nullptr};   // handed out round robin to the mid-class launches of all slots
+    unsigned mid_rr = 0;
     int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
     Slot slot[kMaxSlots];
     // profiling (slot 0 only)
@@ -361,6 +377,8 @@ static int config_backtrack()
     CK(cudaFuncSetAttribute(k_bt_walk<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtWalkSmem<CAP>)));
     MM2GB_BT_CLASSES(X)
 #undef X
+    CK(cudaFuncSetAttribute(k_bt_sort_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1]));
+    CK(cudaFuncSetAttribute(k_bt_walk_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_walk_mid_smem(kBtCaps[kBtBig - 1])));
     return MM2GB_OK;
 }
 
@@ -387,6 +405,17 @@ static void launch_backtrack_big(cudaStream_t s, const uint4 *d_a, const int *d_
                                       sl.d_st, sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos, sl.d_ctr);
 }
 
+// reads of up to cap anchors (8193 .. 196608): global-memory keys, serial parts in shared memory
+static void launch_backtrack_mid(cudaStream_t s, const uint4 *d_a, const int *d_f, const int *d_p, const long long *d_off, const int *list, int n_list,
+                                 int cap, const BtParams &bp, Slot &sl)
+{
+    if (n_list <= 0) return;
+    k_bt_sort_mid<<<n_list, 32, (size_t)cap, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_nz, cap);
+    k_bt_walk_mid<<<n_list, 32, bt_walk_mid_smem(cap), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_zs, sl.d_pay2,
+                                                          sl.d_st, sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos,
+                                                          sl.d_bpos, sl.d_ctr, cap);
+}
+
 // the four per-read result arrays of a batch of n_reads reads, device and pinned host side
 static void slice_rinfo(Slot &sl, int n_reads)
 {
@@ -402,16 +431,21 @@ static void slice_rinfo(Slot &sl, int n_reads)
 // by size class and upload the per-class read lists
 static int prepare_backtrack(Slot &sl, cudaStream_t s, const long long *off_rel, int n_reads)
 {
-    static const int caps[7] = {1024, 1536, 2048, 3072, 4096, 6144, 8192};
-    int *cnt = sl.bt_cnt, *base = sl.bt_base, fill[8];
-    auto cls = [&](long long n) { for (int k = 0; k < 7; ++k) if (n <= caps[k]) return k; return 7; };
-    for (int k = 0; k < 8; ++k) cnt[k] = 0;
+    int *cnt = sl.bt_cnt, *base = sl.bt_base, fill[kBtClasses];
+    const int mid_min = bt_mid_min();
+    auto cls = [&](long long n) {
+        for (int k = 0; k < kBtMid0; ++k) if (n <= kBtCaps[k]) return k;
+        if (n <= mid_min) return kBtBig;
+        for (int k = kBtMid0; k < kBtBig; ++k) if (n <= kBtCaps[k]) return k;
+        return kBtBig;
+    };
+    for (int k = 0; k < kBtClasses; ++k) cnt[k] = 0;
     for (int r = 0; r < n_reads; ++r) ++cnt[cls(off_rel[r + 1] - off_rel[r])];
     base[0] = 0;
-    for (int k = 0; k < 8; ++k) { base[k + 1] = base[k] + cnt[k]; fill[k] = base[k]; }
+    for (int k = 0; k < kBtClasses; ++k) { base[k + 1] = base[k] + cnt[k]; fill[k] = base[k]; }
     for (int r = 0; r < n_reads; ++r) sl.h_list[fill[cls(off_rel[r + 1] - off_rel[r])]++] = r;
     slice_rinfo(sl, n_reads);
-    if (base[8]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[8] * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (base[kBtClasses]) CK(cudaMemcpyAsync(sl.d_list, sl.h_list, (size_t)base[kBtClasses] * sizeof(int), cudaMemcpyHostToDevice, s));
     return MM2GB_OK;
 }
 
@@ -432,12 +466,13 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         // fork: one auxiliary stream per non-empty size class, joined back into the slot's stream
         ProfScope ps(c, T_BACKTRACK, s, prof);
         CK(cudaEventRecord(sl.bt_fork, s));
-        for (int k = 6; k >= 0; --k) { // longest first
+        for (int k = kBtBig - 1; k >= 0; --k) { // longest first
             if (!cnt[k]) continue;
-            cudaStream_t bs = c->bt_stream[k];
+            cudaStream_t bs = k >= kBtMid0 ? c->mid_stream[c->mid_rr++ % kBtMidStreams] : c->bt_stream[k];
             CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
             const int *list = sl.d_list + base[k];
-            switch (k) {
+            if (k >= kBtMid0) launch_backtrack_mid(bs, d_a, d_f, d_p, d_off, list, cnt[k], kBtCaps[k], bp, sl);
+            else switch (k) {
             case 6: launch_backtrack<8192>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             case 5: launch_backtrack<6144>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
             case 4: launch_backtrack<4096>(bs, d_a, d_f, d_p, d_off, list, cnt[k], bp, sl); break;
@@ -450,11 +485,11 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         }
         // the big reads stay on the slot's own stream (next to the forked classes): their kernels are a few long serial warps,
         // and on a stream shared by all slots the chunks of a batch of long reads would queue behind each other
-        if (cnt[7]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, sl.d_list + base[7], cnt[7], false, bp, sl);
-        for (int k = 6; k >= 0; --k)
+        if (cnt[kBtBig]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, sl.d_list + base[kBtBig], cnt[kBtBig], false, bp, sl);
+        for (int k = kBtBig - 1; k >= 0; --k)
             if (cnt[k]) CK(cudaStreamWaitEvent(s, sl.bt_join[k], 0));
         // whatever the shared-memory kernels handed over (normally nothing: 256 CTAs that exit at once)
-        if (base[7]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, nullptr, 0, true, bp, sl);
+        if (base[kBtMid0]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, nullptr, 0, true, bp, sl);
     }
     CK(cudaGetLastError());
     return MM2GB_OK;
@@ -491,7 +526,7 @@ static void free_slot(Slot &s)
     cudaFreeHost(s.h_b); cudaFreeHost(s.h_rinfo); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
     if (s.bt_fork) cudaEventDestroy(s.bt_fork);
-    for (int k = 0; k < 8; ++k) if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]);
+    for (int k = 0; k < kBtClasses; ++k) if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -560,7 +595,8 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         rc = config_backtrack();
         if (rc) goto bad;
         if (c->chains_ok)
-            for (int k = 0; k < 8; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
+            for (int k = 0; k < kBtMid0; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
+            for (int k = 0; k < kBtMidStreams; ++k) CKC(cudaStreamCreateWithFlags(&c->mid_stream[k], cudaStreamNonBlocking));
         const size_t n = max_anchors, n_groups = (n + 31) / 32, n_blocks = (n + kRangeThreads - 1) / kRangeThreads;
         const size_t n_units_cap = n_groups + (size_t)max_reads + 2;
         for (int i = 0; i < n_slots; ++i) {
@@ -568,7 +604,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CKC(cudaEventCreateWithFlags(&s.bt_fork, cudaEventDisableTiming));
-            for (int k = 0; k < 8; ++k) CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
+            for (int k = 0; k < kBtClasses; ++k) CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
             if (c->host_io) CKC(cudaMalloc(&s.d_a, n * sizeof(uint4)));
             CKC(cudaMalloc(&s.d_off, ((size_t)max_reads + 1) * sizeof(long long)));
             CKC(cudaMalloc(&s.d_st, n * sizeof(int)));
@@ -625,7 +661,8 @@ extern "C" void mm2gb_ctx_destroy(mm2gb_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (int i = 0; i < kMaxSlots; ++i) free_slot(c->slot[i]);
-    for (int k = 0; k < 8; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
+    for (int k = 0; k < kBtMid0; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
+    for (int k = 0; k < kBtMidStreams; ++k) if (c->mid_stream[k]) cudaStreamDestroy(c->mid_stream[k]);
     prof_collect(c);
     cudaFree(c->d_lut);
     delete c;

@@ -28,6 +28,8 @@ def _forest(rng, n, kind):
     """random (f, p): p[i] < i or -1; f > 0.  `kind` picks the score distribution."""
     i = np.arange(n)
     back = rng.integers(1, 6, n)
+    far = rng.random(n) < 0.02                                  # links of 255 anchors or more (the escape of the one-byte links)
+    back = np.where(far, rng.integers(255, 3000, n), back)
     p = np.where((rng.random(n) < 0.85) & (i - back >= 0), i - back, -1).astype(np.int32)
     if kind == "few":          # a handful of distinct scores: huge tie groups, one radix level
         f = rng.choice([40, 41, 55, 70, 300], n)
@@ -51,9 +53,13 @@ def _forest(rng, n, kind):
 
 @pytest.mark.parametrize("kind", ["few", "narrow", "wide", "cluster", "chainlike", "huge"])
 @pytest.mark.parametrize("min_cnt,min_score", [(3, 40), (1, 1), (2, 60)])
-def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score):
+def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score, monkeypatch):
+    if min_cnt != 3:    # two of the three parameter sets send every read above 8192 anchors to the mid kernels (default: above 32768)
+        monkeypatch.setenv("MM2GB_BT_MID_MIN", "8192")
     rng = np.random.default_rng(hash((kind, min_cnt)) % (1 << 31))
-    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 66, 200, 1000, 1024, 1025, 2048, 3000, 4096, 5000, 8192, 8193, 9000, 20000, 70001]
+    # every size class: shared-memory kernels (<= 8192), mid kernels (16k / 32k / 64k / 128k / 192k anchors), global-memory kernels
+    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 66, 200, 1000, 1024, 1025, 2048, 3000, 4096, 5000, 8192, 8193, 9000, 16384, 20000, 40000,
+             70001, 140000, 196608, 196609]
     reads, fs, ps = [], [], []
     for n in sizes:
         a = synth.ont_like_anchors(rng, max(n, 1), noise_frac=0.0)[:n]
@@ -66,11 +72,11 @@ def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score):
     off[1:] = np.cumsum(sizes)
     a, f, p = np.concatenate(reads), np.concatenate(fs), np.concatenate(ps)
     misc = pkg.map_ont_misc(min_cnt=min_cnt, min_score=min_score)
-    with pkg.ChainContext(misc, max_anchors=1 << 18, max_reads=64, n_slots=1) as c:
+    with pkg.ChainContext(misc, max_anchors=1 << 20, max_reads=64, n_slots=1) as c:
         u, n_u, b, n_b, nd = c.backtrack_device(a, off, f, p)
     _compare(pkg, misc, a, off, f, p, u, n_u, b, n_b)
-    # reads above 8192 anchors, scores >= 2^19 and reads with more chains than the shared-memory key buffer holds all stay on
-    # the device (k_bt_sort_big / k_bt_walk_big): nothing is handed to the host implementation
+    # reads above 8192 anchors (k_bt_*_mid up to 196608, k_bt_*_big beyond), scores >= 2^19 and reads with more chains than the
+    # shared-memory key buffer holds (device overflow list -> k_bt_*_big) all stay on the device: nothing goes to the host code
     assert nd == 0
 
 
