@@ -149,7 +149,7 @@ def host_stage_alone(pkg, misc, a, off, f, p, n_threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MM2GB_BENCH_WORKLOAD", "ont"), choices=sorted(WORKLOADS))
@@ -246,7 +246,7 @@ def main():
     out = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
            "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
     host_threads = max(1, cpu_threads() // max(1, world))
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 10))
     for _ in range(2):
         ctx_e2e.chain(h_a, off, out=out, packed=True)
     barrier()
@@ -285,13 +285,33 @@ def main():
 
     sec = ms_max / 1e3
     value = tot_pairs * args.steps / sec
+    # kernels launched per step (mirrors enqueue_kernels / enqueue_backtrack in chain_core.cu): 5 range/unit kernels, k_score_long
+    # + the two k_score_units instantiations, then a sort + a walk kernel per non-empty chain-extraction size class (7 shared-memory
+    # classes, the mid classes above MM2GB_BT_MID_MIN = 32768 anchors, the global-memory class) and the overflow pass
     rn = np.diff(off)
-    bt_set = {int(np.searchsorted([1024, 1536, 2048, 3072, 4096, 6144, 8192], x)) for x in rn}
-    bt_classes = len(bt_set) + (1 if bt_set - {7} else 0)   # + the overflow pass behind the shared-memory classes
+    small = [1024, 1536, 2048, 3072, 4096, 6144, 8192]
+    mid = [12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608]
+    mid_min = max(8192, int(os.environ.get("MM2GB_BT_MID_MIN", "32768")))
+
+    def bt_class(x):
+        if x <= small[-1]:
+            return int(np.searchsorted(small, x))
+        if x <= mid_min or x > mid[-1]:
+            return 99
+        return 7 + int(np.searchsorted(mid, x))
+    bt_set = {bt_class(int(x)) for x in rn}
+    bt_classes = len(bt_set) + (1 if any(c < 7 for c in bt_set) else 0)
     dp_ms = sum(prof[k][0] / max(1, prof[k][1]) for k in ("range", "units", "score"))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # DRAM bytes of one k_score_units launch on this workload from the committed `ncu --set full` capture (profiles/traffic.json)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -304,7 +324,7 @@ def main():
     issue_peak = n_sm * 4 * 32 * sm_mhz * 1e6          # thread-instructions/s: 4 schedulers x 32 lanes per SM
     issue_ach = INSTR_PER_PAIR * pairs / score_avg_s
     roofline = {"bound": "hbm", "kernel": "k_score_units", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
+                "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
                 "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms,
                 "note": "this kernel is integer-issue bound, not HBM-bound (~%d pairs x %.0f integer ops per 24 B): see issue" % (round(pairs / max(1, n)), INSTR_PER_PAIR),
                 "issue": {"bound": "int-issue", "achieved": issue_ach, "peak": issue_peak, "unit": "algorithmic int-ops/s", "frac": issue_ach / issue_peak,
@@ -326,7 +346,7 @@ def main():
                     "slots": 6, "chunk_anchors": e2e_cap,
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
-            "gpu_launches": (7 + 2 * bt_classes) * args.steps, "clocks": clocks}
+            "gpu_launches": (8 + 2 * bt_classes) * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
     print(json.dumps(line))

@@ -42,6 +42,8 @@ struct BtParams { int min_cnt, min_sc, max_drop; };
 // ---- key traits ---------------------------------------------------------------------------------------------------
 struct ZKey {   // (score, index) pair packed in 32 bits, ordered by score only (radix_sort_128x on mm128_t.x = f)
     typedef unsigned T;
+    static constexpr bool kPosKey = true;   // positions fit the index field: (score, position) compares as one word
+    __device__ static __forceinline__ unsigned poskey(T k, int pos) { return (k & ~kBtIdxMask) | (unsigned)pos; }
     __device__ static __forceinline__ unsigned digit(T k, int shift) { return ((k >> kBtIdxBits) >> shift) & 255u; }
     __device__ static __forceinline__ bool less(T a, T b) { return (a >> kBtIdxBits) < (b >> kBtIdxBits); }
     __device__ static __forceinline__ unsigned long long key64(T k) { return (unsigned long long)(k >> kBtIdxBits); }
@@ -51,6 +53,8 @@ struct ZKey {   // (score, index) pair packed in 32 bits, ordered by score only 
 };
 struct ZKey64 { // the same pair in 64 bits (any read length, any score): score << 32 | index
     typedef unsigned long long T;
+    static constexpr bool kPosKey = false;
+    __device__ static __forceinline__ unsigned poskey(T, int) { return 0; }
     __device__ static __forceinline__ unsigned digit(T k, int shift) { return ((unsigned)(k >> 32) >> shift) & 255u; }
     __device__ static __forceinline__ bool less(T a, T b) { return (unsigned)(a >> 32) < (unsigned)(b >> 32); }
     __device__ static __forceinline__ unsigned long long key64(T k) { return k >> 32; }
@@ -60,6 +64,8 @@ struct ZKey64 { // the same pair in 64 bits (any read length, any score): score 
 };
 struct WKey {   // chain start position x (64 bit); the chain id travels in a separate payload array
     typedef unsigned long long T;
+    static constexpr bool kPosKey = false;
+    __device__ static __forceinline__ unsigned poskey(T, int) { return 0; }
     __device__ static __forceinline__ unsigned digit(T k, int shift) { return (unsigned)(k >> shift) & 255u; }
     __device__ static __forceinline__ bool less(T a, T b) { return a < b; }
     __device__ static __forceinline__ unsigned long long key64(T k) { return k; }
@@ -88,9 +94,14 @@ __device__ void bt_rank_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA,
             const int m = be - bs;
             if (m >= 2 && m <= 64) {
                 int r = 0;
-                for (int j = bs; j < be; ++j) {
-                    const K kj = A[j];
-                    r += (KO::less(kj, key) || (!KO::less(key, kj) && j < e)) ? 1 : 0;
+                if constexpr (KO::kPosKey) { // stable order = order of (score, position): one compare per bucket mate
+                    const unsigned ce = KO::poskey(key, e);
+                    for (int j = bs; j < be; ++j) r += KO::poskey(A[j], j) < ce ? 1 : 0;
+                } else {
+                    for (int j = bs; j < be; ++j) {
+                        const K kj = A[j];
+                        r += (KO::less(kj, key) || (!KO::less(key, kj) && j < e)) ? 1 : 0;
+                    }
                 }
                 tmpA[bs + r] = key;
                 if (PAY) tmpPay[bs + r] = pay[e];
