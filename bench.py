@@ -146,7 +146,25 @@ def host_stage_alone(pkg, misc, a, off, f, p, n_threads):
     return best
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries print to stdout behind our back (NCCL: "NCCL version ..." at the first collective): everything but the result
+    # line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -177,7 +195,7 @@ def main():
         pairs = sum(v[0] for v in vals); dt = sum(v[1] for v in vals); nr = sum(v[2] for v in vals)
         val = pairs / dt
         info["value"] = val
-        print(json.dumps({"impl": "reference", "metric": "chaining anchor-pairs/s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": "chaining anchor-pairs/s", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                           "config": cfg, "reads_per_s": nr / dt, "cpu_baseline": info,
@@ -349,7 +367,7 @@ def main():
             "gpu_launches": (8 + 2 * bt_classes) * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
-    print(json.dumps(line))
+    emit(line)
     ctx.close()
     ctx_e2e.close()
     if dist is not None:
