@@ -166,6 +166,21 @@ __device__ void bt_flag_pass(typename KO::T *A, PAYT *pay, int lo, int hi, int s
             unsigned d = KO::digit(carried, shift);
             do {
                 const int pos = (int)cnt[d], endd = (int)st[d + 1];
+                {   // common case in shuffled data: the element at the cursor is foreign -- a plain swap, nothing to shift
+                    // (every lane reads the same words: no ballot, two dependent loads per step)
+                    const K front = A[pos];
+                    const unsigned df = KO::digit(front, shift);
+                    if (df != d) {
+                        const PAYT fpay = PAY ? pay[pos] : (PAYT)0;
+                        __syncwarp();
+                        if (lane == 0) { A[pos] = carried; if (PAY) pay[pos] = cpay; cnt[d] = (unsigned)(pos + 1); }
+                        __syncwarp();
+                        carried = front;
+                        cpay = fpay;
+                        d = df;
+                        continue;
+                    }
+                }
                 // elements of bucket d sitting at its cursor are pushed one slot to the right (each is evicted by the
                 // arriving element and re-placed at the next slot); the first foreign element after them is evicted for good
                 int L = 0;
@@ -260,21 +275,33 @@ __device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT
 }
 
 // ---- the same sort for reads too long for shared-memory keys ------------------------------------------------------------
-// One American-flag pass over A[lo, hi) in GLOBAL memory whose serial walk runs on a shared-memory copy of the DIGITS
-// (one byte per element, D[0 .. hi-lo)).  The pass is a deterministic walk over the original array: positions at or
-// behind a bucket's cursor still hold their original element, so the walk needs nothing but the digits and the cursors
-// and can emit, per slot, the ORIGINAL position of the element that ends up there (src[], global, write-only during the
-// walk); the keys are moved afterwards by one parallel gather.  A serial step costs a few shared-memory round trips
-// instead of an L2 round trip.  Bucket boundaries -> st[0..256] (absolute positions).
+// One American-flag pass over A[lo, hi) in GLOBAL memory, reformulated so that its serial part touches two shared-memory
+// words per step and nothing in the pass costs more than O(1) per element.
+//
+// The reference's pass (ksort.h:116-139) is a deterministic walk: every bucket's region is consumed front to back by a
+// cursor, positions at or behind a cursor still hold their original element, and an element that sits in its own region
+// ("own") never changes the walk -- an arriving element is dropped at the cursor, the own elements behind it move up by one
+// and the first FOREIGN element after them is carried on.  So:
+//   * control flow depends on the foreign elements only.  They are compacted, in position order, into tokens
+//     (digit in shared memory, position in global memory); region r owns tokens [fst[r], fen[r]).
+//   * the walk: "carried element with digit d arrives in region d, evicts that region's next foreign token" is
+//     g2 = cur[d]++; next digit = D[g2]  -- two dependent shared-memory loads.  During region k's own turn (the outer
+//     loop) its remaining foreign tokens start cycles and are replaced IN PLACE by the element that closes the cycle.
+//   * where everything lands follows in parallel afterwards: the j-th arrival in region d sits at the region start (j = 0) or
+//     one behind the (j-1)-th evicted token; an own element moves up by one iff it lies before the last token evicted by an
+//     arrival (ecut[d]); a cycle-closing element takes the position of the token that opened the cycle.
+// The O(run length) shifting of the literal algorithm (the hot spot of the first version of this kernel) is gone.
+// Scratch (global, one unsigned per element each): tok (position -> token or ~0 for own), fpos (token -> position),
+// nxt (token -> token it evicted on arrival, or 2^31 | opening token).  Bucket boundaries -> st[0..256] (absolute positions).
 template <class KO>
-__device__ void bt_flag_pass_dig(typename KO::T *A, typename KO::T *tmpA, unsigned *src, int lo, int hi, int shift, unsigned *cnt,
-                                 unsigned *st, unsigned char *D, int lane)
+__device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, unsigned *tok, unsigned *fpos, unsigned *nxt, int lo, int hi,
+                                int shift, unsigned *cnt, unsigned *st, unsigned *fst, unsigned *fen, int *ecut, unsigned char *D, int lane)
 {
     typedef typename KO::T K;
-    const unsigned full = 0xffffffffu;
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     const int m = hi - lo;
     K *Al = A + lo, *Tl = tmpA + lo;
-    unsigned *sl = src + lo;
+    unsigned *tk = tok + lo, *fp = fpos + lo, *nx = nxt + lo;
     for (int d = lane; d < 256; d += 32) cnt[d] = 0;
     __syncwarp();
     for (int e0 = 0; e0 < m; e0 += 128) { // 4 coalesced key loads per lane in flight
@@ -299,67 +326,87 @@ __device__ void bt_flag_pass_dig(typename KO::T *A, typename KO::T *tmpA, unsign
             if (lane >= d) incl += y;
         }
         unsigned run = incl - sum;
-        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            st[lane * 8 + q] = run;
-            cnt[lane * 8 + q] = run;        // cursor of the bucket
-            run += c[q];
-        }
+        for (int q = 0; q < 8; ++q) { st[lane * 8 + q] = run; run += c[q]; }
         if (lane == 31) st[256] = (unsigned)m;
     }
     __syncwarp();
-    bool moved = false;
-    for (int k = 0; k < 256; ++k) {
-        const int endk = (int)st[k + 1];
-        int c = (int)cnt[k];
-        while (c < endk) {
-            // elements that already sit in their home bucket stay where they are
-            const int e = c + lane;
-            const bool mis = e < endk && D[e] != (unsigned char)k;
-            const unsigned mm = __ballot_sync(full, mis);
-            const int stay = mm ? __ffs(mm) - 1 : min(32, endk - c);
-            if (lane < stay) sl[e] = (unsigned)e;
-            c += stay;
-            if (!mm) continue;
-            moved = true;
-            int s = c;                      // original position of the carried element
-            unsigned d = D[s];
-            do {
-                const int pos = (int)cnt[d], endd = (int)st[d + 1];
-                // elements of bucket d sitting at its cursor are pushed one slot to the right; the first foreign element
-                // after them is evicted and carried on
-                int L = 0;
-                unsigned dn;
-                for (;;) {
-                    const int q = pos + L + lane;
-                    const unsigned dq = q < endd ? (unsigned)D[q] : 0x100u;
-                    const unsigned nm = __ballot_sync(full, dq != d);
-                    const int t = nm ? __ffs(nm) - 1 : 32;
-                    if (lane < t) sl[q + 1] = (unsigned)q;
-                    if (nm) { dn = __shfl_sync(full, dq, t); L += t; break; }
-                    L += 32;
-                }
-                if (lane == 0) { sl[pos] = (unsigned)s; cnt[d] = (unsigned)(pos + L + 1); }
-                __syncwarp();
-                s = pos + L;
-                d = dn;
-            } while (d != (unsigned)k);
-            if (lane == 0) sl[c] = (unsigned)s;
-            ++c;
+    // foreign elements -> tokens, region by region (= ascending positions); the digits are compacted in place (token <= position)
+    int g = 0;
+    for (int rb = 0; rb < 256; rb += 32) {
+        const unsigned s0l = st[rb + lane], s1l = st[rb + lane + 1];
+        unsigned mask = __ballot_sync(full, s1l > s0l);
+        while (mask) {
+            const int q = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int r = rb + q;
+            const int s0 = (int)__shfl_sync(full, s0l, q), s1 = (int)__shfl_sync(full, s1l, q);
+            if (lane == 0) { fst[r] = (unsigned)g; cnt[r] = (unsigned)g; }   // cnt[r]: the region's next foreign token
+            for (int c = s0; c < s1; c += 32) {
+                const int e = c + lane;
+                const unsigned d = e < s1 ? (unsigned)D[e] : (unsigned)r;
+                const bool fo = d != (unsigned)r;
+                const unsigned fm = __ballot_sync(full, fo);
+                const int t = g + __popc(fm & lt);
+                if (fo) { D[t] = (unsigned char)d; fp[t] = (unsigned)e; }
+                if (e < s1) tk[e] = fo ? (unsigned)t : 0xffffffffu;
+                g += __popc(fm);
+            }
+            if (lane == 0) fen[r] = (unsigned)g;
         }
     }
     __syncwarp();
-    if (moved) {
-        for (int e0 = 0; e0 < m; e0 += 128) { // gather through src: 4 independent chains of two loads per lane
-            unsigned sv[4];
+    if (g > 0) {
+        // the walk (every lane runs it; lane 0 writes)
+        for (int rb = 0; rb < 256; rb += 32) {
+            const unsigned s0l = st[rb + lane], s1l = st[rb + lane + 1];
+            unsigned mask = __ballot_sync(full, s1l > s0l);
+            while (mask) {
+                const int q = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const unsigned k = (unsigned)(rb + q);
+                const unsigned fe = fen[k];
+                unsigned h = cnt[k];
+                if (lane == 0) ecut[k] = (int)h;   // tokens below h were evicted by arrivals; turned into a position below
+                while (h < fe) {
+                    const unsigned c0 = h++;
+                    unsigned carried = c0;
+                    unsigned d = D[c0];
+                    while (d != k) {
+                        const unsigned g2 = cnt[d];
+                        if (lane == 0) { cnt[d] = g2 + 1; nx[carried] = g2; }
+                        __syncwarp();
+                        carried = g2;
+                        d = D[g2];
+                    }
+                    if (lane == 0) nx[carried] = 0x80000000u | c0;
+                }
+            }
+        }
+        __syncwarp();
+        for (int r = lane; r < 256; r += 32) {
+            int ec = -1;
+            if (st[r + 1] > st[r]) { const unsigned h = (unsigned)ecut[r]; if (h > fst[r]) ec = (int)fp[h - 1]; }
+            ecut[r] = ec;
+        }
+        __syncwarp();
+        for (int e0 = 0; e0 < m; e0 += 128) { // placement: up to three dependent loads per element, 4 elements per lane in flight
             K kv[4];
+            unsigned tv[4], v[4], dst[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; sv[t] = e < m ? sl[e] : 0u; }
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Al[e] : (K)0; tv[t] = e < m ? tk[e] : 0xffffffffu; }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Al[sv[t]] : (K)0; }
+            for (int t = 0; t < 4; ++t) v[t] = tv[t] != 0xffffffffu ? nx[tv[t]] : 0u;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Tl[e] = kv[t]; }
+            for (int t = 0; t < 4; ++t) {
+                const int e = e0 + t * 32 + lane;
+                const unsigned d = KO::digit(kv[t], shift);
+                if (tv[t] == 0xffffffffu) dst[t] = (unsigned)e + (e < ecut[d] ? 1u : 0u);
+                else if (v[t] & 0x80000000u) dst[t] = fp[v[t] & 0x7fffffffu];
+                else dst[t] = v[t] == fst[d] ? st[d] : fp[v[t] - 1] + 1u;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Tl[dst[t]] = kv[t]; }
         }
         __syncwarp();
         for (int e0 = 0; e0 < m; e0 += 128) {
@@ -370,24 +417,27 @@ __device__ void bt_flag_pass_dig(typename KO::T *A, typename KO::T *tmpA, unsign
             for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Al[e] = kv[t]; }
         }
     }
+    __syncwarp();
     for (int d = lane; d <= 256; d += 32) st[d] += (unsigned)lo;
     __syncwarp();
 }
 
-// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors: passes over more than `kcap` elements are
-// digit walks (above), any bucket of at most kcap elements is copied to shared memory (KA, which aliases D) and finished
-// there by bt_sort.  rows: 4 levels (32-bit scores) of kBtRow entries.
+// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors: every pass is bt_flag_pass_fq; only buckets of at
+// most kcap (<= cap / 8) elements are copied to shared memory (KA, which aliases D) and finished there by bt_sort -- for
+// a few hundred elements the literal algorithm beats the fixed cost of a pass through global memory.
+// rows: 4 levels (32-bit scores) of kBtRow entries.
+struct BtFqScratch { unsigned *cnt, *rows, *fst, *fen; int *ecut; unsigned *tok, *fpos, *nxt; };
+
 template <class KO>
-__device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, unsigned *src, int n, unsigned *cnt, unsigned *rows,
-                            unsigned char *D, int kcap, int lane)
+__device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, BtFqScratch q, unsigned char *D, int kcap, int lane)
 {
     typedef typename KO::T K;
     const unsigned full = 0xffffffffu;
     K *KA = reinterpret_cast<K *>(D);
     if (n <= 1) return;
     BtSortScratch<unsigned> sc;
-    sc.cnt = cnt;
-    sc.start = rows;
+    sc.cnt = q.cnt;
+    sc.start = q.rows;
     if (n <= kcap) {
         for (int e = lane; e < n; e += 32) KA[e] = A[e];
         __syncwarp();
@@ -406,13 +456,13 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, unsigned *s
     int shift = 56;
     while (((diff >> shift) & 255ULL) == 0) shift -= 8;
     int lv = 0;
-    unsigned *row = rows;
-    bt_flag_pass_dig<KO>(A, tmpA, src, 0, n, shift, cnt, row, D, lane);
+    unsigned *row = q.rows;
+    bt_flag_pass_fq<KO>(A, tmpA, q.tok, q.fpos, q.nxt, 0, n, shift, q.cnt, row, q.fst, q.fen, q.ecut, D, lane);
     if (shift) bt_rank_sort<KO, false, unsigned, unsigned>(A, nullptr, tmpA, nullptr, 0, n, shift, row, lane);
     if (lane == 0) { row[257] = 0; row[258] = (unsigned)shift; }
     __syncwarp();
     while (lv >= 0) {
-        row = rows + lv * kBtRow;
+        row = q.rows + lv * kBtRow;
         const int sh = (int)row[258];
         int k = (int)row[257];
         if (sh == 0 || k >= 256) { --lv; continue; }
@@ -434,7 +484,7 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, unsigned *s
             const int m = bhi - blo;
             for (int e = lane; e < m; e += 32) KA[e] = A[blo + e];
             __syncwarp();
-            sc.start = rows + (lv + 1) * kBtRow;
+            sc.start = q.rows + (lv + 1) * kBtRow;
             bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA + blo, nullptr, m, sc, lane);
             __syncwarp();
             for (int e = lane; e < m; e += 32) A[blo + e] = KA[e];
@@ -442,8 +492,8 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, unsigned *s
             continue;
         }
         ++lv;
-        unsigned *crow = rows + lv * kBtRow;
-        bt_flag_pass_dig<KO>(A, tmpA, src, blo, bhi, nsh, cnt, crow, D, lane);
+        unsigned *crow = q.rows + lv * kBtRow;
+        bt_flag_pass_fq<KO>(A, tmpA, q.tok, q.fpos, q.nxt, blo, bhi, nsh, q.cnt, crow, q.fst, q.fen, q.ecut, D, lane);
         if (nsh) bt_rank_sort<KO, false, unsigned, unsigned>(A, nullptr, tmpA, nullptr, blo, bhi, nsh, crow, lane);
         if (lane == 0) { crow[257] = 0; crow[258] = (unsigned)nsh; }
         __syncwarp();
@@ -565,14 +615,18 @@ k_bt_sort_big(const int *__restrict__ f, const long long *__restrict__ off, cons
 }
 
 // Reads of 8193 .. 196608 anchors ("mid" classes): 64-bit keys in global scratch as in k_bt_sort_big, but the serial part of
-// every pass runs in shared memory (bt_sort_mid).  Dynamic shared memory: cap bytes (digits / keys of small buckets).
+// every pass runs on one-byte tokens in shared memory (bt_flag_pass_fq).  Dynamic shared memory: cap bytes (digits / tokens;
+// keys of buckets of <= 512 elements).
 __global__ void __launch_bounds__(32)
 k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
-              unsigned long long *zk_scr, unsigned long long *zk2_scr, unsigned *src_scr, int *__restrict__ nz_out, int cap)
+              unsigned long long *zk_scr, unsigned long long *zk2_scr, unsigned *tok_scr, unsigned *fpos_scr, unsigned *nxt_scr,
+              int *__restrict__ nz_out, int cap)
 {
     extern __shared__ int4 bt_raw[];
     __shared__ unsigned s_cnt[256];
     __shared__ unsigned s_rows[4 * kBtRow];     // scores are below 2^31: at most four radix levels
+    __shared__ unsigned s_fst[256], s_fen[256];
+    __shared__ int s_ecut[256];
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;
     const int r = read_list[blockIdx.x];
@@ -583,7 +637,10 @@ k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, cons
     int fmax;
     const int nz = bt_collect<ZKey64>(f + o0, n, bp.min_sc, zk, lane, fmax);
     __syncwarp();
-    bt_sort_mid<ZKey64>(zk, zk2, src_scr + o0, nz, s_cnt, s_rows, reinterpret_cast<unsigned char *>(bt_raw), cap / 8, lane);
+    BtFqScratch q;
+    q.cnt = s_cnt; q.rows = s_rows; q.fst = s_fst; q.fen = s_fen; q.ecut = s_ecut;
+    q.tok = tok_scr + o0; q.fpos = fpos_scr + o0; q.nxt = nxt_scr + o0;
+    bt_sort_mid<ZKey64>(zk, zk2, nz, q, reinterpret_cast<unsigned char *>(bt_raw), min(cap / 8, 512), lane);
     if (lane == 0) nz_out[r] = nz;
 }
 
