@@ -290,148 +290,199 @@ __device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT
 //   * where everything lands follows in parallel afterwards: the j-th arrival in region d sits at the region start (j = 0) or
 //     one behind the (j-1)-th evicted token; an own element moves up by one iff it lies before the last token evicted by an
 //     arrival (ecut[d]); a cycle-closing element takes the position of the token that opened the cycle.
-// The O(run length) shifting of the literal algorithm (the hot spot of the first version of this kernel) is gone.
+// The O(run length) shifting of the literal algorithm (the hot spot of the first version of this kernel) is gone
+// (tests/test_flagpass_model.py checks the reformulation against the literal pass).
+// A CTA of kBtMidThreads threads works on one read: the parallel phases (digits + histogram, placement, copy back, the rank sort
+// of small buckets) use every thread, the token compaction and the walk run on warp 0.  Every thread takes the same path
+// (all control values come from shared memory behind a barrier).
 // Scratch (global, one unsigned per element each): tok (position -> token or ~0 for own), fpos (token -> position),
 // nxt (token -> token it evicted on arrival, or 2^31 | opening token).  Bucket boundaries -> st[0..256] (absolute positions).
+constexpr int kBtMidThreads = 128;
+
+struct BtFqScratch {
+    unsigned *cnt, *rows, *fst, *fen;   // shared: [256], [4 * kBtRow], [256], [256]
+    int *ecut;                          // shared: [256]
+    unsigned *misc;                     // shared: [8] broadcast words
+    unsigned *tok, *fpos, *nxt;         // global, per element
+};
+
 template <class KO>
-__device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, unsigned *tok, unsigned *fpos, unsigned *nxt, int lo, int hi,
-                                int shift, unsigned *cnt, unsigned *st, unsigned *fst, unsigned *fen, int *ecut, unsigned char *D, int lane)
+__device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, const BtFqScratch &q, int lo, int hi, int shift, unsigned *st,
+                                unsigned char *D, int tid)
 {
     typedef typename KO::T K;
+    constexpr int NT = kBtMidThreads;
+    const int lane = tid & 31;
+    const bool w0 = tid < 32;
     const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     const int m = hi - lo;
     K *Al = A + lo, *Tl = tmpA + lo;
-    unsigned *tk = tok + lo, *fp = fpos + lo, *nx = nxt + lo;
-    for (int d = lane; d < 256; d += 32) cnt[d] = 0;
-    __syncwarp();
-    for (int e0 = 0; e0 < m; e0 += 128) { // 4 coalesced key loads per lane in flight
+    unsigned *tk = q.tok + lo, *fp = q.fpos + lo, *nx = q.nxt + lo;
+    unsigned *cnt = q.cnt, *fst = q.fst, *fen = q.fen;
+    int *ecut = q.ecut;
+    for (int d = tid; d < 256; d += NT) cnt[d] = 0;
+    __syncthreads();
+    for (int e0 = 0; e0 < m; e0 += 4 * NT) { // 4 coalesced key loads per thread in flight
         K kv[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Al[e] : (K)0; }
+        for (int t = 0; t < 4; ++t) { const int e = e0 + t * NT + tid; kv[t] = e < m ? Al[e] : (K)0; }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const int e = e0 + t * 32 + lane;
+            const int e = e0 + t * NT + tid;
             if (e < m) { const unsigned d = KO::digit(kv[t], shift); D[e] = (unsigned char)d; atomicAdd(&cnt[d], 1u); }
         }
     }
-    __syncwarp();
-    {   // exclusive scan of 256 counts: 8 per lane (positions relative to lo)
-        unsigned c[8], sum = 0;
+    __syncthreads();
+    if (w0) {
+        {   // exclusive scan of 256 counts: 8 per lane (positions relative to lo)
+            unsigned c[8], sum = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { c[q] = cnt[lane * 8 + q]; sum += c[q]; }
-        unsigned incl = sum;
+            for (int j = 0; j < 8; ++j) { c[j] = cnt[lane * 8 + j]; sum += c[j]; }
+            unsigned incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned y = __shfl_up_sync(full, incl, d);
-            if (lane >= d) incl += y;
-        }
-        unsigned run = incl - sum;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { st[lane * 8 + q] = run; run += c[q]; }
-        if (lane == 31) st[256] = (unsigned)m;
-    }
-    __syncwarp();
-    // foreign elements -> tokens, region by region (= ascending positions); the digits are compacted in place (token <= position)
-    int g = 0;
-    for (int rb = 0; rb < 256; rb += 32) {
-        const unsigned s0l = st[rb + lane], s1l = st[rb + lane + 1];
-        unsigned mask = __ballot_sync(full, s1l > s0l);
-        while (mask) {
-            const int q = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int r = rb + q;
-            const int s0 = (int)__shfl_sync(full, s0l, q), s1 = (int)__shfl_sync(full, s1l, q);
-            if (lane == 0) { fst[r] = (unsigned)g; cnt[r] = (unsigned)g; }   // cnt[r]: the region's next foreign token
-            for (int c = s0; c < s1; c += 32) {
-                const int e = c + lane;
-                const unsigned d = e < s1 ? (unsigned)D[e] : (unsigned)r;
-                const bool fo = d != (unsigned)r;
-                const unsigned fm = __ballot_sync(full, fo);
-                const int t = g + __popc(fm & lt);
-                if (fo) { D[t] = (unsigned char)d; fp[t] = (unsigned)e; }
-                if (e < s1) tk[e] = fo ? (unsigned)t : 0xffffffffu;
-                g += __popc(fm);
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned y = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += y;
             }
-            if (lane == 0) fen[r] = (unsigned)g;
+            unsigned run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { st[lane * 8 + j] = run; run += c[j]; }
+            if (lane == 31) st[256] = (unsigned)m;
         }
-    }
-    __syncwarp();
-    if (g > 0) {
-        // the walk (every lane runs it; lane 0 writes)
+        __syncwarp();
+        // foreign elements -> tokens, region by region (= ascending positions); digits compacted in place (token <= position)
+        int g = 0;
         for (int rb = 0; rb < 256; rb += 32) {
             const unsigned s0l = st[rb + lane], s1l = st[rb + lane + 1];
             unsigned mask = __ballot_sync(full, s1l > s0l);
             while (mask) {
-                const int q = __ffs(mask) - 1;
+                const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const unsigned k = (unsigned)(rb + q);
-                const unsigned fe = fen[k];
-                unsigned h = cnt[k];
-                if (lane == 0) ecut[k] = (int)h;   // tokens below h were evicted by arrivals; turned into a position below
-                while (h < fe) {
-                    const unsigned c0 = h++;
-                    unsigned carried = c0;
-                    unsigned d = D[c0];
-                    while (d != k) {
-                        const unsigned g2 = cnt[d];
-                        if (lane == 0) { cnt[d] = g2 + 1; nx[carried] = g2; }
-                        __syncwarp();
-                        carried = g2;
-                        d = D[g2];
-                    }
-                    if (lane == 0) nx[carried] = 0x80000000u | c0;
+                const int r = rb + j;
+                const int s0 = (int)__shfl_sync(full, s0l, j), s1 = (int)__shfl_sync(full, s1l, j);
+                if (lane == 0) { fst[r] = (unsigned)g; cnt[r] = (unsigned)g; }   // cnt[r]: the region's next foreign token
+                for (int c = s0; c < s1; c += 32) {
+                    const int e = c + lane;
+                    const unsigned d = e < s1 ? (unsigned)D[e] : (unsigned)r;
+                    const bool fo = d != (unsigned)r;
+                    const unsigned fm = __ballot_sync(full, fo);
+                    const int t = g + __popc(fm & lt);
+                    if (fo) { D[t] = (unsigned char)d; fp[t] = (unsigned)e; }
+                    if (e < s1) tk[e] = fo ? (unsigned)t : 0xffffffffu;
+                    g += __popc(fm);
                 }
+                if (lane == 0) fen[r] = (unsigned)g;
             }
         }
         __syncwarp();
-        for (int r = lane; r < 256; r += 32) {
-            int ec = -1;
-            if (st[r + 1] > st[r]) { const unsigned h = (unsigned)ecut[r]; if (h > fst[r]) ec = (int)fp[h - 1]; }
-            ecut[r] = ec;
+        if (g > 0) {
+            // the walk (every lane of warp 0 runs it; lane 0 writes)
+            for (int rb = 0; rb < 256; rb += 32) {
+                const unsigned s0l = st[rb + lane], s1l = st[rb + lane + 1];
+                unsigned mask = __ballot_sync(full, s1l > s0l);
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned k = (unsigned)(rb + j);
+                    const unsigned fe = fen[k];
+                    unsigned h = cnt[k];
+                    if (lane == 0) ecut[k] = (int)h;   // tokens below h were evicted by arrivals; turned into a position below
+                    while (h < fe) {
+                        const unsigned c0 = h++;
+                        unsigned carried = c0;
+                        unsigned d = D[c0];
+                        while (d != k) {
+                            const unsigned g2 = cnt[d];
+                            if (lane == 0) { cnt[d] = g2 + 1; nx[carried] = g2; }
+                            __syncwarp();
+                            carried = g2;
+                            d = D[g2];
+                        }
+                        if (lane == 0) nx[carried] = 0x80000000u | c0;
+                    }
+                }
+            }
+            __syncwarp();
+            for (int r = lane; r < 256; r += 32) {
+                int ec = -1;
+                if (st[r + 1] > st[r]) { const unsigned h = (unsigned)ecut[r]; if (h > fst[r]) ec = (int)fp[h - 1]; }
+                ecut[r] = ec;
+            }
         }
-        __syncwarp();
-        for (int e0 = 0; e0 < m; e0 += 128) { // placement: up to three dependent loads per element, 4 elements per lane in flight
+        if (lane == 0) q.misc[0] = (unsigned)g;
+    }
+    __syncthreads();
+    if (q.misc[0] > 0) {
+        for (int e0 = 0; e0 < m; e0 += 4 * NT) { // placement: up to three dependent loads per element, 4 elements per thread in flight
             K kv[4];
             unsigned tv[4], v[4], dst[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Al[e] : (K)0; tv[t] = e < m ? tk[e] : 0xffffffffu; }
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * NT + tid; kv[t] = e < m ? Al[e] : (K)0; tv[t] = e < m ? tk[e] : 0xffffffffu; }
 #pragma unroll
             for (int t = 0; t < 4; ++t) v[t] = tv[t] != 0xffffffffu ? nx[tv[t]] : 0u;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int e = e0 + t * 32 + lane;
+                const int e = e0 + t * NT + tid;
                 const unsigned d = KO::digit(kv[t], shift);
                 if (tv[t] == 0xffffffffu) dst[t] = (unsigned)e + (e < ecut[d] ? 1u : 0u);
                 else if (v[t] & 0x80000000u) dst[t] = fp[v[t] & 0x7fffffffu];
                 else dst[t] = v[t] == fst[d] ? st[d] : fp[v[t] - 1] + 1u;
             }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Tl[dst[t]] = kv[t]; }
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * NT + tid; if (e < m) Tl[dst[t]] = kv[t]; }
         }
-        __syncwarp();
-        for (int e0 = 0; e0 < m; e0 += 128) {
+        __syncthreads();
+        for (int e0 = 0; e0 < m; e0 += 4 * NT) {
             K kv[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; kv[t] = e < m ? Tl[e] : (K)0; }
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * NT + tid; kv[t] = e < m ? Tl[e] : (K)0; }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int e = e0 + t * 32 + lane; if (e < m) Al[e] = kv[t]; }
+            for (int t = 0; t < 4; ++t) { const int e = e0 + t * NT + tid; if (e < m) Al[e] = kv[t]; }
         }
     }
-    __syncwarp();
-    for (int d = lane; d <= 256; d += 32) st[d] += (unsigned)lo;
-    __syncwarp();
+    __syncthreads();
+    for (int d = tid; d <= 256; d += NT) st[d] += (unsigned)lo;
+    __syncthreads();
 }
 
-// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors: every pass is bt_flag_pass_fq; only buckets of at
-// most kcap (<= cap / 8) elements are copied to shared memory (KA, which aliases D) and finished there by bt_sort -- for
-// a few hundred elements the literal algorithm beats the fixed cost of a pass through global memory.
-// rows: 4 levels (32-bit scores) of kBtRow entries.
-struct BtFqScratch { unsigned *cnt, *rows, *fst, *fen; int *ecut; unsigned *tok, *fpos, *nxt; };
-
+// rank sort of every bucket of 2..64 elements of one pass over A[lo, hi) in global memory, by the whole CTA (bt_rank_sort is
+// the one-warp version): rank = number of bucket mates that order before the element as (score, position)
 template <class KO>
-__device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, BtFqScratch q, unsigned char *D, int kcap, int lane)
+__device__ void bt_rank_sort_blk(typename KO::T *A, typename KO::T *tmpA, int lo, int hi, int shift, const unsigned *start, int tid)
 {
     typedef typename KO::T K;
+    constexpr int NT = kBtMidThreads;
+    for (int e = lo + tid; e < hi; e += NT) {
+        const K key = A[e];
+        const unsigned d = KO::digit(key, shift);
+        const int bs = (int)start[d], be = (int)start[d + 1];
+        const int m = be - bs;
+        int r = e - bs;
+        if (m >= 2 && m <= 64) {
+            r = 0;
+            for (int j = bs; j < be; ++j) {
+                const K kj = A[j];
+                r += (KO::less(kj, key) || (!KO::less(key, kj) && j < e)) ? 1 : 0;
+            }
+        }
+        tmpA[bs + r] = key;
+    }
+    __syncthreads();
+    for (int e = lo + tid; e < hi; e += NT) A[e] = tmpA[e];
+    __syncthreads();
+}
+
+// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors, by a CTA of kBtMidThreads threads: every pass is
+// bt_flag_pass_fq; only buckets of at most kcap (<= cap / 8) elements are copied to shared memory (KA, which aliases D) and
+// finished there by warp 0 with bt_sort -- for a few hundred elements the literal algorithm beats the fixed cost of a pass
+// through global memory.  rows: 4 levels (32-bit scores) of kBtRow entries.
+template <class KO>
+__device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, const BtFqScratch &q, unsigned char *D, int kcap, int tid)
+{
+    typedef typename KO::T K;
+    constexpr int NT = kBtMidThreads;
+    const int lane = tid & 31;
+    const bool w0 = tid < 32;
     const unsigned full = 0xffffffffu;
     K *KA = reinterpret_cast<K *>(D);
     if (n <= 1) return;
@@ -439,64 +490,75 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, BtFq
     sc.cnt = q.cnt;
     sc.start = q.rows;
     if (n <= kcap) {
-        for (int e = lane; e < n; e += 32) KA[e] = A[e];
-        __syncwarp();
-        bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA, nullptr, n, sc, lane);
-        __syncwarp();
-        for (int e = lane; e < n; e += 32) A[e] = KA[e];
-        __syncwarp();
+        if (w0) {
+            for (int e = lane; e < n; e += 32) KA[e] = A[e];
+            __syncwarp();
+            bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA, nullptr, n, sc, lane);
+            __syncwarp();
+            for (int e = lane; e < n; e += 32) A[e] = KA[e];
+        }
+        __syncthreads();
         return;
     }
-    unsigned long long o = 0, an = ~0ULL;
-    for (int e = lane; e < n; e += 32) { const unsigned long long k = KO::key64(A[e]); o |= k; an &= k; }
+    // highest digit in which the keys differ (32-bit scores: two words of OR / AND, reduced through shared memory)
+    if (tid == 0) { q.misc[2] = 0u; q.misc[3] = 0xffffffffu; }
+    __syncthreads();
+    {
+        unsigned o = 0, an = 0xffffffffu;
+        for (int e = tid; e < n; e += NT) { const unsigned k = (unsigned)KO::key64(A[e]); o |= k; an &= k; }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { o |= __shfl_xor_sync(full, o, d); an &= __shfl_xor_sync(full, an, d); }
-    const unsigned long long diff = o ^ an;
+        for (int d = 16; d > 0; d >>= 1) { o |= __shfl_xor_sync(full, o, d); an &= __shfl_xor_sync(full, an, d); }
+        if (lane == 0) { atomicOr(&q.misc[2], o); atomicAnd(&q.misc[3], an); }
+    }
+    __syncthreads();
+    const unsigned diff = q.misc[2] ^ q.misc[3];
     if (!diff) return;
-    int shift = 56;
-    while (((diff >> shift) & 255ULL) == 0) shift -= 8;
+    int shift = 24;
+    while (((diff >> shift) & 255u) == 0) shift -= 8;
     int lv = 0;
     unsigned *row = q.rows;
-    bt_flag_pass_fq<KO>(A, tmpA, q.tok, q.fpos, q.nxt, 0, n, shift, q.cnt, row, q.fst, q.fen, q.ecut, D, lane);
-    if (shift) bt_rank_sort<KO, false, unsigned, unsigned>(A, nullptr, tmpA, nullptr, 0, n, shift, row, lane);
-    if (lane == 0) { row[257] = 0; row[258] = (unsigned)shift; }
-    __syncwarp();
+    bt_flag_pass_fq<KO>(A, tmpA, q, 0, n, shift, row, D, tid);
+    if (shift) bt_rank_sort_blk<KO>(A, tmpA, 0, n, shift, row, tid);
+    if (tid == 0) { row[257] = 0; row[258] = (unsigned)shift; }
+    __syncthreads();
     while (lv >= 0) {
         row = q.rows + lv * kBtRow;
         const int sh = (int)row[258];
         int k = (int)row[257];
         if (sh == 0 || k >= 256) { --lv; continue; }
         int found = -1;
-        while (k < 256) {
+        while (k < 256) { // every warp finds the same bucket
             const int kk = k + lane;
             const bool big = kk < 256 && (int)row[kk + 1] - (int)row[kk] > 64;
             const unsigned bm = __ballot_sync(full, big);
             if (bm) { found = k + __ffs(bm) - 1; break; }
             k += 32;
         }
-        __syncwarp();
-        if (found < 0) { if (lane == 0) row[257] = 256; __syncwarp(); --lv; continue; }
-        if (lane == 0) row[257] = (unsigned)(found + 1);
-        const int blo = (int)row[found], bhi = (int)row[found + 1];
+        int blo = 0, bhi = 0;
+        if (found >= 0) { blo = (int)row[found]; bhi = (int)row[found + 1]; }
+        __syncthreads();   // everyone has read this level's cursor before it moves
+        if (tid == 0) row[257] = (unsigned)(found < 0 ? 256 : found + 1);
+        if (found < 0) { __syncthreads(); --lv; continue; }
         const int nsh = sh > 8 ? sh - 8 : 0;
-        __syncwarp();
         if (bhi - blo <= kcap) { // the whole subtree in shared memory (identity passes are skipped by bt_sort itself)
-            const int m = bhi - blo;
-            for (int e = lane; e < m; e += 32) KA[e] = A[blo + e];
-            __syncwarp();
-            sc.start = q.rows + (lv + 1) * kBtRow;
-            bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA + blo, nullptr, m, sc, lane);
-            __syncwarp();
-            for (int e = lane; e < m; e += 32) A[blo + e] = KA[e];
-            __syncwarp();
+            if (w0) {
+                const int m = bhi - blo;
+                for (int e = lane; e < m; e += 32) KA[e] = A[blo + e];
+                __syncwarp();
+                sc.start = q.rows + (lv + 1) * kBtRow;
+                bt_sort<KO, false, unsigned, unsigned>(KA, nullptr, tmpA + blo, nullptr, m, sc, lane);
+                __syncwarp();
+                for (int e = lane; e < m; e += 32) A[blo + e] = KA[e];
+            }
+            __syncthreads();
             continue;
         }
         ++lv;
         unsigned *crow = q.rows + lv * kBtRow;
-        bt_flag_pass_fq<KO>(A, tmpA, q.tok, q.fpos, q.nxt, blo, bhi, nsh, q.cnt, crow, q.fst, q.fen, q.ecut, D, lane);
-        if (nsh) bt_rank_sort<KO, false, unsigned, unsigned>(A, nullptr, tmpA, nullptr, blo, bhi, nsh, crow, lane);
-        if (lane == 0) { crow[257] = 0; crow[258] = (unsigned)nsh; }
-        __syncwarp();
+        bt_flag_pass_fq<KO>(A, tmpA, q, blo, bhi, nsh, crow, D, tid);
+        if (nsh) bt_rank_sort_blk<KO>(A, tmpA, blo, bhi, nsh, crow, tid);
+        if (tid == 0) { crow[257] = 0; crow[258] = (unsigned)nsh; }
+        __syncthreads();
     }
 }
 
@@ -617,7 +679,7 @@ k_bt_sort_big(const int *__restrict__ f, const long long *__restrict__ off, cons
 // Reads of 8193 .. 196608 anchors ("mid" classes): 64-bit keys in global scratch as in k_bt_sort_big, but the serial part of
 // every pass runs on one-byte tokens in shared memory (bt_flag_pass_fq).  Dynamic shared memory: cap bytes (digits / tokens;
 // keys of buckets of <= 512 elements).
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kBtMidThreads)
 k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
               unsigned long long *zk_scr, unsigned long long *zk2_scr, unsigned *tok_scr, unsigned *fpos_scr, unsigned *nxt_scr,
               int *__restrict__ nz_out, int cap)
@@ -625,23 +687,27 @@ k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, cons
     extern __shared__ int4 bt_raw[];
     __shared__ unsigned s_cnt[256];
     __shared__ unsigned s_rows[4 * kBtRow];     // scores are below 2^31: at most four radix levels
-    __shared__ unsigned s_fst[256], s_fen[256];
+    __shared__ unsigned s_fst[256], s_fen[256], s_misc[8];
     __shared__ int s_ecut[256];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;
     const int r = read_list[blockIdx.x];
     const long long o0 = off[r];
     const int n = (int)(off[r + 1] - o0);
-    if (bp.min_sc < 0 || n > cap) { if (lane == 0) nz_out[r] = -1; return; }
+    if (bp.min_sc < 0 || n > cap) { if (tid == 0) nz_out[r] = -1; return; }
     unsigned long long *zk = zk_scr + o0, *zk2 = zk2_scr + o0;
-    int fmax;
-    const int nz = bt_collect<ZKey64>(f + o0, n, bp.min_sc, zk, lane, fmax);
-    __syncwarp();
+    if (tid < 32) {
+        int fmax;
+        const int nz0 = bt_collect<ZKey64>(f + o0, n, bp.min_sc, zk, tid, fmax);
+        if (tid == 0) s_misc[1] = (unsigned)nz0;
+    }
+    __syncthreads();
+    const int nz = (int)s_misc[1];
     BtFqScratch q;
-    q.cnt = s_cnt; q.rows = s_rows; q.fst = s_fst; q.fen = s_fen; q.ecut = s_ecut;
+    q.cnt = s_cnt; q.rows = s_rows; q.fst = s_fst; q.fen = s_fen; q.ecut = s_ecut; q.misc = s_misc;
     q.tok = tok_scr + o0; q.fpos = fpos_scr + o0; q.nxt = nxt_scr + o0;
-    bt_sort_mid<ZKey64>(zk, zk2, nz, q, reinterpret_cast<unsigned char *>(bt_raw), min(cap / 8, 512), lane);
-    if (lane == 0) nz_out[r] = nz;
+    bt_sort_mid<ZKey64>(zk, zk2, nz, q, reinterpret_cast<unsigned char *>(bt_raw), min(cap / 8, 512), tid);
+    if (tid == 0) nz_out[r] = nz;
 }
 
 template <int CAP>

@@ -410,7 +410,7 @@ static void launch_backtrack_mid(cudaStream_t s, const uint4 *d_a, const int *d_
                                  int cap, const BtParams &bp, Slot &sl)
 {
     if (n_list <= 0) return;
-    k_bt_sort_mid<<<n_list, 32, (size_t)cap, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2,
+    k_bt_sort_mid<<<n_list, kBtMidThreads, (size_t)cap, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2,
                                                   reinterpret_cast<unsigned *>(sl.d_vs), sl.d_nz, cap);
     k_bt_walk_mid<<<n_list, 32, bt_walk_mid_smem(cap), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_zs, sl.d_pay2,
                                                           sl.d_st, sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos,
