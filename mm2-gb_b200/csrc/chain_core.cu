@@ -56,7 +56,7 @@ namespace {
 
 // size classes of the chain-extraction kernels: 0..6 shared-memory kernels (k_bt_sort<CAP> / k_bt_walk<CAP>), 7..11 "mid"
 // (k_bt_sort_mid / k_bt_walk_mid: keys in global scratch, digits / predecessor links in shared memory), 12 = any size
-constexpr int kBtClasses = 17, kBtBig = 16, kBtMid0 = 7, kBtMidStreams = 12;
+constexpr int kBtClasses = 17, kBtBig = 16, kBtMid0 = 7, kBtStreams = 24;
 const int kBtCaps[kBtBig] = {1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608};
 // Reads of 8193 .. mid_min anchors go to the global-memory kernels, longer ones (up to 196608) to the mid kernels.  The two
 // kinds complement each other: the global-memory kernels need no shared memory, so every read of a batch is resident at once
@@ -145,12 +145,13 @@ struct mm2gb_ctx {
     int long_wave = 0;          // the 4096 / 2048 classes go to k_score_long only while the long units fit this many CTAs (0: always)
     bool host_io = true;        // slots own pinned staging + device anchor/f/p buffers (false: device-resident entry points only)
     bool chains_ok = true;      // slots own the chain-extraction buffers (false: DP entry points only)
-    // The size classes of the chain-extraction kernels run side by side (each is a partial wave) on auxiliary streams shared
-    // by all slots ([7] = big reads): with the slots' own streams that stays below the number of hardware work queues
-    // (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 below), so streams do not alias onto one queue and serialise falsely.
-    cudaStream_t bt_stream[kBtMid0] = {nullptr};
-    cudaStream_t mid_stream[kBtMidStreams] = {nullptr};   // handed out round robin to the mid-class launches of all slots
-    unsigned mid_rr = 0;
+    // The size classes of the chain-extraction kernels run side by side (each is a partial wave) on a pool of auxiliary
+    // streams shared by all slots and handed out round robin, so that neither the classes of one chunk nor the same class of
+    // consecutive chunks queue behind each other (the global-memory class runs on the slot's own stream).  With the slots'
+    // own streams the pool stays within the hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 below), so streams
+    // do not alias onto one queue and serialise falsely.
+    cudaStream_t bt_stream[kBtStreams] = {nullptr};   // handed out round robin to the size-class launches of all slots
+    unsigned bt_rr = 0;
     int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
     Slot slot[kMaxSlots];
     // profiling (slot 0 only)
@@ -469,7 +470,7 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         CK(cudaEventRecord(sl.bt_fork, s));
         for (int k = kBtBig - 1; k >= 0; --k) { // longest first
             if (!cnt[k]) continue;
-            cudaStream_t bs = k >= kBtMid0 ? c->mid_stream[c->mid_rr++ % kBtMidStreams] : c->bt_stream[k];
+            cudaStream_t bs = c->bt_stream[c->bt_rr++ % kBtStreams];
             CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
             const int *list = sl.d_list + base[k];
             if (k >= kBtMid0) launch_backtrack_mid(bs, d_a, d_f, d_p, d_off, list, cnt[k], kBtCaps[k], bp, sl);
@@ -596,8 +597,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         rc = config_backtrack();
         if (rc) goto bad;
         if (c->chains_ok)
-            for (int k = 0; k < kBtMid0; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
-            for (int k = 0; k < kBtMidStreams; ++k) CKC(cudaStreamCreateWithFlags(&c->mid_stream[k], cudaStreamNonBlocking));
+            for (int k = 0; k < kBtStreams; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
         const size_t n = max_anchors, n_groups = (n + 31) / 32, n_blocks = (n + kRangeThreads - 1) / kRangeThreads;
         const size_t n_units_cap = n_groups + (size_t)max_reads + 2;
         for (int i = 0; i < n_slots; ++i) {
@@ -662,8 +662,7 @@ extern "C" void mm2gb_ctx_destroy(mm2gb_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (int i = 0; i < kMaxSlots; ++i) free_slot(c->slot[i]);
-    for (int k = 0; k < kBtMid0; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
-    for (int k = 0; k < kBtMidStreams; ++k) if (c->mid_stream[k]) cudaStreamDestroy(c->mid_stream[k]);
+    for (int k = 0; k < kBtStreams; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
     prof_collect(c);
     cudaFree(c->d_lut);
     delete c;
