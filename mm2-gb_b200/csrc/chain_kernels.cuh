@@ -229,7 +229,9 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, con
     }
 }
 
-// k_scan: exclusive prefix of the per-block unit counts (single block), total -> ctr->n_units
+// k_scan: exclusive prefix of the per-block unit counts (single block, 8 consecutive entries per thread and round so that the
+//         ~120 k entries of a 30 M-anchor batch take 15 rounds of barriers, not 121), total -> ctr->n_units
+constexpr int kScanPer = 8;
 __global__ void __launch_bounds__(1024)
 k_scan(const int *__restrict__ block_cnt, const unsigned long long *__restrict__ block_pairs, int n_blocks, int *__restrict__ block_base,
        Counters *__restrict__ ctr)
@@ -241,11 +243,18 @@ k_scan(const int *__restrict__ block_cnt, const unsigned long long *__restrict__
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     unsigned long long pairs = 0;
-    for (int base = 0; base < n_blocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < n_blocks ? block_cnt[i] : 0;
-        if (i < n_blocks) pairs += block_pairs[i];
-        int x = v;
+    for (int base = 0; base < n_blocks; base += 1024 * kScanPer) {
+        const int i0 = base + threadIdx.x * kScanPer;
+        int v[kScanPer];
+        int x = 0;
+#pragma unroll
+        for (int q = 0; q < kScanPer; ++q) {
+            const int i = i0 + q;
+            v[q] = i < n_blocks ? block_cnt[i] : 0;
+            if (i < n_blocks) pairs += block_pairs[i];
+            x += v[q];
+        }
+        const int mine = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, x, d);
@@ -265,7 +274,13 @@ k_scan(const int *__restrict__ block_cnt, const unsigned long long *__restrict__
         __syncthreads();
         const int carry = s_carry;
         const int incl = x + (wid ? s_warp[wid - 1] : 0) + carry;
-        if (i < n_blocks) block_base[i] = incl - v;
+        int run = incl - mine;
+#pragma unroll
+        for (int q = 0; q < kScanPer; ++q) {
+            const int i = i0 + q;
+            if (i < n_blocks) block_base[i] = run;
+            run += v[q];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = incl;
         __syncthreads();
