@@ -736,6 +736,7 @@ struct WalkSmall {
     __device__ __forceinline__ WalkSmall(BtWalkSmem<CAP> &s, const unsigned *z) : S(s), zs(z) {}
     __device__ __forceinline__ int sent() const { return CAP; }
     __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
+    __device__ __forceinline__ void prepare_compaction(int) {}
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
         for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight, then 4 gathers of f[p[i]]
@@ -784,6 +785,7 @@ struct WalkBig {
     unsigned *cnt_s, *start_s;
     __device__ __forceinline__ int sent() const { return n; }
     __device__ __forceinline__ int wc() const { return n; }
+    __device__ __forceinline__ void prepare_compaction(int) {}
     __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
     {
         for (int w = lane; w <= (n_ >> 5); w += 32) tb[w] = 0;
@@ -828,8 +830,21 @@ struct WalkMid {
     unsigned *pay, *pay2;
     int *path_s;
     unsigned *cnt_s, *start_s;
+    size_t smem_bytes;      // dynamic shared memory of the CTA
     __device__ __forceinline__ int sent() const { return n; }
     __device__ __forceinline__ int wc() const { return n; }
+    // the chain-start keys of the compaction (sorted with the serial flag passes) go to shared memory when they fit behind
+    // the sort scratch: the links are dead by then
+    __device__ __forceinline__ void prepare_compaction(int n_u)
+    {
+        const size_t need = (size_t)(256 + kBtLevels * kBtRow) * 4 + (size_t)n_u * 24;
+        if (need > smem_bytes) return;
+        unsigned long long *base = reinterpret_cast<unsigned long long *>(cnt_s + 256 + kBtLevels * kBtRow);
+        zk = base;
+        zk2 = base + n_u;
+        pay = reinterpret_cast<unsigned *>(base + 2 * (size_t)n_u);
+        pay2 = pay + n_u;
+    }
     __device__ __forceinline__ void init(int n_, const int *, const int *__restrict__ prr, int lane)
     {
         for (int i0 = 0; i0 < n_; i0 += 128) {
@@ -896,8 +911,13 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     int n_v = 0, n_u = 0;
     int k = nz - 1;
     bool nothing_claimed = true;    // true until the first chain is claimed: its walk needs no claim tests at all
-    typename ZK::T znext = (k - lane >= 0) ? S.zat(k - lane) : (typename ZK::T)0;   // the 32 ends below k, fetched one round ahead
-    int knext = k;
+    // the sorted ends are read through a sliding window of two register groups: zc = z[B - lane], zn = z[B - 32 - lane]
+    // (fetched one group ahead); the 32 ends below any k in (B - 32, B] come out of them by shuffles, so the array is loaded
+    // once per 32 ends and not once per walk
+    typedef typename ZK::T ZT;
+    int B = k;
+    ZT zc = (B - lane >= 0) ? S.zat(B - lane) : (ZT)0;
+    ZT zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
     IDX *path = S.path();
     while (k >= 0) {
         typename ZK::T zkk;
@@ -905,11 +925,18 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             // walks that can only claim themselves (lchain.c:16-22 evaluates p[i] once and stops): a run of them is settled
             // here in parallel, in visiting order; the first end that needs a real walk goes through the general code below.
             const int e = k - lane;
-            typename ZK::T z = 0;
-            if (knext == k) z = znext;                     // the prefetched group is exactly this one
-            else if (e >= 0) z = S.zat(e);
-            knext = k - 32;                                // prefetch the group a full step further down
-            znext = (knext - lane >= 0) ? S.zat(knext - lane) : (typename ZK::T)0;
+            while (k <= B - 32) {                          // the window left group zc behind
+                zc = zn;
+                B -= 32;
+                zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
+            }
+            ZT z = zc;
+            const int sft = B - k;                         // warp-uniform, 0 .. 31
+            if (sft) {
+                const int srcl = lane + sft;
+                const ZT a0 = __shfl_sync(full, zc, srcl & 31), a1 = __shfl_sync(full, zn, srcl & 31);
+                z = srcl < 32 ? a0 : a1;
+            }
             bool unc = false, simple = false;
             int i0l = 0, n1 = SENT;
             if (e >= 0) {
@@ -957,7 +984,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         // cutj = largest evaluated j whose s_j is a strict new maximum (0 if none): the chain is n_0 .. n_{cutj-1}.
         // The predecessor chase is the serial part: 32 nodes per batch, one load per node (the sentinel points at itself, so
         // the chase needs no end test); where the walk ends is found afterwards for all 32 nodes at once.
-        int cur = i0, max_s = 0, cutj = 0, cutnode = i0, j0 = 0;
+        int cur = i0, max_s = 0, cutj = 0, cutf = 0, j0 = 0;   // cutf = f of the node the chain is cut at
         int mine0 = SENT; // this lane's node of the first batch (enough to mark chains of <= 32 nodes without re-reading)
         for (;;) {
             int nb = 32;
@@ -1011,7 +1038,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             if (nm) {
                 const int l = 31 - __clz(nm);
                 cutj = j0 + l;
-                cutnode = __shfl_sync(full, mine, l);
+                cutf = __shfl_sync(full, fmine, l);
             }
             if (endm) break;
             max_s = max(max_s, __shfl_sync(full, pm, 31));
@@ -1028,7 +1055,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             }
         }
         __syncwarp();
-        const int scv = key - S.fat(cutnode, fr);
+        const int scv = key - cutf;
         if (scv >= bp.min_sc && cnt > 0 && cnt >= bp.min_cnt) {
             if (lane == 0) { ur[n_u] = ((unsigned long long)(unsigned)scv << 32) | (unsigned)cnt; vsr[n_u] = n_v; }
             ++n_u;
@@ -1053,6 +1080,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     bpos = __shfl_sync(full, bpos, 0);
     unsigned long long *uo = u_pack + upos;
     uint4 *bo = b_pack + bpos;
+    S.prepare_compaction(n_u);
     unsigned long long *wk = S.wk();
     IDX *wpay = S.wpay();
     for (int c = lane; c < n_u; c += 32) {
@@ -1179,6 +1207,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.path_s = s_path;
     S.cnt_s = reinterpret_cast<unsigned *>(bt_raw);
     S.start_s = S.cnt_s + 256;
+    S.smem_bytes = bt_walk_mid_smem(cap);
     bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);
 }
