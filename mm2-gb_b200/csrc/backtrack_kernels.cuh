@@ -737,6 +737,9 @@ struct WalkSmall {
     __device__ __forceinline__ int sent() const { return CAP; }
     __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
     __device__ __forceinline__ void prepare_compaction(int) {}
+    static constexpr bool kLanePar = false;     // (its scratch would cost these kernels a resident read per SM)
+    __device__ __forceinline__ int *lp_path() { return nullptr; }
+    __device__ __forceinline__ int *lp_f() { return nullptr; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
         for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight, then 4 gathers of f[p[i]]
@@ -786,6 +789,9 @@ struct WalkBig {
     __device__ __forceinline__ int sent() const { return n; }
     __device__ __forceinline__ int wc() const { return n; }
     __device__ __forceinline__ void prepare_compaction(int) {}
+    static constexpr bool kLanePar = false;
+    __device__ __forceinline__ int *lp_path() { return nullptr; }
+    __device__ __forceinline__ int *lp_f() { return nullptr; }
     __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
     {
         for (int w = lane; w <= (n_ >> 5); w += 32) tb[w] = 0;
@@ -831,6 +837,10 @@ struct WalkMid {
     int *path_s;
     unsigned *cnt_s, *start_s;
     size_t smem_bytes;      // dynamic shared memory of the CTA
+    int *lp_path_s, *lp_f_s;   // [32][33] each: paths and scores of the lane-parallel walks
+    static constexpr bool kLanePar = true;
+    __device__ __forceinline__ int *lp_path() { return lp_path_s; }
+    __device__ __forceinline__ int *lp_f() { return lp_f_s; }
     __device__ __forceinline__ int sent() const { return n; }
     __device__ __forceinline__ int wc() const { return n; }
     // the chain-start keys of the compaction (sorted with the serial flag passes) go to shared memory when they fit behind
@@ -919,66 +929,8 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     ZT zc = (B - lane >= 0) ? S.zat(B - lane) : (ZT)0;
     ZT zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
     IDX *path = S.path();
-    while (k >= 0) {
-        typename ZK::T zkk;
-        {   // next chain end that is not claimed yet.  Ends whose predecessor is already claimed (or absent) are one-step
-            // walks that can only claim themselves (lchain.c:16-22 evaluates p[i] once and stops): a run of them is settled
-            // here in parallel, in visiting order; the first end that needs a real walk goes through the general code below.
-            const int e = k - lane;
-            while (k <= B - 32) {                          // the window left group zc behind
-                zc = zn;
-                B -= 32;
-                zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
-            }
-            ZT z = zc;
-            const int sft = B - k;                         // warp-uniform, 0 .. 31
-            if (sft) {
-                const int srcl = lane + sft;
-                const ZT a0 = __shfl_sync(full, zc, srcl & 31), a1 = __shfl_sync(full, zn, srcl & 31);
-                z = srcl < 32 ? a0 : a1;
-            }
-            bool unc = false, simple = false;
-            int i0l = 0, n1 = SENT;
-            if (e >= 0) {
-                i0l = ZK::idx(z);
-                unc = !S.claimed(i0l);
-                if (unc) {
-                    n1 = S.nextp(i0l);
-                    simple = n1 == SENT || S.claimed(n1);
-                }
-            }
-            const unsigned m = __ballot_sync(full, unc);
-            if (!m) { k -= 32; continue; }
-            const unsigned hard = __ballot_sync(full, unc && !simple);
-            const int nfast = hard ? __ffs(hard) - 1 : 32;
-            const unsigned fastm = nfast >= 32 ? m : (m & ((1u << nfast) - 1u));
-            if (fastm) {
-                const bool mine_f = ((fastm >> lane) & 1u) != 0;
-                const bool claim = mine_f && S.gain(i0l, fr, pr);   // s_1 > 0: cut = p[i0], chain = {i0}
-                if (claim) S.claim(i0l);
-                if (__any_sync(full, claim)) nothing_claimed = false;
-                if (bp.min_cnt <= 1) { // single-anchor chains can be accepted: needs the value of s_1
-                    const int keyl = ZK::score(z);
-                    const int s1 = claim ? keyl - S.fat(n1, fr) : 0;
-                    const bool acc = claim && s1 >= bp.min_sc;
-                    const unsigned am = __ballot_sync(full, acc);
-                    if (am) {
-                        const int rank = __popc(am & ((1u << lane) - 1u));
-                        if (acc) {
-                            ur[n_u + rank] = ((unsigned long long)(unsigned)s1 << 32) | 1ULL;
-                            vsr[n_u + rank] = n_v + rank;
-                            vr[n_v + rank] = i0l;
-                        }
-                        n_u += __popc(am);
-                        n_v += __popc(am);
-                    }
-                }
-                __syncwarp();
-            }
-            k -= nfast;
-            if (!hard) continue;
-            zkk = __shfl_sync(full, z, nfast);     // the end that needs a real walk was fetched by lane nfast
-        }
+    // one cooperative walk from the end zkk = (score, index): the whole warp chases its path and evaluates it
+    auto walk_one = [&](typename ZK::T zkk) {
         const int i0 = ZK::idx(zkk), key = ZK::score(zkk);
         // path n_0 = i0, n_1 = p[n_0], ...; node n_j (j >= 1) is "evaluated": s_j = key - f[n_j] (key if n_j is the sentinel).
         // cutj = largest evaluated j whose s_j is a strict new maximum (0 if none): the chain is n_0 .. n_{cutj-1}.
@@ -1061,6 +1013,139 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             ++n_u;
             n_v += cnt;
         }
+    };
+    while (k >= 0) {
+        typename ZK::T zkk;
+        {   // next chain end that is not claimed yet.  Ends whose predecessor is already claimed (or absent) are one-step
+            // walks that can only claim themselves (lchain.c:16-22 evaluates p[i] once and stops): a run of them is settled
+            // here in parallel, in visiting order; the first end that needs a real walk goes through the general code below.
+            const int e = k - lane;
+            while (k <= B - 32) {                          // the window left group zc behind
+                zc = zn;
+                B -= 32;
+                zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
+            }
+            ZT z = zc;
+            const int sft = B - k;                         // warp-uniform, 0 .. 31
+            if (sft) {
+                const int srcl = lane + sft;
+                const ZT a0 = __shfl_sync(full, zc, srcl & 31), a1 = __shfl_sync(full, zn, srcl & 31);
+                z = srcl < 32 ? a0 : a1;
+            }
+            bool unc = false, simple = false;
+            int i0l = 0, n1 = SENT;
+            if (e >= 0) {
+                i0l = ZK::idx(z);
+                unc = !S.claimed(i0l);
+                if (unc) {
+                    n1 = S.nextp(i0l);
+                    simple = n1 == SENT || S.claimed(n1);
+                }
+            }
+            const unsigned m = __ballot_sync(full, unc);
+            if (!m) { k -= 32; continue; }
+            const unsigned hard = __ballot_sync(full, unc && !simple);
+            if (W::kLanePar && __popc(hard) >= 2) {
+                // Several ends of this window need a real walk (reads full of short side chains): every lane walks ITS end
+                // on its own against the claimed state of now -- chase (<= 32 nodes, shared memory), one gather of f per
+                // path position, evaluation in the lane -- and the results are committed in visiting order.  A result is
+                // used iff no node the lane evaluated was claimed by an earlier lane of the window in the meantime (then
+                // the walk is what the sequential algorithm does); otherwise, and for paths of more than 32 nodes, the end
+                // is walked by the whole warp at its turn as usual.
+                int *lp = S.lp_path() + lane * 33, *lf = S.lp_f() + lane * 33;
+                int len = 0;
+                bool longw = false;
+                if (unc) {
+                    int cur = i0l;
+                    for (int t = 0; t < 32; ++t) {
+                        lp[t] = cur;
+                        len = t + 1;
+                        if (t >= 1 && (cur == SENT || S.claimed(cur))) break;
+                        if (t == 31) { longw = true; break; }
+                        cur = S.nextp(cur);
+                    }
+                }
+                {   // f of every recorded node: 8 independent loads per lane in flight
+                    const int glen = longw ? 0 : len;
+                    const int maxlen = __reduce_max_sync(full, glen);
+                    for (int t0 = 1; t0 < maxlen; t0 += 8) {
+                        int fv[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) fv[q] = t0 + q < glen ? S.fat(lp[t0 + q], fr) : 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (t0 + q < glen) lf[t0 + q] = fv[q];
+                    }
+                }
+                int cutl = 0, maxs = 0, nev = 0;
+                if (unc && !longw) {
+                    const int keyl = ZK::score(z);
+                    for (int j = 1; j < len; ++j) {
+                        const int sj = keyl - lf[j];
+                        nev = j;
+                        if (sj > maxs) { maxs = sj; cutl = j; }
+                        else if ((long long)maxs - (long long)sj > (long long)bp.max_drop) break;
+                    }
+                }
+                __syncwarp();
+                unsigned todo = m;
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int len_l = __shfl_sync(full, len, l), nev_l = __shfl_sync(full, nev, l), cut_l = __shfl_sync(full, cutl, l);
+                    const int sc_l = __shfl_sync(full, maxs, l);
+                    const bool long_l = __shfl_sync(full, longw ? 1 : 0, l) != 0;
+                    const int *rp = S.lp_path() + l * 33;
+                    const int node = (long_l ? lane == 0 : lane <= nev_l) ? rp[lane] : SENT;
+                    // nodes 0 .. len-2 were unclaimed when the lane walked, the last one is where it stopped
+                    const bool nowc = node != SENT && (long_l || lane < len_l - 1) && S.claimed(node);
+                    const unsigned chg = __ballot_sync(full, nowc);
+                    if (chg & 1u) continue;                       // the end itself has been claimed since: not a chain end any more
+                    if (long_l || chg) { walk_one(__shfl_sync(full, z, l)); continue; }
+                    if (cut_l > 0) {
+                        nothing_claimed = false;
+                        if (lane < cut_l) S.claim(node);
+                        if (sc_l >= bp.min_sc && cut_l >= bp.min_cnt) {
+                            if (lane == 0) { ur[n_u] = ((unsigned long long)(unsigned)sc_l << 32) | (unsigned)cut_l; vsr[n_u] = n_v; }
+                            if (lane < cut_l) vr[n_v + lane] = node;
+                            ++n_u;
+                            n_v += cut_l;
+                        }
+                    }
+                    __syncwarp();
+                }
+                k -= 32;
+                continue;
+            }
+            const int nfast = hard ? __ffs(hard) - 1 : 32;
+            const unsigned fastm = nfast >= 32 ? m : (m & ((1u << nfast) - 1u));
+            if (fastm) {
+                const bool mine_f = ((fastm >> lane) & 1u) != 0;
+                const bool claim = mine_f && S.gain(i0l, fr, pr);   // s_1 > 0: cut = p[i0], chain = {i0}
+                if (claim) S.claim(i0l);
+                if (__any_sync(full, claim)) nothing_claimed = false;
+                if (bp.min_cnt <= 1) { // single-anchor chains can be accepted: needs the value of s_1
+                    const int keyl = ZK::score(z);
+                    const int s1 = claim ? keyl - S.fat(n1, fr) : 0;
+                    const bool acc = claim && s1 >= bp.min_sc;
+                    const unsigned am = __ballot_sync(full, acc);
+                    if (am) {
+                        const int rank = __popc(am & ((1u << lane) - 1u));
+                        if (acc) {
+                            ur[n_u + rank] = ((unsigned long long)(unsigned)s1 << 32) | 1ULL;
+                            vsr[n_u + rank] = n_v + rank;
+                            vr[n_v + rank] = i0l;
+                        }
+                        n_u += __popc(am);
+                        n_v += __popc(am);
+                    }
+                }
+                __syncwarp();
+            }
+            k -= nfast;
+            if (!hard) continue;
+            zkk = __shfl_sync(full, z, nfast);     // the end that needs a real walk was fetched by lane nfast
+        }
+        walk_one(zkk);
         --k;
     }
     __syncwarp();
@@ -1187,6 +1272,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
 {
     extern __shared__ int4 bt_raw[];
     __shared__ int s_path[32];
+    __shared__ int s_lp_path[32 * 33], s_lp_f[32 * 33];
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;
     const int r = read_list[blockIdx.x];
@@ -1208,6 +1294,8 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.cnt_s = reinterpret_cast<unsigned *>(bt_raw);
     S.start_s = S.cnt_s + 256;
     S.smem_bytes = bt_walk_mid_smem(cap);
+    S.lp_path_s = s_lp_path;
+    S.lp_f_s = s_lp_f;
     bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);
 }
