@@ -738,6 +738,7 @@ struct WalkSmall {
     __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
     __device__ __forceinline__ void prepare_compaction(int) {}
     static constexpr bool kLanePar = false;     // (its scratch would cost these kernels a resident read per SM)
+    __device__ __forceinline__ unsigned *lp_z() { return nullptr; }
     __device__ __forceinline__ int *lp_path() { return nullptr; }
     __device__ __forceinline__ int *lp_f() { return nullptr; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
@@ -790,6 +791,7 @@ struct WalkBig {
     __device__ __forceinline__ int wc() const { return n; }
     __device__ __forceinline__ void prepare_compaction(int) {}
     static constexpr bool kLanePar = false;
+    __device__ __forceinline__ unsigned long long *lp_z() { return nullptr; }
     __device__ __forceinline__ int *lp_path() { return nullptr; }
     __device__ __forceinline__ int *lp_f() { return nullptr; }
     __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
@@ -839,6 +841,8 @@ struct WalkMid {
     size_t smem_bytes;      // dynamic shared memory of the CTA
     int *lp_path_s, *lp_f_s;   // [32][33] each: paths and scores of the lane-parallel walks
     static constexpr bool kLanePar = true;
+    unsigned long long *lp_z_s;   // [32] pending ends
+    __device__ __forceinline__ unsigned long long *lp_z() { return lp_z_s; }
     __device__ __forceinline__ int *lp_path() { return lp_path_s; }
     __device__ __forceinline__ int *lp_f() { return lp_f_s; }
     __device__ __forceinline__ int sent() const { return n; }
@@ -928,6 +932,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     int B = k;
     ZT zc = (B - lane >= 0) ? S.zat(B - lane) : (ZT)0;
     ZT zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
+    ZT zn2 = (B - 64 - lane >= 0) ? S.zat(B - 64 - lane) : (ZT)0;   // two groups ahead: a run of claimed windows is skipped faster than one load
     IDX *path = S.path();
     // one cooperative walk from the end zkk = (score, index): the whole warp chases its path and evaluates it
     auto walk_one = [&](typename ZK::T zkk) {
@@ -1014,6 +1019,82 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             n_v += cnt;
         }
     };
+    // ---- lane-parallel walks (W::kLanePar: reads full of short side chains) ----------------------------------------------------
+    // Unclaimed ends are not walked as they are met: they are collected, in visiting order, into a batch of up to 32 (the
+    // claimed bits do not change meanwhile, so "unclaimed" stays true).  Then every lane walks ITS end on its own against the
+    // claimed bits of now -- chase (<= 32 nodes, shared memory), one gather of f per path position, evaluation in the lane --
+    // and the results are committed in visiting order.  A result is used iff no node the lane evaluated was claimed by an
+    // earlier end of the batch in the meantime (then the walk is what the sequential algorithm does; an end that was itself
+    // claimed is dropped); otherwise, and for paths of more than 32 nodes, the end is walked by the whole warp at its turn.
+    int nb_pend = 0;
+    auto flush_batch = [&]() {
+        const bool unc = lane < nb_pend;
+        const unsigned m = nb_pend >= 32 ? full : ((1u << nb_pend) - 1u);
+        const ZT z = unc ? S.lp_z()[lane] : (ZT)0;
+        const int i0l = ZK::idx(z);
+        int *lp = S.lp_path() + lane * 33, *lf = S.lp_f() + lane * 33;
+        int len = 0;
+        bool longw = false;
+        if (unc) {
+            int cur = i0l;
+            for (int t = 0; t < 32; ++t) {
+                lp[t] = cur;
+                len = t + 1;
+                if (t >= 1 && (cur == SENT || S.claimed(cur))) break;
+                if (t == 31) { longw = true; break; }
+                cur = S.nextp(cur);
+            }
+        }
+        {   // f of every recorded node: 8 independent loads per lane in flight
+            const int glen = longw ? 0 : len;
+            const int maxlen = __reduce_max_sync(full, glen);
+            for (int t0 = 1; t0 < maxlen; t0 += 8) {
+                int fv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) fv[q] = t0 + q < glen ? S.fat(lp[t0 + q], fr) : 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (t0 + q < glen) lf[t0 + q] = fv[q];
+            }
+        }
+        int cutl = 0, maxs = 0, nev = 0;
+        if (unc && !longw) {
+            const int keyl = ZK::score(z);
+            for (int j = 1; j < len; ++j) {
+                const int sj = keyl - lf[j];
+                nev = j;
+                if (sj > maxs) { maxs = sj; cutl = j; }
+                else if ((long long)maxs - (long long)sj > (long long)bp.max_drop) break;
+            }
+        }
+        __syncwarp();
+        unsigned todo = m;
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int len_l = __shfl_sync(full, len, l), nev_l = __shfl_sync(full, nev, l), cut_l = __shfl_sync(full, cutl, l);
+            const int sc_l = __shfl_sync(full, maxs, l);
+            const bool long_l = __shfl_sync(full, longw ? 1 : 0, l) != 0;
+            const int *rp = S.lp_path() + l * 33;
+            const int node = (long_l ? lane == 0 : lane <= nev_l) ? rp[lane] : SENT;
+            // nodes 0 .. len-2 were unclaimed when the lane walked, the last one is where it stopped
+            const bool nowc = node != SENT && (long_l || lane < len_l - 1) && S.claimed(node);
+            const unsigned chg = __ballot_sync(full, nowc);
+            if (chg & 1u) continue;                       // the end itself has been claimed since: not a chain end any more
+            if (long_l || chg) { walk_one(__shfl_sync(full, z, l)); continue; }
+            if (cut_l > 0) {
+                nothing_claimed = false;
+                if (lane < cut_l) S.claim(node);
+                if (sc_l >= bp.min_sc && cut_l >= bp.min_cnt) {
+                    if (lane == 0) { ur[n_u] = ((unsigned long long)(unsigned)sc_l << 32) | (unsigned)cut_l; vsr[n_u] = n_v; }
+                    if (lane < cut_l) vr[n_v + lane] = node;
+                    ++n_u;
+                    n_v += cut_l;
+                }
+            }
+            __syncwarp();
+        }
+        nb_pend = 0;
+    };
     while (k >= 0) {
         typename ZK::T zkk;
         {   // next chain end that is not claimed yet.  Ends whose predecessor is already claimed (or absent) are one-step
@@ -1022,8 +1103,9 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             const int e = k - lane;
             while (k <= B - 32) {                          // the window left group zc behind
                 zc = zn;
+                zn = zn2;
                 B -= 32;
-                zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
+                zn2 = (B - 64 - lane >= 0) ? S.zat(B - 64 - lane) : (ZT)0;
             }
             ZT z = zc;
             const int sft = B - k;                         // warp-uniform, 0 .. 31
@@ -1045,74 +1127,11 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             const unsigned m = __ballot_sync(full, unc);
             if (!m) { k -= 32; continue; }
             const unsigned hard = __ballot_sync(full, unc && !simple);
-            if (W::kLanePar && __popc(hard) >= 2) {
-                // Several ends of this window need a real walk (reads full of short side chains): every lane walks ITS end
-                // on its own against the claimed state of now -- chase (<= 32 nodes, shared memory), one gather of f per
-                // path position, evaluation in the lane -- and the results are committed in visiting order.  A result is
-                // used iff no node the lane evaluated was claimed by an earlier lane of the window in the meantime (then
-                // the walk is what the sequential algorithm does); otherwise, and for paths of more than 32 nodes, the end
-                // is walked by the whole warp at its turn as usual.
-                int *lp = S.lp_path() + lane * 33, *lf = S.lp_f() + lane * 33;
-                int len = 0;
-                bool longw = false;
-                if (unc) {
-                    int cur = i0l;
-                    for (int t = 0; t < 32; ++t) {
-                        lp[t] = cur;
-                        len = t + 1;
-                        if (t >= 1 && (cur == SENT || S.claimed(cur))) break;
-                        if (t == 31) { longw = true; break; }
-                        cur = S.nextp(cur);
-                    }
-                }
-                {   // f of every recorded node: 8 independent loads per lane in flight
-                    const int glen = longw ? 0 : len;
-                    const int maxlen = __reduce_max_sync(full, glen);
-                    for (int t0 = 1; t0 < maxlen; t0 += 8) {
-                        int fv[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) fv[q] = t0 + q < glen ? S.fat(lp[t0 + q], fr) : 0;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) if (t0 + q < glen) lf[t0 + q] = fv[q];
-                    }
-                }
-                int cutl = 0, maxs = 0, nev = 0;
-                if (unc && !longw) {
-                    const int keyl = ZK::score(z);
-                    for (int j = 1; j < len; ++j) {
-                        const int sj = keyl - lf[j];
-                        nev = j;
-                        if (sj > maxs) { maxs = sj; cutl = j; }
-                        else if ((long long)maxs - (long long)sj > (long long)bp.max_drop) break;
-                    }
-                }
-                __syncwarp();
-                unsigned todo = m;
-                while (todo) {
-                    const int l = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int len_l = __shfl_sync(full, len, l), nev_l = __shfl_sync(full, nev, l), cut_l = __shfl_sync(full, cutl, l);
-                    const int sc_l = __shfl_sync(full, maxs, l);
-                    const bool long_l = __shfl_sync(full, longw ? 1 : 0, l) != 0;
-                    const int *rp = S.lp_path() + l * 33;
-                    const int node = (long_l ? lane == 0 : lane <= nev_l) ? rp[lane] : SENT;
-                    // nodes 0 .. len-2 were unclaimed when the lane walked, the last one is where it stopped
-                    const bool nowc = node != SENT && (long_l || lane < len_l - 1) && S.claimed(node);
-                    const unsigned chg = __ballot_sync(full, nowc);
-                    if (chg & 1u) continue;                       // the end itself has been claimed since: not a chain end any more
-                    if (long_l || chg) { walk_one(__shfl_sync(full, z, l)); continue; }
-                    if (cut_l > 0) {
-                        nothing_claimed = false;
-                        if (lane < cut_l) S.claim(node);
-                        if (sc_l >= bp.min_sc && cut_l >= bp.min_cnt) {
-                            if (lane == 0) { ur[n_u] = ((unsigned long long)(unsigned)sc_l << 32) | (unsigned)cut_l; vsr[n_u] = n_v; }
-                            if (lane < cut_l) vr[n_v + lane] = node;
-                            ++n_u;
-                            n_v += cut_l;
-                        }
-                    }
-                    __syncwarp();
-                }
+            if (W::kLanePar) {
+                const int cntw = __popc(m);
+                if (nb_pend + cntw > 32) { flush_batch(); continue; }   // claims changed: look at this window again
+                if (unc) S.lp_z()[nb_pend + __popc(m & ((1u << lane) - 1u))] = z;
+                nb_pend += cntw;
                 k -= 32;
                 continue;
             }
@@ -1148,6 +1167,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         walk_one(zkk);
         --k;
     }
+    if (W::kLanePar && nb_pend) flush_batch();
     __syncwarp();
     if (n_u == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; u_pos[r] = 0; b_pos[r] = 0; } return; }
 
@@ -1179,23 +1199,74 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     sc.cnt = S.cnt();
     sc.start = S.start();
     bt_sort<WKey, true, IDX, POS>(wk, wpay, S.wtmp(), S.wpay2(), n_u, sc, lane);
+    __syncwarp();
     int out = 0;
-    for (int c = 0; c < n_u; ++c) {
-        const int src = (int)wpay[c];
-        const unsigned long long uv = ur[src];
-        const int cntc = (int)(unsigned)uv, s0 = vsr[src];
-        if (lane == 0) uo[c] = uv;
-        for (int q0 = 0; q0 < cntc; q0 += 128) { // 4 independent gathers per lane in flight
-            int idx[4];
-            uint4 val[4];
+    if (n_u < 8) { // a few chains (the usual read): chain by chain, 4 independent gathers per lane in flight
+        for (int c = 0; c < n_u; ++c) {
+            const int src = (int)wpay[c];
+            const unsigned long long uv = ur[src];
+            const int cntc = (int)(unsigned)uv, s0 = vsr[src];
+            if (lane == 0) uo[c] = uv;
+            for (int q0 = 0; q0 < cntc; q0 += 128) {
+                int idx[4];
+                uint4 val[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int q = q0 + t * 32 + lane; idx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
+                for (int t = 0; t < 4; ++t) { const int q = q0 + t * 32 + lane; idx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) if (idx[t] >= 0) val[t] = ar[idx[t]];
+                for (int t = 0; t < 4; ++t) if (idx[t] >= 0) val[t] = ar[idx[t]];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[out + q0 + t * 32 + lane] = val[t];
+                for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[out + q0 + t * 32 + lane] = val[t];
+            }
+            out += cntc;
         }
-        out += cntc;
+        if (lane == 0) { n_u_out[r] = n_u; n_b_out[r] = out; u_pos[r] = upos; b_pos[r] = bpos; }
+        return;
+    }
+    // Where every chain (in sorted order) starts in the output and where its anchors sit in vr[]: the key array is done with, it
+    // now holds  out start | (vr index of the chain's last = smallest anchor) << 32.  The anchors are then copied by ONE flat
+    // loop over output positions (4 per lane in flight) instead of chain by chain: a read with hundreds of short chains would
+    // pay two dependent global loads per chain otherwise.
+    for (int c0 = 0; c0 < n_u; c0 += 32) {
+        const int c = c0 + lane;
+        int cntc = 0, vb = 0;
+        if (c < n_u) {
+            const int src = (int)wpay[c];
+            const unsigned long long uv = ur[src];
+            cntc = (int)(unsigned)uv;
+            vb = vsr[src] + cntc - 1;
+            uo[c] = uv;
+        }
+        int incl = cntc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (c < n_u) wk[c] = (unsigned long long)(unsigned)(out + incl - cntc) | ((unsigned long long)(unsigned)vb << 32);
+        out += __shfl_sync(full, incl, 31);
+    }
+    __syncwarp();
+    for (int o0 = 0; o0 < out; o0 += 128) {
+        int idx[4];
+        uint4 val[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int o = o0 + t * 32 + lane;
+            idx[t] = -1;
+            if (o < out) {
+                int lo = 0, hi = n_u;       // the chain of position o: start[lo] <= o < start[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((int)(unsigned)wk[mid] <= o) lo = mid; else hi = mid;
+                }
+                const unsigned long long rc = wk[lo];
+                idx[t] = vr[(int)(rc >> 32) - (o - (int)(unsigned)rc)];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (idx[t] >= 0) val[t] = ar[idx[t]];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[o0 + t * 32 + lane] = val[t];
     }
     if (lane == 0) { n_u_out[r] = n_u; n_b_out[r] = out; u_pos[r] = upos; b_pos[r] = bpos; }
 }
@@ -1273,6 +1344,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     extern __shared__ int4 bt_raw[];
     __shared__ int s_path[32];
     __shared__ int s_lp_path[32 * 33], s_lp_f[32 * 33];
+    __shared__ unsigned long long s_lp_z[32];
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;
     const int r = read_list[blockIdx.x];
@@ -1296,6 +1368,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.smem_bytes = bt_walk_mid_smem(cap);
     S.lp_path_s = s_lp_path;
     S.lp_f_s = s_lp_f;
+    S.lp_z_s = s_lp_z;
     bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);
 }
