@@ -305,11 +305,11 @@ def main():
     value = tot_pairs * args.steps / sec
     # kernels launched per step (mirrors enqueue_kernels / enqueue_backtrack in chain_core.cu): 5 range/unit kernels, k_score_long
     # + the two k_score_units instantiations, then a sort + a walk kernel per non-empty chain-extraction size class (7 shared-memory
-    # classes, the mid classes above MM2GB_BT_MID_MIN = 32768 anchors, the global-memory class) and the overflow pass
+    # classes, the mid classes up to 196608 anchors, the global-memory class) and the overflow pass
     rn = np.diff(off)
     small = [1024, 1536, 2048, 3072, 4096, 6144, 8192]
     mid = [12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608]
-    mid_min = max(8192, int(os.environ.get("MM2GB_BT_MID_MIN", "32768")))
+    mid_min = max(8192, int(os.environ.get("MM2GB_BT_MID_MIN", "8192")))
 
     def bt_class(x):
         if x <= small[-1]:

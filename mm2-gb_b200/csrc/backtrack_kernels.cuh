@@ -740,7 +740,6 @@ struct WalkSmall {
     static constexpr bool kLanePar = false;     // (its scratch would cost these kernels a resident read per SM)
     __device__ __forceinline__ unsigned *lp_z() { return nullptr; }
     __device__ __forceinline__ int *lp_path() { return nullptr; }
-    __device__ __forceinline__ int *lp_f() { return nullptr; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
         for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight, then 4 gathers of f[p[i]]
@@ -793,7 +792,6 @@ struct WalkBig {
     static constexpr bool kLanePar = false;
     __device__ __forceinline__ unsigned long long *lp_z() { return nullptr; }
     __device__ __forceinline__ int *lp_path() { return nullptr; }
-    __device__ __forceinline__ int *lp_f() { return nullptr; }
     __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
     {
         for (int w = lane; w <= (n_ >> 5); w += 32) tb[w] = 0;
@@ -839,12 +837,11 @@ struct WalkMid {
     int *path_s;
     unsigned *cnt_s, *start_s;
     size_t smem_bytes;      // dynamic shared memory of the CTA
-    int *lp_path_s, *lp_f_s;   // [32][33] each: paths and scores of the lane-parallel walks
+    int *lp_path_s;         // [32][33]: the paths of the lane-parallel walks
     static constexpr bool kLanePar = true;
     unsigned long long *lp_z_s;   // [32] pending ends
     __device__ __forceinline__ unsigned long long *lp_z() { return lp_z_s; }
     __device__ __forceinline__ int *lp_path() { return lp_path_s; }
-    __device__ __forceinline__ int *lp_f() { return lp_f_s; }
     __device__ __forceinline__ int sent() const { return n; }
     __device__ __forceinline__ int wc() const { return n; }
     // the chain-start keys of the compaction (sorted with the serial flag passes) go to shared memory when they fit behind
@@ -1032,7 +1029,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         const unsigned m = nb_pend >= 32 ? full : ((1u << nb_pend) - 1u);
         const ZT z = unc ? S.lp_z()[lane] : (ZT)0;
         const int i0l = ZK::idx(z);
-        int *lp = S.lp_path() + lane * 33, *lf = S.lp_f() + lane * 33;
+        int *lp = S.lp_path() + lane * 33;
         int len = 0;
         bool longw = false;
         if (unc) {
@@ -1045,25 +1042,26 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
                 cur = S.nextp(cur);
             }
         }
-        {   // f of every recorded node: 8 independent loads per lane in flight
-            const int glen = longw ? 0 : len;
+        // f of every recorded node, 8 independent loads per lane in flight, evaluated as it arrives (lchain.c:16-22 per lane)
+        int cutl = 0, maxs = 0, nev = 0;
+        {
+            const int glen = (unc && !longw) ? len : 0;
             const int maxlen = __reduce_max_sync(full, glen);
+            const int keyl = ZK::score(z);
+            bool live = true;
             for (int t0 = 1; t0 < maxlen; t0 += 8) {
                 int fv[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) fv[q] = t0 + q < glen ? S.fat(lp[t0 + q], fr) : 0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) if (t0 + q < glen) lf[t0 + q] = fv[q];
-            }
-        }
-        int cutl = 0, maxs = 0, nev = 0;
-        if (unc && !longw) {
-            const int keyl = ZK::score(z);
-            for (int j = 1; j < len; ++j) {
-                const int sj = keyl - lf[j];
-                nev = j;
-                if (sj > maxs) { maxs = sj; cutl = j; }
-                else if ((long long)maxs - (long long)sj > (long long)bp.max_drop) break;
+                for (int q = 0; q < 8; ++q) {
+                    if (live && t0 + q < glen) {
+                        const int sj = keyl - fv[q];
+                        nev = t0 + q;
+                        if (sj > maxs) { maxs = sj; cutl = t0 + q; }
+                        else if ((long long)maxs - (long long)sj > (long long)bp.max_drop) live = false;
+                    }
+                }
             }
         }
         __syncwarp();
@@ -1343,7 +1341,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
 {
     extern __shared__ int4 bt_raw[];
     __shared__ int s_path[32];
-    __shared__ int s_lp_path[32 * 33], s_lp_f[32 * 33];
+    __shared__ int s_lp_path[32 * 33];
     __shared__ unsigned long long s_lp_z[32];
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;
@@ -1367,7 +1365,6 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.start_s = S.cnt_s + 256;
     S.smem_bytes = bt_walk_mid_smem(cap);
     S.lp_path_s = s_lp_path;
-    S.lp_f_s = s_lp_f;
     S.lp_z_s = s_lp_z;
     bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);

@@ -54,9 +54,11 @@ extern "C" int mm2gb_device_count(void)
 
 namespace {
 
-// size classes of the chain-extraction kernels: 0..6 shared-memory kernels (k_bt_sort<CAP> / k_bt_walk<CAP>), 7..11 "mid"
-// (k_bt_sort_mid / k_bt_walk_mid: keys in global scratch, digits / predecessor links in shared memory), 12 = any size
+// size classes of the chain-extraction kernels: 0..6 shared-memory kernels (k_bt_sort<CAP> / k_bt_walk<CAP>), 7..15 "mid"
+// (k_bt_sort_mid / k_bt_walk_mid: keys in global scratch, digits / predecessor links in shared memory), 16 = any size
 constexpr int kBtClasses = 17, kBtBig = 16, kBtMid0 = 7, kBtStreams = 24;
+// (finer mid classes -- steps of 2^(1/4) -- were tried: better packing of shared memory, but twice the launches, each with its
+//  own slowest-read tail; measured slower both device-resident and end to end)
 const int kBtCaps[kBtBig] = {1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608};
 // Reads of 8193 .. mid_min anchors go to the global-memory kernels, longer ones (up to 196608) to the mid kernels.  The two
 // kinds complement each other: the global-memory kernels need no shared memory, so every read of a batch is resident at once
