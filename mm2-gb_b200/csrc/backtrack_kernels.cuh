@@ -15,9 +15,15 @@
 //   * buckets of <= 64 elements: insertion sort == stable sort, done as a parallel rank sort.
 //   * chain walks: the predecessor chase is serial, everything else (claimed test, score drop test of
 //     mg_chain_bk_end, prefix maxima) is evaluated for 32 path nodes at a time.
-// Reads that do not fit the shared-memory kernels (more than kBtMaxAnchors anchors; scores >= 2^19; more chains than the
-// key buffer holds) run the SAME code on global-memory scratch with 64-bit keys and 32-bit indices (k_bt_sort_big /
-// k_bt_walk_big): reads above 8192 anchors are listed by the host, the others arrive through a device-side overflow list.
+// Three tiers by read length (the host bins the reads, chain_core.cu):
+//   * up to 8192 anchors: k_bt_sort<CAP> / k_bt_walk<CAP>, the read's working set in shared memory (32-bit packed keys);
+//   * up to 196608 anchors: k_bt_sort_mid / k_bt_walk_mid -- 64-bit keys, f[] and z[] in global scratch, but everything the
+//     SERIAL parts touch in shared memory at one byte per anchor: the radix digits of the foreign elements (the pass is
+//     reformulated as a walk over them, bt_flag_pass_fq) and the predecessor links as distances; short walks run
+//     lane-parallel in batches and are committed in visiting order;
+//   * anything else (longer reads; reads a shared-memory kernel hands over through a device-side overflow list: scores
+//     >= 2^19, more chains than its key buffer holds): the first tier's code on global-memory scratch with 64-bit keys
+//     (k_bt_sort_big / k_bt_walk_big).
 // Compacted anchors and chains of the whole batch are PACKED (positions handed out by atomic cursors, recorded per read),
 // so that only what was produced is moved to the host (k_drain writes it straight into mapped pinned memory).
 #pragma once
