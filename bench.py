@@ -274,6 +274,36 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    # the same call from two host threads, each with its own context and buffers -- how `minimap2 -t 2` drives the drop-in (one
+    # context per worker thread): the pipeline drain of one caller's batch overlaps the other's upload.  Reported next to the
+    # single-caller number, which stays the e2e value.
+    two_callers = None
+    if world == 1:
+        try:
+            ctx_b = pkg.ChainContext(misc, device=local_rank, max_anchors=e2e_cap, max_reads=n_reads + 1, n_slots=6)
+            out_b = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
+                     "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
+            ctx_b.chain(h_a, off, out=out_b, packed=True)
+
+            def caller(c, o):
+                for _ in range(e2e_steps):
+                    c.chain(h_a, off, out=o, packed=True)
+            th = [threading.Thread(target=caller, args=(ctx_e2e, out)), threading.Thread(target=caller, args=(ctx_b, out_b))]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            dt2 = time.perf_counter() - t0
+            assert np.array_equal(out_b["n_u"], res["n_u"]) and np.array_equal(out_b["n_b"], res["n_b"])
+            two_callers = {"value": 2 * e2e_steps * pairs / dt2, "unit": "pairs/s", "ms_per_step": 1e3 * dt2 / (2 * e2e_steps),
+                           "note": "two host threads, one context each, same GPU; every step uploads its anchors and downloads its results"}
+            ctx_b.close()
+            del out_b
+        except Exception as exc:   # extra information only: never fail the bench line over it
+            two_callers = {"error": str(exc)[:200]}
     n_chains = int(res["n_u"].sum())
     n_chain_anchors = int(res["n_b"].sum())
     # where the end-to-end time goes: DP only (upload, kernels, f/p download), the host-stage variant of the same call
@@ -361,7 +391,7 @@ def main():
                     "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps,
                     "includes": "H2D anchors, range+unit+score kernels, device chain extraction + compaction (k_bt_sort/k_bt_walk), packed chains + compacted anchors written to pinned host memory by k_drain (= whole mg_lchain_dp)",
                     "chain_anchors": n_chain_anchors,
-                    "slots": 6, "chunk_anchors": e2e_cap,
+                    "slots": 6, "chunk_anchors": e2e_cap, "two_callers": two_callers,
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
             "gpu_launches": (8 + 2 * bt_classes) * args.steps, "clocks": clocks}

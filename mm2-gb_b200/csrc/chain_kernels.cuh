@@ -629,10 +629,11 @@ enum { MODE_MID = 0, MODE_FAR = 1, MODE_GEN = 2 };
 
 // One candidate.  The validity tests stay ONE predicate chain and the update is a single predicated max.
 // D = x_i - y_i + bw; jk / sti only used when CHECK (window still opening for some lane).
-template <int MODE, bool CHECK>
+template <int MODE, bool CHECK, int SH = kSlotBits>
 __device__ __forceinline__ void packed_upd(int &thr, int &pen, int D, int yi, int re, int rg, int ry, int rq, int maxd_q, unsigned bw,
                                            unsigned bw2, unsigned lut_s, int jk, int sti)
 {
+    constexpr int NEGMUL = -(1 << SH);   // the score sits above SH index bits
     if (MODE == MODE_MID) {
         asm volatile("{\n\t"
             ".reg .pred p;\n\t"
@@ -642,10 +643,10 @@ __device__ __forceinline__ void packed_upd(int &thr, int &pen, int D, int yi, in
             "setp.le.u32 p, tb, %5;\n\t"
             "add.u32 ad, tb, %6;\n\t"
             "@p ld.shared.u8 %1, [ad];\n\t"
-            "mad.lo.s32 key, %1, -8192, %4;\n\t"
+            "mad.lo.s32 key, %1, %7, %4;\n\t"
             "@p max.s32 %0, %0, key;\n\t"
             "}"
-            : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s));
+            : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "n"(NEGMUL));
     } else if (MODE == MODE_FAR) {
         asm volatile("{\n\t"
             ".reg .pred p;\n\t"
@@ -658,11 +659,11 @@ __device__ __forceinline__ void packed_upd(int &thr, int &pen, int D, int yi, in
             "sub.s32 dq, %7, %8;\n\t"
             "setp.le.and.s32 p, dq, %9, p;\n\t"
             "setp.ge.and.s32 p, %10, %11, p;\n\t"
-            "mad.lo.s32 key, %1, -8192, %4;\n\t"
+            "mad.lo.s32 key, %1, %12, %4;\n\t"
             "@p max.s32 %0, %0, key;\n\t"
             "}"
             : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q),
-              "r"(CHECK ? jk : 1), "r"(CHECK ? sti : 0));
+              "r"(CHECK ? jk : 1), "r"(CHECK ? sti : 0), "n"(NEGMUL));
     } else {
         asm volatile("{\n\t"
             ".reg .pred p;\n\t"
@@ -682,11 +683,11 @@ __device__ __forceinline__ void packed_upd(int &thr, int &pen, int D, int yi, in
             "setp.ge.and.s32 p, %10, %11, p;\n\t"
             "sub.s32 d, %13, m;\n\t"
             "add.s32 d, d, %1;\n\t"
-            "mad.lo.s32 key, d, -8192, %4;\n\t"
+            "mad.lo.s32 key, d, %14, %4;\n\t"
             "@p max.s32 %0, %0, key;\n\t"
             "}"
             : "+r"(thr), "+r"(pen) : "r"(D), "r"(re), "r"(rg), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q),
-              "r"(CHECK ? jk : 1), "r"(CHECK ? sti : 0), "r"(bw), "r"(rq));
+              "r"(CHECK ? jk : 1), "r"(CHECK ? sti : 0), "r"(bw), "r"(rq), "n"(NEGMUL));
     }
 }
 
@@ -1044,7 +1045,37 @@ __device__ __forceinline__ void long_walk32(int &thr, int &bj, int &pen, const R
     }
 }
 
-template <int RL, int NW>
+// The same 32 records with the candidates of ONE predecessor tile reduced in a packed register first:
+//     key = (f_j + sc) << 5 | (j & 31),   tkey = max(tkey, key)
+// (the predicated single max of score_unit_packed; 5 index bits are enough inside a tile, so scores up to 2^26 fit), then
+// one merge per tile into (thr, bj) with the '>=' rule.  Inside the tile the max prefers the larger j among equal scores,
+// across tiles '>=' in ascending order does: the result is that of the one-candidate-at-a-time update.
+constexpr int kTileBits = 5;
+template <int MODE, bool CHECK>
+__device__ __forceinline__ void long_walk32_pk(int &thr, int &bj, int &pen, const RecL *rp, int j0, int D, int yi, int maxd_q, unsigned bw,
+                                               unsigned bw2, unsigned lut_s, int sti)
+{
+    int tkey = kNegKey;
+#pragma unroll 1
+    for (int kk = 0; kk < 32; kk += 8) {
+        const RecL *r8 = rp + kk;
+        const int jb = j0 + kk;
+#pragma unroll
+        for (int K = 0; K < 8; ++K) {
+            if (MODE == MODE_MID) {
+                const int2 r = *reinterpret_cast<const int2 *>(r8 + K);
+                packed_upd<MODE, CHECK, kTileBits>(tkey, pen, D, yi, r.x, r.y, 0, 0, maxd_q, bw, bw2, lut_s, jb + K, sti);
+            } else {
+                const int4 r = *reinterpret_cast<const int4 *>(r8 + K);
+                packed_upd<MODE, CHECK, kTileBits>(tkey, pen, D, yi, r.x, r.y, r.z, r.w, maxd_q, bw, bw2, lut_s, jb + K, sti);
+            }
+        }
+    }
+    const int val = tkey >> kTileBits;
+    if (val >= thr) { thr = val; bj = j0 + (tkey & 31); }
+}
+
+template <int RL, int NW, bool PACK>
 __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p, int u0, int u1,
                                 int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecL *ring, int *s_done, int warp, int lane)
 {
@@ -1091,15 +1122,21 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
             }
             const int j0 = u0 + 32 * k;
             const RecL *rp = ring + ((32 * k) & (RL - 1));
+#define MM2GB_LWALK(MODE, CHECK)                                                                                         \
+    do {                                                                                                                \
+        if (PACK) long_walk32_pk<MODE, CHECK>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);                \
+        else long_walk32<MODE, CHECK>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);                        \
+    } while (0)
             if (j0 < wfull) { // some lane's window opens inside or after this tile (or the tile straddles rid/strand runs)
-                long_walk32<MODE_GEN, true>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
+                MM2GB_LWALK(MODE_GEN, true);
             } else {          // inside every lane's window: same rid/strand as the whole tile, x ascending
                 const int xk_first = rp[0].e + rp[0].y, xk_last = rp[31].e + rp[31].y;
                 if (x_first - xk_last > near_d) {
-                    if (x_last - xk_first <= far_d) long_walk32<MODE_MID, false>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
-                    else long_walk32<MODE_FAR, false>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
-                } else long_walk32<MODE_GEN, false>(thr, bj, pen, rp, j0, D, yi, maxd_q, bw, bw2, lut_s, sti);
+                    if (x_last - xk_first <= far_d) MM2GB_LWALK(MODE_MID, false);
+                    else MM2GB_LWALK(MODE_FAR, false);
+                } else MM2GB_LWALK(MODE_GEN, false);
             }
+#undef MM2GB_LWALK
         }
         // publish this tile's static fields (nobody reads them as a predecessor before s_done passes t)
         RecL *tile = ring + ((32 * t) & (RL - 1));
@@ -1139,7 +1176,7 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
         if (act) {
             f[i] = fcur;
             p[i] = bj < 0 ? -1 : bj - rbase;
-            tile[lane].g = fcur + qsi;
+            tile[lane].g = PACK ? (((fcur + qsi) << kTileBits) | lane) : fcur + qsi;
         }
         // tiles finish in order: a tile whose window does not reach back into tile t - 1 (a cut inside the unit) has not
         // waited for it yet
@@ -1182,7 +1219,11 @@ k_score_long(const uint4 *__restrict__ a, const int *__restrict__ st, const int 
         const int u0 = unit_start[k], u1 = unit_start[k + 1], rbase = unit_rbase[k];
         if (unit_has_clip(clipmask, u0, u1, lane)) continue; // exact max_ii path, k_score_units
         if (threadIdx.x == 0) atomicAdd(&ctr->n_long, 1);
-        score_unit_long<RL, NW>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane);
+        // packed per-tile keys hold scores below 2^26 (f <= unit length x largest q_span)
+        if ((long long)(u1 - u0 + 1) * qs_max < (1LL << 26))
+            score_unit_long<RL, NW, true>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane);
+        else
+            score_unit_long<RL, NW, false>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane);
     }
 }
 
