@@ -127,7 +127,7 @@ void *mm2gb_stream(mm2gb_ctx_t *ctx, int slot);
 int mm2gb_device_stats(mm2gb_ctx_t *ctx, mm2gb_stats_t *stats);
 
 /* Per-kernel device time of slot 0, accumulated with CUDA events while profiling is on.
- * ms[0]=range ms[1]=unit-build ms[2]=score ms[3]=chain extraction (k_backtrack) ms[4]=H2D ms[5]=D2H; launches[] likewise. */
+ * ms[0]=range ms[1]=unit-build ms[2]=score ms[3]=chain extraction (k_bt_sort* + k_bt_walk*) ms[4]=H2D ms[5]=D2H; launches[] likewise. */
 #define MM2GB_NTIMERS 6
 int mm2gb_profile(mm2gb_ctx_t *ctx, int enable);
 int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launches[MM2GB_NTIMERS]);
@@ -142,7 +142,7 @@ int mm2gb_debug_drain(mm2gb_ctx_t *ctx, int64_t n, int blocks, float ms[5]);
 int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p, const mm2gb_anchor_t *a, int32_t min_cnt, int32_t min_sc,
                         int32_t max_drop, uint64_t *u, mm2gb_anchor_t *b, int64_t *n_b);
 
-/* The device version of that stage (k_backtrack; what mm2gb_chain_host with n_threads <= 0 and the drop-in run behind the DP
+/* The device version of that stage (k_bt_sort* / k_bt_walk*; what mm2gb_chain_host with n_threads <= 0 and the drop-in run behind the DP
  * kernels) on caller-supplied f / p: same outputs, layout as in mm2gb_chain_host.  *n_declined = reads handed to the host
  * implementation (only with min_score < 0, or more than 256 reads of a batch overflowing the shared-memory kernels).
  * Synchronous; uses slot 0. */

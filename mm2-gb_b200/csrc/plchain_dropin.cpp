@@ -14,7 +14,7 @@
 //   * anchors are gathered straight from chain_read_t.a into pinned memory -- no AoS->SoA repack (plmem.cu:154-198);
 //   * no read is ever handed back for CPU chaining (plchain.cu:421-423): oversized batches grow the context instead;
 //   * --max-chain-skip is ignored, i.e. true infinity (SURVEY.md trap T1), as in the reference's kernels;
-//   * chain extraction + compaction (lchain.c:27-111) run on the device behind the DP kernels (k_backtrack); the calling
+//   * chain extraction + compaction (lchain.c:27-111) run on the device behind the DP kernels (k_bt_sort* / k_bt_walk*); the calling
 //     thread only copies the results into the kalloc arena (kalloc is not thread-safe).  "host_backtrack": 1 in the config
 //     (or MM2GB_HOST_BACKTRACK=1) moves that stage to a small host thread pool instead (csrc/backtrack.cpp).
 #include "../../include/mm2gb_plchain.h"

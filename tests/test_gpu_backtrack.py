@@ -1,4 +1,4 @@
-"""GPU tests (-m gpu) of the device chain-extraction stage (k_backtrack): mg_chain_backtrack + compact_a (lchain.c:27-111)
+"""GPU tests (-m gpu) of the device chain-extraction stage (k_bt_sort / k_bt_walk and their _mid / _big variants): mg_chain_backtrack + compact_a (lchain.c:27-111)
 including the tie order of the reference's unstable radix sort.  Checked against the oracle on real DP output, and against
 the host implementation (itself pinned to the reference by test_oracle / test_gpu_parity) on synthetic score / predecessor
 forests that stress the sort emulation (many equal scores, deep radix recursion, many chains)."""
