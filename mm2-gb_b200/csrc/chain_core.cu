@@ -1187,7 +1187,7 @@ extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void
     return MM2GB_OK;
 }
 
-// device-resident DP + chain extraction: as mm2gb_chain_dp_device, then k_backtrack into slot 0's output buffers
+// device-resident DP + chain extraction: as mm2gb_chain_dp_device, then k_bt_sort* / k_bt_walk* into slot 0's output buffers
 // (`off` = host copy of the offsets, needed to bin the reads by size)
 extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, const int64_t *off, int n_reads, int64_t n_total,
                                   void *d_f, void *d_p)
