@@ -94,26 +94,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def bind_near_gpu(gpu_index):
-    """One rank per GPU: run on (and first-touch the pinned buffers from) the host cores next to this GPU, so that the uploads and
-    downloads of eight ranks do not all cross the socket interconnect.  Best effort: returns the cores used, or None."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        n_cpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
-        near = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
-        allowed = set(os.sched_getaffinity(0))
-        use = sorted(near & allowed)
-        if use and len(use) < len(allowed):
-            os.sched_setaffinity(0, use)
-            return len(use)
-    except Exception:
-        pass
-    return None
-
-
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -227,7 +207,6 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the chaining path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    numa = bind_near_gpu(local_rank) if world > 1 and os.environ.get("MM2GB_BIND_NUMA", "0") == "1" else None   # opt-in
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -416,8 +395,6 @@ def main():
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
             "gpu_launches": (8 + 2 * bt_classes) * args.steps, "clocks": clocks}
-    if numa:
-        line["config"]["host_cores_near_gpu"] = numa
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
     emit(line)

@@ -80,6 +80,7 @@ struct Slot {
     long long *d_off = nullptr;
     int *d_st = nullptr, *d_f = nullptr, *d_p = nullptr;
     unsigned *d_selmask = nullptr, *d_clipmask = nullptr;
+    int *d_chunk_tot = nullptr, *d_chunk_base = nullptr; unsigned long long *d_chunk_pairs = nullptr;   // k_scan: one entry per 8192 blocks
     int *d_block_cnt = nullptr, *d_block_base = nullptr; unsigned long long *d_block_pairs = nullptr; int *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
     int big_cap = 0;
     Counters *d_ctr = nullptr;
@@ -346,8 +347,9 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
     }
     {
         ProfScope ps(c, T_UNITS, s, prof);
-        k_scan<<<1, 1024, 0, s>>>(sl.d_block_cnt, sl.d_block_pairs, n_blocks, sl.d_block_base, sl.d_ctr);
-        k_units<<<(n_groups + 255) / 256, 256, 0, s>>>(sl.d_selmask, sl.d_block_base, d_off, n_reads, n, n_groups, sl.d_unit_start,
+        k_scan<<<(n_blocks + kScanChunk - 1) / kScanChunk, 1024, 0, s>>>(sl.d_block_cnt, sl.d_block_pairs, n_blocks, sl.d_block_base, sl.d_chunk_tot,
+                                                                        sl.d_chunk_pairs, sl.d_chunk_base, sl.d_ctr);
+        k_units<<<(n_groups + 255) / 256, 256, 0, s>>>(sl.d_selmask, sl.d_block_base, sl.d_chunk_base, d_off, n_reads, n, n_groups, sl.d_unit_start,
                                                       sl.d_unit_rbase, sl.d_ctr);
         k_order<<<(n_groups + n_reads + 256) / 256, 256, 0, s>>>(sl.d_unit_start, sl.d_big_order, sl.big_cap, sl.d_ctr);
     }
@@ -523,6 +525,7 @@ static void free_slot(Slot &s)
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
     cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
+    cudaFree(s.d_chunk_tot); cudaFree(s.d_chunk_base); cudaFree(s.d_chunk_pairs);
     cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
     cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_rinfo); cudaFree(s.d_list); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
     cudaFree(s.d_zk); cudaFree(s.d_zk2); cudaFree(s.d_tb); cudaFree(s.d_pay2); cudaFree(s.d_ovf);
@@ -617,6 +620,9 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             CKC(cudaMalloc(&s.d_clipmask, n_groups * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_block_cnt, n_blocks * sizeof(int)));
             CKC(cudaMalloc(&s.d_block_base, n_blocks * sizeof(int)));
+            CKC(cudaMalloc(&s.d_chunk_tot, (n_blocks / kScanChunk + 2) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_chunk_base, (n_blocks / kScanChunk + 2) * sizeof(int)));
+            CKC(cudaMalloc(&s.d_chunk_pairs, (n_blocks / kScanChunk + 2) * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_block_pairs, n_blocks * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_unit_start, n_units_cap * sizeof(int)));
             CKC(cudaMalloc(&s.d_unit_rbase, n_units_cap * sizeof(int)));

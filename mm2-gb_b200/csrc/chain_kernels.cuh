@@ -47,6 +47,7 @@ struct Counters {
     int qs_max;             // largest q_span in the batch (bounds the chain scores: f <= unit length * qs_max)
     int ovf_cnt;            // reads the shared-memory chain-extraction kernels handed to the global-memory ones
     int u_cur, b_cur;       // cursors of the packed chain / compacted-anchor outputs of the batch (k_bt_walk)
+    int scan_done;          // chunks of k_scan that have finished (the last one combines them)
     unsigned long long n_pairs;
 };
 
@@ -229,80 +230,105 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, con
     }
 }
 
-// k_scan: exclusive prefix of the per-block unit counts (single block, 8 consecutive entries per thread and round so that the
-//         ~120 k entries of a 30 M-anchor batch take 15 rounds of barriers, not 121), total -> ctr->n_units
+// k_scan: exclusive prefix of the per-block unit counts, total -> ctr->n_units.  One CTA per chunk of 8192 entries (8 consecutive
+//         entries per thread): block_base[i] = prefix inside the chunk; the CTA that finishes last scans the chunk totals into
+//         chunk_base[] (k_units adds the two) and sums the pair counts.  (A single CTA walking all ~120 k entries of a
+//         30 M-anchor batch took 125 us.)
 constexpr int kScanPer = 8;
+constexpr int kScanChunk = 1024 * kScanPer;
 __global__ void __launch_bounds__(1024)
 k_scan(const int *__restrict__ block_cnt, const unsigned long long *__restrict__ block_pairs, int n_blocks, int *__restrict__ block_base,
-       Counters *__restrict__ ctr)
+       int *chunk_tot, unsigned long long *chunk_pairs, int *__restrict__ chunk_base, Counters *ctr)
 {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
     __shared__ unsigned long long s_pw[32];
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    unsigned long long pairs = 0;
-    for (int base = 0; base < n_blocks; base += 1024 * kScanPer) {
-        const int i0 = base + threadIdx.x * kScanPer;
-        int v[kScanPer];
-        int x = 0;
+    const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanPer;
+    int v[kScanPer];
+    unsigned long long pv[kScanPer];
+    // all 16 loads first (clamped index, no branch around them), so that they are in flight together
 #pragma unroll
-        for (int q = 0; q < kScanPer; ++q) {
-            const int i = i0 + q;
-            v[q] = i < n_blocks ? block_cnt[i] : 0;
-            if (i < n_blocks) pairs += block_pairs[i];
-            x += v[q];
-        }
-        const int mine = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d) x += y;
-        }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int w = s_warp[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, w, d);
-                if (lane >= d) w += y;
-            }
-            s_warp[lane] = w; // inclusive
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int incl = x + (wid ? s_warp[wid - 1] : 0) + carry;
-        int run = incl - mine;
-#pragma unroll
-        for (int q = 0; q < kScanPer; ++q) {
-            const int i = i0 + q;
-            if (i < n_blocks) block_base[i] = run;
-            run += v[q];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = incl;
-        __syncthreads();
+    for (int q = 0; q < kScanPer; ++q) {
+        const int ic = min(i0 + q, n_blocks - 1);
+        v[q] = __ldg(block_cnt + ic);
+        pv[q] = __ldg(block_pairs + ic);
     }
-    // total pair count = sum_i (i - st_i)  (the reference's n_iter, lchain.c:177)
+    int x = 0;
+    unsigned long long pairs = 0;
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) {
+        if (i0 + q >= n_blocks) { v[q] = 0; pv[q] = 0; }
+        pairs += pv[q];
+        x += v[q];
+    }
+    const int mine = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+    if (lane == 31) s_warp[wid] = x;
     if (lane == 0) s_pw[wid] = pairs;
     __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += y;
+        }
+        s_warp[lane] = w; // inclusive
+    }
+    __syncthreads();
+    const int incl = x + (wid ? s_warp[wid - 1] : 0);
+    int run = incl - mine;
+#pragma unroll
+    for (int q = 0; q < kScanPer; ++q) {
+        if (i0 + q < n_blocks) block_base[i0 + q] = run;
+        run += v[q];
+    }
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
         for (int w = 0; w < 32; ++w) t += s_pw[w];
-        ctr->n_pairs = t;
-        ctr->n_units = s_carry;
+        chunk_tot[blockIdx.x] = s_warp[31];
+        chunk_pairs[blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(&ctr->scan_done, 1) == (int)gridDim.x - 1;
     }
+    __syncthreads();
+    if (!s_last || wid != 0) return;
+    // the last chunk to finish: prefix over the chunk totals (a few hundred at most), total pair count = sum_i (i - st_i)
+    // (the reference's n_iter, lchain.c:177)
+    __threadfence();
+    int base = 0;
+    unsigned long long tp = 0;
+    for (int c0 = 0; c0 < (int)gridDim.x; c0 += 32) {
+        const int c = c0 + lane;
+        const int tv = c < (int)gridDim.x ? __ldcg(chunk_tot + c) : 0;
+        if (c < (int)gridDim.x) tp += __ldcg(chunk_pairs + c);
+        int in = tv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, in, d);
+            if (lane >= d) in += y;
+        }
+        if (c < (int)gridDim.x) chunk_base[c] = base + in - tv;
+        base += __shfl_sync(0xffffffffu, in, 31);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, d);
+    if (lane == 0) { ctr->n_pairs = tp; ctr->n_units = base; }
 }
 
 // k_units: ordered scatter of the selected cuts -> unit_start[k], unit_rbase[k] (first anchor of the owning read),
 //          sentinel unit_start[n_units] = n_total.  One thread per 32-anchor group.
 __global__ void __launch_bounds__(256)
-k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base, const long long *__restrict__ off, int n_reads,
-        int n_total, int n_groups, int *__restrict__ unit_start, int *__restrict__ unit_rbase, const Counters *__restrict__ ctr)
+k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base, const int *__restrict__ chunk_base,
+        const long long *__restrict__ off, int n_reads, int n_total, int n_groups, int *__restrict__ unit_start,
+        int *__restrict__ unit_rbase, const Counters *__restrict__ ctr)
 {
     const int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp == 0) unit_start[ctr->n_units] = n_total;
@@ -310,7 +336,7 @@ k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base
     unsigned m = selmask[grp];
     if (!m) return;
     const int b = grp / kGroupsPerBlock;
-    int k = block_base[b];
+    int k = block_base[b] + chunk_base[b / kScanChunk];
     for (int g2 = b * kGroupsPerBlock; g2 < grp; ++g2) k += __popc(selmask[g2]);
     while (m) {
         const int bit = __ffs(m) - 1;
