@@ -141,6 +141,11 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, con
         const unsigned long long yup = __shfl_up_sync(0xffffffffu, ai.y, 1);
         if (lane) yprev = yup;
     }
+    // the first chunk of history and the start of the first anchor's read are always needed: their loads are issued here,
+    // together with the block's own anchors, not one latency later (the kernel is bound by dependent-load latency)
+    const int gpre = g0 - kRangeThreads + (int)threadIdx.x;
+    const unsigned long long xpre = gpre >= 0 ? a[gpre].x : 0ULL;
+    const long long rs0 = off[r0];
     s_x[kRangeHist + threadIdx.x] = ai.x;
     __syncthreads();
     // history: stop once the oldest staged x is outside the first anchor's window (x sorted => outside everyone's), or the
@@ -151,11 +156,10 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, con
         const unsigned long long x0 = s_x[kRangeHist];
         const unsigned x0lo = (unsigned)x0;
         const unsigned long long lower0 = (x0 & 0xffffffff00000000ULL) | (unsigned long long)(x0lo > mdx ? x0lo - mdx : 0u);
-        const long long rs0 = off[r0];
         while (hist < kRangeHist) {
             const int base = g0 - hist - kRangeThreads;    // next chunk [base, base + 256)
             const int gi = base + (int)threadIdx.x;
-            const unsigned long long xv = gi >= 0 ? a[gi].x : 0ULL;
+            const unsigned long long xv = hist == 0 ? xpre : (gi >= 0 ? a[gi].x : 0ULL);
             s_x[kRangeHist - hist - kRangeThreads + threadIdx.x] = xv;
             if (threadIdx.x == 0) s_more = (gi > rs0 && xv >= lower0) ? 1 : 0;   // oldest of the chunk still inside the window
             hist += kRangeThreads;
