@@ -88,17 +88,41 @@ struct BtSortScratch {
 // start = bucket boundaries of that pass (257 entries), or nullptr to sort [lo, hi) as ONE bucket.
 template <class KO, bool PAY, class PAYT, class POS>
 __device__ void bt_rank_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT *tmpPay, int lo, int hi,
-                             int shift, const POS *start, int lane)
+                             int shift, const POS *start, int lane, unsigned *dirty = nullptr)
 {
     typedef typename KO::T K;
+    // Most buckets of real score arrays are sorted already (scores grow along a chain): with `dirty` ([256] words, free after
+    // the pass) a first sweep marks the buckets that hold an element smaller than its left neighbour, and only those are
+    // ranked and moved -- nothing at all if there is none.
+    if (start && dirty) {
+        for (int d = lane; d < 256; d += 32) dirty[d] = 0;
+        __syncwarp();
+        bool any = false;
+        for (int e0 = lo; e0 < hi; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < hi) {
+                const K key = A[e];
+                const unsigned d = KO::digit(key, shift);
+                if (e > (int)start[d] && KO::less(key, A[e - 1])) { dirty[d] = 1; any = true; }
+            }
+        }
+        if (!__any_sync(0xffffffffu, any)) return;
+        __syncwarp();
+    }
     for (int e0 = lo; e0 < hi; e0 += 32) {
         const int e = e0 + lane;
         if (e < hi) {
             const K key = A[e];
             int bs = lo, be = hi;
-            if (start) { const unsigned d = KO::digit(key, shift); bs = (int)start[d]; be = (int)start[d + 1]; }
+            bool todo = true;
+            if (start) {
+                const unsigned d = KO::digit(key, shift);
+                bs = (int)start[d];
+                be = (int)start[d + 1];
+                if (dirty) todo = dirty[d] != 0;
+            }
             const int m = be - bs;
-            if (m >= 2 && m <= 64) {
+            if (todo && m >= 2 && m <= 64) {
                 int r = 0;
                 if constexpr (KO::kPosKey) { // stable order = order of (score, position): one compare per bucket mate
                     const unsigned ce = KO::poskey(key, e);
@@ -248,7 +272,7 @@ __device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT
     int lv = 0;
     POS *row = sc.start;
     bt_flag_pass<KO, PAY, PAYT, POS>(A, pay, 0, n, shift, sc.cnt, row, lane);
-    if (shift) bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, 0, n, shift, row, lane);
+    if (shift) bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, 0, n, shift, row, lane, sc.cnt);
     if (lane == 0) { row[257] = 0; row[258] = (POS)shift; }
     __syncwarp();
     while (lv >= 0) {
@@ -274,7 +298,7 @@ __device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT
         POS *crow = sc.start + lv * kBtRow;
         __syncwarp();
         bt_flag_pass<KO, PAY, PAYT, POS>(A, pay, blo, bhi, nsh, sc.cnt, crow, lane);
-        if (nsh) bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, blo, bhi, nsh, crow, lane);
+        if (nsh) bt_rank_sort<KO, PAY, PAYT, POS>(A, pay, tmpA, tmpPay, blo, bhi, nsh, crow, lane, sc.cnt);
         if (lane == 0) { crow[257] = 0; crow[258] = (POS)nsh; }
         __syncwarp();
     }
@@ -454,13 +478,26 @@ __device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, const B
 // rank sort of every bucket of 2..64 elements of one pass over A[lo, hi) in global memory, by the whole CTA (bt_rank_sort is
 // the one-warp version): rank = number of bucket mates that order before the element as (score, position)
 template <class KO>
-__device__ void bt_rank_sort_blk(typename KO::T *A, typename KO::T *tmpA, int lo, int hi, int shift, const unsigned *start, int tid)
+__device__ void bt_rank_sort_blk(typename KO::T *A, typename KO::T *tmpA, int lo, int hi, int shift, const unsigned *start, int tid,
+                                 unsigned *dirty, unsigned *any_dirty)
 {
     typedef typename KO::T K;
     constexpr int NT = kBtMidThreads;
+    // only buckets that hold an element smaller than its left neighbour need ranking (see bt_rank_sort)
+    for (int d = tid; d < 256; d += NT) dirty[d] = 0;
+    if (tid == 0) *any_dirty = 0;
+    __syncthreads();
     for (int e = lo + tid; e < hi; e += NT) {
         const K key = A[e];
         const unsigned d = KO::digit(key, shift);
+        if (e > (int)start[d] && KO::less(key, A[e - 1])) { dirty[d] = 1; *any_dirty = 1; }
+    }
+    __syncthreads();
+    if (*any_dirty == 0) return;
+    for (int e = lo + tid; e < hi; e += NT) {
+        const K key = A[e];
+        const unsigned d = KO::digit(key, shift);
+        if (!dirty[d]) continue;
         const int bs = (int)start[d], be = (int)start[d + 1];
         const int m = be - bs;
         int r = e - bs;
@@ -474,7 +511,10 @@ __device__ void bt_rank_sort_blk(typename KO::T *A, typename KO::T *tmpA, int lo
         tmpA[bs + r] = key;
     }
     __syncthreads();
-    for (int e = lo + tid; e < hi; e += NT) A[e] = tmpA[e];
+    for (int e = lo + tid; e < hi; e += NT) {
+        const K key = A[e];
+        if (dirty[KO::digit(key, shift)]) A[e] = tmpA[e];
+    }
     __syncthreads();
 }
 
@@ -524,7 +564,7 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, cons
     int lv = 0;
     unsigned *row = q.rows;
     bt_flag_pass_fq<KO>(A, tmpA, q, 0, n, shift, row, D, tid);
-    if (shift) bt_rank_sort_blk<KO>(A, tmpA, 0, n, shift, row, tid);
+    if (shift) bt_rank_sort_blk<KO>(A, tmpA, 0, n, shift, row, tid, q.cnt, q.misc + 4);
     if (tid == 0) { row[257] = 0; row[258] = (unsigned)shift; }
     __syncthreads();
     while (lv >= 0) {
@@ -562,7 +602,7 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, cons
         ++lv;
         unsigned *crow = q.rows + lv * kBtRow;
         bt_flag_pass_fq<KO>(A, tmpA, q, blo, bhi, nsh, crow, D, tid);
-        if (nsh) bt_rank_sort_blk<KO>(A, tmpA, blo, bhi, nsh, crow, tid);
+        if (nsh) bt_rank_sort_blk<KO>(A, tmpA, blo, bhi, nsh, crow, tid, q.cnt, q.misc + 4);
         if (tid == 0) { crow[257] = 0; crow[258] = (unsigned)nsh; }
         __syncthreads();
     }
