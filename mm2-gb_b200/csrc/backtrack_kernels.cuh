@@ -640,12 +640,12 @@ __device__ __forceinline__ int bt_collect(const int *__restrict__ fr, int n, int
     const unsigned full = 0xffffffffu;
     int nz = 0;
     fmax = 0;
-    for (int i0 = 0; i0 < n; i0 += 128) {
-        int fv[4];
+    for (int i0 = 0; i0 < n; i0 += 256) {   // 8 coalesced loads per lane in flight: the loop is bound by their latency
+        int fv[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; fv[t] = i < n ? fr[i] : INT32_MIN; }
+        for (int t = 0; t < 8; ++t) { const int i = i0 + t * 32 + lane; fv[t] = i < n ? fr[i] : INT32_MIN; }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 8; ++t) {
             const int i = i0 + t * 32 + lane;
             const bool keep = fv[t] >= min_sc && i < n;
             const unsigned m = __ballot_sync(full, keep);
@@ -788,12 +788,19 @@ struct WalkSmall {
     __device__ __forceinline__ int *lp_path() { return nullptr; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
-        for (int i0 = 0; i0 < n; i0 += 128) { // 4 coalesced loads of each array per lane in flight, then 4 gathers of f[p[i]]
+        // 4 coalesced loads of each array per lane, then 4 gathers of f[p[i]]; the loads of the NEXT 128 anchors are issued
+        // before the gathers are consumed, so an iteration costs one memory latency, not two
+        int pn[4], fn[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int i = t * 32 + lane; pn[t] = i < n ? pr[i] : -1; fn[t] = i < n ? fr[i] : 0; }
+        for (int i0 = 0; i0 < n; i0 += 128) {
             int pv[4], fv[4], fp[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; pv[t] = i < n ? pr[i] : -1; fv[t] = i < n ? fr[i] : 0; }
+            for (int t = 0; t < 4; ++t) { pv[t] = pn[t]; fv[t] = fn[t]; }
 #pragma unroll
             for (int t = 0; t < 4; ++t) fp[t] = pv[t] >= 0 ? fr[pv[t]] : 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = i0 + 128 + t * 32 + lane; pn[t] = i < n ? pr[i] : -1; fn[t] = i < n ? fr[i] : 0; }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int i = i0 + t * 32 + lane;
