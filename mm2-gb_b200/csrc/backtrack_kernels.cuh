@@ -1263,13 +1263,19 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             const unsigned long long uv = ur[src];
             const int cntc = (int)(unsigned)uv, s0 = vsr[src];
             if (lane == 0) uo[c] = uv;
+            // the indices of the NEXT 128 anchors are fetched while the gathers of the current ones are in flight
+            int nidx[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int q = t * 32 + lane; nidx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
             for (int q0 = 0; q0 < cntc; q0 += 128) {
                 int idx[4];
                 uint4 val[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) { const int q = q0 + t * 32 + lane; idx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
+                for (int t = 0; t < 4; ++t) idx[t] = nidx[t];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) if (idx[t] >= 0) val[t] = ar[idx[t]];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { const int q = q0 + 128 + t * 32 + lane; nidx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
 #pragma unroll
                 for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[out + q0 + t * 32 + lane] = val[t];
             }
