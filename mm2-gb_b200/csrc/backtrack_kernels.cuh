@@ -996,9 +996,12 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         // the chase needs no end test); where the walk ends is found afterwards for all 32 nodes at once.
         int cur = i0, max_s = 0, cutj = 0, cutf = 0, j0 = 0;   // cutf = f of the node the chain is cut at
         int mine0 = SENT; // this lane's node of the first batch (enough to mark chains of <= 32 nodes without re-reading)
+        bool have = false;  // path[] already holds the next batch (chased ahead, below)
         for (;;) {
             int nb = 32;
-            if (j0 == 0 && !nothing_claimed) {
+            if (have) {
+                have = false;
+            } else if (j0 == 0 && !nothing_claimed) {
                 // first batch of a later walk: most of them end within a few nodes (at a claimed anchor), so look as we go
                 nb = 0;
 #pragma unroll 4
@@ -1020,8 +1023,18 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             __syncwarp();
             const int mine = lane < nb ? (int)path[lane] : SENT;
             int fmine = 0;
-            if (lane < nb) fmine = S.fat(mine, fr);      // 0 for the sentinel
+            if (lane < nb) fmine = S.fat(mine, fr);      // 0 for the sentinel; a gather from global memory
             __syncwarp();
+            if (nb == 32) {
+                // a full batch: the walk most likely goes on, so the next 32 nodes are chased (shared memory only) while the
+                // gather is in flight; if the walk ends in this batch the chase was for nothing
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    if (lane == 0) path[b] = (IDX)cur;
+                    cur = S.nextp(cur);
+                }
+                have = true;
+            }
             if (j0 == 0) mine0 = mine;
             const int j = j0 + lane;
             const bool ev = j >= 1 && lane < nb;
