@@ -1074,7 +1074,13 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
                 if (lane < cnt) S.claim(mine0);
             } else {
                 __syncwarp();
-                for (int q = lane; q < cnt; q += 32) S.claim(vr[n_v + q]);
+                for (int q0 = 0; q0 < cnt; q0 += 256) {   // 8 loads of the recorded path per lane in flight
+                    int nd[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) { const int q = q0 + t * 32 + lane; nd[t] = q < cnt ? vr[n_v + q] : -1; }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) if (nd[t] >= 0) S.claim(nd[t]);
+                }
             }
         }
         __syncwarp();
