@@ -911,12 +911,12 @@ struct WalkMid {
     }
     __device__ __forceinline__ void init(int n_, const int *, const int *__restrict__ prr, int lane)
     {
-        for (int i0 = 0; i0 < n_; i0 += 128) {
-            int pv[4];
+        for (int i0 = 0; i0 < n_; i0 += 256) {   // 8 coalesced loads per lane in flight
+            int pv[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; pv[t] = i < n_ ? prr[i] : -1; }
+            for (int t = 0; t < 8; ++t) { const int i = i0 + t * 32 + lane; pv[t] = i < n_ ? prr[i] : -1; }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
                 const int i = i0 + t * 32 + lane;
                 if (i < n_) rel[i] = pv[t] < 0 ? (unsigned char)0 : (unsigned char)min(i - pv[t], 255);
             }
