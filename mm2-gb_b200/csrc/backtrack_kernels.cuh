@@ -982,10 +982,12 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     int B = k;
     ZT zc = (B - lane >= 0) ? S.zat(B - lane) : (ZT)0;
     ZT zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
-    // further groups in flight: a run of claimed windows is skipped much faster than a load returns
-    ZT zn2 = (B - 64 - lane >= 0) ? S.zat(B - 64 - lane) : (ZT)0;
-    ZT zn3 = (B - 96 - lane >= 0) ? S.zat(B - 96 - lane) : (ZT)0;
-    ZT zn4 = (B - 128 - lane >= 0) ? S.zat(B - 128 - lane) : (ZT)0;
+    // further groups in flight (zq[g] = z[B - 64 - 32 g - lane]): a run of claimed windows is skipped much faster than a load
+    // returns, so the scan needs about latency / (time per window) loads outstanding
+    constexpr int kZq = 6;
+    ZT zq[kZq];
+#pragma unroll
+    for (int g = 0; g < kZq; ++g) zq[g] = (B - 64 - 32 * g - lane >= 0) ? S.zat(B - 64 - 32 * g - lane) : (ZT)0;
     IDX *path = S.path();
     // one cooperative walk from the end zkk = (score, index): the whole warp chases its path and evaluates it
     auto walk_one = [&](typename ZK::T zkk) {
@@ -1176,11 +1178,11 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             const int e = k - lane;
             while (k <= B - 32) {                          // the window left group zc behind
                 zc = zn;
-                zn = zn2;
-                zn2 = zn3;
-                zn3 = zn4;
+                zn = zq[0];
+#pragma unroll
+                for (int g = 0; g + 1 < kZq; ++g) zq[g] = zq[g + 1];
                 B -= 32;
-                zn4 = (B - 128 - lane >= 0) ? S.zat(B - 128 - lane) : (ZT)0;
+                zq[kZq - 1] = (B - 64 - 32 * (kZq - 1) - lane >= 0) ? S.zat(B - 64 - 32 * (kZq - 1) - lane) : (ZT)0;
             }
             ZT z = zc;
             const int sft = B - k;                         // warp-uniform, 0 .. 31
