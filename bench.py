@@ -12,8 +12,10 @@ workload  = BASELINE.json configs[1]: 100 Mb random reference, 10k simulated ONT
 value     = pairs chained per second with the anchors already resident in HBM (CUDA events on the launching stream,
             max over ranks); pairs = sum_i (i - st_i) = the reference's n_iter (lchain.c:177), counted by the device and
             cross-checked against the oracle in the tests.
-e2e       = the same metric through the C ABI call mm2gb_chain_host with pinned HOST buffers: upload of the anchors, all
-            kernels, download of the chains and compacted anchors are inside the timed region.
+e2e       = the same metric through the C ABI call mm2gb_chain_host_packed with pinned HOST buffers: upload of the anchors, all
+            kernels, download of the chains and compacted anchors are inside the timed region (one synchronous caller;
+            e2e.two_callers adds the number for two host threads with a context each, as `minimap2 -t 2` drives the drop-in).
+clocks    = SM clock and throttle reasons sampled through NVML every 20 ms over both timed regions.
 roofline  = the score kernel (dominant): algorithmic HBM bytes (24 B/anchor) over its CUDA-event time vs the measured copy
             peak, plus the issue-slot view that actually bounds it (SASS thread-instructions per pair / SM issue rate).
 cpu_baseline / --impl reference = the reference's own lchain.c (oracle/_ref/libref_lchain.so, compiled from the
