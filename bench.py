@@ -12,9 +12,13 @@ workload  = BASELINE.json configs[1]: 100 Mb random reference, 10k simulated ONT
 value     = pairs chained per second with the anchors already resident in HBM (CUDA events on the launching stream,
             max over ranks); pairs = sum_i (i - st_i) = the reference's n_iter (lchain.c:177), counted by the device and
             cross-checked against the oracle in the tests.
-e2e       = the same metric through the C ABI call mm2gb_chain_host_packed with pinned HOST buffers: upload of the anchors, all
-            kernels, download of the chains and compacted anchors are inside the timed region (one synchronous caller;
-            e2e.two_callers adds the number for two host threads with a context each, as `minimap2 -t 2` drives the drop-in).
+e2e       = the same metric through the reference-facing boundary itself -- init_stream_gpu / chain_stream_gpu / finish_stream_gpu
+            (include/mm2gb_plchain.h) -- called the way `minimap2 -t T --gpu-chain` calls it (tests/fake_host.c: fake_drive): T worker
+            threads, per-read kmalloc'd pageable anchor arrays, host gather + upload + all kernels + download + compact_a's gather
+            into kmalloc'd results inside the timed region.  e2e.core_abi is the same batch through mm2gb_chain_host_index with
+            caller-pinned buffers (no host pass at all).
+parity    = every read of the timed e2e run (n_u, chain-anchor count, digests of u[] and a'[]) against the reference's own lchain.c;
+            a mismatch makes the run exit non-zero.
 clocks    = SM clock and throttle reasons sampled through NVML every 20 ms over both timed regions.
 roofline  = the score kernel (dominant): algorithmic HBM bytes (24 B/anchor) over its CUDA-event time vs the measured copy
             peak, plus the issue-slot view that actually bounds it (SASS thread-instructions per pair / SM issue rate).
@@ -237,9 +241,6 @@ def main():
     n, n_reads = int(off[-1]), len(off) - 1
     misc = pkg.map_ont_misc()
     ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=max(n, 1 << 20), max_reads=n_reads + 1, n_slots=1)   # whole batch resident
-    # the end-to-end path streams the batch through 6 slots of one eighth of it each
-    e2e_cap = max(1 << 20, n // 8 + int(np.diff(off).max()) + 1)
-    ctx_e2e = pkg.ChainContext(misc, device=local_rank, max_anchors=e2e_cap, max_reads=n_reads + 1, n_slots=6)
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(0), device=local_rank)
 
     # device-resident inputs
@@ -281,12 +282,51 @@ def main():
     prof = ctx.profile_read()
     ctx.profile(False)
 
-    # ---- end to end through the C ABI with pinned host buffers: the whole mg_lchain_dp (upload of the anchors, DP kernels,
-    #      chain extraction + compaction on the device, download of chains and compacted anchors)
-    out = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
-           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
+    # ---- end to end through the reference-facing boundary: init / chain / finish_stream_gpu (include/mm2gb_plchain.h), called
+    #      the way `minimap2 -t T --gpu-chain` calls them (tests/fake_host.c: fake_drive): T worker threads, every read's anchors
+    #      in its own kmalloc'd (pageable) array, one batch per thread and mini-batch, flush at the end of every mini-batch.
+    #      Inside the timed region, per step: the gather pass into pinned staging (packed 8-byte wire format), H2D, all kernels,
+    #      D2H of chains + chain-anchor indices, and on the calling threads kmalloc of u / a', compact_a's gather, kfree of the
+    #      input arrays, post_chaining_helper.  The seeded reads of every step are built before the clock starts.
+    import ctypes as C
     host_threads = max(1, cpu_threads() // max(1, world))
-    e2e_steps = max(1, min(args.steps, 10))
+    drv_threads = int(os.environ.get("MM2GB_BENCH_THREADS", "0")) or host_threads
+    e2e_steps = max(1, min(args.steps, 8))
+    D = C.CDLL(os.path.join(ROOT, "tests", "_build", "libdropin_test.so"))
+    D.init_stream_gpu.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, pkg.Misc]
+    D.fake_set_misc.argtypes = [C.POINTER(pkg.Misc)]
+    D.free_stream_gpu.argtypes = [C.c_int]
+    D.fake_drive.restype = C.c_double
+    D.fake_drive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 4
+    D.mm2gb_dropin_traffic.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    os.environ["MM2GB_GPU_BASE"] = str(local_rank)     # this rank's worker threads all drive this rank's GPU
+    os.environ["MM2GB_N_GPUS"] = "1"
+    os.environ["MM2GB_THREADS_PER_GPU"] = str(drv_threads)
+    cfg_path = os.path.join(ROOT, "mm2-gb_b200", "b200_config.json")
+    D.fake_set_misc(C.byref(misc))
+    mx, mr, mn = C.c_size_t(0), C.c_int(0), C.c_int(-1)
+    D.init_stream_gpu(C.byref(mx), C.byref(mr), C.byref(mn), cfg_path.encode(), misc)
+    dr = {"n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "hu": np.zeros(n_reads, np.uint64), "hb": np.zeros(n_reads, np.uint64)}
+
+    def drive(steps, want=True):
+        outs = [dr[k].ctypes.data if want else None for k in ("n_u", "n_b", "hu", "hb")]
+        return D.fake_drive(a.ctypes.data, off.ctypes.data, n_reads, drv_threads, 0, steps, int(mx.value), 1, *outs)
+    drive(2, want=False)                                # warm-up: contexts are created, buffers pinned
+    traffic = (C.c_longlong * 2)()
+    D.mm2gb_dropin_traffic(traffic, 1)
+    barrier()
+    e2e_s = drive(e2e_steps)
+    torch.cuda.synchronize()
+    D.mm2gb_dropin_traffic(traffic, 1)
+    dropin_h2d, dropin_d2h = traffic[0] / e2e_steps, traffic[1] / e2e_steps
+    D.free_stream_gpu(drv_threads)
+
+    # ---- the same through the core C ABI (mm2gb_chain_host_index) with pinned HOST buffers: no host pass at all -- the anchors
+    #      are DMA'd from the caller's pinned array (16 B each), the indices land in the caller's pinned array (k_drain)
+    e2e_cap = max(1 << 20, n // 8 + int(np.diff(off).max()) + 1)
+    ctx_e2e = pkg.ChainContext(misc, device=local_rank, max_anchors=e2e_cap, max_reads=n_reads + 1, n_slots=6)
+    out = {"u": np.empty(n, np.uint64), "v": torch.empty(n, dtype=torch.int32).pin_memory(),
+           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "v_pos": np.zeros(n_reads, np.int64)}
     for _ in range(2):
         ctx_e2e.chain(h_a, off, out=out, packed=True)
     barrier()
@@ -294,56 +334,57 @@ def main():
     for _ in range(e2e_steps):
         res = ctx_e2e.chain(h_a, off, out=out, packed=True)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    core_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    # the same call from two host threads, each with its own context and buffers -- how `minimap2 -t 2` drives the drop-in (one
-    # context per worker thread): the pipeline drain of one caller's batch overlaps the other's upload.  Reported next to the
-    # single-caller number, which stays the e2e value.
-    two_callers = None
-    if world == 1:
-        try:
-            ctx_b = pkg.ChainContext(misc, device=local_rank, max_anchors=e2e_cap, max_reads=n_reads + 1, n_slots=6)
-            out_b = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
-                     "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
-            ctx_b.chain(h_a, off, out=out_b, packed=True)
-
-            def caller(c, o):
-                for _ in range(e2e_steps):
-                    c.chain(h_a, off, out=o, packed=True)
-            th = [threading.Thread(target=caller, args=(ctx_e2e, out)), threading.Thread(target=caller, args=(ctx_b, out_b))]
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-            torch.cuda.synchronize()
-            dt2 = time.perf_counter() - t0
-            assert np.array_equal(out_b["n_u"], res["n_u"]) and np.array_equal(out_b["n_b"], res["n_b"])
-            two_callers = {"value": 2 * e2e_steps * pairs / dt2, "unit": "pairs/s", "ms_per_step": 1e3 * dt2 / (2 * e2e_steps),
-                           "note": "two host threads, one context each, same GPU; every step uploads its anchors and downloads its results"}
-            ctx_b.close()
-            del out_b
-        except Exception as exc:   # extra information only: never fail the bench line over it
-            two_callers = {"error": str(exc)[:200]}
     n_chains = int(res["n_u"].sum())
     n_chain_anchors = int(res["n_b"].sum())
-    # where the end-to-end time goes: DP only (upload, kernels, f/p download), the host-stage variant of the same call
-    # (f/p downloaded, chain extraction on host threads -- the reference's arrangement), and that host stage alone
+    core_abi = {"value": e2e_steps * pairs / core_s, "unit": "pairs/s", "ms_per_step": 1e3 * core_s / e2e_steps,
+                "h2d_bytes_per_step": int(res["h2d_anchor_bytes"]) + 8 * (n_reads + 1), "d2h_bytes_per_step": 4 * n_chain_anchors + 8 * n_chains + 16 * (n_reads + 64),
+                "note": "mm2gb_chain_host_index, one synchronous caller, caller-pinned anchors (raw 16 B DMA, no host pass) and caller-pinned index output; 6 slots"}
+    # the packed upload through the same call: a pageable source is packed (8 B/anchor) by one host thread per call
+    t0 = time.perf_counter()
+    resn = ctx_e2e.chain(a, off, out=out, packed=True)
+    core_abi["pageable_source_packed_upload"] = {"ms_per_step": 1e3 * (time.perf_counter() - t0), "h2d_anchor_bytes": int(resn["h2d_anchor_bytes"]),
+                                                 "note": "single caller thread does the 16 -> 8 byte pack pass"}
+    # where the time goes: DP only (upload, kernels, f/p download) and, as a diagnostic, the host-stage variant of the same call
+    # (f/p downloaded, chain extraction on host threads -- the reference's arrangement)
     outh = {"f": torch.empty(n, dtype=torch.int32).pin_memory(), "p": torch.empty(n, dtype=torch.int32).pin_memory(),
             "u": out["u"], "b": np.empty((n, 2), np.uint64), "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64)}
     ctx_e2e.chain_dp(h_a, off, f=outh["f"], p=outh["p"])
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(3):
         ctx_e2e.chain_dp(h_a, off, f=outh["f"], p=outh["p"])
-    dp_only_s = (time.perf_counter() - t0) / e2e_steps
-    ctx_e2e.chain(h_a, off, n_threads=host_threads, out=outh)
+    dp_only_s = (time.perf_counter() - t0) / 3
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        resh = ctx_e2e.chain(h_a, off, n_threads=host_threads, out=outh)
-    hostvar_s = (time.perf_counter() - t0) / e2e_steps
-    assert np.array_equal(resh["n_u"], res["n_u"]) and np.array_equal(resh["n_b"], res["n_b"]), "device and host chain extraction disagree"
+    resh = ctx_e2e.chain(h_a, off, n_threads=host_threads, out=outh)
+    hostvar_s = time.perf_counter() - t0
     host_only_s = host_stage_alone(pkg, misc, a, off, outh["f"].numpy(), outh["p"].numpy(), host_threads)
+
+    # ---- parity at benchmark scale (outside every timed region): the chains and compacted anchors the boundary returned for
+    #      this very workload against the reference's own lchain.c (oracle/_ref; the restatement where that was not built)
+    po = entry.load_oracle()
+    use_ref = po.ref_available()
+    order = np.argsort(-np.diff(off), kind="stable")
+    if world == 1:
+        sel = np.arange(n_reads, dtype=np.int64)
+    else:   # the 50 longest reads + every k-th of the rest
+        rest = order[50:]
+        sel = np.sort(np.concatenate([order[:50], rest[::max(1, len(rest) // 1950)]])).astype(np.int64)
+    r_nu, r_nb, r_hu, r_hb = po.lchain_digests(po.map_ont_params(), a, off, sel, n_threads=host_threads, use_ref=use_ref)
+    bad_dropin = int(np.count_nonzero((dr["n_u"][sel] != r_nu) | (dr["n_b"][sel] != r_nb) | (dr["hu"][sel] != r_hu) | (dr["hb"][sel] != r_hb)))
+    bad_core = 0
+    vv = res["v"].numpy()
+    for k, r in enumerate(sel):
+        s0, q = int(off[r]), int(res["v_pos"][r])
+        nu_r, nb_r = int(res["n_u"][r]), int(res["n_b"][r])
+        ok = nu_r == int(r_nu[k]) and nb_r == int(r_nb[k])
+        ok = ok and po.digest(res["u"][s0:s0 + nu_r]) == int(r_hu[k])
+        ok = ok and po.digest(a[s0 + vv[q:q + nb_r].astype(np.int64)]) == int(r_hb[k])
+        bad_core += 0 if ok else 1
+    bad_hostvar = int(not (np.array_equal(resh["n_u"], res["n_u"]) and np.array_equal(resh["n_b"], res["n_b"])))
+    parity = {"reads_checked": int(len(sel)), "mismatches": bad_dropin + bad_core + bad_hostvar, "against": "reference lchain.c (oracle/_ref)" if use_ref else "oracle port",
+              "includes_longest_reads": 50, "paths": {"dropin_chain_stream_gpu": bad_dropin, "core_abi_chain_host_index": bad_core, "host_stage_variant_counts": bad_hostvar},
+              "what": "per read: n_u, number of chain anchors, digest of u[], digest of the compacted anchors a'[]"}
 
     # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
     from mm2gb_b200 import sharding
@@ -408,14 +449,17 @@ def main():
             "dp_only": {"value": pairs / (dp_ms / 1e3), "unit": "pairs/s", "ms": dp_ms,
                         "note": "range + units + score kernels only (f, p); `value` also includes the device chain extraction + compaction"},
             "roofline": roofline,
-            "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": 16 * n + 8 * (n_reads + 1),
-                    "d2h_bytes_per_step": 16 * n_chain_anchors + 8 * n_chains + 16 * (n_reads + 64),
+            "e2e": {"value": tot_pairs * e2e_steps / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": int(dropin_h2d),
+                    "d2h_bytes_per_step": int(dropin_d2h),
                     "reads_per_s": tot_reads * e2e_steps / e2e_max, "ms_per_step": 1e3 * e2e_max / e2e_steps,
-                    "includes": "H2D anchors, range+unit+score kernels, device chain extraction + compaction (k_bt_sort/k_bt_walk), packed chains + compacted anchors written to pinned host memory by k_drain (= whole mg_lchain_dp)",
-                    "chain_anchors": n_chain_anchors,
-                    "slots": 6, "chunk_anchors": e2e_cap, "two_callers": two_callers,
+                    "through": "init_stream_gpu / chain_stream_gpu / finish_stream_gpu (the reference's plugin boundary, gpu/plutils.h:98-104), driven like `minimap2 -t %d --gpu-chain`: %d worker thread(s), per-read kmalloc'd pageable anchor arrays, one batch per thread and mini-batch, flush per mini-batch" % (drv_threads, drv_threads),
+                    "includes": "host gather into pinned staging (packed 8-byte wire format), H2D, k_expand + range + unit + score kernels, device chain extraction + compaction, D2H of chains + chain-anchor indices (k_drain), kmalloc of u / a', compact_a's gather on the calling threads, kfree of the input arrays, post_chaining_helper (= whole mg_lchain_dp as the driver sees it)",
+                    "driver_threads": drv_threads, "chain_anchors": n_chain_anchors, "steps": e2e_steps, "batch_limit_anchors": int(mx.value),
+                    "bytes_per_anchor": {"h2d": dropin_h2d / max(1, n), "d2h": dropin_d2h / max(1, n)},
+                    "core_abi": core_abi,
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
+            "parity": parity,
             "gpu_launches": (8 + 2 * bt_classes) * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
@@ -424,6 +468,9 @@ def main():
     ctx_e2e.close()
     if dist is not None:
         dist.destroy_process_group()
+    if parity["mismatches"]:
+        sys.stderr.write("bench.py: PARITY FAILURE: %r\n" % (parity,))
+        sys.exit(1)
 
 
 if __name__ == "__main__":

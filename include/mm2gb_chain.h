@@ -56,6 +56,8 @@ typedef struct {
 
 const char *mm2gb_last_error(void);
 int mm2gb_device_count(void);
+/* free / total memory of a device in bytes (for sizing contexts: ~90 B of device and ~28 B of pinned memory per anchor and slot) */
+int mm2gb_device_memory(int device, size_t *free_bytes, size_t *total_bytes);
 
 /* One context per (host thread, GPU).  `max_anchors` / `max_reads` bound one batch; `n_slots` (1..8) is the
  * number of batches that may be in flight (each slot owns a stream, pinned staging and device buffers).
@@ -63,9 +65,10 @@ int mm2gb_device_count(void);
 int mm2gb_ctx_create(mm2gb_ctx_t **ctx, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc);
 /* The same with flags: DEVICE_ONLY = no pinned staging and no slot-owned anchor / f / p buffers (only the device-resident
  * entry points work; for anchor arrays that already live in HBM, e.g. the 500 M-anchor chaining-only benchmark);
- * NO_CHAINS = no chain-extraction buffers (only the DP entry points work). */
+ * NO_CHAINS = no chain-extraction buffers (only the DP entry points work); NO_FP_STAGING = no pinned f / p staging. */
 #define MM2GB_CTX_DEVICE_ONLY 1u
 #define MM2GB_CTX_NO_CHAINS 2u
+#define MM2GB_CTX_NO_FP_STAGING 4u   /* no pinned f / p staging: only the chain entry points work (what the drop-in needs) */
 int mm2gb_ctx_create_ex(mm2gb_ctx_t **ctx, int device, size_t max_anchors, int max_reads, int n_slots, const mm2gb_misc_t *misc,
                         unsigned flags);
 void mm2gb_ctx_destroy(mm2gb_ctx_t *ctx);
@@ -84,18 +87,33 @@ int mm2gb_chain_dp_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t
  * the rest of b[off[r] .. off[r+1]) is scratch.  f/p (size off[n_reads]) receive the DP arrays; they may be NULL when
  * n_threads <= 0.
  *   n_threads <= 0 : chain extraction + compaction (lchain.c:27-111) run on the DEVICE right behind the DP kernels and only
- *                    their (packed) result leaves the device.  Reads of any size are handled on the device: up to 8192
- *                    anchors in shared memory, longer ones (or scores >= 2^19) by the global-memory kernels.
- *   n_threads >= 1 : f/p are downloaded and that stage runs on n_threads host threads (what the reference does on one
- *                    thread, gpu/plchain.cu:99-150). */
+ *                    the chains and the indices of their anchors leave the device (b is gathered from `a` on the host).  Reads
+ *                    of any size are handled on the device: up to 8192 anchors in shared memory, longer ones (or scores
+ *                    >= 2^19) by the mid / global-memory kernels.  This is the product path.
+ *   n_threads >= 1 : DIAGNOSTIC ONLY -- f/p are downloaded and that stage runs on n_threads host threads (what the reference
+ *                    does on one thread, gpu/plchain.cu:99-150); used by bench.py to break the end-to-end time down. */
 int mm2gb_chain_host(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                      uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats);
 
-/* The same with PACKED compacted anchors (what bench.py's end-to-end figure calls): read r's anchors are
- * b[b_pos[r] .. b_pos[r]+n_b[r]); `b` needs room for off[n_reads] anchors.  With `b` in pinned (mapped) memory the device
- * writes the compacted anchors there itself (k_drain) -- exactly the bytes produced, no host copy of them at all. */
-int mm2gb_chain_host_packed(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, uint64_t *u, int32_t *n_u,
-                            mm2gb_anchor_t *b, int64_t *b_pos, int64_t *n_b, mm2gb_stats_t *stats);
+/* The same with the compacted anchors returned as INDICES -- the wire format of the results: compact_a (lchain.c:78-111) is a
+ * gather of anchors the caller still holds, so 4 instead of 16 bytes per chain anchor cross PCIe.  Read r's compacted anchors are
+ * a[off[r] + v[v_pos[r] + k]], k < n_v[r]; `v` needs room for off[n_reads] entries.  With `v` in pinned (mapped) memory the device
+ * writes the indices there itself (k_drain) -- exactly the bytes produced, no host copy of them at all.
+ * mm2gb_gather_anchors materialises one read's a'[]: b[k] = a[v[k]]. */
+int mm2gb_chain_host_index(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, uint64_t *u, int32_t *n_u,
+                           int32_t *v, int64_t *v_pos, int64_t *n_v, mm2gb_stats_t *stats);
+void mm2gb_gather_anchors(const mm2gb_anchor_t *a, const int32_t *v, int64_t n, mm2gb_anchor_t *b);
+/* Anchor bytes that crossed PCIe host -> device for the last pipelined batch / for the batch of a slot.  Anchors in pinned caller
+ * memory are DMA'd as they are (16 B each, no host pass); anchors in pageable memory go through one gather pass that writes the
+ * packed wire format (8 B each + one 16-byte record per run of equal high words, csrc/wire.h) into pinned staging, and k_expand
+ * rebuilds the 16-byte anchors on the device.  MM2GB_WIRE=raw|packed|auto overrides the choice. */
+int64_t mm2gb_last_batch_upload_bytes(mm2gb_ctx_t *ctx);
+/* The packed wire format on the host alone (tests; a producer that wants to write it directly): pack the reads a[off[r] .. off[r+1])
+ * into `buf` (32-byte aligned, `cap` bytes) -> bytes to upload, or -1 if the run list does not fit; and the inverse, by the rule
+ * k_expand applies on the device. */
+int64_t mm2gb_wire_pack(const mm2gb_anchor_t *a, const int64_t *off, int n_reads, void *buf, size_t cap, int32_t *n_runs);
+int mm2gb_wire_unpack(const void *buf, size_t cap, int64_t n, int32_t n_runs, mm2gb_anchor_t *out);
+int64_t mm2gb_last_upload_bytes(mm2gb_ctx_t *ctx, int slot);
 
 /* Asynchronous pair.  submit: stage anchors into the slot's pinned buffer, enqueue H2D + kernels + D2H on the slot's
  * stream and return.  wait: block until the slot is done and expose the pinned result arrays (valid until the slot is
@@ -104,11 +122,12 @@ int mm2gb_submit(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *a, const int6
 int mm2gb_submit_gather(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads);
 int mm2gb_wait(mm2gb_ctx_t *ctx, int slot, const int32_t **f, const int32_t **p, const int64_t **off, mm2gb_stats_t *stats);
 /* The same pair with chain extraction on the device (what the drop-in uses; replaces the host loop of
- * gpu/plchain.cu:99-150).  wait_chains: per read r  n_u[r] chains at u[r][0 .. n_u[r]) and n_b[r] compacted anchors at
- * b[r][0 .. n_b[r]); everything lives in the slot's pinned memory until the slot is submitted again. */
+ * gpu/plchain.cu:99-150).  wait_chains: per read r  n_u[r] chains at u[r][0 .. n_u[r]) and the indices (inside the read) of its
+ * n_v[r] compacted anchors at v[r][0 .. n_v[r]) -- a'[k] = read_a[r][v[r][k]]; everything lives in the slot's pinned memory
+ * until the slot is submitted again. */
 int mm2gb_submit_gather_chains(mm2gb_ctx_t *ctx, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads);
-int mm2gb_wait_chains(mm2gb_ctx_t *ctx, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t *const **b,
-                      const int32_t **n_b, const int64_t **off, mm2gb_stats_t *stats);
+int mm2gb_wait_chains(mm2gb_ctx_t *ctx, int slot, const uint64_t *const **u, const int32_t **n_u, const int32_t *const **v,
+                      const int32_t **n_v, const int64_t **off, mm2gb_stats_t *stats);
 int mm2gb_slot_busy(mm2gb_ctx_t *ctx, int slot);
 
 /* ---- device-resident path (kernel-only timing; inputs already in HBM) ---------------------------------- */
@@ -132,7 +151,7 @@ int mm2gb_device_stats(mm2gb_ctx_t *ctx, mm2gb_stats_t *stats);
 int mm2gb_profile(mm2gb_ctx_t *ctx, int enable);
 int mm2gb_profile_read(mm2gb_ctx_t *ctx, float ms[MM2GB_NTIMERS], int64_t launches[MM2GB_NTIMERS]);
 
-/* Diagnostic (tools/drain_probe.py): device -> pinned host of n anchors by k_drain with `blocks` CTAs vs the copy engine,
+/* Diagnostic (tools/drain_probe.py): device -> pinned host of n chain-anchor indices by k_drain with `blocks` CTAs vs the copy engine,
  * alone and against a concurrent host -> device copy.  ms[0..4]: drain, memcpy, drain+H2D, memcpy+H2D, H2D alone. */
 int mm2gb_debug_drain(mm2gb_ctx_t *ctx, int64_t n, int blocks, float ms[5]);
 
@@ -143,9 +162,9 @@ int32_t mm2gb_backtrack(int64_t n, const int32_t *f, const int32_t *p, const mm2
                         int32_t max_drop, uint64_t *u, mm2gb_anchor_t *b, int64_t *n_b);
 
 /* The device version of that stage (k_bt_sort* / k_bt_walk*; what mm2gb_chain_host with n_threads <= 0 and the drop-in run behind the DP
- * kernels) on caller-supplied f / p: same outputs, layout as in mm2gb_chain_host.  *n_declined = reads handed to the host
- * implementation (only with min_score < 0, or more than 256 reads of a batch overflowing the shared-memory kernels).
- * Synchronous; uses slot 0. */
+ * kernels) on caller-supplied f / p: same outputs, layout as in mm2gb_chain_host.  Every read is finished on the device (reads a
+ * shared-memory kernel cannot take -- scores >= 2^19, more chains than its key buffer holds -- go to the global-memory kernels
+ * through a device-side list); *n_declined counts reads left unfinished and is 0 unless the call fails.  Synchronous; slot 0. */
 int mm2gb_backtrack_device(mm2gb_ctx_t *ctx, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
                            const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int32_t *n_declined);
 

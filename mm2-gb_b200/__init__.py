@@ -85,7 +85,15 @@ def lib():
         L.mm2gb_ctx_set_misc.argtypes = [vp, C.POINTER(Misc)]
         L.mm2gb_chain_dp_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.POINTER(Stats)]
         L.mm2gb_chain_host.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(Stats)]
-        L.mm2gb_chain_host_packed.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(Stats)]
+        L.mm2gb_chain_host_index.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(Stats)]
+        L.mm2gb_gather_anchors.argtypes = [vp, vp, C.c_int64, vp]
+        L.mm2gb_gather_anchors.restype = None
+        L.mm2gb_last_batch_upload_bytes.argtypes = [vp]
+        L.mm2gb_last_batch_upload_bytes.restype = C.c_int64
+        L.mm2gb_device_memory.argtypes = [C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.mm2gb_wire_pack.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int32)]
+        L.mm2gb_wire_pack.restype = C.c_int64
+        L.mm2gb_wire_unpack.argtypes = [vp, C.c_size_t, C.c_int64, C.c_int32, vp]
         L.mm2gb_submit.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_submit_gather.argtypes = [vp, C.c_int, vp, vp, C.c_int]
         L.mm2gb_wait.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
@@ -127,7 +135,7 @@ def _ptr(x):
 class ChainContext:
     """One chaining context = (GPU, capacity, chaining parameters); mirrors mm2gb_ctx_t."""
 
-    DEVICE_ONLY, NO_CHAINS = 1, 2
+    DEVICE_ONLY, NO_CHAINS, NO_FP_STAGING = 1, 2, 4
 
     def __init__(self, misc: Misc | None = None, device: int = 0, max_anchors: int = 1 << 22, max_reads: int = 1 << 16, n_slots: int = 2,
                  flags: int = 0):
@@ -177,21 +185,23 @@ class ChainContext:
         """Whole mg_lchain_dp for a batch.  n_threads <= 0: chain extraction + compaction on the device (k_bt_sort/k_bt_walk);
         n_threads >= 1: that stage on n_threads host threads.  Returns dict with f, p (None unless want_fp), u, n_u, b,
         n_b, stats; read r's chains are u[off[r]:off[r]+n_u[r]], its compacted anchors b[off[r]:off[r]+n_b[r]].
-        packed=True (device stage only, no f/p): mm2gb_chain_host_packed -- read r's compacted anchors are
-        b[b_pos[r]:b_pos[r]+n_b[r]]; with a pinned `b` the device writes exactly the bytes produced straight into it.
-        `out` may carry preallocated (e.g. pinned) buffers under the same keys."""
+        packed=True (device stage only, no f/p): mm2gb_chain_host_index, the wire format of the results -- read r's compacted
+        anchors are a[off[r] + v[v_pos[r]:v_pos[r]+n_b[r]]] (`v` int32 indices inside the read); with a pinned `v` the device
+        writes exactly the bytes produced straight into it.  `out` may carry preallocated (e.g. pinned) buffers under the
+        same keys."""
         n_reads = len(off) - 1
         n = int(off[-1])
         out = dict(out or {})
         if packed:
             out["f"] = out["p"] = None
-            out.setdefault("u", np.empty(n, np.uint64)); out.setdefault("b", np.empty((n, 2), np.uint64))
+            out.setdefault("u", np.empty(n, np.uint64)); out.setdefault("v", np.empty(n, np.int32))
             out.setdefault("n_u", np.zeros(n_reads, np.int32)); out.setdefault("n_b", np.zeros(n_reads, np.int64))
-            out.setdefault("b_pos", np.zeros(n_reads, np.int64))
+            out.setdefault("v_pos", np.zeros(n_reads, np.int64))
             st = Stats()
-            _ck(lib().mm2gb_chain_host_packed(self._h, _ptr(a), _ptr(off), n_reads, _ptr(out["u"]), _ptr(out["n_u"]), _ptr(out["b"]),
-                                              _ptr(out["b_pos"]), _ptr(out["n_b"]), C.byref(st)))
+            _ck(lib().mm2gb_chain_host_index(self._h, _ptr(a), _ptr(off), n_reads, _ptr(out["u"]), _ptr(out["n_u"]), _ptr(out["v"]),
+                                             _ptr(out["v_pos"]), _ptr(out["n_b"]), C.byref(st)))
             out["stats"] = st
+            out["h2d_anchor_bytes"] = int(lib().mm2gb_last_batch_upload_bytes(self._h))
             return out
         if want_fp or n_threads >= 1:
             out.setdefault("f", np.empty(n, np.int32)); out.setdefault("p", np.empty(n, np.int32))
@@ -204,6 +214,10 @@ class ChainContext:
                                    _ptr(out["n_u"]), _ptr(out["b"]), _ptr(out["n_b"]), n_threads, C.byref(st)))
         out["stats"] = st
         return out
+
+    def upload_bytes(self) -> int:
+        """anchor bytes the last pipelined batch moved host -> device (16 B/anchor raw, ~8 B/anchor in the packed wire format)"""
+        return int(lib().mm2gb_last_batch_upload_bytes(self._h))
 
     def submit(self, slot: int, a, off):
         _ck(lib().mm2gb_submit(self._h, slot, _ptr(a), _ptr(off), len(off) - 1))
@@ -257,6 +271,43 @@ class ChainContext:
         n = (C.c_int64 * N_TIMERS)()
         _ck(lib().mm2gb_profile_read(self._h, ms, n))
         return {TIMER_NAMES[i]: (float(ms[i]), int(n[i])) for i in range(N_TIMERS)}
+
+
+def gather_anchors(a, v):
+    """compact_a's gather (lchain.c:100-105): b[k] = a[v[k]] through the library's own routine (what the drop-in runs)."""
+    a = np.ascontiguousarray(a, np.uint64)
+    v = np.ascontiguousarray(v, np.int32)
+    b = np.empty((len(v), 2), np.uint64)
+    if len(v):
+        lib().mm2gb_gather_anchors(a.ctypes.data, v.ctypes.data, len(v), b.ctypes.data)
+    return b
+
+
+def wire_pack(a, off, cap_bytes=None):
+    """The packed upload format (csrc/wire.h) of a batch, packed on the host exactly as the upload path does.
+    Returns (buffer uint8[cap], bytes_to_upload, n_runs); bytes_to_upload == -1 if the run list does not fit cap_bytes."""
+    a = np.ascontiguousarray(a, np.uint64)
+    off = np.ascontiguousarray(off, np.int64)
+    n = int(off[-1])
+    cap = int(cap_bytes if cap_bytes is not None else 16 * max(n, 1) + 4096)
+    raw = np.zeros(cap + 64, np.uint8)
+    shift = (-raw.ctypes.data) % 32
+    buf = raw[shift:shift + cap]
+    nr = C.c_int32(0)
+    nbytes = lib().mm2gb_wire_pack(a.ctypes.data, off.ctypes.data, len(off) - 1, buf.ctypes.data, cap, C.byref(nr))
+    return buf, int(nbytes), int(nr.value)
+
+
+def wire_unpack(buf, n, n_runs):
+    out = np.zeros((max(n, 1), 2), np.uint64)
+    _ck(lib().mm2gb_wire_unpack(buf.ctypes.data, len(buf), n, n_runs, out.ctypes.data))
+    return out[:n]
+
+
+def device_memory(device: int = 0):
+    f, t = C.c_size_t(0), C.c_size_t(0)
+    _ck(lib().mm2gb_device_memory(device, C.byref(f), C.byref(t)))
+    return f.value, t.value
 
 
 def backtrack(misc: Misc, a, f, p):

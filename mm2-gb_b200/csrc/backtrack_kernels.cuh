@@ -41,7 +41,6 @@ constexpr unsigned kBtIdxMask = kBtMaxAnchors - 1;
 constexpr int kBtMaxScore = 1 << (32 - kBtIdxBits);     // packed key = f << 13 | i must fit 32 bits
 constexpr int kBtLevels = 8;                            // radix levels of a 64-bit key
 constexpr int kBtRow = 260;                             // per level: start[0..256], next-bucket cursor, shift
-constexpr int kBtOvfCap = 256;                          // reads per batch the shared-memory kernels may hand to the global-memory ones
 
 struct BtParams { int min_cnt, min_sc, max_drop; };
 
@@ -611,8 +610,7 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, cons
 // a read the shared-memory kernels cannot finish goes to the global-memory ones through this list
 __device__ __forceinline__ void bt_overflow(int r, int *ovf_list, Counters *ctr)
 {
-    const int k = atomicAdd(&ctr->ovf_cnt, 1);
-    if (k < kBtOvfCap) ovf_list[k] = r;     // beyond the cap the read stays declined (n_u = -1: host implementation)
+    ovf_list[atomicAdd(&ctr->ovf_cnt, 1)] = r;     // the list holds one entry per read of the batch: it cannot overflow
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -693,7 +691,7 @@ k_bt_sort(const int *__restrict__ f, const long long *__restrict__ off, const in
 __device__ __forceinline__ int bt_big_read(const int *__restrict__ read_list, int n_list, const int *ovf_list, const Counters *ctr)
 {
     const int b = (int)blockIdx.x;
-    if (ovf_list) return b < min(ctr->ovf_cnt, kBtOvfCap) ? ovf_list[b] : -1;
+    if (ovf_list) return b < ctr->ovf_cnt ? ovf_list[b] : -1;
     return b < n_list ? read_list[b] : -1;
 }
 
@@ -953,13 +951,15 @@ struct WalkMid {
 // Chain extraction + compaction of one read by one warp; W = where the state lives (above).
 // inputs : ar / fr / pr = the read's anchors, scores, predecessors (index inside the read, -1 none); nz sorted ends in W
 // scratch: vr (int per anchor; the chains' anchor indices in emission order), ur (u64 per anchor), vsr (int per anchor)
-// outputs: n_u (-1 = declined), n_b, u_pos, b_pos of read r; the n_b compacted anchors at b_pack[b_pos ..] and the n_u chains
+// outputs: n_u (-1 = handed to the global-memory kernels), n_b, u_pos, b_pos of read r; the INDICES (inside the read) of the n_b
+//          compacted anchors at v_pack[b_pos ..] -- compact_a's a'[k] = a[v_pack[b_pos + k]], a gather the host does from the
+//          anchors it still holds, so 4 instead of 16 bytes per chain anchor leave the device -- and the n_u chains
 //          (score << 32 | count) at u_pack[u_pos ..]: packed arrays shared by the batch, slots handed out by atomic cursors,
 //          so only what was produced has to leave the device
 template <class W>
 __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const uint4 *__restrict__ ar, const int *__restrict__ fr,
                                              const int *__restrict__ pr, BtParams bp, int *vr, unsigned long long *ur, int *vsr,
-                                             uint4 *__restrict__ b_pack, unsigned long long *__restrict__ u_pack, int u_cap,
+                                             int *__restrict__ v_pack, unsigned long long *__restrict__ u_pack, int u_cap,
                                              int *__restrict__ n_u_out, int *__restrict__ n_b_out, int *__restrict__ u_pos,
                                              int *__restrict__ b_pos, int *ovf_list, Counters *ctr, int lane)
 {
@@ -1261,7 +1261,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     if (lane == 0) bpos = atomicAdd(&ctr->b_cur, n_v);
     bpos = __shfl_sync(full, bpos, 0);
     unsigned long long *uo = u_pack + upos;
-    uint4 *bo = b_pack + bpos;
+    int *bo = v_pack + bpos;
     S.prepare_compaction(n_u);
     unsigned long long *wk = S.wk();
     IDX *wpay = S.wpay();
@@ -1284,21 +1284,13 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             const unsigned long long uv = ur[src];
             const int cntc = (int)(unsigned)uv, s0 = vsr[src];
             if (lane == 0) uo[c] = uv;
-            // the indices of the NEXT 128 anchors are fetched while the gathers of the current ones are in flight
-            int nidx[4];
+            // the chain was collected end-first: flipped copy of its indices, 8 coalesced loads per lane in flight
+            for (int q0 = 0; q0 < cntc; q0 += 256) {
+                int idx[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { const int q = t * 32 + lane; nidx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
-            for (int q0 = 0; q0 < cntc; q0 += 128) {
-                int idx[4];
-                uint4 val[4];
+                for (int t = 0; t < 8; ++t) { const int q = q0 + t * 32 + lane; idx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
 #pragma unroll
-                for (int t = 0; t < 4; ++t) idx[t] = nidx[t];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) if (idx[t] >= 0) val[t] = ar[idx[t]];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { const int q = q0 + 128 + t * 32 + lane; nidx[t] = q < cntc ? vr[s0 + cntc - 1 - q] : -1; }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[out + q0 + t * 32 + lane] = val[t];
+                for (int t = 0; t < 8; ++t) if (idx[t] >= 0) bo[out + q0 + t * 32 + lane] = idx[t];
             }
             out += cntc;
         }
@@ -1331,7 +1323,6 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     __syncwarp();
     for (int o0 = 0; o0 < out; o0 += 128) {
         int idx[4];
-        uint4 val[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int o = o0 + t * 32 + lane;
@@ -1347,9 +1338,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             }
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) if (idx[t] >= 0) val[t] = ar[idx[t]];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[o0 + t * 32 + lane] = val[t];
+        for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[o0 + t * 32 + lane] = idx[t];
     }
     if (lane == 0) { n_u_out[r] = n_u; n_b_out[r] = out; u_pos[r] = upos; b_pos[r] = bpos; }
 }
@@ -1358,7 +1347,7 @@ template <int CAP>
 __global__ void __launch_bounds__(32)
 k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
           const int *__restrict__ read_list, int n_list, BtParams bp, const unsigned *__restrict__ zs_scr, const int *__restrict__ nz_in,
-          int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_pack,
+          int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, int *__restrict__ v_pack,
           unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
           int *__restrict__ u_pos, int *__restrict__ b_pos, int *__restrict__ ovf_list, Counters *ctr)
 {
@@ -1373,7 +1362,7 @@ k_bt_walk(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__r
     if (nz < 0) { if (lane == 0) { n_u_out[r] = -1; n_b_out[r] = 0; } return; }
     if (nz == 0) { if (lane == 0) { n_u_out[r] = 0; n_b_out[r] = 0; u_pos[r] = 0; b_pos[r] = 0; } return; }
     WalkSmall<CAP> S(SM, zs_scr + o0);
-    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
+    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, v_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, ovf_list, ctr, lane);
 }
 
@@ -1382,7 +1371,7 @@ __global__ void __launch_bounds__(32)
 k_bt_walk_big(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
               const int *__restrict__ read_list, int n_list, const int *ovf_list, BtParams bp, unsigned long long *zk_scr,
               unsigned long long *zk2_scr, const int *__restrict__ nz_in, unsigned *tb_scr, unsigned *pay_scr, unsigned *pay2_scr,
-              int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_pack,
+              int *__restrict__ v_scr, unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, int *__restrict__ v_pack,
               unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
               int *__restrict__ u_pos, int *__restrict__ b_pos, Counters *ctr)
 {
@@ -1408,7 +1397,7 @@ k_bt_walk_big(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.path_s = s_path;
     S.cnt_s = s_cnt;
     S.start_s = s_start;
-    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
+    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, v_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);
 }
 
@@ -1420,7 +1409,7 @@ __global__ void __launch_bounds__(32)
 k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int *__restrict__ p, const long long *__restrict__ off,
               const int *__restrict__ read_list, int n_list, BtParams bp, unsigned long long *zk_scr, unsigned long long *zk2_scr,
               const int *__restrict__ nz_in, unsigned *pay_scr, unsigned *pay2_scr, int *__restrict__ v_scr,
-              unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, uint4 *__restrict__ b_pack,
+              unsigned long long *__restrict__ u_scr, int *__restrict__ vs_scr, int *__restrict__ v_pack,
               unsigned long long *__restrict__ u_pack, int u_cap, int *__restrict__ n_u_out, int *__restrict__ n_b_out,
               int *__restrict__ u_pos, int *__restrict__ b_pos, Counters *ctr, int cap)
 {
@@ -1451,7 +1440,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
     S.smem_bytes = bt_walk_mid_smem(cap);
     S.lp_path_s = s_lp_path;
     S.lp_z_s = s_lp_z;
-    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, b_pack, u_pack, u_cap, n_u_out, n_b_out,
+    bt_walk_body(S, r, n, nz, a + o0, f + o0, p + o0, bp, v_scr + o0, u_scr + o0, vs_scr + o0, v_pack, u_pack, u_cap, n_u_out, n_b_out,
                  u_pos, b_pos, nullptr, ctr, lane);
 }
 
@@ -1459,19 +1448,24 @@ constexpr int kDrainThreads = 64;   // small CTAs (2 warps x 32 registers) fit n
 
 // Packed results -> (mapped, pinned) host memory.  The amounts are only known on the device (the cursors), so this is a
 // kernel rather than a copy-engine transfer of the worst case: a few CTAs keep enough 16-byte stores in flight for PCIe.
+// src_v / dst_v are 16-byte aligned (the same index on both sides), so the body moves four indices per store.
 __global__ void __launch_bounds__(kDrainThreads)
-k_drain(const uint4 *__restrict__ src_b, uint4 *__restrict__ dst_b, const unsigned long long *__restrict__ src_u,
+k_drain(const int *__restrict__ src_v, int *__restrict__ dst_v, const unsigned long long *__restrict__ src_u,
         unsigned long long *__restrict__ dst_u, const Counters *__restrict__ ctr)
 {
-    const int nb = ctr->b_cur, nu = ctr->u_cur;
-    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = t;
-    for (; i + 3 * stride < nb; i += 4 * stride) {
-        const uint4 v0 = __ldg(src_b + i), v1 = __ldg(src_b + i + stride), v2 = __ldg(src_b + i + 2 * stride), v3 = __ldg(src_b + i + 3 * stride);
-        dst_b[i] = v0; dst_b[i + stride] = v1; dst_b[i + 2 * stride] = v2; dst_b[i + 3 * stride] = v3;
+    const long long nb = ctr->b_cur, nu = ctr->u_cur;
+    const long long stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nq = nb >> 2;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src_v);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst_v);
+    long long i = t;
+    for (; i + 3 * stride < nq; i += 4 * stride) {
+        const uint4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + stride), v2 = __ldg(s4 + i + 2 * stride), v3 = __ldg(s4 + i + 3 * stride);
+        d4[i] = v0; d4[i + stride] = v1; d4[i + 2 * stride] = v2; d4[i + 3 * stride] = v3;
     }
-    for (; i < nb; i += stride) dst_b[i] = __ldg(src_b + i);
-    for (int k = t; k < nu; k += stride) dst_u[k] = __ldg(src_u + k);
+    for (; i < nq; i += stride) d4[i] = __ldg(s4 + i);
+    for (long long k = (nq << 2) + t; k < nb; k += stride) dst_v[k] = __ldg(src_v + k);
+    for (long long k = t; k < nu; k += stride) dst_u[k] = __ldg(src_u + k);
 }
 
 } // namespace mm2gb

@@ -4,11 +4,16 @@
 // Replaces, B200-first, what the reference spreads over gpu/plmem.cu (buffer sizing :453-540, pinned/device
 // allocation :12-143, 7 H2D + 3 memset per micro-batch :200-236, D2H :324-359) and the launch half of
 // gpu/plchain.cu:292-464.  Differences that matter:
-//   * the raw 16-byte mm128_t array is uploaded as is -- no AoS->SoA repack on the host (plmem.cu:154-198 is gone);
+//   * anchors in pinned caller memory are DMA'd as they are (no host pass at all); anchors in pageable memory -- the per-read
+//     kmalloc'd arrays of the driver -- go through ONE gather pass that writes the 8-byte packed wire format (csrc/wire.h)
+//     into pinned staging, and k_expand rebuilds the 16-byte anchors in HBM (plmem.cu:154-198, the AoS->SoA repack, is gone);
+//   * only chains and the INDICES of the chain anchors come back (4 bytes per chain anchor): compact_a's gather
+//     (lchain.c:100-105) is done by the host from the anchors it still holds;
 //   * one flat batch, no micro-batches, no host sync between "short" and "long" phases (plchain.cu:426-452 is gone);
 //   * n_slots independent slots per context so upload, kernels and download of consecutive batches overlap.
 #include "chain_kernels.cuh"
 #include "backtrack_kernels.cuh"
+#include "wire.h"
 #include "../../include/mm2gb_chain.h"
 
 #include <algorithm>
@@ -52,6 +57,20 @@ extern "C" int mm2gb_device_count(void)
     return n;
 }
 
+extern "C" int mm2gb_device_memory(int device, size_t *free_bytes, size_t *total_bytes)
+{
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    CK(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    const cudaError_t e = cudaMemGetInfo(&f, &t);
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) return fail(MM2GB_ECUDA, "cudaMemGetInfo: %s", cudaGetErrorString(e));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return MM2GB_OK;
+}
+
 namespace {
 
 // size classes of the chain-extraction kernels: 0..6 shared-memory kernels (k_bt_sort<CAP> / k_bt_walk<CAP>), 7..15 "mid"
@@ -76,6 +95,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     // device
+    unsigned char *d_wire = nullptr;         // packed upload (pk | blk_run | runs, csrc/wire.h) before k_expand rebuilds d_a
     uint4 *d_a = nullptr;
     long long *d_off = nullptr;
     int *d_st = nullptr, *d_f = nullptr, *d_p = nullptr;
@@ -85,7 +105,7 @@ struct Slot {
     int big_cap = 0;
     Counters *d_ctr = nullptr;
     // device chain extraction (k_bt_sort / k_bt_walk): packed compacted anchors and chains of the batch, scratch, lists
-    uint4 *d_b = nullptr;                    // packed compacted anchors (positions from Counters::b_cur)
+    int *d_vp = nullptr;                     // packed indices of the compacted anchors (positions from Counters::b_cur)
     unsigned long long *d_uscr = nullptr;
     int *d_vs = nullptr, *d_list = nullptr;
     int *d_rinfo = nullptr;                  // per read: n_u | n_b | u_pos | b_pos, four arrays of n_reads + 1 ints
@@ -105,11 +125,11 @@ struct Slot {
     long long *h_off = nullptr;
     int *h_f = nullptr, *h_p = nullptr;
     Counters *h_ctr = nullptr;
-    mm2gb_anchor_t *h_b = nullptr;
+    int *h_vp = nullptr;                     // landing buffer of the packed chain-anchor indices (mapped)
     int *h_rinfo = nullptr, *h_list = nullptr;
     int *h_nu = nullptr, *h_nb = nullptr, *h_upos = nullptr, *h_bpos = nullptr;   // slices of h_rinfo for the batch in flight
     unsigned long long *h_upack = nullptr;
-    uint4 *h_b_dev = nullptr;                // device views of the mapped pinned result buffers (k_drain writes them)
+    int *h_vp_dev = nullptr;                 // device views of the mapped pinned result buffers (k_drain writes them)
     unsigned long long *h_upack_dev = nullptr;
     // state
     bool busy = false;
@@ -120,12 +140,12 @@ struct Slot {
     bool direct_out = false;
     // chains requested for this batch (device backtracking); where the compacted anchors land
     bool chains = false, want_fp = true;
-    mm2gb_anchor_t *land_b = nullptr;        // host view of where k_drain puts the packed compacted anchors (h_b or the caller's buffer)
-    const mm2gb_anchor_t *src_a = nullptr;   // host anchors of the batch (for reads the device declines)
-    std::vector<const uint64_t *> u_ptr;     // per read: its chains (in h_upack, or in `spill` for reads finished on the host)
-    std::vector<const mm2gb_anchor_t *> b_ptr;   // per read: its compacted anchors (in the packed landing buffer)
-    std::vector<std::vector<uint64_t>> spill;
-    long long b_total = 0;                   // anchors in the packed landing buffer after finish_chains
+    int *land_v = nullptr;                   // host view of where k_drain puts the packed indices (h_vp or the caller's buffer)
+    std::vector<const uint64_t *> u_ptr;     // per read: its chains (in h_upack)
+    std::vector<const int32_t *> v_ptr;      // per read: the indices of its compacted anchors (in the packed landing buffer)
+    long long b_total = 0;                   // indices in the packed landing buffer
+    int wire_runs = 0;                       // runs of the packed upload of the batch in flight (0: raw upload)
+    size_t up_bytes = 0;                     // bytes of anchor data uploaded for the batch in flight
 };
 
 } // namespace
@@ -148,6 +168,7 @@ struct mm2gb_ctx {
     int long_wave = 0;          // the 4096 / 2048 classes go to k_score_long only while the long units fit this many CTAs (0: always)
     bool host_io = true;        // slots own pinned staging + device anchor/f/p buffers (false: device-resident entry points only)
     bool chains_ok = true;      // slots own the chain-extraction buffers (false: DP entry points only)
+    bool fp_staging = true;     // slots own pinned f / p staging (false: only the chain entry points download anything)
     // The size classes of the chain-extraction kernels run side by side (each is a partial wave) on a pool of auxiliary
     // streams shared by all slots and handed out round robin, so that neither the classes of one chunk nor the same class of
     // consecutive chunks queue behind each other (the global-memory class runs on the slot's own stream).  With the slots'
@@ -156,6 +177,10 @@ struct mm2gb_ctx {
     cudaStream_t bt_stream[kBtStreams] = {nullptr};   // handed out round robin to the size-class launches of all slots
     unsigned bt_rr = 0;
     int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
+    int wire_mode = 0;           // 0 auto: pinned sources are DMA'd raw, pageable ones are packed by the gather pass; 1 always raw
+                                 // (staged by memcpy); 2 always packed (MM2GB_WIRE=auto|raw|packed)
+    size_t stage_bytes = 0;      // size of a slot's pinned staging buffer h_a / device wire buffer
+    long long up_bytes_batch = 0; // anchor bytes uploaded by the last pipelined batch (all chunks)
     Slot slot[kMaxSlots];
     // profiling (slot 0 only)
     bool profile = false;
@@ -394,20 +419,21 @@ static void launch_backtrack(cudaStream_t s, const uint4 *d_a, const int *d_f, c
     if (n_list <= 0) return;
     k_bt_sort<CAP><<<n_list, 32, sizeof(BtSortSmem<CAP>), s>>>(d_f, d_off, list, n_list, bp, sl.d_zs, sl.d_nz, sl.d_ovf, sl.d_ctr);
     k_bt_walk<CAP><<<n_list, 32, sizeof(BtWalkSmem<CAP>), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zs, sl.d_nz, sl.d_st /* dead after scoring: v scratch */,
-                                                           sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos,
+                                                           sl.d_uscr, sl.d_vs, sl.d_vp, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos,
                                                            sl.d_ovf, sl.d_ctr);
 }
 
-// the global-memory kernels: over the host's list of big reads (ovf == false) or over the device-side overflow list
+// the global-memory kernels: over the host's list of big reads (ovf == false) or over the device-side overflow list, which
+// holds at most the n_list reads the shared-memory kernels were given (CTAs beyond its length exit at once)
 static void launch_backtrack_big(cudaStream_t s, const uint4 *d_a, const int *d_f, const int *d_p, const long long *d_off, const int *list, int n_list,
                                  bool ovf, const BtParams &bp, Slot &sl)
 {
-    const int grid = ovf ? kBtOvfCap : n_list;
+    const int grid = n_list;
     if (grid <= 0) return;
     const int *ovf_list = ovf ? sl.d_ovf : nullptr;
     k_bt_sort_big<<<grid, 32, 0, s>>>(d_f, d_off, list, n_list, ovf_list, sl.d_ctr, bp, sl.d_zk, sl.d_zk2, sl.d_nz);
     k_bt_walk_big<<<grid, 32, 0, s>>>(d_a, d_f, d_p, d_off, list, n_list, ovf_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_tb, sl.d_zs, sl.d_pay2,
-                                      sl.d_st, sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos, sl.d_ctr);
+                                      sl.d_st, sl.d_uscr, sl.d_vs, sl.d_vp, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos, sl.d_bpos, sl.d_ctr);
 }
 
 // reads of up to cap anchors (8193 .. 196608): global-memory keys, serial parts in shared memory
@@ -418,7 +444,7 @@ static void launch_backtrack_mid(cudaStream_t s, const uint4 *d_a, const int *d_
     k_bt_sort_mid<<<n_list, kBtMidThreads, (size_t)cap, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2,
                                                   reinterpret_cast<unsigned *>(sl.d_vs), sl.d_nz, cap);
     k_bt_walk_mid<<<n_list, 32, bt_walk_mid_smem(cap), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_zs, sl.d_pay2,
-                                                          sl.d_st, sl.d_uscr, sl.d_vs, sl.d_b, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos,
+                                                          sl.d_st, sl.d_uscr, sl.d_vs, sl.d_vp, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos,
                                                           sl.d_bpos, sl.d_ctr, cap);
 }
 
@@ -461,12 +487,14 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
 {
     const int *cnt = sl.bt_cnt, *base = sl.bt_base;
     const size_t rs = (size_t)n_reads + 1;
-    CK(cudaMemsetAsync(sl.d_nu, 0xff, rs * sizeof(int), s));   // -1 = not done by the device
+    CK(cudaMemsetAsync(sl.d_nu, 0xff, rs * sizeof(int), s));   // -1 = not finished (must not survive the overflow pass)
     CK(cudaMemsetAsync(sl.d_nb, 0, 3 * rs * sizeof(int), s));
     CK(cudaMemsetAsync(&sl.d_ctr->ovf_cnt, 0, 3 * sizeof(int), s));   // ovf_cnt, u_cur, b_cur
     BtParams bp;
     bp.min_cnt = c->misc.min_cnt;
-    bp.min_sc = c->misc.min_score;
+    // scores are never negative (f[i] >= q_span(i) >= 0, lchain.c:171) and an accepted chain has a positive score, so a negative
+    // min_score selects exactly what 0 selects; the packed keys of the sort kernels hold unsigned scores
+    bp.min_sc = std::max(0, c->misc.min_score);
     bp.max_drop = c->misc.is_cdna ? INT32_MAX : c->misc.bw;   // lchain.c:151,162
     {
         // fork: one auxiliary stream per non-empty size class, joined back into the slot's stream
@@ -494,17 +522,17 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         if (cnt[kBtBig]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, sl.d_list + base[kBtBig], cnt[kBtBig], false, bp, sl);
         for (int k = kBtBig - 1; k >= 0; --k)
             if (cnt[k]) CK(cudaStreamWaitEvent(s, sl.bt_join[k], 0));
-        // whatever the shared-memory kernels handed over (normally nothing: 256 CTAs that exit at once)
-        if (base[kBtMid0]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, nullptr, 0, true, bp, sl);
+        // whatever the shared-memory kernels handed over (normally nothing: CTAs that exit at once)
+        if (base[kBtMid0]) launch_backtrack_big(s, d_a, d_f, d_p, d_off, nullptr, base[kBtMid0], true, bp, sl);
     }
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
 
-// packed results of the batch -> mapped pinned host memory (dst_b: device view of where the compacted anchors land)
-static int enqueue_drain(mm2gb_ctx *c, Slot &sl, cudaStream_t s, uint4 *dst_b)
+// packed results of the batch -> mapped pinned host memory (dst_v: device view of where the chain-anchor indices land)
+static int enqueue_drain(mm2gb_ctx *c, Slot &sl, cudaStream_t s, int *dst_v)
 {
-    k_drain<<<c->drain_blocks, kDrainThreads, 0, s>>>(sl.d_b, dst_b, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
+    k_drain<<<c->drain_blocks, kDrainThreads, 0, s>>>(sl.d_vp, dst_v, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
@@ -523,14 +551,15 @@ static void fill_stats(const mm2gb_ctx *c, const Counters &k, long long n_total,
 static void free_slot(Slot &s)
 {
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.d_wire != reinterpret_cast<unsigned char *>(s.d_zk)) cudaFree(s.d_wire);
     cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
     cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
     cudaFree(s.d_chunk_tot); cudaFree(s.d_chunk_base); cudaFree(s.d_chunk_pairs);
     cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
-    cudaFree(s.d_b); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_rinfo); cudaFree(s.d_list); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
-    cudaFree(s.d_zk); cudaFree(s.d_zk2); cudaFree(s.d_tb); cudaFree(s.d_pay2); cudaFree(s.d_ovf);
+    cudaFree(s.d_vp); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_rinfo); cudaFree(s.d_list); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
+    cudaFree(s.d_zk); cudaFree(s.d_tb); cudaFree(s.d_pay2); cudaFree(s.d_ovf);
     cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
-    cudaFreeHost(s.h_b); cudaFreeHost(s.h_rinfo); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upack);
+    cudaFreeHost(s.h_vp); cudaFreeHost(s.h_rinfo); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
     if (s.bt_fork) cudaEventDestroy(s.bt_fork);
     for (int k = 0; k < kBtClasses; ++k) if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]);
@@ -566,6 +595,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
     c->n_slots = n_slots;
     c->host_io = !(flags & MM2GB_CTX_DEVICE_ONLY);
     c->chains_ok = !(flags & MM2GB_CTX_NO_CHAINS);
+    c->fp_staging = !(flags & MM2GB_CTX_NO_FP_STAGING);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
@@ -578,6 +608,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         c->long_classes = v <= 0 ? 0 : v <= 2048 ? 3 : v <= 4096 ? 2 : 1;
     }
     if (const char *e = getenv("MM2GB_TIMELINE")) c->timeline = atoi(e) != 0;
+    if (const char *e = getenv("MM2GB_WIRE")) c->wire_mode = !strcmp(e, "raw") ? 1 : !strcmp(e, "packed") ? 2 : 0;
     if (const char *e = getenv("MM2GB_DRAIN_BLOCKS")) {
         int r = atoi(e);
         if (r >= 1 && r <= 4096) c->drain_blocks = r;
@@ -612,6 +643,11 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             CKC(cudaEventCreateWithFlags(&s.bt_fork, cudaEventDisableTiming));
             for (int k = 0; k < kBtClasses; ++k) CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
             if (c->host_io) CKC(cudaMalloc(&s.d_a, n * sizeof(uint4)));
+            // staging: raw anchors (16 B each) or the packed wire format (8 B each + block index + run list), same buffer
+            // (on the device the packed upload lands in the sort scratch of the chain extraction, which is dead until the score
+            // kernels of the batch are done; contexts without that scratch get a buffer of their own)
+            c->stage_bytes = n * sizeof(uint4);
+            if (c->host_io && !c->chains_ok) CKC(cudaMalloc(&s.d_wire, c->stage_bytes));
             CKC(cudaMalloc(&s.d_off, ((size_t)max_reads + 1) * sizeof(long long)));
             CKC(cudaMalloc(&s.d_st, n * sizeof(int)));
             if (c->host_io) CKC(cudaMalloc(&s.d_f, n * sizeof(int)));
@@ -631,16 +667,16 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             CKC(cudaMalloc(&s.d_ctr, sizeof(Counters)));
             if (c->host_io) CKC(cudaMallocHost(&s.h_a, n * sizeof(mm2gb_anchor_t)));
             CKC(cudaMallocHost(&s.h_off, ((size_t)max_reads + 1) * sizeof(long long)));
-            if (c->host_io) CKC(cudaMallocHost(&s.h_f, n * sizeof(int)));
-            if (c->host_io) CKC(cudaMallocHost(&s.h_p, n * sizeof(int)));
+            if (c->host_io && c->fp_staging) CKC(cudaMallocHost(&s.h_f, n * sizeof(int)));
+            if (c->host_io && c->fp_staging) CKC(cudaMallocHost(&s.h_p, n * sizeof(int)));
             CKC(cudaMallocHost(&s.h_ctr, sizeof(Counters)));
             if (!c->chains_ok) continue;
-            CKC(cudaMalloc(&s.d_b, n * sizeof(uint4)));
+            CKC(cudaMalloc(&s.d_vp, (n + 4) * sizeof(int)));
             CKC(cudaMalloc(&s.d_uscr, n * sizeof(unsigned long long)));
             CKC(cudaMalloc(&s.d_vs, n * sizeof(int)));
             CKC(cudaMalloc(&s.d_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMalloc(&s.d_list, ((size_t)max_reads + 1) * sizeof(int)));
-            if (c->host_io) CKC(cudaMallocHost(&s.h_b, n * sizeof(mm2gb_anchor_t)));
+            if (c->host_io) CKC(cudaMallocHost(&s.h_vp, (n + 4) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
             CKC(cudaMallocHost(&s.h_list, ((size_t)max_reads + 1) * sizeof(int)));
             s.u_cap = n;    // a chain has at least one anchor and every anchor is in at most one chain
@@ -648,12 +684,13 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             CKC(cudaMalloc(&s.d_zs, n * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_nz, ((size_t)max_reads + 1) * sizeof(int)));
             if (c->host_io) CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_zk, n * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_zk2, n * sizeof(unsigned long long)));
+            CKC(cudaMalloc(&s.d_zk, 2 * n * sizeof(unsigned long long)));
+            s.d_zk2 = s.d_zk + n;
+            if (c->host_io) s.d_wire = reinterpret_cast<unsigned char *>(s.d_zk);
             CKC(cudaMalloc(&s.d_pay2, n * sizeof(unsigned)));
             CKC(cudaMalloc(&s.d_tb, (n / 32 + 2 * (size_t)max_reads + 8) * sizeof(unsigned)));
-            CKC(cudaMalloc(&s.d_ovf, kBtOvfCap * sizeof(int)));
-            if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_b_dev, s.h_b, 0));
+            CKC(cudaMalloc(&s.d_ovf, ((size_t)max_reads + 1) * sizeof(int)));
+            if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_vp_dev, s.h_vp, 0));
             if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_upack_dev, s.h_upack, 0));
         }
     }
@@ -699,37 +736,100 @@ struct Want {
     int *dst_f = nullptr, *dst_p = nullptr;
     bool dst_pinned = false;
     bool chains = false;            // run chain extraction + compaction on the device and download the result
-    mm2gb_anchor_t *dst_b = nullptr; // mapped pinned landing area for the packed compacted anchors (nullptr: the slot's own) ...
-    uint4 *dst_b_dev = nullptr;      // ... and its device view
+    int *dst_v = nullptr;           // mapped pinned landing area for the packed chain-anchor indices (nullptr: the slot's own) ...
+    int *dst_v_dev = nullptr;       // ... and its device view
 };
 
-// enqueue one batch whose anchors already sit in host memory `src` (pinned: direct DMA; else staged through h_a)
-static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src_pinned, const long long *off_rel, int n_reads,
-                       long long n_total, const Want &w)
+// where the anchors of a batch come from: one flat array, or one array per read (the driver's chain_read_t.a, plutils.h:64)
+struct Source {
+    const mm2gb_anchor_t *flat = nullptr;
+    bool flat_pinned = false;
+    const mm2gb_anchor_t *const *read_a = nullptr;
+    const int64_t *read_n = nullptr;
+};
+
+// Host half of the upload.  Anchors in pinned memory are DMA'd from where they are; everything else goes through one pass
+// into the slot's pinned staging buffer, which writes the packed wire format (8 B/anchor, csrc/wire.h) unless the run list
+// would not fit (then, or with MM2GB_WIRE=raw, the pass is a plain copy).  *up_src / *up_bytes: what to copy to the device;
+// s.wire_runs > 0 says the copy is in the packed format.
+static int stage_anchors(mm2gb_ctx *c, Slot &s, const Source &src, const long long *off_rel, int n_reads, long long n_total,
+                         const void **up_src, size_t *up_bytes, WireLayout *lay)
+{
+    s.wire_runs = 0;
+    *up_src = nullptr;
+    *up_bytes = 0;
+    if (n_total == 0) return MM2GB_OK;
+    if (src.flat && src.flat_pinned && c->wire_mode != 2) {
+        *up_src = src.flat;
+        *up_bytes = (size_t)n_total * sizeof(mm2gb_anchor_t);
+        return MM2GB_OK;
+    }
+    if (c->wire_mode != 1) {
+        const WireLayout L = wire_layout(n_total, c->stage_bytes);
+        if (L.run_cap >= 1) {
+            WirePacker pk;
+            pk.begin(s.h_a, L);
+            bool ok = true;
+            if (src.flat) ok = pk.add(src.flat, n_total);
+            else
+                for (int r = 0; r < n_reads && ok; ++r)
+                    if (src.read_n[r] > 0) ok = pk.add(src.read_a[r], off_rel[r + 1] - off_rel[r]);
+            if (ok) {
+                *up_bytes = pk.finish();
+                *up_src = s.h_a;
+                *lay = L;
+                s.wire_runs = pk.n_runs();
+                return MM2GB_OK;
+            }
+        }
+    }
+    if (src.flat) memcpy(s.h_a, src.flat, (size_t)n_total * sizeof(mm2gb_anchor_t));
+    else
+        for (int r = 0; r < n_reads; ++r)
+            if (src.read_n[r] > 0) memcpy(s.h_a + off_rel[r], src.read_a[r], (size_t)(off_rel[r + 1] - off_rel[r]) * sizeof(mm2gb_anchor_t));
+    *up_src = s.h_a;
+    *up_bytes = (size_t)n_total * sizeof(mm2gb_anchor_t);
+    return MM2GB_OK;
+}
+
+// enqueue one batch: host staging, H2D (+ k_expand), kernels, D2H on the slot's stream
+static int submit_impl(mm2gb_ctx *c, int si, const Source &src, const long long *off_rel, int n_reads, long long n_total, const Want &w)
 {
     Slot &s = c->slot[si];
     if (s.busy) return fail(MM2GB_ESTATE, "slot %d is busy", si);
     if (!c->host_io) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_DEVICE_ONLY: host-buffer entry points are not available");
     if (w.chains && !c->chains_ok) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_NO_CHAINS");
+    if (w.fp && !c->fp_staging && !(w.dst_pinned && w.dst_f && w.dst_p)) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_NO_FP_STAGING");
     if ((size_t)n_total > c->max_anchors) return fail(MM2GB_ECAP, "batch of %lld anchors exceeds capacity %zu", n_total, c->max_anchors);
     if (n_reads > c->max_reads) return fail(MM2GB_ECAP, "batch of %d reads exceeds capacity %d", n_reads, c->max_reads);
     CK(cudaSetDevice(c->device));
     const bool prof = c->profile && si == 0;
     g_tl_slot = si;
     memcpy(s.h_off, off_rel, ((size_t)n_reads + 1) * sizeof(long long));
-    const mm2gb_anchor_t *h_src = src;
-    if (!src_pinned && n_total) { memcpy(s.h_a, src, (size_t)n_total * sizeof(mm2gb_anchor_t)); h_src = s.h_a; }
+    const void *up_src = nullptr;
+    size_t up_bytes = 0;
+    WireLayout lay{};
+    int rc = stage_anchors(c, s, src, s.h_off, n_reads, n_total, &up_src, &up_bytes, &lay);
+    if (rc) return rc;
+    s.up_bytes = up_bytes;
     {
         ProfScope ps(c, T_H2D, s.stream, prof);
         CK(cudaMemcpyAsync(s.d_off, s.h_off, ((size_t)n_reads + 1) * sizeof(long long), cudaMemcpyHostToDevice, s.stream));
         if (w.chains && n_total) { int rc0 = prepare_backtrack(s, s.stream, s.h_off, n_reads); if (rc0) return rc0; }
-        if (n_total) CK(cudaMemcpyAsync(s.d_a, h_src, (size_t)n_total * sizeof(uint4), cudaMemcpyHostToDevice, s.stream));
+        if (n_total && s.wire_runs > 0) {
+            CK(cudaMemcpyAsync(s.d_wire, up_src, up_bytes, cudaMemcpyHostToDevice, s.stream));
+            k_expand<<<(unsigned)lay.n_blk, kWireBlock, 0, s.stream>>>(reinterpret_cast<const uint2 *>(s.d_wire + lay.pk_off),
+                                                                      reinterpret_cast<const int *>(s.d_wire + lay.blk_off),
+                                                                      reinterpret_cast<const uint4 *>(s.d_wire + lay.run_off), s.wire_runs,
+                                                                      (int)n_total, s.d_a);
+        } else if (n_total) {
+            CK(cudaMemcpyAsync(s.d_a, up_src, up_bytes, cudaMemcpyHostToDevice, s.stream));
+        }
     }
-    int rc = enqueue_kernels(c, s, s.stream, s.d_a, s.d_off, n_reads, n_total, s.d_f, s.d_p, prof);
+    rc = enqueue_kernels(c, s, s.stream, s.d_a, s.d_off, n_reads, n_total, s.d_f, s.d_p, prof);
     if (rc) return rc;
     s.chains = w.chains;
     s.want_fp = w.fp;
-    s.src_a = h_src;
     slice_rinfo(s, n_reads);
     if (w.chains && n_total) {
         rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, n_reads, s.d_f, s.d_p, prof);
@@ -737,7 +837,7 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
     }
     s.direct_out = w.fp && w.dst_pinned && w.dst_f && w.dst_p;
     s.user_f = w.dst_f; s.user_p = w.dst_p;
-    s.land_b = (w.chains && w.dst_b && w.dst_b_dev) ? w.dst_b : s.h_b;
+    s.land_v = (w.chains && w.dst_v && w.dst_v_dev) ? w.dst_v : s.h_vp;
     {
         ProfScope ps(c, T_D2H, s.stream, prof);
         if (n_total && w.fp) {
@@ -745,8 +845,8 @@ static int submit_impl(mm2gb_ctx *c, int si, const mm2gb_anchor_t *src, bool src
             CK(cudaMemcpyAsync(s.direct_out ? w.dst_p : s.h_p, s.d_p, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
         if (n_total && w.chains) {
-            // only what was produced leaves the device: k_drain writes the packed chains / compacted anchors into mapped memory
-            rc = enqueue_drain(c, s, s.stream, s.land_b == s.h_b ? s.h_b_dev : w.dst_b_dev);
+            // only what was produced leaves the device: k_drain writes the packed chains / chain-anchor indices into mapped memory
+            rc = enqueue_drain(c, s, s.stream, s.land_v == s.h_vp ? s.h_vp_dev : w.dst_v_dev);
             if (rc) return rc;
             CK(cudaMemcpyAsync(s.h_rinfo, s.d_rinfo, 4 * ((size_t)n_reads + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
@@ -773,23 +873,27 @@ static int wait_impl(mm2gb_ctx *c, int si)
     return MM2GB_OK;
 }
 
-// f / p of one read of a finished batch, fetched on demand (reads the device declined to backtrack)
-static int fetch_fp(mm2gb_ctx *c, Slot &s, int r, int32_t *f, int32_t *p)
+// after an error in the middle of a pipelined batch: let every slot run dry and mark it idle, so that the context stays usable
+// and nothing writes into the caller's buffers after the call has returned
+static void drain_slots(mm2gb_ctx *c)
 {
-    const long long o = s.h_off[r], n = s.h_off[r + 1] - o;
-    if (n <= 0) return MM2GB_OK;
-    CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(f, s.d_f + o, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaMemcpyAsync(p, s.d_p + o, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    return MM2GB_OK;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < c->n_slots; ++i) {
+        Slot &s = c->slot[i];
+        if (!s.busy) continue;
+        cudaStreamSynchronize(s.stream);
+        s.busy = false;
+    }
+    cudaGetLastError();
 }
+
+static Source flat_source(const mm2gb_anchor_t *a) { Source s; s.flat = a; s.flat_pinned = a && is_pinned(a); return s; }
 
 extern "C" int mm2gb_submit(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_t *a, const int64_t *off, int n_reads)
 {
     if (!c || slot < 0 || slot >= c->n_slots || n_reads < 0 || !off) return fail(MM2GB_EARG, "bad argument");
     if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
-    return submit_impl(c, slot, a, is_pinned(a), (const long long *)off, n_reads, off[n_reads], Want());
+    return submit_impl(c, slot, flat_source(a), (const long long *)off, n_reads, off[n_reads], Want());
 }
 
 static int gather_impl(mm2gb_ctx *c, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads, const Want &w)
@@ -803,9 +907,10 @@ static int gather_impl(mm2gb_ctx *c, int slot, const mm2gb_anchor_t *const *read
     for (int r = 0; r < n_reads; ++r) { off[(size_t)r] = tot; tot += read_n[r] > 0 ? read_n[r] : 0; }
     off[(size_t)n_reads] = tot;
     if ((size_t)tot > c->max_anchors) return fail(MM2GB_ECAP, "batch of %lld anchors exceeds capacity %zu", tot, c->max_anchors);
-    for (int r = 0; r < n_reads; ++r)
-        if (read_n[r] > 0) memcpy(s.h_a + off[(size_t)r], read_a[r], (size_t)read_n[r] * sizeof(mm2gb_anchor_t));
-    return submit_impl(c, slot, s.h_a, true, off.data(), n_reads, tot, w);
+    Source src;
+    src.read_a = read_a;
+    src.read_n = read_n;
+    return submit_impl(c, slot, src, off.data(), n_reads, tot, w);
 }
 
 extern "C" int mm2gb_submit_gather(mm2gb_ctx_t *c, int slot, const mm2gb_anchor_t *const *read_a, const int64_t *read_n, int n_reads)
@@ -835,49 +940,28 @@ extern "C" int mm2gb_wait(mm2gb_ctx_t *c, int slot, const int32_t **f, const int
     return MM2GB_OK;
 }
 
-// Chains of a finished batch: device results are used as they are; reads the device declined (n_u = -1: only with a negative
-// min_score, or if more than kBtOvfCap reads of one batch overflow the shared-memory kernels) are finished here with the host
-// implementation, f/p fetched on demand, their compacted anchors appended to the packed landing buffer.
-// After the call  s.h_nu / s.h_nb  hold the counts,  s.b_ptr[r] / s.u_ptr[r]  point at the read's compacted anchors / chains.
+// Chains of a finished batch.  Every read is finished on the device (reads the shared-memory kernels cannot take go to the
+// global-memory ones through the device-side list); an unfinished read here is an internal error, not a cue for a CPU path.
+// After the call  s.h_nu / s.h_nb  hold the counts,  s.v_ptr[r] / s.u_ptr[r]  point at the read's chain-anchor indices / chains.
 static int finish_chains(mm2gb_ctx *c, Slot &s)
 {
+    (void)c;
     const int n_reads = s.n_reads;
     s.u_ptr.assign((size_t)n_reads, nullptr);
-    s.b_ptr.assign((size_t)n_reads, nullptr);
-    s.spill.clear();
+    s.v_ptr.assign((size_t)n_reads, nullptr);
     s.b_total = 0;
     if (!s.n_total) { for (int r = 0; r < n_reads; ++r) s.h_nu[r] = s.h_nb[r] = s.h_bpos[r] = 0; return MM2GB_OK; }
     s.b_total = s.h_ctr->b_cur;
-    const int32_t max_drop = c->misc.is_cdna ? INT32_MAX : c->misc.bw;
-    std::vector<int32_t> f, p;
-    std::vector<uint64_t> u;
-    std::vector<mm2gb_anchor_t> bb;
     for (int r = 0; r < n_reads; ++r) {
-        const long long o = s.h_off[r], n = s.h_off[r + 1] - o;
-        if (s.h_nu[r] >= 0) {
-            s.u_ptr[(size_t)r] = reinterpret_cast<const uint64_t *>(s.h_upack) + s.h_upos[r];
-            s.b_ptr[(size_t)r] = s.land_b + s.h_bpos[r];
-            continue;
-        }
-        f.resize((size_t)n); p.resize((size_t)n); u.resize((size_t)n); bb.resize((size_t)n);
-        int rc = fetch_fp(c, s, r, f.data(), p.data());
-        if (rc) return rc;
-        int64_t nb = 0;
-        const int32_t nu = mm2gb_backtrack(n, f.data(), p.data(), s.src_a + o, c->misc.min_cnt, c->misc.min_score, max_drop, u.data(), bb.data(), &nb);
-        s.h_nu[r] = nu;
-        s.h_nb[r] = (int)nb;
-        s.h_bpos[r] = (int)s.b_total;
-        memcpy(s.land_b + s.b_total, bb.data(), (size_t)nb * sizeof(mm2gb_anchor_t));   // fits: every anchor is in at most one chain
-        s.b_ptr[(size_t)r] = s.land_b + s.b_total;
-        s.b_total += nb;
-        s.spill.emplace_back(u.begin(), u.begin() + nu);
-        s.u_ptr[(size_t)r] = s.spill.back().data();
+        if (s.h_nu[r] < 0) return fail(MM2GB_ECUDA, "device chain extraction left read %d of the batch unfinished", r);
+        s.u_ptr[(size_t)r] = reinterpret_cast<const uint64_t *>(s.h_upack) + s.h_upos[r];
+        s.v_ptr[(size_t)r] = s.land_v + s.h_bpos[r];
     }
     return MM2GB_OK;
 }
 
-extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const **u, const int32_t **n_u, const mm2gb_anchor_t *const **b,
-                                 const int32_t **n_b, const int64_t **off, mm2gb_stats_t *stats)
+extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const **u, const int32_t **n_u, const int32_t *const **v,
+                                 const int32_t **n_v, const int64_t **off, mm2gb_stats_t *stats)
 {
     if (!c || slot < 0 || slot >= c->n_slots) return fail(MM2GB_EARG, "bad argument");
     if (c->slot[slot].busy && !c->slot[slot].chains) return fail(MM2GB_ESTATE, "slot %d was not submitted for chains", slot);
@@ -888,8 +972,8 @@ extern "C" int mm2gb_wait_chains(mm2gb_ctx_t *c, int slot, const uint64_t *const
     if (rc) return rc;
     if (u) *u = s.u_ptr.data();
     if (n_u) *n_u = s.h_nu;
-    if (b) *b = s.b_ptr.data();
-    if (n_b) *n_b = s.h_nb;
+    if (v) *v = s.v_ptr.data();
+    if (n_v) *n_v = s.h_nb;
     if (off) *off = (const int64_t *)s.h_off;
     fill_stats(c, *s.h_ctr, s.n_total, stats);
     return MM2GB_OK;
@@ -901,15 +985,67 @@ extern "C" int mm2gb_slot_busy(mm2gb_ctx_t *c, int slot)
     return c->slot[slot].busy ? 1 : 0;
 }
 
+extern "C" void mm2gb_gather_anchors(const mm2gb_anchor_t *a, const int32_t *v, int64_t n, mm2gb_anchor_t *b)
+{
+    wire_gather(a, v, n, b);
+}
+
+// The packed wire format on the host alone (no device involved): pack a batch into `buf` exactly as the upload path does, and
+// the inverse by the rule k_expand applies on the device (block index -> bracketed run search).  Returns the bytes to upload,
+// or -1 when the run list does not fit `cap` bytes (the upload path then sends the anchors raw).
+extern "C" int64_t mm2gb_wire_pack(const mm2gb_anchor_t *a, const int64_t *off, int n_reads, void *buf, size_t cap, int32_t *n_runs)
+{
+    if (!off || n_reads < 0 || !buf || (reinterpret_cast<uintptr_t>(buf) & 31)) return -1;
+    const int64_t n = off[n_reads];
+    const WireLayout L = wire_layout(n, cap);
+    if (L.run_cap < 1 || L.run_off > cap) return -1;
+    WirePacker pk;
+    pk.begin(buf, L);
+    for (int r = 0; r < n_reads; ++r)
+        if (!pk.add(a + off[r], off[r + 1] - off[r])) return -1;
+    if (n_runs) *n_runs = pk.n_runs();
+    return (int64_t)pk.finish();
+}
+
+extern "C" int mm2gb_wire_unpack(const void *buf, size_t cap, int64_t n, int32_t n_runs, mm2gb_anchor_t *out)
+{
+    if (!buf || n < 0 || (n > 0 && (!out || n_runs < 1))) return MM2GB_EARG;
+    const WireLayout L = wire_layout(n, cap);
+    const char *base = static_cast<const char *>(buf);
+    const uint64_t *pk = reinterpret_cast<const uint64_t *>(base + L.pk_off);
+    const int32_t *blk = reinterpret_cast<const int32_t *>(base + L.blk_off);
+    const WireRun *runs = reinterpret_cast<const WireRun *>(base + L.run_off);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t b = i / kWireBlock;
+        int lo = blk[b], hi = std::min(blk[b + 1], n_runs - 1);
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (runs[mid].start <= i) lo = mid; else hi = mid - 1;
+        }
+        out[i].x = (uint64_t)(uint32_t)pk[i] | ((uint64_t)runs[lo].x_hi << 32);
+        out[i].y = (pk[i] >> 32) | ((uint64_t)runs[lo].y_hi << 32);
+    }
+    return MM2GB_OK;
+}
+
+extern "C" int64_t mm2gb_last_upload_bytes(mm2gb_ctx_t *c, int slot)
+{
+    if (!c || slot < 0 || slot >= c->n_slots) return -1;
+    return (int64_t)c->slot[slot].up_bytes;
+}
+
 // Shared driver of the host-buffer entry points: split the reads into chunks, run them round-robin through the slots
 // (upload / kernels / download of consecutive chunks overlap) and call on_done(slot, r0, r1) as each chunk's results land.
 template <class Done>
-static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p, mm2gb_anchor_t *b,
-                       uint4 *b_dev, bool chains, mm2gb_stats_t *stats, Done on_done)
+static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p, int32_t *v,
+                       int *v_dev, bool chains, mm2gb_stats_t *stats, Done on_done)
 {
     for (int i = 0; i < c->n_slots; ++i)
         if (c->slot[i].busy) return fail(MM2GB_ESTATE, "slot %d is busy", i);
-    const bool in_pinned = a && is_pinned(a);
+    for (int r = 0; r < n_reads; ++r)   // before anything is in flight
+        if (off[r + 1] - off[r] > (long long)c->max_anchors)
+            return fail(MM2GB_ECAP, "read %d has %lld anchors, capacity is %zu", r, (long long)(off[r + 1] - off[r]), c->max_anchors);
+    const Source src_all = flat_source(a);
     Want w;
     w.fp = f && p;
     w.dst_pinned = w.fp && is_pinned(f) && is_pinned(p);
@@ -921,6 +1057,7 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
     if (const char *e = getenv("MM2GB_CHUNK")) target = std::min<long long>(std::max(1LL, atoll(e)), (long long)c->max_anchors);
     mm2gb_stats_t acc;
     memset(&acc, 0, sizeof(acc));
+    c->up_bytes_batch = 0;
     std::vector<long long> rel;
     int slot_r0[kMaxSlots] = {0}, slot_r1[kMaxSlots] = {0};
     int r0 = 0, chunk = 0, rc = MM2GB_OK;
@@ -943,28 +1080,31 @@ static int run_chunked(mm2gb_ctx *c, const mm2gb_anchor_t *a, const int64_t *off
         const long long this_target = std::max<long long>(1 << 18, std::min(std::min(target, ramp), std::max(target / 4, remaining * 2 / 5)));
         while (r1 < n_reads && r1 - r0 < c->max_reads) {
             const long long nr = off[r1 + 1] - off[r1];
-            if (nr > (long long)c->max_anchors) return fail(MM2GB_ECAP, "read %d has %lld anchors, capacity is %zu", r1, nr, c->max_anchors);
             if (cnt && cnt + nr > this_target) break;
             cnt += nr; ++r1;
         }
         const int si = chunk % c->n_slots;
-        if (c->slot[si].busy && (rc = reap(si))) return rc;
+        if (c->slot[si].busy && (rc = reap(si))) break;
         rel.resize((size_t)(r1 - r0) + 1);
         for (int r = r0; r <= r1; ++r) rel[(size_t)(r - r0)] = off[r] - off[r0];
         w.dst_f = w.fp ? f + off[r0] : nullptr;
         w.dst_p = w.fp ? p + off[r0] : nullptr;
-        w.dst_b = (b && b_dev) ? b + off[r0] : nullptr;      // a chunk's packed results land where its anchors start
-        w.dst_b_dev = (b && b_dev) ? b_dev + off[r0] : nullptr;
-        rc = submit_impl(c, si, a + off[r0], in_pinned, rel.data(), r1 - r0, cnt, w);
-        if (rc) return rc;
+        w.dst_v = (v && v_dev) ? v + off[r0] : nullptr;      // a chunk's packed results land where its anchors start
+        w.dst_v_dev = (v && v_dev) ? v_dev + off[r0] : nullptr;
+        Source src = src_all;
+        src.flat = a + off[r0];
+        rc = submit_impl(c, si, src, rel.data(), r1 - r0, cnt, w);
+        if (rc) break;
+        c->up_bytes_batch += (long long)c->slot[si].up_bytes;
         slot_r0[si] = r0; slot_r1[si] = r1;
         r0 = r1; ++chunk;
     }
     // drain in submission order
-    for (int k = 0; k < c->n_slots; ++k) {
+    for (int k = 0; k < c->n_slots && !rc; ++k) {
         const int si = (chunk + k) % c->n_slots;
-        if (c->slot[si].busy && (rc = reap(si))) return rc;
+        if (c->slot[si].busy) rc = reap(si);
     }
+    if (rc) { drain_slots(c); return rc; }
     if (stats) *stats = acc;
     if (c->timeline) timeline_dump(c);
     return MM2GB_OK;
@@ -980,9 +1120,9 @@ extern "C" int mm2gb_chain_dp_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, cons
     return run_chunked(c, a, off, n_reads, f, p, nullptr, nullptr, false, stats, [](int, int, int) { return MM2GB_OK; });
 }
 
-// Whole mg_lchain_dp (lchain.c:148-217) for a batch, host-stage variant: device DP, then backtracking + compaction on
-// `n_threads` host worker threads that start on a chunk's reads as soon as its f/p have landed, while later chunks are
-// still on the GPU.  Outputs per read r: u[off[r] .. off[r]+n_u[r]), b[off[r] .. off[r]+n_b[r]).
+// Whole mg_lchain_dp (lchain.c:148-217) for a batch, host-stage variant (a diagnostic: how the reference arranges the work,
+// gpu/plchain.cu:99-150): device DP, then backtracking + compaction on `n_threads` host worker threads that start on a chunk's
+// reads as soon as its f/p have landed, while later chunks are still on the GPU.
 static int chain_host_hoststage(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                                 uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats)
 {
@@ -1025,8 +1165,8 @@ static int chain_host_hoststage(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
 }
 
 // Device variant (default): chain extraction + compaction run on the GPU right behind the DP kernels (k_bt_sort / k_bt_walk)
-// and only their packed result leaves the device.  f / p are downloaded only if the caller passes buffers for them.
-// Output layout of mm2gb_chain_host: read r's compacted anchors at b[off[r] ..], copied there from the slot's landing buffer.
+// and only the chains and the indices of their anchors leave the device.  f / p are downloaded only if the caller passes
+// buffers for them.  Output layout of mm2gb_chain_host: read r's compacted anchors at b[off[r] ..], gathered here from `a`.
 static int chain_host_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                              uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, mm2gb_stats_t *stats)
 {
@@ -1039,50 +1179,52 @@ static int chain_host_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int6
             n_u[r] = s.h_nu[k];
             n_b[r] = s.h_nb[k];
             if (s.h_nu[k] > 0) memcpy(u + off[r], s.u_ptr[(size_t)k], (size_t)s.h_nu[k] * sizeof(uint64_t));
-            if (s.h_nb[k] > 0) memcpy(b + off[r], s.b_ptr[(size_t)k], (size_t)s.h_nb[k] * sizeof(mm2gb_anchor_t));
+            if (s.h_nb[k] > 0) wire_gather(a + off[r], s.v_ptr[(size_t)k], s.h_nb[k], b + off[r]);
         }
         return MM2GB_OK;
     });
 }
 
 // device view of a caller's buffer if it is mapped pinned memory, else nullptr
-static uint4 *mapped_view(mm2gb_anchor_t *b)
+static int *mapped_view(int32_t *v)
 {
-    if (!b || !is_pinned(b)) return nullptr;
+    if (!v || !is_pinned(v)) return nullptr;
     void *d = nullptr;
-    if (cudaHostGetDevicePointer(&d, b, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return reinterpret_cast<uint4 *>(d);
+    if (cudaHostGetDevicePointer(&d, v, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return reinterpret_cast<int *>(d);
 }
 
-// Packed output: the compacted anchors of read r are b[b_pos[r] .. b_pos[r] + n_b[r]); the reads of one chunk are packed
-// behind each other (in no particular order) starting where the chunk's anchors start in `a`.  With `b` in pinned memory
+// Index output: the compacted anchors of read r are a[off[r] + v[v_pos[r] + k]], k < n_v[r]; the reads of one chunk are packed
+// behind each other (in no particular order) starting at index off[first read of the chunk] of `v`.  With `v` in pinned memory
 // the device writes them there directly and the host only copies the (few) chains.
-extern "C" int mm2gb_chain_host_packed(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, uint64_t *u, int32_t *n_u,
-                                       mm2gb_anchor_t *b, int64_t *b_pos, int64_t *n_b, mm2gb_stats_t *stats)
+extern "C" int mm2gb_chain_host_index(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, uint64_t *u, int32_t *n_u,
+                                      int32_t *v, int64_t *v_pos, int64_t *n_v, mm2gb_stats_t *stats)
 {
-    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || !n_u || !n_b || !b_pos) return fail(MM2GB_EARG, "bad argument");
-    if (off[n_reads] > 0 && (!u || !b)) return fail(MM2GB_EARG, "bad argument");
+    if (!c || !off || n_reads < 0 || (!a && off[n_reads] > 0) || !n_u || !n_v || !v_pos) return fail(MM2GB_EARG, "bad argument");
+    if (off[n_reads] > 0 && (!u || !v)) return fail(MM2GB_EARG, "bad argument");
     if (off[0] != 0) return fail(MM2GB_EARG, "off[0] must be 0");
     if (stats) memset(stats, 0, sizeof(*stats));
     if (n_reads == 0) return MM2GB_OK;
     CK(cudaSetDevice(c->device));
-    uint4 *b_dev = mapped_view(b);
-    return run_chunked(c, a, off, n_reads, nullptr, nullptr, b, b_dev, true, stats, [&](int si, int r0, int r1) {
+    int *v_dev = mapped_view(v);
+    return run_chunked(c, a, off, n_reads, nullptr, nullptr, v, v_dev, true, stats, [&](int si, int r0, int r1) {
         Slot &s = c->slot[si];
         int rc = finish_chains(c, s);
         if (rc) return rc;
-        mm2gb_anchor_t *dst = b + off[r0];
-        if (s.land_b != dst && s.b_total > 0) memcpy(dst, s.land_b, (size_t)s.b_total * sizeof(mm2gb_anchor_t));
+        int32_t *dst = v + off[r0];
+        if (s.land_v != dst && s.b_total > 0) memcpy(dst, s.land_v, (size_t)s.b_total * sizeof(int32_t));
         for (int r = r0; r < r1; ++r) {
             const int k = r - r0;
             n_u[r] = s.h_nu[k];
-            n_b[r] = s.h_nb[k];
-            b_pos[r] = off[r0] + (s.h_nb[k] > 0 ? s.h_bpos[k] : 0);
+            n_v[r] = s.h_nb[k];
+            v_pos[r] = off[r0] + (s.h_nb[k] > 0 ? s.h_bpos[k] : 0);
             if (s.h_nu[k] > 0) memcpy(u + off[r], s.u_ptr[(size_t)k], (size_t)s.h_nu[k] * sizeof(uint64_t));
         }
         return MM2GB_OK;
     });
 }
+
+extern "C" int64_t mm2gb_last_batch_upload_bytes(mm2gb_ctx_t *c) { return c ? (int64_t)c->up_bytes_batch : -1; }
 
 extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int32_t *f, int32_t *p,
                                 uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads, mm2gb_stats_t *stats)
@@ -1099,7 +1241,7 @@ extern "C" int mm2gb_chain_host(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, const i
     return chain_host_device(c, a, off, n_reads, f, p, u, n_u, b, n_b, stats);
 }
 
-// The host stage alone for a batch whose f/p are already in host memory (what mm2gb_chain_host runs behind the device).
+// The host stage alone for a batch whose f/p are already in host memory (diagnostic; what the reference runs behind its kernels).
 extern "C" int mm2gb_backtrack_batch(const mm2gb_misc_t *m, const mm2gb_anchor_t *a, const int64_t *off, int n_reads, const int32_t *f,
                                      const int32_t *p, uint64_t *u, int32_t *n_u, mm2gb_anchor_t *b, int64_t *n_b, int n_threads)
 {
@@ -1138,13 +1280,12 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
     if (n_reads > c->max_reads) return fail(MM2GB_ECAP, "batch of %d reads exceeds capacity %d", n_reads, c->max_reads);
     Slot &s = c->slot[0];
     if (s.busy) return fail(MM2GB_ESTATE, "slot 0 is busy");
-    if (!c->host_io || !c->chains_ok) return fail(MM2GB_ESTATE, "context was created without host staging / chain-extraction buffers");
+    if (!c->host_io || !c->chains_ok || !c->fp_staging) return fail(MM2GB_ESTATE, "context was created without host staging / chain-extraction buffers");
     CK(cudaSetDevice(c->device));
     if (n_declined) *n_declined = 0;
     memcpy(s.h_off, off, ((size_t)n_reads + 1) * sizeof(long long));
     s.n_reads = n_reads;
     s.n_total = n_total;
-    s.src_a = s.h_a;
     if (n_total) {
         memcpy(s.h_a, a, (size_t)n_total * sizeof(mm2gb_anchor_t));
         memcpy(s.h_f, f, (size_t)n_total * sizeof(int));
@@ -1158,13 +1299,13 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
         if (rc) return rc;
         rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, n_reads, s.d_f, s.d_p, false);
         if (rc) return rc;
-        s.land_b = s.h_b;
-        rc = enqueue_drain(c, s, s.stream, s.h_b_dev);
+        s.land_v = s.h_vp;
+        rc = enqueue_drain(c, s, s.stream, s.h_vp_dev);
         if (rc) return rc;
         CK(cudaMemcpyAsync(s.h_rinfo, s.d_rinfo, 4 * ((size_t)n_reads + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
-        if (n_declined) for (int r = 0; r < n_reads; ++r) *n_declined += s.h_nu[r] < 0 ? 1 : 0;
+        if (n_declined) for (int r = 0; r < n_reads; ++r) *n_declined += s.h_nu[r] < 0 ? 1 : 0;   // must stay 0
     } else {
         slice_rinfo(s, n_reads);
     }
@@ -1174,7 +1315,7 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
         n_u[r] = s.h_nu[r];
         n_b[r] = s.h_nb[r];
         if (s.h_nu[r] > 0) memcpy(u + off[r], s.u_ptr[(size_t)r], (size_t)s.h_nu[r] * sizeof(uint64_t));
-        if (s.h_nb[r] > 0) memcpy(b + off[r], s.b_ptr[(size_t)r], (size_t)s.h_nb[r] * sizeof(mm2gb_anchor_t));
+        if (s.h_nb[r] > 0) wire_gather(a + off[r], s.v_ptr[(size_t)r], s.h_nb[r], b + off[r]);
     }
     return MM2GB_OK;
 }
@@ -1208,9 +1349,10 @@ extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d
     return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, (const int *)d_f, (const int *)d_p, c->profile);
 }
 
-// Diagnostic: device -> pinned host of n anchors (16 B each) from slot 0's buffers, by k_drain with `blocks` CTAs and by the
-// copy engine, each optionally with a host -> device copy of the same size running on a second stream (PCIe is full duplex).
-// ms[0] = k_drain alone, ms[1] = cudaMemcpyAsync alone, ms[2] = k_drain + H2D, ms[3] = cudaMemcpyAsync + H2D, ms[4] = H2D alone.
+// Diagnostic: device -> pinned host of n chain-anchor indices (4 B each) from slot 0's buffers, by k_drain with `blocks` CTAs and
+// by the copy engine, each optionally with a host -> device copy of the same number of bytes running on a second stream (PCIe
+// is full duplex).  ms[0] = k_drain alone, ms[1] = cudaMemcpyAsync alone, ms[2] = k_drain + H2D, ms[3] = cudaMemcpyAsync + H2D,
+// ms[4] = H2D alone.
 extern "C" int mm2gb_debug_drain(mm2gb_ctx_t *c, int64_t n, int blocks, float ms[5])
 {
     if (!c || !ms || n <= 0 || (size_t)n > c->max_anchors || !c->host_io || !c->chains_ok || blocks < 1) return fail(MM2GB_EARG, "bad argument");
@@ -1230,9 +1372,9 @@ extern "C" int mm2gb_debug_drain(mm2gb_ctx_t *c, int64_t n, int blocks, float ms
             CK(cudaDeviceSynchronize());
             CK(cudaEventRecord(e0, s.stream));
             CK(cudaStreamWaitEvent(s2, e0, 0));
-            if (mode == 0 || mode == 2) k_drain<<<blocks, kDrainThreads, 0, s.stream>>>(s.d_b, s.h_b_dev, s.d_upack, s.h_upack_dev, s.d_ctr);
-            if (mode == 1 || mode == 3) CK(cudaMemcpyAsync(s.h_b, s.d_b, (size_t)n * 16, cudaMemcpyDeviceToHost, s.stream));
-            if (mode >= 2) CK(cudaMemcpyAsync(s.d_a, s.h_a, (size_t)n * 16, cudaMemcpyHostToDevice, s2));
+            if (mode == 0 || mode == 2) k_drain<<<blocks, kDrainThreads, 0, s.stream>>>(s.d_vp, s.h_vp_dev, s.d_upack, s.h_upack_dev, s.d_ctr);
+            if (mode == 1 || mode == 3) CK(cudaMemcpyAsync(s.h_vp, s.d_vp, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+            if (mode >= 2) CK(cudaMemcpyAsync(s.d_a, s.h_a, (size_t)n * 4, cudaMemcpyHostToDevice, s2));
             CK(cudaEventRecord(e2, s2));
             CK(cudaStreamWaitEvent(s.stream, e2, 0));
             CK(cudaEventRecord(e1, s.stream));

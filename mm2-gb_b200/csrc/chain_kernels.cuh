@@ -75,6 +75,30 @@ __device__ __forceinline__ int long_classes_eff(const Counters *ctr, int big_cap
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// k_expand: packed wire format -> 16-byte anchors in HBM               (replaces the H2D of gpu/plmem.cu:200-236)
+//   The upload carries 8 bytes per anchor (low words of x and y) plus one 16-byte record per run of equal high words
+//   (csrc/wire.h).  One thread per anchor: blk_run[] brackets the runs a 256-anchor block can touch (almost always one or
+//   two), so finding the run is a 0-2 step search, and the anchor is written back as one 16-byte store.  Reads 8 B, writes
+//   16 B per anchor: HBM-bound, ~0.12 ms for 31.7 M anchors.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_expand(const uint2 *__restrict__ pk, const int *__restrict__ blk_run, const uint4 *__restrict__ runs, int n_runs, int n_total,
+         uint4 *__restrict__ a)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_total) return;
+    const uint2 v = __ldg(pk + i);
+    int lo = __ldg(blk_run + blockIdx.x), hi = min(__ldg(blk_run + blockIdx.x + 1), n_runs - 1);
+    uint4 r = __ldg(runs + lo);
+    while (lo < hi) {   // largest run in [lo, hi] that starts at or before i
+        const int mid = (lo + hi + 1) >> 1;
+        const uint4 rm = __ldg(runs + mid);
+        if ((int)rm.x <= i) { lo = mid; r = rm; } else hi = mid - 1;
+    }
+    a[i] = make_uint4(v.x, r.y, v.y, r.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // k_range: window start, cuts, clipped windows, pair count            (replaces gpu/plrange.cu:38-76)
 //   one thread per anchor of the flat batch; a block first finds the read that holds its first anchor.
 // ---------------------------------------------------------------------------------------------------------------------

@@ -8,44 +8,52 @@
 //   * finish_stream_gpu drains; free_stream_gpu tears down and is a no-op when nothing was initialised.
 // What is different:
 //   * the new batch is submitted BEFORE the previous one is finished on the host, so the GPU chains batch k+1 while this
-//     thread backtracks batch k (the reference synchronises first, plchain.cu:299-305);
-//   * every thread_id owns a context (2 slots: stream + pinned staging + device buffers) on GPU thread_id % n_gpus, so
-//     `-t N` and several GPUs work (the reference is limited to -t 1 / one stream, README.md:46-47);
-//   * anchors are gathered straight from chain_read_t.a into pinned memory -- no AoS->SoA repack (plmem.cu:154-198);
-//   * no read is ever handed back for CPU chaining (plchain.cu:421-423): oversized batches grow the context instead;
-//   * --max-chain-skip is ignored, i.e. true infinity (SURVEY.md trap T1), as in the reference's kernels;
-//   * chain extraction + compaction (lchain.c:27-111) run on the device behind the DP kernels (k_bt_sort* / k_bt_walk*); the calling
-//     thread only copies the results into the kalloc arena (kalloc is not thread-safe).  "host_backtrack": 1 in the config
-//     (or MM2GB_HOST_BACKTRACK=1) moves that stage to a small host thread pool instead (csrc/backtrack.cpp).
+//     thread publishes batch k (the reference synchronises first, plchain.cu:299-305);
+//   * a batch is cut into up to four sub-batches that go through their own slots (stream + pinned staging + device buffers):
+//     while this thread gathers sub-batch j+1 into pinned memory, sub-batch j is already uploading / being chained, and on the
+//     way back sub-batch j is published while j+1 is still on the GPU;
+//   * every thread_id owns a context on GPU thread_id % n_gpus, so `-t N` and several GPUs work (the reference is limited to
+//     -t 1 / one stream, README.md:46-47);
+//   * the gather pass over chain_read_t.a writes the packed 8-byte wire format (csrc/wire.h) -- the reference's pass is an
+//     AoS->SoA repack of 13 B/anchor (plmem.cu:154-198) -- and what comes back are chains and the INDICES of their anchors:
+//     compact_a's gather (lchain.c:100-105) runs here, from the read's own array, straight into the kmalloc'd result;
+//   * no read is ever handed back for CPU chaining (plchain.cu:421-423) and there is no host chaining or backtracking path:
+//     oversized batches grow the context instead; without a CUDA device every call fails;
+//   * --max-chain-skip is ignored, i.e. true infinity (SURVEY.md trap T1), as in the reference's kernels.
 #include "../../include/mm2gb_plchain.h"
 
+#include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
-#include <thread>
+#include <unistd.h>
 #include <vector>
 
 namespace {
 
-constexpr int kMaxThreads = 256;
+constexpr int kMaxSub = 4;          // sub-batches of one batch (2 batches in flight x 4 = the 8 slots of a context)
 
 struct Config {
-    size_t max_total_n = 64u << 20; // anchors per launched batch
+    size_t max_total_n = 16u << 20; // anchors per launched batch
     int max_read = 200000;          // reads per batch
     int min_n = 0;                  // plumbed through, unused downstream (map.c:1314)
     int n_gpus = 0;                 // 0 = all visible
-    int n_slots = 2;
-    int host_threads = 8;
-    int host_backtrack = 0;         // 1 = chain extraction on host threads instead of the device kernel
+    int gpu_base = 0;               // first GPU used (thread_id t runs on GPU gpu_base + t % n_gpus)
+    int sub_batches = kMaxSub;      // 1..4
+    int threads_per_gpu = 4;        // sizing hint: how many driver threads share a GPU (minimap2 -t N / n_gpus)
+    int64_t sub_min = 1 << 19;      // a batch is only cut into sub-batches of at least this many anchors (enough to fill the GPU)
 };
+
+struct Sub { int slot, r0, r1; };
 
 struct ThreadState {
     mm2gb_ctx_t *ctx = nullptr;
     int device = 0;
-    size_t cap_anchors = 0;
+    size_t cap_anchors = 0;         // capacity of ONE slot
     int cap_reads = 0;
     Misc_abi misc;
     bool has_misc = false;
@@ -53,13 +61,9 @@ struct ThreadState {
     bool busy = false;
     mm2gb_chain_read_t *reads = nullptr;
     int n_reads = 0;
-    int slot = 0;
-    bool submitted = false; // false for batches without anchors
-    // scratch of the host stage
-    std::vector<uint64_t> su;
-    std::vector<mm2gb_anchor_t> sb;
-    std::vector<int32_t> s_nu;
-    std::vector<int64_t> s_nb, s_off;
+    int half = 0;                   // which half of the slots it uses
+    std::vector<Sub> subs;          // its sub-batches (empty for a batch without anchors)
+    // scratch
     std::vector<const mm2gb_anchor_t *> ptrs;
     std::vector<int64_t> ns;
 };
@@ -68,7 +72,8 @@ Config g_cfg;
 bool g_inited = false;
 Misc_abi g_misc;
 std::mutex g_mu;
-ThreadState *g_state[kMaxThreads];
+std::vector<ThreadState *> g_state;
+std::atomic<long long> g_h2d_bytes(0), g_d2h_bytes(0);   // bytes that crossed PCIe since the last reset (mm2gb_dropin_traffic)
 
 [[noreturn]] void die(const char *what)
 {
@@ -76,23 +81,94 @@ ThreadState *g_state[kMaxThreads];
     exit(1);
 }
 
-// minimal reader for the flat numeric keys of gpu/gpu_config.json-style files
-bool json_number(const std::string &txt, const char *key, double *out)
-{
-    const std::string pat = std::string("\"") + key + "\"";
-    size_t at = 0;
-    while ((at = txt.find(pat, at)) != std::string::npos) {
-        size_t q = at + pat.size();
-        while (q < txt.size() && (txt[q] == ' ' || txt[q] == '\t' || txt[q] == '\n' || txt[q] == '\r')) ++q;
-        if (q < txt.size() && txt[q] == ':') {
-            char *end = nullptr;
-            const double v = strtod(txt.c_str() + q + 1, &end);
-            if (end != txt.c_str() + q + 1) { *out = v; return true; }
+// ---- gpu config file: the reference's gpu/*.json (parsed there with cJSON, gpu/plmem.cu:373-451) --------------------------
+// A small recursive-descent JSON reader that collects the NUMERIC members of the TOP-LEVEL object only; nested objects
+// ("range_kernel", "score_kernel": the tuning keys of the old kernels) and arrays are parsed and skipped, strings may hold
+// anything, so a key of the same name inside a nested object or a string value is never picked up.
+struct JsonReader {
+    const char *p, *end;
+    bool ok = true;
+    std::vector<std::pair<std::string, double>> top;
+
+    void ws() { while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
+    bool lit(const char *s) { const size_t n = strlen(s); if ((size_t)(end - p) >= n && !strncmp(p, s, n)) { p += n; return true; } return false; }
+    bool string(std::string *out)
+    {
+        if (p >= end || *p != '"') return ok = false;
+        ++p;
+        while (p < end && *p != '"') {
+            if (*p == '\\') { if (++p >= end) return ok = false; }   // escaped character (\uXXXX digits pass as plain characters)
+            if (out) out->push_back(*p);
+            ++p;
         }
-        at += pat.size();
+        if (p >= end) return ok = false;
+        ++p;
+        return true;
     }
-    return false;
-}
+    bool number(double *out)
+    {
+        char *e = nullptr;
+        const double v = strtod(p, &e);
+        if (e == p || e > end) return ok = false;
+        p = e;
+        if (out) *out = v;
+        return true;
+    }
+    bool value(int depth, const std::string *key)
+    {
+        ws();
+        if (p >= end || depth > 64) return ok = false;
+        if (*p == '{') {
+            ++p; ws();
+            if (p < end && *p == '}') { ++p; return true; }
+            for (;;) {
+                ws();
+                std::string k;
+                if (!string(&k)) return false;
+                ws();
+                if (p >= end || *p != ':') return ok = false;
+                ++p;
+                if (!value(depth + 1, depth == 0 ? &k : nullptr)) return false;
+                ws();
+                if (p < end && *p == ',') { ++p; continue; }
+                if (p < end && *p == '}') { ++p; return true; }
+                return ok = false;
+            }
+        }
+        if (*p == '[') {
+            ++p; ws();
+            if (p < end && *p == ']') { ++p; return true; }
+            for (;;) {
+                if (!value(depth + 1, nullptr)) return false;
+                ws();
+                if (p < end && *p == ',') { ++p; continue; }
+                if (p < end && *p == ']') { ++p; return true; }
+                return ok = false;
+            }
+        }
+        if (*p == '"') return string(nullptr);
+        if (lit("true") || lit("false") || lit("null")) return true;
+        double v;
+        if (!number(&v)) return false;
+        if (key) top.emplace_back(*key, v);
+        return true;
+    }
+    bool parse(const std::string &txt)
+    {
+        p = txt.data(); end = p + txt.size();
+        if (!value(0, nullptr)) return false;
+        ws();
+        return ok && p == end;
+    }
+    bool get(const char *key, double *out) const
+    {
+        for (const auto &kv : top) if (kv.first == key) { *out = kv.second; return true; }
+        return false;
+    }
+};
+
+// bytes per anchor of batch capacity a driver thread's context costs (two batches in flight): see DESIGN.md section 2
+constexpr size_t kDevBytesPerAnchor = 2 * 90, kPinnedBytesPerAnchor = 2 * 28;
 
 void load_config(const char *path)
 {
@@ -108,21 +184,48 @@ void load_config(const char *path)
             fprintf(stderr, "[WARNING] mm2gb chaining: cannot open gpu config '%s'; using built-in defaults\n", path);
         }
     }
+    JsonReader js;
+    if (!txt.empty() && !js.parse(txt)) {
+        fprintf(stderr, "[ERROR] mm2gb chaining: gpu config '%s' is not valid JSON\n", path);   // plmem.cu:390-413 exits too
+        exit(1);
+    }
     double v;
-    if (json_number(txt, "max_total_n", &v) && v >= 1) g_cfg.max_total_n = (size_t)v;
-    if (json_number(txt, "max_read", &v) && v >= 1) g_cfg.max_read = (int)v;
-    if (json_number(txt, "min_n", &v) && v >= 0) g_cfg.min_n = (int)v;
-    if (json_number(txt, "n_gpus", &v) && v >= 0) g_cfg.n_gpus = (int)v;
-    if (json_number(txt, "n_slots", &v) && v >= 2 && v <= 4) g_cfg.n_slots = (int)v;
-    if (json_number(txt, "host_threads", &v) && v >= 1) g_cfg.host_threads = (int)v;
-    if (json_number(txt, "host_backtrack", &v)) g_cfg.host_backtrack = v != 0;
-    if (const char *e = getenv("MM2GB_HOST_BACKTRACK")) g_cfg.host_backtrack = atoi(e) != 0;
-    if (const char *e = getenv("MM2GB_HOST_THREADS")) g_cfg.host_threads = atoi(e) > 0 ? atoi(e) : g_cfg.host_threads;
+    if (js.get("max_total_n", &v) && v >= 1) g_cfg.max_total_n = (size_t)v;
+    if (js.get("max_read", &v) && v >= 1) g_cfg.max_read = (int)v;
+    if (js.get("min_n", &v) && v >= 0) g_cfg.min_n = (int)v;
+    if (js.get("n_gpus", &v) && v >= 0) g_cfg.n_gpus = (int)v;
+    if (js.get("sub_batches", &v) && v >= 1 && v <= kMaxSub) g_cfg.sub_batches = (int)v;
+    if (js.get("threads_per_gpu", &v) && v >= 1) g_cfg.threads_per_gpu = (int)v;
+    if (js.get("gpu_base", &v) && v >= 0) g_cfg.gpu_base = (int)v;
     if (const char *e = getenv("MM2GB_N_GPUS")) g_cfg.n_gpus = atoi(e) > 0 ? atoi(e) : g_cfg.n_gpus;
+    if (const char *e = getenv("MM2GB_GPU_BASE")) g_cfg.gpu_base = std::max(0, atoi(e));
+    if (const char *e = getenv("MM2GB_SUB_BATCHES")) g_cfg.sub_batches = std::min(kMaxSub, std::max(1, atoi(e)));
+    if (const char *e = getenv("MM2GB_THREADS_PER_GPU")) g_cfg.threads_per_gpu = std::max(1, atoi(e));
+    if (const char *e = getenv("MM2GB_SUB_MIN")) g_cfg.sub_min = std::max<int64_t>(1, atoll(e));
     if (g_cfg.max_total_n > ((size_t)1 << 31) - 2048) g_cfg.max_total_n = ((size_t)1 << 31) - 2048;
     const int ndev = mm2gb_device_count();
     if (ndev <= 0) { fprintf(stderr, "[ERROR] mm2gb chaining: --gpu-chain needs a CUDA device (no CPU fallback)\n"); exit(1); }
-    if (g_cfg.n_gpus <= 0 || g_cfg.n_gpus > ndev) g_cfg.n_gpus = ndev;
+    if (g_cfg.gpu_base >= ndev) g_cfg.gpu_base = 0;
+    if (g_cfg.n_gpus <= 0 || g_cfg.n_gpus > ndev - g_cfg.gpu_base) g_cfg.n_gpus = ndev - g_cfg.gpu_base;
+    // Every driver thread owns a context with room for two batches, so the batch limit handed to the driver has to fit the
+    // memory that is actually there: 80 % of the GPU's free memory shared by threads_per_gpu threads, half of the host's
+    // available memory (pinned staging) shared by all of them.  The reference's own gpu_config.json asks for 500 M anchors
+    // (sized for its 13 B/anchor buffers and one thread); that is shrunk here with a warning instead of failing in cudaMalloc.
+    size_t dev_free = 0, dev_total = 0;
+    if (mm2gb_device_memory(g_cfg.gpu_base, &dev_free, &dev_total) == MM2GB_OK && dev_free) {
+        const size_t by_dev = (size_t)(0.8 * (double)dev_free) / ((size_t)g_cfg.threads_per_gpu * kDevBytesPerAnchor);
+        const long pages = sysconf(_SC_AVPHYS_PAGES), psz = sysconf(_SC_PAGESIZE);
+        size_t by_host = SIZE_MAX;
+        if (pages > 0 && psz > 0)
+            by_host = (size_t)(0.5 * (double)pages * (double)psz) / ((size_t)g_cfg.threads_per_gpu * (size_t)g_cfg.n_gpus * kPinnedBytesPerAnchor);
+        const size_t cap = std::max<size_t>(1u << 20, std::min(by_dev, by_host));
+        if (g_cfg.max_total_n > cap) {
+            fprintf(stderr, "[WARNING] mm2gb chaining: max_total_n %zu shrunk to %zu anchors (%zu B of device and %zu B of pinned memory per "
+                            "anchor and driver thread, %d thread(s) per GPU assumed; set \"threads_per_gpu\" in the gpu config)\n",
+                    g_cfg.max_total_n, cap, kDevBytesPerAnchor, kPinnedBytesPerAnchor, g_cfg.threads_per_gpu);
+            g_cfg.max_total_n = cap;
+        }
+    }
 }
 
 bool same_misc(const Misc_abi &a, const Misc_abi &b) { return memcmp(&a, &b, sizeof(Misc_abi)) == 0; }
@@ -131,7 +234,8 @@ void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi 
 {
     if (S.ctx) mm2gb_ctx_destroy(S.ctx);
     S.ctx = nullptr;
-    if (mm2gb_ctx_create(&S.ctx, S.device, cap_anchors, cap_reads, g_cfg.n_slots, &misc) != MM2GB_OK) die("cannot create the chaining context");
+    if (mm2gb_ctx_create_ex(&S.ctx, S.device, cap_anchors, cap_reads, 2 * g_cfg.sub_batches, &misc, MM2GB_CTX_NO_FP_STAGING) != MM2GB_OK)
+        die("cannot create the chaining context");
     S.cap_anchors = cap_anchors;
     S.cap_reads = cap_reads;
     S.misc = misc;
@@ -140,78 +244,74 @@ void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi 
 
 ThreadState &state_of(int tid)
 {
-    if (tid < 0 || tid >= kMaxThreads) { fprintf(stderr, "[ERROR] mm2gb chaining: thread id %d out of range\n", tid); exit(1); }
+    if (tid < 0) { fprintf(stderr, "[ERROR] mm2gb chaining: thread id %d out of range\n", tid); exit(1); }
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) { fprintf(stderr, "[ERROR] mm2gb chaining: chain_stream_gpu before init_stream_gpu\n"); exit(1); }
-    if (!g_state[tid]) {
-        g_state[tid] = new ThreadState();
-        g_state[tid]->device = tid % g_cfg.n_gpus;
+    if ((size_t)tid >= g_state.size()) g_state.resize((size_t)tid + 1, nullptr);
+    if (!g_state[(size_t)tid]) {
+        g_state[(size_t)tid] = new ThreadState();
+        g_state[(size_t)tid]->device = g_cfg.gpu_base + tid % g_cfg.n_gpus;
     }
-    return *g_state[tid];
+    return *g_state[(size_t)tid];
 }
 
-// finish the batch in flight: wait for the device, publish the chains into the arena, run the driver's helper.
-// Chain extraction + compaction (lchain.c:27-111) ran on the device behind the DP kernels (g_cfg.host_backtrack == 0,
-// default) or runs here on a small thread pool (host_backtrack == 1: the reference's arrangement, plchain.cu:99-150).
+// The chaining parameters of a batch.  The boundary chains every read of a batch with ONE parameter set, built for a single
+// segment with qlen_sum = 0 (plchain.cu:497-500; the reference guards that with an assert that release builds compile out).
+// That is only right when build_misc does not depend on the read: with the short-read / fragment presets (MM_F_SR, or
+// max_frag_len > max_gap without max_gap_ref; map.c:398-406) it does, and chaining would silently use the wrong
+// max_dist_x / max_dist_y.  Fail loudly instead.
+Misc_abi batch_misc(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt)
+{
+    const Misc_abi misc = build_misc(mi, opt, 0, 1);
+    const Misc_abi probe = build_misc(mi, opt, (int64_t)1 << 28, 1);
+    if (!same_misc(misc, probe)) {
+        fprintf(stderr, "[ERROR] mm2gb chaining: with these options the chaining parameters depend on the read length (short-read / "
+                        "fragment mode); --gpu-chain supports single-segment long-read chaining only\n");
+        exit(1);
+    }
+    return misc;
+}
+
+// finish the batch in flight: sub-batch by sub-batch, wait for the device, publish the chains into the arena, run the
+// driver's helper.  Chain extraction + compaction (lchain.c:27-111) ran on the device behind the DP kernels; what arrives
+// are the chains u[] and the indices of the chain anchors, and compact_a's gather is done here from the read's own array.
 void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt, const Misc_abi &misc, void *km)
 {
     mm2gb_chain_read_t *reads = S.reads;
     const int n_reads = S.n_reads;
-    const int64_t *off = nullptr;
-    const uint64_t *const *dev_u = nullptr;
-    const int32_t *dev_nu = nullptr, *dev_nb = nullptr;
-    const mm2gb_anchor_t *const *dev_b = nullptr;
-    if (S.submitted && !g_cfg.host_backtrack) {
-        if (mm2gb_wait_chains(S.ctx, S.slot, &dev_u, &dev_nu, &dev_b, &dev_nb, &off, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
-    } else if (S.submitted) {
-        const int32_t *f = nullptr, *p = nullptr;
-        if (mm2gb_wait(S.ctx, S.slot, &f, &p, &off, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
-        const int64_t total = off[n_reads];
-        if ((int64_t)S.su.size() < total) { S.su.resize((size_t)total); S.sb.resize((size_t)total); }
-        S.s_nu.assign((size_t)n_reads, 0);
-        S.s_nb.assign((size_t)n_reads, 0);
-        const int32_t max_drop = misc.is_cdna ? INT32_MAX : misc.bw; // lchain.c:151,162
-        std::atomic<int> next(0);
-        auto work = [&]() {
-            for (;;) {
-                const int r = next.fetch_add(1);
-                if (r >= n_reads) return;
-                const int64_t s = off[r], n = off[r + 1] - s;
-                if (n <= 0) continue;
-                S.s_nu[(size_t)r] = mm2gb_backtrack(n, f + s, p + s, reads[r].a, misc.min_cnt, misc.min_score, max_drop,
-                                                    S.su.data() + s, S.sb.data() + s, &S.s_nb[(size_t)r]);
-            }
-        };
-        const int nt = std::max(1, std::min(g_cfg.host_threads, n_reads));
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-        work();
-        for (auto &t : pool) t.join();
-    }
-    for (int r = 0; r < n_reads; ++r) { // arena traffic stays on the calling thread
-        mm2gb_chain_read_t &rd = reads[r];
-        int32_t n_u = 0;
-        int64_t n_b = 0;
-        const uint64_t *src_u = nullptr;
-        const mm2gb_anchor_t *src_b = nullptr;
-        if (S.submitted && dev_nu) { n_u = dev_nu[r]; n_b = dev_nb[r]; src_u = dev_u[r]; src_b = dev_b[r]; }
-        else if (S.submitted) { n_u = S.s_nu[(size_t)r]; n_b = S.s_nb[(size_t)r]; src_u = S.su.data() + off[r]; src_b = S.sb.data() + off[r]; }
-        if (n_u > 0) {
+    int done_to = 0;
+    auto publish = [&](mm2gb_chain_read_t &rd, int32_t n_u, int32_t n_v, const uint64_t *src_u, const int32_t *src_v) {
+        if (n_u > 0) {   // arena traffic stays on the calling thread (kalloc is not thread-safe)
             uint64_t *u = (uint64_t *)kmalloc(km, (size_t)n_u * sizeof(uint64_t));
             memcpy(u, src_u, (size_t)n_u * sizeof(uint64_t));
-            mm2gb_anchor_t *b = (mm2gb_anchor_t *)kmalloc(km, (size_t)n_b * sizeof(mm2gb_anchor_t));
-            memcpy(b, src_b, (size_t)n_b * sizeof(mm2gb_anchor_t));
-            kfree(km, rd.a); // compact_a frees the oversized input array (lchain.c:107-109)
+            mm2gb_anchor_t *b = (mm2gb_anchor_t *)kmalloc(km, (size_t)n_v * sizeof(mm2gb_anchor_t));
+            mm2gb_gather_anchors(rd.a, src_v, n_v, b);   // lchain.c:100-105
+            kfree(km, rd.a);                             // compact_a frees the oversized input array (lchain.c:107-109)
             rd.a = b; rd.u = u; rd.n_u = n_u;
-        } else {             // lchain.c:212-215 / plchain.cu:135-143
+        } else {                                         // lchain.c:212-215 / plchain.cu:135-143
             kfree(km, rd.a);
             rd.a = nullptr; rd.u = nullptr; rd.n_u = 0;
         }
         post_chaining_helper(mi, opt, &rd, misc, km);
+    };
+    for (const Sub &sb : S.subs) {
+        const uint64_t *const *dev_u = nullptr;
+        const int32_t *dev_nu = nullptr, *dev_nv = nullptr;
+        const int32_t *const *dev_v = nullptr;
+        if (mm2gb_wait_chains(S.ctx, sb.slot, &dev_u, &dev_nu, &dev_v, &dev_nv, nullptr, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
+        long long down = 16LL * (sb.r1 - sb.r0 + 1) + 64;   // per-read counts / positions + the batch counters
+        for (int r = sb.r0; r < sb.r1; ++r) {
+            publish(reads[r], dev_nu[r - sb.r0], dev_nv[r - sb.r0], dev_u[r - sb.r0], dev_v[r - sb.r0]);
+            down += 8LL * dev_nu[r - sb.r0] + 4LL * dev_nv[r - sb.r0];
+        }
+        g_d2h_bytes += down;
+        done_to = sb.r1;
     }
+    for (int r = done_to; r < n_reads; ++r) publish(reads[r], 0, 0, nullptr, nullptr);   // a batch without anchors
     S.busy = false;
     S.reads = nullptr;
     S.n_reads = 0;
+    S.subs.clear();
 }
 
 } // namespace
@@ -230,46 +330,65 @@ extern "C" void init_stream_gpu(size_t *max_total_n, int *max_reads, int *min_n,
 extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt, mm2gb_chain_read_t **in_arr_, int *n_read_, int thread_id, void *km)
 {
     ThreadState &S = state_of(thread_id);
-    const Misc_abi misc = build_misc(mi, opt, 0, 1); // single segment, qlen_sum irrelevant (plchain.cu:498-500)
+    const Misc_abi misc = batch_misc(mi, opt);
     mm2gb_chain_read_t *in = in_arr_ ? *in_arr_ : nullptr;
     const int n_in = (n_read_ && in) ? *n_read_ : 0;
 
-    int64_t total = 0;
+    int64_t total = 0, longest = 0;
     S.ptrs.resize((size_t)n_in);
     S.ns.resize((size_t)n_in);
     for (int r = 0; r < n_in; ++r) {
+        if (in[r].n_seg > 1) {
+            fprintf(stderr, "[ERROR] mm2gb chaining: read %ld has %d segments; --gpu-chain chains single-segment reads only\n", in[r].seq.i, in[r].n_seg);
+            exit(1);
+        }
         S.ptrs[(size_t)r] = in[r].a;
         S.ns[(size_t)r] = in[r].a ? in[r].n : 0;
         total += S.ns[(size_t)r];
+        longest = std::max(longest, S.ns[(size_t)r]);
     }
-    // (re)size the context: first use, a batch beyond the configured limits, or new chaining parameters
-    const bool need_grow = !S.ctx || (size_t)total > S.cap_anchors || n_in > S.cap_reads;
+    // sub-batches: enough anchors each to fill the GPU, at most sub_batches of them
+    const int n_sub = (int)std::max<int64_t>(1, std::min<int64_t>(g_cfg.sub_batches, total / g_cfg.sub_min));
+    const int64_t target = total / n_sub + 1;
+    // (re)size the context: first use, a batch beyond the configured limits, or new chaining parameters.  A slot has to hold
+    // one sub-batch: its share of the batch plus the read that overshoots it.
+    const size_t need_slot = (size_t)(target + longest);
+    const bool need_grow = !S.ctx || need_slot > S.cap_anchors || n_in > S.cap_reads;
     const bool new_misc = S.ctx && !same_misc(S.misc, misc);
     mm2gb_chain_read_t *prev = S.busy ? S.reads : nullptr;
     const int n_prev = S.busy ? S.n_reads : 0;
     const bool had_prev = S.busy;
     if ((need_grow || new_misc) && S.busy) complete_inflight(S, mi, opt, S.misc, km); // old buffers / parameters still in use
     if (need_grow) {
-        size_t cap = std::max(g_cfg.max_total_n, (size_t)total + (size_t)total / 2);
+        // sized by the batch at hand, not by the configured limit: the driver fills its batches up to max_total_n, so the first
+        // batch of a thread already shows how large they are, and a thread that only ever sees small batches stays small
+        size_t cap = need_slot + need_slot / 4 + (size_t)longest + 4096;
         if (cap > ((size_t)1 << 31) - 2048) cap = ((size_t)1 << 31) - 2048;
-        if ((size_t)total > cap) { fprintf(stderr, "[ERROR] mm2gb chaining: a batch of %lld anchors cannot be indexed with 31 bits\n", (long long)total); exit(1); }
+        if (need_slot > cap) { fprintf(stderr, "[ERROR] mm2gb chaining: a sub-batch of %zu anchors cannot be indexed with 31 bits\n", need_slot); exit(1); }
         make_ctx(S, cap, std::max(g_cfg.max_read, n_in + n_in / 2) + 1, misc);
     } else if (new_misc) {
         if (mm2gb_ctx_set_misc(S.ctx, &misc) != MM2GB_OK) die("updating the chaining parameters");
         S.misc = misc;
     }
     // launch the new batch first, so the device works while this thread finishes the previous one
-    const int slot = S.busy ? (S.slot + 1) % g_cfg.n_slots : 0;
-    bool submitted = false;
+    const int half = S.busy ? 1 - S.half : 0;
+    std::vector<Sub> subs;
     if (in && total > 0) {
-        const int rc = g_cfg.host_backtrack ? mm2gb_submit_gather(S.ctx, slot, S.ptrs.data(), S.ns.data(), n_in)
-                                            : mm2gb_submit_gather_chains(S.ctx, slot, S.ptrs.data(), S.ns.data(), n_in);
-        if (rc != MM2GB_OK) die("launching a chaining batch");
-        submitted = true;
+        int r0 = 0;
+        for (int k = 0; k < n_sub && r0 < n_in; ++k) {
+            int r1 = r0;
+            int64_t cnt = 0;
+            while (r1 < n_in && (k == n_sub - 1 || cnt < target)) cnt += S.ns[(size_t)r1++];   // every sub-batch but the last reaches the target: the last is not above it
+            const int slot = half * g_cfg.sub_batches + k;
+            if (mm2gb_submit_gather_chains(S.ctx, slot, S.ptrs.data() + r0, S.ns.data() + r0, r1 - r0) != MM2GB_OK) die("launching a chaining batch");
+            g_h2d_bytes += mm2gb_last_upload_bytes(S.ctx, slot) + 8LL * (r1 - r0 + 1) + 4LL * (r1 - r0);   // anchors + offsets + class lists
+            subs.push_back({slot, r0, r1});
+            r0 = r1;
+        }
     }
     if (S.busy) complete_inflight(S, mi, opt, misc, km);
     if (in) {
-        S.busy = true; S.reads = in; S.n_reads = n_in; S.slot = slot; S.submitted = submitted;
+        S.busy = true; S.reads = in; S.n_reads = n_in; S.half = half; S.subs.swap(subs);
     }
     if (in_arr_) *in_arr_ = had_prev ? prev : nullptr;
     if (n_read_) *n_read_ = had_prev ? n_prev : 0;
@@ -285,7 +404,7 @@ extern "C" void finish_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *o
     }
     mm2gb_chain_read_t *prev = S.reads;
     const int n_prev = S.n_reads;
-    const Misc_abi misc = build_misc(mi, opt, 0, 1);
+    const Misc_abi misc = batch_misc(mi, opt);
     complete_inflight(S, mi, opt, misc, km);
     if (reads_) *reads_ = prev;
     if (n_read_) *n_read_ = n_prev;
@@ -295,11 +414,31 @@ extern "C" void free_stream_gpu(int n_threads)
 {
     (void)n_threads;
     std::lock_guard<std::mutex> lk(g_mu);
-    for (int t = 0; t < kMaxThreads; ++t) {
-        if (!g_state[t]) continue;
-        if (g_state[t]->ctx) mm2gb_ctx_destroy(g_state[t]->ctx);
-        delete g_state[t];
-        g_state[t] = nullptr;
+    for (ThreadState *&st : g_state) {
+        if (!st) continue;
+        if (st->ctx) mm2gb_ctx_destroy(st->ctx);
+        delete st;
+        st = nullptr;
     }
+    g_state.clear();
     g_inited = false;
+}
+
+// test hook: parse a gpu config text the way init_stream_gpu does; returns 1 and the value if `key` is a numeric member of the
+// top-level object, 0 if it is not there, -1 if the text is not valid JSON
+extern "C" int mm2gb_dropin_parse_config_key(const char *text, const char *key, double *out)
+{
+    JsonReader js;
+    if (!js.parse(text ? text : "")) return -1;
+    double v;
+    if (!js.get(key, &v)) return 0;
+    if (out) *out = v;
+    return 1;
+}
+
+// bytes moved host -> device (out[0]) and device -> host (out[1]) by the boundary since the last reset
+extern "C" void mm2gb_dropin_traffic(long long out[2], int reset)
+{
+    if (out) { out[0] = g_h2d_bytes.load(); out[1] = g_d2h_bytes.load(); }
+    if (reset) { g_h2d_bytes = 0; g_d2h_bytes = 0; }
 }

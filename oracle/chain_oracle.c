@@ -339,3 +339,57 @@ int64_t orc_lchain_batch(const orc_params_t *prm, const orc_anchor_t *a, const i
     free(tid); free(jobs);
     return total;
 }
+
+/* ---- per-read digests of the whole mg_lchain_dp result, for parity checks at benchmark scale ------------------------
+ * digest(w[0..m)) = C (m + 1) + sum_k w[k] (2k + 1) C  (mod 2^64), C = 0x9E3779B97F4A7C15: order-sensitive, cheap to restate
+ * (tests/fake_host.c: fake_digest, bench.py: digest).  For read sel[k]: n_u, number of chain anchors, digest of u[] and of
+ * the compacted anchors as 2 n_b words. */
+static uint64_t orc_digest(const uint64_t *w, int64_t n)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ULL * (uint64_t)(n + 1);
+    int64_t k;
+    for (k = 0; k < n; ++k) h += w[k] * ((2 * (uint64_t)k + 1) * 0x9E3779B97F4A7C15ULL);
+    return h;
+}
+
+typedef struct {
+    const orc_params_t *prm; const orc_anchor_t *a; const int64_t *off, *sel; int64_t n_sel; int64_t *next;
+    int32_t *nu; int64_t *nb; uint64_t *hu, *hb;
+} orc_djob_t;
+
+static void *orc_digest_worker(void *arg)
+{
+    orc_djob_t *jb = (orc_djob_t *)arg;
+    for (;;) {
+        int64_t k = __sync_fetch_and_add(jb->next, 1), r, n, nb = 0, np = 0;
+        int32_t nu = 0;
+        uint64_t *u;
+        orc_anchor_t *b;
+        if (k >= jb->n_sel) break;
+        r = jb->sel[k];
+        n = jb->off[r + 1] - jb->off[r];
+        u = (uint64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(*u));
+        b = (orc_anchor_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(*b));
+        if (n > 0) nu = orc_lchain(jb->prm, n, jb->a + jb->off[r], u, b, &nb, 0, 0, &np);
+        jb->nu[k] = nu; jb->nb[k] = nb;
+        jb->hu[k] = orc_digest(u, nu); jb->hb[k] = orc_digest((const uint64_t *)b, 2 * nb);
+        free(u); free(b);
+    }
+    return 0;
+}
+
+void orc_lchain_digest_batch(const orc_params_t *prm, const orc_anchor_t *a, const int64_t *off, const int64_t *sel, int64_t n_sel,
+                             int n_threads, int32_t *nu, int64_t *nb, uint64_t *hu, uint64_t *hb)
+{
+    int64_t next = 0;
+    int i;
+    pthread_t *tid;
+    orc_djob_t jb;
+    if (n_threads < 1) n_threads = 1;
+    jb.prm = prm, jb.a = a, jb.off = off, jb.sel = sel, jb.n_sel = n_sel, jb.next = &next;
+    jb.nu = nu, jb.nb = nb, jb.hu = hu, jb.hb = hb;
+    tid = (pthread_t *)malloc((size_t)n_threads * sizeof(*tid));
+    for (i = 0; i < n_threads; ++i) pthread_create(&tid[i], 0, orc_digest_worker, &jb);
+    for (i = 0; i < n_threads; ++i) pthread_join(tid[i], 0);
+    free(tid);
+}

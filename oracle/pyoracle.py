@@ -217,6 +217,40 @@ def lchain_batch(prm: Params, a, off, r0=0, r1=None, n_threads=1, want_fp=False,
     return int(pairs), f, p
 
 
+DIGEST_C = 0x9E3779B97F4A7C15
+
+
+def digest(w) -> int:
+    """order-sensitive 64-bit digest of a word array: C (m + 1) + sum_k w[k] (2k + 1) C  mod 2^64 (chain_oracle.c: orc_digest)"""
+    w = np.ascontiguousarray(w, np.uint64).reshape(-1)
+    k = np.arange(len(w), dtype=np.uint64)
+    c = np.uint64(DIGEST_C)
+    with np.errstate(over="ignore"):
+        return int(c * np.uint64(len(w) + 1) + (w * ((np.uint64(2) * k + np.uint64(1)) * c)).sum(dtype=np.uint64))
+
+
+def lchain_digests(prm: Params, a, off, sel, n_threads=1, use_ref=False):
+    """Whole mg_lchain_dp of the reads `sel` on n_threads host threads; per read (n_u, n_b, digest(u), digest(b)).
+    use_ref: the reference's own lchain.c (oracle/_ref), else the restatement."""
+    a = _anchors(a)
+    off = np.ascontiguousarray(off, np.int64)
+    sel = np.ascontiguousarray(sel, np.int64)
+    m = len(sel)
+    nu = np.zeros(m, np.int32); nb = np.zeros(m, np.int64); hu = np.zeros(m, np.uint64); hb = np.zeros(m, np.uint64)
+    if use_ref:
+        r = ref()
+        r.ref_lchain_digest_batch.restype = None
+        r.ref_lchain_digest_batch.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 4
+        fn = r.ref_lchain_digest_batch
+    else:
+        L = lib()
+        L.orc_lchain_digest_batch.restype = None
+        L.orc_lchain_digest_batch.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 4
+        fn = L.orc_lchain_digest_batch
+    fn(C.byref(prm), a.ctypes.data, off.ctypes.data, sel.ctypes.data, m, n_threads, nu.ctypes.data, nb.ctypes.data, hu.ctypes.data, hb.ctypes.data)
+    return nu, nb, hu, hb
+
+
 def read_dump(path: str):
     """Anchor dump written by oracle/dump_stub.c: (Params, [ (n_seg, qlen_sum, anchors uint64[n,2]) ... ])."""
     with open(path, "rb") as fh:

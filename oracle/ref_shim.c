@@ -172,3 +172,53 @@ void ref_lchain_batch(const ref_params_t *prm, const mm128_t *a, const int64_t *
     for (i = 0; i < n_threads; ++i) pthread_join(tid[i], 0);
     free(tid);
 }
+
+/* per-read digests of the REFERENCE's whole mg_lchain_dp result (same digest as chain_oracle.c: orc_lchain_digest_batch) */
+static uint64_t ref_digest(const uint64_t *w, int64_t n)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ULL * (uint64_t)(n + 1);
+    int64_t k;
+    for (k = 0; k < n; ++k) h += w[k] * ((2 * (uint64_t)k + 1) * 0x9E3779B97F4A7C15ULL);
+    return h;
+}
+typedef struct {
+    const ref_params_t *prm; const mm128_t *a; const int64_t *off, *sel; int64_t n_sel; int64_t *next;
+    int32_t *nu; int64_t *nb; uint64_t *hu, *hb;
+} ref_djob_t;
+static void *ref_digest_worker(void *arg)
+{
+    ref_djob_t *jb = (ref_djob_t *)arg;
+    for (;;) {
+        int64_t k = __sync_fetch_and_add(jb->next, 1), r, n, nb = 0;
+        int32_t nu = 0;
+        uint64_t *u;
+        mm128_t *b;
+        if (k >= jb->n_sel) break;
+        r = jb->sel[k];
+        n = jb->off[r + 1] - jb->off[r];
+        u = (uint64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(*u));
+        b = (mm128_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(*b));
+        if (n > 0) nu = ref_lchain(jb->prm, n, jb->a + jb->off[r], u, b, &nb, 0, 0);
+        jb->nu[k] = nu; jb->nb[k] = nb;
+        jb->hu[k] = ref_digest(u, nu); jb->hb[k] = ref_digest((const uint64_t *)b, 2 * nb);
+        free(u); free(b);
+    }
+    free(g_log); free(g_dead);
+    g_log = 0, g_dead = 0, g_m = g_md = 0;
+    return 0;
+}
+void ref_lchain_digest_batch(const ref_params_t *prm, const mm128_t *a, const int64_t *off, const int64_t *sel, int64_t n_sel,
+                             int n_threads, int32_t *nu, int64_t *nb, uint64_t *hu, uint64_t *hb)
+{
+    int64_t next = 0;
+    int i;
+    pthread_t *tid;
+    ref_djob_t jb;
+    if (n_threads < 1) n_threads = 1;
+    jb.prm = prm, jb.a = a, jb.off = off, jb.sel = sel, jb.n_sel = n_sel, jb.next = &next;
+    jb.nu = nu, jb.nb = nb, jb.hu = hu, jb.hb = hb;
+    tid = (pthread_t *)malloc((size_t)n_threads * sizeof(*tid));
+    for (i = 0; i < n_threads; ++i) pthread_create(&tid[i], 0, ref_digest_worker, &jb);
+    for (i = 0; i < n_threads; ++i) pthread_join(tid[i], 0);
+    free(tid);
+}

@@ -2,6 +2,9 @@
 with a fake host (tests/fake_host.c) that supplies kmalloc/kfree/build_misc/post_chaining_helper."""
 import ctypes as C
 import os
+import subprocess
+import sys
+import textwrap
 
 import numpy as np
 import pytest
@@ -35,6 +38,39 @@ def test_dropin_exports_reference_symbols():
     for name in ("init_stream_gpu", "chain_stream_gpu", "finish_stream_gpu", "free_stream_gpu"):
         assert hasattr(L, name), name
     L.free_stream_gpu(1)   # never initialised: must be a no-op (main.c:466 calls it unconditionally)
+
+
+def test_gpu_config_is_parsed_as_json():
+    """--gpu-cfg is real JSON (the reference parses it with cJSON, gpu/plmem.cu:373-451): only numeric members of the TOP-LEVEL
+    object count; same-named keys inside nested objects, comment keys with string values and strings are skipped"""
+    L = C.CDLL(SO)
+    L.mm2gb_dropin_parse_config_key.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
+
+    def get(text, key):
+        v = C.c_double(-1.0)
+        rc = L.mm2gb_dropin_parse_config_key(text.encode(), key.encode(), C.byref(v))
+        return rc, v.value
+
+    ref_cfg = """{
+        "num_streams": 1, "//num_streams": "Must set to 1", "min_n": 512,
+        "//min_n": "queries with less anchors will be handled on cpu: \\"max_total_n\\": 7",
+        "max_total_n": 500000000, "max_read": 500000,
+        "range_kernel": {"blockdim": 512, "max_total_n": 1, "nested": {"max_read": 2, "list": [1, 2, {"min_n": 3}]}},
+        "score_kernel": {"micro_batch": 4, "//micro_batch": "text", "mid_blockdim": 512},
+        "flags": [true, false, null, -1.5e3], "n_gpus": 2
+    }"""
+    assert get(ref_cfg, "max_total_n") == (1, 500000000.0)
+    assert get(ref_cfg, "max_read") == (1, 500000.0)
+    assert get(ref_cfg, "min_n") == (1, 512.0)
+    assert get(ref_cfg, "n_gpus") == (1, 2.0)
+    assert get(ref_cfg, "blockdim")[0] == 0 and get(ref_cfg, "micro_batch")[0] == 0      # nested: not ours
+    assert get(ref_cfg, "//min_n")[0] == 0                                                # a string, not a number
+    assert get("{}", "max_total_n")[0] == 0
+    for bad in ("{", '{"a": }', '{"a": 1,}', '{"a" 1}', '{"a": 1} x', '["max_total_n", 5'):
+        assert get(bad, "a")[0] == -1, bad
+    # the reference's own config file format, as shipped (copied as a fixture string: keys with "//" comments, nested kernels)
+    here = os.path.join(ROOT, "mm2-gb_b200", "b200_config.json")
+    assert get(open(here).read(), "max_total_n") == (1, 16777216.0)
 
 
 def _lib(pkg):
@@ -89,7 +125,8 @@ def test_batch_handoff_protocol(pkg, po, synth, tmp_path):
     L = _lib(pkg)
     cfg = tmp_path / "cfg.json"
     cfg.write_text('{"num_streams": 1, "min_n": 512, "max_total_n": 300000, "max_read": 500, "host_threads": 4,\n'
-                   ' "range_kernel": {"blockdim": 512}, "score_kernel": {"micro_batch": 4}}')
+                   ' "range_kernel": {"blockdim": 512, "max_total_n": 5}, "score_kernel": {"micro_batch": 4}}')
+    os.environ["MM2GB_SUB_MIN"] = "20000"     # small batches are cut into sub-batches too (default: 512 k anchors each at least)
     misc = pkg.map_ont_misc()
     prm = po.map_ont_params()
     L.fake_set_misc(C.byref(misc))
@@ -132,3 +169,85 @@ def test_batch_handoff_protocol(pkg, po, synth, tmp_path):
     assert L.fake_live_blocks() == 0                        # no arena leak, no double free
     L.free_stream_gpu(2)
     L.free_stream_gpu(2)
+    del os.environ["MM2GB_SUB_MIN"]
+
+
+def _digest(w):
+    """fake_digest of tests/fake_host.c"""
+    w = np.ascontiguousarray(w, np.uint64).reshape(-1)
+    k = np.arange(len(w), dtype=np.uint64)
+    c = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        return int((c * np.uint64(len(w) + 1) + (w * ((np.uint64(2) * k + np.uint64(1)) * c)).sum(dtype=np.uint64)) & np.uint64(0xFFFFFFFFFFFFFFFF))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_threads,batch_anchors,sync", [(1, 1 << 30, 1), (3, 150000, 1), (4, 60000, 0)])
+def test_driver_call_pattern_many_threads(pkg, po, synth, tmp_path, n_threads, batch_anchors, sync):
+    """fake_drive = the call pattern of `minimap2 -t T --gpu-chain` (what bench.py's end-to-end leg times): T worker threads,
+    per-read kmalloc'd anchor arrays, chain_stream_gpu per batch, finish_stream_gpu per mini-batch.  Every read's chains and
+    compacted anchors (digests) equal the oracle's whole mg_lchain_dp."""
+    L = _lib(pkg)
+    L.fake_drive.restype = C.c_double
+    L.fake_drive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_void_p]
+    cfg = tmp_path / "cfg.json"
+    cfg.write_text('{"max_total_n": 400000, "max_read": 5000}')
+    os.environ["MM2GB_SUB_MIN"] = "30000"
+    misc = pkg.map_ont_misc()
+    prm = po.map_ont_params()
+    L.fake_set_misc(C.byref(misc))
+    mx, mr, mn = C.c_size_t(0), C.c_int(0), C.c_int(-1)
+    L.init_stream_gpu(C.byref(mx), C.byref(mr), C.byref(mn), str(cfg).encode(), misc)
+    a, off = synth.ont_like_batch(300 + n_threads, 150, 1, 4000, repeat_copies=2, repeat_len=40)
+    n_reads = len(off) - 1
+    nu = np.zeros(n_reads, np.int32); nb = np.zeros(n_reads, np.int64)
+    hu = np.zeros(n_reads, np.uint64); hb = np.zeros(n_reads, np.uint64)
+    helper0, live0 = L.fake_helper_calls(), L.fake_live_blocks()
+    dt = L.fake_drive(a.ctypes.data, off.ctypes.data, n_reads, n_threads, 0, 3, batch_anchors, sync, nu.ctypes.data, nb.ctypes.data,
+                      hu.ctypes.data, hb.ctypes.data)
+    assert dt > 0
+    assert L.fake_helper_calls() - helper0 == 3 * n_reads and L.fake_live_blocks() == live0
+    for r in range(n_reads):
+        o = po.oracle_lchain(prm, a[int(off[r]):int(off[r + 1])])
+        assert nu[r] == len(o.u) and nb[r] == len(o.b), r
+        assert int(hu[r]) == _digest(o.u) and int(hb[r]) == _digest(o.b), r
+    L.free_stream_gpu(n_threads)
+    del os.environ["MM2GB_SUB_MIN"]
+
+
+_GUARD = """
+import ctypes as C, os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import __graft_entry__ as entry
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+import test_dropin as T
+pkg = entry.load_package()
+L = T._lib(pkg)
+L.fake_set_misc_depends_on_qlen.argtypes = [C.c_int]
+misc = pkg.map_ont_misc()
+L.fake_set_misc(C.byref(misc))
+mx, mr, mn = C.c_size_t(0), C.c_int(0), C.c_int(-1)
+L.init_stream_gpu(C.byref(mx), C.byref(mr), C.byref(mn), b"", misc)
+from mm2gb_b200 import synth
+a, off = synth.ont_like_batch(1, 3, 50, 200)
+arr = T._make_batch(L, a, off)
+if {mode!r} == "qlen":
+    L.fake_set_misc_depends_on_qlen(1)
+else:
+    arr[1].n_seg = 2
+ptr = C.cast(arr, C.POINTER(T.ChainRead)); n = C.c_int(3)
+L.chain_stream_gpu(None, None, C.byref(ptr), C.byref(n), 0, None)
+print("NOT REACHED")
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,msg", [("qlen", "depend on the read length"), ("nseg", "single-segment reads only")])
+def test_unsupported_modes_fail_loudly(mode, msg):
+    """plchain.cu:497 guards the single-segment assumption with an assert that release builds drop; here a preset whose
+    chaining parameters depend on the read (short-read / fragment mode) or a multi-segment read ends the run with a message"""
+    out = subprocess.run([sys.executable, "-c", textwrap.dedent(_GUARD.format(root=ROOT, mode=mode))], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 1, out.stderr[-400:]
+    assert msg in out.stderr and "NOT REACHED" not in out.stdout

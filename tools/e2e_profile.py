@@ -17,8 +17,8 @@ def main():
     cap = int(os.environ.get("CAP", "0")) or max(n, 1 << 20)
     ctx = pkg.ChainContext(pkg.map_ont_misc(), device=0, max_anchors=cap, max_reads=n_reads + 1, n_slots=int(os.environ.get("SLOTS", "3")))
     h_a = torch.from_numpy(a.view(np.int64)).pin_memory()
-    out = {"u": np.empty(n, np.uint64), "b": torch.empty((n, 2), dtype=torch.int64).pin_memory(),
-           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "b_pos": np.zeros(n_reads, np.int64)}
+    out = {"u": np.empty(n, np.uint64), "v": torch.empty(n, dtype=torch.int32).pin_memory(),
+           "n_u": np.zeros(n_reads, np.int32), "n_b": np.zeros(n_reads, np.int64), "v_pos": np.zeros(n_reads, np.int64)}
     for _ in range(2):
         ctx.chain(h_a, off, out=out, packed=True)
     ctx.profile(True)
