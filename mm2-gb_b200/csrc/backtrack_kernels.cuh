@@ -1448,23 +1448,25 @@ constexpr int kDrainThreads = 64;   // small CTAs (2 warps x 32 registers) fit n
 
 // Packed results -> (mapped, pinned) host memory.  The amounts are only known on the device (the cursors), so this is a
 // kernel rather than a copy-engine transfer of the worst case: a few CTAs keep enough 16-byte stores in flight for PCIe.
-// src_v / dst_v are 16-byte aligned (the same index on both sides), so the body moves four indices per store.
+// The indices occupy [first, b_cur) of src_v and go to the same positions of dst_v; both bases are 16-byte aligned (the
+// device packs from `first` = the misalignment of the landing area on), so the body moves four indices per store.
 __global__ void __launch_bounds__(kDrainThreads)
-k_drain(const int *__restrict__ src_v, int *__restrict__ dst_v, const unsigned long long *__restrict__ src_u,
+k_drain(const int *__restrict__ src_v, int *__restrict__ dst_v, int first, const unsigned long long *__restrict__ src_u,
         unsigned long long *__restrict__ dst_u, const Counters *__restrict__ ctr)
 {
     const long long nb = ctr->b_cur, nu = ctr->u_cur;
     const long long stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nq = nb >> 2;
+    const long long q0 = first ? 1 : 0, nq = nb >> 2;     // whole 16-byte groups [q0, nq)
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src_v);
     uint4 *d4 = reinterpret_cast<uint4 *>(dst_v);
-    long long i = t;
+    if (first && t < 4 && t >= first && t < nb) dst_v[t] = __ldg(src_v + t);   // the partial first group
+    long long i = q0 + t;
     for (; i + 3 * stride < nq; i += 4 * stride) {
         const uint4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + stride), v2 = __ldg(s4 + i + 2 * stride), v3 = __ldg(s4 + i + 3 * stride);
         d4[i] = v0; d4[i + stride] = v1; d4[i + 2 * stride] = v2; d4[i + 3 * stride] = v3;
     }
     for (; i < nq; i += stride) d4[i] = __ldg(s4 + i);
-    for (long long k = (nq << 2) + t; k < nb; k += stride) dst_v[k] = __ldg(src_v + k);
+    for (long long k = max(nq << 2, (long long)(first ? 4 : 0)) + t; k < nb; k += stride) dst_v[k] = __ldg(src_v + k);
     for (long long k = t; k < nu; k += stride) dst_u[k] = __ldg(src_u + k);
 }
 

@@ -144,6 +144,8 @@ struct Slot {
     std::vector<const uint64_t *> u_ptr;     // per read: its chains (in h_upack)
     std::vector<const int32_t *> v_ptr;      // per read: the indices of its compacted anchors (in the packed landing buffer)
     long long b_total = 0;                   // indices in the packed landing buffer
+    int v_mis = 0;                           // land_v is this many entries past a 16-byte boundary: the device packs its indices from
+                                             // position v_mis on, so that k_drain moves aligned 16-byte pieces on both sides
     int wire_runs = 0;                       // runs of the packed upload of the batch in flight (0: raw upload)
     size_t up_bytes = 0;                     // bytes of anchor data uploaded for the batch in flight
 };
@@ -490,6 +492,7 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
     CK(cudaMemsetAsync(sl.d_nu, 0xff, rs * sizeof(int), s));   // -1 = not finished (must not survive the overflow pass)
     CK(cudaMemsetAsync(sl.d_nb, 0, 3 * rs * sizeof(int), s));
     CK(cudaMemsetAsync(&sl.d_ctr->ovf_cnt, 0, 3 * sizeof(int), s));   // ovf_cnt, u_cur, b_cur
+    if (sl.v_mis) CK(cudaMemsetAsync(&sl.d_ctr->b_cur, sl.v_mis, 1, s));   // low byte (little endian): b_cur = v_mis
     BtParams bp;
     bp.min_cnt = c->misc.min_cnt;
     // scores are never negative (f[i] >= q_span(i) >= 0, lchain.c:171) and an accepted chain has a positive score, so a negative
@@ -532,7 +535,7 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
 // packed results of the batch -> mapped pinned host memory (dst_v: device view of where the chain-anchor indices land)
 static int enqueue_drain(mm2gb_ctx *c, Slot &sl, cudaStream_t s, int *dst_v)
 {
-    k_drain<<<c->drain_blocks, kDrainThreads, 0, s>>>(sl.d_vp, dst_v, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
+    k_drain<<<c->drain_blocks, kDrainThreads, 0, s>>>(sl.d_vp, dst_v - sl.v_mis, sl.v_mis, sl.d_upack, sl.h_upack_dev, sl.d_ctr);
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
@@ -765,7 +768,8 @@ static int stage_anchors(mm2gb_ctx *c, Slot &s, const Source &src, const long lo
         return MM2GB_OK;
     }
     if (c->wire_mode != 1) {
-        const WireLayout L = wire_layout(n_total, c->stage_bytes);
+        // worth it only while the run list stays small: at most 12 of the raw format's 16 bytes per anchor
+        const WireLayout L = wire_layout(n_total, std::min(c->stage_bytes, (size_t)n_total * 12));
         if (L.run_cap >= 1) {
             WirePacker pk;
             pk.begin(s.h_a, L);
@@ -831,13 +835,14 @@ static int submit_impl(mm2gb_ctx *c, int si, const Source &src, const long long 
     s.chains = w.chains;
     s.want_fp = w.fp;
     slice_rinfo(s, n_reads);
+    s.land_v = (w.chains && w.dst_v && w.dst_v_dev) ? w.dst_v : s.h_vp;
+    s.v_mis = (int)((reinterpret_cast<uintptr_t>(s.land_v) >> 2) & 3);
     if (w.chains && n_total) {
         rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, n_reads, s.d_f, s.d_p, prof);
         if (rc) return rc;
     }
     s.direct_out = w.fp && w.dst_pinned && w.dst_f && w.dst_p;
     s.user_f = w.dst_f; s.user_p = w.dst_p;
-    s.land_v = (w.chains && w.dst_v && w.dst_v_dev) ? w.dst_v : s.h_vp;
     {
         ProfScope ps(c, T_D2H, s.stream, prof);
         if (n_total && w.fp) {
@@ -951,10 +956,11 @@ static int finish_chains(mm2gb_ctx *c, Slot &s)
     s.v_ptr.assign((size_t)n_reads, nullptr);
     s.b_total = 0;
     if (!s.n_total) { for (int r = 0; r < n_reads; ++r) s.h_nu[r] = s.h_nb[r] = s.h_bpos[r] = 0; return MM2GB_OK; }
-    s.b_total = s.h_ctr->b_cur;
+    s.b_total = s.h_ctr->b_cur - s.v_mis;
     for (int r = 0; r < n_reads; ++r) {
         if (s.h_nu[r] < 0) return fail(MM2GB_ECUDA, "device chain extraction left read %d of the batch unfinished", r);
         s.u_ptr[(size_t)r] = reinterpret_cast<const uint64_t *>(s.h_upack) + s.h_upos[r];
+        s.h_bpos[r] -= s.v_mis;     // positions relative to land_v
         s.v_ptr[(size_t)r] = s.land_v + s.h_bpos[r];
     }
     return MM2GB_OK;
@@ -1295,11 +1301,12 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
         CK(cudaMemcpyAsync(s.d_f, s.h_f, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.d_p, s.h_p, (size_t)n_total * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), s.stream));
+        s.land_v = s.h_vp;
+        s.v_mis = 0;
         int rc = prepare_backtrack(s, s.stream, s.h_off, n_reads);
         if (rc) return rc;
         rc = enqueue_backtrack(c, s, s.stream, s.d_a, s.d_off, n_reads, s.d_f, s.d_p, false);
         if (rc) return rc;
-        s.land_v = s.h_vp;
         rc = enqueue_drain(c, s, s.stream, s.h_vp_dev);
         if (rc) return rc;
         CK(cudaMemcpyAsync(s.h_rinfo, s.d_rinfo, 4 * ((size_t)n_reads + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
@@ -1344,6 +1351,7 @@ extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d
     int rc = mm2gb_chain_dp_device(c, d_a, d_off, n_reads, n_total, d_f, d_p);
     if (rc || n_total == 0) return rc;
     Slot &s = c->slot[0];
+    s.v_mis = 0;
     rc = prepare_backtrack(s, s.stream, (const long long *)off, n_reads);
     if (rc) return rc;
     return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, (const int *)d_f, (const int *)d_p, c->profile);
@@ -1372,7 +1380,7 @@ extern "C" int mm2gb_debug_drain(mm2gb_ctx_t *c, int64_t n, int blocks, float ms
             CK(cudaDeviceSynchronize());
             CK(cudaEventRecord(e0, s.stream));
             CK(cudaStreamWaitEvent(s2, e0, 0));
-            if (mode == 0 || mode == 2) k_drain<<<blocks, kDrainThreads, 0, s.stream>>>(s.d_vp, s.h_vp_dev, s.d_upack, s.h_upack_dev, s.d_ctr);
+            if (mode == 0 || mode == 2) k_drain<<<blocks, kDrainThreads, 0, s.stream>>>(s.d_vp, s.h_vp_dev, 0, s.d_upack, s.h_upack_dev, s.d_ctr);
             if (mode == 1 || mode == 3) CK(cudaMemcpyAsync(s.h_vp, s.d_vp, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
             if (mode >= 2) CK(cudaMemcpyAsync(s.d_a, s.h_a, (size_t)n * 4, cudaMemcpyHostToDevice, s2));
             CK(cudaEventRecord(e2, s2));
