@@ -38,7 +38,7 @@ namespace {
 constexpr int kMaxSub = 4;          // sub-batches of one batch (2 batches in flight x 4 = the 8 slots of a context)
 
 struct Config {
-    size_t max_total_n = 16u << 20; // anchors per launched batch
+    size_t max_total_n = 2u << 20;  // anchors per launched batch
     int max_read = 200000;          // reads per batch
     int min_n = 0;                  // plumbed through, unused downstream (map.c:1314)
     int n_gpus = 0;                 // 0 = all visible

@@ -139,7 +139,22 @@ void wire_gather(const mm2gb_anchor_t *a, const int32_t *v, int64_t n, mm2gb_anc
 {
     int64_t k = 0;
 #if defined(__x86_64__)
-    for (; k + 4 <= n; k += 4) {   // four independent 16-byte moves in flight
+    if ((reinterpret_cast<uintptr_t>(b) & 15) == 0 && n >= 64) {
+        // non-temporal stores: the result array is written once here and read much later by the driver, so it should not pull
+        // its own cache lines in first (read-for-ownership) nor push the source lines out
+        for (; k + 4 <= n; k += 4) {   // four independent 16-byte moves in flight
+            const __m128i t0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k]));
+            const __m128i t1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k + 1]));
+            const __m128i t2 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k + 2]));
+            const __m128i t3 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k + 3]));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(b + k), t0);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(b + k + 1), t1);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(b + k + 2), t2);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(b + k + 3), t3);
+        }
+        _mm_sfence();
+    }
+    for (; k + 4 <= n; k += 4) {
         const __m128i t0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k]));
         const __m128i t1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k + 1]));
         const __m128i t2 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(a + v[k + 2]));

@@ -6,6 +6,7 @@
  * T worker threads, each accumulating its own batch of seeded reads (per-read kmalloc'd anchor arrays), launching it with
  * chain_stream_gpu(thread_id) and flushing with finish_stream_gpu at the end of every mini-batch. */
 #define _GNU_SOURCE
+#include <malloc.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,18 +24,30 @@ void fake_set_misc_depends_on_qlen(int on) { g_misc_depends_on_qlen = on; }
 long fake_live_blocks(void) { return __atomic_load_n(&g_live, __ATOMIC_RELAXED); }
 long fake_helper_calls(void) { return __atomic_load_n(&g_helper_calls, __ATOMIC_RELAXED); }
 
+/* km == NULL: plain malloc (the protocol tests count the blocks).  km != NULL: a per-thread arena that, like kalloc
+ * (kalloc.c:71-145), hands out pieces of memory it already owns -- no system call and no page fault per request; the driver
+ * recycles its arenas once a mini-batch has been written out, fake_drive resets them at the start of every mini-batch. */
+typedef struct { char *base; size_t cap, used; } fake_arena_t;
+
 void *kmalloc(void *km, size_t size)
 {
-    (void)km;
     if (size == 0) return 0; /* kalloc.c returns NULL for empty requests */
     __atomic_add_fetch(&g_live, 1, __ATOMIC_RELAXED);
+    if (km) {
+        fake_arena_t *ar = (fake_arena_t *)km;
+        const size_t need = (size + 15) & ~(size_t)15;   /* kalloc's unit is 16 bytes */
+        if (ar->used + need <= ar->cap) { void *p = ar->base + ar->used; ar->used += need; return p; }
+    }
     return malloc(size);
 }
 void kfree(void *km, void *ptr)
 {
-    (void)km;
     if (!ptr) return;
     __atomic_sub_fetch(&g_live, 1, __ATOMIC_RELAXED);
+    if (km) {
+        fake_arena_t *ar = (fake_arena_t *)km;
+        if ((char *)ptr >= ar->base && (char *)ptr < ar->base + ar->cap) return;   /* recycled with the arena */
+    }
     free(ptr);
 }
 Misc_abi build_misc(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt, const int64_t qlen_sum, const int n_seg)
@@ -75,6 +88,7 @@ typedef struct {
     int n_batches;              /* per step */
     fake_batch_t *batches;      /* [steps][n_batches] */
     pthread_barrier_t *bar;
+    fake_arena_t arena;         /* where the results of this thread's reads go (u, a') */
 } fake_worker_t;
 
 static void *fake_worker(void *arg)
@@ -82,16 +96,17 @@ static void *fake_worker(void *arg)
     fake_worker_t *w = (fake_worker_t *)arg;
     pthread_barrier_wait(w->bar);       /* start of the timed region */
     for (int s = 0; s < w->steps; ++s) {
+        w->arena.used = 0;              /* the previous mini-batch has been written out: its arena is recycled */
         for (int b = 0; b < w->n_batches; ++b) {
             fake_batch_t *fb = &w->batches[s * w->n_batches + b];
             mm2gb_chain_read_t *ptr = fb->reads;
             int n = fb->n;
-            chain_stream_gpu(0, 0, &ptr, &n, w->tid, 0);   /* map.c:1026: hands back the batch launched before (results are in its reads) */
+            chain_stream_gpu(0, 0, &ptr, &n, w->tid, &w->arena);   /* map.c:1026: hands back the batch launched before (results are in its reads) */
         }
         {   /* kt_for's flush call at the end of the mini-batch (kthread.c:52-55 -> map.c:1069) */
             mm2gb_chain_read_t *ptr = 0;
             int n = 0;
-            finish_stream_gpu(0, 0, &ptr, &n, w->tid, 0);
+            finish_stream_gpu(0, 0, &ptr, &n, w->tid, &w->arena);
         }
         if (w->sync_steps) pthread_barrier_wait(w->bar);   /* kt_for joins its workers before the next mini-batch */
     }
@@ -112,6 +127,12 @@ double fake_drive(const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int 
 {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n_reads && n_reads > 0) n_threads = n_reads;
+    /* kalloc hands out pieces of arena blocks it keeps (kalloc.c:71-99): no system call, no page fault per read.  Make malloc
+     * behave alike -- no mmap / munmap per large array, no trimming -- so that the timed region measures the boundary and not
+     * the kernel's page-fault path */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
     fake_worker_t *ws = (fake_worker_t *)calloc((size_t)n_threads, sizeof(*ws));
     pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(*th));
     pthread_barrier_t bar;
@@ -128,6 +149,13 @@ double fake_drive(const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int 
         while (q < r1) { int64_t c = 0; int q1 = q; while (q1 < r1 && (q1 == q || c + (off[q1 + 1] - off[q1]) <= batch_anchors)) c += off[q1 + 1] - off[q1], ++q1; ++nb; q = q1; }
         ws[t].tid = tid0 + t; ws[t].steps = steps; ws[t].sync_steps = sync_steps; ws[t].n_batches = nb; ws[t].bar = &bar;
         ws[t].batches = (fake_batch_t *)calloc((size_t)steps * (size_t)(nb > 0 ? nb : 1), sizeof(fake_batch_t));
+        {   /* room for the results of one mini-batch of this share (at most every anchor in a chain: 16 B a' + 8 B u), touched once */
+            const int64_t share = off[r1] - off[r];
+            ws[t].arena.cap = (size_t)share * 24 + (size_t)(r1 - r) * 32 + 4096;
+            ws[t].arena.base = (char *)malloc(ws[t].arena.cap);
+            memset(ws[t].arena.base, 0, ws[t].arena.cap);
+            ws[t].arena.used = 0;
+        }
         for (int s = 0; s < steps; ++s) {
             int b = 0;
             q = r;
@@ -168,11 +196,12 @@ double fake_drive(const mm2gb_anchor_t *a, const int64_t *off, int n_reads, int 
                         if (out_hu) out_hu[fb->r0 + k] = fake_digest(rd->u, rd->n_u);
                         if (out_hb) out_hb[fb->r0 + k] = fake_digest((const uint64_t *)rd->a, 2 * nb);
                     }
-                    kfree(0, rd->a); kfree(0, rd->u);
+                    kfree(&ws[t].arena, rd->a); kfree(&ws[t].arena, rd->u);
                 }
                 free(fb->reads);
             }
         free(ws[t].batches);
+        free(ws[t].arena.base);
     }
     pthread_barrier_destroy(&bar);
     free(ws); free(th);

@@ -70,7 +70,7 @@ def test_gpu_config_is_parsed_as_json():
         assert get(bad, "a")[0] == -1, bad
     # the reference's own config file format, as shipped (copied as a fixture string: keys with "//" comments, nested kernels)
     here = os.path.join(ROOT, "mm2-gb_b200", "b200_config.json")
-    assert get(open(here).read(), "max_total_n") == (1, 16777216.0)
+    assert get(open(here).read(), "max_total_n") == (1, 2097152.0)
 
 
 def _lib(pkg):
