@@ -432,14 +432,31 @@ def main():
     hbm_gbs = HBM_BYTES_PER_ANCHOR * n / score_avg_s / 1e9
     sm_mhz = clocks["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
     n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    issue_peak = n_sm * 4 * 32 * sm_mhz * 1e6          # thread-instructions/s: 4 schedulers x 32 lanes per SM
+    # integer / issue ceilings MEASURED on this GPU type by tools/int_peak.cu (profiles/int_peak.json): both integer pipes kept
+    # busy by independent add + mad chains at the score kernel's own residency -> thread-instructions/s; and the speed of light
+    # of a kernel made of nothing but the MID loop of score_unit_packed.  Scaled by the SM clock of this run.
+    ip = {}
+    try:
+        ip = json.load(open(os.path.join(ROOT, "profiles", "int_peak.json")))
+    except Exception:
+        pass
+    nominal_issue = n_sm * 4 * 32 * sm_mhz * 1e6          # 4 schedulers x 32 lanes per SM
+    clk_scale = sm_mhz / 1965.0
+    issue_peak = float(ip.get("issue_mix", {}).get("thread_instr_per_s", 0.0)) * clk_scale or nominal_issue
+    issue_src = "measured (tools/int_peak.cu issue_mix, profiles/int_peak.json)" if ip else "computed (148 SM x 128 lanes x clock)"
+    mid_peak = float(ip.get("mid_mix", {}).get("pairs_per_s", 0.0)) * clk_scale
     issue_ach = INSTR_PER_PAIR * pairs / score_avg_s
-    roofline = {"bound": "hbm", "kernel": "k_score_units", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
+    kernel_pairs_s = pairs / score_avg_s
+    roofline = {"bound": "int-issue", "kernel": "k_score_units", "achieved": issue_ach, "peak": issue_peak, "unit": "int-ops/s", "frac": issue_ach / issue_peak,
+                "peak_source": issue_src, "int_ops_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": kernel_pairs_s, "sm_mhz": sm_mhz, "n_sm": n_sm,
                 "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms,
-                "note": "this kernel is integer-issue bound, not HBM-bound (~%d pairs x %.0f integer ops per 24 B): see issue" % (round(pairs / max(1, n)), INSTR_PER_PAIR),
-                "issue": {"bound": "int-issue", "achieved": issue_ach, "peak": issue_peak, "unit": "algorithmic int-ops/s", "frac": issue_ach / issue_peak,
-                          "int_ops_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": pairs / score_avg_s, "sm_mhz": sm_mhz, "n_sm": n_sm}}
+                "traffic": traffic, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
+                "note": "achieved = %.0f algorithmic integer ops per pair (SURVEY.md 8d) x pairs / kernel time; the kernel executes 17.4 SASS thread-instructions per pair "
+                        "(profiles/r4*_score_units_ncu.md), i.e. %.2f of the measured issue peak" % (INSTR_PER_PAIR, 17.4 * kernel_pairs_s / issue_peak),
+                "mid_loop_speed_of_light": {"pairs_per_s": mid_peak or None, "frac": (kernel_pairs_s / mid_peak) if mid_peak else None,
+                                            "note": "a kernel of MID pairs only (6.6 instr/pair, LSU-bound); the score kernel also pays the in-tile triangle, GEN / FAR pairs and tile set-up"},
+                "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "peak_source": peak_src, "traffic": traffic,
+                        "note": "not the binding bound: ~%d pairs per 24-byte anchor" % round(pairs / max(1, n))}}
     line = {"metric": "chaining anchor-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": cfg, "reads_per_s": tot_reads * args.steps / sec, "anchors_per_s": tot_anchors * args.steps / sec,

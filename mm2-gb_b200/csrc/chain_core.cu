@@ -26,6 +26,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 using namespace mm2gb;
@@ -184,6 +185,8 @@ struct mm2gb_ctx {
     size_t stage_bytes = 0;      // size of a slot's pinned staging buffer h_a / device wire buffer
     long long up_bytes_batch = 0; // anchor bytes uploaded by the last pipelined batch (all chunks)
     Slot slot[kMaxSlots];
+    void *dev_block = nullptr, *pin_block = nullptr;   // all buffers of all slots (one allocation each)
+    size_t dev_bytes = 0, pin_bytes = 0;
     // profiling (slot 0 only)
     bool profile = false;
     bool timeline = false;      // MM2GB_TIMELINE=1: every slot records its stages; dumped (ms since the first event) to stderr
@@ -554,20 +557,11 @@ static void fill_stats(const mm2gb_ctx *c, const Counters &k, long long n_total,
 static void free_slot(Slot &s)
 {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    if (s.d_wire != reinterpret_cast<unsigned char *>(s.d_zk)) cudaFree(s.d_wire);
-    cudaFree(s.d_a); cudaFree(s.d_off); cudaFree(s.d_st); cudaFree(s.d_f); cudaFree(s.d_p);
-    cudaFree(s.d_selmask); cudaFree(s.d_clipmask); cudaFree(s.d_block_cnt); cudaFree(s.d_block_base); cudaFree(s.d_block_pairs);
-    cudaFree(s.d_chunk_tot); cudaFree(s.d_chunk_base); cudaFree(s.d_chunk_pairs);
-    cudaFree(s.d_unit_start); cudaFree(s.d_unit_rbase); cudaFree(s.d_big_order); cudaFree(s.d_ctr);
-    cudaFree(s.d_vp); cudaFree(s.d_uscr); cudaFree(s.d_vs); cudaFree(s.d_rinfo); cudaFree(s.d_list); cudaFree(s.d_upack); cudaFree(s.d_zs); cudaFree(s.d_nz);
-    cudaFree(s.d_zk); cudaFree(s.d_tb); cudaFree(s.d_pay2); cudaFree(s.d_ovf);
-    cudaFreeHost(s.h_a); cudaFreeHost(s.h_off); cudaFreeHost(s.h_f); cudaFreeHost(s.h_p); cudaFreeHost(s.h_ctr);
-    cudaFreeHost(s.h_vp); cudaFreeHost(s.h_rinfo); cudaFreeHost(s.h_list); cudaFreeHost(s.h_upack);
     if (s.done) cudaEventDestroy(s.done);
     if (s.bt_fork) cudaEventDestroy(s.bt_fork);
     for (int k = 0; k < kBtClasses; ++k) if (s.bt_join[k]) cudaEventDestroy(s.bt_join[k]);
     if (s.stream) cudaStreamDestroy(s.stream);
-    s = Slot();
+    s = Slot();     // the buffers live in the context's two blocks
 }
 
 // ---- C ABI -------------------------------------------------------------------------------------------------------------
@@ -639,62 +633,82 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             for (int k = 0; k < kBtStreams; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
         const size_t n = max_anchors, n_groups = (n + 31) / 32, n_blocks = (n + kRangeThreads - 1) / kRangeThreads;
         const size_t n_units_cap = n_groups + (size_t)max_reads + 2;
+        const size_t n_chunks = n_blocks / kScanChunk + 2, n_rd = (size_t)max_reads + 1;
+        c->stage_bytes = n * sizeof(uint4);
+        // Every buffer of every slot is carved out of ONE device block and ONE pinned block per context: a context is a few
+        // dozen buffers per slot, and allocation calls serialise inside the driver -- sixteen driver threads creating their
+        // contexts buffer by buffer spent 2-10 s each in cudaMalloc / cudaMallocHost (profiles/r4g_driver_ont_*.json).
+        // The same layout function runs twice: once to size the blocks, once to hand out the pointers.
+        auto layout = [&](char *dev, char *pin, size_t *dev_bytes, size_t *pin_bytes) {
+            size_t d = 0, h = 0;
+            auto dtake = [&](auto *&ptr, size_t count) {
+                typedef typename std::remove_reference<decltype(*ptr)>::type T;
+                d = (d + 255) & ~(size_t)255;
+                if (dev) ptr = reinterpret_cast<T *>(dev + d);
+                d += count * sizeof(T);
+            };
+            auto htake = [&](auto *&ptr, size_t count) {
+                typedef typename std::remove_reference<decltype(*ptr)>::type T;
+                h = (h + 255) & ~(size_t)255;
+                if (pin) ptr = reinterpret_cast<T *>(pin + h);
+                h += count * sizeof(T);
+            };
+            for (int i = 0; i < n_slots; ++i) {
+                Slot &s = c->slot[i];
+                if (c->host_io) dtake(s.d_a, n);
+                dtake(s.d_off, n_rd);
+                dtake(s.d_st, n);
+                if (c->host_io) { dtake(s.d_f, n); dtake(s.d_p, n); }
+                dtake(s.d_selmask, n_groups); dtake(s.d_clipmask, n_groups);
+                dtake(s.d_block_cnt, n_blocks); dtake(s.d_block_base, n_blocks); dtake(s.d_block_pairs, n_blocks);
+                dtake(s.d_chunk_tot, n_chunks); dtake(s.d_chunk_base, n_chunks); dtake(s.d_chunk_pairs, n_chunks);
+                dtake(s.d_unit_start, n_units_cap); dtake(s.d_unit_rbase, n_units_cap);
+                s.big_cap = (int)(n / kBigMin) + 2;
+                dtake(s.d_big_order, (size_t)kBigClasses * s.big_cap);
+                dtake(s.d_ctr, 1);
+                // staging: raw anchors (16 B each) or the packed wire format (8 B each + block index + run list), same buffer
+                if (c->host_io) htake(s.h_a, n);
+                htake(s.h_off, n_rd);
+                if (c->host_io && c->fp_staging) { htake(s.h_f, n); htake(s.h_p, n); }
+                htake(s.h_ctr, 1);
+                if (!c->chains_ok) {
+                    if (c->host_io) dtake(s.d_wire, c->stage_bytes);   // no sort scratch to borrow (see below)
+                    continue;
+                }
+                dtake(s.d_vp, n + 4); dtake(s.d_uscr, n); dtake(s.d_vs, n);
+                dtake(s.d_rinfo, 4 * n_rd); dtake(s.d_list, n_rd);
+                s.u_cap = n;    // a chain has at least one anchor and every anchor is in at most one chain
+                dtake(s.d_upack, s.u_cap); dtake(s.d_zs, n); dtake(s.d_nz, n_rd);
+                dtake(s.d_zk, 2 * n);
+                if (dev) {
+                    s.d_zk2 = s.d_zk + n;
+                    // on the device the packed upload lands in the sort scratch of the chain extraction, which is dead until the
+                    // score kernels of the batch are done
+                    if (c->host_io) s.d_wire = reinterpret_cast<unsigned char *>(s.d_zk);
+                }
+                dtake(s.d_pay2, n); dtake(s.d_tb, n / 32 + 2 * (size_t)max_reads + 8); dtake(s.d_ovf, n_rd);
+                if (c->host_io) { htake(s.h_vp, n + 4); htake(s.h_upack, s.u_cap); }
+                htake(s.h_rinfo, 4 * n_rd); htake(s.h_list, n_rd);
+            }
+            *dev_bytes = d + 256;
+            *pin_bytes = h + 256;
+        };
+        size_t dev_bytes = 0, pin_bytes = 0;
+        layout(nullptr, nullptr, &dev_bytes, &pin_bytes);
+        CKC(cudaMalloc(&c->dev_block, dev_bytes));
+        CKC(cudaMallocHost(&c->pin_block, pin_bytes));
+        layout(static_cast<char *>(c->dev_block), static_cast<char *>(c->pin_block), &dev_bytes, &pin_bytes);
+        c->dev_bytes = dev_bytes; c->pin_bytes = pin_bytes;
         for (int i = 0; i < n_slots; ++i) {
             Slot &s = c->slot[i];
             CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CKC(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
             CKC(cudaEventCreateWithFlags(&s.bt_fork, cudaEventDisableTiming));
             for (int k = 0; k < kBtClasses; ++k) CKC(cudaEventCreateWithFlags(&s.bt_join[k], cudaEventDisableTiming));
-            if (c->host_io) CKC(cudaMalloc(&s.d_a, n * sizeof(uint4)));
-            // staging: raw anchors (16 B each) or the packed wire format (8 B each + block index + run list), same buffer
-            // (on the device the packed upload lands in the sort scratch of the chain extraction, which is dead until the score
-            // kernels of the batch are done; contexts without that scratch get a buffer of their own)
-            c->stage_bytes = n * sizeof(uint4);
-            if (c->host_io && !c->chains_ok) CKC(cudaMalloc(&s.d_wire, c->stage_bytes));
-            CKC(cudaMalloc(&s.d_off, ((size_t)max_reads + 1) * sizeof(long long)));
-            CKC(cudaMalloc(&s.d_st, n * sizeof(int)));
-            if (c->host_io) CKC(cudaMalloc(&s.d_f, n * sizeof(int)));
-            if (c->host_io) CKC(cudaMalloc(&s.d_p, n * sizeof(int)));
-            CKC(cudaMalloc(&s.d_selmask, n_groups * sizeof(unsigned)));
-            CKC(cudaMalloc(&s.d_clipmask, n_groups * sizeof(unsigned)));
-            CKC(cudaMalloc(&s.d_block_cnt, n_blocks * sizeof(int)));
-            CKC(cudaMalloc(&s.d_block_base, n_blocks * sizeof(int)));
-            CKC(cudaMalloc(&s.d_chunk_tot, (n_blocks / kScanChunk + 2) * sizeof(int)));
-            CKC(cudaMalloc(&s.d_chunk_base, (n_blocks / kScanChunk + 2) * sizeof(int)));
-            CKC(cudaMalloc(&s.d_chunk_pairs, (n_blocks / kScanChunk + 2) * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_block_pairs, n_blocks * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_unit_start, n_units_cap * sizeof(int)));
-            CKC(cudaMalloc(&s.d_unit_rbase, n_units_cap * sizeof(int)));
-            s.big_cap = (int)(n / kBigMin) + 2;
-            CKC(cudaMalloc(&s.d_big_order, (size_t)kBigClasses * s.big_cap * sizeof(int)));
-            CKC(cudaMalloc(&s.d_ctr, sizeof(Counters)));
-            if (c->host_io) CKC(cudaMallocHost(&s.h_a, n * sizeof(mm2gb_anchor_t)));
-            CKC(cudaMallocHost(&s.h_off, ((size_t)max_reads + 1) * sizeof(long long)));
-            if (c->host_io && c->fp_staging) CKC(cudaMallocHost(&s.h_f, n * sizeof(int)));
-            if (c->host_io && c->fp_staging) CKC(cudaMallocHost(&s.h_p, n * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_ctr, sizeof(Counters)));
-            if (!c->chains_ok) continue;
-            CKC(cudaMalloc(&s.d_vp, (n + 4) * sizeof(int)));
-            CKC(cudaMalloc(&s.d_uscr, n * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_vs, n * sizeof(int)));
-            CKC(cudaMalloc(&s.d_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMalloc(&s.d_list, ((size_t)max_reads + 1) * sizeof(int)));
-            if (c->host_io) CKC(cudaMallocHost(&s.h_vp, (n + 4) * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_rinfo, 4 * ((size_t)max_reads + 1) * sizeof(int)));
-            CKC(cudaMallocHost(&s.h_list, ((size_t)max_reads + 1) * sizeof(int)));
-            s.u_cap = n;    // a chain has at least one anchor and every anchor is in at most one chain
-            CKC(cudaMalloc(&s.d_upack, s.u_cap * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_zs, n * sizeof(unsigned)));
-            CKC(cudaMalloc(&s.d_nz, ((size_t)max_reads + 1) * sizeof(int)));
-            if (c->host_io) CKC(cudaMallocHost(&s.h_upack, s.u_cap * sizeof(unsigned long long)));
-            CKC(cudaMalloc(&s.d_zk, 2 * n * sizeof(unsigned long long)));
-            s.d_zk2 = s.d_zk + n;
-            if (c->host_io) s.d_wire = reinterpret_cast<unsigned char *>(s.d_zk);
-            CKC(cudaMalloc(&s.d_pay2, n * sizeof(unsigned)));
-            CKC(cudaMalloc(&s.d_tb, (n / 32 + 2 * (size_t)max_reads + 8) * sizeof(unsigned)));
-            CKC(cudaMalloc(&s.d_ovf, ((size_t)max_reads + 1) * sizeof(int)));
-            if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_vp_dev, s.h_vp, 0));
-            if (c->host_io) CKC(cudaHostGetDevicePointer((void **)&s.h_upack_dev, s.h_upack, 0));
+            if (c->chains_ok && c->host_io) {
+                CKC(cudaHostGetDevicePointer((void **)&s.h_vp_dev, s.h_vp, 0));
+                CKC(cudaHostGetDevicePointer((void **)&s.h_upack_dev, s.h_upack, 0));
+            }
         }
     }
     *out = c;
@@ -711,6 +725,8 @@ extern "C" void mm2gb_ctx_destroy(mm2gb_ctx_t *c)
     cudaSetDevice(c->device);
     for (int i = 0; i < kMaxSlots; ++i) free_slot(c->slot[i]);
     for (int k = 0; k < kBtStreams; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
+    cudaFree(c->dev_block);
+    cudaFreeHost(c->pin_block);
     prof_collect(c);
     cudaFree(c->d_lut);
     delete c;

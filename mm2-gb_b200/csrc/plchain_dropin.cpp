@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -66,7 +67,12 @@ struct ThreadState {
     // scratch
     std::vector<const mm2gb_anchor_t *> ptrs;
     std::vector<int64_t> ns;
+    // where this thread's time at the boundary goes (seconds; reported by free_stream_gpu with MM2GB_VERBOSE=1)
+    double t_ctx = 0, t_submit = 0, t_wait = 0, t_publish = 0;
+    long long n_batches = 0, n_anchors = 0, n_ctx = 0;
 };
+
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 Config g_cfg;
 bool g_inited = false;
@@ -232,6 +238,7 @@ bool same_misc(const Misc_abi &a, const Misc_abi &b) { return memcmp(&a, &b, siz
 
 void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi &misc)
 {
+    const double t0 = now_s();
     if (S.ctx) mm2gb_ctx_destroy(S.ctx);
     S.ctx = nullptr;
     if (mm2gb_ctx_create_ex(&S.ctx, S.device, cap_anchors, cap_reads, 2 * g_cfg.sub_batches, &misc, MM2GB_CTX_NO_FP_STAGING) != MM2GB_OK)
@@ -240,6 +247,8 @@ void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi 
     S.cap_reads = cap_reads;
     S.misc = misc;
     S.has_misc = true;
+    S.t_ctx += now_s() - t0;
+    ++S.n_ctx;
 }
 
 ThreadState &state_of(int tid)
@@ -298,13 +307,17 @@ void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt
         const uint64_t *const *dev_u = nullptr;
         const int32_t *dev_nu = nullptr, *dev_nv = nullptr;
         const int32_t *const *dev_v = nullptr;
+        const double t0 = now_s();
         if (mm2gb_wait_chains(S.ctx, sb.slot, &dev_u, &dev_nu, &dev_v, &dev_nv, nullptr, nullptr) != MM2GB_OK) die("waiting for a chaining batch");
+        const double t1 = now_s();
+        S.t_wait += t1 - t0;
         long long down = 16LL * (sb.r1 - sb.r0 + 1) + 64;   // per-read counts / positions + the batch counters
         for (int r = sb.r0; r < sb.r1; ++r) {
             publish(reads[r], dev_nu[r - sb.r0], dev_nv[r - sb.r0], dev_u[r - sb.r0], dev_v[r - sb.r0]);
             down += 8LL * dev_nu[r - sb.r0] + 4LL * dev_nv[r - sb.r0];
         }
         g_d2h_bytes += down;
+        S.t_publish += now_s() - t1;
         done_to = sb.r1;
     }
     for (int r = done_to; r < n_reads; ++r) publish(reads[r], 0, 0, nullptr, nullptr);   // a batch without anchors
@@ -373,7 +386,10 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
     // launch the new batch first, so the device works while this thread finishes the previous one
     const int half = S.busy ? 1 - S.half : 0;
     std::vector<Sub> subs;
+    const double t_sub0 = now_s();
     if (in && total > 0) {
+        ++S.n_batches;
+        S.n_anchors += total;
         int r0 = 0;
         for (int k = 0; k < n_sub && r0 < n_in; ++k) {
             int r1 = r0;
@@ -386,6 +402,7 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
             r0 = r1;
         }
     }
+    S.t_submit += now_s() - t_sub0;
     if (S.busy) complete_inflight(S, mi, opt, misc, km);
     if (in) {
         S.busy = true; S.reads = in; S.n_reads = n_in; S.half = half; S.subs.swap(subs);
@@ -414,9 +431,18 @@ extern "C" void free_stream_gpu(int n_threads)
 {
     (void)n_threads;
     std::lock_guard<std::mutex> lk(g_mu);
+    const char *verbose = getenv("MM2GB_VERBOSE");
+    int tid = 0;
     for (ThreadState *&st : g_state) {
+        ++tid;
         if (!st) continue;
+        const double t0 = now_s();
         if (st->ctx) mm2gb_ctx_destroy(st->ctx);
+        if (verbose && atoi(verbose))
+            fprintf(stderr, "[mm2gb] thread %d (GPU %d): %lld batches, %lld anchors; context x%lld %.3f s (slot capacity %zu anchors), gather+submit %.3f s, "
+                            "wait %.3f s, publish %.3f s, teardown %.3f s\n",
+                    tid - 1, st->device, st->n_batches, st->n_anchors, st->n_ctx, st->t_ctx, st->cap_anchors, st->t_submit, st->t_wait, st->t_publish,
+                    now_s() - t0);
         delete st;
         st = nullptr;
     }

@@ -51,7 +51,10 @@ def main():
     gen_s = time.time() - t0
     REF = os.path.join(ROOT, "oracle", "_ref")
     cfg = os.path.join(ROOT, "mm2-gb_b200", "b200_config.json")
-    env = dict(os.environ, MM2GB_THREADS_PER_GPU=str(G))
+    env = dict(os.environ, MM2GB_THREADS_PER_GPU=str(G), MM2GB_VERBOSE="1")
+    if os.environ.get("MM2GB_MAX_TOTAL_N"):     # a batch limit other than the shipped config's
+        cfg = os.path.join(d, "cfg.json")
+        open(cfg, "w").write('{"max_total_n": %d, "max_read": 200000}' % int(os.environ["MM2GB_MAX_TOTAL_N"]))
 
     def run(binary, args):
         t1 = time.time()
@@ -66,11 +69,13 @@ def main():
     a, b = cpu_paf.splitlines(), gpu_paf.splitlines()
     ndiff = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
     warn = [ln for ln in gpu_err.splitlines() if "WARNING" in ln or "ERROR" in ln][:5]
+    per_thread = [ln for ln in gpu_err.splitlines() if ln.startswith("[mm2gb] thread")]
     print(json.dumps({"workload": wl, "reads": w["n_reads"], "ref_len": w["ref_len"], "fasta_generation_s": gen_s,
                       "cpu": {"binary": "minimap2_ref_timed -t %d --max-chain-skip=2147483647" % T, "wall_s": cpu_s, "paf_md5": hashlib.md5(cpu_paf).hexdigest(),
                               "paf_lines": len(a), "timers": timers(cpu_err)},
                       "gpu": {"binary": "minimap2_b200_timed -t %d --gpu-chain" % G, "wall_s": gpu_s, "paf_md5": hashlib.md5(gpu_paf).hexdigest(),
-                              "paf_lines": len(b), "timers": timers(gpu_err), "messages": warn},
+                              "paf_lines": len(b), "timers": timers(gpu_err), "messages": warn,
+                              "boundary_per_thread": per_thread[:4] + (["... %d more" % (len(per_thread) - 4)] if len(per_thread) > 4 else [])},
                       "paf_lines_differing": ndiff, "paf_identical": cpu_paf == gpu_paf}))
     if cpu_paf != gpu_paf:
         open(os.path.join(d, "cpu.paf"), "wb").write(cpu_paf); open(os.path.join(d, "gpu.paf"), "wb").write(gpu_paf)
