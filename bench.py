@@ -52,9 +52,9 @@ WORKLOADS = {
     "ont": dict(name="synthetic 100 Mb random reference, 10k ONT-like reads 10-100 kb @10% error, map-ont",
                 ref_len=100_000_000, contig_len=25_000_000, n_reads=10_000, lo=10_000, hi=100_000, err=0.10),
     # configs[2]: super-long reads, lower error + planted repeats so that reads exceed 50k anchors
-    "long": dict(name="synthetic 100 Mb reference with planted repeats, 1000 super-long reads 100-300 kb @3% error, map-ont",
-                 ref_len=100_000_000, contig_len=25_000_000, n_reads=1000, lo=100_000, hi=300_000, err=0.03,
-                 n_repeat_copies=3000, repeat_unit=3000),
+    "long": dict(name="synthetic 100 Mb reference with 4000 planted 3 kb repeat copies, 2000 super-long reads 100-300 kb @2% error, map-ont",
+                 ref_len=100_000_000, contig_len=25_000_000, n_reads=2000, lo=100_000, hi=300_000, err=0.02,
+                 n_repeat_copies=4000, repeat_unit=3000),
     # small variant for quick checks
     "mini": dict(name="synthetic 5 Mb random reference, 400 ONT-like reads 10-100 kb @10% error, map-ont",
                  ref_len=5_000_000, contig_len=0, n_reads=400, lo=10_000, hi=100_000, err=0.10),
@@ -118,6 +118,26 @@ class ClockSampler(threading.Thread):
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.rows)}
+
+
+def workload_shape(a, off, sample=64):
+    """anchors per read, and (on a sample of the longest reads) the independent segments = runs of anchors no chaining window
+    crosses (st_i == i starts a segment; lchain.c:172 with max_dist_x = 5000) -- what SURVEY.md 8d asks configs[2] to print"""
+    rn = np.diff(off)
+    out = {"anchors_per_read": {"mean": float(rn.mean()), "min": int(rn.min()), "max": int(rn.max()), "median": float(np.median(rn))}}
+    seg_max, seg_over_10k, n_seg = 0, 0, 0
+    for r in np.argsort(-rn)[:sample]:
+        x = a[int(off[r]):int(off[r + 1]), 0]
+        lo32 = x & np.uint64(0xffffffff)
+        lower = (x & np.uint64(0xffffffff00000000)) | np.where(lo32 > 5000, lo32 - np.uint64(5000), np.uint64(0))
+        st = np.searchsorted(x, lower, side="left")
+        cuts = np.flatnonzero(st == np.arange(len(x)))
+        seg = np.diff(np.append(cuts, len(x)))
+        n_seg += len(seg)
+        seg_max = max(seg_max, int(seg.max()))
+        seg_over_10k += int((seg > 10_000).sum())
+    out["independent_segments_of_the_%d_longest_reads" % min(sample, len(rn))] = {"segments": n_seg, "largest": seg_max, "over_10k_anchors": seg_over_10k}
+    return out
 
 
 def cpu_threads():
@@ -240,21 +260,24 @@ def main():
     a, off = make_workload(w, rank)
     n, n_reads = int(off[-1]), len(off) - 1
     misc = pkg.map_ont_misc()
-    ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=max(n, 1 << 20), max_reads=n_reads + 1, n_slots=1)   # whole batch resident
-    stream = torch.cuda.ExternalStream(ctx.stream_ptr(0), device=local_rank)
+    # whole batch resident; two slots (stream + scratch each) so that two batches can be in flight
+    in_flight = max(1, min(2, int(os.environ.get("MM2GB_BENCH_IN_FLIGHT", "2"))))
+    ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=max(n, 1 << 20), max_reads=n_reads + 1, n_slots=in_flight,
+                           flags=pkg.ChainContext.DEVICE_ONLY)
+    streams = [torch.cuda.ExternalStream(ctx.stream_ptr(k), device=local_rank) for k in range(in_flight)]
 
     # device-resident inputs
     h_a = torch.from_numpy(a.view(np.int64)).pin_memory()
     h_off = torch.from_numpy(off).pin_memory()
     d_a = h_a.cuda(non_blocking=True)
     d_off = h_off.cuda(non_blocking=True)
-    d_f = torch.empty(n, dtype=torch.int32, device="cuda")
-    d_p = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_f = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(in_flight)]
+    d_p = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(in_flight)]
     torch.cuda.synchronize()
 
-    def step():
+    def step(slot=0):
         # the whole device side of mg_lchain_dp: range -> units -> score (f, p) -> chain extraction + compaction (u, a')
-        ctx.chain_device(d_a, d_off, off, n_reads, n, d_f, d_p)
+        ctx.chain_device(d_a, d_off, off, n_reads, n, d_f[slot], d_p[slot], slot=slot)
 
     def barrier():
         torch.cuda.synchronize()
@@ -262,25 +285,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    ctx.sync()
+    for k in range(max(3, args.warmup)):
+        step(k % in_flight)
+    for k in range(in_flight):
+        ctx.sync(k)
     st = ctx.device_stats()
     pairs = int(st.n_pairs)
     sampler = ClockSampler(local_rank)
+    # (1) one batch at a time on one stream, with the per-kernel CUDA-event timers on: the step's latency and the kernel times
+    #     the roofline is computed from (a kernel timed while another batch's kernels share the GPU would not be its own time)
     ctx.profile(True)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(streams[0])
     for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    ctx.sync()
+        step(0)
+    e1.record(streams[0])
+    ctx.sync(0)
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms_seq = e0.elapsed_time(e1)
     prof = ctx.profile_read()
     ctx.profile(False)
+    # (2) the timed region of `value`: the same K steps with two batches in flight, alternating between the two slots -- batches
+    #     are independent, and the latency-bound chain extraction of one overlaps the score kernels of the next.  Every step
+    #     does all of its work; the clock is a pair of CUDA events on the launching streams around all K steps.
+    ms = ms_seq
+    if in_flight > 1:
+        ej = [torch.cuda.Event(enable_timing=False) for _ in range(in_flight)]
+        barrier()
+        e0.record(streams[0])
+        for k in range(1, in_flight):
+            streams[k].wait_event(e0)           # no slot starts before the clock does
+        for k in range(args.steps):
+            step(k % in_flight)
+        for k in range(1, in_flight):
+            ej[k].record(streams[k])
+            streams[0].wait_event(ej[k])        # the clock stops when every slot is done
+        e1.record(streams[0])
+        for k in range(in_flight):
+            ctx.sync(k)
+        barrier()
+        ms = e0.elapsed_time(e1)
 
     # ---- end to end through the reference-facing boundary: init / chain / finish_stream_gpu (include/mm2gb_plchain.h), called
     #      the way `minimap2 -t T --gpu-chain` calls them (tests/fake_host.c: fake_drive): T worker threads, every read's anchors
@@ -449,7 +495,7 @@ def main():
     kernel_pairs_s = pairs / score_avg_s
     roofline = {"bound": "int-issue", "kernel": "k_score_units", "achieved": issue_ach, "peak": issue_peak, "unit": "int-ops/s", "frac": issue_ach / issue_peak,
                 "peak_source": issue_src, "int_ops_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": kernel_pairs_s, "sm_mhz": sm_mhz, "n_sm": n_sm,
-                "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms,
+                "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms_seq,
                 "traffic": traffic, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
                 "note": "achieved = %.0f algorithmic integer ops per pair (SURVEY.md 8d) x pairs / kernel time; the kernel executes 17.4 SASS thread-instructions per pair "
                         "(profiles/r4*_score_units_ncu.md), i.e. %.2f of the measured issue peak" % (INSTR_PER_PAIR, 17.4 * kernel_pairs_s / issue_peak),
@@ -458,10 +504,13 @@ def main():
                 "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "peak_source": peak_src, "traffic": traffic,
                         "note": "not the binding bound: ~%d pairs per 24-byte anchor" % round(pairs / max(1, n))}}
     line = {"metric": "chaining anchor-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "ms_per_step": ms_max / args.steps, "batches_in_flight": in_flight,
+            "one_batch_at_a_time": {"ms_per_step": ms_seq / args.steps, "value": pairs * args.steps / (ms_seq / 1e3), "unit": "pairs/s",
+                                    "note": "the same steps strictly one after the other on one stream (latency of a step; the per-kernel timers and the roofline come from this run)"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": cfg, "reads_per_s": tot_reads * args.steps / sec, "anchors_per_s": tot_anchors * args.steps / sec,
             "batch": {"reads": n_reads, "anchors": n, "pairs": pairs, "pairs_per_anchor": pairs / max(1, n), "units": int(st.n_units),
-                      "units_exact": int(st.n_units_exact), "chains": n_chains},
+                      "units_exact": int(st.n_units_exact), "units_long_kernel": int(st.n_long), "chains": n_chains, **workload_shape(a, off)},
             "kernel_ms_per_step": {k: v[0] / max(1, v[1]) for k, v in prof.items() if v[1]},
             "dp_only": {"value": pairs / (dp_ms / 1e3), "unit": "pairs/s", "ms": dp_ms,
                         "note": "range + units + score kernels only (f, p); `value` also includes the device chain extraction + compaction"},

@@ -139,6 +139,10 @@ int mm2gb_chain_dp_device(mm2gb_ctx_t *ctx, const void *d_a, const void *d_off, 
  * the whole device side of mg_lchain_dp).  `off` = host copy of d_off. */
 int mm2gb_chain_device(mm2gb_ctx_t *ctx, const void *d_a, const void *d_off, const int64_t *off, int n_reads, int64_t n_total,
                        void *d_f, void *d_p);
+/* The same on the stream and scratch of another slot: batches on different slots are independent, so the latency-bound chain
+ * extraction of one batch overlaps the score kernels of the next (d_f / d_p must be distinct per batch in flight). */
+int mm2gb_chain_device_slot(mm2gb_ctx_t *ctx, int slot, const void *d_a, const void *d_off, const int64_t *off, int n_reads,
+                            int64_t n_total, void *d_f, void *d_p);
 int mm2gb_sync(mm2gb_ctx_t *ctx, int slot);
 /* the cudaStream_t of a slot, as an opaque pointer (so a caller can record its own events on it) */
 void *mm2gb_stream(mm2gb_ctx_t *ctx, int slot);

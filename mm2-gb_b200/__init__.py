@@ -102,6 +102,7 @@ def lib():
         L.mm2gb_slot_busy.argtypes = [vp, C.c_int]
         L.mm2gb_chain_dp_device.argtypes = [vp, vp, vp, C.c_int, C.c_int64, vp, vp]
         L.mm2gb_chain_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
+        L.mm2gb_chain_device_slot.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, vp, vp]
         L.mm2gb_sync.argtypes = [vp, C.c_int]
         L.mm2gb_stream.argtypes = [vp, C.c_int]
         L.mm2gb_stream.restype = vp
@@ -248,9 +249,9 @@ class ChainContext:
         """Enqueue the kernels on slot 0's stream; all arguments are device tensors/pointers.  Asynchronous."""
         _ck(lib().mm2gb_chain_dp_device(self._h, _ptr(d_a), _ptr(d_off), n_reads, n_total, _ptr(d_f), _ptr(d_p)))
 
-    def chain_device(self, d_a, d_off, off, n_reads: int, n_total: int, d_f, d_p):
-        """chain_dp_device + chain extraction on the device (off = host copy of the offsets).  Asynchronous."""
-        _ck(lib().mm2gb_chain_device(self._h, _ptr(d_a), _ptr(d_off), _ptr(off), n_reads, n_total, _ptr(d_f), _ptr(d_p)))
+    def chain_device(self, d_a, d_off, off, n_reads: int, n_total: int, d_f, d_p, slot: int = 0):
+        """chain_dp_device + chain extraction on the device (off = host copy of the offsets), on slot `slot`.  Asynchronous."""
+        _ck(lib().mm2gb_chain_device_slot(self._h, slot, _ptr(d_a), _ptr(d_off), _ptr(off), n_reads, n_total, _ptr(d_f), _ptr(d_p)))
 
     def sync(self, slot: int = 0):
         _ck(lib().mm2gb_sync(self._h, slot))

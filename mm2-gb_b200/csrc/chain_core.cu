@@ -1343,34 +1343,47 @@ extern "C" int mm2gb_backtrack_device(mm2gb_ctx_t *c, const mm2gb_anchor_t *a, c
     return MM2GB_OK;
 }
 
-extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p)
+static int chain_dp_device_slot(mm2gb_ctx_t *c, int si, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p)
 {
-    if (!c || n_reads < 0 || n_total < 0 || !d_off) return fail(MM2GB_EARG, "bad argument");
+    if (!c || si < 0 || si >= c->n_slots || n_reads < 0 || n_total < 0 || !d_off) return fail(MM2GB_EARG, "bad argument");
     if ((size_t)n_total > c->max_anchors) return fail(MM2GB_ECAP, "batch of %lld anchors exceeds capacity %zu", (long long)n_total, c->max_anchors);
     if (n_reads > c->max_reads) return fail(MM2GB_ECAP, "batch of %d reads exceeds capacity %d", n_reads, c->max_reads);
     CK(cudaSetDevice(c->device));
-    Slot &s = c->slot[0];
-    int rc = enqueue_kernels(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, n_total, (int *)d_f, (int *)d_p, c->profile);
+    Slot &s = c->slot[si];
+    int rc = enqueue_kernels(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, n_total, (int *)d_f, (int *)d_p, c->profile && si == 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
     s.n_total = n_total;
     return MM2GB_OK;
 }
 
-// device-resident DP + chain extraction: as mm2gb_chain_dp_device, then k_bt_sort* / k_bt_walk* into slot 0's output buffers
-// (`off` = host copy of the offsets, needed to bin the reads by size)
-extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, const int64_t *off, int n_reads, int64_t n_total,
-                                  void *d_f, void *d_p)
+extern "C" int mm2gb_chain_dp_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, int n_reads, int64_t n_total, void *d_f, void *d_p)
+{
+    return chain_dp_device_slot(c, 0, d_a, d_off, n_reads, n_total, d_f, d_p);
+}
+
+// device-resident DP + chain extraction on the stream and scratch of slot `slot`: as mm2gb_chain_dp_device, then k_bt_sort* /
+// k_bt_walk* into the slot's output buffers (`off` = host copy of the offsets, needed to bin the reads by size).  Batches
+// enqueued on different slots are independent: the latency-bound chain extraction of one overlaps the score kernels of the next.
+extern "C" int mm2gb_chain_device_slot(mm2gb_ctx_t *c, int slot, const void *d_a, const void *d_off, const int64_t *off, int n_reads,
+                                       int64_t n_total, void *d_f, void *d_p)
 {
     if (!off) return fail(MM2GB_EARG, "bad argument");
     if (c && !c->chains_ok) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_NO_CHAINS");
-    int rc = mm2gb_chain_dp_device(c, d_a, d_off, n_reads, n_total, d_f, d_p);
+    int rc = chain_dp_device_slot(c, slot, d_a, d_off, n_reads, n_total, d_f, d_p);
     if (rc || n_total == 0) return rc;
-    Slot &s = c->slot[0];
+    Slot &s = c->slot[slot];
     s.v_mis = 0;
     rc = prepare_backtrack(s, s.stream, (const long long *)off, n_reads);
     if (rc) return rc;
-    return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, (const int *)d_f, (const int *)d_p, c->profile);
+    return enqueue_backtrack(c, s, s.stream, (const uint4 *)d_a, (const long long *)d_off, n_reads, (const int *)d_f, (const int *)d_p,
+                             c->profile && slot == 0);
+}
+
+extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d_off, const int64_t *off, int n_reads, int64_t n_total,
+                                  void *d_f, void *d_p)
+{
+    return mm2gb_chain_device_slot(c, 0, d_a, d_off, off, n_reads, n_total, d_f, d_p);
 }
 
 // Diagnostic: device -> pinned host of n chain-anchor indices (4 B each) from slot 0's buffers, by k_drain with `blocks` CTAs and
