@@ -73,6 +73,9 @@ struct ThreadState {
 };
 
 inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+const double g_t_load = now_s();    // when the library was loaded (= process start for a statically linked driver)
+int verbose_level() { static const int v = getenv("MM2GB_VERBOSE") ? atoi(getenv("MM2GB_VERBOSE")) : 0; return v; }
+#define VLOG(lvl, ...) do { if (verbose_level() >= (lvl)) { fprintf(stderr, "[mm2gb %8.3f] ", now_s() - g_t_load); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); } } while (0)
 
 Config g_cfg;
 bool g_inited = false;
@@ -249,6 +252,7 @@ void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi 
     S.has_misc = true;
     S.t_ctx += now_s() - t0;
     ++S.n_ctx;
+    VLOG(2, "context on GPU %d: %zu anchors x %d slots created in %.3f s", S.device, cap_anchors, 2 * g_cfg.sub_batches, now_s() - t0);
 }
 
 ThreadState &state_of(int tid)
@@ -332,7 +336,9 @@ void complete_inflight(ThreadState &S, const mm2gb_idx_t *mi, const mm2gb_mapopt
 extern "C" void init_stream_gpu(size_t *max_total_n, int *max_reads, int *min_n, char gpu_config_file[], Misc_abi misc)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    VLOG(2, "init_stream_gpu: start");
     load_config(gpu_config_file);
+    VLOG(2, "init_stream_gpu: config loaded, %d GPU(s), batch limit %zu anchors", g_cfg.n_gpus, g_cfg.max_total_n);
     g_misc = misc;
     g_inited = true;
     if (max_total_n) *max_total_n = g_cfg.max_total_n;
@@ -433,6 +439,7 @@ extern "C" void free_stream_gpu(int n_threads)
     std::lock_guard<std::mutex> lk(g_mu);
     const char *verbose = getenv("MM2GB_VERBOSE");
     int tid = 0;
+    VLOG(2, "free_stream_gpu: start");
     for (ThreadState *&st : g_state) {
         ++tid;
         if (!st) continue;
@@ -448,6 +455,7 @@ extern "C" void free_stream_gpu(int n_threads)
     }
     g_state.clear();
     g_inited = false;
+    VLOG(2, "free_stream_gpu: done");
 }
 
 // test hook: parse a gpu config text the way init_stream_gpu does; returns 1 and the value if `key` is a numeric member of the
