@@ -55,6 +55,16 @@ WORKLOADS = {
     "long": dict(name="synthetic 100 Mb reference with 4000 planted 3 kb repeat copies, 2000 super-long reads 100-300 kb @2% error, map-ont",
                  ref_len=100_000_000, contig_len=25_000_000, n_reads=2000, lo=100_000, hi=300_000, err=0.02,
                  n_repeat_copies=4000, repeat_unit=3000),
+    # configs[4]-shaped: the hit mix of a 3 Gb, 24-contig reference (4 real contigs of 25 Mb that the reads come from + the chance hits
+    # of 20 virtual contigs of 50-250 Mb, 2.9 Gb in total: ~0.5 per read minimizer) -- ~2.5x the anchors per read of configs[1] at a
+    # lower pairs/anchor.  configs[4]'s 1 M reads are processed as steps of 20 k reads per GPU (every rank draws its own reads).
+    "hg": dict(name="synthetic human-scale hit mix: 100 Mb real + 2.9 Gb virtual reference in 24 contigs, 20k ONT-like reads 10-100 kb @10% error per GPU and step, map-ont",
+               ref_len=100_000_000, contig_len=25_000_000, n_reads=20_000, lo=10_000, hi=100_000, err=0.10, bg_len=2_900_000_000, bg_contigs=20),
+    # reads from a tandem array with the occurrence filter off (minimap2 -f 10000): every window is clipped by
+    # max_iter, so every unit takes the exact max_ii path (score_unit_exact)
+    "tandem": dict(name="tandem-repeat reads: 300 x 200 bp array @2% divergence, 48 reads of 15 kb @5% error, occurrence filter off (-f 10000 style), map-ont",
+                   ref_len=20_000_000, contig_len=5_000_000, n_reads=48, lo=15_000, hi=15_000, err=0.05, tandem_copies=300, tandem_unit=200,
+                   tandem_div=0.02, tandem_read_frac=1.0, mid_occ=100_000),
     # small variant for quick checks
     "mini": dict(name="synthetic 5 Mb random reference, 400 ONT-like reads 10-100 kb @10% error, map-ont",
                  ref_len=5_000_000, contig_len=0, n_reads=400, lo=10_000, hi=100_000, err=0.10),
@@ -63,7 +73,8 @@ WORKLOADS = {
 
 def make_workload(w, rank):
     from mm2gb_b200 import synth
-    kw = {k: w[k] for k in ("n_repeat_copies", "repeat_unit") if k in w}
+    kw = {k: w[k] for k in ("n_repeat_copies", "repeat_unit", "bg_len", "bg_contigs", "tandem_copies", "tandem_unit", "tandem_div", "tandem_read_frac",
+                            "mid_occ") if k in w}
     return synth.seeded_workload(1, w["ref_len"], w["n_reads"], w["lo"], w["hi"], read_seed=1000 + rank, err=w["err"],
                                  contig_len=w["contig_len"], **kw)
 
@@ -447,7 +458,7 @@ def main():
     # classes, the mid classes up to 196608 anchors, the global-memory class) and the overflow pass
     rn = np.diff(off)
     small = [1024, 1536, 2048, 3072, 4096, 6144, 8192]
-    mid = [12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608]
+    mid = [10048, 13952, 19776, 29504, 37248, 48640, 65536, 98304, 196608]
     mid_min = max(8192, int(os.environ.get("MM2GB_BT_MID_MIN", "8192")))
 
     def bt_class(x):

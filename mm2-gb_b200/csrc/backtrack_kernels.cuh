@@ -405,7 +405,15 @@ __device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, const B
         }
         __syncwarp();
         if (g > 0) {
-            // the walk (every lane of warp 0 runs it; lane 0 writes)
+            // the walk, by lane 0 alone.  A region's cursor and the digit of the token under it travel in ONE word,
+            // cnt[d] = cursor | digit << 24 (cursors stay below 2^24: reads of at most 196608 anchors), so a step of the
+            // dependent chain is a single shared-memory load: the digit of the evicted token comes with the cursor, and the
+            // word for the region's next visit (cursor + 1 and the digit there) is prepared off the critical path.
+            for (int r = lane; r < 256; r += 32) {
+                const unsigned c0 = cnt[r];                     // = fst[r] (0 for an empty region): c0 <= g <= m, D[m] is slack
+                cnt[r] = c0 | ((unsigned)D[c0] << 24);
+            }
+            __syncwarp();
             for (int rb = 0; rb < 256; rb += 32) {
                 const unsigned s0l = st[rb + lane], s1l = st[rb + lane + 1];
                 unsigned mask = __ballot_sync(full, s1l > s0l);
@@ -413,21 +421,24 @@ __device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, const B
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const unsigned k = (unsigned)(rb + j);
-                    const unsigned fe = fen[k];
-                    unsigned h = cnt[k];
-                    if (lane == 0) ecut[k] = (int)h;   // tokens below h were evicted by arrivals; turned into a position below
-                    while (h < fe) {
-                        const unsigned c0 = h++;
-                        unsigned carried = c0;
-                        unsigned d = D[c0];
-                        while (d != k) {
-                            const unsigned g2 = cnt[d];
-                            if (lane == 0) { cnt[d] = g2 + 1; nx[carried] = g2; }
-                            __syncwarp();
-                            carried = g2;
-                            d = D[g2];
+                    if (lane == 0) {
+                        const unsigned fe = fen[k];
+                        unsigned h = cnt[k] & 0xffffffu;
+                        ecut[k] = (int)h;   // tokens below h were evicted by arrivals; turned into a position below
+                        while (h < fe) {
+                            const unsigned c0 = h++;
+                            unsigned carried = c0;
+                            unsigned d = D[c0];
+                            while (d != k) {
+                                const unsigned w = cnt[d];
+                                const unsigned g2 = w & 0xffffffu;
+                                nx[carried] = g2;
+                                cnt[d] = (g2 + 1u) | ((unsigned)D[g2 + 1u] << 24);
+                                carried = g2;
+                                d = w >> 24;
+                            }
+                            nx[carried] = 0x80000000u | c0;
                         }
-                        if (lane == 0) nx[carried] = 0x80000000u | c0;
                     }
                 }
             }
@@ -782,8 +793,9 @@ struct WalkSmall {
     __device__ __forceinline__ int wc() const { return BtWalkSmem<CAP>::WC; }
     __device__ __forceinline__ void prepare_compaction(int) {}
     static constexpr bool kLanePar = false;     // (its scratch would cost these kernels a resident read per SM)
+    static constexpr int kZq = 6;               // groups of sorted ends in flight ahead of the scan
     __device__ __forceinline__ unsigned *lp_z() { return nullptr; }
-    __device__ __forceinline__ int *lp_path() { return nullptr; }
+    __device__ __forceinline__ unsigned short *lp_path() { return nullptr; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
     {
         // 4 coalesced loads of each array per lane, then 4 gathers of f[p[i]]; the loads of the NEXT 128 anchors are issued
@@ -811,6 +823,7 @@ struct WalkSmall {
     }
     __device__ __forceinline__ int fat(int i, const int *__restrict__ fr) const { return i < CAP ? fr[i] : 0; }
     __device__ __forceinline__ int nextp(int cur) const { return S.ps[cur]; }
+    __device__ __forceinline__ int nextp_blind(int cur, unsigned &) const { return S.ps[cur]; }
     __device__ __forceinline__ bool claimed(int i) const { return ((S.tb[i >> 5] >> (i & 31)) & 1u) != 0; }
     __device__ __forceinline__ void claim(int i) { atomicOr(&S.tb[i >> 5], 1u << (i & 31)); }
     __device__ __forceinline__ bool gain(int i, const int *, const int *) const { return ((S.gp[i >> 5] >> (i & 31)) & 1u) != 0; }
@@ -841,8 +854,9 @@ struct WalkBig {
     __device__ __forceinline__ int wc() const { return n; }
     __device__ __forceinline__ void prepare_compaction(int) {}
     static constexpr bool kLanePar = false;
+    static constexpr int kZq = 6;
     __device__ __forceinline__ unsigned long long *lp_z() { return nullptr; }
-    __device__ __forceinline__ int *lp_path() { return nullptr; }
+    __device__ __forceinline__ unsigned short *lp_path() { return nullptr; }
     __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
     {
         for (int w = lane; w <= (n_ >> 5); w += 32) tb[w] = 0;
@@ -853,6 +867,7 @@ struct WalkBig {
         if (cur < n) { const int q = pr[cur]; nx = q < 0 ? n : q; }
         return nx;
     }
+    __device__ __forceinline__ int nextp_blind(int cur, unsigned &) const { return nextp(cur); }
     __device__ __forceinline__ int fat(int i, const int *fr) const { return i < n ? fr[i] : 0; }
     __device__ __forceinline__ bool claimed(int i) const { return ((tb[i >> 5] >> (i & 31)) & 1u) != 0; }
     __device__ __forceinline__ void claim(int i) { atomicOr(&tb[i >> 5], 1u << (i & 31)); }
@@ -888,11 +903,14 @@ struct WalkMid {
     int *path_s;
     unsigned *cnt_s, *start_s;
     size_t smem_bytes;      // dynamic shared memory of the CTA
-    int *lp_path_s;         // [32][33]: the paths of the lane-parallel walks
+    unsigned short *lp_path_s;   // [32][33]: the paths of the lane-parallel walks, as distances below the lane's chain end
     static constexpr bool kLanePar = true;
+    // the sorted ends sit in global scratch (an L2 round trip per group) and a run of claimed windows is skipped in a few dozen
+    // cycles each: 16 groups in flight (the kernel has registers to spare: shared memory caps it at a few warps per SM)
+    static constexpr int kZq = 14;
     unsigned long long *lp_z_s;   // [32] pending ends
     __device__ __forceinline__ unsigned long long *lp_z() { return lp_z_s; }
-    __device__ __forceinline__ int *lp_path() { return lp_path_s; }
+    __device__ __forceinline__ unsigned short *lp_path() { return lp_path_s; }
     __device__ __forceinline__ int sent() const { return n; }
     __device__ __forceinline__ int wc() const { return n; }
     // the chain-start keys of the compaction (sorted with the serial flag passes) go to shared memory when they fit behind
@@ -929,6 +947,14 @@ struct WalkMid {
         if (d == 0u) nx = n;
         else if (d == 255u) nx = pr[cur];
         return nx;
+    }
+    // the same step for a blind chase of many nodes: no branch on the dependent chain (load, compare, select).  A link of 255
+    // or more is followed wrongly and flagged in esc (esc == 255 afterwards: redo that stretch with nextp)
+    __device__ __forceinline__ int nextp_blind(int cur, unsigned &esc) const
+    {
+        const unsigned d = rel[cur];
+        esc = max(esc, d);
+        return d ? cur - (int)d : n;
     }
     __device__ __forceinline__ int fat(int i, const int *fr) const { return i < n ? fr[i] : 0; }
     __device__ __forceinline__ bool claimed(int i) const { return ((tb[i >> 5] >> (i & 31)) & 1u) != 0; }
@@ -984,7 +1010,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
     ZT zn = (B - 32 - lane >= 0) ? S.zat(B - 32 - lane) : (ZT)0;
     // further groups in flight (zq[g] = z[B - 64 - 32 g - lane]): a run of claimed windows is skipped much faster than a load
     // returns, so the scan needs about latency / (time per window) loads outstanding
-    constexpr int kZq = 6;
+    constexpr int kZq = W::kZq;
     ZT zq[kZq];
 #pragma unroll
     for (int g = 0; g < kZq; ++g) zq[g] = (B - 64 - 32 * g - lane >= 0) ? S.zat(B - 64 - 32 * g - lane) : (ZT)0;
@@ -999,6 +1025,23 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         int cur = i0, max_s = 0, cutj = 0, cutf = 0, j0 = 0;   // cutf = f of the node the chain is cut at
         int mine0 = SENT; // this lane's node of the first batch (enough to mark chains of <= 32 nodes without re-reading)
         bool have = false;  // path[] already holds the next batch (chased ahead, below)
+        // 32 nodes from cur on into path[], blind (the sentinel points at itself, so no end test)
+        auto chase32 = [&]() {
+            const int cur0 = cur;
+            unsigned esc = 0;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                if (lane == 0) path[b] = (IDX)cur;
+                cur = S.nextp_blind(cur, esc);
+            }
+            if (esc == 255u) {   // (WalkMid) a link that does not fit a byte was followed wrongly: the same stretch, looking it up
+                cur = cur0;
+                for (int b = 0; b < 32; ++b) {
+                    if (lane == 0) path[b] = (IDX)cur;
+                    cur = S.nextp(cur);
+                }
+            }
+        };
         for (;;) {
             int nb = 32;
             if (have) {
@@ -1016,11 +1059,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
                     cur = nxt;
                 }
             } else {
-#pragma unroll
-                for (int b = 0; b < 32; ++b) {
-                    if (lane == 0) path[b] = (IDX)cur;
-                    cur = S.nextp(cur);
-                }
+                chase32();
             }
             __syncwarp();
             const int mine = lane < nb ? (int)path[lane] : SENT;
@@ -1030,11 +1069,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             if (nb == 32) {
                 // a full batch: the walk most likely goes on, so the next 32 nodes are chased (shared memory only) while the
                 // gather is in flight; if the walk ends in this batch the chase was for nothing
-#pragma unroll
-                for (int b = 0; b < 32; ++b) {
-                    if (lane == 0) path[b] = (IDX)cur;
-                    cur = S.nextp(cur);
-                }
+                chase32();
                 have = true;
             }
             if (j0 == 0) mine0 = mine;
@@ -1106,13 +1141,17 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         const unsigned m = nb_pend >= 32 ? full : ((1u << nb_pend) - 1u);
         const ZT z = unc ? S.lp_z()[lane] : (ZT)0;
         const int i0l = ZK::idx(z);
-        int *lp = S.lp_path() + lane * 33;
+        // a path is recorded as 16-bit distances below its end (0xffff = the sentinel); an end whose path leaves that range is
+        // walked by the whole warp like any long one.  (As ints the 32 paths cost the 64 k class a resident read per SM.)
+        unsigned short *lp = S.lp_path() + lane * 33;
+        auto lp_node = [&](const unsigned short *q, int t, int end_i) { const int v = q[t]; return v == 0xffff ? SENT : end_i - v; };
         int len = 0;
         bool longw = false;
         if (unc) {
             int cur = i0l;
             for (int t = 0; t < 32; ++t) {
-                lp[t] = cur;
+                if (cur != SENT && i0l - cur > 0xfffe) { longw = true; break; }   // (t >= 1 here: lp[0] is set)
+                lp[t] = cur == SENT ? (unsigned short)0xffff : (unsigned short)(i0l - cur);
                 len = t + 1;
                 if (t >= 1 && (cur == SENT || S.claimed(cur))) break;
                 if (t == 31) { longw = true; break; }
@@ -1129,7 +1168,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             for (int t0 = 1; t0 < maxlen; t0 += 8) {
                 int fv[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) fv[q] = t0 + q < glen ? S.fat(lp[t0 + q], fr) : 0;
+                for (int q = 0; q < 8; ++q) fv[q] = t0 + q < glen ? S.fat(lp_node(lp, t0 + q, i0l), fr) : 0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     if (live && t0 + q < glen) {
@@ -1149,8 +1188,9 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
             const int len_l = __shfl_sync(full, len, l), nev_l = __shfl_sync(full, nev, l), cut_l = __shfl_sync(full, cutl, l);
             const int sc_l = __shfl_sync(full, maxs, l);
             const bool long_l = __shfl_sync(full, longw ? 1 : 0, l) != 0;
-            const int *rp = S.lp_path() + l * 33;
-            const int node = (long_l ? lane == 0 : lane <= nev_l) ? rp[lane] : SENT;
+            const unsigned short *rp = S.lp_path() + l * 33;
+            const int end_l = __shfl_sync(full, i0l, l);
+            const int node = (long_l ? lane == 0 : lane <= nev_l) ? lp_node(rp, lane, end_l) : SENT;
             // nodes 0 .. len-2 were unclaimed when the lane walked, the last one is where it stopped
             const bool nowc = node != SENT && (long_l || lane < len_l - 1) && S.claimed(node);
             const unsigned chg = __ballot_sync(full, nowc);
@@ -1321,14 +1361,26 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         out += __shfl_sync(full, incl, 31);
     }
     __syncwarp();
+    int clo = 0;    // chain of position o0 (chain starts ascend with the chain number, so the range of a chunk only moves up)
     for (int o0 = 0; o0 < out; o0 += 128) {
+        // chains [clo, chi] cover the 128 positions of this chunk: chi by a warp-wide scan from clo (a chunk usually holds a
+        // handful of chains), then every position looks its chain up among those few instead of among all n_u
+        const int oend = min(out, o0 + 128) - 1;
+        int chi = clo;
+        for (;;) {
+            const int c = chi + 1 + lane;
+            const bool le = c < n_u && (int)(unsigned)wk[c] <= oend;
+            const unsigned b = __ballot_sync(full, le);     // a prefix of the lanes
+            chi += __popc(b);
+            if (b != full) break;
+        }
         int idx[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int o = o0 + t * 32 + lane;
             idx[t] = -1;
             if (o < out) {
-                int lo = 0, hi = n_u;       // the chain of position o: start[lo] <= o < start[hi]
+                int lo = clo, hi = chi + 1;       // the chain of position o: start[lo] <= o < start[hi]
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
                     if ((int)(unsigned)wk[mid] <= o) lo = mid; else hi = mid;
@@ -1339,6 +1391,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) if (idx[t] >= 0) bo[o0 + t * 32 + lane] = idx[t];
+        clo = chi;
     }
     if (lane == 0) { n_u_out[r] = n_u; n_b_out[r] = out; u_pos[r] = upos; b_pos[r] = bpos; }
 }
@@ -1415,7 +1468,7 @@ k_bt_walk_mid(const uint4 *__restrict__ a, const int *__restrict__ f, const int 
 {
     extern __shared__ int4 bt_raw[];
     __shared__ int s_path[32];
-    __shared__ int s_lp_path[32 * 33];
+    __shared__ unsigned short s_lp_path[32 * 33];
     __shared__ unsigned long long s_lp_z[32];
     const int lane = threadIdx.x;
     if ((int)blockIdx.x >= n_list) return;

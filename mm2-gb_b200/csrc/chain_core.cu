@@ -79,7 +79,11 @@ namespace {
 constexpr int kBtClasses = 17, kBtBig = 16, kBtMid0 = 7, kBtStreams = 24;
 // (finer mid classes -- steps of 2^(1/4) -- were tried: better packing of shared memory, but twice the launches, each with its
 //  own slowest-read tail; measured slower both device-resident and end to end)
-const int kBtCaps[kBtBig] = {1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072, 196608};
+// The mid caps are the largest reads of which k = 12, 10, 8, 6, 5, 4, 3, 2, 1 fit an SM in BOTH kernels: a CTA costs
+// cap + 8288 + 1024 B (k_bt_sort_mid) / bt_walk_mid_smem(cap) + 2496 + 1024 B (k_bt_walk_mid) of the SM's 233472 B.  These
+// latency-bound kernels are as fast as the number of reads resident per SM, and with power-of-two-ish caps the 49152 class
+// missed its fourth and the 65536 class its third resident read by under 2 KB.
+const int kBtCaps[kBtBig] = {1024, 1536, 2048, 3072, 4096, 6144, 8192, 10048, 13952, 19776, 29504, 37248, 48640, 65536, 98304, 196608};
 // Reads of 8193 .. mid_min anchors go to the global-memory kernels, longer ones (up to 196608) to the mid kernels.  The two
 // kinds complement each other: the global-memory kernels need no shared memory, so every read of a batch is resident at once
 // but each serial step costs an L2 round trip (fine for the shorter reads); the mid kernels take ~5x less time per read but
@@ -412,8 +416,16 @@ static int config_backtrack()
     CK(cudaFuncSetAttribute(k_bt_walk<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtWalkSmem<CAP>)));
     MM2GB_BT_CLASSES(X)
 #undef X
-    CK(cudaFuncSetAttribute(k_bt_sort_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1]));
+    CK(cudaFuncSetAttribute(k_bt_sort_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1] + 16));
     CK(cudaFuncSetAttribute(k_bt_walk_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_walk_mid_smem(kBtCaps[kBtBig - 1])));
+    if (const char *e = getenv("MM2GB_VERBOSE")) if (atoi(e) >= 3) {   // reads resident per SM, per mid class
+        for (int k = kBtMid0; k < kBtBig; ++k) {
+            int ns = 0, nw = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ns, k_bt_sort_mid, kBtMidThreads, (size_t)kBtCaps[k] + 16));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nw, k_bt_walk_mid, 32, bt_walk_mid_smem(kBtCaps[k])));
+            fprintf(stderr, "[mm2gb] chain-extraction class %6d anchors: %d sorts / %d walks resident per SM\n", kBtCaps[k], ns, nw);
+        }
+    }
     return MM2GB_OK;
 }
 
@@ -446,7 +458,7 @@ static void launch_backtrack_mid(cudaStream_t s, const uint4 *d_a, const int *d_
                                  int cap, const BtParams &bp, Slot &sl)
 {
     if (n_list <= 0) return;
-    k_bt_sort_mid<<<n_list, kBtMidThreads, (size_t)cap, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2,
+    k_bt_sort_mid<<<n_list, kBtMidThreads, (size_t)cap + 16 /* D[m]: read ahead by the walk */, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2,
                                                   reinterpret_cast<unsigned *>(sl.d_vs), sl.d_nz, cap);
     k_bt_walk_mid<<<n_list, 32, bt_walk_mid_smem(cap), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_zs, sl.d_pay2,
                                                           sl.d_st, sl.d_uscr, sl.d_vs, sl.d_vp, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos,

@@ -10,6 +10,7 @@
 // valid input for lchain.c and for the device path alike.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -98,10 +99,39 @@ void parallel_for(int64_t n, int n_threads, F fn)
 
 extern "C" {
 
+// Optional shape parameters of a workload (mm2gb_synth_create_ex); all zero = the plain workload of mm2gb_synth_create.
+struct mm2gb_synth_extra_t {
+    // "human-scale" hit mix without building a 3 Gb index: every read minimizer additionally gets Poisson(lambda) hits at uniformly
+    // random positions of bg_contigs virtual contigs (ids after the real ones, 50-250 Mb each, bg_len bp in total), on a random
+    // strand; lambda = (minimizers per bp of the real reference) x bg_len / 4^k, i.e. the chance hits a random reference of that
+    // size produces (~0.5 per minimizer for 3 Gb at k = 15, w = 10).
+    int64_t bg_len;
+    int bg_contigs;
+    // a tandem array (tandem_copies x tandem_unit bp, each copy diverged by tandem_div) planted in the middle of contig 0; a fraction
+    // tandem_read_frac of the reads is drawn from inside it.  With mid_occ > 0 the occurrence filter is fixed at that value instead of
+    // the 2e-4 quantile (minimap2 -f <large>): repetitive seeds are kept, windows overflow max_iter.
+    int tandem_copies, tandem_unit;
+    double tandem_div, tandem_read_frac;
+    int mid_occ;
+};
+
+void *mm2gb_synth_create_ex(uint64_t seed, uint64_t read_seed, int64_t ref_len, int64_t contig_len, int n_repeat_copies, int repeat_unit, double repeat_div,
+                            int n_reads, int len_lo, int len_hi, double err, int k, int w, int n_threads, const mm2gb_synth_extra_t *extra);
+
 // Generates the workload (`seed` fixes the reference, `read_seed` the reads); returns an opaque handle (NULL on bad arguments).  n_total / n_reads via the getters.
 void *mm2gb_synth_create(uint64_t seed, uint64_t read_seed, int64_t ref_len, int64_t contig_len, int n_repeat_copies, int repeat_unit, double repeat_div,
                          int n_reads, int len_lo, int len_hi, double err, int k, int w, int n_threads)
 {
+    return mm2gb_synth_create_ex(seed, read_seed, ref_len, contig_len, n_repeat_copies, repeat_unit, repeat_div, n_reads, len_lo, len_hi, err, k, w,
+                                 n_threads, nullptr);
+}
+
+void *mm2gb_synth_create_ex(uint64_t seed, uint64_t read_seed, int64_t ref_len, int64_t contig_len, int n_repeat_copies, int repeat_unit, double repeat_div,
+                            int n_reads, int len_lo, int len_hi, double err, int k, int w, int n_threads, const mm2gb_synth_extra_t *extra)
+{
+    mm2gb_synth_extra_t X;
+    memset(&X, 0, sizeof(X));
+    if (extra) X = *extra;
     if (ref_len < 1000 || n_reads < 0 || k < 8 || k > 28 || w < 1 || w > 64 || len_lo < k || len_hi < len_lo || ref_len >= (1LL << 32))
         return nullptr;
     if (n_threads < 1) n_threads = 1;
@@ -129,6 +159,19 @@ void *mm2gb_synth_create(uint64_t seed, uint64_t read_seed, int64_t ref_len, int
                 for (int j = 0; j < repeat_unit; ++j)
                     ref[(size_t)(pos + j)] = r.uniform() < repeat_div ? (uint8_t)((unit[(size_t)j] + 1 + r.below(3)) & 3) : unit[(size_t)j];
             }
+        }
+    }
+    int64_t tandem_lo = 0, tandem_hi = 0;
+    if (X.tandem_copies > 0 && X.tandem_unit > 0 && (int64_t)X.tandem_copies * X.tandem_unit < contig_len / 2) {
+        Rng r(seed ^ 0x7a4de3ULL);
+        std::vector<uint8_t> unit((size_t)X.tandem_unit);
+        for (auto &b : unit) b = r.next() & 3;
+        const int64_t span = (int64_t)X.tandem_copies * X.tandem_unit;
+        tandem_lo = (contig_len - span) / 2;
+        tandem_hi = tandem_lo + span;
+        for (int64_t i = 0; i < span; ++i) {
+            const uint8_t b = unit[(size_t)(i % X.tandem_unit)];
+            ref[(size_t)(tandem_lo + i)] = r.uniform() < X.tandem_div ? (uint8_t)((b + 1 + r.below(3)) & 3) : b;
         }
     }
     // ---- index: minimizers of the reference, bucketed by the top bits of the hash
@@ -192,6 +235,22 @@ void *mm2gb_synth_create(uint64_t seed, uint64_t read_seed, int64_t ref_len, int
         int cut = 4095;
         for (; cut > 0; --cut) { above += hist[(size_t)cut]; if (above > lim) break; }
         idx.mid_occ = std::max(10, cut + 1);
+        if (X.mid_occ > 0) idx.mid_occ = X.mid_occ;
+    }
+    // background hits of a reference much larger than the one that was built
+    std::vector<int64_t> bg_start;     // cumulative lengths of the virtual contigs
+    double bg_lambda = 0.0;
+    if (X.bg_len > 0 && X.bg_contigs > 0) {
+        Rng r(seed ^ 0x5eedb6ULL);
+        std::vector<double> len((size_t)X.bg_contigs);
+        double sum = 0;
+        for (auto &l : len) { l = 50e6 + 200e6 * r.uniform(); sum += l; }
+        bg_start.assign((size_t)X.bg_contigs + 1, 0);
+        for (int c = 0; c < X.bg_contigs; ++c)
+            bg_start[(size_t)c + 1] = bg_start[(size_t)c] + std::min<int64_t>((int64_t)(len[(size_t)c] * (double)X.bg_len / sum), (1LL << 31) - 1);
+        double space = 1.0;
+        for (int i = 0; i < k; ++i) space *= 4.0;
+        bg_lambda = (double)idx.key.size() / (double)ref_len * (double)bg_start.back() / space;
     }
     // ---- reads -> anchors
     Workload *wl = new Workload();
@@ -201,10 +260,15 @@ void *mm2gb_synth_create(uint64_t seed, uint64_t read_seed, int64_t ref_len, int
     parallel_for(n_reads, n_threads, [&](int64_t r, int) {
         Rng rng(read_seed * 6364136223846793005ULL + 1442695040888963407ULL * (uint64_t)(r + 1));
         const int64_t ln = len_lo + (int64_t)rng.below((uint64_t)(len_hi - len_lo + 1));
-        const int64_t contig = (int64_t)rng.below((uint64_t)n_contigs);
+        int64_t contig = (int64_t)rng.below((uint64_t)n_contigs);
+        const bool from_tandem = tandem_hi > tandem_lo && rng.uniform() < X.tandem_read_frac;
+        if (from_tandem) contig = 0;
         const int64_t c0 = contig * contig_len, c1 = std::min(ref_len, c0 + contig_len);
         const int64_t span = std::min(ln, c1 - c0 - 1);
-        const int64_t st = c0 + (int64_t)rng.below((uint64_t)(c1 - c0 - span));
+        int64_t st = c0 + (int64_t)rng.below((uint64_t)(c1 - c0 - span));
+        if (from_tandem)   // anywhere that keeps the read inside the array (or centred on it if the read is longer)
+            st = span < tandem_hi - tandem_lo ? tandem_lo + (int64_t)rng.below((uint64_t)(tandem_hi - tandem_lo - span))
+                                              : std::max<int64_t>(c0, std::min<int64_t>(c1 - span - 1, (tandem_lo + tandem_hi - span) / 2));
         std::vector<uint8_t> q;
         q.reserve((size_t)(span + span / 8));
         for (int64_t i = 0; i < span; ++i) {
@@ -220,6 +284,22 @@ void *mm2gb_synth_create(uint64_t seed, uint64_t read_seed, int64_t ref_len, int
         std::vector<Mz> mz;
         sketch(q.data(), qlen, k, w, mz);
         std::vector<std::pair<uint64_t, uint64_t>> hits;
+        if (bg_lambda > 0.0) {
+            const double p0 = std::exp(-bg_lambda);
+            const int64_t bg_total = bg_start.back();
+            for (auto &m : mz) {
+                double u = rng.uniform(), pk = p0, cum = p0;   // Poisson(lambda) by inversion
+                int nh = 0;
+                while (u > cum && nh < 64) { ++nh; pk *= bg_lambda / nh; cum += pk; }
+                for (int h = 0; h < nh; ++h) {
+                    const int64_t g = (int64_t)rng.below((uint64_t)bg_total);
+                    const int64_t c = (int64_t)(std::upper_bound(bg_start.begin(), bg_start.end(), g) - bg_start.begin()) - 1;
+                    const uint64_t rid = (uint64_t)(n_contigs + c), rpos = (uint64_t)(g - bg_start[(size_t)c]);
+                    if (rng.next() & 1) hits.push_back({rid << 32 | rpos, (uint64_t)k << 32 | m.pos});
+                    else hits.push_back({1ULL << 63 | rid << 32 | rpos, (uint64_t)k << 32 | (uint64_t)(qlen - ((int64_t)m.pos + 1 - k) - 1)});
+                }
+            }
+        }
         for (auto &m : mz) {
             const size_t b = (size_t)(m.h >> sh);
             uint32_t s = idx.bstart[b], e = idx.bstart[b + 1];

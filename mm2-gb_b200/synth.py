@@ -120,25 +120,35 @@ def chaining_only_array(seed: int, n: int, seg_len: int, *, mean_gap: float = 25
 
 def seeded_workload(seed: int, ref_len: int, n_reads: int, len_lo: int, len_hi: int, *, read_seed: int | None = None, err: float = 0.10,
                     contig_len: int = 0, n_repeat_copies: int = 0, repeat_unit: int = 3000, repeat_div: float = 0.03,
-                    k: int = 15, w: int = 10, n_threads: int = 0):
+                    k: int = 15, w: int = 10, n_threads: int = 0, bg_len: int = 0, bg_contigs: int = 0, tandem_copies: int = 0,
+                    tandem_unit: int = 0, tandem_div: float = 0.0, tandem_read_frac: float = 0.0, mid_occ: int = 0):
     """Random reference of `ref_len` bp (+ optional planted repeats), `n_reads` ONT-like reads U[len_lo,len_hi] at
     `err` error (40% sub / 30% del / 30% ins, half reverse-complemented), (w,k)-minimizer seeding with a mid-occ
     filter.  Returns (anchors uint64[N,2], offsets int64[n_reads+1]) -- x-sorted per read, as collect_seed_hits
-    (map.c:295-331) would hand them to the chaining stage."""
+    (map.c:295-331) would hand them to the chaining stage.
+
+    bg_len / bg_contigs: the chance hits of a (virtual) reference of bg_len more bp in bg_contigs more contigs -- the hit mix of a
+    human-scale index without building one.  tandem_*: a tandem array in contig 0 that tandem_read_frac of the reads come from;
+    mid_occ > 0 fixes the occurrence cut-off (minimap2 -f <large>) so repetitive seeds survive."""
     import ctypes as C
     import os
     lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmm2gb_synth.so"))
-    lib.mm2gb_synth_create.restype = C.c_void_p
-    lib.mm2gb_synth_create.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
-                                       C.c_double, C.c_int, C.c_int, C.c_int]
+
+    class Extra(C.Structure):
+        _fields_ = [("bg_len", C.c_int64), ("bg_contigs", C.c_int), ("tandem_copies", C.c_int), ("tandem_unit", C.c_int),
+                    ("tandem_div", C.c_double), ("tandem_read_frac", C.c_double), ("mid_occ", C.c_int)]
+    lib.mm2gb_synth_create_ex.restype = C.c_void_p
+    lib.mm2gb_synth_create_ex.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                          C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(Extra)]
     lib.mm2gb_synth_n_anchors.restype = C.c_int64
     lib.mm2gb_synth_n_anchors.argtypes = [C.c_void_p]
     lib.mm2gb_synth_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mm2gb_synth_free.argtypes = [C.c_void_p]
     if n_threads <= 0:
         n_threads = min(32, os.cpu_count() or 1)
-    h = lib.mm2gb_synth_create(seed, seed + 1 if read_seed is None else read_seed, ref_len, contig_len, n_repeat_copies, repeat_unit, repeat_div, n_reads, len_lo, len_hi,
-                               err, k, w, n_threads)
+    ex = Extra(bg_len, bg_contigs, tandem_copies, tandem_unit, tandem_div, tandem_read_frac, mid_occ)
+    h = lib.mm2gb_synth_create_ex(seed, seed + 1 if read_seed is None else read_seed, ref_len, contig_len, n_repeat_copies, repeat_unit, repeat_div, n_reads,
+                                  len_lo, len_hi, err, k, w, n_threads, C.byref(ex))
     if not h:
         raise ValueError("bad workload parameters")
     try:

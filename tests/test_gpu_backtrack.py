@@ -57,9 +57,10 @@ def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score, monkeypatch):
     if min_cnt != 3:    # two of the three parameter sets send every read above 8192 anchors to the mid kernels (default: above 32768)
         monkeypatch.setenv("MM2GB_BT_MID_MIN", "8192")
     rng = np.random.default_rng(hash((kind, min_cnt)) % (1 << 31))
-    # every size class: shared-memory kernels (<= 8192), mid kernels (16k / 32k / 64k / 128k / 192k anchors), global-memory kernels
-    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 66, 200, 1000, 1024, 1025, 2048, 3000, 4096, 5000, 8192, 8193, 9000, 16384, 20000, 40000,
-             70001, 140000, 196608, 196609]
+    # every size class: shared-memory kernels (<= 8192), the nine mid classes (caps 10048 .. 196608 anchors, both sides of several
+    # class boundaries), global-memory kernels
+    sizes = [0, 1, 2, 3, 31, 32, 33, 64, 65, 66, 200, 1000, 1024, 1025, 2048, 3000, 4096, 5000, 8192, 8193, 9000, 10048, 10049, 13952, 16384,
+             20000, 29504, 33000, 40000, 48640, 48641, 60000, 65536, 70001, 98304, 140000, 196608, 196609]
     reads, fs, ps = [], [], []
     for n in sizes:
         a = synth.ont_like_anchors(rng, max(n, 1), noise_frac=0.0)[:n]
@@ -72,7 +73,7 @@ def test_forests_vs_host(pkg, synth, kind, min_cnt, min_score, monkeypatch):
     off[1:] = np.cumsum(sizes)
     a, f, p = np.concatenate(reads), np.concatenate(fs), np.concatenate(ps)
     misc = pkg.map_ont_misc(min_cnt=min_cnt, min_score=min_score)
-    with pkg.ChainContext(misc, max_anchors=1 << 20, max_reads=64, n_slots=1) as c:
+    with pkg.ChainContext(misc, max_anchors=1 << 21, max_reads=64, n_slots=1) as c:
         u, n_u, b, n_b, nd = c.backtrack_device(a, off, f, p)
     _compare(pkg, misc, a, off, f, p, u, n_u, b, n_b)
     # reads above 8192 anchors (k_bt_*_mid up to 196608, k_bt_*_big beyond), scores >= 2^19 and reads with more chains than the
