@@ -15,7 +15,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmm2gb_chain.so")
+# MM2GB_LIB: an alternative build of the library (kernel experiments, see csrc/Makefile EXTRA); the product is libmm2gb_chain.so
+LIB_PATH = os.environ.get("MM2GB_LIB") or os.path.join(HERE, "libmm2gb_chain.so")
 INT32_MAX = 2**31 - 1
 N_TIMERS = 6
 TIMER_NAMES = ("range", "units", "score", "backtrack", "h2d", "d2h")

@@ -321,12 +321,14 @@ __device__ void bt_sort(typename KO::T *A, PAYT *pay, typename KO::T *tmpA, PAYT
 //     arrival (ecut[d]); a cycle-closing element takes the position of the token that opened the cycle.
 // The O(run length) shifting of the literal algorithm (the hot spot of the first version of this kernel) is gone
 // (tests/test_flagpass_model.py checks the reformulation against the literal pass).
-// A CTA of kBtMidThreads threads works on one read: the parallel phases (digits + histogram, placement, copy back, the rank sort
+// A CTA of NT threads works on one read: the parallel phases (digits + histogram, placement, copy back, the rank sort
 // of small buckets) use every thread, the token compaction and the walk run on warp 0.  Every thread takes the same path
 // (all control values come from shared memory behind a barrier).
 // Scratch (global, one unsigned per element each): tok (position -> token or ~0 for own), fpos (token -> position),
 // nxt (token -> token it evicted on arrival, or 2^31 | opening token).  Bucket boundaries -> st[0..256] (absolute positions).
-constexpr int kBtMidThreads = 128;
+constexpr int kBtMidThreads = 512;    // largest CTA of k_bt_sort_mid<NT> (NT = 128 / 256 / 512 by size class, see bt_mid_threads)
+// the fewer reads of a class fit an SM, the more threads each gets for the parallel phases (registers: 40 x NT x resident reads)
+__host__ __device__ inline int bt_mid_threads(int cap) { return cap <= 20480 ? 128 : cap <= 49152 ? 256 : 512; }
 
 struct BtFqScratch {
     unsigned *cnt, *rows, *fst, *fen;   // shared: [256], [4 * kBtRow], [256], [256]
@@ -335,12 +337,11 @@ struct BtFqScratch {
     unsigned *tok, *fpos, *nxt;         // global, per element
 };
 
-template <class KO>
+template <class KO, int NT>
 __device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, const BtFqScratch &q, int lo, int hi, int shift, unsigned *st,
                                 unsigned char *D, int tid)
 {
     typedef typename KO::T K;
-    constexpr int NT = kBtMidThreads;
     const int lane = tid & 31;
     const bool w0 = tid < 32;
     const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
@@ -487,12 +488,11 @@ __device__ void bt_flag_pass_fq(typename KO::T *A, typename KO::T *tmpA, const B
 
 // rank sort of every bucket of 2..64 elements of one pass over A[lo, hi) in global memory, by the whole CTA (bt_rank_sort is
 // the one-warp version): rank = number of bucket mates that order before the element as (score, position)
-template <class KO>
+template <class KO, int NT>
 __device__ void bt_rank_sort_blk(typename KO::T *A, typename KO::T *tmpA, int lo, int hi, int shift, const unsigned *start, int tid,
                                  unsigned *dirty, unsigned *any_dirty)
 {
     typedef typename KO::T K;
-    constexpr int NT = kBtMidThreads;
     // only buckets that hold an element smaller than its left neighbour need ranking (see bt_rank_sort)
     for (int d = tid; d < 256; d += NT) dirty[d] = 0;
     if (tid == 0) *any_dirty = 0;
@@ -528,15 +528,14 @@ __device__ void bt_rank_sort_blk(typename KO::T *A, typename KO::T *tmpA, int lo
     __syncthreads();
 }
 
-// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors, by a CTA of kBtMidThreads threads: every pass is
+// radix_sort_128x of A[0, n) (global memory) for reads of up to `cap` anchors, by a CTA of NT threads: every pass is
 // bt_flag_pass_fq; only buckets of at most kcap (<= cap / 8) elements are copied to shared memory (KA, which aliases D) and
 // finished there by warp 0 with bt_sort -- for a few hundred elements the literal algorithm beats the fixed cost of a pass
 // through global memory.  rows: 4 levels (32-bit scores) of kBtRow entries.
-template <class KO>
+template <class KO, int NT>
 __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, const BtFqScratch &q, unsigned char *D, int kcap, int tid)
 {
     typedef typename KO::T K;
-    constexpr int NT = kBtMidThreads;
     const int lane = tid & 31;
     const bool w0 = tid < 32;
     const unsigned full = 0xffffffffu;
@@ -573,8 +572,8 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, cons
     while (((diff >> shift) & 255u) == 0) shift -= 8;
     int lv = 0;
     unsigned *row = q.rows;
-    bt_flag_pass_fq<KO>(A, tmpA, q, 0, n, shift, row, D, tid);
-    if (shift) bt_rank_sort_blk<KO>(A, tmpA, 0, n, shift, row, tid, q.cnt, q.misc + 4);
+    bt_flag_pass_fq<KO, NT>(A, tmpA, q, 0, n, shift, row, D, tid);
+    if (shift) bt_rank_sort_blk<KO, NT>(A, tmpA, 0, n, shift, row, tid, q.cnt, q.misc + 4);
     if (tid == 0) { row[257] = 0; row[258] = (unsigned)shift; }
     __syncthreads();
     while (lv >= 0) {
@@ -611,8 +610,8 @@ __device__ void bt_sort_mid(typename KO::T *A, typename KO::T *tmpA, int n, cons
         }
         ++lv;
         unsigned *crow = q.rows + lv * kBtRow;
-        bt_flag_pass_fq<KO>(A, tmpA, q, blo, bhi, nsh, crow, D, tid);
-        if (nsh) bt_rank_sort_blk<KO>(A, tmpA, blo, bhi, nsh, crow, tid, q.cnt, q.misc + 4);
+        bt_flag_pass_fq<KO, NT>(A, tmpA, q, blo, bhi, nsh, crow, D, tid);
+        if (nsh) bt_rank_sort_blk<KO, NT>(A, tmpA, blo, bhi, nsh, crow, tid, q.cnt, q.misc + 4);
         if (tid == 0) { crow[257] = 0; crow[258] = (unsigned)nsh; }
         __syncthreads();
     }
@@ -665,6 +664,46 @@ __device__ __forceinline__ int bt_collect(const int *__restrict__ fr, int n, int
     }
     fmax = __reduce_max_sync(full, fmax);
     return nz;
+}
+
+// the same by every warp of a CTA: warp w takes the w-th slice of the read, counts, and writes behind the slices before it
+// (wcnt: one shared word per warp).  Same output as bt_collect.
+template <class ZK, int NT>
+__device__ __forceinline__ int bt_collect_blk(const int *__restrict__ fr, int n, int min_sc, typename ZK::T *zk, int tid, unsigned *wcnt)
+{
+    constexpr int NW = NT / 32;
+    const unsigned full = 0xffffffffu;
+    const int lane = tid & 31, w = tid >> 5;
+    const int per = ((n + NW - 1) / NW + 255) & ~255;   // slice length: whole 256-anchor rounds
+    const int s0 = min(n, w * per), s1 = min(n, s0 + per);
+    int cntw = 0;
+    for (int i0 = s0; i0 < s1; i0 += 256) {
+        int fv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const int i = i0 + t * 32 + lane; fv[t] = i < s1 ? fr[i] : INT32_MIN; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cntw += (fv[t] >= min_sc && i0 + t * 32 + lane < s1) ? 1 : 0;
+    }
+    cntw = __reduce_add_sync(full, cntw);
+    if (lane == 0) wcnt[w] = (unsigned)cntw;
+    __syncthreads();
+    int nz = 0, total = 0;
+    for (int k = 0; k < NW; ++k) { const int c = (int)wcnt[k]; if (k < w) nz += c; total += c; }
+    for (int i0 = s0; i0 < s1; i0 += 256) {
+        int fv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const int i = i0 + t * 32 + lane; fv[t] = i < s1 ? fr[i] : INT32_MIN; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int i = i0 + t * 32 + lane;
+            const bool keep = fv[t] >= min_sc && i < s1;
+            const unsigned m = __ballot_sync(full, keep);
+            if (keep) zk[nz + __popc(m & ((1u << lane) - 1u))] = ZK::make(fv[t], i);
+            nz += __popc(m);
+        }
+    }
+    __syncthreads();
+    return total;
 }
 
 template <int CAP>
@@ -734,7 +773,8 @@ k_bt_sort_big(const int *__restrict__ f, const long long *__restrict__ off, cons
 // Reads of 8193 .. 196608 anchors ("mid" classes): 64-bit keys in global scratch as in k_bt_sort_big, but the serial part of
 // every pass runs on one-byte tokens in shared memory (bt_flag_pass_fq).  Dynamic shared memory: cap bytes (digits / tokens;
 // keys of buckets of <= 512 elements).
-__global__ void __launch_bounds__(kBtMidThreads)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, const int *__restrict__ read_list, int n_list, BtParams bp,
               unsigned long long *zk_scr, unsigned long long *zk2_scr, unsigned *tok_scr, unsigned *fpos_scr, unsigned *nxt_scr,
               int *__restrict__ nz_out, int cap)
@@ -751,17 +791,11 @@ k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, cons
     const int n = (int)(off[r + 1] - o0);
     if (bp.min_sc < 0 || n > cap) { if (tid == 0) nz_out[r] = -1; return; }
     unsigned long long *zk = zk_scr + o0, *zk2 = zk2_scr + o0;
-    if (tid < 32) {
-        int fmax;
-        const int nz0 = bt_collect<ZKey64>(f + o0, n, bp.min_sc, zk, tid, fmax);
-        if (tid == 0) s_misc[1] = (unsigned)nz0;
-    }
-    __syncthreads();
-    const int nz = (int)s_misc[1];
+    const int nz = bt_collect_blk<ZKey64, NT>(f + o0, n, bp.min_sc, zk, tid, s_cnt);
     BtFqScratch q;
     q.cnt = s_cnt; q.rows = s_rows; q.fst = s_fst; q.fen = s_fen; q.ecut = s_ecut; q.misc = s_misc;
     q.tok = tok_scr + o0; q.fpos = fpos_scr + o0; q.nxt = nxt_scr + o0;
-    bt_sort_mid<ZKey64>(zk, zk2, nz, q, reinterpret_cast<unsigned char *>(bt_raw), min(cap / 8, 512), tid);
+    bt_sort_mid<ZKey64, NT>(zk, zk2, nz, q, reinterpret_cast<unsigned char *>(bt_raw), min(cap / 8, 512), tid);
     if (tid == 0) nz_out[r] = nz;
 }
 
@@ -794,6 +828,8 @@ struct WalkSmall {
     __device__ __forceinline__ void prepare_compaction(int) {}
     static constexpr bool kLanePar = false;     // (its scratch would cost these kernels a resident read per SM)
     static constexpr int kZq = 6;               // groups of sorted ends in flight ahead of the scan
+    static constexpr int kZpf = 0;
+    __device__ __forceinline__ void zprefetch(int) const {}
     __device__ __forceinline__ unsigned *lp_z() { return nullptr; }
     __device__ __forceinline__ unsigned short *lp_path() { return nullptr; }
     __device__ __forceinline__ void init(int n, const int *__restrict__ fr, const int *__restrict__ pr, int lane)
@@ -855,6 +891,8 @@ struct WalkBig {
     __device__ __forceinline__ void prepare_compaction(int) {}
     static constexpr bool kLanePar = false;
     static constexpr int kZq = 6;
+    static constexpr int kZpf = 0;
+    __device__ __forceinline__ void zprefetch(int) const {}
     __device__ __forceinline__ unsigned long long *lp_z() { return nullptr; }
     __device__ __forceinline__ unsigned short *lp_path() { return nullptr; }
     __device__ __forceinline__ void init(int n_, const int *, const int *, int lane)
@@ -908,6 +946,13 @@ struct WalkMid {
     // the sorted ends sit in global scratch (an L2 round trip per group) and a run of claimed windows is skipped in a few dozen
     // cycles each: 16 groups in flight (the kernel has registers to spare: shared memory caps it at a few warps per SM)
     static constexpr int kZq = 14;
+    // ... and the lines 64 groups (16 KB) further down are pulled into L2 meanwhile: the sorted ends of a batch of long reads
+    // (8 B per anchor) do not survive in L2 between the sort and the walk kernel, and a DRAM round trip is ~3 groups of scanning
+    static constexpr int kZpf = 64;
+    __device__ __forceinline__ void zprefetch(int e) const
+    {
+        if (e >= 0 && (threadIdx.x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(zk + e));   // 32 lanes x 8 B = two 128-byte lines
+    }
     unsigned long long *lp_z_s;   // [32] pending ends
     __device__ __forceinline__ unsigned long long *lp_z() { return lp_z_s; }
     __device__ __forceinline__ unsigned short *lp_path() { return lp_path_s; }
@@ -1223,6 +1268,7 @@ __device__ __forceinline__ void bt_walk_body(W &S, int r, int n, int nz, const u
                 for (int g = 0; g + 1 < kZq; ++g) zq[g] = zq[g + 1];
                 B -= 32;
                 zq[kZq - 1] = (B - 64 - 32 * (kZq - 1) - lane >= 0) ? S.zat(B - 64 - 32 * (kZq - 1) - lane) : (ZT)0;
+                S.zprefetch(B - 32 * W::kZpf - lane);
             }
             ZT z = zc;
             const int sft = B - k;                         // warp-uniform, 0 .. 31

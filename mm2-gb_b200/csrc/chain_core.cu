@@ -184,6 +184,7 @@ struct mm2gb_ctx {
     cudaStream_t bt_stream[kBtStreams] = {nullptr};   // handed out round robin to the size-class launches of all slots
     unsigned bt_rr = 0;
     int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
+    bool range_tma = false;      // k_range_tma (history staged by cp.async.bulk) instead of k_range: MM2GB_RANGE_TMA=1
     int wire_mode = 0;           // 0 auto: pinned sources are DMA'd raw, pageable ones are packed by the gather pass; 1 always raw
                                  // (staged by memcpy); 2 always packed (MM2GB_WIRE=auto|raw|packed)
     size_t stage_bytes = 0;      // size of a slot's pinned staging buffer h_a / device wire buffer
@@ -270,7 +271,7 @@ static int config_score(mm2gb_ctx *c, size_t smem)
 template <int R>
 static int config_ring(mm2gb_ctx *c)
 {
-    const size_t smem = (size_t)kScoreWarps * R * sizeof(Rec);
+    const size_t smem = (size_t)kScoreWarps * (R * sizeof(Rec) + kStageBytes);
     c->score_smem = smem;
     c->score_blocks = 0;
     int rc = config_score<R, true>(c, smem);
@@ -282,7 +283,7 @@ template <int R, bool FAST>
 static void launch_score(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int *st, const int *us, const int *ur,
                          const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode)
 {
-    const size_t smem = (size_t)kScoreWarps * R * sizeof(Rec);
+    const size_t smem = (size_t)kScoreWarps * (R * sizeof(Rec) + kStageBytes);
     k_score_units<R, FAST><<<c->score_blocks, kScoreWarps * 32, smem, s>>>(a, st, us, ur, clip, f, p, big, big_cap, ctr, c->prm,
                                                                           c->d_lut, run_mode, FAST ? c->long_classes : 0, c->long_wave);
 }
@@ -376,8 +377,12 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
     {
         ProfScope ps(c, T_RANGE, s, prof);
         k_block_reads<<<(n_blocks + 255) / 256, 256, 0, s>>>(d_off, n_reads, n_blocks, sl.d_block_base);   // d_block_base doubles as block_read until k_scan
-        k_range<<<n_blocks, kRangeThreads, 0, s>>>(reinterpret_cast<const ulonglong2 *>(d_a), d_off, sl.d_block_base, n, c->prm, sl.d_st,
-                                                  sl.d_selmask, sl.d_clipmask, sl.d_block_cnt, sl.d_block_pairs, sl.d_ctr);
+        if (c->range_tma)
+            k_range_tma<<<n_blocks, kRangeThreads, 0, s>>>(reinterpret_cast<const ulonglong2 *>(d_a), d_off, sl.d_block_base, n, c->prm, sl.d_st,
+                                                          sl.d_selmask, sl.d_clipmask, sl.d_block_cnt, sl.d_block_pairs, sl.d_ctr);
+        else
+            k_range<<<n_blocks, kRangeThreads, 0, s>>>(reinterpret_cast<const ulonglong2 *>(d_a), d_off, sl.d_block_base, n, c->prm, sl.d_st,
+                                                      sl.d_selmask, sl.d_clipmask, sl.d_block_cnt, sl.d_block_pairs, sl.d_ctr);
     }
     {
         ProfScope ps(c, T_UNITS, s, prof);
@@ -416,12 +421,17 @@ static int config_backtrack()
     CK(cudaFuncSetAttribute(k_bt_walk<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtWalkSmem<CAP>)));
     MM2GB_BT_CLASSES(X)
 #undef X
-    CK(cudaFuncSetAttribute(k_bt_sort_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1] + 16));
+    CK(cudaFuncSetAttribute(k_bt_sort_mid<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1] + 16));
+    CK(cudaFuncSetAttribute(k_bt_sort_mid<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1] + 16));
+    CK(cudaFuncSetAttribute(k_bt_sort_mid<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBtCaps[kBtBig - 1] + 16));
     CK(cudaFuncSetAttribute(k_bt_walk_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_walk_mid_smem(kBtCaps[kBtBig - 1])));
     if (const char *e = getenv("MM2GB_VERBOSE")) if (atoi(e) >= 3) {   // reads resident per SM, per mid class
         for (int k = kBtMid0; k < kBtBig; ++k) {
             int ns = 0, nw = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ns, k_bt_sort_mid, kBtMidThreads, (size_t)kBtCaps[k] + 16));
+            const int nt = bt_mid_threads(kBtCaps[k]);
+            if (nt == 128) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ns, k_bt_sort_mid<128>, nt, (size_t)kBtCaps[k] + 16));
+            else if (nt == 256) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ns, k_bt_sort_mid<256>, nt, (size_t)kBtCaps[k] + 16));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ns, k_bt_sort_mid<512>, nt, (size_t)kBtCaps[k] + 16));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nw, k_bt_walk_mid, 32, bt_walk_mid_smem(kBtCaps[k])));
             fprintf(stderr, "[mm2gb] chain-extraction class %6d anchors: %d sorts / %d walks resident per SM\n", kBtCaps[k], ns, nw);
         }
@@ -458,8 +468,13 @@ static void launch_backtrack_mid(cudaStream_t s, const uint4 *d_a, const int *d_
                                  int cap, const BtParams &bp, Slot &sl)
 {
     if (n_list <= 0) return;
-    k_bt_sort_mid<<<n_list, kBtMidThreads, (size_t)cap + 16 /* D[m]: read ahead by the walk */, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2,
-                                                  reinterpret_cast<unsigned *>(sl.d_vs), sl.d_nz, cap);
+    const size_t sm = (size_t)cap + 16;   // + D[m], read ahead by the serial walk
+    unsigned *tok = reinterpret_cast<unsigned *>(sl.d_vs);
+    switch (bt_mid_threads(cap)) {
+    case 128: k_bt_sort_mid<128><<<n_list, 128, sm, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2, tok, sl.d_nz, cap); break;
+    case 256: k_bt_sort_mid<256><<<n_list, 256, sm, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2, tok, sl.d_nz, cap); break;
+    default: k_bt_sort_mid<512><<<n_list, 512, sm, s>>>(d_f, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_zs, sl.d_pay2, tok, sl.d_nz, cap); break;
+    }
     k_bt_walk_mid<<<n_list, 32, bt_walk_mid_smem(cap), s>>>(d_a, d_f, d_p, d_off, list, n_list, bp, sl.d_zk, sl.d_zk2, sl.d_nz, sl.d_zs, sl.d_pay2,
                                                           sl.d_st, sl.d_uscr, sl.d_vs, sl.d_vp, sl.d_upack, (int)sl.u_cap, sl.d_nu, sl.d_nb, sl.d_upos,
                                                           sl.d_bpos, sl.d_ctr, cap);
@@ -617,6 +632,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         c->long_classes = v <= 0 ? 0 : v <= 2048 ? 3 : v <= 4096 ? 2 : 1;
     }
     if (const char *e = getenv("MM2GB_TIMELINE")) c->timeline = atoi(e) != 0;
+    if (const char *e = getenv("MM2GB_RANGE_TMA")) c->range_tma = atoi(e) != 0;
     if (const char *e = getenv("MM2GB_WIRE")) c->wire_mode = !strcmp(e, "raw") ? 1 : !strcmp(e, "packed") ? 2 : 0;
     if (const char *e = getenv("MM2GB_DRAIN_BLOCKS")) {
         int r = atoi(e);

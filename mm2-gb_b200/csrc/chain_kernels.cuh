@@ -141,6 +141,81 @@ k_block_reads(const long long *__restrict__ off, int n_reads, int n_blocks, int 
     block_read[b] = lo;
 }
 
+// what a k_range thread does once the x history of its block is staged: XS(j) = x of anchor j for j in [max(h0, 0), g0 + 256)
+template <class XS>
+__device__ __forceinline__ void range_tail(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, int r0, int n_total,
+                                           const DevParams &prm, const ulonglong2 &ai, unsigned long long yprev, int g0, int h0, XS xs,
+                                           int *__restrict__ st, unsigned *__restrict__ selmask, unsigned *__restrict__ clipmask,
+                                           int *__restrict__ block_cnt, unsigned long long *__restrict__ block_pairs, Counters *__restrict__ ctr,
+                                           int *s_cnt, unsigned long long *s_pairs)
+{
+    const int g = g0 + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool act = g < n_total;
+    const unsigned mdx = (unsigned)prm.max_dist_x;
+    bool cut = false, clipped = false, rstart = false;
+    int npair = 0, qspan = 0;
+    if (act) {
+        int r = r0;
+        while (off[r + 1] <= (long long)g) ++r;
+        const int rs = (int)off[r];
+        const unsigned long long xi = ai.x;
+        const unsigned lo32 = (unsigned)xi;
+        // lchain.c:172: j is in the window iff same rid/strand and x_i <= x_j + max_dist_x  <=>  x_j >= lower
+        const unsigned long long lower = (xi & 0xffffffff00000000ULL) | (unsigned long long)(lo32 > mdx ? lo32 - mdx : 0u);
+        const long long lo_ll = (long long)g - (long long)prm.max_iter;   // lchain.c:173
+        const int lo0 = lo_ll > (long long)rs ? (int)lo_ll : rs;
+        int hi;
+        const int lo_s = max(lo0, max(h0, 0));   // oldest candidate available in shared memory
+        if (lo_s > lo0 && xs(lo_s) >= lower) {
+            hi = window_start_global(a, g, lo0, lower);   // window reaches beyond the staged history (rare)
+        } else {
+            // first index in [lo_s, g] with x >= lower; x[g] itself qualifies
+            int bad = lo_s - 1;
+            hi = g;
+            while (hi - bad > 1) {
+                const int mid = (hi + bad) >> 1;
+                if (xs(mid) >= lower) hi = mid; else bad = mid;
+            }
+        }
+        st[g] = hi;
+        npair = g - hi;
+        cut = hi == g;
+        rstart = g == rs;
+        clipped = lo0 > rs && hi == lo0 && a[lo0 - 1].x >= lower;
+        // lchain.c:115-116 compares the segment ids of the two anchors; one id per read is the common case
+        qspan = (int)((ai.y >> 32) & 0xff);
+        // (the table path also assumes q_span > 0, which every real seed satisfies)
+        if ((g > rs && (unsigned)((ai.y >> 48) & 0xff) != (unsigned)((yprev >> 48) & 0xff)) || ((ai.y >> 32) & 0xff) == 0) atomicOr(&ctr->multi_sid, 1);
+    }
+    const unsigned cutm = __ballot_sync(0xffffffffu, cut);
+    const unsigned rsm = __ballot_sync(0xffffffffu, rstart);
+    const unsigned clm = __ballot_sync(0xffffffffu, clipped);
+    // unit boundaries: the first cut of every 32-anchor group, plus every read start (so no unit spans two reads)
+    const unsigned sel = (cutm & (0u - cutm)) | rsm;
+    // pairs of this block: summed by k_scan, not by a million same-address atomics.  npair < 2^31, so the warp sum is
+    // taken in two 16-bit halves to stay inside 32-bit redux
+    const unsigned long long psum = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair & 0xffffu) +
+                                    ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair >> 16) << 16);
+    const int qmax = __reduce_max_sync(0xffffffffu, qspan);
+    if (lane == 0) {
+        if (qmax > ctr->qs_max) atomicMax(&ctr->qs_max, qmax);
+        const int grp = g >> 5;
+        if (g0 + wid * 32 < n_total) { selmask[grp] = sel; clipmask[grp] = clm; }
+        s_cnt[wid] = __popc(sel);
+        s_pairs[wid] = psum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0;
+        unsigned long long ps = 0;
+#pragma unroll
+        for (int w = 0; w < kGroupsPerBlock; ++w) c += s_cnt[w], ps += s_pairs[w];
+        block_cnt[blockIdx.x] = c;
+        block_pairs[blockIdx.x] = ps;
+    }
+}
+
 __global__ void __launch_bounds__(kRangeThreads)
 k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, const int *__restrict__ block_read, int n_total, DevParams prm,
         int *__restrict__ st, unsigned *__restrict__ selmask, unsigned *__restrict__ clipmask, int *__restrict__ block_cnt,
@@ -154,7 +229,7 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, con
     __shared__ unsigned long long s_pairs[kGroupsPerBlock];
     const int g0 = blockIdx.x * kRangeThreads;
     const int g = g0 + threadIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int r0 = block_read[blockIdx.x];
     const bool act = g < n_total;
     ulonglong2 ai = make_ulonglong2(0, 0);
@@ -194,68 +269,97 @@ k_range(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, con
         }
     }
     const int h0 = g0 - hist;   // s_x[kRangeHist + (j - g0)] is valid for j in [max(h0, 0), g0 + 256)
-    bool cut = false, clipped = false, rstart = false;
-    int npair = 0, qspan = 0;
-    if (act) {
-        int r = r0;
-        while (off[r + 1] <= (long long)g) ++r;
-        const int rs = (int)off[r];
-        const unsigned long long xi = ai.x;
-        const unsigned lo32 = (unsigned)xi;
-        // lchain.c:172: j is in the window iff same rid/strand and x_i <= x_j + max_dist_x  <=>  x_j >= lower
-        const unsigned long long lower = (xi & 0xffffffff00000000ULL) | (unsigned long long)(lo32 > mdx ? lo32 - mdx : 0u);
-        const long long lo_ll = (long long)g - (long long)prm.max_iter;   // lchain.c:173
-        const int lo0 = lo_ll > (long long)rs ? (int)lo_ll : rs;
-        int hi;
-        const int lo_s = max(lo0, max(h0, 0));   // oldest candidate available in shared memory
-        const int sb = kRangeHist - g0;   // s_x[sb + j] = x of anchor j
-        if (lo_s > lo0 && s_x[sb + lo_s] >= lower) {
-            hi = window_start_global(a, g, lo0, lower);   // window reaches beyond the staged history (rare)
-        } else {
-            // first index in [lo_s, g] with x >= lower; x[g] itself qualifies
-            int bad = lo_s - 1;
-            hi = g;
-            while (hi - bad > 1) {
-                const int mid = (hi + bad) >> 1;
-                if (s_x[sb + mid] >= lower) hi = mid; else bad = mid;
-            }
-        }
-        st[g] = hi;
-        npair = g - hi;
-        cut = hi == g;
-        rstart = g == rs;
-        clipped = lo0 > rs && hi == lo0 && a[lo0 - 1].x >= lower;
-        // lchain.c:115-116 compares the segment ids of the two anchors; one id per read is the common case
-        qspan = (int)((ai.y >> 32) & 0xff);
-        // (the table path also assumes q_span > 0, which every real seed satisfies)
-        if ((g > rs && (unsigned)((ai.y >> 48) & 0xff) != (unsigned)((yprev >> 48) & 0xff)) || ((ai.y >> 32) & 0xff) == 0) atomicOr(&ctr->multi_sid, 1);
-    }
-    const unsigned cutm = __ballot_sync(0xffffffffu, cut);
-    const unsigned rsm = __ballot_sync(0xffffffffu, rstart);
-    const unsigned clm = __ballot_sync(0xffffffffu, clipped);
-    // unit boundaries: the first cut of every 32-anchor group, plus every read start (so no unit spans two reads)
-    const unsigned sel = (cutm & (0u - cutm)) | rsm;
-    // pairs of this block: summed by k_scan, not by a million same-address atomics.  npair < 2^31, so the warp sum is
-    // taken in two 16-bit halves to stay inside 32-bit redux
-    const unsigned long long psum = (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair & 0xffffu) +
-                                    ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)npair >> 16) << 16);
-    const int qmax = __reduce_max_sync(0xffffffffu, qspan);
-    if (lane == 0) {
-        if (qmax > ctr->qs_max) atomicMax(&ctr->qs_max, qmax);
-        const int grp = g >> 5;
-        if (g0 + wid * 32 < n_total) { selmask[grp] = sel; clipmask[grp] = clm; }
-        s_cnt[wid] = __popc(sel);
-        s_pairs[wid] = psum;
-    }
+    const unsigned long long *xb = s_x + (kRangeHist - g0);   // xb[j] = x of anchor j
+    range_tail(a, off, r0, n_total, prm, ai, yprev, g0, h0, [xb](int j) { return xb[j]; }, st, selmask, clipmask, block_cnt, block_pairs, ctr,
+               s_cnt, s_pairs);
+}
+
+// ---- the same kernel with the staging done by the bulk-copy engine (TMA, 1-D): thread 0 issues ONE cp.async.bulk for the block's own
+//      256 anchors plus the first 256 of history (8 KB of whole 16-byte anchors, contiguous in the flat array), every thread waits
+//      on the mbarrier, and further history comes 4 KB at a time the same way.  No LDG -> STS hop through registers and a single
+//      wait per chunk instead of two block barriers; the price is 16 instead of 8 bytes of shared memory per staged anchor and
+//      a binary search over 16-byte strides.  Selected with MM2GB_RANGE_TMA=1 (measured against the plain kernel in profiles/).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__global__ void __launch_bounds__(kRangeThreads)
+k_range_tma(const ulonglong2 *__restrict__ a, const long long *__restrict__ off, const int *__restrict__ block_read, int n_total, DevParams prm,
+            int *__restrict__ st, unsigned *__restrict__ selmask, unsigned *__restrict__ clipmask, int *__restrict__ block_cnt,
+            unsigned long long *__restrict__ block_pairs, Counters *__restrict__ ctr)
+{
+    __shared__ __align__(128) ulonglong2 s_a[kRangeHist + kRangeThreads];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_cnt[kGroupsPerBlock];
+    __shared__ unsigned long long s_pairs[kGroupsPerBlock];
+    const int g0 = blockIdx.x * kRangeThreads;
+    const int g = g0 + threadIdx.x;
+    const int r0 = block_read[blockIdx.x];
+    const bool act = g < n_total;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int c = 0;
-        unsigned long long ps = 0;
-#pragma unroll
-        for (int w = 0; w < kGroupsPerBlock; ++w) c += s_cnt[w], ps += s_pairs[w];
-        block_cnt[blockIdx.x] = c;
-        block_pairs[blockIdx.x] = ps;
+    unsigned phase = 0;
+    // own anchors + the first chunk of history: [max(0, g0 - 256), min(n_total, g0 + 256))
+    {
+        const int lo = max(0, g0 - kRangeThreads), hi = min(n_total, g0 + kRangeThreads);
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)(hi - lo) * 16u;
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(&s_a[kRangeHist + (lo - g0)], a + lo, bytes, &s_bar);
+        }
     }
+    const long long rs0 = off[r0];
+    mbar_wait(&s_bar, phase);
+    phase ^= 1u;
+    const ulonglong2 *ab = s_a + (kRangeHist - g0);   // ab[j] = anchor j
+    ulonglong2 ai = make_ulonglong2(0, 0);
+    if (act) ai = ab[g];
+    const unsigned long long yprev = (act && g > 0) ? ab[g - 1].y : 0ULL;
+    const unsigned mdx = (unsigned)prm.max_dist_x;
+    int hist = kRangeThreads;
+    {
+        const unsigned long long x0 = ab[g0].x;
+        const unsigned x0lo = (unsigned)x0;
+        const unsigned long long lower0 = (x0 & 0xffffffff00000000ULL) | (unsigned long long)(x0lo > mdx ? x0lo - mdx : 0u);
+        for (;;) {
+            // the oldest staged anchor (g0 - hist) still inside the first anchor's window and read?  every thread decides alike
+            const int oldest = g0 - hist;
+            if (!(oldest > rs0 && ab[oldest].x >= lower0) || hist >= kRangeHist) break;
+            const int lo = max(0, oldest - kRangeThreads);
+            __syncthreads();    // everyone has passed the previous wait before the barrier is armed again
+            if (threadIdx.x == 0) {
+                const unsigned bytes = (unsigned)(oldest - lo) * 16u;
+                mbar_expect_tx(&s_bar, bytes);
+                bulk_g2s(&s_a[kRangeHist + (lo - g0)], a + lo, bytes, &s_bar);
+            }
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            hist += kRangeThreads;
+        }
+    }
+    const int h0 = g0 - hist;
+    range_tail(a, off, r0, n_total, prm, ai, yprev, g0, h0, [ab](int j) { return ab[j].x; }, st, selmask, clipmask, block_cnt, block_pairs, ctr,
+               s_cnt, s_pairs);
 }
 
 // k_scan: exclusive prefix of the per-block unit counts, total -> ctr->n_units.  One CTA per chunk of 8192 entries (8 consecutive
@@ -819,9 +923,15 @@ __device__ __forceinline__ int ring_lower_bound(const RecP *ring, int u0, int fr
     return t0;
 }
 
+#ifndef MM2GB_SCORE_PREFETCH
+#define MM2GB_SCORE_PREFETCH 2     // measured (profiles/r5b_ab.jsonl): 0 -> 2.104 ms, 1 -> 2.117 ms, 2 -> 2.097 ms per launch on configs[1]
+#endif
+constexpr int kStageBytes = MM2GB_SCORE_PREFETCH == 2 ? 32 * 16 + 32 * 4 : 0;   // per warp, behind the rings
+
 template <int R>
 __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p,
-                                  int u0, int u1, int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecP *ring, int lane)
+                                  int u0, int u1, int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecP *ring, int lane,
+                                  unsigned char *stage)
 {
     const unsigned full = 0xffffffffu;
     const unsigned bw = (unsigned)P.bw, bw2 = 2u * (unsigned)P.bw;
@@ -830,12 +940,46 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
     const int far_d = maxd_q - P.bw;        // dr <= far_d   =>  dq <= maxd_q inside the band
     int pen = 0; // scratch of the table load, only rewritten inside the band
     int jA = u0, jB = u0; // first predecessor with x >= x_last - far_d / x >= x_first - near_d (monotone inside a rid/strand run)
+    // MM2GB_SCORE_PREFETCH (build-time experiment, profiles/r5*_prefetch*): how a tile's own anchors + window starts reach the
+    // lanes.  0 = loaded at the top of the tile (other warps cover the latency); 1 = the next tile's loads are issued into
+    // registers before this tile's predecessors are walked; 2 = the same through cp.async (LDGSTS) into a 640-byte per-warp
+    // staging area behind the rings, so the prefetch costs no registers (the kernel sits at its 80-register cap).
+#if MM2GB_SCORE_PREFETCH == 1
+    uint4 an = make_uint4(0, 0, 0, 0);
+    int stn = INT32_MAX;
+    if (u0 + lane < u1) { an = __ldg(a + u0 + lane); stn = st[u0 + lane]; }
+#elif MM2GB_SCORE_PREFETCH == 2
+    uint4 *stage_a = reinterpret_cast<uint4 *>(stage);
+    int *stage_st = reinterpret_cast<int *>(stage_a + 32);
+    const unsigned sa_s = (unsigned)__cvta_generic_to_shared(stage_a + lane), ss_s = (unsigned)__cvta_generic_to_shared(stage_st + lane);
+    if (u0 + lane < u1) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa_s), "l"(a + u0 + lane) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ss_s), "l"(st + u0 + lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     for (int t0 = u0; t0 < u1; t0 += 32) {
         const int i = t0 + lane;
         const bool act = i < u1;
         uint4 ai = make_uint4(0, 0, 0, 0);
         int sti = INT32_MAX; // inactive lanes: empty window
+#if MM2GB_SCORE_PREFETCH == 1
+        ai = an; sti = stn;
+        an = make_uint4(0, 0, 0, 0); stn = INT32_MAX;
+        if (i + 32 < u1) { an = __ldg(a + i + 32); stn = st[i + 32]; }
+#elif MM2GB_SCORE_PREFETCH == 2
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (act) { ai = stage_a[lane]; sti = stage_st[lane]; }
+        // a lane only ever reads and refills its own slot; the refill is issued after the reads above have returned (in-order
+        // issue: the instructions between consume ai / sti) and lands hundreds of cycles later
+        if (i + 32 < u1 && (int)ai.x + sti != INT32_MIN + 1) {   // (always true: ties the refill to the values just read)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa_s), "l"(a + i + 32) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ss_s), "l"(st + i + 32) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#else
         if (act) { ai = __ldg(a + i); sti = st[i]; }
+#endif
         const int xi = (int)ai.x, yi = (int)ai.z, qsi = (int)(ai.w & 0xffu);
         const int D = xi - yi + (int)bw;
         const int nact = min(32, u1 - t0);
@@ -881,9 +1025,14 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
         const int slot = i - u0;
         const int qk = qsi << kSlotBits;
         int gown = ((thr & ~kSlotMask) | slot) + qk; // this anchor as a predecessor: current score (+ own q_span), own slot
+        // bit s: anchor t0 + s is inside the window of its successor t0 + s + 1.  Window starts never decrease along a unit, so a
+        // clear bit means NO later anchor of the tile has t0 + s in its window either: a half without set bits has no in-tile
+        // candidates at all (tiles of isolated hits -- the chance hits of a large reference -- skip the triangle altogether)
+        const unsigned needm = __ballot_sync(full, act && sti < i) >> 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
+            if (((needm >> (16 * h)) & 0xffffu) == 0) continue;
             int w[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -960,7 +1109,8 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
             if (lane == 0) atomicAdd(&ctr->n_exact, 1);
             score_unit_exact<FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, lane);
         } else if (FAST && u1 - u0 <= (1 << kSlotBits) && (u1 - u0 + 1) * qs_max < (1 << 18)) {
-            score_unit_packed<R>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, reinterpret_cast<RecP *>(ring), lane);
+            score_unit_packed<R>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, reinterpret_cast<RecP *>(ring), lane,
+                                 reinterpret_cast<unsigned char *>(smem_raw) + (size_t)kScoreWarps * R * sizeof(Rec) + (threadIdx.x >> 5) * kStageBytes);
         } else {
             score_unit_tiled<R, FAST>(a, st, f, p, u0, u1, rbase, P, lut_s, ring, lane);
         }

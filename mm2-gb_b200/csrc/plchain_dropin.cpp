@@ -83,6 +83,8 @@ Misc_abi g_misc;
 std::mutex g_mu;
 std::vector<ThreadState *> g_state;
 std::atomic<long long> g_h2d_bytes(0), g_d2h_bytes(0);   // bytes that crossed PCIe since the last reset (mm2gb_dropin_traffic)
+constexpr int kMaxDev = 64;
+std::atomic<long long> g_dev_batches[kMaxDev];           // batches launched per GPU since init_stream_gpu (mm2gb_dropin_device_batches)
 
 [[noreturn]] void die(const char *what)
 {
@@ -341,6 +343,7 @@ extern "C" void init_stream_gpu(size_t *max_total_n, int *max_reads, int *min_n,
     VLOG(2, "init_stream_gpu: config loaded, %d GPU(s), batch limit %zu anchors", g_cfg.n_gpus, g_cfg.max_total_n);
     g_misc = misc;
     g_inited = true;
+    for (auto &b : g_dev_batches) b = 0;
     if (max_total_n) *max_total_n = g_cfg.max_total_n;
     if (max_reads) *max_reads = g_cfg.max_read;
     if (min_n) *min_n = g_cfg.min_n;
@@ -396,6 +399,7 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
     if (in && total > 0) {
         ++S.n_batches;
         S.n_anchors += total;
+        if (S.device >= 0 && S.device < kMaxDev) ++g_dev_batches[S.device];
         int r0 = 0;
         for (int k = 0; k < n_sub && r0 < n_in; ++k) {
             int r1 = r0;
@@ -475,4 +479,10 @@ extern "C" void mm2gb_dropin_traffic(long long out[2], int reset)
 {
     if (out) { out[0] = g_h2d_bytes.load(); out[1] = g_d2h_bytes.load(); }
     if (reset) { g_h2d_bytes = 0; g_d2h_bytes = 0; }
+}
+
+// batches launched on GPU `device` since init_stream_gpu (thread_id t drives GPU gpu_base + t % n_gpus)
+extern "C" long long mm2gb_dropin_device_batches(int device)
+{
+    return device >= 0 && device < kMaxDev ? g_dev_batches[device].load() : 0;
 }

@@ -216,6 +216,44 @@ def test_driver_call_pattern_many_threads(pkg, po, synth, tmp_path, n_threads, b
     del os.environ["MM2GB_SUB_MIN"]
 
 
+@pytest.mark.gpu
+def test_threads_spread_over_gpus(pkg, po, synth, tmp_path):
+    """thread_id t drives GPU t % n_gpus (all visible GPUs by default).  Six worker threads on a box with at least two
+    GPUs: every GPU chains batches and every read's result equals the oracle's.  Skipped on a one-GPU box."""
+    n_gpus = pkg.lib().mm2gb_device_count()
+    if n_gpus < 2:
+        pytest.skip("needs at least two GPUs")
+    L = _lib(pkg)
+    L.fake_drive.restype = C.c_double
+    L.fake_drive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_void_p]
+    L.mm2gb_dropin_device_batches.restype = C.c_longlong
+    L.mm2gb_dropin_device_batches.argtypes = [C.c_int]
+    cfg = tmp_path / "cfg.json"
+    cfg.write_text('{"max_total_n": 400000, "max_read": 5000, "n_gpus": 0}')
+    for k in ("MM2GB_N_GPUS", "MM2GB_GPU_BASE"):
+        os.environ.pop(k, None)
+    misc = pkg.map_ont_misc()
+    prm = po.map_ont_params()
+    L.fake_set_misc(C.byref(misc))
+    mx, mr, mn = C.c_size_t(0), C.c_int(0), C.c_int(-1)
+    L.init_stream_gpu(C.byref(mx), C.byref(mr), C.byref(mn), str(cfg).encode(), misc)
+    n_threads = 6
+    a, off = synth.ont_like_batch(411, 240, 1, 4000, repeat_copies=2, repeat_len=40)
+    n_reads = len(off) - 1
+    nu = np.zeros(n_reads, np.int32); nb = np.zeros(n_reads, np.int64)
+    hu = np.zeros(n_reads, np.uint64); hb = np.zeros(n_reads, np.uint64)
+    dt = L.fake_drive(a.ctypes.data, off.ctypes.data, n_reads, n_threads, 0, 2, 60000, 1, nu.ctypes.data, nb.ctypes.data, hu.ctypes.data, hb.ctypes.data)
+    assert dt > 0
+    used = [L.mm2gb_dropin_device_batches(d) for d in range(n_gpus)]
+    assert all(u > 0 for u in used[:min(n_gpus, n_threads)]), used
+    for r in range(n_reads):
+        o = po.oracle_lchain(prm, a[int(off[r]):int(off[r + 1])])
+        assert nu[r] == len(o.u) and nb[r] == len(o.b), r
+        assert int(hu[r]) == _digest(o.u) and int(hb[r]) == _digest(o.b), r
+    L.free_stream_gpu(n_threads)
+
+
 _GUARD = """
 import ctypes as C, os, sys
 sys.path.insert(0, {root!r})

@@ -225,3 +225,27 @@ def test_large_batch_properties(pkg, po, synth):
 def test_smoke_entry():
     import __graft_entry__ as entry
     entry.smoke()
+
+
+def test_range_kernel_tma_variant(pkg, po, synth, monkeypatch):
+    """k_range_tma (x history staged by cp.async.bulk + mbarrier, MM2GB_RANGE_TMA=1) against the plain k_range and the oracle:
+    ragged batches with empty reads, reads that start on and next to a 256-anchor block boundary, windows longer than the staged
+    history (dense reads: global-memory fallback), clipped windows, the golden reads"""
+    rng = np.random.default_rng(77)
+    reads = [a for _, (a, over) in synth.adversarial_suite().items() if not over]
+    reads += [synth.ont_like_anchors(rng, n) for n in (255, 256, 257, 511, 513, 1, 2, 3000, 9000)]
+    reads += [synth.ont_like_anchors(rng, 4000, mean_gap=3.0)]           # ~1700 anchors per window: beyond the 1024 staged
+    reads = [reads[0][:0]] + reads + [reads[0][:0]]
+    off = np.zeros(len(reads) + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    a = np.concatenate(reads)
+    prm = po.map_ont_params()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MM2GB_RANGE_TMA", mode)
+        with pkg.ChainContext(pkg.map_ont_misc(), max_anchors=1 << 18, max_reads=256, n_slots=1) as c:
+            st = _check_batch(pkg, po, c, a, off, prm, chains=False)
+            f, p, _ = c.chain_dp(a, off)
+            out[mode] = (f.copy(), p.copy(), st.n_pairs, st.n_units, st.n_units_exact)
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    assert out["0"][2:] == out["1"][2:]
