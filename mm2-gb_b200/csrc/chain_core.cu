@@ -16,9 +16,12 @@
 #include "wire.h"
 #include "../../include/mm2gb_chain.h"
 
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -159,6 +162,20 @@ struct Slot {
 
 constexpr int kMaxSlots = 8;
 
+// per-device state shared by every context of the process on that device (never torn down: the streams live as long as the
+// process does)
+struct DevicePool {
+    std::mutex mu;
+    bool ready = false;
+    int ring = 0;
+    size_t score_smem = 0;
+    int score_blocks = 0, long_blocks = 0;
+    cudaStream_t bt_stream[kBtStreams] = {nullptr};
+    std::atomic<unsigned> rr{0};
+};
+constexpr int kMaxDevices = 64;
+static DevicePool g_pool[kMaxDevices];
+
 struct mm2gb_ctx {
     int device = 0, n_sm = 0;
     size_t max_anchors = 0;
@@ -181,8 +198,9 @@ struct mm2gb_ctx {
     // consecutive chunks queue behind each other (the global-memory class runs on the slot's own stream).  With the slots'
     // own streams the pool stays within the hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 below), so streams
     // do not alias onto one queue and serialise falsely.
-    cudaStream_t bt_stream[kBtStreams] = {nullptr};   // handed out round robin to the size-class launches of all slots
-    unsigned bt_rr = 0;
+    cudaStream_t *bt_stream = nullptr;                // the device's pool of class streams (DevicePool), round robin over all contexts
+    std::atomic<unsigned> *bt_rr = nullptr;
+    bool pin_registered = false;                      // pin_block is our own huge-page allocation, registered with CUDA
     int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
     bool range_tma = false;      // k_range_tma (history staged by cp.async.bulk) instead of k_range: MM2GB_RANGE_TMA=1
     int wire_mode = 0;           // 0 auto: pinned sources are DMA'd raw, pageable ones are packed by the gather pass; 1 always raw
@@ -535,7 +553,7 @@ static int enqueue_backtrack(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4
         CK(cudaEventRecord(sl.bt_fork, s));
         for (int k = kBtBig - 1; k >= 0; --k) { // longest first
             if (!cnt[k]) continue;
-            cudaStream_t bs = c->bt_stream[c->bt_rr++ % kBtStreams];
+            cudaStream_t bs = c->bt_stream[c->bt_rr->fetch_add(1) % kBtStreams];
             CK(cudaStreamWaitEvent(bs, sl.bt_fork, 0));
             const int *list = sl.d_list + base[k];
             if (k >= kBtMid0) launch_backtrack_mid(bs, d_a, d_f, d_p, d_off, list, cnt[k], kBtCaps[k], bp, sl);
@@ -610,7 +628,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
+    if (device < 0 || device >= ndev || device >= kMaxDevices) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
     CK(cudaSetDevice(device));
     mm2gb_ctx *c = new mm2gb_ctx();
     c->device = device;
@@ -638,6 +656,18 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         int r = atoi(e);
         if (r >= 1 && r <= 4096) c->drain_blocks = r;
     }
+    // where the time of a context creation goes (MM2GB_VERBOSE >= 3; driver threads create theirs concurrently and the CUDA
+    // driver serialises most of these calls)
+    const bool vt = getenv("MM2GB_VERBOSE") && atoi(getenv("MM2GB_VERBOSE")) >= 3;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_phase = now();
+    auto phase = [&](const char *what) {
+        if (!vt) return;
+        const double t = now();
+        fprintf(stderr, "[mm2gb] ctx %p: %-28s %8.3f ms\n", (void *)c, what, 1e3 * (t - t_phase));
+        t_phase = t;
+    };
+    phase("device + properties");
     int rc = MM2GB_OK;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
@@ -651,14 +681,34 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         CKC(cudaMalloc(&c->d_lut, (size_t)2 * kLutMax + 16));
         rc = setup_params(c, misc);
         if (rc) goto bad;
-        rc = c->ring == 256 ? config_ring<256>(c) : c->ring == 1024 ? config_ring<1024>(c) : config_ring<512>(c);
-        if (rc) goto bad;
-        rc = config_long(c);
-        if (rc) goto bad;
-        rc = config_backtrack();
-        if (rc) goto bad;
-        if (c->chains_ok)
-            for (int k = 0; k < kBtStreams; ++k) CKC(cudaStreamCreateWithFlags(&c->bt_stream[k], cudaStreamNonBlocking));
+        phase("penalty table");
+        {
+            // what is the same for every context of a device is set up once: the kernels' shared-memory attributes and grid sizes,
+            // and the pool of class streams.  (Sixteen driver threads creating their contexts at once spent seconds queueing for the
+            // driver's lock on ~30 attribute calls and 24 stream creations EACH; profiles/r5d_ctx_probe.txt.)
+            DevicePool &dp = g_pool[device];
+            std::lock_guard<std::mutex> lk(dp.mu);
+            if (!dp.ready || dp.ring != c->ring) {
+                rc = c->ring == 256 ? config_ring<256>(c) : c->ring == 1024 ? config_ring<1024>(c) : config_ring<512>(c);
+                if (rc) goto bad;
+                rc = config_long(c);
+                if (rc) goto bad;
+                rc = config_backtrack();
+                if (rc) goto bad;
+                for (int k = 0; k < kBtStreams; ++k)
+                    if (!dp.bt_stream[k]) CKC(cudaStreamCreateWithFlags(&dp.bt_stream[k], cudaStreamNonBlocking));
+                dp.ring = c->ring; dp.score_smem = c->score_smem; dp.score_blocks = c->score_blocks; dp.long_blocks = c->long_blocks;
+                dp.ready = true;
+            } else {
+                c->score_smem = dp.score_smem; c->score_blocks = dp.score_blocks; c->long_blocks = dp.long_blocks;
+            }
+            c->long_wave = c->long_blocks;
+            if (const char *e = getenv("MM2GB_LONG_WAVE")) c->long_wave = atoi(e);
+            c->bt_stream = dp.bt_stream;
+            c->bt_rr = &dp.rr;
+        }
+        phase("kernel attributes + streams");
+        phase("24 class streams");
         const size_t n = max_anchors, n_groups = (n + 31) / 32, n_blocks = (n + kRangeThreads - 1) / kRangeThreads;
         const size_t n_units_cap = n_groups + (size_t)max_reads + 2;
         const size_t n_chunks = n_blocks / kScanChunk + 2, n_rd = (size_t)max_reads + 1;
@@ -724,7 +774,30 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
         size_t dev_bytes = 0, pin_bytes = 0;
         layout(nullptr, nullptr, &dev_bytes, &pin_bytes);
         CKC(cudaMalloc(&c->dev_block, dev_bytes));
-        CKC(cudaMallocHost(&c->pin_block, pin_bytes));
+        phase("device block");
+        {
+            // The staging block: transparent-huge-page backed memory of our own, registered with CUDA.  Pinning is paid per page,
+            // so 2 MB pages make this ~10x cheaper than cudaMallocHost's 4 KB pages (which took ~100 ms per 230 MB and serialised
+            // the driver threads), and the host pass over the staging area takes fewer TLB misses.  MM2GB_PIN=alloc: cudaMallocHost.
+            const char *pm = getenv("MM2GB_PIN");
+            bool done = false;
+            if (!pm || strcmp(pm, "alloc") != 0) {
+                const size_t huge = (size_t)2 << 20, bytes = (pin_bytes + huge - 1) & ~(huge - 1);
+                void *ptr = nullptr;
+                if (posix_memalign(&ptr, huge, bytes) == 0 && ptr) {
+                    madvise(ptr, bytes, MADV_HUGEPAGE);
+                    for (size_t o = 0; o < bytes; o += 4096) static_cast<volatile char *>(ptr)[o] = 0;   // fault the pages in
+                    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+                        c->pin_block = ptr; c->pin_registered = true; done = true;
+                    } else {
+                        cudaGetLastError();
+                        free(ptr);
+                    }
+                }
+            }
+            if (!done) CKC(cudaMallocHost(&c->pin_block, pin_bytes));
+        }
+        phase("pinned block");
         layout(static_cast<char *>(c->dev_block), static_cast<char *>(c->pin_block), &dev_bytes, &pin_bytes);
         c->dev_bytes = dev_bytes; c->pin_bytes = pin_bytes;
         for (int i = 0; i < n_slots; ++i) {
@@ -739,6 +812,8 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             }
         }
     }
+    phase("slot streams + events");
+    if (vt) fprintf(stderr, "[mm2gb] ctx %p: %.1f MB device, %.1f MB pinned\n", (void *)c, c->dev_bytes / 1e6, c->pin_bytes / 1e6);
     *out = c;
     return MM2GB_OK;
 bad:
@@ -752,9 +827,9 @@ extern "C" void mm2gb_ctx_destroy(mm2gb_ctx_t *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (int i = 0; i < kMaxSlots; ++i) free_slot(c->slot[i]);
-    for (int k = 0; k < kBtStreams; ++k) if (c->bt_stream[k]) cudaStreamDestroy(c->bt_stream[k]);
     cudaFree(c->dev_block);
-    cudaFreeHost(c->pin_block);
+    if (c->pin_registered) { if (c->pin_block) { cudaHostUnregister(c->pin_block); free(c->pin_block); } }
+    else cudaFreeHost(c->pin_block);
     prof_collect(c);
     cudaFree(c->d_lut);
     delete c;

@@ -70,11 +70,17 @@ def main():
     ndiff = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
     warn = [ln for ln in gpu_err.splitlines() if "WARNING" in ln or "ERROR" in ln][:5]
     per_thread = [ln for ln in gpu_err.splitlines() if ln.startswith("[mm2gb] thread")]
+    gpus = {}
+    for ln in per_thread:   # "[mm2gb] thread 3 (GPU 1): 2 batches, 1989314 anchors; ..."
+        m = re.match(r"\[mm2gb\] thread \d+ \(GPU (\d+)\): (\d+) batches, (\d+) anchors", ln)
+        if m:
+            g = gpus.setdefault("gpu%s" % m.group(1), {"threads": 0, "batches": 0, "anchors": 0})
+            g["threads"] += 1; g["batches"] += int(m.group(2)); g["anchors"] += int(m.group(3))
     print(json.dumps({"workload": wl, "reads": w["n_reads"], "ref_len": w["ref_len"], "fasta_generation_s": gen_s,
                       "cpu": {"binary": "minimap2_ref_timed -t %d --max-chain-skip=2147483647" % T, "wall_s": cpu_s, "paf_md5": hashlib.md5(cpu_paf).hexdigest(),
                               "paf_lines": len(a), "timers": timers(cpu_err)},
                       "gpu": {"binary": "minimap2_b200_timed -t %d --gpu-chain" % G, "wall_s": gpu_s, "paf_md5": hashlib.md5(gpu_paf).hexdigest(),
-                              "paf_lines": len(b), "timers": timers(gpu_err), "messages": warn,
+                              "paf_lines": len(b), "timers": timers(gpu_err), "messages": warn, "work_per_gpu": gpus,
                               "boundary_per_thread": per_thread[:4] + (["... %d more" % (len(per_thread) - 4)] if len(per_thread) > 4 else [])},
                       "paf_lines_differing": ndiff, "paf_identical": cpu_paf == gpu_paf}))
     if cpu_paf != gpu_paf:
