@@ -58,6 +58,8 @@ const char *mm2gb_last_error(void);
 int mm2gb_device_count(void);
 /* free / total memory of a device in bytes (for sizing contexts: ~90 B of device and ~28 B of pinned memory per anchor and slot) */
 int mm2gb_device_memory(int device, size_t *free_bytes, size_t *total_bytes);
+/* total memory only, without creating a context on the device (bringing a GPU up can take seconds) */
+int mm2gb_device_total_memory(int device, size_t *total_bytes);
 
 /* One context per (host thread, GPU).  `max_anchors` / `max_reads` bound one batch; `n_slots` (1..8) is the
  * number of batches that may be in flight (each slot owns a stream, pinned staging and device buffers).

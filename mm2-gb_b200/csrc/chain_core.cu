@@ -61,6 +61,15 @@ extern "C" int mm2gb_device_count(void)
     return n;
 }
 
+// total memory of a device WITHOUT creating a context on it (a context costs seconds the first time a GPU is brought up)
+extern "C" int mm2gb_device_total_memory(int device, size_t *total_bytes)
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (total_bytes) *total_bytes = prop.totalGlobalMem;
+    return MM2GB_OK;
+}
+
 extern "C" int mm2gb_device_memory(int device, size_t *free_bytes, size_t *total_bytes)
 {
     int cur = 0;

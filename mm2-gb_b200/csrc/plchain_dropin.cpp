@@ -29,8 +29,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unistd.h>
 #include <vector>
 
@@ -85,6 +87,97 @@ std::vector<ThreadState *> g_state;
 std::atomic<long long> g_h2d_bytes(0), g_d2h_bytes(0);   // bytes that crossed PCIe since the last reset (mm2gb_dropin_traffic)
 constexpr int kMaxDev = 64;
 std::atomic<long long> g_dev_batches[kMaxDev];           // batches launched per GPU since init_stream_gpu (mm2gb_dropin_device_batches)
+
+// ---- start-up off the critical path -------------------------------------------------------------------------------------
+// Bringing CUDA up (driver initialisation, a primary context per GPU, loading the kernels) takes 1-3 s per process and a
+// chaining context ~50 ms more per driver thread, all serialised inside the driver -- on a 10 k-read input that was most of the
+// chaining stage (profiles/r4h_driver_ont.json: 3.2 s per thread).  None of it depends on the reads, so it runs on background
+// threads while the driver is still busy elsewhere:
+//   * early_warm: started by a load-time constructor when the process was started with --gpu-chain (or MM2GB_EARLY_INIT=1):
+//     initialises every visible GPU while the driver parses options and loads / builds the index;
+//   * the context pool: started by init_stream_gpu (the batch limits are known then): creates threads_per_gpu contexts per GPU,
+//     sized for the configured batch limit, while the driver reads and seeds its first mini-batch.  A driver thread takes a
+//     ready context on its first batch (waiting for one that is still being created) and only creates its own when the pool
+//     is used up or the batch does not fit.
+std::thread *g_early = nullptr, *g_pool_thread = nullptr;   // heap objects, never destroyed: exit(1) on an error path must not meet a joinable std::thread
+std::mutex g_pool_mu;
+std::condition_variable g_pool_cv;
+struct PoolCtx { mm2gb_ctx_t *ctx; size_t cap_anchors; int cap_reads; };
+std::vector<PoolCtx> g_ready[kMaxDev];
+int g_planned[kMaxDev];            // contexts the pool thread will still deliver, per GPU
+bool g_pool_stop = false;
+std::atomic<bool> g_early_done(true);   // false while the early warm-up thread is still bringing the GPUs up
+
+Misc_abi warm_misc()
+{
+    Misc_abi m;
+    memset(&m, 0, sizeof(m));
+    m.max_iter = 5000; m.max_dist_x = 5000; m.max_dist_y = 5000; m.max_skip = 25; m.bw = 500; m.min_cnt = 3; m.min_score = 40; m.n_seg = 1;
+    m.chn_pen_gap = 0.12f; m.chn_pen_skip = 0.0f;
+    return m;
+}
+
+void warm_device(int d)
+{
+    mm2gb_ctx_t *tmp = nullptr;
+    const Misc_abi m = warm_misc();
+    if (mm2gb_ctx_create_ex(&tmp, d, 1 << 16, 16, 1, &m, MM2GB_CTX_NO_FP_STAGING) == MM2GB_OK) mm2gb_ctx_destroy(tmp);
+}
+
+void early_warm()
+{
+    const int ndev = mm2gb_device_count();
+    int n = ndev;
+    if (const char *e = getenv("MM2GB_N_GPUS")) if (atoi(e) > 0) n = std::min(ndev, atoi(e));
+    const int base = getenv("MM2GB_GPU_BASE") ? std::max(0, atoi(getenv("MM2GB_GPU_BASE"))) : 0;
+    VLOG(2, "early warm-up: CUDA is up, %d device(s)", ndev);
+    for (int d = base; d < std::min(ndev, base + n); ++d) warm_device(d);
+    VLOG(2, "early warm-up: done");
+    g_early_done = true;
+}
+
+struct EarlyInit {
+    EarlyInit()
+    {
+        bool want = getenv("MM2GB_EARLY_INIT") && atoi(getenv("MM2GB_EARLY_INIT")) != 0;
+        if (!want && !getenv("MM2GB_EARLY_INIT")) {
+            if (FILE *fp = fopen("/proc/self/cmdline", "rb")) {
+                char buf[8192];
+                const size_t n = fread(buf, 1, sizeof(buf) - 1, fp);
+                fclose(fp);
+                buf[n] = 0;
+                for (size_t i = 0; i < n; i += strlen(buf + i) + 1)
+                    if (!strcmp(buf + i, "--gpu-chain")) { want = true; break; }
+            }
+        }
+        if (want) { g_early_done = false; g_early = new std::thread(early_warm); }
+    }
+} g_early_init;
+
+std::mutex g_early_mu;
+void join_early()
+{
+    std::lock_guard<std::mutex> lk(g_early_mu);     // callable from every driver thread at once
+    if (g_early && g_early->joinable()) g_early->join();
+}
+
+void stop_pool()
+{
+    {
+        std::lock_guard<std::mutex> pl(g_pool_mu);
+        g_pool_stop = true;
+        g_pool_cv.notify_all();
+    }
+    if (g_pool_thread && g_pool_thread->joinable()) g_pool_thread->join();
+    delete g_pool_thread;
+    g_pool_thread = nullptr;
+    std::lock_guard<std::mutex> pl(g_pool_mu);
+    for (int d = 0; d < kMaxDev; ++d) {
+        for (auto &pc : g_ready[d]) mm2gb_ctx_destroy(pc.ctx);
+        g_ready[d].clear();
+        g_planned[d] = 0;
+    }
+}
 
 [[noreturn]] void die(const char *what)
 {
@@ -223,7 +316,11 @@ void load_config(const char *path)
     // available memory (pinned staging) shared by all of them.  The reference's own gpu_config.json asks for 500 M anchors
     // (sized for its 13 B/anchor buffers and one thread); that is shrunk here with a warning instead of failing in cudaMalloc.
     size_t dev_free = 0, dev_total = 0;
-    if (mm2gb_device_memory(g_cfg.gpu_base, &dev_free, &dev_total) == MM2GB_OK && dev_free) {
+    // while the GPUs are still being brought up in the background the exact free memory would mean waiting for that (a context
+    // on the device): 90 % of the total, which needs no context, is close enough for a sanity clamp
+    const bool have_mem = g_early_done.load() ? mm2gb_device_memory(g_cfg.gpu_base, &dev_free, &dev_total) == MM2GB_OK
+                                              : (mm2gb_device_total_memory(g_cfg.gpu_base, &dev_total) == MM2GB_OK && ((dev_free = (size_t)(0.9 * (double)dev_total)), true));
+    if (have_mem && dev_free) {
         const size_t by_dev = (size_t)(0.8 * (double)dev_free) / ((size_t)g_cfg.threads_per_gpu * kDevBytesPerAnchor);
         const long pages = sysconf(_SC_AVPHYS_PAGES), psz = sysconf(_SC_PAGESIZE);
         size_t by_host = SIZE_MAX;
@@ -246,8 +343,29 @@ void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi 
     const double t0 = now_s();
     if (S.ctx) mm2gb_ctx_destroy(S.ctx);
     S.ctx = nullptr;
-    if (mm2gb_ctx_create_ex(&S.ctx, S.device, cap_anchors, cap_reads, 2 * g_cfg.sub_batches, &misc, MM2GB_CTX_NO_FP_STAGING) != MM2GB_OK)
+    {   // a context from the pool, if one that fits is ready or on its way
+        std::unique_lock<std::mutex> lk(g_pool_mu);
+        const int d = S.device;
+        for (;;) {
+            auto &v = g_ready[d];
+            bool took = false;
+            for (size_t i = 0; i < v.size(); ++i)
+                if (v[i].cap_anchors >= cap_anchors && v[i].cap_reads >= cap_reads) {
+                    S.ctx = v[i].ctx; cap_anchors = v[i].cap_anchors; cap_reads = v[i].cap_reads;
+                    v.erase(v.begin() + (long)i);
+                    took = true;
+                    break;
+                }
+            if (took || g_planned[d] <= 0 || g_pool_stop) break;
+            g_pool_cv.wait(lk);
+        }
+    }
+    if (!S.ctx) join_early();
+    if (S.ctx) {
+        if (mm2gb_ctx_set_misc(S.ctx, &misc) != MM2GB_OK) die("setting the chaining parameters");
+    } else if (mm2gb_ctx_create_ex(&S.ctx, S.device, cap_anchors, cap_reads, 2 * g_cfg.sub_batches, &misc, MM2GB_CTX_NO_FP_STAGING) != MM2GB_OK) {
         die("cannot create the chaining context");
+    }
     S.cap_anchors = cap_anchors;
     S.cap_reads = cap_reads;
     S.misc = misc;
@@ -347,11 +465,52 @@ extern "C" void init_stream_gpu(size_t *max_total_n, int *max_reads, int *min_n,
     if (max_total_n) *max_total_n = g_cfg.max_total_n;
     if (max_reads) *max_reads = g_cfg.max_read;
     if (min_n) *min_n = g_cfg.min_n;
+    // the context pool (see above); MM2GB_POOL=0 switches it off
+    const bool pool_on = !(getenv("MM2GB_POOL") && atoi(getenv("MM2GB_POOL")) == 0);
+    stop_pool();    // (a second init_stream_gpu without free_stream_gpu in between: start over)
+    {
+        std::lock_guard<std::mutex> pl(g_pool_mu);
+        g_pool_stop = false;
+        for (int d = 0; d < kMaxDev; ++d) g_planned[d] = 0;
+        if (pool_on)
+            for (int k = 0; k < g_cfg.n_gpus; ++k) g_planned[g_cfg.gpu_base + k] = std::min(g_cfg.threads_per_gpu, 64);
+    }
+    if (pool_on) {
+        const Config cfg = g_cfg;
+        const Misc_abi m = misc;
+        g_pool_thread = new std::thread([cfg, m]() {
+            join_early();       // the GPUs come up on the early thread; the driver meanwhile reads and seeds its first reads
+            // a slot holds one sub-batch: its share of a full batch + the read that overshoots it (see chain_stream_gpu), with the
+            // same head room make_ctx gives a context it sizes from a first batch
+            const size_t share = cfg.max_total_n / (size_t)cfg.sub_batches + 1;
+            size_t cap = share + share / 4 + cfg.max_total_n / 8 + 4096;
+            if (cap > ((size_t)1 << 31) - 2048) cap = ((size_t)1 << 31) - 2048;
+            const int reads = cfg.max_read + cfg.max_read / 2 + 1;
+            for (int round = 0; round < std::min(cfg.threads_per_gpu, 64); ++round)
+                for (int k = 0; k < cfg.n_gpus; ++k) {       // round robin over the GPUs: every GPU gets its first context early
+                    const int d = cfg.gpu_base + k;
+                    {
+                        std::lock_guard<std::mutex> pl(g_pool_mu);
+                        if (g_pool_stop) { for (int q = 0; q < kMaxDev; ++q) g_planned[q] = 0; g_pool_cv.notify_all(); return; }
+                    }
+                    mm2gb_ctx_t *ctx = nullptr;
+                    const int rc = mm2gb_ctx_create_ex(&ctx, d, cap, reads, 2 * cfg.sub_batches, &m, MM2GB_CTX_NO_FP_STAGING);
+                    VLOG(2, "context pool: context %d for GPU %d ready", round, d);
+                    std::lock_guard<std::mutex> pl(g_pool_mu);
+                    if (rc == MM2GB_OK) g_ready[d].push_back({ctx, cap, reads});
+                    else g_planned[d] = 1;      // out of memory or similar: deliver nothing more for this GPU, threads create their own
+                    --g_planned[d];
+                    g_pool_cv.notify_all();
+                    if (rc != MM2GB_OK) { VLOG(1, "context pool: GPU %d: %s", d, mm2gb_last_error()); }
+                }
+        });
+    }
 }
 
 extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt, mm2gb_chain_read_t **in_arr_, int *n_read_, int thread_id, void *km)
 {
     ThreadState &S = state_of(thread_id);
+    if (S.n_batches == 0) VLOG(2, "thread %d: first chain_stream_gpu", thread_id);
     const Misc_abi misc = batch_misc(mi, opt);
     mm2gb_chain_read_t *in = in_arr_ ? *in_arr_ : nullptr;
     const int n_in = (n_read_ && in) ? *n_read_ : 0;
@@ -444,6 +603,8 @@ extern "C" void free_stream_gpu(int n_threads)
     const char *verbose = getenv("MM2GB_VERBOSE");
     int tid = 0;
     VLOG(2, "free_stream_gpu: start");
+    join_early();
+    stop_pool();
     for (ThreadState *&st : g_state) {
         ++tid;
         if (!st) continue;

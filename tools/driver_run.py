@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """The reference's UNMODIFIED host driver on a BASELINE.json config, CPU path against --gpu-chain (the B200 drop-in):
 
-    python tools/driver_run.py [ont|long|mini] [threads] [gpu_threads]
+    python tools/driver_run.py [ont|ont40k|long|mini] [threads] [gpu_threads]
 
 generates the reference / read FASTA of the workload (numpy simulator of mm2-gb_b200/synth.py, fixed seeds), runs
   oracle/_ref/minimap2_ref_timed  -t T -x map-ont --max-chain-skip=2147483647        (CPU ground truth, SURVEY.md trap T1)
@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry
 
 WORK = {"ont": dict(ref_len=100_000_000, n_contigs=4, n_reads=10_000, lo=10_000, hi=100_000, err=0.10, repeats=0),
+        "ont40k": dict(ref_len=100_000_000, n_contigs=4, n_reads=40_000, lo=10_000, hi=100_000, err=0.10, repeats=0),
         "long": dict(ref_len=100_000_000, n_contigs=4, n_reads=1000, lo=100_000, hi=300_000, err=0.03, repeats=3000),
         "mini": dict(ref_len=5_000_000, n_contigs=2, n_reads=300, lo=10_000, hi=100_000, err=0.10, repeats=0)}
 
@@ -51,7 +52,7 @@ def main():
     gen_s = time.time() - t0
     REF = os.path.join(ROOT, "oracle", "_ref")
     cfg = os.path.join(ROOT, "mm2-gb_b200", "b200_config.json")
-    env = dict(os.environ, MM2GB_THREADS_PER_GPU=str(G), MM2GB_VERBOSE="1")
+    env = dict(os.environ, MM2GB_THREADS_PER_GPU=str(G), MM2GB_VERBOSE=os.environ.get("MM2GB_VERBOSE", "1"))
     if os.environ.get("MM2GB_MAX_TOTAL_N"):     # a batch limit other than the shipped config's
         cfg = os.path.join(d, "cfg.json")
         open(cfg, "w").write('{"max_total_n": %d, "max_read": 200000}' % int(os.environ["MM2GB_MAX_TOTAL_N"]))
@@ -61,6 +62,8 @@ def main():
         p = subprocess.run([os.path.join(REF, binary)] + args + [ref_fa, reads_fa], capture_output=True, cwd=d, env=env)
         dt = time.time() - t1
         err = p.stderr.decode(errors="replace")
+        if os.environ.get("MM2GB_LOG_DIR"):     # the driver's own log (its [M::...] lines carry wall-clock stamps) next to the JSON
+            open(os.path.join(os.environ["MM2GB_LOG_DIR"], "%s_%s.log" % (binary, wl)), "w").write(err)
         if p.returncode != 0:
             raise SystemExit("%s failed (%d):\n%s" % (binary, p.returncode, err[-3000:]))
         return p.stdout, dt, err
