@@ -41,7 +41,7 @@ namespace {
 constexpr int kMaxSub = 4;          // sub-batches of one batch (2 batches in flight x 4 = the 8 slots of a context)
 
 struct Config {
-    size_t max_total_n = 2u << 20;  // anchors per launched batch
+    size_t max_total_n = 4u << 20;  // anchors per launched batch
     int max_read = 200000;          // reads per batch
     int min_n = 0;                  // plumbed through, unused downstream (map.c:1314)
     int n_gpus = 0;                 // 0 = all visible
@@ -49,6 +49,7 @@ struct Config {
     int sub_batches = kMaxSub;      // 1..4
     int threads_per_gpu = 4;        // sizing hint: how many driver threads share a GPU (minimap2 -t N / n_gpus)
     int64_t sub_min = 1 << 19;      // a batch is only cut into sub-batches of at least this many anchors (enough to fill the GPU)
+    int sub_min_reads = 64;         // ... and at least this many reads
 };
 
 struct Sub { int slot, r0, r1; };
@@ -306,6 +307,7 @@ void load_config(const char *path)
     if (const char *e = getenv("MM2GB_SUB_BATCHES")) g_cfg.sub_batches = std::min(kMaxSub, std::max(1, atoi(e)));
     if (const char *e = getenv("MM2GB_THREADS_PER_GPU")) g_cfg.threads_per_gpu = std::max(1, atoi(e));
     if (const char *e = getenv("MM2GB_SUB_MIN")) g_cfg.sub_min = std::max<int64_t>(1, atoll(e));
+    if (const char *e = getenv("MM2GB_SUB_MIN_READS")) g_cfg.sub_min_reads = std::max(1, atoi(e));
     if (g_cfg.max_total_n > ((size_t)1 << 31) - 2048) g_cfg.max_total_n = ((size_t)1 << 31) - 2048;
     const int ndev = mm2gb_device_count();
     if (ndev <= 0) { fprintf(stderr, "[ERROR] mm2gb chaining: --gpu-chain needs a CUDA device (no CPU fallback)\n"); exit(1); }
@@ -529,7 +531,9 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
         longest = std::max(longest, S.ns[(size_t)r]);
     }
     // sub-batches: enough anchors each to fill the GPU, at most sub_batches of them
-    const int n_sub = (int)std::max<int64_t>(1, std::min<int64_t>(g_cfg.sub_batches, total / g_cfg.sub_min));
+    // ... and enough READS each: the chain-extraction kernels run one CTA per read, and a launch of a dozen long reads leaves the
+    // GPU idle for the milliseconds its longest read takes (batches of 100-300 kb reads are not cut at all at the default limit)
+    const int n_sub = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(g_cfg.sub_batches, total / g_cfg.sub_min), n_in / g_cfg.sub_min_reads));
     const int64_t target = total / n_sub + 1;
     // (re)size the context: first use, a batch beyond the configured limits, or new chaining parameters.  A slot has to hold
     // one sub-batch: its share of the batch plus the read that overshoots it.

@@ -70,7 +70,7 @@ def test_gpu_config_is_parsed_as_json():
         assert get(bad, "a")[0] == -1, bad
     # the reference's own config file format, as shipped (copied as a fixture string: keys with "//" comments, nested kernels)
     here = os.path.join(ROOT, "mm2-gb_b200", "b200_config.json")
-    assert get(open(here).read(), "max_total_n") == (1, 2097152.0)
+    assert get(open(here).read(), "max_total_n") == (1, 4194304.0)
 
 
 def _lib(pkg):
@@ -126,7 +126,8 @@ def test_batch_handoff_protocol(pkg, po, synth, tmp_path):
     cfg = tmp_path / "cfg.json"
     cfg.write_text('{"num_streams": 1, "min_n": 512, "max_total_n": 300000, "max_read": 500, "host_threads": 4,\n'
                    ' "range_kernel": {"blockdim": 512, "max_total_n": 5}, "score_kernel": {"micro_batch": 4}}')
-    os.environ["MM2GB_SUB_MIN"] = "20000"     # small batches are cut into sub-batches too (default: 512 k anchors each at least)
+    os.environ["MM2GB_SUB_MIN"] = "20000"     # small batches are cut into sub-batches too (default: 512 k anchors and 64 reads each at least)
+    os.environ["MM2GB_SUB_MIN_READS"] = "2"
     misc = pkg.map_ont_misc()
     prm = po.map_ont_params()
     L.fake_set_misc(C.byref(misc))
@@ -170,6 +171,7 @@ def test_batch_handoff_protocol(pkg, po, synth, tmp_path):
     L.free_stream_gpu(2)
     L.free_stream_gpu(2)
     del os.environ["MM2GB_SUB_MIN"]
+    del os.environ["MM2GB_SUB_MIN_READS"]
 
 
 def _digest(w):
@@ -194,6 +196,7 @@ def test_driver_call_pattern_many_threads(pkg, po, synth, tmp_path, n_threads, b
     cfg = tmp_path / "cfg.json"
     cfg.write_text('{"max_total_n": 400000, "max_read": 5000}')
     os.environ["MM2GB_SUB_MIN"] = "30000"
+    os.environ["MM2GB_SUB_MIN_READS"] = "2"
     misc = pkg.map_ont_misc()
     prm = po.map_ont_params()
     L.fake_set_misc(C.byref(misc))
@@ -214,6 +217,7 @@ def test_driver_call_pattern_many_threads(pkg, po, synth, tmp_path, n_threads, b
         assert int(hu[r]) == _digest(o.u) and int(hb[r]) == _digest(o.b), r
     L.free_stream_gpu(n_threads)
     del os.environ["MM2GB_SUB_MIN"]
+    del os.environ["MM2GB_SUB_MIN_READS"]
 
 
 @pytest.mark.gpu
