@@ -720,6 +720,9 @@ __device__ void score_unit_tiled(const uint4 *__restrict__ a, const int *__restr
         // phase B: in-tile triangle.  static part first (independent of f), then the serial chain
         const int nact = min(32, u1 - t0);
         int fcur = bj >= 0 ? thr : qsi;
+        // the tile slots s that are predecessors of this lane's anchor (s < lane and t0 + s >= st_i), one bit test per slot below
+        const int vlo = sti - t0;
+        const unsigned vm = vlo >= lane ? 0u : (((1u << lane) - 1u) & ~((1u << max(vlo, 0)) - 1u));
 #pragma unroll
         for (int h = 0; h < 2; ++h) { // two halves keep the pre-scored set at 16 registers
             if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
@@ -730,7 +733,7 @@ __device__ void score_unit_tiled(const uint4 *__restrict__ a, const int *__restr
                 if (s < 31) {
                     int sc;
                     const bool ok = pair_score<FAST>(xi, yi, sidi, tile[s], P, lut_s, pen, sc);
-                    w[q] = (ok && s < lane && t0 + s >= sti) ? sc : kNeg;
+                    w[q] = (ok && ((vm >> s) & 1u)) ? sc : kNeg;
                 }
             }
 #pragma unroll
@@ -873,17 +876,20 @@ __device__ __forceinline__ void packed_walk(int &thr, int &pen, int j0, int j1, 
     }
 }
 
-// in-tile candidate, f-independent part: -(q_j - m + pen) << 13 if the pair is valid and (extra) holds, else kNegKey
+// in-tile candidate, f-independent part: -(q_j - m + pen) << 13 if the pair is valid and bit `BIT` of vm is set (vm: which tile
+// slots are predecessors of this lane's anchor), else kNegKey.  The vm test (bit = 1 << slot, an immediate once the slot loop is unrolled) opens the predicate chain, so it costs one LOP3.
 __device__ __forceinline__ int packed_static(int &pen, int D, int yi, int re, int ry, int rq, int maxd_q, unsigned bw, unsigned bw2,
-                                             unsigned lut_s, int extra)
+                                             unsigned lut_s, unsigned vm, unsigned bit)
 {
     int w;
     asm volatile("{\n\t"
         ".reg .pred p;\n\t"
         ".reg .s32 dq, dr, m, d;\n\t"
-        ".reg .u32 tb, ad;\n\t"
+        ".reg .u32 tb, ad, vb;\n\t"
+        "and.b32 vb, %9, %12;\n\t"
+        "setp.ne.u32 p, vb, 0;\n\t"
         "sub.s32 tb, %2, %3;\n\t"
-        "setp.le.u32 p, tb, %4;\n\t"
+        "setp.le.and.u32 p, tb, %4, p;\n\t"
         "add.u32 ad, tb, %5;\n\t"
         "@p ld.shared.u8 %1, [ad];\n\t"
         "sub.s32 dq, %6, %7;\n\t"
@@ -893,14 +899,13 @@ __device__ __forceinline__ int packed_static(int &pen, int D, int yi, int re, in
         "min.s32 m, m, %11;\n\t"
         "setp.gt.and.s32 p, m, 0, p;\n\t"
         "setp.le.and.s32 p, dq, %8, p;\n\t"
-        "setp.ne.and.s32 p, %9, 0, p;\n\t"
         "sub.s32 d, m, %11;\n\t"
         "sub.s32 d, d, %1;\n\t"
         "shl.b32 d, d, 13;\n\t"
         "selp.s32 %0, d, -1073741824, p;\n\t"
         "}"
         : "=r"(w), "+r"(pen)
-        : "r"(D), "r"(re), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q), "r"(extra), "r"(bw), "r"(rq));
+        : "r"(D), "r"(re), "r"(bw2), "r"(lut_s), "r"(yi), "r"(ry), "r"(maxd_q), "r"(vm), "r"(bw), "r"(rq), "r"(bit));
     return w;
 }
 
@@ -1029,6 +1034,9 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
         // clear bit means NO later anchor of the tile has t0 + s in its window either: a half without set bits has no in-tile
         // candidates at all (tiles of isolated hits -- the chance hits of a large reference -- skip the triangle altogether)
         const unsigned needm = __ballot_sync(full, act && sti < i) >> 1;
+        // vm: the tile slots s that are predecessors of this lane's anchor, s < lane and t0 + s >= st_i (none for an inactive lane)
+        const int vlo = sti - t0;
+        const unsigned vm = vlo >= lane ? 0u : (((1u << lane) - 1u) & ~((1u << max(vlo, 0)) - 1u));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
@@ -1039,7 +1047,7 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
                 const int s = h * 16 + q;
                 if (s < 31) {
                     const int4 r = *reinterpret_cast<const int4 *>(tile + s);
-                    w[q] = packed_static(pen, D, yi, r.x, r.z, r.w, maxd_q, bw, bw2, lut_s, (s < lane && t0 + s >= sti) ? 1 : 0);
+                    w[q] = packed_static(pen, D, yi, r.x, r.z, r.w, maxd_q, bw, bw2, lut_s, vm, 1u << s);
                 }
             }
 #pragma unroll
@@ -1348,6 +1356,9 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
         __syncwarp();
         // phase B: the in-tile triangle, f-independent parts first, then the serial chain (one shuffle per step)
         int fcur = bj >= 0 ? thr : qsi;
+        // the tile slots s that are predecessors of this lane's anchor (s < lane and t0 + s >= st_i), one bit test per slot below
+        const int vlo = sti - t0;
+        const unsigned vm = vlo >= lane ? 0u : (((1u << lane) - 1u) & ~((1u << max(vlo, 0)) - 1u));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h == 1 && nact <= 17) break; // warp-uniform: a short last tile has no candidates s >= 16
@@ -1358,12 +1369,12 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
                 if (s < 31) {
                     const int4 r = *reinterpret_cast<const int4 *>(tile + s);
                     const unsigned tb = (unsigned)(D - r.x);
-                    bool ok = tb <= bw2;
+                    bool ok = ((vm >> s) & 1u) && tb <= bw2;
                     if (ok) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pen) : "r"(lut_s + tb));
                     const int dq = yi - r.z;
                     const int dr = dq + (int)tb - (int)bw;
                     const int m = min(min(dr, dq), r.w);
-                    ok = ok && m > 0 && dq <= maxd_q && s < lane && t0 + s >= sti;
+                    ok = ok && m > 0 && dq <= maxd_q;
                     w[q] = ok ? m - pen : kNeg;
                 }
             }
