@@ -802,16 +802,27 @@ k_bt_sort_mid(const int *__restrict__ f, const long long *__restrict__ off, cons
 template <int CAP>
 struct BtWalkSmem {
     static constexpr int WC = CAP / 16 < 64 ? 64 : CAP / 16;   // chains whose start keys can be sorted here
-    unsigned long long wk[WC], wtmp[WC];    // chain-start keys (x of the first anchor) + sort scratch
-    // f[] is read from global memory (one 32-wide gather per chase batch): keeping it here would double the footprint and
-    // halve the reads resident on an SM, and this one-warp kernel is bound by latency, not by bandwidth
-    unsigned short ps[CAP + 2];             // p[] by anchor index; "none" is the sentinel index CAP, whose own entry is CAP
-    unsigned short path[32];                // the nodes of one chase batch
-    unsigned tb[CAP / 32 + 1];              // claimed bits (lchain.c: t[]); the sentinel's bit is never set
-    unsigned gp[CAP / 32];                  // bit i: f[i] - f[p[i]] > 0 (f[i] > 0 for a root), the sign a one-step walk needs
-    unsigned short wpay[WC], wpay2[WC];     // chain ids + sort scratch
-    unsigned cnt[256];
-    unsigned short start[kBtLevels * kBtRow];
+    // Two phases, one footprint: the links and claimed bits of the chain extraction are dead when the compaction sorts the chain
+    // starts, so its scratch lies over them.  (Side by side they were 26.8 KB for the 6144 class = 8 reads per SM; 13.9 KB = 15
+    // reads, and these one-warp kernels are as fast as the number of reads resident per SM.)
+    struct Walk {
+        // f[] is read from global memory (one 32-wide gather per chase batch): keeping it here would double the footprint and
+        // halve the reads resident on an SM, and this one-warp kernel is bound by latency, not by bandwidth
+        unsigned short ps[CAP + 2];             // p[] by anchor index; "none" is the sentinel index CAP, whose own entry is CAP
+        unsigned short path[32];                // the nodes of one chase batch
+        unsigned tb[CAP / 32 + 1];              // claimed bits (lchain.c: t[]); the sentinel's bit is never set
+        unsigned gp[CAP / 32];                  // bit i: f[i] - f[p[i]] > 0 (f[i] > 0 for a root), the sign a one-step walk needs
+    };
+    struct Compact {
+        unsigned long long wk[WC], wtmp[WC];    // chain-start keys (x of the first anchor) + sort scratch
+        unsigned short wpay[WC], wpay2[WC];     // chain ids + sort scratch
+        unsigned cnt[256];
+        unsigned short start[kBtLevels * kBtRow];
+    };
+    union {
+        Walk w;
+        Compact c;
+    };
 };
 
 // ---- where the walk keeps its state: shared memory (reads of <= CAP anchors) ...
@@ -850,27 +861,27 @@ struct WalkSmall {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int i = i0 + t * 32 + lane;
-                if (i < n) S.ps[i] = pv[t] < 0 ? (unsigned short)CAP : (unsigned short)pv[t];
+                if (i < n) S.w.ps[i] = pv[t] < 0 ? (unsigned short)CAP : (unsigned short)pv[t];
                 const unsigned g = __ballot_sync(0xffffffffu, i < n && fv[t] - fp[t] > 0);
-                if (lane == 0 && i0 + t * 32 < n) { S.gp[(i0 >> 5) + t] = g; S.tb[(i0 >> 5) + t] = 0; }
+                if (lane == 0 && i0 + t * 32 < n) { S.w.gp[(i0 >> 5) + t] = g; S.w.tb[(i0 >> 5) + t] = 0; }
             }
         }
-        if (lane == 0) { S.ps[CAP] = (unsigned short)CAP; S.tb[CAP / 32] = 0; }
+        if (lane == 0) { S.w.ps[CAP] = (unsigned short)CAP; S.w.tb[CAP / 32] = 0; }
     }
     __device__ __forceinline__ int fat(int i, const int *__restrict__ fr) const { return i < CAP ? fr[i] : 0; }
-    __device__ __forceinline__ int nextp(int cur) const { return S.ps[cur]; }
-    __device__ __forceinline__ int nextp_blind(int cur, unsigned &) const { return S.ps[cur]; }
-    __device__ __forceinline__ bool claimed(int i) const { return ((S.tb[i >> 5] >> (i & 31)) & 1u) != 0; }
-    __device__ __forceinline__ void claim(int i) { atomicOr(&S.tb[i >> 5], 1u << (i & 31)); }
-    __device__ __forceinline__ bool gain(int i, const int *, const int *) const { return ((S.gp[i >> 5] >> (i & 31)) & 1u) != 0; }
+    __device__ __forceinline__ int nextp(int cur) const { return S.w.ps[cur]; }
+    __device__ __forceinline__ int nextp_blind(int cur, unsigned &) const { return S.w.ps[cur]; }
+    __device__ __forceinline__ bool claimed(int i) const { return ((S.w.tb[i >> 5] >> (i & 31)) & 1u) != 0; }
+    __device__ __forceinline__ void claim(int i) { atomicOr(&S.w.tb[i >> 5], 1u << (i & 31)); }
+    __device__ __forceinline__ bool gain(int i, const int *, const int *) const { return ((S.w.gp[i >> 5] >> (i & 31)) & 1u) != 0; }
     __device__ __forceinline__ unsigned zat(int e) const { return zs[e]; }
-    __device__ __forceinline__ IDX *path() { return S.path; }
-    __device__ __forceinline__ unsigned long long *wk() { return S.wk; }
-    __device__ __forceinline__ unsigned long long *wtmp() { return S.wtmp; }
-    __device__ __forceinline__ IDX *wpay() { return S.wpay; }
-    __device__ __forceinline__ IDX *wpay2() { return S.wpay2; }
-    __device__ __forceinline__ unsigned *cnt() { return S.cnt; }
-    __device__ __forceinline__ POS *start() { return S.start; }
+    __device__ __forceinline__ IDX *path() { return S.w.path; }
+    __device__ __forceinline__ unsigned long long *wk() { return S.c.wk; }
+    __device__ __forceinline__ unsigned long long *wtmp() { return S.c.wtmp; }
+    __device__ __forceinline__ IDX *wpay() { return S.c.wpay; }
+    __device__ __forceinline__ IDX *wpay2() { return S.c.wpay2; }
+    __device__ __forceinline__ unsigned *cnt() { return S.c.cnt; }
+    __device__ __forceinline__ POS *start() { return S.c.start; }
 };
 
 // ---- ... or global scratch (any read).  p[] is read in place, the claimed bits sit in a global bit array, the sorted z[]

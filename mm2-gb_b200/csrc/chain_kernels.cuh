@@ -876,7 +876,7 @@ __device__ __forceinline__ void packed_walk(int &thr, int &pen, int j0, int j1, 
     }
 }
 
-// in-tile candidate, f-independent part: -(q_j - m + pen) << 13 if the pair is valid and bit `BIT` of vm is set (vm: which tile
+// in-tile candidate, f-independent part: (m - pen) << 13 if the pair is valid and bit `BIT` of vm is set (vm: which tile
 // slots are predecessors of this lane's anchor), else kNegKey.  The vm test (bit = 1 << slot, an immediate once the slot loop is unrolled) opens the predicate chain, so it costs one LOP3.
 __device__ __forceinline__ int packed_static(int &pen, int D, int yi, int re, int ry, int rq, int maxd_q, unsigned bw, unsigned bw2,
                                              unsigned lut_s, unsigned vm, unsigned bit)
@@ -899,8 +899,7 @@ __device__ __forceinline__ int packed_static(int &pen, int D, int yi, int re, in
         "min.s32 m, m, %11;\n\t"
         "setp.gt.and.s32 p, m, 0, p;\n\t"
         "setp.le.and.s32 p, dq, %8, p;\n\t"
-        "sub.s32 d, m, %11;\n\t"
-        "sub.s32 d, d, %1;\n\t"
+        "sub.s32 d, m, %1;\n\t"
         "shl.b32 d, d, 13;\n\t"
         "selp.s32 %0, d, -1073741824, p;\n\t"
         "}"
@@ -1029,7 +1028,9 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
         // registers, then resolved by the serial chain; halving keeps the live set at 16 values instead of 31.
         const int slot = i - u0;
         const int qk = qsi << kSlotBits;
-        int gown = ((thr & ~kSlotMask) | slot) + qk; // this anchor as a predecessor: current score (+ own q_span), own slot
+        // this anchor as an in-tile predecessor: current score, own slot.  (Ring records carry score + q_span so that the MID
+        // path needs no add; inside the tile the plain score saves one operation on every step of the serial chain.)
+        int gown = (thr & ~kSlotMask) | slot;
         // bit s: anchor t0 + s is inside the window of its successor t0 + s + 1.  Window starts never decrease along a unit, so a
         // clear bit means NO later anchor of the tile has t0 + s in its window either: a half without set bits has no in-tile
         // candidates at all (tiles of isolated hits -- the chance hits of a large reference -- skip the triangle altogether)
@@ -1056,14 +1057,14 @@ __device__ void score_unit_packed(const uint4 *__restrict__ a, const int *__rest
                 if (s < 31) {
                     const int gs = __shfl_sync(full, gown, s);
                     thr = max(thr, gs + w[q]);
-                    gown = ((thr & ~kSlotMask) | slot) + qk;
+                    gown = (thr & ~kSlotMask) | slot;
                 }
             }
         }
         if (act) {
             f[i] = thr >> kSlotBits;
             p[i] = thr == thr0 ? -1 : u0 + (thr & kSlotMask) - rbase;
-            tile[lane].g = gown;
+            tile[lane].g = gown + qk;
         }
         __syncwarp();
     }
