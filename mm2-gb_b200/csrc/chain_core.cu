@@ -119,7 +119,9 @@ struct Slot {
     unsigned *d_selmask = nullptr, *d_clipmask = nullptr;
     int *d_chunk_tot = nullptr, *d_chunk_base = nullptr; unsigned long long *d_chunk_pairs = nullptr;   // k_scan: one entry per 8192 blocks
     int *d_block_cnt = nullptr, *d_block_base = nullptr; unsigned long long *d_block_pairs = nullptr; int *d_unit_start = nullptr, *d_unit_rbase = nullptr, *d_big_order = nullptr;
+    unsigned *d_unit_clip = nullptr;         // per unit: holds a window clipped by max_iter (k_unit_clip)
     int big_cap = 0;
+    int *d_exact_list = nullptr;             // clipped units of >= kExactMin anchors, queued by k_score_units for k_score_exact
     Counters *d_ctr = nullptr;
     // device chain extraction (k_bt_sort / k_bt_walk): packed compacted anchors and chains of the batch, scratch, lists
     int *d_vp = nullptr;                     // packed indices of the compacted anchors (positions from Counters::b_cur)
@@ -211,6 +213,7 @@ struct mm2gb_ctx {
     std::atomic<unsigned> *bt_rr = nullptr;
     bool pin_registered = false;                      // pin_block is our own huge-page allocation, registered with CUDA
     int drain_blocks = 148;      // CTAs of k_drain (enough 16-byte stores in flight to fill PCIe; MM2GB_DRAIN_BLOCKS)
+    bool exact_big = true;       // the clipped units of >= kExactMin anchors that k_score_units queues: k_score_exact (a CTA each); 0: a warp each
     bool range_tma = false;      // k_range_tma (history staged by cp.async.bulk) instead of k_range: MM2GB_RANGE_TMA=1
     int wire_mode = 0;           // 0 auto: pinned sources are DMA'd raw, pageable ones are packed by the gather pass; 1 always raw
                                  // (staged by memcpy); 2 always packed (MM2GB_WIRE=auto|raw|packed)
@@ -308,7 +311,7 @@ static int config_ring(mm2gb_ctx *c)
 
 template <int R, bool FAST>
 static void launch_score(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int *st, const int *us, const int *ur,
-                         const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode)
+                         const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode, int *exact_list)
 {
     const size_t smem = (size_t)kScoreWarps * (R * sizeof(Rec) + kStageBytes);
     k_score_units<R, FAST><<<c->score_blocks, kScoreWarps * 32, smem, s>>>(a, st, us, ur, clip, f, p, big, big_cap, ctr, c->prm,
@@ -317,12 +320,12 @@ static void launch_score(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int
 
 template <bool FAST>
 static void launch_score_ring(mm2gb_ctx *c, cudaStream_t s, const uint4 *a, const int *st, const int *us, const int *ur,
-                              const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode)
+                              const unsigned *clip, int *f, int *p, const int *big, int big_cap, Counters *ctr, int run_mode, int *exact_list)
 {
     switch (c->ring) {
-    case 256: launch_score<256, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
-    case 1024: launch_score<1024, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
-    default: launch_score<512, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode); break;
+    case 256: launch_score<256, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode, exact_list); break;
+    case 1024: launch_score<1024, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode, exact_list); break;
+    default: launch_score<512, FAST>(c, s, a, st, us, ur, clip, f, p, big, big_cap, ctr, run_mode, exact_list); break;
     }
 }
 
@@ -330,6 +333,7 @@ static int config_long(mm2gb_ctx *c)
 {
     const size_t smem = (size_t)kLongRing * sizeof(RecL);
     CK(cudaFuncSetAttribute(k_score_long<kLongRing, kLongWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_score_exact<kExactRing, kExactWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kExactRing * sizeof(RecL))));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_score_long<kLongRing, kLongWarps>, kLongWarps * 32, smem));
     if (nb < 1) return fail(MM2GB_ECUDA, "long score kernel does not fit on an SM (smem %zu)", smem);
@@ -416,8 +420,9 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
         k_scan<<<(n_blocks + kScanChunk - 1) / kScanChunk, 1024, 0, s>>>(sl.d_block_cnt, sl.d_block_pairs, n_blocks, sl.d_block_base, sl.d_chunk_tot,
                                                                         sl.d_chunk_pairs, sl.d_chunk_base, sl.d_ctr);
         k_units<<<(n_groups + 255) / 256, 256, 0, s>>>(sl.d_selmask, sl.d_block_base, sl.d_chunk_base, d_off, n_reads, n, n_groups, sl.d_unit_start,
-                                                      sl.d_unit_rbase, sl.d_ctr);
-        k_order<<<(n_groups + n_reads + 256) / 256, 256, 0, s>>>(sl.d_unit_start, sl.d_big_order, sl.big_cap, sl.d_ctr);
+                                                      sl.d_unit_rbase, sl.d_unit_clip, sl.d_ctr);
+        k_unit_clip<<<(n_groups + 255) / 256, 256, 0, s>>>(sl.d_clipmask, sl.d_unit_start, n_groups, sl.d_unit_clip, sl.d_ctr);
+        k_order<<<(n_groups + n_reads + 256) / 256, 256, 0, s>>>(sl.d_unit_start, sl.d_unit_clip, sl.d_big_order, sl.big_cap, sl.d_ctr, c->fast ? 1 : 0);
     }
     {
         ProfScope ps(c, T_SCORE, s, prof);
@@ -426,10 +431,17 @@ static int enqueue_kernels(mm2gb_ctx *c, Slot &sl, cudaStream_t s, const uint4 *
                 k_score_long<kLongRing, kLongWarps><<<c->long_blocks, kLongWarps * 32, (size_t)kLongRing * sizeof(RecL), s>>>(
                     d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, c->prm, c->d_lut,
                     c->long_classes, c->long_wave);
-            launch_score_ring<true>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 1);
-            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 2);
+            int *xl = sl.d_exact_list;
+            launch_score_ring<true>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 1, xl);
+            // clipped units of >= kExactMin anchors queued by the kernel above: one CTA each (exits at once if there are none)
+            if (c->exact_big)
+                k_score_exact<kExactRing, kExactWarps><<<c->n_sm, kExactWarps * 32, (size_t)kExactRing * sizeof(RecL), s>>>(
+                    d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, d_f, d_p, xl, sl.d_ctr, c->prm, c->d_lut);
+            else
+                k_score_exact_warp<<<c->n_sm, 256, 0, s>>>(d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, d_f, d_p, xl, sl.d_ctr, c->prm, c->d_lut);
+            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 2, nullptr);
         } else {
-            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 0);
+            launch_score_ring<false>(c, s, d_a, sl.d_st, sl.d_unit_start, sl.d_unit_rbase, sl.d_clipmask, d_f, d_p, sl.d_big_order, sl.big_cap, sl.d_ctr, 0, nullptr);
         }
     }
     CK(cudaGetLastError());
@@ -660,6 +672,7 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
     }
     if (const char *e = getenv("MM2GB_TIMELINE")) c->timeline = atoi(e) != 0;
     if (const char *e = getenv("MM2GB_RANGE_TMA")) c->range_tma = atoi(e) != 0;
+    if (const char *e = getenv("MM2GB_EXACT_BIG")) c->exact_big = atoi(e) != 0;
     if (const char *e = getenv("MM2GB_WIRE")) c->wire_mode = !strcmp(e, "raw") ? 1 : !strcmp(e, "packed") ? 2 : 0;
     if (const char *e = getenv("MM2GB_DRAIN_BLOCKS")) {
         int r = atoi(e);
@@ -749,9 +762,10 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
                 dtake(s.d_selmask, n_groups); dtake(s.d_clipmask, n_groups);
                 dtake(s.d_block_cnt, n_blocks); dtake(s.d_block_base, n_blocks); dtake(s.d_block_pairs, n_blocks);
                 dtake(s.d_chunk_tot, n_chunks); dtake(s.d_chunk_base, n_chunks); dtake(s.d_chunk_pairs, n_chunks);
-                dtake(s.d_unit_start, n_units_cap); dtake(s.d_unit_rbase, n_units_cap);
+                dtake(s.d_unit_start, n_units_cap); dtake(s.d_unit_rbase, n_units_cap); dtake(s.d_unit_clip, n_units_cap);
                 s.big_cap = (int)(n / kBigMin) + 2;
-                dtake(s.d_big_order, (size_t)kBigClasses * s.big_cap);
+                dtake(s.d_big_order, (size_t)kBigClasses * s.big_cap + n / kExactMin + 2);   // + the queue of k_score_exact
+                if (dev) s.d_exact_list = s.d_big_order + (size_t)kBigClasses * s.big_cap;
                 dtake(s.d_ctr, 1);
                 // staging: raw anchors (16 B each) or the packed wire format (8 B each + block index + run list), same buffer
                 if (c->host_io) htake(s.h_a, n);

@@ -48,10 +48,13 @@ struct Counters {
     int ovf_cnt;            // reads the shared-memory chain-extraction kernels handed to the global-memory ones
     int u_cur, b_cur;       // cursors of the packed chain / compacted-anchor outputs of the batch (k_bt_walk)
     int scan_done;          // chunks of k_scan that have finished (the last one combines them)
+    int exact_cnt;          // clipped units of >= kExactMin anchors, queued by k_score_units for k_score_exact
+    int next_exact;         // work-queue cursor of k_score_exact
     unsigned long long n_pairs;
 };
 
 constexpr int kBigMin = 512;                // smallest unit that goes through the longest-first lists
+constexpr int kExactMin = 1024;             // clipped units of at least this many anchors get a CTA of their own (k_score_exact)
 constexpr int kBigClasses = 5;
 __device__ __forceinline__ int big_class(int len) { return len >= 8192 ? 0 : len >= 4096 ? 1 : len >= 2048 ? 2 : len >= 1024 ? 3 : 4; }
 // smallest unit of the first `n` classes (the ones k_score_long takes when long_classes = n)
@@ -167,7 +170,10 @@ __device__ __forceinline__ void range_tail(const ulonglong2 *__restrict__ a, con
         const int lo0 = lo_ll > (long long)rs ? (int)lo_ll : rs;
         int hi;
         const int lo_s = max(lo0, max(h0, 0));   // oldest candidate available in shared memory
-        if (lo_s > lo0 && xs(lo_s) >= lower) {
+        if (g > lo_s && xs(g - 1) < lower) {
+            hi = g;     // the previous anchor is already out of reach (x is sorted): empty window.  An isolated hit -- most of the
+                        // anchors of a large reference's hit mix -- costs one probe instead of a binary search
+        } else if (lo_s > lo0 && xs(lo_s) >= lower) {
             hi = window_start_global(a, g, lo0, lower);   // window reaches beyond the staged history (rare)
         } else {
             // first index in [lo_s, g] with x >= lower; x[g] itself qualifies
@@ -460,7 +466,7 @@ k_scan(const int *__restrict__ block_cnt, const unsigned long long *__restrict__
 __global__ void __launch_bounds__(256)
 k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base, const int *__restrict__ chunk_base,
         const long long *__restrict__ off, int n_reads, int n_total, int n_groups, int *__restrict__ unit_start,
-        int *__restrict__ unit_rbase, const Counters *__restrict__ ctr)
+        int *__restrict__ unit_rbase, unsigned *__restrict__ unit_clip, const Counters *__restrict__ ctr)
 {
     const int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp == 0) unit_start[ctr->n_units] = n_total;
@@ -481,19 +487,56 @@ k_units(const unsigned *__restrict__ selmask, const int *__restrict__ block_base
         }
         unit_start[k] = g;
         unit_rbase[k] = (int)off[lo];
+        unit_clip[k] = 0;
         ++k;
+    }
+}
+
+// k_unit_clip: unit_clip[k] = 1 for every unit that holds a window clipped by max_iter (those need the max_ii fallback of
+//              lchain.c:189-205).  One thread per 32-anchor group of clipmask; a group without clipped windows -- every group of
+//              ordinary reads -- costs one load, so the score kernels read one flag per unit instead of scanning the unit's mask.
+__global__ void __launch_bounds__(256)
+k_unit_clip(const unsigned *__restrict__ clipmask, const int *__restrict__ unit_start, int n_groups, unsigned *__restrict__ unit_clip,
+            const Counters *__restrict__ ctr)
+{
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= n_groups) return;
+    unsigned m = clipmask[grp];
+    if (!m) return;
+    const int n_units = ctr->n_units;
+    int k = -1;
+    while (m) {
+        const int i = grp * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        if (k < 0 || i >= unit_start[k + 1]) {      // the unit of anchor i: largest k with unit_start[k] <= i
+            int lo = 0, hi = n_units;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (unit_start[mid] <= i) lo = mid; else hi = mid;
+            }
+            k = lo;
+            unit_clip[k] = 1u;
+        }
     }
 }
 
 // k_order: units of >= kBigMin anchors are listed per size class so that the score kernel starts the longest units first
 // (a 5000-anchor unit is ~1 ms of one warp's time: started last it would be the tail of the launch).
+// Clipped units of >= kExactMin anchors are queued for k_score_exact (behind the lists in big_order) and appear in no list.
 __global__ void __launch_bounds__(256)
-k_order(const int *__restrict__ unit_start, int *__restrict__ big_order, int big_cap, Counters *__restrict__ ctr)
+k_order(const int *__restrict__ unit_start, const unsigned *__restrict__ unit_clip, int *__restrict__ big_order, int big_cap,
+        Counters *__restrict__ ctr, int fast)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ctr->n_units) return;
     const int len = unit_start[k + 1] - unit_start[k];
     if (len < kBigMin) return;
+    // (only when the table path scores the batch: the general path -- float penalties, mixed segment ids -- keeps them in the lists)
+    if (fast && ctr->multi_sid == 0 && len >= kExactMin && unit_clip[k]) {
+        big_order[kBigClasses * big_cap + atomicAdd(&ctr->exact_cnt, 1)] = k;
+        atomicAdd(&ctr->n_exact, 1);
+        return;
+    }
     const int c = big_class(len);
     const int pos = atomicAdd(&ctr->big_cnt[c], 1);
     if (pos < big_cap) big_order[c * big_cap + pos] = k;
@@ -1288,9 +1331,72 @@ __device__ __forceinline__ void long_walk32_pk(int &thr, int &bj, int &pen, cons
     if (val >= thr) { thr = val; bj = j0 + (tkey & 31); }
 }
 
-template <int RL, int NW, bool PACK>
+struct ExactState;
+template <int RL>
+__device__ __forceinline__ void exact_row(ExactState &M, int s, int t0, const uint4 *__restrict__ a, const int *f, const uint4 &ai, int sti,
+                                          int &fcur, int &bj, const DevParams &P, unsigned lut_s, int &pen, int lane);
+
+// EXACT: the unit has windows clipped by max_iter, so the max_ii fallback of lchain.c:189-205 (SURVEY.md trap T3) runs as well.
+// Its state -- max_ii and that anchor's x, y, q_span, f -- is one more serial dependency from row to row: inside a tile it is
+// carried in warp-uniform registers through the steps of the in-tile chain (row s is final, fallback candidate included,
+// before its score is broadcast to the rows behind it), between tiles through s_mi[] (written before the release of s_done).
+// The rescan of a whole window (max_ii has left the max_dist_x range) is a warp-wide argmax over f[].
+struct ExactState { int mi, xhi, xlo, y, q, f; };
+
+// Row t0 + s of an EXACT tile, executed by the whole warp when the in-tile chain reaches it: lane s holds the row's best
+// (fcur, bj) over its window; M is the max_ii state after row t0 + s - 1 (warp-uniform).  lchain.c:189-205:
+//   rescan  if max_ii < 0 or x_i - x[max_ii] > max_dist_x:  max_ii = argmax f over the window (largest j among equals, -1 if empty)
+//   try     if 0 <= max_ii < st_i - 1:  the pair (i, max_ii) as one more candidate (strictly better wins)
+//   keep    f[i] is final; if max_ii < 0 or (x_i - x[max_ii] <= max_dist_x and f[max_ii] < f[i]):  max_ii = i
+template <int RL>
+__device__ __forceinline__ void exact_row(ExactState &M, int s, int t0, const uint4 *__restrict__ a, const int *f, const uint4 &ai, int sti,
+                                          int &fcur, int &bj, const DevParams &P, unsigned lut_s, int &pen, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const int i = t0 + s;
+    const int xlo = __shfl_sync(full, (int)ai.x, s), xhi = __shfl_sync(full, (int)ai.y, s), st_s = __shfl_sync(full, sti, s);
+    // x is sorted, so x_i >= x[max_ii]: another rid/strand word means a distance of at least 2^32
+    bool far = M.mi < 0 || xhi != M.xhi || (unsigned)(xlo - M.xlo) > (unsigned)P.max_dist_x;
+    if (far) {
+        int fv = INT32_MIN, fj = -1;
+        for (int j0 = st_s; j0 < min(i, t0); j0 += 32) {       // finished tiles: from global memory (L2)
+            const int j = j0 + lane;
+            if (j < min(i, t0)) { const int v = __ldcg(f + j); if (v >= fv) fv = v, fj = j; }
+        }
+        if (lane < s && t0 + lane >= st_s && fcur >= fv) fv = fcur, fj = t0 + lane;    // rows of this tile that are final already
+        const int fm = __reduce_max_sync(full, fv);
+        M.mi = __reduce_max_sync(full, (fv == fm && fj >= 0) ? fj : -1);
+        if (M.mi >= 0) {
+            M.f = fm;
+            if (M.mi >= t0) {
+                const int l = M.mi - t0;
+                M.xlo = __shfl_sync(full, (int)ai.x, l); M.xhi = __shfl_sync(full, (int)ai.y, l);
+                M.y = __shfl_sync(full, (int)ai.z, l); M.q = __shfl_sync(full, (int)(ai.w & 0xffu), l);
+            } else {
+                const uint4 v = __ldg(a + M.mi);
+                M.xlo = (int)v.x; M.xhi = (int)v.y; M.y = (int)v.z; M.q = (int)(v.w & 0xffu);
+            }
+            far = xhi != M.xhi || (unsigned)(xlo - M.xlo) > (unsigned)P.max_dist_x;
+        }
+    }
+    int fs = fcur;
+    if (M.mi >= 0 && M.mi < st_s - 1 && lane == s) {
+        Rec r; r.x = M.xlo; r.y = M.y; r.f = M.f; r.q = M.q;
+        int sc;
+        if (pair_fast((int)ai.x, (int)ai.z, r, P.maxd_q, (unsigned)P.bw, lut_s, pen, sc) && fcur < sc + M.f) { fcur = sc + M.f; bj = M.mi; }
+        fs = fcur;
+    }
+    fs = __shfl_sync(full, fs, s);      // f[i], final
+    if (M.mi < 0 || (!far && M.f < fs)) {
+        M.mi = i; M.xlo = xlo; M.xhi = xhi; M.f = fs;
+        M.y = __shfl_sync(full, (int)ai.z, s); M.q = __shfl_sync(full, (int)(ai.w & 0xffu), s);
+    }
+}
+
+template <int RL, int NW, bool PACK, bool EXACT = false>
 __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restrict__ st, int *f, int *__restrict__ p, int u0, int u1,
-                                int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecL *ring, int *s_done, int warp, int lane)
+                                int rbase, const DevParams &P, int qs_max, unsigned lut_s, RecL *ring, int *s_done, int warp, int lane,
+                                ExactState *s_mi = nullptr)
 {
     const unsigned full = 0xffffffffu;
     const unsigned bw = (unsigned)P.bw, bw2 = 2u * (unsigned)P.bw;
@@ -1357,6 +1463,11 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
         __syncwarp();
         // phase B: the in-tile triangle, f-independent parts first, then the serial chain (one shuffle per step)
         int fcur = bj >= 0 ? thr : qsi;
+        ExactState M = {-1, 0, 0, 0, 0, 0};
+        if (EXACT) {    // the state after row t0 - 1: tile t - 1 has to be finished (it usually is: it is in every window)
+            while (done < t) done = ld_acquire_shared(s_done);
+            M = *s_mi;
+        }
         // the tile slots s that are predecessors of this lane's anchor (s < lane and t0 + s >= st_i), one bit test per slot below
         const int vlo = sti - t0;
         const unsigned vm = vlo >= lane ? 0u : (((1u << lane) - 1u) & ~((1u << max(vlo, 0)) - 1u));
@@ -1383,17 +1494,23 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
             for (int q = 0; q < 16; ++q) {
                 const int s = h * 16 + q;
                 if (s < 31) {
+                    if (EXACT && s < nact) exact_row<RL>(M, s, t0, a, f, ai, sti, fcur, bj, P, lut_s, pen, lane);
                     const int fs = __shfl_sync(full, fcur, s);
                     const int val = fs + w[q];                  // kNeg + f stays far below any threshold
                     if (val >= thr) thr = val, fcur = val, bj = t0 + s;
                 }
             }
         }
+        if (EXACT) {
+            // rows the loops above did not finalise: row 31 always, rows 16 .. 30 if the second half was skipped (short last tile)
+            for (int s = (nact <= 17 ? 16 : 31); s < nact; ++s) exact_row<RL>(M, s, t0, a, f, ai, sti, fcur, bj, P, lut_s, pen, lane);
+        }
         if (act) {
             f[i] = fcur;
             p[i] = bj < 0 ? -1 : bj - rbase;
             tile[lane].g = PACK ? (((fcur + qsi) << kTileBits) | lane) : fcur + qsi;
         }
+        if (EXACT && lane == 0) *s_mi = M;
         // tiles finish in order: a tile whose window does not reach back into tile t - 1 (a cut inside the unit) has not
         // waited for it yet
         while (done < t) done = ld_acquire_shared(s_done);
@@ -1440,6 +1557,75 @@ k_score_long(const uint4 *__restrict__ a, const int *__restrict__ st, const int 
             score_unit_long<RL, NW, true>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane);
         else
             score_unit_long<RL, NW, false>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_score_exact: the clipped units of >= kExactMin anchors that k_score_units queued (tandem repeats, dense repeat families:
+// more than max_iter anchors inside max_dist_x), one CTA each, score_unit_long in EXACT mode.  The ring holds 8192 records, so
+// windows of max_iter = 5000 anchors plus the tiles in flight are served from shared memory.  Launched behind k_score_units on
+// the same stream; exits at once when nothing was queued (the usual case).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kExactRing = 8192;
+constexpr int kExactWarps = 16;            // tiles in flight per unit (the CTA has the SM to itself: 128 KB of ring)
+
+template <int RL, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_score_exact(const uint4 *__restrict__ a, const int *__restrict__ st, const int *__restrict__ unit_start, const int *__restrict__ unit_rbase,
+              int *f, int *__restrict__ p, const int *__restrict__ exact_list, Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g)
+{
+    __shared__ __align__(16) unsigned char lut[2 * kLutMax + 16];
+    __shared__ int s_unit, s_done;
+    __shared__ ExactState s_mi;
+    extern __shared__ int4 smem_raw[];
+    RecL *ring = reinterpret_cast<RecL *>(smem_raw);
+    unsigned lut_s = (unsigned)__cvta_generic_to_shared(lut);
+    asm volatile("" : "+r"(lut_s));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ctr->multi_sid != 0) return; // the table path is not valid for this batch: k_score_units<false> takes every unit
+    const int n_list = ctr->exact_cnt;
+    if ((int)blockIdx.x >= n_list) return;
+    for (int k = threadIdx.x; k < P.lut_n; k += blockDim.x) lut[k] = lut_g[k];
+    const int qs_max = max(ctr->qs_max, 1);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_unit = atomicAdd(&ctr->next_exact, 1);
+            s_done = 0;
+            s_mi.mi = -1; s_mi.xhi = s_mi.xlo = s_mi.y = s_mi.q = s_mi.f = 0;
+        }
+        __syncthreads();
+        const int w = s_unit;
+        if (w >= n_list) break;
+        const int k = exact_list[w];
+        const int u0 = unit_start[k], u1 = unit_start[k + 1], rbase = unit_rbase[k];
+        if ((long long)(u1 - u0 + 1) * qs_max < (1LL << 26))
+            score_unit_long<RL, NW, true, true>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane, &s_mi);
+        else
+            score_unit_long<RL, NW, false, true>(a, st, f, p, u0, u1, rbase, P, qs_max, lut_s, ring, &s_done, warp, lane, &s_mi);
+    }
+}
+
+// the same queue, one WARP per unit with the row-by-row path (score_unit_exact): what these units cost before k_score_exact
+// existed; kept as the A/B switch MM2GB_EXACT_BIG=0
+__global__ void __launch_bounds__(256)
+k_score_exact_warp(const uint4 *__restrict__ a, const int *__restrict__ st, const int *__restrict__ unit_start, const int *__restrict__ unit_rbase,
+                   int *f, int *__restrict__ p, const int *__restrict__ exact_list, Counters *ctr, DevParams P, const unsigned char *__restrict__ lut_g)
+{
+    __shared__ __align__(16) unsigned char lut[2 * kLutMax + 16];
+    const unsigned lut_s = (unsigned)__cvta_generic_to_shared(lut);
+    const int lane = threadIdx.x & 31;
+    const int n_list = ctr->exact_cnt;
+    if (n_list == 0 || ctr->multi_sid != 0) return;
+    for (int k = threadIdx.x; k < P.lut_n; k += blockDim.x) lut[k] = lut_g[k];
+    __syncthreads();
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&ctr->next_exact, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_list) break;
+        const int k = exact_list[w];
+        score_unit_exact<true>(a, st, f, p, unit_start[k], unit_start[k + 1], unit_rbase[k], P, lut_s, lane);
     }
 }
 
