@@ -453,9 +453,10 @@ def main():
 
     sec = ms_max / 1e3
     value = tot_pairs * args.steps / sec
-    # kernels launched per step (mirrors enqueue_kernels / enqueue_backtrack in chain_core.cu): 5 range/unit kernels, k_score_long
-    # + the two k_score_units instantiations, then a sort + a walk kernel per non-empty chain-extraction size class (7 shared-memory
-    # classes, the mid classes up to 196608 anchors, the global-memory class) and the overflow pass
+    # kernels launched per step (mirrors enqueue_kernels / enqueue_backtrack in chain_core.cu): 6 range/unit kernels (k_block_reads,
+    # k_range, k_scan, k_units, k_unit_clip, k_order), k_score_long + the two k_score_units instantiations + k_score_exact, then a
+    # sort + a walk kernel per non-empty chain-extraction size class (7 shared-memory classes, the 9 mid classes up to 196608
+    # anchors, the global-memory class) and the overflow pass
     rn = np.diff(off)
     small = [1024, 1536, 2048, 3072, 4096, 6144, 8192]
     mid = [10048, 13952, 19776, 29504, 37248, 48640, 65536, 98304, 196608]
@@ -476,10 +477,11 @@ def main():
     except Exception:
         pass
     # DRAM bytes of one k_score_units launch on this workload from the committed `ncu --set full` capture (profiles/traffic.json)
-    traffic = None
+    traffic, sass_per_pair = None, 15.54
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
+        sass_per_pair = float(tj.get("ont", {}).get("thread_instr_per_pair", sass_per_pair))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -508,8 +510,8 @@ def main():
                 "peak_source": issue_src, "int_ops_per_pair": INSTR_PER_PAIR, "pairs_per_s_kernel": kernel_pairs_s, "sm_mhz": sm_mhz, "n_sm": n_sm,
                 "kernel_ms": score_avg_s * 1e3, "kernel_share_of_step": score_ms / ms_seq,
                 "traffic": traffic, "algorithmic_bytes_per_launch": HBM_BYTES_PER_ANCHOR * n,
-                "note": "achieved = %.0f algorithmic integer ops per pair (SURVEY.md 8d) x pairs / kernel time; the kernel executes 17.4 SASS thread-instructions per pair "
-                        "(profiles/r4*_score_units_ncu.md), i.e. %.2f of the measured issue peak" % (INSTR_PER_PAIR, 17.4 * kernel_pairs_s / issue_peak),
+                "note": "achieved = %.0f algorithmic integer ops per pair (SURVEY.md 8d) x pairs / kernel time; the kernel executes %.2f SASS thread-instructions per pair "
+                        "on configs[1] (profiles/traffic.json, from the ncu capture named there), i.e. %.2f of the measured issue peak" % (INSTR_PER_PAIR, sass_per_pair, sass_per_pair * kernel_pairs_s / issue_peak),
                 "mid_loop_speed_of_light": {"pairs_per_s": mid_peak or None, "frac": (kernel_pairs_s / mid_peak) if mid_peak else None,
                                             "note": "a kernel of MID pairs only (6.6 instr/pair, LSU-bound); the score kernel also pays the in-tile triangle, GEN / FAR pairs and tile set-up"},
                 "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "peak_source": peak_src, "traffic": traffic,
@@ -537,7 +539,7 @@ def main():
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
             "parity": parity,
-            "gpu_launches": (8 + 2 * bt_classes) * args.steps, "clocks": clocks}
+            "gpu_launches": (10 + 2 * bt_classes) * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
     emit(line)

@@ -1185,6 +1185,10 @@ k_score_units(const uint4 *__restrict__ a, const int *__restrict__ st, const int
 // the chain score is bounded.  Records are in diagonal form as in score_unit_packed: e = x - y, g = f + q_span, y, q_span;
 // predecessor tiles are classified MID / FAR / GEN per (tile, predecessor tile) exactly as there.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef MM2GB_LONG_SLEEP_NEAR
+#define MM2GB_LONG_SLEEP_NEAR 20     // ns between polls while waiting for the tile right before this warp's own ...
+#define MM2GB_LONG_SLEEP_FAR 200     // ... and for an older one
+#endif
 constexpr int kLongWarps = 8;
 constexpr int kLongRing = 4096;
 
@@ -1436,7 +1440,7 @@ __device__ void score_unit_long(const uint4 *__restrict__ a, const int *__restri
                 for (;;) {
                     done = ld_acquire_shared(s_done);
                     if (k < done) break;
-                    __nanosleep(t - done > 1 ? 200 : 20);
+                    __nanosleep(t - done > 1 ? MM2GB_LONG_SLEEP_FAR : MM2GB_LONG_SLEEP_NEAR);
                 }
             }
             const int j0 = u0 + 32 * k;
