@@ -145,6 +145,14 @@ int mm2gb_chain_device(mm2gb_ctx_t *ctx, const void *d_a, const void *d_off, con
  * extraction of one batch overlaps the score kernels of the next (d_f / d_p must be distinct per batch in flight). */
 int mm2gb_chain_device_slot(mm2gb_ctx_t *ctx, int slot, const void *d_a, const void *d_off, const int64_t *off, int n_reads,
                             int64_t n_total, void *d_f, void *d_p);
+/* Results of a batch enqueued by mm2gb_chain_device_slot -> host, for producers that create the anchors on the device (mm2gb_seed.h:
+ * the host holds no copy of them): the compacted anchors themselves (16 B each) and the packed chains are written into caller-supplied
+ * pinned (mapped) host memory with room for n_total entries each; fetch enqueues, results waits.  Per read r: n_u[r] chains at
+ * u_pinned[u_pos[r] ..], n_b[r] compacted anchors at b_pinned[b_pos[r] ..] (the per-read arrays live in the slot until its next use). */
+int mm2gb_chain_device_fetch(mm2gb_ctx_t *ctx, int slot, const void *d_a, const void *d_off, int n_reads, int64_t n_total,
+                             mm2gb_anchor_t *b_pinned, uint64_t *u_pinned);
+int mm2gb_chain_device_results(mm2gb_ctx_t *ctx, int slot, const int32_t **n_u, const int32_t **u_pos, const int32_t **n_b,
+                               const int32_t **b_pos, int64_t *n_chains, int64_t *n_chain_anchors, mm2gb_stats_t *stats);
 int mm2gb_sync(mm2gb_ctx_t *ctx, int slot);
 /* the cudaStream_t of a slot, as an opaque pointer (so a caller can record its own events on it) */
 void *mm2gb_stream(mm2gb_ctx_t *ctx, int slot);

@@ -1580,4 +1580,24 @@ k_drain(const int *__restrict__ src_v, int *__restrict__ dst_v, int first, const
     for (long long k = t; k < nu; k += stride) dst_u[k] = __ldg(src_u + k);
 }
 
+// Results of a DEVICE-RESIDENT batch (anchors produced on the device, e.g. by the seeding kernels: the host holds no copy to
+// gather from) -> mapped pinned host memory: the compacted anchors themselves, b[b_pos[r] + k] = a[off[r] + v[b_pos[r] + k]]
+// (compact_a's gather, lchain.c:100-105, fused into the transfer; one warp per read, 16-byte stores), and the packed chains.
+__global__ void __launch_bounds__(256)
+k_drain_anchors(const uint4 *__restrict__ a, const long long *__restrict__ off, const int *__restrict__ v, const int *__restrict__ n_b,
+                const int *__restrict__ b_pos, int n_reads, uint4 *__restrict__ dst_b, const unsigned long long *__restrict__ src_u,
+                unsigned long long *__restrict__ dst_u, const Counters *__restrict__ ctr)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_reads; r += n_warps) {
+        const int nb = n_b[r], bp = b_pos[r];
+        const long long o = off[r];
+        for (int t = lane; t < nb; t += 32) dst_b[bp + t] = __ldg(a + o + __ldg(v + bp + t));
+    }
+    const long long nu = ctr->u_cur, stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nu; k += stride) dst_u[k] = __ldg(src_u + k);
+}
+
+
 } // namespace mm2gb

@@ -52,6 +52,8 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 extern "C" const char *mm2gb_last_error(void) { return g_err; }
+// for the other translation units of the library (seed_core.cu): same per-thread message buffer
+extern "C" void mm2gb_internal_set_error(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
 
 extern "C" int mm2gb_device_count(void)
 {
@@ -1510,6 +1512,62 @@ extern "C" int mm2gb_chain_device(mm2gb_ctx_t *c, const void *d_a, const void *d
                                   void *d_f, void *d_p)
 {
     return mm2gb_chain_device_slot(c, 0, d_a, d_off, off, n_reads, n_total, d_f, d_p);
+}
+
+// Results of a batch enqueued by mm2gb_chain_device_slot -> host.  The producer of the anchors lives on the device (mm2gb_seed), so
+// the compacted anchors themselves cross PCIe (16 B each, gathered by k_drain_anchors) next to the packed chains; both land in
+// caller-supplied pinned memory, the per-read counts / positions in the slot's own.  Works on MM2GB_CTX_DEVICE_ONLY contexts.
+extern "C" int mm2gb_chain_device_fetch(mm2gb_ctx_t *c, int slot, const void *d_a, const void *d_off, int n_reads, int64_t n_total,
+                                        mm2gb_anchor_t *b_pinned, uint64_t *u_pinned)
+{
+    if (!c || slot < 0 || slot >= c->n_slots || n_reads < 0 || !b_pinned || !u_pinned) return fail(MM2GB_EARG, "bad argument");
+    if (!c->chains_ok) return fail(MM2GB_ESTATE, "context was created with MM2GB_CTX_NO_CHAINS");
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slot[slot];
+    if (s.busy) return fail(MM2GB_ESTATE, "slot %d is busy", slot);
+    void *b_dev = nullptr, *u_dev = nullptr;
+    if (cudaHostGetDevicePointer(&b_dev, b_pinned, 0) != cudaSuccess || cudaHostGetDevicePointer(&u_dev, u_pinned, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MM2GB_EARG, "result buffers must be pinned (mapped) host memory");
+    }
+    slice_rinfo(s, n_reads);
+    if (n_total) {
+        k_drain_anchors<<<c->drain_blocks * 2, 256, 0, s.stream>>>((const uint4 *)d_a, (const long long *)d_off, s.d_vp, s.d_nb, s.d_bpos, n_reads,
+                                                                   (uint4 *)b_dev, s.d_upack, (unsigned long long *)u_dev, s.d_ctr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s.h_rinfo, s.d_rinfo, 4 * ((size_t)n_reads + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    }
+    CK(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaEventRecord(s.done, s.stream));
+    s.busy = true;
+    s.chains = true; s.want_fp = false; s.direct_out = false; s.user_f = s.user_p = nullptr;
+    s.n_reads = n_reads;
+    s.n_total = n_total;
+    return MM2GB_OK;
+}
+
+// wait for mm2gb_chain_device_fetch: per read r  n_u[r] chains at u_pinned[u_pos[r] ..], n_b[r] anchors at b_pinned[b_pos[r] ..]
+extern "C" int mm2gb_chain_device_results(mm2gb_ctx_t *c, int slot, const int32_t **n_u, const int32_t **u_pos, const int32_t **n_b,
+                                          const int32_t **b_pos, int64_t *n_chains, int64_t *n_chain_anchors, mm2gb_stats_t *stats)
+{
+    if (!c || slot < 0 || slot >= c->n_slots) return fail(MM2GB_EARG, "bad argument");
+    int rc = wait_impl(c, slot);
+    if (rc) return rc;
+    Slot &s = c->slot[slot];
+    if (!s.n_total) {
+        for (int r = 0; r < s.n_reads; ++r) s.h_nu[r] = s.h_nb[r] = s.h_upos[r] = s.h_bpos[r] = 0;
+    } else {
+        for (int r = 0; r < s.n_reads; ++r)
+            if (s.h_nu[r] < 0) return fail(MM2GB_ECUDA, "device chain extraction left read %d of the batch unfinished", r);
+    }
+    if (n_u) *n_u = s.h_nu;
+    if (u_pos) *u_pos = s.h_upos;
+    if (n_b) *n_b = s.h_nb;
+    if (b_pos) *b_pos = s.h_bpos;
+    if (n_chains) *n_chains = s.n_total ? s.h_ctr->u_cur : 0;
+    if (n_chain_anchors) *n_chain_anchors = s.n_total ? s.h_ctr->b_cur : 0;
+    fill_stats(c, *s.h_ctr, s.n_total, stats);
+    return MM2GB_OK;
 }
 
 // Diagnostic: device -> pinned host of n chain-anchor indices (4 B each) from slot 0's buffers, by k_drain with `blocks` CTAs and

@@ -1,0 +1,645 @@
+// seed_core.cu -- host side of the device seeding stage (include/mm2gb_seed.h), part of libmm2gb_chain.so.
+//
+// Replaces what the reference does per read on a host thread before its GPU path starts -- mm_map_seed (map.c:355-391): mm_sketch
+// (sketch.c:77), mm_seed_mz_flt (seed.c:5), mm_collect_matches (seed.c:98) with mm_idx_get (index.c:81), anchor construction and
+// radix_sort_128x (map.c:295-331) -- by a pipeline of kernels over the whole batch (seed_kernels.cuh) whose output, the x-sorted
+// anchor arrays, is consumed by the chaining kernels where it lies in HBM.  The index (mm_idx_t: minimizer -> positions sorted
+// ascending, index.c:213-266) is sketched on the device by the same kernel, grouped on the host once per index part, and kept
+// as an open-addressing table in HBM.
+#include "seed_kernels.cuh"
+#include "../../include/mm2gb_seed.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+using namespace mm2gb_seed;
+
+extern "C" void mm2gb_internal_set_error(const char *msg);
+
+namespace {
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    mm2gb_internal_set_error(buf);
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(MM2GB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// flags of mm_mapopt_t (minimap.h:11-40) that change what collect_seed_hits / skip_seed do
+constexpr int64_t F_NO_DIAG = 0x001, F_NO_DUAL = 0x002, F_FOR_ONLY = 0x100000, F_REV_ONLY = 0x200000, F_HEAP_SORT = 0x400000,
+                  F_QSTRAND = 0x100000000LL;
+
+template <class T> int dalloc(T *&p, size_t n)
+{
+    p = nullptr;
+    CK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return MM2GB_OK;
+}
+
+} // namespace
+
+// ---- index -----------------------------------------------------------------------------------------------------------------
+
+struct mm2gb_index {
+    int device = 0, w = 0, k = 0;
+    // host copy: keys ascending, occurrences of keys[i] at occ[off[i] .. off[i+1]) ascending
+    std::vector<uint64_t> keys, off, occ;
+    // device table
+    u64 *d_key = nullptr, *d_val = nullptr, *d_occ = nullptr;
+    uint64_t mask = 0;
+};
+
+struct mm2gb_seeder {
+    const mm2gb_index *idx = nullptr;
+    int device = 0;
+    int64_t max_bases = 0, max_mv = 0, max_anchors = 0;
+    int max_reads = 0, max_tiles = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[MM2GB_SEED_NTIMERS + 1] = {nullptr};
+    cudaEvent_t ev_join = nullptr, ev_stage[2] = {nullptr, nullptr};
+    // sequences
+    unsigned char *d_seq = nullptr;
+    long long *d_seq_off = nullptr;
+    int *d_tile_first = nullptr;
+    u32 *d_tile_cnt = nullptr;
+    u64 *d_tile_base = nullptr, *d_part = nullptr;
+    // minimizers
+    u64 *d_mv_x = nullptr, *d_mv_y = nullptr, *d_mv_off = nullptr;
+    u32 *d_mv_seq = nullptr;
+    unsigned char *d_keep = nullptr, *d_tandem = nullptr;
+    u64 *d_tab_key = nullptr;
+    u32 *d_tab_cnt = nullptr;
+    u32 *d_occ_n = nullptr, *d_has = nullptr;
+    u64 *d_occ_off = nullptr, *d_m_idx = nullptr;
+    // seeds
+    Seeds m{};
+    u32 *d_cnt_a = nullptr, *d_kept = nullptr;
+    u64 *d_a_pos = nullptr, *d_mp_pos = nullptr, *d_mini_pos = nullptr;
+    // per read
+    long long *d_a_off = nullptr, *d_mp_off = nullptr;
+    int *d_rep_len = nullptr;
+    // anchors
+    uint4 *d_a_tmp = nullptr, *d_a = nullptr;
+    u32 *d_words = nullptr;
+    int2 *d_queue = nullptr;
+    int *d_f = nullptr, *d_p = nullptr;
+    int sort_smem_words = 0;
+    // pinned host
+    long long *h_a_off = nullptr, *h_mp_off = nullptr;
+    int *h_rep_len = nullptr;
+    u64 *h_tot = nullptr;
+    mm2gb_anchor_t *h_b = nullptr;
+    uint64_t *h_u = nullptr;
+    unsigned char *h_seq = nullptr;      // staging for pageable sequences
+    std::vector<int> tile_first;
+    std::vector<int64_t> a_off_copy;
+    // last batch
+    long long n_mv = 0, n_m = 0, n_a = 0, n_mp = 0;
+    int n_tiles = 0;
+    float ms[MM2GB_SEED_NTIMERS] = {0};
+    bool timed = false;
+};
+
+namespace {
+
+int scan_u32(cudaStream_t st, const u32 *in, long long n, u64 *out, u64 *part)
+{
+    if (n <= 0) { CK(cudaMemsetAsync(out, 0, sizeof(u64), st)); return MM2GB_OK; }
+    const int nb = (int)((n + kScanChunk - 1) / kScanChunk);
+    k_scan_reduce<<<nb, kScanThreads, 0, st>>>(in, n, part);
+    k_scan_top<<<1, 1024, 0, st>>>(part, nb);
+    k_scan_apply<<<nb, kScanThreads, 0, st>>>(in, n, part, out);
+    CK(cudaGetLastError());
+    return MM2GB_OK;
+}
+
+inline unsigned grid_for(long long n, int threads) { return (unsigned)std::max<long long>(1, (n + threads - 1) / threads); }
+
+// tiles per sequence; -1 if the batch does not fit
+int plan_tiles(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
+{
+    sd->tile_first.resize((size_t)n_seq + 1);
+    long long t = 0;
+    for (int s = 0; s < n_seq; ++s) {
+        sd->tile_first[(size_t)s] = (int)t;
+        const int64_t len = seq_off[s + 1] - seq_off[s];
+        if (len < 0 || len > INT32_MAX - 2 * kTile) return -1;
+        t += (len + kTile - 1) / kTile;
+        if (t > sd->max_tiles) return -1;
+    }
+    sd->tile_first[(size_t)n_seq] = (int)t;
+    return (int)t;
+}
+
+// sequences (already on the device) -> minimizers in d_mv_*; n_mv on the host (one synchronisation)
+int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
+{
+    cudaStream_t st = sd->stream;
+    const mm2gb_index *ix = sd->idx;
+    const int nt = sd->n_tiles;
+    sd->n_mv = 0;
+    if (nt == 0) { CK(cudaMemsetAsync(sd->d_mv_off, 0, ((size_t)n_seq + 1) * sizeof(u64), st)); return MM2GB_OK; }
+    k_sketch<false><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, ix->w, ix->k, rid_is_seq, sd->d_tile_cnt,
+                                          nullptr, nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+    int rc = scan_u32(st, sd->d_tile_cnt, nt, sd->d_tile_base, sd->d_part);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sd->h_tot, sd->d_tile_base + nt, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    sd->n_mv = (long long)sd->h_tot[0];
+    if (sd->n_mv > sd->max_mv)
+        return fail(MM2GB_ECAP, "batch has %lld minimizers, the seeder holds %lld (max_bases too small for this sequence content)",
+                    sd->n_mv, (long long)sd->max_mv);
+    k_sketch<true><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, ix->w, ix->k, rid_is_seq, nullptr, sd->d_tile_base,
+                                         sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq);
+    k_seq_mv_off<<<grid_for(n_seq + 1, 256), 256, 0, st>>>(sd->d_tile_first, sd->d_tile_base, n_seq, sd->d_mv_off);
+    CK(cudaGetLastError());
+    return MM2GB_OK;
+}
+
+int upload_offsets(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
+{
+    if (n_seq < 0 || n_seq > sd->max_reads) return fail(MM2GB_ECAP, "batch of %d sequences exceeds capacity %d", n_seq, sd->max_reads);
+    if (seq_off[0] != 0) return fail(MM2GB_EARG, "seq_off[0] must be 0");
+    if (seq_off[n_seq] > sd->max_bases) return fail(MM2GB_ECAP, "batch of %lld bases exceeds capacity %lld", (long long)seq_off[n_seq], (long long)sd->max_bases);
+    const int nt = plan_tiles(sd, seq_off, n_seq);
+    if (nt < 0) return fail(MM2GB_ECAP, "batch does not fit the seeder (tiles)");
+    sd->n_tiles = nt;
+    CK(cudaMemcpyAsync(sd->d_seq_off, seq_off, ((size_t)n_seq + 1) * sizeof(long long), cudaMemcpyHostToDevice, sd->stream));
+    CK(cudaMemcpyAsync(sd->d_tile_first, sd->tile_first.data(), ((size_t)n_seq + 1) * sizeof(int), cudaMemcpyHostToDevice, sd->stream));
+    return MM2GB_OK;
+}
+
+int upload_seqs(mm2gb_seeder *sd, const char *seqs, int64_t n_bases)
+{
+    if (n_bases <= 0) return MM2GB_OK;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, seqs) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) { CK(cudaMemcpyAsync(sd->d_seq, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, sd->stream)); return MM2GB_OK; }
+    // pageable source: staged through pinned memory in two halves so that the copy of one overlaps the DMA of the other
+    const size_t half = ((size_t)sd->max_bases + 1) / 2;
+    size_t done = 0;
+    int which = 0;
+    cudaEvent_t evs[2] = {sd->ev_stage[0], sd->ev_stage[1]};
+    bool used[2] = {false, false};
+    const size_t piece = std::min<size_t>(half, (size_t)8 << 20);
+    while (done < (size_t)n_bases) {
+        const size_t n = std::min(piece, (size_t)n_bases - done);
+        // two staging windows of `piece` bytes
+        unsigned char *stg = sd->h_seq + (size_t)which * piece;
+        if (used[which]) CK(cudaEventSynchronize(evs[which]));
+        memcpy(stg, seqs + done, n);
+        CK(cudaMemcpyAsync(sd->d_seq + done, stg, n, cudaMemcpyHostToDevice, sd->stream));
+        CK(cudaEventRecord(evs[which], sd->stream));
+        used[which] = true;
+        which ^= 1;
+        done += n;
+    }
+    return MM2GB_OK;
+}
+
+int check_params(const mm2gb_seed_params_t *p)
+{
+    if (!p) return fail(MM2GB_EARG, "null parameters");
+    if (p->flag & (F_NO_DIAG | F_NO_DUAL | F_FOR_ONLY | F_REV_ONLY | F_HEAP_SORT | F_QSTRAND))
+        return fail(MM2GB_EARG, "map flag 0x%llx changes seed collection (no-diag / no-dual / for-only / rev-only / heap-sort / qstrand): "
+                                "not supported by the device seeding path", (long long)p->flag);
+    if (p->sdust_thres > 0) return fail(MM2GB_EARG, "sdust masking of query minimizers is not supported by the device seeding path");
+    if (p->mid_occ <= 0) return fail(MM2GB_EARG, "mid_occ must be positive (run mm_mapopt_update / mm2gb_index_cal_max_occ first)");
+    return MM2GB_OK;
+}
+
+// the stages behind the sketch, up to the x-sorted anchors in sd->d_a and the per-read offsets on the host (sd->h_a_off)
+int run_seed(mm2gb_seeder *sd, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads, bool want_mini_pos)
+{
+    cudaStream_t st = sd->stream;
+    const mm2gb_index *ix = sd->idx;
+    const int T = 256;
+    sd->n_m = sd->n_a = sd->n_mp = 0;
+    CK(cudaEventRecord(sd->ev[0], st));
+    int rc = run_sketch(sd, n_reads, 0);
+    if (rc) return rc;
+    const long long n_mv = sd->n_mv;
+    CK(cudaEventRecord(sd->ev[1], st));
+    CK(cudaMemsetAsync(sd->d_rep_len, 0, (size_t)std::max(n_reads, 1) * sizeof(int), st));
+    // opt->max_qlen (map.c:376): such reads get no anchors -- drop their minimizers through the keep flags
+    const bool qflt = prm->q_occ_frac > 0.0f && prm->mid_occ > 0;
+    if (n_mv) {
+        if (qflt) {
+            CK(cudaMemsetAsync(sd->d_tab_key, 0xff, (size_t)2 * n_mv * sizeof(u64), st));
+            CK(cudaMemsetAsync(sd->d_tab_cnt, 0, (size_t)2 * n_mv * sizeof(u32), st));
+            k_qocc_count<<<grid_for(n_mv, T), T, 0, st>>>(sd->d_mv_x, sd->d_mv_seq, sd->d_mv_off, n_mv, prm->mid_occ, sd->d_tab_key, sd->d_tab_cnt);
+            k_qocc_flag<<<grid_for(n_mv, T), T, 0, st>>>(sd->d_mv_x, sd->d_mv_seq, sd->d_mv_off, n_mv, prm->mid_occ, prm->q_occ_frac, sd->d_tab_key,
+                                                         sd->d_tab_cnt, sd->d_keep);
+        } else CK(cudaMemsetAsync(sd->d_keep, 1, (size_t)n_mv, st));
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(sd->ev[2], st));
+    if (n_mv) {
+        DevIndex di{ix->d_key, ix->d_val, ix->d_occ, ix->mask};
+        k_lookup<<<grid_for(n_mv, T), T, 0, st>>>(di, sd->d_mv_x, sd->d_mv_seq, sd->d_keep, n_mv, sd->d_occ_n, sd->d_occ_off, sd->d_tandem, sd->d_has);
+        CK(cudaGetLastError());
+    }
+    rc = scan_u32(st, sd->d_has, n_mv, sd->d_m_idx, sd->d_part);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sd->h_tot, sd->d_m_idx + n_mv, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const long long n_m = sd->n_m = (long long)sd->h_tot[0];
+    if (n_m) {
+        k_compact_seeds<<<grid_for(n_mv, T), T, 0, st>>>(sd->d_mv_y, sd->d_mv_seq, sd->d_occ_n, sd->d_occ_off, sd->d_tandem, sd->d_m_idx, n_mv, sd->m);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(sd->ev[3], st));
+    if (n_m) {
+        k_select<<<grid_for(n_m, T), T, 0, st>>>(sd->m, sd->d_m_idx, sd->d_mv_off, sd->d_seq_off, n_m, prm->mid_occ, prm->max_max_occ, prm->occ_dist,
+                                                 ix->k, sd->d_cnt_a, sd->d_kept);
+        k_rep_len<<<grid_for(n_m, T), T, 0, st>>>(sd->m, sd->d_m_idx, sd->d_mv_off, n_m, ix->k, sd->d_rep_len);
+        CK(cudaGetLastError());
+    }
+    rc = scan_u32(st, sd->d_cnt_a, n_m, sd->d_a_pos, sd->d_part);
+    if (rc) return rc;
+    rc = scan_u32(st, sd->d_kept, n_m, sd->d_mp_pos, sd->d_part);
+    if (rc) return rc;
+    k_read_offsets<<<grid_for(n_reads + 1, T), T, 0, st>>>(sd->d_m_idx, sd->d_mv_off, sd->d_a_pos, sd->d_mp_pos, n_reads, sd->d_a_off, sd->d_mp_off);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sd->h_a_off, sd->d_a_off, ((size_t)n_reads + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sd->h_mp_off, sd->d_mp_off, ((size_t)n_reads + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sd->h_rep_len, sd->d_rep_len, (size_t)std::max(n_reads, 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const long long n_a = sd->n_a = sd->h_a_off[n_reads];
+    sd->n_mp = sd->h_mp_off[n_reads];
+    if (n_a > sd->max_anchors) return fail(MM2GB_ECAP, "batch seeds %lld anchors, the seeder holds %lld", n_a, (long long)sd->max_anchors);
+    CK(cudaEventRecord(sd->ev[4], st));
+    if (n_m) {
+        k_expand<<<grid_for(n_m, T), T, 0, st>>>(sd->m, ix->d_occ, sd->d_a_pos, sd->d_mp_pos, sd->d_seq_off, n_m, ix->k, sd->d_a_tmp,
+                                                 want_mini_pos ? sd->d_mini_pos : nullptr);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(sd->ev[5], st));
+    if (n_a) {
+        k_seed_sort<<<n_reads, kSortThreads, (size_t)sd->sort_smem_words * sizeof(u32), st>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, nullptr, n_reads,
+                                                                                             sd->sort_smem_words, sd->d_words, sd->d_queue);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(sd->ev[6], st));
+    sd->timed = true;
+    (void)seq_off;
+    return MM2GB_OK;
+}
+
+} // namespace
+
+// ---- C ABI: seeder ---------------------------------------------------------------------------------------------------------
+
+extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *idx, int64_t max_bases, int max_reads, int64_t max_anchors)
+{
+    if (!out || !idx || max_bases <= 0 || max_reads <= 0 || max_anchors <= 0) return fail(MM2GB_EARG, "bad argument");
+    if (max_anchors > (int64_t)INT32_MAX - 1024) return fail(MM2GB_EARG, "max_anchors must be below 2^31");
+    *out = nullptr;
+    CK(cudaSetDevice(idx->device));
+    mm2gb_seeder *sd = new mm2gb_seeder();
+    sd->idx = idx;
+    sd->device = idx->device;
+    sd->max_bases = max_bases;
+    sd->max_reads = max_reads;
+    sd->max_anchors = max_anchors;
+    sd->max_tiles = (int)std::min<int64_t>(INT32_MAX - 1, max_bases / kTile + max_reads + 1);
+    // expected density of (w, k)-minimizers is 2 / (w + 1) per base; repeats of short period exceed it, hence the margin
+    sd->max_mv = std::max<int64_t>(1024, (int64_t)((double)max_bases * 3.0 / (idx->w + 1)) + 64 * (int64_t)max_reads);
+    const size_t M = (size_t)sd->max_mv, A = (size_t)max_anchors, R = (size_t)max_reads + 2, NT = (size_t)sd->max_tiles + 2;
+    int rc = MM2GB_OK;
+#define TRY(x) do { if ((rc = (x)) != MM2GB_OK) { mm2gb_seeder_destroy(sd); return rc; } } while (0)
+#define TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(MM2GB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); mm2gb_seeder_destroy(sd); return rc; } } while (0)
+    TRYC(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
+    for (auto &e : sd->ev) TRYC(cudaEventCreate(&e));
+    TRYC(cudaEventCreateWithFlags(&sd->ev_join, cudaEventDisableTiming));
+    for (auto &e : sd->ev_stage) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TRY(dalloc(sd->d_seq, (size_t)max_bases + 16));
+    TRY(dalloc(sd->d_seq_off, R)); TRY(dalloc(sd->d_tile_first, R));
+    TRY(dalloc(sd->d_tile_cnt, NT)); TRY(dalloc(sd->d_tile_base, NT));
+    TRY(dalloc(sd->d_part, std::max(M, NT) / kScanChunk + 4));
+    TRY(dalloc(sd->d_mv_x, M)); TRY(dalloc(sd->d_mv_y, M)); TRY(dalloc(sd->d_mv_seq, M)); TRY(dalloc(sd->d_mv_off, R));
+    TRY(dalloc(sd->d_keep, M)); TRY(dalloc(sd->d_tandem, M));
+    TRY(dalloc(sd->d_tab_key, 2 * M)); TRY(dalloc(sd->d_tab_cnt, 2 * M));
+    TRY(dalloc(sd->d_occ_n, M)); TRY(dalloc(sd->d_has, M)); TRY(dalloc(sd->d_occ_off, M)); TRY(dalloc(sd->d_m_idx, M + 1));
+    TRY(dalloc(sd->m.n, M)); TRY(dalloc(sd->m.q_pos, M)); TRY(dalloc(sd->m.off, M)); TRY(dalloc(sd->m.seq, M));
+    TRY(dalloc(sd->m.tandem, M)); TRY(dalloc(sd->m.flt, M));
+    TRY(dalloc(sd->d_cnt_a, M)); TRY(dalloc(sd->d_kept, M)); TRY(dalloc(sd->d_a_pos, M + 1)); TRY(dalloc(sd->d_mp_pos, M + 1));
+    TRY(dalloc(sd->d_mini_pos, M));
+    TRY(dalloc(sd->d_a_off, R)); TRY(dalloc(sd->d_mp_off, R)); TRY(dalloc(sd->d_rep_len, R));
+    TRY(dalloc(sd->d_a_tmp, A)); TRY(dalloc(sd->d_a, A)); TRY(dalloc(sd->d_words, A));
+    TRY(dalloc(sd->d_queue, 2 * (A / 64 + 2 * R + 8)));
+    TRY(dalloc(sd->d_f, A)); TRY(dalloc(sd->d_p, A));
+    TRYC(cudaHostAlloc((void **)&sd->h_a_off, R * sizeof(long long), cudaHostAllocDefault));
+    TRYC(cudaHostAlloc((void **)&sd->h_mp_off, R * sizeof(long long), cudaHostAllocDefault));
+    TRYC(cudaHostAlloc((void **)&sd->h_rep_len, R * sizeof(int), cudaHostAllocDefault));
+    TRYC(cudaHostAlloc((void **)&sd->h_tot, 64, cudaHostAllocDefault));
+    TRYC(cudaHostAlloc((void **)&sd->h_b, A * sizeof(mm2gb_anchor_t), cudaHostAllocMapped));
+    TRYC(cudaHostAlloc((void **)&sd->h_u, A * sizeof(uint64_t), cudaHostAllocMapped));
+    TRYC(cudaHostAlloc((void **)&sd->h_seq, (size_t)16 << 20, cudaHostAllocDefault));
+    {
+        // shared memory of the sort: the words of reads up to this size live on chip (two CTAs per SM); longer reads use HBM
+        int dev_smem = 0;
+        TRYC(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, sd->device));
+        int want = 24 * 1024;   // words (96 KB)
+        if (const char *e = getenv("MM2GB_SEED_SORT_WORDS")) want = std::max(64, atoi(e));
+        const int fit = (dev_smem - (int)sizeof(SortShared) - 1024) / 4;
+        sd->sort_smem_words = std::min(want, fit);
+        TRYC(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_smem_words * 4));
+    }
+#undef TRY
+#undef TRYC
+    *out = sd;
+    return MM2GB_OK;
+}
+
+extern "C" void mm2gb_seeder_destroy(mm2gb_seeder_t *sd)
+{
+    if (!sd) return;
+    cudaSetDevice(sd->device);
+    if (sd->stream) cudaStreamSynchronize(sd->stream);
+    void *dev[] = {sd->d_seq, sd->d_seq_off, sd->d_tile_first, sd->d_tile_cnt, sd->d_tile_base, sd->d_part, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq,
+                   sd->d_mv_off, sd->d_keep, sd->d_tandem, sd->d_tab_key, sd->d_tab_cnt, sd->d_occ_n, sd->d_has, sd->d_occ_off, sd->d_m_idx,
+                   sd->m.n, sd->m.q_pos, sd->m.off, sd->m.seq, sd->m.tandem, sd->m.flt, sd->d_cnt_a, sd->d_kept, sd->d_a_pos, sd->d_mp_pos,
+                   sd->d_mini_pos, sd->d_a_off, sd->d_mp_off, sd->d_rep_len, sd->d_a_tmp, sd->d_a, sd->d_words, sd->d_queue, sd->d_f, sd->d_p};
+    for (void *p : dev) if (p) cudaFree(p);
+    void *pin[] = {sd->h_a_off, sd->h_mp_off, sd->h_rep_len, sd->h_tot, sd->h_b, sd->h_u, sd->h_seq};
+    for (void *p : pin) if (p) cudaFreeHost(p);
+    for (auto &e : sd->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : sd->ev_stage) if (e) cudaEventDestroy(e);
+    if (sd->ev_join) cudaEventDestroy(sd->ev_join);
+    if (sd->stream) cudaStreamDestroy(sd->stream);
+    cudaGetLastError();
+    delete sd;
+}
+
+extern "C" int mm2gb_sketch_host(mm2gb_seeder_t *sd, const char *seqs, const int64_t *seq_off, int n_seq, int rid_is_seq, uint64_t *out_xy,
+                                 int64_t cap, int64_t *mv_off)
+{
+    if (!sd || !seqs || !seq_off || !mv_off) return fail(MM2GB_EARG, "bad argument");
+    CK(cudaSetDevice(sd->device));
+    int rc = upload_offsets(sd, seq_off, n_seq);
+    if (rc) return rc;
+    rc = upload_seqs(sd, seqs, seq_off[n_seq]);
+    if (rc) return rc;
+    rc = run_sketch(sd, n_seq, rid_is_seq);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(mv_off, sd->d_mv_off, ((size_t)n_seq + 1) * sizeof(u64), cudaMemcpyDeviceToHost, sd->stream));
+    const long long n = std::min<long long>(sd->n_mv, cap);
+    std::vector<u64> x((size_t)n), y((size_t)n);
+    if (n && out_xy) {
+        CK(cudaMemcpyAsync(x.data(), sd->d_mv_x, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost, sd->stream));
+        CK(cudaMemcpyAsync(y.data(), sd->d_mv_y, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost, sd->stream));
+    }
+    CK(cudaStreamSynchronize(sd->stream));
+    if (out_xy) for (long long i = 0; i < n; ++i) out_xy[2 * i] = x[(size_t)i], out_xy[2 * i + 1] = y[(size_t)i];
+    return MM2GB_OK;
+}
+
+extern "C" int mm2gb_seed_host(mm2gb_seeder_t *sd, const mm2gb_seed_params_t *prm, const char *seqs, const int64_t *seq_off, int n_reads,
+                               mm2gb_anchor_t *a, int64_t a_cap, int64_t *a_off, int32_t *rep_len, uint64_t *mini_pos, int64_t mp_cap,
+                               int64_t *mp_off)
+{
+    if (!sd || !seqs || !seq_off || !a_off) return fail(MM2GB_EARG, "bad argument");
+    int rc = check_params(prm);
+    if (rc) return rc;
+    CK(cudaSetDevice(sd->device));
+    rc = upload_offsets(sd, seq_off, n_reads);
+    if (rc) return rc;
+    rc = upload_seqs(sd, seqs, seq_off[n_reads]);
+    if (rc) return rc;
+    rc = run_seed(sd, prm, seq_off, n_reads, mini_pos != nullptr);
+    if (rc) return rc;
+    if (a && sd->n_a > a_cap) return fail(MM2GB_ECAP, "%lld anchors do not fit the output (%lld)", sd->n_a, (long long)a_cap);
+    if (mini_pos && sd->n_mp > mp_cap) return fail(MM2GB_ECAP, "%lld mini_pos entries do not fit the output (%lld)", sd->n_mp, (long long)mp_cap);
+    if (a && sd->n_a) CK(cudaMemcpyAsync(a, sd->d_a, (size_t)sd->n_a * sizeof(mm2gb_anchor_t), cudaMemcpyDeviceToHost, sd->stream));
+    if (mini_pos && sd->n_mp) CK(cudaMemcpyAsync(mini_pos, sd->d_mini_pos, (size_t)sd->n_mp * sizeof(u64), cudaMemcpyDeviceToHost, sd->stream));
+    CK(cudaStreamSynchronize(sd->stream));
+    // max_qlen (map.c:376) is applied by the caller of mm_map_seed's equivalent: reads above it are not in the batch
+    for (int r = 0; r <= n_reads; ++r) a_off[r] = sd->h_a_off[r];
+    if (mp_off) for (int r = 0; r <= n_reads; ++r) mp_off[r] = sd->h_mp_off[r];
+    if (rep_len) for (int r = 0; r < n_reads; ++r) rep_len[r] = sd->h_rep_len[r];
+    return MM2GB_OK;
+}
+
+static int seed_chain_common(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads)
+{
+    int rc = run_seed(sd, prm, seq_off, n_reads, false);
+    if (rc) return rc;
+    // the chaining kernels run on the context's own stream: order them behind the seeding stream
+    cudaStream_t cs = (cudaStream_t)mm2gb_stream(ctx, 0);
+    if (!cs) return fail(MM2GB_EARG, "chaining context has no slot 0");
+    CK(cudaEventRecord(sd->ev_join, sd->stream));
+    CK(cudaStreamWaitEvent(cs, sd->ev_join, 0));
+    sd->a_off_copy.assign(sd->h_a_off, sd->h_a_off + n_reads + 1);
+    return mm2gb_chain_device_slot(ctx, 0, sd->d_a, sd->d_a_off, sd->a_off_copy.data(), n_reads, sd->n_a, sd->d_f, sd->d_p);
+}
+
+extern "C" int mm2gb_seed_chain(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const char *seqs, const int64_t *seq_off,
+                                int n_reads, mm2gb_seed_chain_result_t *res)
+{
+    if (!sd || !ctx || !seqs || !seq_off || !res) return fail(MM2GB_EARG, "bad argument");
+    int rc = check_params(prm);
+    if (rc) return rc;
+    CK(cudaSetDevice(sd->device));
+    rc = upload_offsets(sd, seq_off, n_reads);
+    if (rc) return rc;
+    rc = upload_seqs(sd, seqs, seq_off[n_reads]);
+    if (rc) return rc;
+    rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads);
+    if (rc) return rc;
+    rc = mm2gb_chain_device_fetch(ctx, 0, sd->d_a, sd->d_a_off, n_reads, sd->n_a, sd->h_b, sd->h_u);
+    if (rc) return rc;
+    memset(res, 0, sizeof(*res));
+    rc = mm2gb_chain_device_results(ctx, 0, &res->n_u, &res->u_pos, &res->n_b, &res->b_pos, &res->n_chains, &res->n_chain_anchors, &res->stats);
+    if (rc) return rc;
+    res->n_reads = n_reads;
+    res->n_anchors = sd->n_a;
+    res->a_off = (const int64_t *)sd->h_a_off;
+    res->rep_len = sd->h_rep_len;
+    res->u = sd->h_u;
+    res->b = sd->h_b;
+    res->h2d_bytes = seq_off[n_reads] + ((int64_t)n_reads + 1) * 12;
+    res->d2h_bytes = res->n_chain_anchors * 16 + res->n_chains * 8 + ((int64_t)n_reads + 1) * (16 + 8 + 8 + 4) + 24;
+    return MM2GB_OK;
+}
+
+extern "C" int mm2gb_seed_chain_device(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const void *d_seqs,
+                                       const int64_t *seq_off, int n_reads, int64_t *n_anchors)
+{
+    if (!sd || !ctx || !d_seqs || !seq_off) return fail(MM2GB_EARG, "bad argument");
+    int rc = check_params(prm);
+    if (rc) return rc;
+    CK(cudaSetDevice(sd->device));
+    rc = upload_offsets(sd, seq_off, n_reads);
+    if (rc) return rc;
+    unsigned char *own = sd->d_seq;
+    sd->d_seq = (unsigned char *)const_cast<void *>(d_seqs);
+    rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads);
+    sd->d_seq = own;
+    if (n_anchors) *n_anchors = sd->n_a;
+    return rc;
+}
+
+extern "C" int mm2gb_seed_profile(mm2gb_seeder_t *sd, float ms[MM2GB_SEED_NTIMERS], int64_t *n_minimizers, int64_t *n_seeds)
+{
+    if (!sd || !ms) return fail(MM2GB_EARG, "bad argument");
+    if (!sd->timed) return fail(MM2GB_ESTATE, "no batch has been seeded yet");
+    CK(cudaSetDevice(sd->device));
+    CK(cudaEventSynchronize(sd->ev[MM2GB_SEED_NTIMERS]));
+    for (int i = 0; i < MM2GB_SEED_NTIMERS; ++i) CK(cudaEventElapsedTime(&ms[i], sd->ev[i], sd->ev[i + 1]));
+    if (n_minimizers) *n_minimizers = sd->n_mv;
+    if (n_seeds) *n_seeds = sd->n_m;
+    return MM2GB_OK;
+}
+
+// ---- C ABI: index ------------------------------------------------------------------------------------------------------------
+
+extern "C" void mm2gb_index_destroy(mm2gb_index_t *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->d_key) cudaFree(ix->d_key);
+    if (ix->d_val) cudaFree(ix->d_val);
+    if (ix->d_occ) cudaFree(ix->d_occ);
+    cudaGetLastError();
+    delete ix;
+}
+
+extern "C" int mm2gb_index_build(mm2gb_index_t **out, int device, const char *seqs, const int64_t *seq_off, int n_seq, int w, int k, int is_hpc,
+                                 int bucket_bits)
+{
+    (void)bucket_bits;
+    if (!out || !seqs || !seq_off || n_seq <= 0) return fail(MM2GB_EARG, "bad argument");
+    *out = nullptr;
+    if (is_hpc) return fail(MM2GB_EARG, "homopolymer-compressed minimizers (MM_I_HPC) are not supported by the device seeding path");
+    if (k < 1 || k > 28 || !(k & 1)) return fail(MM2GB_EARG, "device seeding needs an odd k <= 28 (got %d)", k);
+    if (w < 1 || w > kMaxW) return fail(MM2GB_EARG, "device seeding needs 1 <= w <= %d (got %d)", kMaxW, w);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    mm2gb_index *ix = new mm2gb_index();
+    ix->device = device; ix->w = w; ix->k = k;
+    // sketch every sequence with the read kernel (rid = sequence number), in pieces of at most 256 M bases
+    std::vector<std::pair<u64, u64>> mz;     // (minimizer = x >> 8, y)
+    {
+        const int64_t piece = (int64_t)256 << 20;
+        int s0 = 0;
+        while (s0 < n_seq) {
+            int s1 = s0;
+            int64_t bases = 0;
+            while (s1 < n_seq && (s1 == s0 || bases + (seq_off[s1 + 1] - seq_off[s1]) <= piece)) { bases += seq_off[s1 + 1] - seq_off[s1]; ++s1; }
+            mm2gb_seeder *sd = nullptr;
+            // a throw-away seeder sized for this piece (only its sketch buffers matter: ask for the smallest anchor capacity)
+            int rc = mm2gb_seeder_create(&sd, ix, std::max<int64_t>(bases, 1), s1 - s0, 1024);
+            if (rc) { delete ix; return rc; }
+            std::vector<int64_t> off((size_t)(s1 - s0) + 1), mvo((size_t)(s1 - s0) + 1);
+            for (int s = s0; s <= s1; ++s) off[(size_t)(s - s0)] = seq_off[s] - seq_off[s0];
+            std::vector<uint64_t> xy((size_t)2 * sd->max_mv);
+            rc = mm2gb_sketch_host(sd, seqs + seq_off[s0], off.data(), s1 - s0, 1, xy.data(), sd->max_mv, mvo.data());
+            const long long n = sd->n_mv;
+            mm2gb_seeder_destroy(sd);
+            if (rc) { delete ix; return rc; }
+            mz.reserve(mz.size() + (size_t)n);
+            for (long long i = 0; i < n; ++i) mz.emplace_back(xy[2 * i] >> 8, xy[2 * i + 1] + ((u64)s0 << 32));
+            s0 = s1;
+        }
+    }
+    // group: by minimizer, positions ascending (index.c:224,253).  Sorted in slices on host threads (set-up, once per index)
+    {
+        const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const size_t n = mz.size();
+        if (n < (1u << 16) || nt == 1) std::sort(mz.begin(), mz.end());
+        else {
+            std::vector<size_t> cut(nt + 1);
+            for (unsigned t = 0; t <= nt; ++t) cut[t] = n * t / nt;
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() { std::sort(mz.begin() + (long)cut[t], mz.begin() + (long)cut[t + 1]); });
+            for (auto &x : th) x.join();
+            for (unsigned step = 1; step < nt; step *= 2) {
+                std::vector<std::thread> mt;
+                for (unsigned t = 0; t + step < nt; t += 2 * step)
+                    mt.emplace_back([&, t, step]() {
+                        std::inplace_merge(mz.begin() + (long)cut[t], mz.begin() + (long)cut[t + step], mz.begin() + (long)cut[std::min(nt, t + 2 * step)]);
+                    });
+                for (auto &x : mt) x.join();
+            }
+        }
+    }
+    ix->occ.resize(mz.size());
+    for (size_t i = 0; i < mz.size(); ++i) {
+        if (i == 0 || mz[i].first != mz[i - 1].first) { ix->keys.push_back(mz[i].first); ix->off.push_back(i); }
+        ix->occ[i] = mz[i].second;
+    }
+    ix->off.push_back(mz.size());
+    std::vector<std::pair<u64, u64>>().swap(mz);
+    const size_t nk = ix->keys.size();
+    size_t slots = 1024;
+    while (slots < 2 * nk) slots <<= 1;
+    ix->mask = slots - 1;
+    std::vector<u64> hk(slots, kNone), hv(slots, 0);
+    for (size_t i = 0; i < nk; ++i) {
+        const u64 cnt = ix->off[i + 1] - ix->off[i];
+        if (cnt >= (1ULL << 28) || ix->off[i] >= (1ULL << 36)) { delete ix; return fail(MM2GB_ECAP, "index too large for the table encoding"); }
+        u64 key = ix->keys[i], h = key;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;   // mix64 of seed_kernels.cuh
+        h &= ix->mask;
+        while (hk[h] != kNone) h = (h + 1) & ix->mask;
+        hk[h] = key; hv[h] = ix->off[i] << 28 | cnt;
+    }
+    auto bad = [&](cudaError_t e, const char *what) { int rc = fail(MM2GB_ECUDA, "%s: %s", what, cudaGetErrorString(e)); mm2gb_index_destroy(ix); return rc; };
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&ix->d_key, slots * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index keys)");
+    if ((e = cudaMalloc((void **)&ix->d_val, slots * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index values)");
+    if ((e = cudaMalloc((void **)&ix->d_occ, std::max<size_t>(ix->occ.size(), 1) * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index occurrences)");
+    if ((e = cudaMemcpy(ix->d_key, hk.data(), slots * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(index keys)");
+    if ((e = cudaMemcpy(ix->d_val, hv.data(), slots * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(index values)");
+    if (!ix->occ.empty() && (e = cudaMemcpy(ix->d_occ, ix->occ.data(), ix->occ.size() * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bad(e, "cudaMemcpy(index occurrences)");
+    *out = ix;
+    return MM2GB_OK;
+}
+
+extern "C" int32_t mm2gb_index_cal_max_occ(const mm2gb_index_t *ix, float f)
+{
+    if (!ix || f <= 0.f) return INT32_MAX;           // index.c:192
+    const size_t n = ix->keys.size();
+    if (n == 0) return INT32_MAX;
+    std::vector<uint32_t> a(n);
+    for (size_t i = 0; i < n; ++i) a[i] = (uint32_t)(ix->off[i + 1] - ix->off[i]);
+    size_t kk = (uint32_t)((1. - f) * n);           // index.c:204 (double arithmetic, truncated to 32 bits)
+    if (kk >= n) kk = n - 1;
+    std::nth_element(a.begin(), a.begin() + (long)kk, a.end());
+    return (int32_t)(a[kk] + 1);
+}
+
+extern "C" int64_t mm2gb_index_get(const mm2gb_index_t *ix, uint64_t minier, uint64_t *out, int64_t cap)
+{
+    if (!ix) return 0;
+    auto it = std::lower_bound(ix->keys.begin(), ix->keys.end(), minier);
+    if (it == ix->keys.end() || *it != minier) return 0;
+    const size_t i = (size_t)(it - ix->keys.begin());
+    const int64_t n = (int64_t)(ix->off[i + 1] - ix->off[i]);
+    for (int64_t t = 0; t < n && t < cap && out; ++t) out[t] = ix->occ[ix->off[i] + (size_t)t];
+    return n;
+}
+
+extern "C" int64_t mm2gb_index_n_keys(const mm2gb_index_t *ix) { return ix ? (int64_t)ix->keys.size() : 0; }
+extern "C" int64_t mm2gb_index_n_occ(const mm2gb_index_t *ix) { return ix ? (int64_t)ix->occ.size() : 0; }

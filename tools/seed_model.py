@@ -1,0 +1,305 @@
+"""Pure-Python model of the data-parallel restatements used by the device seeding kernels (seed_kernels.cuh), checked against the
+reference through oracle/pyrefseed.py.  Development aid: validates the per-position sketch rules, the closed form of
+mm_seed_select and the replay of radix_sort_128x on the CPU before GPU time is spent.  Not part of the product or the tests."""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+
+NONE = (1 << 64) - 1
+M64 = (1 << 64) - 1
+
+def hash64(key, mask):
+    key = (~key + (key << 21)) & mask
+    key = key ^ key >> 24
+    key = ((key + (key << 3)) + (key << 8)) & mask
+    key = key ^ key >> 14
+    key = ((key + (key << 2)) + (key << 4)) & mask
+    key = key ^ key >> 28
+    key = (key + (key << 31)) & mask
+    return key
+
+NT4 = {ord('A'): 0, ord('a'): 0, ord('C'): 1, ord('c'): 1, ord('G'): 2, ord('g'): 2, ord('T'): 3, ord('t'): 3, ord('U'): 3, ord('u'): 3}
+
+def sketch_model(seq: bytes, w: int, k: int, rid: int = 0):
+    n = len(seq)
+    code = [NT4.get(c, 4) for c in seq]
+    mask = (1 << (2 * k)) - 1
+    ix = [NONE] * n
+    iz = [0] * n
+    run = 0
+    l = [0] * n
+    for i in range(n):
+        run = run + 1 if code[i] < 4 else 0
+        l[i] = run
+        if run >= k:
+            f = r = 0
+            for t in range(k - 1, -1, -1):
+                c = code[i - t]
+                f = (f << 2 | c) & mask
+                r = (r >> 2) | (3 ^ c) << (2 * (k - 1))
+            if f != r:
+                z = 0 if f < r else 1
+                ix[i] = hash64(r if z else f, mask) << 8 | k
+                iz[i] = z
+    def X(p):
+        return ix[p] if p >= 0 else NONE
+    out = []
+    T1 = w + k - 1
+    for i in range(n):
+        cur = ix[i]
+        mprev_x, mprev_p = NONE, -1
+        for d in range(w, 0, -1):
+            x = X(i - d)
+            if x <= mprev_x:
+                mprev_x, mprev_p = x, i - d
+        mode = 0
+        mx, mp = NONE, -1
+        if cur <= mprev_x:
+            mode = 2
+        elif mprev_p == i - w:
+            mode = 3
+            for d in range(w - 1, -1, -1):
+                x = X(i - d)
+                if x <= mx:
+                    mx, mp = x, i - d
+        def emit(p):
+            out.append((ix[p], rid << 32 | p << 1 | iz[p]))
+        if l[i] == T1 and mprev_x != NONE:
+            for d in range(w - 1, 0, -1):
+                if X(i - d) == mprev_x and i - d != mprev_p:
+                    emit(i - d)
+        if mode == 2:
+            if l[i] >= T1 + 1 and mprev_x != NONE:
+                emit(mprev_p)
+        elif mode == 3:
+            if l[i] >= T1:
+                emit(mprev_p)
+            if l[i] >= T1 and mx != NONE:
+                for d in range(w - 1, -1, -1):
+                    if X(i - d) == mx and i - d != mp:
+                        emit(i - d)
+        if i == n - 1:
+            fx, fp = (cur, i) if mode == 2 else (mx, mp) if mode == 3 else (mprev_x, mprev_p)
+            if fx != NONE:
+                emit(fp)
+    return np.array(out, dtype=np.uint64).reshape(-1, 2)
+
+
+def flag_sort_model(keys):
+    """radix_sort_128x (ksort.h:98-151) replayed the way k_seed_sort does it: returns the permutation (indices into keys)."""
+    n = len(keys)
+    W = list(range(n))
+    def small(beg, end):
+        seg = W[beg:end]
+        seg = [x for _, x in sorted(zip([keys[i] for i in seg], range(len(seg))), key=lambda t: (t[0], t[1]))]
+        W[beg:end] = [W[beg + j] for j in seg]
+    if n <= 64:
+        small(0, n)
+        return W
+    level = [(0, n)]
+    sh = 56
+    while sh >= 0 and level:
+        nxt = []
+        for beg, end in level:
+            m = end - beg
+            dig = {i: (keys[W[i]] >> sh) & 255 for i in range(beg, end)}
+            cnt = [0] * 256
+            for i in range(beg, end):
+                cnt[dig[i]] += 1
+            if max(cnt) == m:
+                if sh > 0:
+                    nxt.append((beg, end))
+                continue
+            cur = [0] * 256
+            en = [0] * 256
+            run = beg
+            for d in range(256):
+                cur[d] = run
+                run += cnt[d]
+                en[d] = run
+            D = [0] * n
+            for i in range(beg, end):
+                D[i] = dig[i]
+            for kk in range(256):
+                kb = cur[kk]
+                while kb != en[kk]:
+                    cw, cd = W[kb], D[kb]
+                    if cd == kk:
+                        kb += 1
+                        continue
+                    while True:
+                        pos = cur[cd]
+                        cur[cd] = pos + 1
+                        ew, ed = W[pos], D[pos]
+                        W[pos], D[pos] = cw, cd
+                        cw, cd = ew, ed
+                        if cd == kk:
+                            break
+                    W[kb], D[kb] = cw, cd
+                    kb += 1
+            if sh > 0:
+                for kk in range(256):
+                    bb = en[kk - 1] if kk else beg
+                    be = en[kk]
+                    if be - bb > 64:
+                        nxt.append((bb, be))
+                    elif be - bb > 1:
+                        small(bb, be)
+        level = nxt
+        sh -= 8
+    return W
+
+
+if __name__ == "__main__":
+    import pyrefseed as rs
+    rng = np.random.default_rng(7)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    cases = []
+    for n in (1, 5, 14, 15, 16, 24, 25, 26, 40, 300, 3000):
+        cases.append(acgt[rng.integers(0, 4, n)].tobytes())
+    s = bytearray(acgt[rng.integers(0, 4, 4000)].tobytes())
+    for p in (10, 30, 31, 100, 101, 102, 500, 523, 524, 525, 526, 2000, 3999):
+        s[p] = ord('N')
+    cases.append(bytes(s))
+    cases.append(b"A" * 500)
+    cases.append(b"AC" * 400)
+    cases.append(b"ACG" * 300 + b"N" + b"ACGTT" * 100)
+    unit = acgt[rng.integers(0, 4, 37)].tobytes()
+    cases.append(unit * 60)
+    cases.append(b"acgtn" * 100 + unit * 5)
+    bad = 0
+    for w, k in ((10, 15), (5, 15), (19, 19), (1, 15), (11, 21), (32, 27)):
+        for c in cases:
+            a = rs.sketch(c, w, k)
+            b = sketch_model(c, w, k)
+            if a.shape != b.shape or not np.array_equal(a, b):
+                bad += 1
+                print("MISMATCH w", w, "k", k, "len", len(c), a.shape, b.shape)
+    print("sketch model mismatches:", bad)
+
+
+def seed_model(ix, seq: bytes, w, k, mid_occ, max_max_occ, occ_dist, q_occ_frac):
+    """mm_map_seed the way the kernels compute it; index lookups through the reference index object."""
+    mv = sketch_model(seq, w, k)
+    n = len(mv)
+    keep = [True] * n
+    if n > mid_occ and q_occ_frac > 0 and mid_occ > 0:
+        from collections import Counter
+        cnt = Counter(int(x) for x in mv[:, 0])
+        for i in range(n):
+            c = cnt[int(mv[i, 0])]
+            if c > mid_occ and np.float32(c) > np.float32(n) * np.float32(q_occ_frac):
+                keep[i] = False
+    surv = [i for i in range(n) if keep[i]]
+    seeds = []  # (n_occ, q_pos, occ list, tandem)
+    for t, i in enumerate(surv):
+        mz = int(mv[i, 0]) >> 8
+        occ = ix.get(mz)
+        if len(occ) == 0:
+            continue
+        td = (t > 0 and int(mv[surv[t - 1], 0]) >> 8 == mz) or (t + 1 < len(surv) and int(mv[surv[t + 1], 0]) >> 8 == mz)
+        seeds.append([len(occ), int(mv[i, 1]) & 0xffffffff, occ, td])
+    m = len(seeds)
+    flt = [0] * m
+    for i in range(m):
+        ni = seeds[i][0]
+        if occ_dist > 0 and max_max_occ > mid_occ:
+            if m >= 2 and ni > mid_occ:
+                st, en, rank = i, i + 1, 0
+                while st > 0 and seeds[st - 1][0] > mid_occ:
+                    st -= 1
+                    if seeds[st][0] <= ni:
+                        rank += 1
+                while en < m and seeds[en][0] > mid_occ:
+                    if seeds[en][0] < ni:
+                        rank += 1
+                    en += 1
+                ps = seeds[st - 1][1] >> 1 if st > 0 else 0
+                pe = seeds[en][1] >> 1 if en < m else len(seq)
+                mho = int((pe - ps) / occ_dist + .499)
+                mho = min(mho, 128)
+                flt[i] = 0 if (mho > 0 and rank < mho) else 1
+                if ni > max_max_occ:
+                    flt[i] = 1
+        elif ni > mid_occ:
+            flt[i] = 1
+    rep = 0
+    prev_en = 0
+    for i in range(m):
+        if flt[i]:
+            en = (seeds[i][1] >> 1) + 1
+            st = en - k
+            rep += en - max(st, prev_en)
+            prev_en = en
+    a = []
+    mp = []
+    qlen = len(seq)
+    for i in range(m):
+        if flt[i]:
+            continue
+        nocc, qp, occ, td = seeds[i]
+        fl = (1 << 42) if td else 0
+        for r in occ:
+            r = int(r)
+            rpos = (r & 0xffffffff) >> 1
+            if (r & 1) == (qp & 1):
+                a.append(((r & 0xffffffff00000000) | rpos, k << 32 | qp >> 1 | fl))
+            else:
+                a.append((1 << 63 | (r & 0xffffffff00000000) | rpos, k << 32 | (qlen - ((qp >> 1) + 1 - k) - 1) | fl))
+        mp.append(k << 32 | qp >> 1)
+    perm = flag_sort_model([x for x, _ in a])
+    a = np.array([a[i] for i in perm], dtype=np.uint64).reshape(-1, 2)
+    return a, rep, np.array(mp, dtype=np.uint64)
+
+
+def check_pipeline():
+    import pyrefseed as rs
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    # sort replay against the reference on keys with many ties
+    bad = 0
+    for n in (10, 64, 65, 200, 1000, 5000):
+        for spread in (3, 50, 1 << 20, 1 << 40):
+            x = rng.integers(0, spread, n).astype(np.uint64) * np.uint64(0x0101010101) + (rng.integers(0, 2, n).astype(np.uint64) << np.uint64(63))
+            xy = np.stack([x, np.arange(n, dtype=np.uint64)], axis=1)
+            ref = rs.radix_sort_128x(xy)
+            perm = flag_sort_model([int(v) for v in x])
+            if not np.array_equal(ref[:, 1], np.array(perm, dtype=np.uint64)):
+                bad += 1
+                print("sort MISMATCH n", n, "spread", spread)
+    print("sort model mismatches:", bad)
+    # a reference with repeat families and a tandem array; reads spanning them
+    ref = bytearray(acgt[rng.integers(0, 4, 300000)].tobytes())
+    unit = acgt[rng.integers(0, 4, 800)].tobytes()
+    for p in rng.integers(0, 290000, 60):
+        u = bytearray(unit)
+        for q in rng.integers(0, 800, 20):
+            u[q] = acgt[rng.integers(0, 4)]
+        ref[p:p + 800] = u
+    tu = acgt[rng.integers(0, 4, 53)].tobytes()
+    ref[100000:100000 + 53 * 80] = tu * 80
+    ref = bytes(ref)
+    ix = rs.RefIndex([ref, ref[5000:60000][::-1]])
+    bad = 0
+    for mid_occ, dist, frac in ((10, 500, 0.01), (3, 500, 0.01), (3, 0, 0.01), (5, 100, 0.0), (2, 50, 0.002)):
+        ix.field("mid_occ", mid_occ); ix.field("occ_dist", dist); ix.field("q_occ_frac", frac)
+        for st, ln in ((1000, 3000), (99000, 8000), (100100, 2000), (50000, 20000), (0, 300), (200000, 12000)):
+            read = bytearray(ref[st:st + ln])
+            for q in rng.integers(0, ln, ln // 12):
+                read[q] = acgt[rng.integers(0, 4)]
+            if st % 2000 == 0:
+                comp = bytes.maketrans(b"ACGT", b"TGCA")
+                read = bytearray(bytes(read).translate(comp)[::-1])
+            read = bytes(read)
+            a0, rep0, mp0 = ix.seed(read)
+            a1, rep1, mp1 = seed_model(ix, read, 10, 15, mid_occ, 4095, dist, np.float32(frac))
+            ok = a0.shape == a1.shape and np.array_equal(a0, a1) and rep0 == rep1 and np.array_equal(mp0, mp1)
+            if not ok:
+                bad += 1
+                same_set = a0.shape == a1.shape and np.array_equal(a0[np.lexsort((a0[:, 1], a0[:, 0]))], a1[np.lexsort((a1[:, 1], a1[:, 0]))])
+                print("seed MISMATCH", mid_occ, dist, frac, st, ln, a0.shape, a1.shape, rep0, rep1, len(mp0), len(mp1), "same set" if same_set else "different set")
+    print("seed model mismatches:", bad)
+
+
+if __name__ == "__main__":
+    check_pipeline()
