@@ -22,6 +22,10 @@ parity    = every read of the timed e2e run (n_u, chain-anchor count, digests of
 clocks    = SM clock and throttle reasons sampled through NVML every 20 ms over both timed regions.
 roofline  = the score kernel (dominant): algorithmic HBM bytes (24 B/anchor) over its CUDA-event time vs the measured copy
             peak, plus the issue-slot view that actually bounds it (SASS thread-instructions per pair / SM issue rate).
+seed_chain = (row N2) the fused device step on a sample of the same kind of reads: read SEQUENCES in (host memory), minimizers /
+            index lookups / seed filters / anchors / x-sort on the device (mm_map_seed, map.c:355-391), the anchors handed to the
+            chaining kernels in HBM, chains + compacted anchors out; next to the reference's mm_map_seed + mg_lchain_dp on the host
+            threads (oracle/_ref/libref_seed.so), with a per-read parity check of n_u, u[] and a'[].
 cpu_baseline / --impl reference = the reference's own lchain.c (oracle/_ref/libref_lchain.so, compiled from the
             reference sources in the build container; falls back to the oracle port) on all host threads.
 """
@@ -204,6 +208,95 @@ def host_stage_alone(pkg, misc, a, off, f, p, n_threads):
 
 
 _REAL_STDOUT = None
+
+
+def seed_chain_leg(pkg, torch, dist, w, rank, local_rank, world, host_threads, n_reads=3000, steps=5):
+    """Device seeding + chaining (include/mm2gb_seed.h) on `n_reads` reads of the workload's reference: end to end from host
+    sequences, device-resident, stage timers; the reference's mm_map_seed + mg_lchain_dp on the host threads beside it."""
+    from mm2gb_b200 import seed, synth
+    ref = synth.simulate_reference(w["ref_len"], seed=1, n_repeat_copies=w.get("n_repeat_copies", 0), repeat_unit=w.get("repeat_unit", 3000))
+    reads = synth.simulate_reads(ref, n_reads, w["lo"], w["hi"], seed=100 + rank, err=w["err"])
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    buf = synth._NT[np.concatenate(reads)]
+    ref_b = synth._NT[ref]
+    del ref, reads
+    t0 = time.perf_counter()
+    ix = seed.Index((ref_b, np.array([0, len(ref_b)], dtype=np.int64)), w=10, k=15, device=local_rank)
+    index_s = time.perf_counter() - t0
+    mid_occ = ix.mid_occ()
+    prm = seed.map_ont_seed_params(mid_occ)
+    misc = pkg.map_ont_misc()
+    bases = int(off[-1])
+    probe = seed.Seeder(ix, max_bases=bases + 4096, max_reads=n_reads + 8, max_anchors=max(1 << 20, bases))
+    _, a_off, _, _, _ = probe.seed(prm, buf, off, want_mini_pos=False)
+    n_a = int(a_off[-1])
+    probe.close()
+    cap = n_a + 4096
+    ctx = pkg.ChainContext(misc, device=local_rank, max_anchors=cap, max_reads=n_reads + 8, n_slots=1, flags=pkg.ChainContext.DEVICE_ONLY)
+    sd = seed.Seeder(ix, max_bases=bases + 4096, max_reads=n_reads + 8, max_anchors=cap)
+    for _ in range(2):
+        res = sd.seed_chain(ctx, prm, buf, off, copy=False)
+    pairs = int(res.stats.n_pairs)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = sd.seed_chain(ctx, prm, buf, off, copy=False)     # pageable host sequences in, chains + compacted anchors in host memory out
+    e2e_s = (time.perf_counter() - t0) / steps
+    stage_ms, n_mv, n_m = sd.profile()
+    d_seq = torch.from_numpy(buf).cuda()
+    sd.seed_chain_device(ctx, prm, d_seq.data_ptr(), off); ctx.sync(0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sd.seed_chain_device(ctx, prm, d_seq.data_ptr(), off)
+        ctx.sync(0)
+    dev_s = (time.perf_counter() - t0) / steps
+    full = sd.seed_chain(ctx, prm, buf, off)
+    out = {"what": "read sequences -> minimizers -> index lookups -> seed filters -> anchors -> x-sort (mm_map_seed, map.c:355-391) on the device, "
+                   "anchors handed to the chaining kernels in HBM, chains + compacted anchors back (include/mm2gb_seed.h: mm2gb_seed_chain)",
+           "sample": {"reads": n_reads, "bases": bases, "minimizers": n_mv, "seeds": n_m, "anchors": n_a, "pairs": pairs,
+                      "chains": int(full["n_chains"]), "chain_anchors": int(full["n_chain_anchors"]), "mid_occ": mid_occ},
+           "index": {"keys": ix.n_keys, "occurrences": ix.n_occ, "build_s": index_s,
+                     "note": "reference sketched by the same device kernel, grouped on the host once, open-addressing table in HBM"},
+           "e2e": {"ms_per_step": 1e3 * e2e_s, "reads_per_s": n_reads / e2e_s, "pairs_per_s": pairs / e2e_s, "bases_per_s": bases / e2e_s,
+                   "h2d_bytes_per_step": int(full["h2d_bytes"]), "d2h_bytes_per_step": int(full["d2h_bytes"])},
+           "device_resident": {"ms_per_step": 1e3 * dev_s, "reads_per_s": n_reads / dev_s, "pairs_per_s": pairs / dev_s},
+           "seed_stage_ms": stage_ms}
+    # the reference's own seeding + chaining on the host threads, and parity per read
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyrefseed as rs
+        if rank == 0 and rs.available():
+            rix = rs.RefIndex([ref_b.tobytes()], w=10, k=15)
+            rix.field("max_chain_skip", 2147483647)
+            ref_mid = int(rix.field("mid_occ"))
+            nc = min(n_reads, 1000)
+            sub = off[:nc + 1].copy()
+            t0 = time.perf_counter()
+            r_na, r_nu, r_dig, _ = rix.seed_batch(buf[:sub[-1]], sub, chain=True, threads=host_threads)
+            cpu_s = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rix.seed_batch(buf[:sub[-1]], sub, chain=False, threads=host_threads)
+            cpu_seed_s = time.perf_counter() - t0
+            bad = int(ref_mid != mid_occ)
+            for r in range(nc):
+                u = full["u"][full["u_pos"][r]:full["u_pos"][r] + full["n_u"][r]]
+                b = full["b"][full["b_pos"][r]:full["b_pos"][r] + full["n_b"][r]]
+                ok = int(full["n_u"][r]) == int(r_nu[r]) and int(full["a_off"][r + 1] - full["a_off"][r]) == int(r_na[r])
+                ok = ok and rs.chain_digest(u, b) == int(r_dig[r])
+                bad += 0 if ok else 1
+            out["cpu_reference"] = {"kind": "reference", "cores": host_threads, "sample": "first %d reads" % nc,
+                                    "seed_chain_reads_per_s": nc / cpu_s, "seed_only_reads_per_s": nc / cpu_seed_s,
+                                    "what": "mm_map_seed + mg_lchain_dp (max-chain-skip = inf) per read on the host threads"}
+            out["parity"] = {"reads_checked": nc, "mismatches": bad, "against": "reference mm_map_seed + mg_lchain_dp (oracle/_ref/libref_seed.so)",
+                             "what": "per read: anchors seeded, n_u, digest of u[] and of the compacted anchors a'[]"}
+            rix.close()
+    except Exception as e:  # noqa: BLE001
+        out["cpu_reference"] = {"error": repr(e)}
+    sd.close(); ctx.close(); ix.close()
+    return out, (n_reads, pairs), e2e_s
 
 
 def emit(obj):
@@ -443,8 +536,18 @@ def main():
               "includes_longest_reads": 50, "paths": {"dropin_chain_stream_gpu": bad_dropin, "core_abi_chain_host_index": bad_core, "host_stage_variant_counts": bad_hostvar},
               "what": "per read: n_u, number of chain anchors, digest of u[], digest of the compacted anchors a'[]"}
 
-    # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
+    # ---- row N2: device seeding + chaining fused (sequences in, chains out) ------------------------------------------------
+    seed_leg = None
+    if args.workload in ("ont", "mini") and not os.environ.get("MM2GB_BENCH_NO_SEED"):
+        seed_leg, (s_reads, s_pairs), s_sec = seed_chain_leg(pkg, torch, dist, w, rank, local_rank, world, host_threads,
+                                                            n_reads=min(3000, w["n_reads"]))
     from mm2gb_b200 import sharding
+    if seed_leg is not None:
+        (j_reads, j_pairs), (j_sec,) = sharding.reduce_job(dist, [s_reads, s_pairs], [s_sec], device="cuda")
+        seed_leg["job"] = {"n_gpus": world, "reads_per_s": j_reads / j_sec, "pairs_per_s": j_pairs / j_sec,
+                           "note": "every rank seeds + chains its own reads; sum of work / max over ranks of the end-to-end time"}
+
+    # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
     (tot_pairs, tot_anchors, tot_reads), (ms_max, e2e_max) = sharding.reduce_job(dist, [pairs, n, n_reads], [ms, e2e_s], device="cuda")
     if rank != 0:
         if dist is not None:
@@ -538,7 +641,7 @@ def main():
                     "core_abi": core_abi,
                     "breakdown_ms": {"dp_only_upload_kernels_fp_download": 1e3 * dp_only_s, "host_stage_variant_same_call": 1e3 * hostvar_s,
                                      "host_stage_alone": 1e3 * host_only_s, "host_threads": host_threads}},
-            "parity": parity,
+            "parity": parity, "seed_chain": seed_leg,
             "gpu_launches": (10 + 2 * bt_classes) * args.steps, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a, off)[0]
@@ -547,6 +650,9 @@ def main():
     ctx_e2e.close()
     if dist is not None:
         dist.destroy_process_group()
+    if seed_leg is not None and seed_leg.get("parity", {}).get("mismatches"):
+        sys.stderr.write("bench.py: PARITY FAILURE (seed_chain): %r\n" % (seed_leg["parity"],))
+        sys.exit(1)
     if parity["mismatches"]:
         sys.stderr.write("bench.py: PARITY FAILURE: %r\n" % (parity,))
         sys.exit(1)

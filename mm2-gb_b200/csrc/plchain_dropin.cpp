@@ -180,10 +180,20 @@ void stop_pool()
     }
 }
 
+// Fatal error: message already on stderr, exit status 1 -- as the reference (hipify.cuh:47-55).  Other threads (the context pool, the
+// driver threads of other GPUs) may be inside CUDA calls: running the atexit handlers / static destructors under them tears the
+// runtime down while it is in use (seen as a SIGSEGV instead of status 1), so every stdio stream is flushed and the process ends
+// without them.
+[[noreturn]] void fatal_exit()
+{
+    fflush(nullptr);
+    _exit(1);
+}
+
 [[noreturn]] void die(const char *what)
 {
     fprintf(stderr, "[ERROR] mm2gb chaining: %s: %s\n", what, mm2gb_last_error());
-    exit(1);
+    fatal_exit();
 }
 
 // ---- gpu config file: the reference's gpu/*.json (parsed there with cJSON, gpu/plmem.cu:373-451) --------------------------
@@ -292,7 +302,7 @@ void load_config(const char *path)
     JsonReader js;
     if (!txt.empty() && !js.parse(txt)) {
         fprintf(stderr, "[ERROR] mm2gb chaining: gpu config '%s' is not valid JSON\n", path);   // plmem.cu:390-413 exits too
-        exit(1);
+        fatal_exit();
     }
     double v;
     if (js.get("max_total_n", &v) && v >= 1) g_cfg.max_total_n = (size_t)v;
@@ -310,7 +320,7 @@ void load_config(const char *path)
     if (const char *e = getenv("MM2GB_SUB_MIN_READS")) g_cfg.sub_min_reads = std::max(1, atoi(e));
     if (g_cfg.max_total_n > ((size_t)1 << 31) - 2048) g_cfg.max_total_n = ((size_t)1 << 31) - 2048;
     const int ndev = mm2gb_device_count();
-    if (ndev <= 0) { fprintf(stderr, "[ERROR] mm2gb chaining: --gpu-chain needs a CUDA device (no CPU fallback)\n"); exit(1); }
+    if (ndev <= 0) { fprintf(stderr, "[ERROR] mm2gb chaining: --gpu-chain needs a CUDA device (no CPU fallback)\n"); fatal_exit(); }
     if (g_cfg.gpu_base >= ndev) g_cfg.gpu_base = 0;
     if (g_cfg.n_gpus <= 0 || g_cfg.n_gpus > ndev - g_cfg.gpu_base) g_cfg.n_gpus = ndev - g_cfg.gpu_base;
     // Every driver thread owns a context with room for two batches, so the batch limit handed to the driver has to fit the
@@ -379,9 +389,9 @@ void make_ctx(ThreadState &S, size_t cap_anchors, int cap_reads, const Misc_abi 
 
 ThreadState &state_of(int tid)
 {
-    if (tid < 0) { fprintf(stderr, "[ERROR] mm2gb chaining: thread id %d out of range\n", tid); exit(1); }
+    if (tid < 0) { fprintf(stderr, "[ERROR] mm2gb chaining: thread id %d out of range\n", tid); fatal_exit(); }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_inited) { fprintf(stderr, "[ERROR] mm2gb chaining: chain_stream_gpu before init_stream_gpu\n"); exit(1); }
+    if (!g_inited) { fprintf(stderr, "[ERROR] mm2gb chaining: chain_stream_gpu before init_stream_gpu\n"); fatal_exit(); }
     if ((size_t)tid >= g_state.size()) g_state.resize((size_t)tid + 1, nullptr);
     if (!g_state[(size_t)tid]) {
         g_state[(size_t)tid] = new ThreadState();
@@ -402,7 +412,7 @@ Misc_abi batch_misc(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt)
     if (!same_misc(misc, probe)) {
         fprintf(stderr, "[ERROR] mm2gb chaining: with these options the chaining parameters depend on the read length (short-read / "
                         "fragment mode); --gpu-chain supports single-segment long-read chaining only\n");
-        exit(1);
+        fatal_exit();
     }
     return misc;
 }
@@ -523,7 +533,7 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
     for (int r = 0; r < n_in; ++r) {
         if (in[r].n_seg > 1) {
             fprintf(stderr, "[ERROR] mm2gb chaining: read %ld has %d segments; --gpu-chain chains single-segment reads only\n", in[r].seq.i, in[r].n_seg);
-            exit(1);
+            fatal_exit();
         }
         S.ptrs[(size_t)r] = in[r].a;
         S.ns[(size_t)r] = in[r].a ? in[r].n : 0;
@@ -549,7 +559,7 @@ extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *op
         // batch of a thread already shows how large they are, and a thread that only ever sees small batches stays small
         size_t cap = need_slot + need_slot / 4 + (size_t)longest + 4096;
         if (cap > ((size_t)1 << 31) - 2048) cap = ((size_t)1 << 31) - 2048;
-        if (need_slot > cap) { fprintf(stderr, "[ERROR] mm2gb chaining: a sub-batch of %zu anchors cannot be indexed with 31 bits\n", need_slot); exit(1); }
+        if (need_slot > cap) { fprintf(stderr, "[ERROR] mm2gb chaining: a sub-batch of %zu anchors cannot be indexed with 31 bits\n", need_slot); fatal_exit(); }
         make_ctx(S, cap, std::max(g_cfg.max_read, n_in + n_in / 2) + 1, misc);
     } else if (new_misc) {
         if (mm2gb_ctx_set_misc(S.ctx, &misc) != MM2GB_OK) die("updating the chaining parameters");

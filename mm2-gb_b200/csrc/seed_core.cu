@@ -71,13 +71,15 @@ struct mm2gb_seeder {
     int max_reads = 0, max_tiles = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[MM2GB_SEED_NTIMERS + 1] = {nullptr};
-    cudaEvent_t ev_join = nullptr, ev_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_join = nullptr;
+    cudaStream_t stage_stream[4] = {nullptr};
+    cudaEvent_t stage_ev[4][2] = {{nullptr}}, stage_done[4] = {nullptr};
     // sequences
     unsigned char *d_seq = nullptr;
     long long *d_seq_off = nullptr;
     int *d_tile_first = nullptr;
     u32 *d_tile_cnt = nullptr;
-    u64 *d_tile_base = nullptr, *d_part = nullptr;
+    u64 *d_tile_base = nullptr, *d_part = nullptr, *d_scan_state = nullptr;
     // minimizers
     u64 *d_mv_x = nullptr, *d_mv_y = nullptr, *d_mv_off = nullptr;
     u32 *d_mv_seq = nullptr;
@@ -95,10 +97,14 @@ struct mm2gb_seeder {
     int *d_rep_len = nullptr;
     // anchors
     uint4 *d_a_tmp = nullptr, *d_a = nullptr;
-    u32 *d_words = nullptr;
-    int2 *d_queue = nullptr;
+    u32 *d_dest = nullptr, *d_lst = nullptr;       // x-sort: destinations of a pass, scratch lists
+    unsigned char *d_dig = nullptr;                // digits of reads too long for shared memory
+    int4 *d_stack = nullptr;
+    int *d_sort_list = nullptr, *h_sort_list = nullptr;
+    cudaStream_t sort_stream[4] = {nullptr};
+    cudaEvent_t sort_fork = nullptr, sort_join[4] = {nullptr};
     int *d_f = nullptr, *d_p = nullptr;
-    int sort_smem_words = 0;
+    int sort_max_cap = 0;
     // pinned host
     long long *h_a_off = nullptr, *h_mp_off = nullptr;
     int *h_rep_len = nullptr;
@@ -154,21 +160,23 @@ int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
     const int nt = sd->n_tiles;
     sd->n_mv = 0;
     if (nt == 0) { CK(cudaMemsetAsync(sd->d_mv_off, 0, ((size_t)n_seq + 1) * sizeof(u64), st)); return MM2GB_OK; }
-    k_sketch<false><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, ix->w, ix->k, rid_is_seq, sd->d_tile_cnt,
-                                          nullptr, nullptr, nullptr, nullptr);
+    // one pass (chained scan across tiles); the total is needed on the host only for the capacity check and the later grids
+    CK(cudaMemsetAsync(sd->d_scan_state, 0, ((size_t)nt + 1) * sizeof(u64), st));
+    if (ix->k <= 15)
+        k_sketch32<<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
+                                            (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
+    else
+        k_sketch<u64><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
+                                            (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     CK(cudaGetLastError());
-    int rc = scan_u32(st, sd->d_tile_cnt, nt, sd->d_tile_base, sd->d_part);
-    if (rc) return rc;
     CK(cudaMemcpyAsync(sd->h_tot, sd->d_tile_base + nt, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    k_seq_mv_off<<<grid_for(n_seq + 1, 256), 256, 0, st>>>(sd->d_tile_first, sd->d_tile_base, n_seq, sd->d_mv_off);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     sd->n_mv = (long long)sd->h_tot[0];
     if (sd->n_mv > sd->max_mv)
         return fail(MM2GB_ECAP, "batch has %lld minimizers, the seeder holds %lld (max_bases too small for this sequence content)",
                     sd->n_mv, (long long)sd->max_mv);
-    k_sketch<true><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, ix->w, ix->k, rid_is_seq, nullptr, sd->d_tile_base,
-                                         sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq);
-    k_seq_mv_off<<<grid_for(n_seq + 1, 256), 256, 0, st>>>(sd->d_tile_first, sd->d_tile_base, n_seq, sd->d_mv_off);
-    CK(cudaGetLastError());
     return MM2GB_OK;
 }
 
@@ -185,6 +193,12 @@ int upload_offsets(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
     return MM2GB_OK;
 }
 
+// Sequences -> device.  Pinned sources are DMA'd as they are.  Pageable ones are staged through pinned windows by kStageThreads
+// host threads, each with its own stream and two windows (the copy into one overlaps the DMA of the other): a single thread's
+// memcpy (~10 GB/s) would be five times slower than the link.
+constexpr int kStageThreads = 4;
+constexpr size_t kStageWindow = (size_t)4 << 20;
+
 int upload_seqs(mm2gb_seeder *sd, const char *seqs, int64_t n_bases)
 {
     if (n_bases <= 0) return MM2GB_OK;
@@ -192,24 +206,36 @@ int upload_seqs(mm2gb_seeder *sd, const char *seqs, int64_t n_bases)
     const bool pinned = cudaPointerGetAttributes(&at, seqs) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned) { CK(cudaMemcpyAsync(sd->d_seq, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, sd->stream)); return MM2GB_OK; }
-    // pageable source: staged through pinned memory in two halves so that the copy of one overlaps the DMA of the other
-    const size_t half = ((size_t)sd->max_bases + 1) / 2;
-    size_t done = 0;
-    int which = 0;
-    cudaEvent_t evs[2] = {sd->ev_stage[0], sd->ev_stage[1]};
-    bool used[2] = {false, false};
-    const size_t piece = std::min<size_t>(half, (size_t)8 << 20);
-    while (done < (size_t)n_bases) {
-        const size_t n = std::min(piece, (size_t)n_bases - done);
-        // two staging windows of `piece` bytes
-        unsigned char *stg = sd->h_seq + (size_t)which * piece;
-        if (used[which]) CK(cudaEventSynchronize(evs[which]));
-        memcpy(stg, seqs + done, n);
-        CK(cudaMemcpyAsync(sd->d_seq + done, stg, n, cudaMemcpyHostToDevice, sd->stream));
-        CK(cudaEventRecord(evs[which], sd->stream));
-        used[which] = true;
-        which ^= 1;
-        done += n;
+    const int nt = (size_t)n_bases < 4 * kStageWindow ? 1 : kStageThreads;
+    cudaError_t err[kStageThreads];
+    auto work = [&](int t) {
+        err[t] = cudaSetDevice(sd->device);
+        const size_t b0 = (size_t)n_bases * (size_t)t / (size_t)nt, b1 = (size_t)n_bases * (size_t)(t + 1) / (size_t)nt;
+        bool used[2] = {false, false};
+        int which = 0;
+        for (size_t done = b0; done < b1 && err[t] == cudaSuccess; which ^= 1) {
+            const size_t n = std::min(kStageWindow, b1 - done);
+            unsigned char *stg = sd->h_seq + ((size_t)t * 2 + (size_t)which) * kStageWindow;
+            cudaEvent_t ev = sd->stage_ev[t][which];
+            if (used[which] && (err[t] = cudaEventSynchronize(ev)) != cudaSuccess) break;
+            memcpy(stg, seqs + done, n);
+            if ((err[t] = cudaMemcpyAsync(sd->d_seq + done, stg, n, cudaMemcpyHostToDevice, sd->stage_stream[t])) != cudaSuccess) break;
+            err[t] = cudaEventRecord(ev, sd->stage_stream[t]);
+            used[which] = true;
+            done += n;
+        }
+        if (err[t] == cudaSuccess) err[t] = cudaEventRecord(sd->stage_done[t], sd->stage_stream[t]);
+    };
+    // the staging streams start behind whatever still reads d_seq on the main stream
+    CK(cudaEventRecord(sd->ev_join, sd->stream));
+    for (int t = 0; t < nt; ++t) CK(cudaStreamWaitEvent(sd->stage_stream[t], sd->ev_join, 0));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (int t = 0; t < nt; ++t) {
+        if (err[t] != cudaSuccess) return fail(MM2GB_ECUDA, "staging the sequences: %s", cudaGetErrorString(err[t]));
+        CK(cudaStreamWaitEvent(sd->stream, sd->stage_done[t], 0));
     }
     return MM2GB_OK;
 }
@@ -222,6 +248,57 @@ int check_params(const mm2gb_seed_params_t *p)
                                 "not supported by the device seeding path", (long long)p->flag);
     if (p->sdust_thres > 0) return fail(MM2GB_EARG, "sdust masking of query minimizers is not supported by the device seeding path");
     if (p->mid_occ <= 0) return fail(MM2GB_EARG, "mid_occ must be positive (run mm_mapopt_update / mm2gb_index_cal_max_occ first)");
+    return MM2GB_OK;
+}
+
+// x-sort of every read (k_seed_sort): reads binned by anchor count into shared-memory size classes (digit bytes per read,
+// warps = reads per CTA), the classes side by side on auxiliary streams, longest reads first inside a class
+int run_sort(mm2gb_seeder *sd, int n_reads)
+{
+    struct Cls { int cap, warps; };
+    static const Cls base[] = {{2048, 4}, {4096, 4}, {8192, 2}, {16384, 1}, {32768, 1}, {65536, 1}, {131072, 1}};
+    std::vector<Cls> cls;
+    for (const Cls &c : base) if (c.cap < sd->sort_max_cap) cls.push_back(c);
+    cls.push_back({sd->sort_max_cap, 1});
+    const int nc = (int)cls.size();            // class nc = reads whose digits stay in HBM
+    std::vector<std::vector<int>> bin((size_t)nc + 1);
+    const long long *off = sd->h_a_off;
+    for (int r = 0; r < n_reads; ++r) {
+        const long long n = off[r + 1] - off[r];
+        if (n <= 0) continue;
+        int k = 0;
+        while (k < nc && n > cls[(size_t)k].cap) ++k;
+        bin[(size_t)k].push_back(r);
+    }
+    int pos = 0;
+    std::vector<int> start((size_t)nc + 2, 0);
+    for (int k = nc; k >= 0; --k) {
+        auto &b = bin[(size_t)k];
+        std::sort(b.begin(), b.end(), [&](int x, int y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; });
+        start[(size_t)k] = pos;
+        for (int r : b) sd->h_sort_list[pos++] = r;
+    }
+    if (!pos) return MM2GB_OK;
+    cudaStream_t st = sd->stream;
+    CK(cudaMemcpyAsync(sd->d_sort_list, sd->h_sort_list, (size_t)pos * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(sd->sort_fork, st));
+    int used = 0;
+    for (int k = nc; k >= 0; --k) {
+        const int cnt = (int)bin[(size_t)k].size();
+        if (!cnt) continue;
+        const int cap = k < nc ? cls[(size_t)k].cap : 0, warps = k < nc ? cls[(size_t)k].warps : 1;
+        cudaStream_t ss = sd->sort_stream[used & 3];
+        CK(cudaStreamWaitEvent(ss, sd->sort_fork, 0));
+        const size_t smem = (size_t)warps * ((size_t)cap + sizeof(SortShared));
+        k_seed_sort<<<(cnt + warps - 1) / warps, warps * 32, smem, ss>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, sd->d_sort_list + start[(size_t)k], cnt, cap,
+                                                                          sd->d_dig, sd->d_dest, sd->d_lst, sd->d_stack);
+        CK(cudaGetLastError());
+        ++used;
+    }
+    for (int i = 0; i < std::min(used, 4); ++i) {
+        CK(cudaEventRecord(sd->sort_join[i], sd->sort_stream[i]));
+        CK(cudaStreamWaitEvent(st, sd->sort_join[i], 0));
+    }
     return MM2GB_OK;
 }
 
@@ -293,9 +370,8 @@ int run_seed(mm2gb_seeder *sd, const mm2gb_seed_params_t *prm, const int64_t *se
     }
     CK(cudaEventRecord(sd->ev[5], st));
     if (n_a) {
-        k_seed_sort<<<n_reads, kSortThreads, (size_t)sd->sort_smem_words * sizeof(u32), st>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, nullptr, n_reads,
-                                                                                             sd->sort_smem_words, sd->d_words, sd->d_queue);
-        CK(cudaGetLastError());
+        rc = run_sort(sd, n_reads);
+        if (rc) return rc;
     }
     CK(cudaEventRecord(sd->ev[6], st));
     sd->timed = true;
@@ -329,10 +405,14 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
     TRYC(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
     for (auto &e : sd->ev) TRYC(cudaEventCreate(&e));
     TRYC(cudaEventCreateWithFlags(&sd->ev_join, cudaEventDisableTiming));
-    for (auto &e : sd->ev_stage) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int t = 0; t < 4; ++t) {
+        TRYC(cudaStreamCreateWithFlags(&sd->stage_stream[t], cudaStreamNonBlocking));
+        TRYC(cudaEventCreateWithFlags(&sd->stage_done[t], cudaEventDisableTiming));
+        for (auto &e : sd->stage_ev[t]) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     TRY(dalloc(sd->d_seq, (size_t)max_bases + 16));
     TRY(dalloc(sd->d_seq_off, R)); TRY(dalloc(sd->d_tile_first, R));
-    TRY(dalloc(sd->d_tile_cnt, NT)); TRY(dalloc(sd->d_tile_base, NT));
+    TRY(dalloc(sd->d_tile_cnt, NT)); TRY(dalloc(sd->d_tile_base, NT)); TRY(dalloc(sd->d_scan_state, NT + 1));
     TRY(dalloc(sd->d_part, std::max(M, NT) / kScanChunk + 4));
     TRY(dalloc(sd->d_mv_x, M)); TRY(dalloc(sd->d_mv_y, M)); TRY(dalloc(sd->d_mv_seq, M)); TRY(dalloc(sd->d_mv_off, R));
     TRY(dalloc(sd->d_keep, M)); TRY(dalloc(sd->d_tandem, M));
@@ -343,25 +423,25 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
     TRY(dalloc(sd->d_cnt_a, M)); TRY(dalloc(sd->d_kept, M)); TRY(dalloc(sd->d_a_pos, M + 1)); TRY(dalloc(sd->d_mp_pos, M + 1));
     TRY(dalloc(sd->d_mini_pos, M));
     TRY(dalloc(sd->d_a_off, R)); TRY(dalloc(sd->d_mp_off, R)); TRY(dalloc(sd->d_rep_len, R));
-    TRY(dalloc(sd->d_a_tmp, A)); TRY(dalloc(sd->d_a, A)); TRY(dalloc(sd->d_words, A));
-    TRY(dalloc(sd->d_queue, 2 * (A / 64 + 2 * R + 8)));
+    TRY(dalloc(sd->d_a_tmp, A)); TRY(dalloc(sd->d_a, A)); TRY(dalloc(sd->d_dest, A)); TRY(dalloc(sd->d_lst, A)); TRY(dalloc(sd->d_dig, A));
+    TRY(dalloc(sd->d_stack, A / 64 + 16 * R + 16)); TRY(dalloc(sd->d_sort_list, R));
+    TRYC(cudaHostAlloc((void **)&sd->h_sort_list, R * sizeof(int), cudaHostAllocDefault));
+    for (auto &x : sd->sort_stream) TRYC(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    TRYC(cudaEventCreateWithFlags(&sd->sort_fork, cudaEventDisableTiming));
+    for (auto &x : sd->sort_join) TRYC(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     TRY(dalloc(sd->d_f, A)); TRY(dalloc(sd->d_p, A));
     TRYC(cudaHostAlloc((void **)&sd->h_a_off, R * sizeof(long long), cudaHostAllocDefault));
     TRYC(cudaHostAlloc((void **)&sd->h_mp_off, R * sizeof(long long), cudaHostAllocDefault));
     TRYC(cudaHostAlloc((void **)&sd->h_rep_len, R * sizeof(int), cudaHostAllocDefault));
     TRYC(cudaHostAlloc((void **)&sd->h_tot, 64, cudaHostAllocDefault));
-    TRYC(cudaHostAlloc((void **)&sd->h_b, A * sizeof(mm2gb_anchor_t), cudaHostAllocMapped));
-    TRYC(cudaHostAlloc((void **)&sd->h_u, A * sizeof(uint64_t), cudaHostAllocMapped));
-    TRYC(cudaHostAlloc((void **)&sd->h_seq, (size_t)16 << 20, cudaHostAllocDefault));
+    TRYC(cudaHostAlloc((void **)&sd->h_seq, (size_t)kStageThreads * 2 * kStageWindow, cudaHostAllocDefault));
     {
-        // shared memory of the sort: the words of reads up to this size live on chip (two CTAs per SM); longer reads use HBM
+        // the x-sort keeps one digit byte per anchor of a read in shared memory; reads above the largest class use HBM for them
         int dev_smem = 0;
         TRYC(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, sd->device));
-        int want = 24 * 1024;   // words (96 KB)
-        if (const char *e = getenv("MM2GB_SEED_SORT_WORDS")) want = std::max(64, atoi(e));
-        const int fit = (dev_smem - (int)sizeof(SortShared) - 1024) / 4;
-        sd->sort_smem_words = std::min(want, fit);
-        TRYC(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_smem_words * 4));
+        sd->sort_max_cap = ((dev_smem - (int)sizeof(SortShared) - 1024) / 16) * 16;
+        if (const char *e = getenv("MM2GB_SEED_SORT_CAP")) sd->sort_max_cap = std::max(64, std::min(sd->sort_max_cap, atoi(e) / 16 * 16));
+        TRYC(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_max_cap + (int)sizeof(SortShared)));
     }
 #undef TRY
 #undef TRYC
@@ -374,16 +454,23 @@ extern "C" void mm2gb_seeder_destroy(mm2gb_seeder_t *sd)
     if (!sd) return;
     cudaSetDevice(sd->device);
     if (sd->stream) cudaStreamSynchronize(sd->stream);
-    void *dev[] = {sd->d_seq, sd->d_seq_off, sd->d_tile_first, sd->d_tile_cnt, sd->d_tile_base, sd->d_part, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq,
+    void *dev[] = {sd->d_seq, sd->d_seq_off, sd->d_tile_first, sd->d_tile_cnt, sd->d_tile_base, sd->d_scan_state, sd->d_part, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq,
                    sd->d_mv_off, sd->d_keep, sd->d_tandem, sd->d_tab_key, sd->d_tab_cnt, sd->d_occ_n, sd->d_has, sd->d_occ_off, sd->d_m_idx,
                    sd->m.n, sd->m.q_pos, sd->m.off, sd->m.seq, sd->m.tandem, sd->m.flt, sd->d_cnt_a, sd->d_kept, sd->d_a_pos, sd->d_mp_pos,
-                   sd->d_mini_pos, sd->d_a_off, sd->d_mp_off, sd->d_rep_len, sd->d_a_tmp, sd->d_a, sd->d_words, sd->d_queue, sd->d_f, sd->d_p};
+                   sd->d_mini_pos, sd->d_a_off, sd->d_mp_off, sd->d_rep_len, sd->d_a_tmp, sd->d_a, sd->d_dest, sd->d_lst, sd->d_dig, sd->d_stack, sd->d_sort_list, sd->d_f, sd->d_p};
     for (void *p : dev) if (p) cudaFree(p);
-    void *pin[] = {sd->h_a_off, sd->h_mp_off, sd->h_rep_len, sd->h_tot, sd->h_b, sd->h_u, sd->h_seq};
+    void *pin[] = {sd->h_a_off, sd->h_mp_off, sd->h_rep_len, sd->h_tot, sd->h_b, sd->h_u, sd->h_seq, sd->h_sort_list};
     for (void *p : pin) if (p) cudaFreeHost(p);
     for (auto &e : sd->ev) if (e) cudaEventDestroy(e);
-    for (auto &e : sd->ev_stage) if (e) cudaEventDestroy(e);
+    for (int t = 0; t < 4; ++t) {
+        if (sd->stage_stream[t]) { cudaStreamSynchronize(sd->stage_stream[t]); cudaStreamDestroy(sd->stage_stream[t]); }
+        if (sd->stage_done[t]) cudaEventDestroy(sd->stage_done[t]);
+        for (auto &e : sd->stage_ev[t]) if (e) cudaEventDestroy(e);
+    }
     if (sd->ev_join) cudaEventDestroy(sd->ev_join);
+    if (sd->sort_fork) cudaEventDestroy(sd->sort_fork);
+    for (auto &e : sd->sort_join) if (e) cudaEventDestroy(e);
+    for (auto &x : sd->sort_stream) if (x) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
     if (sd->stream) cudaStreamDestroy(sd->stream);
     cudaGetLastError();
     delete sd;
@@ -462,6 +549,10 @@ extern "C" int mm2gb_seed_chain(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2g
     if (rc) return rc;
     rc = upload_seqs(sd, seqs, seq_off[n_reads]);
     if (rc) return rc;
+    if (!sd->h_b) {   // result landing buffers (pinned, mapped): allocated on first use, the parity / device-resident entries never need them
+        CK(cudaHostAlloc((void **)&sd->h_b, (size_t)sd->max_anchors * sizeof(mm2gb_anchor_t), cudaHostAllocMapped));
+        CK(cudaHostAlloc((void **)&sd->h_u, (size_t)sd->max_anchors * sizeof(uint64_t), cudaHostAllocMapped));
+    }
     rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads);
     if (rc) return rc;
     rc = mm2gb_chain_device_fetch(ctx, 0, sd->d_a, sd->d_a_off, n_reads, sd->n_a, sd->h_b, sd->h_u);

@@ -25,7 +25,10 @@ namespace mm2gb_seed {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-constexpr int kTile = 1024;          // positions per sketch tile = threads per CTA
+#ifndef MM2GB_SKETCH_TILE
+#define MM2GB_SKETCH_TILE 512
+#endif
+constexpr int kTile = MM2GB_SKETCH_TILE;   // positions per sketch tile = threads per CTA (a multiple of 32)
 constexpr int kHalo = 96;            // staged positions ahead of a tile (>= w + k, a multiple of 32)
 constexpr int kMaxW = 32;
 constexpr u64 kNone = ~0ULL;
@@ -67,158 +70,427 @@ __host__ __device__ __forceinline__ u64 hash64(u64 key, u64 mask)
 //   (P3) else if min(i-1) sits at i-w: emit it if l(i) >= w+k-1; then, if l(i) >= w+k-1 and the new minimum min(i) of
 //        [i-w+1, i] is not NONE, emit the other records of that window equal to min(i).x, oldest first;
 //   (P4) after the last position emit the final minimum if it is not NONE.
+// One pass: a tile's minimizer count is published to the tiles behind it through a chained scan with decoupled look-back
+// (ticket-ordered tiles; status word = flag << 62 | value), so the ordered output offset is known without a counting pass.
+// Bases are staged as 2-bit codes packed 32 per 64-bit word (earlier base = higher bits), so a k-mer is one funnel shift and
+// its reverse complement one bit reversal; for k <= 16 the hash and all window comparisons are 32-bit (HT = u32).
+template <typename HT>
 struct SketchTile {
-    unsigned char code[kHalo + kTile];
+    u64 pk[(kHalo + kTile) / 32];
     u32 nmask[(kHalo + kTile) / 32];
-    u64 ix[kMaxW + kTile];            // info.x of positions t0 - w .. t0 + kTile - 1
+    HT ih[kMaxW + kTile];             // hash of the k-mer ending at positions t0 - w .. t0 + kTile - 1 (all ones: none)
     unsigned char iz[kMaxW + kTile];  // strand bit
     u32 warp_sum[kTile / 32];
-    int seq;
+    u64 excl;
+    int seq, tile;
 };
 
-template <bool WRITE>
+__device__ __forceinline__ u64 spread32(u32 v)
+{
+    u64 x = v;
+    x = (x | x << 16) & 0x0000FFFF0000FFFFULL;
+    x = (x | x << 8) & 0x00FF00FF00FF00FFULL;
+    x = (x | x << 4) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | x << 2) & 0x3333333333333333ULL;
+    x = (x | x << 1) & 0x5555555555555555ULL;
+    return x;
+}
+
+__device__ __forceinline__ u32 hash32(u32 key, u32 mask)    // hash64 (sketch.c:28-38) for masks of at most 32 bits
+{
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return key;
+}
+
+#define MM2GB_FLAG_AGG (1ULL << 62)
+#define MM2GB_FLAG_PREFIX (2ULL << 62)
+#define MM2GB_VAL_MASK ((1ULL << 62) - 1ULL)
+
+// scan_state[0] = ticket counter, scan_state[1 + tile] = status; all zero before the launch
+template <typename HT>
 __global__ void __launch_bounds__(kTile)
 k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, int n_seq,
-         int w, int k, int rid_is_seq, u32 *__restrict__ tile_cnt, const u64 *__restrict__ tile_base, u64 *__restrict__ mv_x,
-         u64 *__restrict__ mv_y, u32 *__restrict__ mv_seq)
+         int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
+         u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
 {
-    __shared__ SketchTile S;
-    const int tid = threadIdx.x, tile = blockIdx.x;
+    __shared__ SketchTile<HT> S;
+    constexpr HT NONE = (HT)~(HT)0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
+        const int tile = (int)atomicAdd(scan_state, 1ULL);
         int lo = 0, hi = n_seq;   // last s with tile_first[s] <= tile
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_first[mid] <= tile) lo = mid; else hi = mid; }
         S.seq = lo;
+        S.tile = tile;
     }
     __syncthreads();
-    const int s = S.seq;
+    const int s = S.seq, tile = S.tile;
     const long long base = seq_off[s];
     const int len = (int)(seq_off[s + 1] - base);
     const int t0 = (tile - tile_first[s]) * kTile;
-    // stage the codes of positions t0 - kHalo .. t0 + kTile - 1 (outside the sequence: ambiguous)
+    // stage positions t0 - kHalo .. t0 + kTile - 1 (outside the sequence: ambiguous)
     for (int j = tid; j < kHalo + kTile; j += kTile) {
         const int pos = t0 - kHalo + j;
         const int c = (pos >= 0 && pos < len) ? nt4(__ldg(seqs + base + pos)) : 4;
-        S.code[j] = (unsigned char)c;
-        const u32 m = __ballot_sync(0xffffffffu, c == 4);
-        if ((tid & 31) == 0) S.nmask[j >> 5] = m;
+        const u32 b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), bn = __ballot_sync(0xffffffffu, c == 4);
+        if (lane == 0) {
+            S.pk[j >> 5] = spread32(__brev(b1)) << 1 | spread32(__brev(b0));
+            S.nmask[j >> 5] = bn;
+        }
     }
     __syncthreads();
     const u64 mask = (1ULL << (2 * k)) - 1;
-    const int shift1 = 2 * (k - 1);
-    // info of positions t0 - w .. t0 + kTile - 1
+    // hashes of positions t0 - w .. t0 + kTile - 1
     for (int j = tid; j < w + kTile; j += kTile) {
-        const int sj = kHalo - w + j;          // staged index of the position
-        const int pos = t0 - w + j;
-        u64 x = kNone;
+        const int sj = kHalo - w + j, pos = t0 - w + j;
+        HT h = NONE;
         unsigned char z = 0;
         if (pos >= k - 1 && pos < len) {
-            u64 f = 0, r = 0;
-            bool ok = true;
-            for (int t = k - 1; t >= 0; --t) {
-                const int c = S.code[sj - t];
-                ok = ok && c < 4;
-                f = (f << 2 | (u64)(c & 3)) & mask;
-                r = (r >> 2) | (u64)(3 ^ (c & 3)) << shift1;
-            }
-            if (ok && f != r) {
-                z = f < r ? 0 : 1;
-                x = hash64(z ? r : f, mask) << 8 | (u64)k;
+            const int q = sj >> 5, r = sj & 31;
+            // no ambiguous base among the last k positions: bits r-k+1 .. r of the mask words
+            const u64 nm = ((u64)S.nmask[q] << 32 | S.nmask[q - 1]) >> (r + 1);          // bit 31 = position sj, bit 31 - t = position sj - t
+            const bool ok = ((nm << 32 >> 32) >> (32 - k)) == 0;                          // k <= 28
+            if (ok) {
+                const int sft = 2 * (31 - r);
+                const u64 f64 = sft ? (S.pk[q] >> sft) | (S.pk[q - 1] << (64 - sft)) : S.pk[q];
+                const u64 f = f64 & mask;
+                u64 y = __brevll(f);
+                y = ((y & 0x5555555555555555ULL) << 1) | ((y >> 1) & 0x5555555555555555ULL);
+                const u64 rc = ((~y) >> (64 - 2 * k)) & mask;
+                if (f != rc) {
+                    z = f < rc ? 0 : 1;
+                    const u64 km = z ? rc : f;
+                    h = sizeof(HT) == 4 ? (HT)hash32((u32)km, (u32)mask) : (HT)hash64(km, mask);
+                }
             }
         }
-        S.ix[j] = x;
+        S.ih[j] = h;
         S.iz[j] = z;
     }
     __syncthreads();
     // the rules of the loop for position i = t0 + tid
-    const int i = t0 + tid;
-    int cnt = 0;
-    u64 wpos = 0;
-    // two passes over the same rules: count, then (after the block scan) write
-    const int jj = w + tid;   // index of position i in S.ix
+    const int i = t0 + tid, jj = w + tid;
     int l = 0;
-    u64 cur = kNone, mprev_x = kNone, mx = kNone;
+    HT cur = NONE, mprev_x = NONE, mx = NONE;
     int mprev_p = -1, mp = -1;
-    bool in_range = i < len;
+    const bool in_range = i < len;
+    int mode = 0;                                  // 2: rule P2, 3: rule P3
+    const int T1 = w + k - 1;
     if (in_range) {
-        // run of unambiguous bases ending at i (capped at 96, more than any threshold below)
+        // run of unambiguous bases ending at i (capped at 97, more than any threshold below)
         const int sj = kHalo + tid, q = sj >> 5, r = sj & 31;
         const u32 w2 = S.nmask[q] & (r == 31 ? 0xffffffffu : ((2u << r) - 1u));
         if (w2) l = r - (31 - __clz(w2));
         else {
-            const u32 w1 = q >= 1 ? S.nmask[q - 1] : 0xffffffffu;
+            const u32 w1 = S.nmask[q - 1];
             if (w1) l = r + 1 + __clz(w1);
             else {
-                const u32 w0 = q >= 2 ? S.nmask[q - 2] : 0xffffffffu;
+                const u32 w0 = S.nmask[q - 2];
                 l = w0 ? r + 33 + __clz(w0) : 97;
             }
         }
-        cur = S.ix[jj];
+        cur = S.ih[jj];
         for (int d = w; d >= 1; --d) {           // oldest -> newest, `<=` keeps the rightmost minimum
-            const u64 x = S.ix[jj - d];
+            const HT x = S.ih[jj - d];
             if (x <= mprev_x) mprev_x = x, mprev_p = i - d;
         }
-    }
-    const int T1 = w + k - 1;
-    int mode = 0;                                  // 2: rule P2, 3: rule P3
-    if (in_range) {
         if (cur <= mprev_x) mode = 2;
         else if (mprev_p == i - w) {
             mode = 3;
             for (int d = w - 1; d >= 0; --d) {
-                const u64 x = S.ix[jj - d];
+                const HT x = S.ih[jj - d];
                 if (x <= mx) mx = x, mp = i - d;
             }
         }
     }
-    for (int pass = 0; pass < (WRITE ? 2 : 1); ++pass) {
+    u64 wpos = 0;
+    for (int pass = 0; pass < 2; ++pass) {       // the same rules twice: count, then (after the scans) write
         int c = 0;
         auto emit = [&](int p) {
-            if (pass == 1) {
+            if (pass == 1 && (long long)(wpos + c) < cap) {
                 const int q = w + (p - t0);
-                mv_x[wpos + c] = S.ix[q];
+                mv_x[wpos + c] = (u64)S.ih[q] << 8 | (u64)k;
                 mv_y[wpos + c] = (rid_is_seq ? (u64)s << 32 : 0ULL) | (u64)(u32)p << 1 | (u64)S.iz[q];
                 mv_seq[wpos + c] = (u32)s;
             }
             ++c;
         };
         if (in_range) {
-            if (l == T1 && mprev_x != kNone)                                   // P1
+            if (l == T1 && mprev_x != NONE)                                    // P1
                 for (int d = w - 1; d >= 1; --d)
-                    if (S.ix[jj - d] == mprev_x && i - d != mprev_p) emit(i - d);
+                    if (S.ih[jj - d] == mprev_x && i - d != mprev_p) emit(i - d);
             if (mode == 2) {                                                  // P2
-                if (l >= T1 + 1 && mprev_x != kNone) emit(mprev_p);
+                if (l >= T1 + 1 && mprev_x != NONE) emit(mprev_p);
             } else if (mode == 3) {                                           // P3
                 if (l >= T1) emit(mprev_p);
-                if (l >= T1 && mx != kNone)
+                if (l >= T1 && mx != NONE)
                     for (int d = w - 1; d >= 0; --d)
-                        if (S.ix[jj - d] == mx && i - d != mp) emit(i - d);
+                        if (S.ih[jj - d] == mx && i - d != mp) emit(i - d);
             }
             if (i == len - 1) {                                               // P4
-                const u64 fx = mode == 2 ? cur : mode == 3 ? mx : mprev_x;
+                const HT fx = mode == 2 ? cur : mode == 3 ? mx : mprev_x;
                 const int fp = mode == 2 ? i : mode == 3 ? mp : mprev_p;
-                if (fx != kNone) emit(fp);
+                if (fx != NONE) emit(fp);
             }
         }
         if (pass == 0) {
-            cnt = c;
-            // block exclusive scan of cnt
-            u32 v = (u32)cnt;
-            const int lane = tid & 31, wid = tid >> 5;
+            // block exclusive scan of the counts
+            u32 v = (u32)c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
             if (lane == 31) S.warp_sum[wid] = v;
             __syncthreads();
             if (wid == 0) {
-                u32 t = S.warp_sum[lane];
+                u32 t = lane < kTile / 32 ? S.warp_sum[lane] : 0u;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
-                S.warp_sum[lane] = t;
+                if (lane < kTile / 32) S.warp_sum[lane] = t;
+                // chained scan across tiles: publish the aggregate, look back for the prefix, publish the inclusive prefix
+                const u64 tot = __shfl_sync(0xffffffffu, t, 31);
+                volatile u64 *st = scan_state + 1;
+                if (lane == 0) {
+                    __threadfence();
+                    st[tile] = (tile == 0 ? MM2GB_FLAG_PREFIX : MM2GB_FLAG_AGG) | tot;
+                }
+                u64 excl = 0;
+                if (tile > 0) {
+                    int look = tile - 1;
+                    for (;;) {
+                        const int idx = look - lane;
+                        u64 sv = idx >= 0 ? st[idx] : MM2GB_FLAG_PREFIX;
+                        while (__any_sync(0xffffffffu, (sv >> 62) == 0)) sv = idx >= 0 ? st[idx] : MM2GB_FLAG_PREFIX;
+                        const u32 pref = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                        const int first = pref ? __ffs(pref) - 1 : 32;      // nearest predecessor holding a full prefix
+                        u64 add = lane <= first ? (sv & MM2GB_VAL_MASK) : 0;
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                        excl += add;
+                        if (pref) break;
+                        look -= 32;
+                    }
+                    if (lane == 0) { __threadfence(); st[tile] = MM2GB_FLAG_PREFIX | (excl + tot); }
+                }
+                if (lane == 0) {
+                    S.excl = excl;
+                    tile_excl[tile] = excl;
+                    if (tile == n_tiles - 1) tile_excl[n_tiles] = excl + tot;
+                }
             }
             __syncthreads();
-            const u32 excl = v - (u32)cnt + (wid ? S.warp_sum[wid - 1] : 0u);
-            if (!WRITE) { if (tid == kTile - 1) tile_cnt[tile] = excl + (u32)cnt; }
-            else wpos = tile_base[tile] + excl;
+            wpos = S.excl + (v - (u32)c) + (wid ? S.warp_sum[wid - 1] : 0u);
         }
+    }
+}
+
+// ---- the same for k <= 15 (hashes of at most 30 bits; map-ont), restructured for instruction count ---------------------------
+// ncu of the kernel above (profiles/r6e_sketch_ncu.md): issue-bound, ~1000 warp instructions per 32 positions, most of them in
+// the two w-step window scans and in evaluating the rules twice.  Here the window minima come from prefix / suffix minima over
+// chunks of w positions (one thread per chunk; window [j-w+1, j] = suffix of one chunk + prefix of the next): keys
+// hash << 11 | (2047 - local position) give the RIGHTMOST minimum, hash << 11 | local position the leftmost one -- the two differ
+// exactly when the minimal hash occurs more than once in the window, the only case in which the "identical k-mer" loops of
+// rules P1 / P3 can emit anything.  The rules are evaluated once; a position emits at most two records unless such duplicates
+// exist (then it is re-evaluated when writing).
+struct SketchTile32 {
+    u64 pk[(kHalo + kTile) / 32];
+    u32 nmask[(kHalo + kTile) / 32];
+    u32 ih[kMaxW + kTile];
+    unsigned char iz[kMaxW + kTile];
+    u64 pre_r[kMaxW + kTile], suf_r[kMaxW + kTile], pre_l[kMaxW + kTile], suf_l[kMaxW + kTile];
+    u32 warp_sum[kTile / 32];
+    u64 excl;
+    int seq, tile;
+};
+
+__device__ __forceinline__ int nt4_fast(u32 ch)
+{
+    const u32 up = ch & 0xDFu, t = up - 'A';
+    const u32 x = (ch >> 1) & 3u;
+    const bool letter = t < 26u && ((1u << t) & ((1u << 0) | (1u << 2) | (1u << 6) | (1u << 19) | (1u << 20)));
+    return ch < 4u ? (int)ch : letter ? (int)(x ^ (x >> 1)) : 4;
+}
+
+__global__ void __launch_bounds__(kTile)
+k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, int n_seq,
+           int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
+           u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
+{
+    __shared__ SketchTile32 S;
+    constexpr u32 NONE = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        const int tile = (int)atomicAdd(scan_state, 1ULL);
+        int lo = 0, hi = n_seq;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_first[mid] <= tile) lo = mid; else hi = mid; }
+        S.seq = lo;
+        S.tile = tile;
+    }
+    __syncthreads();
+    const int s = S.seq, tile = S.tile;
+    const long long base = seq_off[s];
+    const int len = (int)(seq_off[s + 1] - base);
+    const int t0 = (tile - tile_first[s]) * kTile;
+    for (int j = tid; j < kHalo + kTile; j += kTile) {
+        const int pos = t0 - kHalo + j;
+        const int c = (pos >= 0 && pos < len) ? nt4_fast(__ldg(seqs + base + pos)) : 4;
+        const u32 b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), bn = __ballot_sync(0xffffffffu, c == 4);
+        if (lane == 0) {
+            S.pk[j >> 5] = spread32(__brev(b1)) << 1 | spread32(__brev(b0));
+            S.nmask[j >> 5] = bn;
+        }
+    }
+    __syncthreads();
+    const u32 mask = (u32)((1ULL << (2 * k)) - 1);
+    const int nloc = w + kTile;                    // local index 0 = position t0 - w
+    for (int j = tid; j < nloc; j += kTile) {
+        const int sj = kHalo - w + j, pos = t0 - w + j;
+        u32 h = NONE;
+        unsigned char z = 0;
+        if (pos >= k - 1 && pos < len) {
+            const int q = sj >> 5, r = sj & 31;
+            const u64 nm = ((u64)S.nmask[q] << 32 | S.nmask[q - 1]) >> (r + 1);
+            if ((((u32)nm) >> (32 - k)) == 0) {
+                const int sft = 2 * (31 - r);
+                const u64 f64 = sft ? (S.pk[q] >> sft) | (S.pk[q - 1] << (64 - sft)) : S.pk[q];
+                const u32 f = (u32)f64 & mask;
+                u32 y = __brev(f);
+                y = ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
+                const u32 rc = ((~y) >> (32 - 2 * k)) & mask;
+                if (f != rc) {
+                    z = f < rc ? 0 : 1;
+                    h = hash32(z ? rc : f, mask);
+                }
+            }
+        }
+        S.ih[j] = h;
+        S.iz[j] = z;
+    }
+    __syncthreads();
+    // prefix / suffix minima over chunks of w local positions
+    for (int cidx = tid; cidx * w < nloc; cidx += kTile) {
+        const int c0 = cidx * w, c1 = min(c0 + w, nloc);
+        u64 mr = ~0ULL, ml = ~0ULL;
+        for (int j = c0; j < c1; ++j) {
+            const u32 h = S.ih[j];
+            const u64 kr = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)(2047 - j)), kl = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)j);
+            mr = min(mr, kr); ml = min(ml, kl);
+            S.pre_r[j] = mr; S.pre_l[j] = ml;
+        }
+        mr = ~0ULL; ml = ~0ULL;
+        for (int j = c1 - 1; j >= c0; --j) {
+            const u32 h = S.ih[j];
+            const u64 kr = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)(2047 - j)), kl = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)j);
+            mr = min(mr, kr); ml = min(ml, kl);
+            S.suf_r[j] = mr; S.suf_l[j] = ml;
+        }
+    }
+    __syncthreads();
+    const int i = t0 + tid, jj = w + tid;
+    const bool in_range = i < len;
+    const int T1 = w + k - 1;
+    int l = 0, mode = 0, mprev_j = -1, mp_j = -1;  // local indices of min(i-1) and (rule P3) min(i)
+    u32 cur = NONE, mprev_x = NONE, mx = NONE;
+    bool dup1 = false, dup0 = false;               // the minimal hash of window (i-1) / (i) occurs more than once
+    if (in_range) {
+        const int sj = kHalo + tid, q = sj >> 5, r = sj & 31;
+        const u32 w2 = S.nmask[q] & (r == 31 ? 0xffffffffu : ((2u << r) - 1u));
+        if (w2) l = r - (31 - __clz(w2));
+        else {
+            const u32 w1 = S.nmask[q - 1];
+            if (w1) l = r + 1 + __clz(w1);
+            else { const u32 w0 = S.nmask[q - 2]; l = w0 ? r + 33 + __clz(w0) : 97; }
+        }
+        cur = S.ih[jj];
+        // window (i-1) = local [jj - w, jj - 1]; the rightmost minimum with `<=` semantics over all-NONE windows is its newest slot
+        const u64 m1r = min(S.suf_r[jj - w], S.pre_r[jj - 1]), m1l = min(S.suf_l[jj - w], S.pre_l[jj - 1]);
+        if (m1r != ~0ULL) { mprev_x = (u32)(m1r >> 11); mprev_j = 2047 - (int)(m1r & 2047u); dup1 = (int)(m1l & 2047u) != mprev_j; }
+        else mprev_j = jj - 1;
+        if (cur <= mprev_x) mode = 2;
+        else if (mprev_j == jj - w) {
+            mode = 3;
+            const u64 m0r = min(S.suf_r[jj - w + 1], S.pre_r[jj]), m0l = min(S.suf_l[jj - w + 1], S.pre_l[jj]);
+            if (m0r != ~0ULL) { mx = (u32)(m0r >> 11); mp_j = 2047 - (int)(m0r & 2047u); dup0 = (int)(m0l & 2047u) != mp_j; }
+        }
+    }
+    auto rules = [&](auto &&emit) {                // emit(local index)
+        if (!in_range) return;
+        if (l == T1 && mprev_x != NONE && dup1)                                // P1
+            for (int d = w - 1; d >= 1; --d)
+                if (S.ih[jj - d] == mprev_x && jj - d != mprev_j) emit(jj - d);
+        if (mode == 2) {                                                      // P2
+            if (l >= T1 + 1 && mprev_x != NONE) emit(mprev_j);
+        } else if (mode == 3) {                                               // P3
+            if (l >= T1) emit(mprev_j);
+            if (l >= T1 && mx != NONE && dup0)
+                for (int d = w - 1; d >= 0; --d)
+                    if (S.ih[jj - d] == mx && jj - d != mp_j) emit(jj - d);
+        }
+        if (i == len - 1) {                                                   // P4
+            const u32 fx = mode == 2 ? cur : mode == 3 ? mx : mprev_x;
+            const int fj = mode == 2 ? jj : mode == 3 ? mp_j : mprev_j;
+            if (fx != NONE) emit(fj);
+        }
+    };
+    int c = 0, e0 = 0, e1 = 0;
+    rules([&](int j) { if (c == 0) e0 = j; else if (c == 1) e1 = j; ++c; });
+    // block exclusive scan of the counts, chained scan across tiles
+    u32 v = (u32)c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) S.warp_sum[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        u32 t = lane < kTile / 32 ? S.warp_sum[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+        if (lane < kTile / 32) S.warp_sum[lane] = t;
+        const u64 tot = __shfl_sync(0xffffffffu, t, 31);
+        volatile u64 *st = scan_state + 1;
+        if (lane == 0) { __threadfence(); st[tile] = (tile == 0 ? MM2GB_FLAG_PREFIX : MM2GB_FLAG_AGG) | tot; }
+        u64 excl = 0;
+        if (tile > 0) {
+            int look = tile - 1;
+            for (;;) {
+                const int idx = look - lane;
+                u64 sv = idx >= 0 ? st[idx] : MM2GB_FLAG_PREFIX;
+                while (__any_sync(0xffffffffu, (sv >> 62) == 0)) sv = idx >= 0 ? st[idx] : MM2GB_FLAG_PREFIX;
+                const u32 pref = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                const int first = pref ? __ffs(pref) - 1 : 32;
+                u64 add = lane <= first ? (sv & MM2GB_VAL_MASK) : 0;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                excl += add;
+                if (pref) break;
+                look -= 32;
+            }
+            if (lane == 0) { __threadfence(); st[tile] = MM2GB_FLAG_PREFIX | (excl + tot); }
+        }
+        if (lane == 0) {
+            S.excl = excl;
+            tile_excl[tile] = excl;
+            if (tile == n_tiles - 1) tile_excl[n_tiles] = excl + tot;
+        }
+    }
+    __syncthreads();
+    const u64 wpos = S.excl + (v - (u32)c) + (wid ? S.warp_sum[wid - 1] : 0u);
+    const u64 ridbits = rid_is_seq ? (u64)s << 32 : 0ULL;
+    auto put = [&](u64 at, int j) {
+        if ((long long)at >= cap) return;
+        mv_x[at] = (u64)S.ih[j] << 8 | (u64)k;
+        mv_y[at] = ridbits | (u64)(u32)(t0 - w + j) << 1 | (u64)S.iz[j];
+        mv_seq[at] = (u32)s;
+    };
+    if (c <= 2) {
+        if (c >= 1) put(wpos, e0);
+        if (c == 2) put(wpos + 1, e1);
+    } else {
+        int n = 0;
+        rules([&](int j) { put(wpos + n, j); ++n; });
     }
 }
 
@@ -504,35 +776,37 @@ __global__ void k_expand(Seeds m, const u64 *__restrict__ occ, const u64 *__rest
 
 // ---- radix_sort_128x (ksort.h:98-151) replayed per read --------------------------------------------------------------------
 //
-// One CTA per read.  W[i] = digit << 24 | index of the element now at position i (index into the read's unsorted anchors).
-// A segment [beg, end) at byte `sh` is taken by one warp: histogram of the digits (a pass in which all digits agree is the
-// identity and moves on to the next byte), bucket bounds, then lane 0 replays the American-flag permutation (ksort.h:125-138)
-// on the words; buckets of more than 64 elements are queued for the next byte, smaller ones (stable insertion sort in the
-// reference, ksort.h:105-115) are ranked by the warp on the full key.  At byte 0 nothing follows (ksort.h:140).
-constexpr int kSortWarps = 8;
-constexpr int kSortThreads = kSortWarps * 32;
-constexpr u32 kIdxMask = 0xffffffu;
-
+// One warp per read (reads binned by size so that the digit array of a read fits the shared memory of its class; several reads
+// per SM).  A segment [beg, end) at byte `sh` lives in one of two anchor buffers (ping-pong):
+//   1. digits: D[i] = byte `sh` of x, histogram (a pass in which all digits agree is the identity: next byte, nothing moves);
+//   2. destinations: the American-flag permutation (ksort.h:125-138) only ever reads slots that still hold their ORIGINAL
+//      element (a bucket's cursor never passes a slot twice), so it is replayed on the digits alone -- lane 0, two dependent
+//      shared-memory loads per moved element -- and emits dest[src]; a pass with exactly two non-empty buckets (the strand
+//      split at byte 7, always) has a closed form evaluated by all lanes (tools/seed_model.py: pass_dest_walk / pass_dest_two);
+//   3. scatter: other[dest[i]] = this[i], all lanes, 16-byte elements;
+//   4. buckets of more than 64 elements are pushed for the next byte; the others (stable insertion sort in the reference,
+//      ksort.h:105-115,143) are ranked on the full key inside 32-element windows and written to their final place.
+// At byte 0 nothing follows (ksort.h:140).  The sorted read ends up in the second buffer, which the chaining kernels read.
 struct SortShared {
-    u32 cur[kSortWarps][256];
-    u32 end[kSortWarps][256];
-    int q_n[2];
-    int q_take;
+    u32 cur[256];
+    u32 end[256];
 };
 
-__device__ __forceinline__ u64 key_of(const uint4 *__restrict__ in, u32 idx)
+__device__ __forceinline__ u64 key_x(const uint4 *p)
 {
-    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(in + idx));
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
     return (u64)v.y << 32 | v.x;
 }
 
-// stable rank sort of W[beg, end) (at most 64 elements) on the full key, by one warp
-__device__ __forceinline__ void small_sort(u32 *W, const uint4 *__restrict__ in, int beg, int end, int lane)
+// stable rank sort of src[beg, end) (at most 64 elements) on the full key into out[beg, end), by one warp (src may alias out)
+__device__ __forceinline__ void sort64_out(const uint4 *src, uint4 *out, int beg, int end, int lane)
 {
     const int m = end - beg;
-    if (m <= 1) return;
-    const u32 i0 = lane < m ? (W[beg + lane] & kIdxMask) : 0u, i1 = lane + 32 < m ? (W[beg + lane + 32] & kIdxMask) : 0u;
-    const u64 k0 = lane < m ? key_of(in, i0) : kNone, k1 = lane + 32 < m ? key_of(in, i1) : kNone;
+    if (m <= 0) return;
+    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
+    if (lane < m) e0 = src[beg + lane];
+    if (lane + 32 < m) e1 = src[beg + lane + 32];
+    const u64 k0 = (u64)e0.y << 32 | e0.x, k1 = (u64)e1.y << 32 | e1.x;
     int r0 = 0, r1 = 0;
     for (int t = 0; t < m; ++t) {
         const u64 kt = t < 32 ? __shfl_sync(0xffffffffu, k0, t) : __shfl_sync(0xffffffffu, k1, t - 32);
@@ -540,117 +814,223 @@ __device__ __forceinline__ void small_sort(u32 *W, const uint4 *__restrict__ in,
         r1 += (kt < k1 || (kt == k1 && t < lane + 32)) ? 1 : 0;
     }
     __syncwarp();
-    if (lane < m) W[beg + r0] = i0;
-    if (lane + 32 < m) W[beg + r1] = i1;
+    if (lane < m) out[beg + r0] = e0;
+    if (lane + 32 < m) out[beg + r1] = e1;
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-k_seed_sort(const uint4 *__restrict__ a_in, uint4 *__restrict__ a_out, const long long *__restrict__ a_off, const int *__restrict__ order,
-            int n_reads, int smem_words, u32 *__restrict__ g_words, int2 *__restrict__ g_queue)
+__global__ void __launch_bounds__(128)
+k_seed_sort(uint4 *__restrict__ buf_a, uint4 *__restrict__ buf_b, const long long *__restrict__ a_off, const int *__restrict__ list, int n_list,
+            int cap, unsigned char *__restrict__ g_dig, u32 *__restrict__ g_dest, u32 *__restrict__ g_lst, int4 *__restrict__ g_stack)
 {
-    extern __shared__ u32 sort_dyn[];
-    __shared__ SortShared S;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int r = order ? order[blockIdx.x] : blockIdx.x;
-    if (r >= n_reads) return;
+    extern __shared__ __align__(16) unsigned char sort_dyn[];      // per warp: cap digit bytes, then SortShared
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int li = blockIdx.x * wpb + wid;
+    if (li >= n_list) return;
+    const int r = list[li];
     const long long o0 = a_off[r];
     const int n = (int)(a_off[r + 1] - o0);
     if (n == 0) return;
-    const uint4 *in = a_in + o0;
-    uint4 *out = a_out + o0;
-    u32 *W = n <= smem_words ? sort_dyn : g_words + o0;
-    // segment queues of the read (two levels, ping-pong): entries (beg, end); at most n / 65 + 1 segments per level
-    int2 *Q[2];
-    const long long qcap = n / 64 + 2;
-    Q[0] = g_queue + 2 * (o0 / 64 + 2LL * r);
-    Q[1] = Q[0] + qcap;
-    for (int i = tid; i < n; i += kSortThreads) W[i] = (u32)i;
-    if (tid == 0) { S.q_n[0] = S.q_n[1] = 0; S.q_take = 0; }
-    __syncthreads();
-    if (n <= 64) {                                   // ksort.h:148
-        if (wid == 0) small_sort(W, in, 0, n, lane);
-    } else {
-        if (tid == 0) { Q[0][0] = make_int2(0, n); S.q_n[0] = 1; }
-        __syncthreads();
-        int level = 0;
-        for (int sh = 56; sh >= 0; sh -= 8, level ^= 1) {
-            const int nq = S.q_n[level];
-            if (nq == 0) break;
-            for (;;) {
-                int qi = 0;
-                if (lane == 0) qi = atomicAdd(&S.q_take, 1);
-                qi = __shfl_sync(0xffffffffu, qi, 0);
-                if (qi >= nq) break;
-                const int2 seg = Q[level][qi];
-                const int beg = seg.x, end = seg.y, m = end - beg;
-                u32 *cur = S.cur[wid], *en = S.end[wid];
-                for (int t = lane; t < 256; t += 32) cur[t] = 0;
-                __syncwarp();
-                for (int i = beg + lane; i < end; i += 32) {
-                    const u32 idx = W[i] & kIdxMask;
-                    const u32 d = (u32)(key_of(in, idx) >> sh) & 255u;
-                    W[i] = d << 24 | idx;
-                    atomicAdd(&cur[d], 1u);
-                }
-                __syncwarp();
-                // bucket bounds: lane t owns digits 8t .. 8t+7
-                u32 c[8], sum = 0;
-                bool single = false;
+    uint4 *const XA = buf_a + o0, *const OUT = buf_b + o0;
+    if (n <= 64) { sort64_out(XA, OUT, 0, n, lane); return; }        // ksort.h:148
+    unsigned char *mine = sort_dyn + (size_t)wid * ((size_t)cap + sizeof(SortShared));
+    unsigned char *D = n <= cap ? mine : g_dig + o0;
+    SortShared *SSw = reinterpret_cast<SortShared *>(mine + cap);
+    u32 *dest = g_dest + o0, *lst = g_lst + o0;
+    int4 *stack = g_stack + (o0 / 64 + 16LL * r);
+    u32 *cur = SSw->cur, *en = SSw->end;
+    int sp = 0;
+    if (lane == 0) stack[0] = make_int4(0, n, 0, 56);
+    sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        --sp;
+        const int4 seg = stack[sp];
+        const int beg = seg.x, end = seg.y, buf = seg.z, m = end - beg;
+        int sh = seg.w;
+        const uint4 *src = buf ? OUT : XA;
+        uint4 *dst = buf ? XA : OUT;
+        u32 c[8];
+        int n_nonempty = 0;
+        bool done = sh < 0;
+        u64 diff = 0;                                                  // bits in which the keys of the segment differ
+        while (!done) {
+            for (int t = lane; t < 256; t += 32) cur[t] = 0;
+            __syncwarp();
+            u64 k_or = 0, k_and = ~0ULL;
+            for (int i0 = beg; i0 < end; i0 += 128) {
+                u64 kx[4];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) { c[t] = cur[lane * 8 + t]; sum += c[t]; single = single || c[t] == (u32)m; }
-                single = __any_sync(0xffffffffu, single);
-                if (single) {                        // identity pass: the whole segment moves on to the next byte
-                    if (sh > 0 && lane == 0) { const int q = atomicAdd(&S.q_n[level ^ 1], 1); Q[level ^ 1][q] = seg; }
-                    continue;
-                }
-                u32 incl = sum;
+                for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; kx[t] = i < end ? key_x(src + i) : 0ULL; }
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                u32 run = (u32)beg + incl - sum;
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < 8; ++t) { cur[lane * 8 + t] = run; run += c[t]; en[lane * 8 + t] = run; }
-                __syncwarp();
-                if (lane == 0) {                     // ksort.h:125-138
-                    for (int kk = 0; kk < 256; ++kk) {
-                        const u32 ke = en[kk];
-                        u32 kb = cur[kk];
-                        while (kb != ke) {
-                            u32 carried = W[kb];
-                            u32 d = carried >> 24;
-                            if (d == (u32)kk) { ++kb; continue; }
-                            do {
-                                const u32 pos = cur[d];
-                                cur[d] = pos + 1;
-                                const u32 ev = W[pos];
-                                W[pos] = carried;
-                                carried = ev;
-                                d = carried >> 24;
-                            } while (d != (u32)kk);
-                            W[kb++] = carried;
-                        }
-                        cur[kk] = kb;
+                for (int t = 0; t < 4; ++t) {
+                    const int i = i0 + t * 32 + lane;
+                    const bool act = i < end;
+                    u32 d = 256;
+                    if (act) {
+                        d = (u32)(kx[t] >> sh) & 255u;
+                        D[i] = (unsigned char)d;
+                        dest[i] = (u32)i;
+                        k_or |= kx[t]; k_and &= kx[t];
                     }
+                    const u32 peers = __match_any_sync(0xffffffffu, d);
+                    if (act && lane == __ffs(peers) - 1) cur[d] += __popc(peers);
+                    __syncwarp();
+                }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) { k_or |= __shfl_xor_sync(0xffffffffu, k_or, o); k_and &= __shfl_xor_sync(0xffffffffu, k_and, o); }
+            diff = k_or ^ k_and;
+            bool single = false;
+            n_nonempty = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { c[t] = cur[lane * 8 + t]; single = single || c[t] == (u32)m; n_nonempty += c[t] ? 1 : 0; }
+            single = __any_sync(0xffffffffu, single);
+            if (!single) break;
+            // identity pass (nothing moves): on to the highest lower byte in which the keys differ at all
+            const u64 low = sh ? diff & ((1ULL << sh) - 1ULL) : 0ULL;
+            if (!low) { done = true; break; }                          // all keys equal from here down
+            sh = (63 - __clzll(low)) & ~7;
+        }
+        if (done) {
+            if (buf != 1) for (int i = beg + lane; i < end; i += 32) OUT[i] = src[i];
+            __syncwarp();
+            continue;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) n_nonempty += __shfl_xor_sync(0xffffffffu, n_nonempty, o);
+        u32 sum = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sum += c[t];
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        u32 run = (u32)beg + incl - sum;
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { cur[lane * 8 + t] = run; run += c[t]; en[lane * 8 + t] = run; }
+        __syncwarp();
+        if (n_nonempty == 2) {
+            // closed form.  A = lower digit, region [beg, mid); B = [mid, end).  p_j: B-elements in A's region, q_j: A-elements in B's
+            // region (equally many).  p_j -> q_{j-1} + 1 (mid for j = 0), q_j -> p_j, B-elements of B's region before q_last move up by one.
+            u32 dA = 256;
+#pragma unroll
+            for (int t = 7; t >= 0; --t) if (c[t]) dA = (u32)(lane * 8 + t);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) dA = min(dA, __shfl_xor_sync(0xffffffffu, dA, o));
+            const int mid = (int)en[dA];
+            int cntq = 0;
+            for (int i0 = mid; i0 < end; i0 += 32) {
+                const int i = i0 + lane;
+                const bool q = i < end && D[i] == (unsigned char)dA;
+                const u32 bal = __ballot_sync(0xffffffffu, q);
+                if (q) lst[cntq + __popc(bal & ((1u << lane) - 1u))] = (u32)i;
+                cntq += __popc(bal);
+            }
+            __syncwarp();
+            const int q_last = cntq ? (int)lst[cntq - 1] : -1;
+            for (int i = mid + lane; i < end; i += 32)
+                if (D[i] != (unsigned char)dA && i < q_last) dest[i] = (u32)i + 1u;
+            int cntp = 0;
+            for (int i0 = beg; i0 < mid; i0 += 32) {
+                const int i = i0 + lane;
+                const bool p = i < mid && D[i] != (unsigned char)dA;
+                const u32 bal = __ballot_sync(0xffffffffu, p);
+                if (p) {
+                    const int j = cntp + __popc(bal & ((1u << lane) - 1u));
+                    dest[i] = j ? lst[j - 1] + 1u : (u32)mid;
+                    dest[lst[j]] = (u32)i;
+                }
+                cntp += __popc(bal);
+            }
+        } else if (lane == 0) {                                        // ksort.h:125-138 on the digits
+            for (int kk = 0; kk < 256; ++kk) {
+                const u32 ke = en[kk];
+                u32 kb = cur[kk];
+                while (kb != ke) {
+                    u32 d = D[kb];
+                    if (d == (u32)kk) { ++kb; continue; }
+                    u32 from = kb;
+                    do {
+                        const u32 pos = cur[d];
+                        cur[d] = pos + 1;
+                        dest[from] = pos;
+                        from = pos;
+                        d = D[pos];
+                    } while (d != (u32)kk);
+                    dest[from] = kb;
+                    ++kb;
+                }
+            }
+        }
+        __syncwarp();
+        // scatter into the other buffer
+        for (int i0 = beg; i0 < end; i0 += 128) {
+            uint4 e[4];
+            u32 dd[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; if (i < end) { e[t] = src[i]; dd[t] = dest[i]; } }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = i0 + t * 32 + lane; if (i < end) dst[dd[t]] = e[t]; }
+        }
+        __syncwarp();
+        const int nbuf = buf ^ 1;
+        if (sh == 0) {                                                 // ksort.h:140: nothing follows the last byte
+            if (nbuf != 1) for (int i = beg + lane; i < end; i += 32) OUT[i] = dst[i];
+            __syncwarp();
+            continue;
+        }
+        // buckets of more than 64 elements: next byte -- directly the highest lower byte in which the keys of this segment differ (the
+        // passes in between would be identities for every subset); none left: the bucket is final as it stands (sh = -8: copied out)
+        const u64 low_diff = diff & ((1ULL << sh) - 1ULL);
+        const int child_sh = low_diff ? ((63 - __clzll(low_diff)) & ~7) : -8;
+        for (int t = 0; t < 8; ++t) {
+            const bool big = c[t] > 64u;
+            u32 bal = __ballot_sync(0xffffffffu, big);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                if (lane == l) { const int kk = lane * 8 + t; stack[sp] = make_int4((int)(en[kk] - c[t]), (int)en[kk], nbuf, child_sh); }
+                ++sp;
+            }
+        }
+        // the rest: ranked on the full key (stable) inside windows of 32 consecutive elements, written to their final place
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (beg + lane < end) e = dst[beg + lane];
+        for (int s = beg; s < end;) {
+            const int last = min(s + 32, end), i = s + lane;
+            int bs = -1, be = -1;
+            if (i < last) {
+                const u32 d = (u32)((((u64)e.y << 32 | e.x) >> sh) & 255u);
+                be = (int)en[d];
+                bs = d ? (int)en[d - 1] : beg;
+            }
+            const u64 key = (u64)e.y << 32 | e.x;
+            const int l_bs = __shfl_sync(0xffffffffu, bs, last - 1 - s), l_be = __shfl_sync(0xffffffffu, be, last - 1 - s);
+            const int cut = l_be > last ? l_bs : last;
+            const int f_be = __shfl_sync(0xffffffffu, be, 0);
+            const int next_s = cut == s ? f_be : cut;
+            uint4 e_next = make_uint4(0, 0, 0, 0);
+            if (next_s + lane < end) e_next = dst[next_s + lane];      // in flight while this window is ranked (disjoint from its writes)
+            if (cut == s) {                                            // the bucket starting here does not fit the window
+                if (f_be - s <= 64) sort64_out(dst, OUT, s, f_be, lane);
+            } else {
+                int rk = 0;
+                const int nw = cut - s;
+                for (int t = 0; t < nw; ++t) {
+                    const u64 kt = __shfl_sync(0xffffffffu, key, t);
+                    const int bt = __shfl_sync(0xffffffffu, bs, t);
+                    rk += (bt == bs && (kt < key || (kt == key && t < lane))) ? 1 : 0;
                 }
                 __syncwarp();
-                if (sh > 0) {                        // ksort.h:140-145
-                    for (int kk = 0; kk < 256; ++kk) {
-                        const int be = (int)en[kk], bb = kk ? (int)en[kk - 1] : beg;
-                        const int sz = be - bb;
-                        if (sz > 64) { if (lane == 0) { const int q = atomicAdd(&S.q_n[level ^ 1], 1); Q[level ^ 1][q] = make_int2(bb, be); } }
-                        else if (sz > 1) small_sort(W, in, bb, be, lane);
-                    }
-                }
+                if (i < cut) OUT[bs + rk] = e;
                 __syncwarp();
             }
-            __syncthreads();
-            if (tid == 0) { S.q_n[level] = 0; S.q_take = 0; }
-            __syncthreads();
+            s = next_s;
+            e = e_next;
         }
+        __syncwarp();
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += kSortThreads) out[i] = __ldg(in + (W[i] & kIdxMask));
 }
 
 } // namespace mm2gb_seed

@@ -59,6 +59,23 @@ def sketch(seq: bytes, w: int, k: int, rid: int = 0, hpc: bool = False) -> np.nd
         cap = int(n)
 
 
+DIGEST_C = 0x9E3779B97F4A7C15
+
+
+def word_digest(w) -> int:
+    """seed_shim.c word_digest: C (m + 1) + sum_k w[k] (2k + 1) C  mod 2^64 over the 64-bit words of `w`."""
+    w = np.ascontiguousarray(w, np.uint64).reshape(-1)
+    k = np.arange(len(w), dtype=np.uint64)
+    c = np.uint64(DIGEST_C)
+    with np.errstate(over="ignore"):
+        return int(c * np.uint64(len(w) + 1) + (w * ((np.uint64(2) * k + np.uint64(1)) * c)).sum(dtype=np.uint64))
+
+
+def chain_digest(u, b) -> int:
+    """what seed_batch(chain=True) reports per read: digest(u[]) + 31 * digest(compacted anchors)"""
+    return (word_digest(u) + 31 * word_digest(b)) & 0xFFFFFFFFFFFFFFFF
+
+
 def radix_sort_128x(xy: np.ndarray) -> np.ndarray:
     """The reference's unstable in-place MSD radix sort of mm128_t by x (ksort.h:98-151) on a copy of the (n, 2) array."""
     out = np.ascontiguousarray(xy, dtype=np.uint64).copy()

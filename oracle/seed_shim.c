@@ -124,11 +124,14 @@ typedef struct {
     Misc misc;
 } batch_t;
 
-static uint64_t fnv(uint64_t h, const void *p, size_t n)
+/* order-sensitive digest of a 64-bit word array, the formula of chain_oracle.c (orc_digest): C (m + 1) + sum_k w[k] (2k + 1) C mod 2^64
+ * (vectorisable on the checking side: oracle/pyoracle.py digest) */
+static uint64_t word_digest(const uint64_t *w, size_t m)
 {
-    const unsigned char *s = (const unsigned char *)p;
-    size_t i;
-    for (i = 0; i < n; ++i) h = (h ^ s[i]) * 1099511628211ULL;
+    const uint64_t c = 0x9E3779B97F4A7C15ULL;
+    uint64_t h = c * (uint64_t)(m + 1);
+    size_t k;
+    for (k = 0; k < m; ++k) h += w[k] * ((2 * (uint64_t)k + 1) * c);
     return h;
 }
 
@@ -151,21 +154,17 @@ static void *batch_worker(void *arg)
         }
         if (t->chain) {
             int n_u = 0;
-            uint64_t *u = 0, h = 1469598103934665603ULL;
+            uint64_t *u = 0;
             mm128_t *a2 = mg_lchain_dp(t->misc.max_dist_x, t->misc.max_dist_y, t->misc.bw, t->misc.max_skip, t->misc.max_iter,
                                        t->misc.min_cnt, t->misc.min_score, t->misc.chn_pen_gap, t->misc.chn_pen_skip,
                                        t->misc.is_cdna, t->misc.n_seg, n, rd.a, &n_u, &u, km);
             int64_t nb = 0;
             for (i = 0; i < n_u; ++i) nb += (int32_t)u[i];
             if (t->n_u) t->n_u[r] = n_u;
-            if (t->digest) {
-                h = fnv(h, u, (size_t)n_u * 8);
-                h = fnv(h, a2, (size_t)nb * 16);
-                t->digest[r] = h;
-            }
+            if (t->digest) t->digest[r] = word_digest(u, (size_t)n_u) + 31 * word_digest((const uint64_t *)a2, (size_t)nb * 2);
             kfree(km, a2); kfree(km, u);
         } else {
-            if (t->digest) t->digest[r] = fnv(1469598103934665603ULL, rd.a, (size_t)n * 16);
+            if (t->digest) t->digest[r] = word_digest((const uint64_t *)rd.a, (size_t)n * 2);
             kfree(km, rd.a);
         }
         kfree(km, rd.mini_pos);
@@ -175,8 +174,8 @@ static void *batch_worker(void *arg)
     return 0;
 }
 
-/* reads r = 0..n_reads-1 are seqs[seq_off[r] .. seq_off[r+1]); per read n_a, and -- with chain -- n_u and an FNV-1a digest of
- * u[] followed by the compacted anchors (without chain: digest of the anchor array).  n_threads host threads. */
+/* reads r = 0..n_reads-1 are seqs[seq_off[r] .. seq_off[r+1]); per read n_a, and -- with chain -- n_u and
+ * digest(u[]) + 31 * digest(compacted anchors) (without chain: digest of the anchor array; word_digest above).  n_threads host threads. */
 int refseed_seed_batch(const void *mi, const void *opt, const char *seqs, const int64_t *seq_off, int n_reads, int chain,
                        int n_threads, uint64_t *out_xy, const int64_t *out_off, int64_t *n_a, int32_t *n_u, uint64_t *digest)
 {

@@ -303,3 +303,109 @@ def check_pipeline():
 
 if __name__ == "__main__":
     check_pipeline()
+
+
+# ---- second formulation of one American-flag pass (what k_seed_sort does since r6b) ------------------------------------------
+# The walk only ever reads slots that still hold their original element (a bucket's cursor never passes a slot twice), so it can
+# run on the ORIGINAL digits alone and emit, per moved element, its destination; the elements are then scattered in parallel.
+
+def pass_dest_walk(dig):
+    n = len(dig)
+    cnt = [0] * 256
+    for d in dig:
+        cnt[d] += 1
+    cur, en, run = [0] * 256, [0] * 256, 0
+    for d in range(256):
+        cur[d] = run
+        run += cnt[d]
+        en[d] = run
+    dest = list(range(n))
+    for kk in range(256):
+        kb = cur[kk]
+        while kb != en[kk]:
+            d = dig[kb]
+            if d == kk:
+                kb += 1
+                continue
+            src = kb
+            while True:
+                pos = cur[d]
+                cur[d] = pos + 1
+                dest[src] = pos
+                src = pos
+                d = dig[pos]
+                if d == kk:
+                    break
+            dest[src] = kb
+            kb += 1
+    return dest, en
+
+
+def pass_dest_two(dig):
+    """closed form for a pass with exactly two non-empty buckets"""
+    n = len(dig)
+    lo = min(dig)
+    ca = sum(1 for d in dig if d == lo)
+    dest = list(range(n))
+    q = [x for x in range(ca, n) if dig[x] == lo]
+    p = [x for x in range(0, ca) if dig[x] != lo]
+    assert len(p) == len(q)
+    t = len(p)
+    for j in range(t):
+        dest[p[j]] = (q[j - 1] + 1) if j else ca
+        dest[q[j]] = p[j]
+    qt = q[-1] if t else -1
+    for x in range(ca, n):
+        if dig[x] != lo and x < qt:
+            dest[x] = x + 1
+    return dest
+
+
+def check_dest_forms():
+    rng = np.random.default_rng(3)
+    bad = 0
+    for n in (2, 3, 10, 100, 1000):
+        for nb in (2, 3, 7, 256):
+            for _ in range(20):
+                dig = [int(v) for v in rng.choice(rng.choice(256, nb, replace=False), n)]
+                keys = [d << 56 for d in dig]
+                # the reference order after ONE pass at shift 56 = flag pass on the digits; emulate with the word model
+                W = list(range(n))
+                cnt = [0] * 256
+                for d in dig:
+                    cnt[d] += 1
+                cur, en, run = [0] * 256, [0] * 256, 0
+                for d in range(256):
+                    cur[d] = run; run += cnt[d]; en[d] = run
+                D = list(dig)
+                for kk in range(256):
+                    kb = cur[kk]
+                    while kb != en[kk]:
+                        cw, cd = W[kb], D[kb]
+                        if cd == kk:
+                            kb += 1; continue
+                        while True:
+                            pos = cur[cd]; cur[cd] = pos + 1
+                            ew, ed = W[pos], D[pos]
+                            W[pos], D[pos] = cw, cd
+                            cw, cd = ew, ed
+                            if cd == kk:
+                                break
+                        W[kb], D[kb] = cw, cd
+                        kb += 1
+                dest, _ = pass_dest_walk(dig)
+                W2 = [0] * n
+                for s in range(n):
+                    W2[dest[s]] = s
+                if W2 != W:
+                    bad += 1
+                if len(set(dig)) == 2:
+                    d2 = pass_dest_two(dig)
+                    if d2 != dest:
+                        bad += 1
+                        print("two-bucket form differs", n, nb)
+    print("dest-form mismatches:", bad)
+
+
+if __name__ == "__main__":
+    check_dest_forms()
