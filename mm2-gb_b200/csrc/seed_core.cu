@@ -162,11 +162,12 @@ int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
     if (nt == 0) { CK(cudaMemsetAsync(sd->d_mv_off, 0, ((size_t)n_seq + 1) * sizeof(u64), st)); return MM2GB_OK; }
     // one pass (chained scan across tiles); the total is needed on the host only for the capacity check and the later grids
     CK(cudaMemsetAsync(sd->d_scan_state, 0, ((size_t)nt + 1) * sizeof(u64), st));
+    k_tile_map<<<grid_for(n_seq, 256), 256, 0, st>>>(sd->d_tile_first, n_seq, (int *)sd->d_tile_cnt);
     if (ix->k <= 15)
-        k_sketch32<<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
+        k_sketch32<<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
                                             (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     else
-        k_sketch<u64><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
+        k_sketch<u64><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
                                             (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sd->h_tot, sd->d_tile_base + nt, sizeof(u64), cudaMemcpyDeviceToHost, st));

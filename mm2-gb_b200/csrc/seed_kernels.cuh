@@ -115,7 +115,7 @@ __device__ __forceinline__ u32 hash32(u32 key, u32 mask)    // hash64 (sketch.c:
 // scan_state[0] = ticket counter, scan_state[1 + tile] = status; all zero before the launch
 template <typename HT>
 __global__ void __launch_bounds__(kTile)
-k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, int n_seq,
+k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq, int n_seq,
          int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
          u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
 {
@@ -124,9 +124,7 @@ k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ s
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         const int tile = (int)atomicAdd(scan_state, 1ULL);
-        int lo = 0, hi = n_seq;   // last s with tile_first[s] <= tile
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_first[mid] <= tile) lo = mid; else hi = mid; }
-        S.seq = lo;
+        S.seq = tile_seq[tile];
         S.tile = tile;
     }
     __syncthreads();
@@ -316,7 +314,7 @@ __device__ __forceinline__ int nt4_fast(u32 ch)
 }
 
 __global__ void __launch_bounds__(kTile)
-k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, int n_seq,
+k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq, int n_seq,
            int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
            u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
 {
@@ -325,9 +323,7 @@ k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         const int tile = (int)atomicAdd(scan_state, 1ULL);
-        int lo = 0, hi = n_seq;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_first[mid] <= tile) lo = mid; else hi = mid; }
-        S.seq = lo;
+        S.seq = tile_seq[tile];
         S.tile = tile;
     }
     __syncthreads();
@@ -565,6 +561,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const u32 *__restri
 #pragma unroll
     for (int t = 0; t < kScanItems; ++t) { const long long i = b0 + t; if (i < n) out[i] = e; e += v[t]; }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) out[n] = part[gridDim.x];
+}
+
+// tile -> sequence (one thread per sequence fills the entries of its tiles)
+__global__ void k_tile_map(const int *__restrict__ tile_first, int n_seq, int *__restrict__ tile_seq)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    for (int t = tile_first[s]; t < tile_first[s + 1]; ++t) tile_seq[t] = s;
 }
 
 // ---- per-sequence minimizer offsets -------------------------------------------------------------------------------------
@@ -1015,12 +1019,27 @@ k_seed_sort(uint4 *__restrict__ buf_a, uint4 *__restrict__ buf_b, const long lon
             if (cut == s) {                                            // the bucket starting here does not fit the window
                 if (f_be - s <= 64) sort64_out(dst, OUT, s, f_be, lane);
             } else {
+                // rank inside the own bucket (stable): elements before me count if their key is <= mine, elements behind me if it is
+                // smaller.  The members of a bucket sit in adjacent lanes, so offsets 1 .. (largest bucket of the window) - 1 cover
+                // every pair; below byte 4 the keys of a bucket differ in their low 32 bits only.
                 int rk = 0;
-                const int nw = cut - s;
-                for (int t = 0; t < nw; ++t) {
-                    const u64 kt = __shfl_sync(0xffffffffu, key, t);
-                    const int bt = __shfl_sync(0xffffffffu, bs, t);
-                    rk += (bt == bs && (kt < key || (kt == key && t < lane))) ? 1 : 0;
+                int mb = (i < cut) ? be - bs : 0;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+                const int lo_lane = bs - s, hi_lane = be - s;          // my bucket = lanes [lo_lane, hi_lane)
+                if (sh < 32) {
+                    const u32 k32 = e.x;
+                    for (int o = 1; o < mb; ++o) {
+                        const u32 kd = __shfl_up_sync(0xffffffffu, k32, o), ku = __shfl_down_sync(0xffffffffu, k32, o);
+                        rk += (lane - o >= lo_lane && kd <= k32) ? 1 : 0;
+                        rk += (lane + o < hi_lane && ku < k32) ? 1 : 0;
+                    }
+                } else {
+                    for (int o = 1; o < mb; ++o) {
+                        const u64 kd = __shfl_up_sync(0xffffffffu, key, o), ku = __shfl_down_sync(0xffffffffu, key, o);
+                        rk += (lane - o >= lo_lane && kd <= key) ? 1 : 0;
+                        rk += (lane + o < hi_lane && ku < key) ? 1 : 0;
+                    }
                 }
                 __syncwarp();
                 if (i < cut) OUT[bs + rk] = e;

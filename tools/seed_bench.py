@@ -87,6 +87,33 @@ def main():
         times.append(time.perf_counter() - t0)
     dev = float(np.median(times[2:]))
     out["fused_device"] = {"ms_per_step": 1e3 * dev, "reads_per_s": len(reads) / dev, "pairs_per_s": pairs / dev}
+    # two callers (host threads), each with its own seeder + chaining context and half of the reads: the latency-bound kernels of one
+    # batch (x-sort, chain extraction) overlap the issue-bound ones (sketch, score) of the other
+    import threading
+    half = len(reads) // 2
+    parts = []
+    for lo, hi in ((0, half), (half, len(reads))):
+        o = (off[lo:hi + 1] - off[lo]).copy()
+        b = buf[off[lo]:off[hi]].copy()
+        c2 = pkg.ChainContext(misc, device=0, max_anchors=cap, max_reads=len(reads) + 8, n_slots=1, flags=pkg.ChainContext.DEVICE_ONLY)
+        s2 = seed.Seeder(ix, max_bases=int(o[-1]) + 4096, max_reads=len(reads) + 8, max_anchors=cap)
+        parts.append((s2, c2, torch.from_numpy(b).pin_memory(), o))
+    def run(part, n):
+        s2, c2, pb, o = part
+        for _ in range(n):
+            s2.seed_chain(c2, prm, pb.data_ptr(), o, copy=False)
+    for part in parts:
+        run(part, 2)
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=run, args=(part, args.steps)) for part in parts]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    two = (time.perf_counter() - t0) / args.steps
+    out["fused_e2e_two_callers"] = {"ms_per_step": 1e3 * two, "reads_per_s": len(reads) / two, "pairs_per_s": pairs / two}
+    for s2, c2, _, _ in parts:
+        s2.close(); c2.close()
     # parity + CPU baseline: the reference's mm_map_seed + mg_lchain_dp on the host threads
     try:
         po_dir = os.path.join(ROOT, "oracle")
