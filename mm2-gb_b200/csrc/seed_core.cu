@@ -105,6 +105,8 @@ struct mm2gb_seeder {
     cudaEvent_t sort_fork = nullptr, sort_join[4] = {nullptr};
     int *d_f = nullptr, *d_p = nullptr;
     int sort_max_cap = 0;
+    bool sketch_persistent = true;     // k_sketch32p (MM2GB_SKETCH_PERSISTENT=0: one CTA per tile, k_sketch32)
+    int sketch_grid = 0;
     // pinned host
     long long *h_a_off = nullptr, *h_mp_off = nullptr;
     int *h_rep_len = nullptr;
@@ -163,7 +165,11 @@ int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
     // one pass (chained scan across tiles); the total is needed on the host only for the capacity check and the later grids
     CK(cudaMemsetAsync(sd->d_scan_state, 0, ((size_t)nt + 1) * sizeof(u64), st));
     k_tile_map<<<grid_for(n_seq, 256), 256, 0, st>>>(sd->d_tile_first, n_seq, (int *)sd->d_tile_cnt);
-    if (ix->k <= 15)
+    if (ix->k <= 15 && sd->sketch_persistent)
+        k_sketch32p<<<std::min(nt, sd->sketch_grid), kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k,
+                                                                    rid_is_seq, sd->d_scan_state, (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq,
+                                                                    sd->d_tile_base);
+    else if (ix->k <= 15)
         k_sketch32<<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
                                             (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     else
@@ -443,6 +449,11 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
         sd->sort_max_cap = ((dev_smem - (int)sizeof(SortShared) - 1024) / 16) * 16;
         if (const char *e = getenv("MM2GB_SEED_SORT_CAP")) sd->sort_max_cap = std::max(64, std::min(sd->sort_max_cap, atoi(e) / 16 * 16));
         TRYC(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_max_cap + (int)sizeof(SortShared)));
+        int n_sm = 0, per_sm = 0;
+        TRYC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, sd->device));
+        TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sketch32p, kTile, 0));
+        sd->sketch_grid = std::max(1, n_sm * std::max(1, per_sm));
+        if (const char *e = getenv("MM2GB_SKETCH_PERSISTENT")) sd->sketch_persistent = atoi(e) != 0;
     }
 #undef TRY
 #undef TRYC

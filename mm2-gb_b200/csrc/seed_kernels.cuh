@@ -490,6 +490,231 @@ k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__
     }
 }
 
+// ---- k_sketch32 as a persistent, software-pipelined kernel --------------------------------------------------------------------
+// ncu of k_sketch32 (profiles/r6h_sketch32_ncu.md): 35 % of the stall samples sit behind the look-back of the chained scan (the whole
+// CTA waits for one warp's global round trips), 16 % behind the ticket at the start of every tile.  Here a CTA loops over tickets;
+// the ticket of the next tile is fetched while the current one is computed, and the WRITE phase of a tile is deferred by one
+// iteration: the CTA publishes the tile's count, computes the next tile, and only then resolves the first tile's prefix -- by
+// then its predecessors have published theirs, so the look-back (done by the whole CTA at once: one status word per thread, up
+// to kTile tiles back in one round trip) does not wait.  Every CTA publishes the aggregate of a tile before it waits for anything,
+// so ticket order guarantees progress.  A tile in which some position emits more than two records (duplicate minimal k-mers)
+// is written at once instead of deferred (its rules are re-evaluated when writing).
+struct SketchTile32P {
+    u64 pk[(kHalo + kTile) / 32];
+    u32 nmask[(kHalo + kTile) / 32];
+    u32 ih[2][kMaxW + kTile];
+    unsigned char iz[2][kMaxW + kTile];
+    u64 pre_r[kMaxW + kTile], suf_r[kMaxW + kTile], pre_l[kMaxW + kTile], suf_l[kMaxW + kTile];
+    u32 warp_sum[2][kTile / 32];
+    u64 red[kTile / 32];
+    int first[kTile / 32];
+    u64 excl;
+    int ticket[2];
+};
+
+// prefix of tile `tile` (> 0) by the whole CTA; publishes it; returns it to every thread.  `tot` = the tile's own count.
+__device__ __forceinline__ u64 cta_lookback(volatile u64 *st, int tile, u64 tot, SketchTile32P &S)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    u64 excl = 0;
+    int look = tile - 1;
+    for (;;) {
+        const int idx = look - tid;
+        u64 sv = idx >= 0 ? st[idx] : MM2GB_FLAG_PREFIX;
+        while ((sv >> 62) == 0) sv = st[idx];
+        const u32 pref = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+        if (lane == 0) S.first[wid] = pref ? wid * 32 + __ffs(pref) - 1 : 1 << 30;
+        __syncthreads();
+        int first = 1 << 30;
+#pragma unroll
+        for (int q = 0; q < kTile / 32; ++q) first = min(first, S.first[q]);
+        u64 add = tid <= first ? (sv & MM2GB_VAL_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+        if (lane == 0) S.red[wid] = add;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kTile / 32; ++q) excl += S.red[q];
+        __syncthreads();
+        if (first != 1 << 30) break;
+        look -= kTile;
+    }
+    if (tid == 0) { __threadfence(); st[tile] = MM2GB_FLAG_PREFIX | (excl + tot); }
+    return excl;
+}
+
+#ifndef MM2GB_SKETCHP_MIN_CTAS
+#define MM2GB_SKETCHP_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kTile, MM2GB_SKETCHP_MIN_CTAS)
+k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq,
+            int n_seq, int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x,
+            u64 *__restrict__ mv_y, u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
+{
+    __shared__ SketchTile32P S;
+    constexpr u32 NONE = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    volatile u64 *st = scan_state + 1;
+    const u32 mask = (u32)((1ULL << (2 * k)) - 1);
+    const int nloc = w + kTile, T1 = w + k - 1;
+    if (tid == 0) S.ticket[0] = (int)atomicAdd(scan_state, 1ULL);
+    // the deferred tile
+    bool have_prev = false;
+    int p_tile = 0, p_seq = 0, p_t0 = 0, p_c = 0, p_e0 = 0, p_e1 = 0, p_buf = 0;
+    u32 p_off = 0, p_tot = 0;
+    auto put = [&](int buf, int sq, int t0, u64 at, int j) {
+        if ((long long)at >= cap) return;
+        mv_x[at] = (u64)S.ih[buf][j] << 8 | (u64)k;
+        mv_y[at] = (rid_is_seq ? (u64)sq << 32 : 0ULL) | (u64)(u32)(t0 - w + j) << 1 | (u64)S.iz[buf][j];
+        mv_seq[at] = (u32)sq;
+    };
+    for (int it = 0;; ++it) {
+        const int buf = it & 1;
+        __syncthreads();
+        const int tile = S.ticket[buf];
+        const bool valid = tile < n_tiles;
+        if (tid == 0 && valid) S.ticket[buf ^ 1] = (int)atomicAdd(scan_state, 1ULL);     // in flight while this tile is computed
+        int s = 0, t0 = 0, c = 0, e0 = 0, e1 = 0, i = 0, jj = 0, l = 0, mode = 0, mprev_j = -1, mp_j = -1, len = 0;
+        u32 cur = NONE, mprev_x = NONE, mx = NONE, v = 0, tot = 0;
+        bool dup1 = false, dup0 = false, in_range = false;
+        auto rules = [&](auto &&emit) {                // emit(local index)
+            if (!in_range) return;
+            if (l == T1 && mprev_x != NONE && dup1)                                // P1
+                for (int d = w - 1; d >= 1; --d)
+                    if (S.ih[buf][jj - d] == mprev_x && jj - d != mprev_j) emit(jj - d);
+            if (mode == 2) {                                                      // P2
+                if (l >= T1 + 1 && mprev_x != NONE) emit(mprev_j);
+            } else if (mode == 3) {                                               // P3
+                if (l >= T1) emit(mprev_j);
+                if (l >= T1 && mx != NONE && dup0)
+                    for (int d = w - 1; d >= 0; --d)
+                        if (S.ih[buf][jj - d] == mx && jj - d != mp_j) emit(jj - d);
+            }
+            if (i == len - 1) {                                                   // P4
+                const u32 fx = mode == 2 ? cur : mode == 3 ? mx : mprev_x;
+                const int fj = mode == 2 ? jj : mode == 3 ? mp_j : mprev_j;
+                if (fx != NONE) emit(fj);
+            }
+        };
+        if (valid) {
+            s = tile_seq[tile];
+            const long long base = seq_off[s];
+            len = (int)(seq_off[s + 1] - base);
+            t0 = (tile - tile_first[s]) * kTile;
+            for (int j = tid; j < kHalo + kTile; j += kTile) {
+                const int pos = t0 - kHalo + j;
+                const int cc = (pos >= 0 && pos < len) ? nt4_fast(__ldg(seqs + base + pos)) : 4;
+                const u32 b0 = __ballot_sync(0xffffffffu, cc & 1), b1 = __ballot_sync(0xffffffffu, cc & 2), bn = __ballot_sync(0xffffffffu, cc == 4);
+                if (lane == 0) {
+                    S.pk[j >> 5] = spread32(__brev(b1)) << 1 | spread32(__brev(b0));
+                    S.nmask[j >> 5] = bn;
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < nloc; j += kTile) {
+                const int sj = kHalo - w + j, pos = t0 - w + j;
+                u32 h = NONE;
+                unsigned char z = 0;
+                if (pos >= k - 1 && pos < len) {
+                    const int q = sj >> 5, r = sj & 31;
+                    const u64 nm = ((u64)S.nmask[q] << 32 | S.nmask[q - 1]) >> (r + 1);
+                    if ((((u32)nm) >> (32 - k)) == 0) {
+                        const int sft = 2 * (31 - r);
+                        const u64 f64 = sft ? (S.pk[q] >> sft) | (S.pk[q - 1] << (64 - sft)) : S.pk[q];
+                        const u32 f = (u32)f64 & mask;
+                        u32 y = __brev(f);
+                        y = ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
+                        const u32 rc = ((~y) >> (32 - 2 * k)) & mask;
+                        if (f != rc) {
+                            z = f < rc ? 0 : 1;
+                            h = hash32(z ? rc : f, mask);
+                        }
+                    }
+                }
+                S.ih[buf][j] = h;
+                S.iz[buf][j] = z;
+            }
+            __syncthreads();
+            for (int cidx = tid; cidx * w < nloc; cidx += kTile) {
+                const int c0 = cidx * w, c1 = min(c0 + w, nloc);
+                u64 mr = ~0ULL, ml = ~0ULL;
+                for (int j = c0; j < c1; ++j) {
+                    const u32 h = S.ih[buf][j];
+                    const u64 kr = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)(2047 - j)), kl = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)j);
+                    mr = min(mr, kr); ml = min(ml, kl);
+                    S.pre_r[j] = mr; S.pre_l[j] = ml;
+                }
+                mr = ~0ULL; ml = ~0ULL;
+                for (int j = c1 - 1; j >= c0; --j) {
+                    const u32 h = S.ih[buf][j];
+                    const u64 kr = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)(2047 - j)), kl = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)j);
+                    mr = min(mr, kr); ml = min(ml, kl);
+                    S.suf_r[j] = mr; S.suf_l[j] = ml;
+                }
+            }
+            __syncthreads();
+            i = t0 + tid; jj = w + tid;
+            in_range = i < len;
+            if (in_range) {
+                const int sj = kHalo + tid, q = sj >> 5, r = sj & 31;
+                const u32 w2 = S.nmask[q] & (r == 31 ? 0xffffffffu : ((2u << r) - 1u));
+                if (w2) l = r - (31 - __clz(w2));
+                else {
+                    const u32 w1 = S.nmask[q - 1];
+                    if (w1) l = r + 1 + __clz(w1);
+                    else { const u32 w0 = S.nmask[q - 2]; l = w0 ? r + 33 + __clz(w0) : 97; }
+                }
+                cur = S.ih[buf][jj];
+                const u64 m1r = min(S.suf_r[jj - w], S.pre_r[jj - 1]), m1l = min(S.suf_l[jj - w], S.pre_l[jj - 1]);
+                if (m1r != ~0ULL) { mprev_x = (u32)(m1r >> 11); mprev_j = 2047 - (int)(m1r & 2047u); dup1 = (int)(m1l & 2047u) != mprev_j; }
+                else mprev_j = jj - 1;
+                if (cur <= mprev_x) mode = 2;
+                else if (mprev_j == jj - w) {
+                    mode = 3;
+                    const u64 m0r = min(S.suf_r[jj - w + 1], S.pre_r[jj]), m0l = min(S.suf_l[jj - w + 1], S.pre_l[jj]);
+                    if (m0r != ~0ULL) { mx = (u32)(m0r >> 11); mp_j = 2047 - (int)(m0r & 2047u); dup0 = (int)(m0l & 2047u) != mp_j; }
+                }
+            }
+            rules([&](int j) { if (c == 0) e0 = j; else if (c == 1) e1 = j; ++c; });
+            v = (u32)c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+            if (lane == 31) S.warp_sum[buf][wid] = v;
+        }
+        const bool many = __syncthreads_or(valid && c > 2);
+        if (valid) {
+            if (wid == 0) {
+                u32 t = lane < kTile / 32 ? S.warp_sum[buf][lane] : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+                if (lane < kTile / 32) S.warp_sum[buf][lane] = t;
+                if (lane == 31) { __threadfence(); st[tile] = (tile == 0 ? MM2GB_FLAG_PREFIX : MM2GB_FLAG_AGG) | (u64)t; }
+            }
+            __syncthreads();
+            tot = S.warp_sum[buf][kTile / 32 - 1];
+            v = v - (u32)c + (wid ? S.warp_sum[buf][wid - 1] : 0u);      // exclusive offset of this thread inside the tile
+        }
+        // finish the deferred tile: its predecessors have had a whole tile's time to publish
+        if (have_prev) {
+            const u64 excl = p_tile ? cta_lookback(st, p_tile, p_tot, S) : 0ULL;
+            if (tid == 0) { tile_excl[p_tile] = excl; if (p_tile == n_tiles - 1) tile_excl[n_tiles] = excl + p_tot; }
+            if (p_c >= 1) put(p_buf, p_seq, p_t0, excl + p_off, p_e0);
+            if (p_c == 2) put(p_buf, p_seq, p_t0, excl + p_off + 1, p_e1);
+            have_prev = false;
+        }
+        if (!valid) break;
+        if (many) {                                   // written at once: the rules are re-evaluated with the state still in registers
+            const u64 excl = tile ? cta_lookback(st, tile, tot, S) : 0ULL;
+            if (tid == 0) { tile_excl[tile] = excl; if (tile == n_tiles - 1) tile_excl[n_tiles] = excl + tot; }
+            int n = 0;
+            rules([&](int j) { put(buf, s, t0, excl + v + n, j); ++n; });
+        } else {
+            have_prev = true;
+            p_tile = tile; p_seq = s; p_t0 = t0; p_c = c; p_e0 = e0; p_e1 = e1; p_buf = buf; p_off = v; p_tot = tot;
+        }
+    }
+}
+
 // ---- exclusive scan of a u32 array into u64 (three kernels; n up to 2^40) -------------------------------------------------
 constexpr int kScanThreads = 256, kScanItems = 16, kScanChunk = kScanThreads * kScanItems;
 
@@ -794,6 +1019,7 @@ __global__ void k_expand(Seeds m, const u64 *__restrict__ occ, const u64 *__rest
 struct SortShared {
     u32 cur[256];
     u32 end[256];
+    u32 nonempty[64];      // 256 bytes: digits of the non-empty buckets of the segment, ascending
 };
 
 __device__ __forceinline__ u64 key_x(const uint4 *p)
@@ -947,23 +1173,39 @@ k_seed_sort(uint4 *__restrict__ buf_a, uint4 *__restrict__ buf_b, const long lon
                 }
                 cntp += __popc(bal);
             }
-        } else if (lane == 0) {                                        // ksort.h:125-138 on the digits
-            for (int kk = 0; kk < 256; ++kk) {
-                const u32 ke = en[kk];
-                u32 kb = cur[kk];
-                while (kb != ke) {
-                    u32 d = D[kb];
-                    if (d == (u32)kk) { ++kb; continue; }
-                    u32 from = kb;
-                    do {
-                        const u32 pos = cur[d];
-                        cur[d] = pos + 1;
-                        dest[from] = pos;
-                        from = pos;
-                        d = D[pos];
-                    } while (d != (u32)kk);
-                    dest[from] = kb;
-                    ++kb;
+        } else {                                                       // ksort.h:125-138 on the digits
+            // the non-empty buckets in ascending order (the walk visits only those: segments of a few hundred anchors are common
+            // below repeat copies, and 256 empty-bucket tests per segment would cost more than their elements)
+            int mine = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) mine += c[t] ? 1 : 0;
+            int before = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, before, o); if (lane >= o) before += t; }
+            before -= mine;
+            unsigned char *nb = reinterpret_cast<unsigned char *>(SSw->nonempty);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) if (c[t]) nb[before++] = (unsigned char)(lane * 8 + t);
+            __syncwarp();
+            if (lane == 0) {
+                for (int q = 0; q < n_nonempty; ++q) {
+                    const u32 kk = nb[q];
+                    const u32 ke = en[kk];
+                    u32 kb = cur[kk];
+                    while (kb != ke) {
+                        u32 d = D[kb];
+                        if (d == kk) { ++kb; continue; }
+                        u32 from = kb;
+                        do {
+                            const u32 pos = cur[d];
+                            cur[d] = pos + 1;
+                            dest[from] = pos;
+                            from = pos;
+                            d = D[pos];
+                        } while (d != kk);
+                        dest[from] = kb;
+                        ++kb;
+                    }
                 }
             }
         }
