@@ -45,6 +45,11 @@ typedef struct {
  * it: worker_post sorts every list by position). */
 int mm2gb_index_build(mm2gb_index_t **idx, int device, const char *seqs, const int64_t *seq_off, int n_seq, int w, int k, int is_hpc,
                       int bucket_bits);
+/* The same index from lists a host index already holds (what enumerating mm_idx_t's buckets gives, index.c:213-266; works for indices
+ * loaded from .mmi files and for indices built without their sequences, MM_I_NO_SEQ): key i = minimizer (mm128_t.x >> 8) with its
+ * occurrences occ[off[i] .. off[i+1]) in the index's order (ascending positions).  Keys in any order. */
+int mm2gb_index_from_lists(mm2gb_index_t **idx, int device, int w, int k, int is_hpc, int64_t n_keys, const uint64_t *keys, const int64_t *off,
+                           const uint64_t *occ);
 void mm2gb_index_destroy(mm2gb_index_t *idx);
 /* mm_idx_cal_max_occ (index.c:186-207): what mm_mapopt_update makes of mid_occ_frac before clamping (options.c:72-77) */
 int32_t mm2gb_index_cal_max_occ(const mm2gb_index_t *idx, float frac);
@@ -87,6 +92,10 @@ typedef struct {
 } mm2gb_seed_chain_result_t;
 int mm2gb_seed_chain(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const char *seqs, const int64_t *seq_off,
                      int n_reads, mm2gb_seed_chain_result_t *res);
+
+/* mini_pos of the last batch (mm_collect_matches, seed.c:124: q_span << 32 | q_pos >> 1 of every kept seed; what mm_est_err reads later,
+ * map.c:608): read r's entries at mini_pos[mp_off[r] .. mp_off[r+1]).  Fetched on demand -- the fused step does not ship them. */
+int mm2gb_seed_last_mini_pos(mm2gb_seeder_t *sd, int n_reads, uint64_t *mini_pos, int64_t cap, int64_t *mp_off);
 
 /* The same with the sequences already resident in HBM (device pointer to the concatenated bases) and the results left on the
  * device: kernel-only timing of seeding + chaining.  Enqueues and synchronises once for the anchor counts (the chain-extraction

@@ -297,8 +297,12 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
         cudaStream_t ss = sd->sort_stream[used & 3];
         CK(cudaStreamWaitEvent(ss, sd->sort_fork, 0));
         const size_t smem = (size_t)warps * ((size_t)cap + sizeof(SortShared));
-        k_seed_sort<<<(cnt + warps - 1) / warps, warps * 32, smem, ss>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, sd->d_sort_list + start[(size_t)k], cnt, cap,
-                                                                          sd->d_dig, sd->d_dest, sd->d_lst, sd->d_stack);
+        if (k < nc)
+            k_seed_sort<true><<<(cnt + warps - 1) / warps, warps * 32, smem, ss>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, sd->d_sort_list + start[(size_t)k], cnt, cap,
+                                                                                    sd->d_dig, sd->d_dest, sd->d_lst, sd->d_stack);
+        else
+            k_seed_sort<false><<<cnt, 32, sizeof(SortShared), ss>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, sd->d_sort_list + start[(size_t)k], cnt, 0,
+                                                                     sd->d_dig, sd->d_dest, sd->d_lst, sd->d_stack);
         CK(cudaGetLastError());
         ++used;
     }
@@ -448,7 +452,7 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
         TRYC(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, sd->device));
         sd->sort_max_cap = ((dev_smem - (int)sizeof(SortShared) - 1024) / 16) * 16;
         if (const char *e = getenv("MM2GB_SEED_SORT_CAP")) sd->sort_max_cap = std::max(64, std::min(sd->sort_max_cap, atoi(e) / 16 * 16));
-        TRYC(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_max_cap + (int)sizeof(SortShared)));
+        TRYC(cudaFuncSetAttribute(k_seed_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_max_cap + (int)sizeof(SortShared)));
         int n_sm = 0, per_sm = 0;
         TRYC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, sd->device));
         TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sketch32p, kTile, 0));
@@ -539,7 +543,7 @@ extern "C" int mm2gb_seed_host(mm2gb_seeder_t *sd, const mm2gb_seed_params_t *pr
 
 static int seed_chain_common(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads)
 {
-    int rc = run_seed(sd, prm, seq_off, n_reads, false);
+    int rc = run_seed(sd, prm, seq_off, n_reads, true);
     if (rc) return rc;
     // the chaining kernels run on the context's own stream: order them behind the seeding stream
     cudaStream_t cs = (cudaStream_t)mm2gb_stream(ctx, 0);
@@ -600,6 +604,18 @@ extern "C" int mm2gb_seed_chain_device(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, con
     return rc;
 }
 
+extern "C" int mm2gb_seed_last_mini_pos(mm2gb_seeder_t *sd, int n_reads, uint64_t *mini_pos, int64_t cap, int64_t *mp_off)
+{
+    if (!sd || !mp_off || n_reads < 0 || n_reads > sd->max_reads) return fail(MM2GB_EARG, "bad argument");
+    if (!sd->timed) return fail(MM2GB_ESTATE, "no batch has been seeded yet");
+    CK(cudaSetDevice(sd->device));
+    if (mini_pos && sd->n_mp > cap) return fail(MM2GB_ECAP, "%lld mini_pos entries do not fit the output (%lld)", sd->n_mp, (long long)cap);
+    if (mini_pos && sd->n_mp) CK(cudaMemcpyAsync(mini_pos, sd->d_mini_pos, (size_t)sd->n_mp * sizeof(u64), cudaMemcpyDeviceToHost, sd->stream));
+    CK(cudaStreamSynchronize(sd->stream));
+    for (int r = 0; r <= n_reads; ++r) mp_off[r] = sd->h_mp_off[r];
+    return MM2GB_OK;
+}
+
 extern "C" int mm2gb_seed_profile(mm2gb_seeder_t *sd, float ms[MM2GB_SEED_NTIMERS], int64_t *n_minimizers, int64_t *n_seeds)
 {
     if (!sd || !ms) return fail(MM2GB_EARG, "bad argument");
@@ -623,6 +639,35 @@ extern "C" void mm2gb_index_destroy(mm2gb_index_t *ix)
     if (ix->d_occ) cudaFree(ix->d_occ);
     cudaGetLastError();
     delete ix;
+}
+
+// host lists (keys ascending, off, occ) -> open-addressing table + occurrence array in HBM; destroys ix on failure
+static int index_upload(mm2gb_index *ix)
+{
+    const size_t nk = ix->keys.size();
+    size_t slots = 1024;
+    while (slots < 2 * nk) slots <<= 1;
+    ix->mask = slots - 1;
+    std::vector<u64> hk(slots, kNone), hv(slots, 0);
+    for (size_t i = 0; i < nk; ++i) {
+        const u64 cnt = ix->off[i + 1] - ix->off[i];
+        if (cnt >= (1ULL << 28) || ix->off[i] >= (1ULL << 36)) { delete ix; return fail(MM2GB_ECAP, "index too large for the table encoding"); }
+        u64 key = ix->keys[i], h = key;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;   // mix64 of seed_kernels.cuh
+        h &= ix->mask;
+        while (hk[h] != kNone) h = (h + 1) & ix->mask;
+        hk[h] = key; hv[h] = ix->off[i] << 28 | cnt;
+    }
+    auto bad = [&](cudaError_t e, const char *what) { int rc = fail(MM2GB_ECUDA, "%s: %s", what, cudaGetErrorString(e)); mm2gb_index_destroy(ix); return rc; };
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&ix->d_key, slots * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index keys)");
+    if ((e = cudaMalloc((void **)&ix->d_val, slots * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index values)");
+    if ((e = cudaMalloc((void **)&ix->d_occ, std::max<size_t>(ix->occ.size(), 1) * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index occurrences)");
+    if ((e = cudaMemcpy(ix->d_key, hk.data(), slots * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(index keys)");
+    if ((e = cudaMemcpy(ix->d_val, hv.data(), slots * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(index values)");
+    if (!ix->occ.empty() && (e = cudaMemcpy(ix->d_occ, ix->occ.data(), ix->occ.size() * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bad(e, "cudaMemcpy(index occurrences)");
+    return MM2GB_OK;
 }
 
 extern "C" int mm2gb_index_build(mm2gb_index_t **out, int device, const char *seqs, const int64_t *seq_off, int n_seq, int w, int k, int is_hpc,
@@ -693,29 +738,46 @@ extern "C" int mm2gb_index_build(mm2gb_index_t **out, int device, const char *se
     }
     ix->off.push_back(mz.size());
     std::vector<std::pair<u64, u64>>().swap(mz);
-    const size_t nk = ix->keys.size();
-    size_t slots = 1024;
-    while (slots < 2 * nk) slots <<= 1;
-    ix->mask = slots - 1;
-    std::vector<u64> hk(slots, kNone), hv(slots, 0);
-    for (size_t i = 0; i < nk; ++i) {
-        const u64 cnt = ix->off[i + 1] - ix->off[i];
-        if (cnt >= (1ULL << 28) || ix->off[i] >= (1ULL << 36)) { delete ix; return fail(MM2GB_ECAP, "index too large for the table encoding"); }
-        u64 key = ix->keys[i], h = key;
-        h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;   // mix64 of seed_kernels.cuh
-        h &= ix->mask;
-        while (hk[h] != kNone) h = (h + 1) & ix->mask;
-        hk[h] = key; hv[h] = ix->off[i] << 28 | cnt;
+    {
+        const int rc = index_upload(ix);
+        if (rc) return rc;
     }
-    auto bad = [&](cudaError_t e, const char *what) { int rc = fail(MM2GB_ECUDA, "%s: %s", what, cudaGetErrorString(e)); mm2gb_index_destroy(ix); return rc; };
-    cudaError_t e;
-    if ((e = cudaMalloc((void **)&ix->d_key, slots * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index keys)");
-    if ((e = cudaMalloc((void **)&ix->d_val, slots * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index values)");
-    if ((e = cudaMalloc((void **)&ix->d_occ, std::max<size_t>(ix->occ.size(), 1) * sizeof(u64))) != cudaSuccess) return bad(e, "cudaMalloc(index occurrences)");
-    if ((e = cudaMemcpy(ix->d_key, hk.data(), slots * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(index keys)");
-    if ((e = cudaMemcpy(ix->d_val, hv.data(), slots * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(index values)");
-    if (!ix->occ.empty() && (e = cudaMemcpy(ix->d_occ, ix->occ.data(), ix->occ.size() * sizeof(u64), cudaMemcpyHostToDevice)) != cudaSuccess)
-        return bad(e, "cudaMemcpy(index occurrences)");
+    *out = ix;
+    return MM2GB_OK;
+}
+
+extern "C" int mm2gb_index_from_lists(mm2gb_index_t **out, int device, int w, int k, int is_hpc, int64_t n_keys, const uint64_t *keys,
+                                      const int64_t *off, const uint64_t *occ)
+{
+    if (!out || n_keys < 0 || (n_keys && (!keys || !off || !occ))) return fail(MM2GB_EARG, "bad argument");
+    *out = nullptr;
+    if (is_hpc) return fail(MM2GB_EARG, "homopolymer-compressed minimizers (MM_I_HPC) are not supported by the device seeding path");
+    if (k < 1 || k > 28 || !(k & 1)) return fail(MM2GB_EARG, "device seeding needs an odd k <= 28 (got %d)", k);
+    if (w < 1 || w > kMaxW) return fail(MM2GB_EARG, "device seeding needs 1 <= w <= %d (got %d)", kMaxW, w);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    mm2gb_index *ix = new mm2gb_index();
+    ix->device = device; ix->w = w; ix->k = k;
+    // keys in any order (a hash table is enumerated): sort the key order, keep every list as it is (index.c:253 sorted it)
+    std::vector<int64_t> order((size_t)n_keys);
+    for (int64_t i = 0; i < n_keys; ++i) order[(size_t)i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
+    ix->keys.resize((size_t)n_keys);
+    ix->off.resize((size_t)n_keys + 1);
+    ix->occ.resize(n_keys ? (size_t)off[n_keys] : 0);
+    size_t pos = 0;
+    for (int64_t i = 0; i < n_keys; ++i) {
+        const int64_t s = order[(size_t)i];
+        if (i && keys[s] == ix->keys[(size_t)i - 1]) { delete ix; return fail(MM2GB_EARG, "duplicate minimizer key in the lists"); }
+        ix->keys[(size_t)i] = keys[s];
+        ix->off[(size_t)i] = pos;
+        for (int64_t t = off[s]; t < off[s + 1]; ++t) ix->occ[pos++] = occ[t];
+    }
+    ix->off[(size_t)n_keys] = pos;
+    const int rc = index_upload(ix);
+    if (rc) return rc;
     *out = ix;
     return MM2GB_OK;
 }

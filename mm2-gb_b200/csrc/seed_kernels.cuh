@@ -1049,6 +1049,7 @@ __device__ __forceinline__ void sort64_out(const uint4 *src, uint4 *out, int beg
     __syncwarp();
 }
 
+template <bool DSMEM>     // digits of the read in shared memory (explicit LDS in the walk) or, for reads above the largest class, in HBM
 __global__ void __launch_bounds__(128)
 k_seed_sort(uint4 *__restrict__ buf_a, uint4 *__restrict__ buf_b, const long long *__restrict__ a_off, const int *__restrict__ list, int n_list,
             int cap, unsigned char *__restrict__ g_dig, u32 *__restrict__ g_dest, u32 *__restrict__ g_lst, int4 *__restrict__ g_stack)
@@ -1064,7 +1065,8 @@ k_seed_sort(uint4 *__restrict__ buf_a, uint4 *__restrict__ buf_b, const long lon
     uint4 *const XA = buf_a + o0, *const OUT = buf_b + o0;
     if (n <= 64) { sort64_out(XA, OUT, 0, n, lane); return; }        // ksort.h:148
     unsigned char *mine = sort_dyn + (size_t)wid * ((size_t)cap + sizeof(SortShared));
-    unsigned char *D = n <= cap ? mine : g_dig + o0;
+    unsigned char *D;
+    if (DSMEM) D = mine; else D = g_dig + o0;
     SortShared *SSw = reinterpret_cast<SortShared *>(mine + cap);
     u32 *dest = g_dest + o0, *lst = g_lst + o0;
     int4 *stack = g_stack + (o0 / 64 + 16LL * r);

@@ -62,6 +62,7 @@ def lib():
         L.mm2gb_seed_host.argtypes = [vp, C.POINTER(SeedParams), vp, vp, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int64, vp]
         L.mm2gb_seed_chain.argtypes = [vp, vp, C.POINTER(SeedParams), vp, vp, C.c_int, C.POINTER(SeedChainResult)]
         L.mm2gb_seed_chain_device.argtypes = [vp, vp, C.POINTER(SeedParams), vp, vp, C.c_int, C.POINTER(C.c_int64)]
+        L.mm2gb_seed_last_mini_pos.argtypes = [vp, C.c_int, vp, C.c_int64, vp]
         L.mm2gb_seed_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _bound = True
     return L
@@ -197,6 +198,13 @@ class Seeder:
         else:
             out["b"] = np.zeros((0, 2), dtype=np.uint64)
         return out
+
+    def last_mini_pos(self, n_reads: int, cap: int):
+        """mini_pos of the last batch (what mm_est_err needs): (entries, per-read offsets)."""
+        mp = np.zeros(max(cap, 1), dtype=np.uint64)
+        mp_off = np.zeros(n_reads + 1, dtype=np.int64)
+        _ck(lib().mm2gb_seed_last_mini_pos(self._h, n_reads, mp.ctypes.data, cap, mp_off.ctypes.data))
+        return mp[:int(mp_off[-1])], mp_off
 
     def seed_chain_device(self, ctx, prm: SeedParams, d_seqs: int, off: np.ndarray) -> int:
         n_a = C.c_int64(0)

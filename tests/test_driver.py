@@ -75,3 +75,38 @@ def test_max_chain_skip_spelling_is_ignored_by_gpu_path(synth, tmp_path):
     b = run(B200, base + [ref, reads], tmp_path)
     cpu = run(CPU, ["-t", "2", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)
     assert a == b == cpu
+
+
+# ---- row N2: seeding + chaining on the device inside the reference's driver ------------------------------------------------
+# oracle/_ref/minimap2_b200_seed = the reference's host sources + the three-line change of integration/map_gpu_seed.sed + the
+# reference-side binding integration/mm2gb_seed_glue.c.  With MM2GB_GPU_SEED=1 no read is seeded or chained on the host; the PAF
+# (alignment, mapq, dv: everything downstream of seeds, chains, rep_len and mini_pos) must equal the CPU driver's.
+SEED = os.path.join(REF, "minimap2_b200_seed")
+needs_seed_driver = pytest.mark.skipif(not os.path.exists(SEED), reason="oracle/_ref/minimap2_b200_seed not built")
+
+
+def run_env(binary, args, cwd, **env):
+    out = subprocess.run([binary] + args, capture_output=True, cwd=cwd, timeout=900, env=dict(os.environ, **env))
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    return out.stdout.decode(), out.stderr.decode()
+
+
+@needs_seed_driver
+@pytest.mark.parametrize("tag,t,q", [("MT", "MT-human.fa", "MT-orang.fa"), ("inv", "t-inv.fa", "q-inv.fa"), ("t2", "t2.fa", "q2.fa")])
+def test_gpu_seed_driver_fixtures_paf(tmp_path, golden_dir, tag, t, q):
+    gpu, _ = run_env(SEED, ["-t", "1", "--max-chain-skip=2147483647", os.path.join(FIX, t), os.path.join(FIX, q)], tmp_path, MM2GB_GPU_SEED="1")
+    assert gpu == open(os.path.join(golden_dir, tag + ".paf")).read()
+
+
+@needs_seed_driver
+@pytest.mark.parametrize("threads", [1, 4])
+def test_gpu_seed_driver_ont_like_reads_paf(synth, tmp_path, threads):
+    """300 ONT-like reads on a 3 Mb reference with repeats (batches of 64 reads per driver thread, map.c:23)"""
+    ref, reads = _synth_fasta(synth, tmp_path, 3_000_000, 300, 5000, 40000, repeats=150, seed=11)
+    gpu, err = run_env(SEED, ["-t", str(threads), "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path, MM2GB_GPU_SEED="1", MM2GB_VERBOSE="1")
+    off, _ = run_env(SEED, ["-t", "4", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)     # same binary, host path
+    cpu = run(CPU, ["-t", "4", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)
+    assert len(cpu.splitlines()) >= 300
+    assert off == cpu
+    assert gpu == cpu
+    assert "seed+chain thread" in err          # the device path really ran

@@ -183,6 +183,10 @@ def test_seed_chain_fused_vs_reference(pkg, sd, index, cases):
             sd.Seeder(index, max_bases=int(off[-1]) + 1024, max_reads=1024, max_anchors=cap) as s:
         res = s.seed_chain(ctx, sd.map_ont_seed_params(mid), buf, off)
         res2 = s.seed_chain(ctx, sd.map_ont_seed_params(mid), buf, off)       # buffers are reusable
+        mp, mp_off = s.last_mini_pos(len(reads), int(off[-1]))
+    for r in (0, 7, 150, len(reads) - 1, len(reads) - 5):
+        exp = ix.seed(reads[r])[2]
+        assert np.array_equal(mp[mp_off[r]:mp_off[r + 1]], exp), r
     assert np.array_equal(np.diff(res["a_off"]), n_a)
     assert np.array_equal(res["n_u"], n_u)
     for r in range(len(reads)):

@@ -14,17 +14,21 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ref-len", type=int, default=20_000_000)
 ap.add_argument("--reads", type=int, default=2000)
 ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--lo", type=int, default=10000)
+ap.add_argument("--hi", type=int, default=100000)
+ap.add_argument("--err", type=float, default=0.10)
+ap.add_argument("--repeats", type=int, default=-1)
 args = ap.parse_args()
 pkg = entry.load_package()
 from mm2gb_b200 import seed, synth  # noqa: E402
-ref = synth.simulate_reference(args.ref_len, seed=1, n_repeat_copies=args.ref_len // 16667, repeat_unit=3000)
-reads = synth.simulate_reads(ref, args.reads, 10000, 100000, seed=2, err=0.10)
+ref = synth.simulate_reference(args.ref_len, seed=1, n_repeat_copies=(args.ref_len // 16667 if args.repeats < 0 else args.repeats), repeat_unit=3000)
+reads = synth.simulate_reads(ref, args.reads, args.lo, args.hi, seed=2, err=args.err)
 off = np.zeros(len(reads) + 1, dtype=np.int64)
 off[1:] = np.cumsum([len(r) for r in reads])
 buf = synth._NT[np.concatenate(reads)]
 ix = seed.Index((synth._NT[ref], np.array([0, len(ref)], dtype=np.int64)), w=10, k=15)
 prm = seed.map_ont_seed_params(ix.mid_occ())
-sd = seed.Seeder(ix, max_bases=int(off[-1]) + 4096, max_reads=len(reads) + 8, max_anchors=int(off[-1]) // 4)
+sd = seed.Seeder(ix, max_bases=int(off[-1]) + 4096, max_reads=len(reads) + 8, max_anchors=int(off[-1]))
 for _ in range(args.iters):
     a, a_off, rep, _, _ = sd.seed(prm, buf, off, want_mini_pos=False)
 print("anchors", int(a_off[-1]), sd.profile())
