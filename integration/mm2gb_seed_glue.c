@@ -57,6 +57,15 @@ static void glue_die(const char *what)
     _exit(1);
 }
 
+/* CUDA bring-up (driver + context: 1-3 s on a fresh process) in the background from process start, while the driver reads / builds its
+ * index; the first batch then finds the device ready */
+static void *glue_early(void *arg) { size_t f = 0, t = 0; (void)arg; mm2gb_device_memory(0, &f, &t); return 0; }
+__attribute__((constructor)) static void glue_ctor(void)
+{
+    const char *e = getenv("MM2GB_GPU_SEED");
+    if (e && atoi(e)) { pthread_t th; if (pthread_create(&th, 0, glue_early, 0) == 0) pthread_detach(th); }
+}
+
 void mm2gb_glue_report(int n_threads);
 static void glue_atexit(void) { mm2gb_glue_report(GLUE_MAX_THREADS); }
 
@@ -68,6 +77,14 @@ int mm2gb_glue_enabled(void)
         if (g_enabled) atexit(glue_atexit);
     }
     return g_enabled;
+}
+
+/* reads per device batch and driver thread (the host path's N_ACCUM = 64, map.c:23, is sized for per-read host chaining) */
+int mm2gb_glue_batch_reads(void)
+{
+    const char *e = getenv("MM2GB_SEED_BATCH_READS");
+    int n = e ? atoi(e) : 512;
+    return n < 1 ? 1 : n > 65536 ? 65536 : n;
 }
 
 /* what mm_map_seed leaves in a read before any seeding happened (map.c:372-376): qlen_sum, nothing else */
@@ -145,7 +162,7 @@ void mm2gb_glue_seed_chain_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, cha
     prm.mid_occ = opt->mid_occ; prm.max_max_occ = opt->max_max_occ; prm.occ_dist = opt->occ_dist; prm.q_occ_frac = opt->q_occ_frac;
     prm.flag = opt->flag; prm.sdust_thres = opt->sdust_thres; prm.max_qlen = opt->max_qlen;
     t0 = realtime();
-    glue_size(ts, mi, opt, idx, bases, n_reads, ts->cap_anchors ? ts->cap_anchors : (bases / 2 > (1 << 20) ? bases / 2 : (1 << 20)));
+    glue_size(ts, mi, opt, idx, bases, n_reads, ts->cap_anchors ? ts->cap_anchors : (bases / 4 > (1 << 20) ? bases / 4 : (1 << 20)));
     for (;;) {
         rc = mm2gb_seed_chain(ts->sd, ts->ctx, &prm, ts->buf, ts->off, n_reads, &r);
         if (rc == MM2GB_ECAP) { glue_size(ts, mi, opt, idx, bases, n_reads, ts->cap_anchors * 2); continue; }   /* more anchors than planned for: grow, again */

@@ -59,6 +59,8 @@ struct mm2gb_index {
     int device = 0, w = 0, k = 0;
     // host copy: keys ascending, occurrences of keys[i] at occ[off[i] .. off[i+1]) ascending
     std::vector<uint64_t> keys, off, occ;
+    bool keys_sorted = true;               // false: built from an enumerated hash table (mm2gb_index_from_lists); lookups go through hk / hv
+    std::vector<uint64_t> hk, hv;          // host copy of the device table
     // device table
     u64 *d_key = nullptr, *d_val = nullptr, *d_occ = nullptr;
     uint64_t mask = 0;
@@ -648,7 +650,8 @@ static int index_upload(mm2gb_index *ix)
     size_t slots = 1024;
     while (slots < 2 * nk) slots <<= 1;
     ix->mask = slots - 1;
-    std::vector<u64> hk(slots, kNone), hv(slots, 0);
+    std::vector<uint64_t> &hk = ix->hk, &hv = ix->hv;
+    hk.assign(slots, kNone); hv.assign(slots, 0);
     for (size_t i = 0; i < nk; ++i) {
         const u64 cnt = ix->off[i + 1] - ix->off[i];
         if (cnt >= (1ULL << 28) || ix->off[i] >= (1ULL << 36)) { delete ix; return fail(MM2GB_ECAP, "index too large for the table encoding"); }
@@ -760,22 +763,13 @@ extern "C" int mm2gb_index_from_lists(mm2gb_index_t **out, int device, int w, in
     CK(cudaSetDevice(device));
     mm2gb_index *ix = new mm2gb_index();
     ix->device = device; ix->w = w; ix->k = k;
-    // keys in any order (a hash table is enumerated): sort the key order, keep every list as it is (index.c:253 sorted it)
-    std::vector<int64_t> order((size_t)n_keys);
-    for (int64_t i = 0; i < n_keys; ++i) order[(size_t)i] = i;
-    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
-    ix->keys.resize((size_t)n_keys);
+    // keys arrive in the enumeration order of the host hash tables and stay in it: the device side is a hash table anyway, and the
+    // host-side lookups (mm2gb_index_get: tests) go through the host copy of that table
+    ix->keys.assign(keys, keys + n_keys);
     ix->off.resize((size_t)n_keys + 1);
-    ix->occ.resize(n_keys ? (size_t)off[n_keys] : 0);
-    size_t pos = 0;
-    for (int64_t i = 0; i < n_keys; ++i) {
-        const int64_t s = order[(size_t)i];
-        if (i && keys[s] == ix->keys[(size_t)i - 1]) { delete ix; return fail(MM2GB_EARG, "duplicate minimizer key in the lists"); }
-        ix->keys[(size_t)i] = keys[s];
-        ix->off[(size_t)i] = pos;
-        for (int64_t t = off[s]; t < off[s + 1]; ++t) ix->occ[pos++] = occ[t];
-    }
-    ix->off[(size_t)n_keys] = pos;
+    for (int64_t i = 0; i <= n_keys; ++i) ix->off[(size_t)i] = n_keys ? (uint64_t)off[i] : 0;
+    ix->occ.assign(occ, occ + (n_keys ? off[n_keys] : 0));
+    ix->keys_sorted = false;
     const int rc = index_upload(ix);
     if (rc) return rc;
     *out = ix;
@@ -797,12 +791,14 @@ extern "C" int32_t mm2gb_index_cal_max_occ(const mm2gb_index_t *ix, float f)
 
 extern "C" int64_t mm2gb_index_get(const mm2gb_index_t *ix, uint64_t minier, uint64_t *out, int64_t cap)
 {
-    if (!ix) return 0;
-    auto it = std::lower_bound(ix->keys.begin(), ix->keys.end(), minier);
-    if (it == ix->keys.end() || *it != minier) return 0;
-    const size_t i = (size_t)(it - ix->keys.begin());
-    const int64_t n = (int64_t)(ix->off[i + 1] - ix->off[i]);
-    for (int64_t t = 0; t < n && t < cap && out; ++t) out[t] = ix->occ[ix->off[i] + (size_t)t];
+    if (!ix || ix->hk.empty()) return 0;
+    uint64_t h = minier;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;   // the probe k_lookup does
+    h &= ix->mask;
+    while (ix->hk[h] != minier) { if (ix->hk[h] == kNone) return 0; h = (h + 1) & ix->mask; }
+    const uint64_t o = ix->hv[h] >> 28;
+    const int64_t n = (int64_t)(ix->hv[h] & 0xfffffffu);
+    for (int64_t t = 0; t < n && t < cap && out; ++t) out[t] = ix->occ[o + (size_t)t];
     return n;
 }
 

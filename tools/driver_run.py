@@ -79,13 +79,34 @@ def main():
         if m:
             g = gpus.setdefault("gpu%s" % m.group(1), {"threads": 0, "batches": 0, "anchors": 0})
             g["threads"] += 1; g["batches"] += int(m.group(2)); g["anchors"] += int(m.group(3))
+    # row N2: the driver with seeding + chaining on the device (integration/: three-line change of map.c + the glue); no --gpu-chain,
+    # MM2GB_GPU_SEED=1 routes every batch of a worker thread through mm2gb_seed_chain
+    seed_res = None
+    if os.path.exists(os.path.join(REF, "minimap2_b200_seed")) and not os.environ.get("MM2GB_SKIP_SEED_DRIVER"):
+        S = int(os.environ.get("MM2GB_SEED_THREADS", "0")) or G
+        env_seed = dict(env, MM2GB_GPU_SEED="1")
+        t1 = time.time()
+        p = subprocess.run([os.path.join(REF, "minimap2_b200_seed"), "-t", str(S), "-x", "map-ont", "--max-chain-skip=2147483647", ref_fa, reads_fa],
+                           capture_output=True, cwd=d, env=env_seed)
+        seed_s = time.time() - t1
+        seed_err = p.stderr.decode(errors="replace")
+        if p.returncode != 0:
+            raise SystemExit("minimap2_b200_seed failed (%d):\n%s" % (p.returncode, seed_err[-3000:]))
+        c = p.stdout.splitlines()
+        seed_res = {"binary": "MM2GB_GPU_SEED=1 minimap2_b200_seed -t %d (batches of %s reads per thread)" % (S, os.environ.get("MM2GB_SEED_BATCH_READS", "512")),
+                    "wall_s": seed_s, "paf_md5": hashlib.md5(p.stdout).hexdigest(), "paf_lines": len(c),
+                    "paf_lines_differing_from_cpu": sum(1 for x, y in zip(a, c) if x != y) + abs(len(a) - len(c)), "paf_identical": p.stdout == cpu_paf,
+                    "timers": timers(seed_err), "fused_call_per_thread": [ln for ln in seed_err.splitlines() if ln.startswith("[mm2gb] seed+chain")][:4]}
     print(json.dumps({"workload": wl, "reads": w["n_reads"], "ref_len": w["ref_len"], "fasta_generation_s": gen_s,
                       "cpu": {"binary": "minimap2_ref_timed -t %d --max-chain-skip=2147483647" % T, "wall_s": cpu_s, "paf_md5": hashlib.md5(cpu_paf).hexdigest(),
                               "paf_lines": len(a), "timers": timers(cpu_err)},
                       "gpu": {"binary": "minimap2_b200_timed -t %d --gpu-chain" % G, "wall_s": gpu_s, "paf_md5": hashlib.md5(gpu_paf).hexdigest(),
                               "paf_lines": len(b), "timers": timers(gpu_err), "messages": warn, "work_per_gpu": gpus,
                               "boundary_per_thread": per_thread[:4] + (["... %d more" % (len(per_thread) - 4)] if len(per_thread) > 4 else [])},
+                      "gpu_seed": seed_res,
                       "paf_lines_differing": ndiff, "paf_identical": cpu_paf == gpu_paf}))
+    if seed_res is not None and not seed_res["paf_identical"]:
+        sys.exit(1)
     if cpu_paf != gpu_paf:
         open(os.path.join(d, "cpu.paf"), "wb").write(cpu_paf); open(os.path.join(d, "gpu.paf"), "wb").write(gpu_paf)
         sys.exit(1)
