@@ -32,8 +32,10 @@ int64_t mm_idx_export(const mm_idx_t *mi, uint64_t **keys_, int64_t **off_, uint
 
 static int g_enabled = -1;
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
-static mm2gb_index_t *g_idx;
-static const mm_idx_t *g_idx_of;
+#define GLUE_MAX_GPUS 16
+static mm2gb_index_t *g_idx[GLUE_MAX_GPUS];      /* one device index per GPU: worker thread tid drives GPU tid % n_gpus */
+static const mm_idx_t *g_idx_of[GLUE_MAX_GPUS];
+static int g_n_gpus;
 
 typedef struct {
     mm2gb_seeder_t *sd;
@@ -96,20 +98,32 @@ void mm2gb_glue_defer_seed(chain_read_t *rd)
     rd->a = 0; rd->n = 0; rd->u = 0; rd->n_u = 0; rd->mini_pos = 0; rd->n_mini_pos = 0; rd->rep_len = 0;
 }
 
-static mm2gb_index_t *glue_index(const mm_idx_t *mi)
+static int glue_n_gpus(void)
+{
+    if (!g_n_gpus) {
+        const char *e = getenv("MM2GB_N_GPUS");
+        int n = mm2gb_device_count();
+        if (n <= 0) { fprintf(stderr, "[ERROR] mm2gb seeding: MM2GB_GPU_SEED=1 needs a CUDA device (no CPU fallback)\n"); fflush(0); _exit(1); }
+        if (e && atoi(e) > 0 && atoi(e) < n) n = atoi(e);
+        g_n_gpus = n > GLUE_MAX_GPUS ? GLUE_MAX_GPUS : n;
+    }
+    return g_n_gpus;
+}
+
+static mm2gb_index_t *glue_index(const mm_idx_t *mi, int dev)
 {
     pthread_mutex_lock(&g_mu);
-    if (g_idx_of != mi) {          /* once per index part: the part's minimizer lists (integration/index_export.inc) -> device index */
+    if (g_idx_of[dev] != mi) {     /* once per index part and GPU: the part's minimizer lists (integration/index_export.inc) -> device index */
         uint64_t *keys = 0, *occ = 0;
         int64_t *off = 0, n_keys;
-        if (g_idx) mm2gb_index_destroy(g_idx), g_idx = 0;
+        if (g_idx[dev]) mm2gb_index_destroy(g_idx[dev]), g_idx[dev] = 0;
         n_keys = mm_idx_export(mi, &keys, &off, &occ);
-        if (mm2gb_index_from_lists(&g_idx, 0, mi->w, mi->k, mi->flag & MM_I_HPC, n_keys, keys, off, occ)) glue_die("building the device index");
+        if (mm2gb_index_from_lists(&g_idx[dev], dev, mi->w, mi->k, mi->flag & MM_I_HPC, n_keys, keys, off, occ)) glue_die("building the device index");
         free(keys); free(off); free(occ);
-        g_idx_of = mi;
+        g_idx_of[dev] = mi;
     }
     pthread_mutex_unlock(&g_mu);
-    return g_idx;
+    return g_idx[dev];
 }
 
 static void glue_size(tstate_t *ts, const mm_idx_t *mi, const mm_mapopt_t *opt, mm2gb_index_t *idx, int64_t bases, int n_reads, int64_t anchors)
@@ -141,8 +155,9 @@ void mm2gb_glue_seed_chain_batch(const mm_idx_t *mi, const mm_mapopt_t *opt, cha
     double t0;
     if (n_reads <= 0) return;
     if (tid < 0 || tid >= GLUE_MAX_THREADS) { fprintf(stderr, "[ERROR] mm2gb seeding: thread id %d out of range\n", tid); fflush(0); _exit(1); }
-    idx = glue_index(mi);
     ts = &g_ts[tid];
+    ts->device = tid % glue_n_gpus();
+    idx = glue_index(mi, ts->device);
     misc = build_misc(mi, opt, 0, 1);
     if (n_reads + 1 > ts->off_cap) {
         ts->off_cap = n_reads + 65;

@@ -110,3 +110,16 @@ def test_gpu_seed_driver_ont_like_reads_paf(synth, tmp_path, threads):
     assert off == cpu
     assert gpu == cpu
     assert "seed+chain thread" in err          # the device path really ran
+
+
+@needs_seed_driver
+def test_gpu_seed_driver_threads_spread_over_gpus(pkg, synth, tmp_path):
+    """worker thread t drives GPU t % n_gpus (one device index per GPU); skipped on a one-GPU box"""
+    if pkg.lib().mm2gb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ref, reads = _synth_fasta(synth, tmp_path, 3_000_000, 300, 5000, 40000, repeats=150, seed=11)
+    gpu, err = run_env(SEED, ["-t", "4", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path, MM2GB_GPU_SEED="1", MM2GB_VERBOSE="1",
+                       MM2GB_SEED_BATCH_READS="32")
+    cpu = run(CPU, ["-t", "4", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)
+    assert gpu == cpu
+    assert err.count("seed+chain thread") >= 2
