@@ -117,8 +117,11 @@ static mm2gb_index_t *glue_index(const mm_idx_t *mi, int dev)
         uint64_t *keys = 0, *occ = 0;
         int64_t *off = 0, n_keys;
         if (g_idx[dev]) mm2gb_index_destroy(g_idx[dev]), g_idx[dev] = 0;
+        double t0 = realtime(), t1;
         n_keys = mm_idx_export(mi, &keys, &off, &occ);
+        t1 = realtime();
         if (mm2gb_index_from_lists(&g_idx[dev], dev, mi->w, mi->k, mi->flag & MM_I_HPC, n_keys, keys, off, occ)) glue_die("building the device index");
+        if (getenv("MM2GB_VERBOSE")) fprintf(stderr, "[mm2gb] device index on GPU %d: %ld keys, export %.3f s, table + upload %.3f s\n", dev, (long)n_keys, t1 - t0, realtime() - t1);
         free(keys); free(off); free(occ);
         g_idx_of[dev] = mi;
     }
@@ -138,8 +141,10 @@ static void glue_size(tstate_t *ts, const mm_idx_t *mi, const mm_mapopt_t *opt, 
         Misc m = build_misc(mi, opt, 0, 1);
         mm2gb_misc_t misc;
         memcpy(&misc, &m, sizeof(misc));
+        double t0 = realtime();
         if (mm2gb_seeder_create(&ts->sd, idx, ts->cap_bases, ts->cap_reads, ts->cap_anchors)) glue_die("creating the seeder");
         if (mm2gb_ctx_create_ex(&ts->ctx, ts->device, (size_t)ts->cap_anchors, ts->cap_reads, 1, &misc, MM2GB_CTX_DEVICE_ONLY)) glue_die("creating the chaining context");
+        if (getenv("MM2GB_VERBOSE")) fprintf(stderr, "[mm2gb] seeder + context for %ld bases / %ld anchors: %.3f s\n", (long)ts->cap_bases, (long)ts->cap_anchors, realtime() - t0);
     }
 }
 
