@@ -1011,7 +1011,7 @@ __global__ void k_expand(Seeds m, const u64 *__restrict__ occ, const u64 *__rest
 //   2. destinations: the American-flag permutation (ksort.h:125-138) only ever reads slots that still hold their ORIGINAL
 //      element (a bucket's cursor never passes a slot twice), so it is replayed on the digits alone -- lane 0, two dependent
 //      shared-memory loads per moved element -- and emits dest[src]; a pass with exactly two non-empty buckets (the strand
-//      split at byte 7, always) has a closed form evaluated by all lanes (tools/seed_model.py: pass_dest_walk / pass_dest_two);
+//      split at byte 7, always) has a closed form evaluated by all lanes (oracle/seed_model.py: pass_dest_walk / pass_dest_two);
 //   3. scatter: other[dest[i]] = this[i], all lanes, 16-byte elements;
 //   4. buckets of more than 64 elements are pushed for the next byte; the others (stable insertion sort in the reference,
 //      ksort.h:105-115,143) are ranked on the full key inside 32-element windows and written to their final place.

@@ -1,9 +1,21 @@
-"""Pure-Python model of the data-parallel restatements used by the device seeding kernels (seed_kernels.cuh), checked against the
-reference through oracle/pyrefseed.py.  Development aid: validates the per-position sketch rules, the closed form of
-mm_seed_select and the replay of radix_sort_128x on the CPU before GPU time is spent.  Not part of the product or the tests."""
+"""seed_model.py -- CPU restatement (pure Python, small cases) of the reference's seeding stage in the DATA-PARALLEL form the device
+kernels use (mm2-gb_b200/csrc/seed_kernels.cuh), pinned against the reference itself through oracle/pyrefseed.py.
+
+TEST INFRASTRUCTURE ONLY (tests/test_seed_oracle.py); nothing in the product imports it.  What it restates, and from where:
+  sketch_model      mm_sketch, sketch.c:77-143, as per-position rules P1-P4 over the hashes of the last w + 1 positions and the
+                    run length of unambiguous bases (odd k, no HPC: the loop never takes its `continue`, sketch.c:104)
+  flag_sort_model   radix_sort_128x, ksort.h:98-151: MSD American-flag passes on (digit, index) words, insertion sort of buckets
+                    of <= 64 elements as a stable rank -- reproduces the tie order the unstable sort leaves among equal keys
+  pass_dest_walk /  one flag pass (ksort.h:125-138) replayed on the ORIGINAL digits alone, emitting a destination per moved
+  pass_dest_two     element, and its closed form for passes with exactly two non-empty buckets (what k_seed_sort runs)
+  seed_model        mm_map_seed, map.c:355-391: mm_seed_mz_flt (seed.c:5-29), mm_seed_collect_all (:31-53), mm_seed_select in
+                    closed form (:57-96: the heap keeps the k smallest (n, j) of a streak), rep_len (:117-121,128), anchors
+                    (map.c:303-325) and the sort
+Parity pinned: every function is checked against oracle/_ref/libref_seed.so (the reference's own sketch.c / seed.c / map.c / ksort.h
+compiled where they lie) in tests/test_seed_oracle.py and by `python oracle/seed_model.py`."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 NONE = (1 << 64) - 1
 M64 = (1 << 64) - 1

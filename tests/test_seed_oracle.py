@@ -1,6 +1,6 @@
 """CPU-side tests of the seeding row: the checker (oracle/_ref/libref_seed.so = the reference's own sketch.c /
-index.c / seed.c / map.c) against the committed golden vectors, the pure-Python model of the data-parallel restatements the
-kernels use (tools/seed_model.py) against the reference, and the exported C ABI.  No GPU needed."""
+index.c / seed.c / map.c) against the committed golden vectors, the pure-Python restatement of the seeding stage in the data-parallel form the
+kernels use (oracle/seed_model.py) against the reference, and the exported C ABI.  No GPU needed."""
 import os
 import re
 import sys
@@ -11,7 +11,6 @@ import pytest
 import seed_cases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pyrefseed as rs  # noqa: E402
 
