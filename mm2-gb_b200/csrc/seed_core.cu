@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -74,8 +76,18 @@ struct mm2gb_seeder {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[MM2GB_SEED_NTIMERS + 1] = {nullptr};
     cudaEvent_t ev_join = nullptr;
-    cudaStream_t stage_stream[4] = {nullptr};
-    cudaEvent_t stage_ev[4][2] = {{nullptr}}, stage_done[4] = {nullptr};
+    cudaStream_t stage_stream[8] = {nullptr};
+    cudaEvent_t stage_ev[8][2] = {{nullptr}}, stage_done[8] = {nullptr};
+    // staging workers (pageable sources): created on first use, parked on a condition variable between jobs
+    std::vector<std::thread> pool;
+    std::mutex pool_mu;
+    std::condition_variable pool_cv, pool_done_cv;
+    unsigned pool_gen = 0;
+    int pool_pending = 0, pool_nt = 0;
+    bool pool_stop = false;
+    const char *job_seqs = nullptr;
+    size_t job_b0 = 0, job_b1 = 0;
+    cudaError_t job_err[8] = {cudaSuccess};
     // sequences
     unsigned char *d_seq = nullptr;
     long long *d_seq_off = nullptr;
@@ -156,28 +168,49 @@ int plan_tiles(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
     return (int)t;
 }
 
-// sequences (already on the device) -> minimizers in d_mv_*; n_mv on the host (one synchronisation)
-int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
+// ---- sketch of a batch: prepare, one or several launches over consecutive tile ranges, finish -------------------------------
+constexpr int kMaxChunks = 12;      // launches per batch; d_scan_state = 16 ticket counters, then one status word per tile
+
+int sketch_prepare(mm2gb_seeder *sd, int n_seq)
 {
     cudaStream_t st = sd->stream;
-    const mm2gb_index *ix = sd->idx;
     const int nt = sd->n_tiles;
     sd->n_mv = 0;
     if (nt == 0) { CK(cudaMemsetAsync(sd->d_mv_off, 0, ((size_t)n_seq + 1) * sizeof(u64), st)); return MM2GB_OK; }
-    // one pass (chained scan across tiles); the total is needed on the host only for the capacity check and the later grids
-    CK(cudaMemsetAsync(sd->d_scan_state, 0, ((size_t)nt + 1) * sizeof(u64), st));
+    CK(cudaMemsetAsync(sd->d_scan_state, 0, ((size_t)nt + 17) * sizeof(u64), st));
     k_tile_map<<<grid_for(n_seq, 256), 256, 0, st>>>(sd->d_tile_first, n_seq, (int *)sd->d_tile_cnt);
-    if (ix->k <= 15 && sd->sketch_persistent)
-        k_sketch32p<<<std::min(nt, sd->sketch_grid), kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k,
-                                                                    rid_is_seq, sd->d_scan_state, (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq,
-                                                                    sd->d_tile_base);
-    else if (ix->k <= 15)
-        k_sketch32<<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
-                                            (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
-    else
-        k_sketch<u64><<<nt, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, (const int *)sd->d_tile_cnt, n_seq, nt, ix->w, ix->k, rid_is_seq, sd->d_scan_state,
-                                            (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     CK(cudaGetLastError());
+    return MM2GB_OK;
+}
+
+// tiles [t0, t1) of the batch on the main stream (launch number c of the batch)
+int sketch_launch(mm2gb_seeder *sd, int n_seq, int rid_is_seq, int c, int t0, int t1)
+{
+    if (t1 <= t0) return MM2GB_OK;
+    cudaStream_t st = sd->stream;
+    const mm2gb_index *ix = sd->idx;
+    const int nt = sd->n_tiles, n = t1 - t0;
+    u64 *ticket = sd->d_scan_state + c, *status = sd->d_scan_state + 16;
+    const int *tile_seq = (const int *)sd->d_tile_cnt;
+    if (ix->k <= 15 && sd->sketch_persistent)
+        k_sketch32p<<<std::min(n, sd->sketch_grid), kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket,
+                                                                   t0, t1, status, (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
+    else if (ix->k <= 15)
+        k_sketch32<<<n, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket, t0, t1, status,
+                                        (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
+    else
+        k_sketch<u64><<<n, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket, t0, t1, status,
+                                           (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
+    CK(cudaGetLastError());
+    return MM2GB_OK;
+}
+
+// per-sequence offsets, the minimizer count on the host (one synchronisation: capacity check, grids of the later kernels)
+int sketch_finish(mm2gb_seeder *sd, int n_seq)
+{
+    cudaStream_t st = sd->stream;
+    const int nt = sd->n_tiles;
+    if (nt == 0) return MM2GB_OK;
     CK(cudaMemcpyAsync(sd->h_tot, sd->d_tile_base + nt, sizeof(u64), cudaMemcpyDeviceToHost, st));
     k_seq_mv_off<<<grid_for(n_seq + 1, 256), 256, 0, st>>>(sd->d_tile_first, sd->d_tile_base, n_seq, sd->d_mv_off);
     CK(cudaGetLastError());
@@ -187,6 +220,16 @@ int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
         return fail(MM2GB_ECAP, "batch has %lld minimizers, the seeder holds %lld (max_bases too small for this sequence content)",
                     sd->n_mv, (long long)sd->max_mv);
     return MM2GB_OK;
+}
+
+// sequences already on the device -> minimizers in d_mv_*
+int run_sketch(mm2gb_seeder *sd, int n_seq, int rid_is_seq)
+{
+    int rc = sketch_prepare(sd, n_seq);
+    if (rc) return rc;
+    rc = sketch_launch(sd, n_seq, rid_is_seq, 0, 0, sd->n_tiles);
+    if (rc) return rc;
+    return sketch_finish(sd, n_seq);
 }
 
 int upload_offsets(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
@@ -205,48 +248,134 @@ int upload_offsets(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
 // Sequences -> device.  Pinned sources are DMA'd as they are.  Pageable ones are staged through pinned windows by kStageThreads
 // host threads, each with its own stream and two windows (the copy into one overlaps the DMA of the other): a single thread's
 // memcpy (~10 GB/s) would be five times slower than the link.
-constexpr int kStageThreads = 4;
-constexpr size_t kStageWindow = (size_t)4 << 20;
+constexpr int kStageThreads = 8;
+constexpr size_t kStageWindow = (size_t)2 << 20;
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+
+// one worker's share of the job: its slice of [job_b0, job_b1) through its two pinned windows and its own stream
+static void stage_slice(mm2gb_seeder *sd, int t, int nt)
+{
+    cudaError_t &err = sd->job_err[t];
+    err = cudaSetDevice(sd->device);
+    const size_t n_bases = sd->job_b1 - sd->job_b0;
+    const size_t lo = sd->job_b0 + n_bases * (size_t)t / (size_t)nt, hi = sd->job_b0 + n_bases * (size_t)(t + 1) / (size_t)nt;
+    int which = 0;
+    for (size_t done = lo; done < hi && err == cudaSuccess; which ^= 1) {
+        const size_t n = std::min(kStageWindow, hi - done);
+        unsigned char *stg = sd->h_seq + ((size_t)t * 2 + (size_t)which) * kStageWindow;
+        cudaEvent_t ev = sd->stage_ev[t][which];
+        if ((err = cudaEventSynchronize(ev)) != cudaSuccess) break;     // the window's previous DMA (a never-recorded event is complete)
+        memcpy(stg, sd->job_seqs + done, n);
+        if ((err = cudaMemcpyAsync(sd->d_seq + done, stg, n, cudaMemcpyHostToDevice, sd->stage_stream[t])) != cudaSuccess) break;
+        err = cudaEventRecord(ev, sd->stage_stream[t]);
+        done += n;
+    }
+    if (err == cudaSuccess) err = cudaEventRecord(sd->stage_done[t], sd->stage_stream[t]);
+}
+
+static void stage_worker(mm2gb_seeder *sd, int t)
+{
+    unsigned seen = 0;
+    for (;;) {
+        int nt;
+        {
+            std::unique_lock<std::mutex> lk(sd->pool_mu);
+            sd->pool_cv.wait(lk, [&] { return sd->pool_stop || sd->pool_gen != seen; });
+            if (sd->pool_stop) return;
+            seen = sd->pool_gen;
+            nt = sd->pool_nt;
+        }
+        if (t < nt) stage_slice(sd, t, nt);
+        {
+            std::lock_guard<std::mutex> lk(sd->pool_mu);
+            if (--sd->pool_pending == 0) sd->pool_done_cv.notify_one();
+        }
+    }
+}
+
+// bases [b0, b1) of a pageable source -> d_seq, staged by up to kStageThreads host threads (the caller + parked workers); afterwards
+// the main stream waits for their copies
+int stage_range(mm2gb_seeder *sd, const char *seqs, size_t b0, size_t b1)
+{
+    if (b1 <= b0) return MM2GB_OK;
+    const size_t n_bases = b1 - b0;
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int nt = n_bases < 2 * kStageWindow ? 1 : std::max(1, std::min(kStageThreads, hw / 2));
+    if (nt > 1 && sd->pool.empty())
+        for (int t = 1; t < kStageThreads; ++t) sd->pool.emplace_back(stage_worker, sd, t);
+    sd->job_seqs = seqs; sd->job_b0 = b0; sd->job_b1 = b1;
+    if (nt > 1) {
+        { std::lock_guard<std::mutex> lk(sd->pool_mu); sd->pool_nt = nt; sd->pool_pending = (int)sd->pool.size(); ++sd->pool_gen; }
+        sd->pool_cv.notify_all();
+    }
+    stage_slice(sd, 0, nt);
+    if (nt > 1) {
+        std::unique_lock<std::mutex> lk(sd->pool_mu);
+        sd->pool_done_cv.wait(lk, [&] { return sd->pool_pending == 0; });
+    }
+    for (int t = 0; t < nt; ++t) {
+        if (sd->job_err[t] != cudaSuccess) return fail(MM2GB_ECUDA, "staging the sequences: %s", cudaGetErrorString(sd->job_err[t]));
+        CK(cudaStreamWaitEvent(sd->stream, sd->stage_done[t], 0));
+    }
+    return MM2GB_OK;
+}
+
+// the staging streams start behind whatever still reads d_seq on the main stream
+int stage_begin(mm2gb_seeder *sd)
+{
+    CK(cudaEventRecord(sd->ev_join, sd->stream));
+    for (int t = 0; t < kStageThreads; ++t) CK(cudaStreamWaitEvent(sd->stage_stream[t], sd->ev_join, 0));
+    return MM2GB_OK;
+}
 
 int upload_seqs(mm2gb_seeder *sd, const char *seqs, int64_t n_bases)
 {
     if (n_bases <= 0) return MM2GB_OK;
-    cudaPointerAttributes at;
-    const bool pinned = cudaPointerGetAttributes(&at, seqs) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned) { CK(cudaMemcpyAsync(sd->d_seq, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, sd->stream)); return MM2GB_OK; }
-    const int nt = (size_t)n_bases < 4 * kStageWindow ? 1 : kStageThreads;
-    cudaError_t err[kStageThreads];
-    auto work = [&](int t) {
-        err[t] = cudaSetDevice(sd->device);
-        const size_t b0 = (size_t)n_bases * (size_t)t / (size_t)nt, b1 = (size_t)n_bases * (size_t)(t + 1) / (size_t)nt;
-        bool used[2] = {false, false};
-        int which = 0;
-        for (size_t done = b0; done < b1 && err[t] == cudaSuccess; which ^= 1) {
-            const size_t n = std::min(kStageWindow, b1 - done);
-            unsigned char *stg = sd->h_seq + ((size_t)t * 2 + (size_t)which) * kStageWindow;
-            cudaEvent_t ev = sd->stage_ev[t][which];
-            if (used[which] && (err[t] = cudaEventSynchronize(ev)) != cudaSuccess) break;
-            memcpy(stg, seqs + done, n);
-            if ((err[t] = cudaMemcpyAsync(sd->d_seq + done, stg, n, cudaMemcpyHostToDevice, sd->stage_stream[t])) != cudaSuccess) break;
-            err[t] = cudaEventRecord(ev, sd->stage_stream[t]);
-            used[which] = true;
-            done += n;
+    if (is_pinned_host(seqs)) { CK(cudaMemcpyAsync(sd->d_seq, seqs, (size_t)n_bases, cudaMemcpyHostToDevice, sd->stream)); return MM2GB_OK; }
+    int rc = stage_begin(sd);
+    if (rc) return rc;
+    return stage_range(sd, seqs, 0, (size_t)n_bases);
+}
+
+// Host sequences -> minimizers: the batch is cut into a few chunks of whole reads; chunk c is sketched while chunk c + 1 is still
+// being staged / crossing PCIe (the chained scan of the sketch continues across the launches).
+int upload_and_sketch(mm2gb_seeder *sd, const char *seqs, const int64_t *seq_off, int n_seq, int rid_is_seq)
+{
+    int rc = sketch_prepare(sd, n_seq);
+    if (rc) return rc;
+    const int64_t total = seq_off[n_seq];
+    if (total > 0) {
+        const bool pinned = is_pinned_host(seqs);
+        rc = stage_begin(sd);
+        if (rc) return rc;
+        const int64_t target = std::max<int64_t>((int64_t)8 << 20, (total + kMaxChunks - 1) / kMaxChunks);
+        int r0 = 0, c = 0;
+        while (r0 < n_seq) {
+            int r1 = r0;
+            while (r1 < n_seq && (r1 == r0 || seq_off[r1 + 1] - seq_off[r0] <= target || c == kMaxChunks - 1)) ++r1;
+            const size_t b0 = (size_t)seq_off[r0], b1 = (size_t)seq_off[r1];
+            if (pinned) {
+                if (b1 > b0) CK(cudaMemcpyAsync(sd->d_seq + b0, seqs + b0, b1 - b0, cudaMemcpyHostToDevice, sd->stage_stream[0]));
+                CK(cudaEventRecord(sd->stage_done[0], sd->stage_stream[0]));
+                CK(cudaStreamWaitEvent(sd->stream, sd->stage_done[0], 0));
+            } else {
+                rc = stage_range(sd, seqs, b0, b1);
+                if (rc) return rc;
+            }
+            rc = sketch_launch(sd, n_seq, rid_is_seq, c, sd->tile_first[(size_t)r0], sd->tile_first[(size_t)r1]);
+            if (rc) return rc;
+            r0 = r1;
+            ++c;
         }
-        if (err[t] == cudaSuccess) err[t] = cudaEventRecord(sd->stage_done[t], sd->stage_stream[t]);
-    };
-    // the staging streams start behind whatever still reads d_seq on the main stream
-    CK(cudaEventRecord(sd->ev_join, sd->stream));
-    for (int t = 0; t < nt; ++t) CK(cudaStreamWaitEvent(sd->stage_stream[t], sd->ev_join, 0));
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
-    for (int t = 0; t < nt; ++t) {
-        if (err[t] != cudaSuccess) return fail(MM2GB_ECUDA, "staging the sequences: %s", cudaGetErrorString(err[t]));
-        CK(cudaStreamWaitEvent(sd->stream, sd->stage_done[t], 0));
     }
-    return MM2GB_OK;
+    return sketch_finish(sd, n_seq);
 }
 
 int check_params(const mm2gb_seed_params_t *p)
@@ -316,14 +445,14 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
 }
 
 // the stages behind the sketch, up to the x-sorted anchors in sd->d_a and the per-read offsets on the host (sd->h_a_off)
-int run_seed(mm2gb_seeder *sd, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads, bool want_mini_pos)
+int run_seed(mm2gb_seeder *sd, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads, bool want_mini_pos, const char *host_seqs)
 {
     cudaStream_t st = sd->stream;
     const mm2gb_index *ix = sd->idx;
     const int T = 256;
     sd->n_m = sd->n_a = sd->n_mp = 0;
     CK(cudaEventRecord(sd->ev[0], st));
-    int rc = run_sketch(sd, n_reads, 0);
+    int rc = host_seqs ? upload_and_sketch(sd, host_seqs, seq_off, n_reads, 0) : run_sketch(sd, n_reads, 0);
     if (rc) return rc;
     const long long n_mv = sd->n_mv;
     CK(cudaEventRecord(sd->ev[1], st));
@@ -418,14 +547,14 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
     TRYC(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
     for (auto &e : sd->ev) TRYC(cudaEventCreate(&e));
     TRYC(cudaEventCreateWithFlags(&sd->ev_join, cudaEventDisableTiming));
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 8; ++t) {
         TRYC(cudaStreamCreateWithFlags(&sd->stage_stream[t], cudaStreamNonBlocking));
         TRYC(cudaEventCreateWithFlags(&sd->stage_done[t], cudaEventDisableTiming));
         for (auto &e : sd->stage_ev[t]) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     TRY(dalloc(sd->d_seq, (size_t)max_bases + 16));
     TRY(dalloc(sd->d_seq_off, R)); TRY(dalloc(sd->d_tile_first, R));
-    TRY(dalloc(sd->d_tile_cnt, NT)); TRY(dalloc(sd->d_tile_base, NT)); TRY(dalloc(sd->d_scan_state, NT + 1));
+    TRY(dalloc(sd->d_tile_cnt, NT)); TRY(dalloc(sd->d_tile_base, NT)); TRY(dalloc(sd->d_scan_state, NT + 18));
     TRY(dalloc(sd->d_part, std::max(M, NT) / kScanChunk + 4));
     TRY(dalloc(sd->d_mv_x, M)); TRY(dalloc(sd->d_mv_y, M)); TRY(dalloc(sd->d_mv_seq, M)); TRY(dalloc(sd->d_mv_off, R));
     TRY(dalloc(sd->d_keep, M)); TRY(dalloc(sd->d_tandem, M));
@@ -480,7 +609,13 @@ extern "C" void mm2gb_seeder_destroy(mm2gb_seeder_t *sd)
     void *pin[] = {sd->h_a_off, sd->h_mp_off, sd->h_rep_len, sd->h_tot, sd->h_b, sd->h_u, sd->h_seq, sd->h_sort_list};
     for (void *p : pin) if (p) cudaFreeHost(p);
     for (auto &e : sd->ev) if (e) cudaEventDestroy(e);
-    for (int t = 0; t < 4; ++t) {
+    if (!sd->pool.empty()) {
+        { std::lock_guard<std::mutex> lk(sd->pool_mu); sd->pool_stop = true; }
+        sd->pool_cv.notify_all();
+        for (auto &t : sd->pool) t.join();
+        sd->pool.clear();
+    }
+    for (int t = 0; t < 8; ++t) {
         if (sd->stage_stream[t]) { cudaStreamSynchronize(sd->stage_stream[t]); cudaStreamDestroy(sd->stage_stream[t]); }
         if (sd->stage_done[t]) cudaEventDestroy(sd->stage_done[t]);
         for (auto &e : sd->stage_ev[t]) if (e) cudaEventDestroy(e);
@@ -527,9 +662,7 @@ extern "C" int mm2gb_seed_host(mm2gb_seeder_t *sd, const mm2gb_seed_params_t *pr
     CK(cudaSetDevice(sd->device));
     rc = upload_offsets(sd, seq_off, n_reads);
     if (rc) return rc;
-    rc = upload_seqs(sd, seqs, seq_off[n_reads]);
-    if (rc) return rc;
-    rc = run_seed(sd, prm, seq_off, n_reads, mini_pos != nullptr);
+    rc = run_seed(sd, prm, seq_off, n_reads, mini_pos != nullptr, seqs);
     if (rc) return rc;
     if (a && sd->n_a > a_cap) return fail(MM2GB_ECAP, "%lld anchors do not fit the output (%lld)", sd->n_a, (long long)a_cap);
     if (mini_pos && sd->n_mp > mp_cap) return fail(MM2GB_ECAP, "%lld mini_pos entries do not fit the output (%lld)", sd->n_mp, (long long)mp_cap);
@@ -543,9 +676,9 @@ extern "C" int mm2gb_seed_host(mm2gb_seeder_t *sd, const mm2gb_seed_params_t *pr
     return MM2GB_OK;
 }
 
-static int seed_chain_common(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads)
+static int seed_chain_common(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2gb_seed_params_t *prm, const int64_t *seq_off, int n_reads, const char *host_seqs)
 {
-    int rc = run_seed(sd, prm, seq_off, n_reads, true);
+    int rc = run_seed(sd, prm, seq_off, n_reads, true, host_seqs);
     if (rc) return rc;
     // the chaining kernels run on the context's own stream: order them behind the seeding stream
     cudaStream_t cs = (cudaStream_t)mm2gb_stream(ctx, 0);
@@ -565,13 +698,11 @@ extern "C" int mm2gb_seed_chain(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2g
     CK(cudaSetDevice(sd->device));
     rc = upload_offsets(sd, seq_off, n_reads);
     if (rc) return rc;
-    rc = upload_seqs(sd, seqs, seq_off[n_reads]);
-    if (rc) return rc;
     if (!sd->h_b) {   // result landing buffers (pinned, mapped): allocated on first use, the parity / device-resident entries never need them
         CK(cudaHostAlloc((void **)&sd->h_b, (size_t)sd->max_anchors * sizeof(mm2gb_anchor_t), cudaHostAllocMapped));
         CK(cudaHostAlloc((void **)&sd->h_u, (size_t)sd->max_anchors * sizeof(uint64_t), cudaHostAllocMapped));
     }
-    rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads);
+    rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads, seqs);
     if (rc) return rc;
     rc = mm2gb_chain_device_fetch(ctx, 0, sd->d_a, sd->d_a_off, n_reads, sd->n_a, sd->h_b, sd->h_u);
     if (rc) return rc;
@@ -600,7 +731,7 @@ extern "C" int mm2gb_seed_chain_device(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, con
     if (rc) return rc;
     unsigned char *own = sd->d_seq;
     sd->d_seq = (unsigned char *)const_cast<void *>(d_seqs);
-    rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads);
+    rc = seed_chain_common(sd, ctx, prm, seq_off, n_reads, nullptr);
     sd->d_seq = own;
     if (n_anchors) *n_anchors = sd->n_a;
     return rc;

@@ -112,18 +112,20 @@ __device__ __forceinline__ u32 hash32(u32 key, u32 mask)    // hash64 (sketch.c:
 #define MM2GB_FLAG_PREFIX (2ULL << 62)
 #define MM2GB_VAL_MASK ((1ULL << 62) - 1ULL)
 
-// scan_state[0] = ticket counter, scan_state[1 + tile] = status; all zero before the launch
+// A launch covers the tiles [tile_begin, tile_end) (a batch is sketched in a few launches so that the upload of its later reads
+// overlaps the sketch of its earlier ones; launches of a batch run in stream order, so every predecessor tile of an earlier launch
+// is complete); *ticket = that launch's ticket counter, scan_state[tile] = status word; all zero before the first launch
 template <typename HT>
 __global__ void __launch_bounds__(kTile)
 k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq, int n_seq,
-         int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
+         int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ ticket, int tile_begin, int tile_end, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
          u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
 {
     __shared__ SketchTile<HT> S;
     constexpr HT NONE = (HT)~(HT)0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
-        const int tile = (int)atomicAdd(scan_state, 1ULL);
+        const int tile = tile_begin + (int)atomicAdd(ticket, 1ULL);
         S.seq = tile_seq[tile];
         S.tile = tile;
     }
@@ -251,7 +253,7 @@ k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ s
                 if (lane < kTile / 32) S.warp_sum[lane] = t;
                 // chained scan across tiles: publish the aggregate, look back for the prefix, publish the inclusive prefix
                 const u64 tot = __shfl_sync(0xffffffffu, t, 31);
-                volatile u64 *st = scan_state + 1;
+                volatile u64 *st = scan_state;
                 if (lane == 0) {
                     __threadfence();
                     st[tile] = (tile == 0 ? MM2GB_FLAG_PREFIX : MM2GB_FLAG_AGG) | tot;
@@ -315,14 +317,14 @@ __device__ __forceinline__ int nt4_fast(u32 ch)
 
 __global__ void __launch_bounds__(kTile)
 k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq, int n_seq,
-           int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
+           int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ ticket, int tile_begin, int tile_end, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
            u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
 {
     __shared__ SketchTile32 S;
     constexpr u32 NONE = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
-        const int tile = (int)atomicAdd(scan_state, 1ULL);
+        const int tile = tile_begin + (int)atomicAdd(ticket, 1ULL);
         S.seq = tile_seq[tile];
         S.tile = tile;
     }
@@ -446,7 +448,7 @@ k_sketch32(const unsigned char *__restrict__ seqs, const long long *__restrict__
         for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
         if (lane < kTile / 32) S.warp_sum[lane] = t;
         const u64 tot = __shfl_sync(0xffffffffu, t, 31);
-        volatile u64 *st = scan_state + 1;
+        volatile u64 *st = scan_state;
         if (lane == 0) { __threadfence(); st[tile] = (tile == 0 ? MM2GB_FLAG_PREFIX : MM2GB_FLAG_AGG) | tot; }
         u64 excl = 0;
         if (tile > 0) {
@@ -548,16 +550,16 @@ __device__ __forceinline__ u64 cta_lookback(volatile u64 *st, int tile, u64 tot,
 #endif
 __global__ void __launch_bounds__(kTile, MM2GB_SKETCHP_MIN_CTAS)
 k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq,
-            int n_seq, int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x,
+            int n_seq, int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ ticket, int tile_begin, int tile_end, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x,
             u64 *__restrict__ mv_y, u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
 {
     __shared__ SketchTile32P S;
     constexpr u32 NONE = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    volatile u64 *st = scan_state + 1;
+    volatile u64 *st = scan_state;
     const u32 mask = (u32)((1ULL << (2 * k)) - 1);
     const int nloc = w + kTile, T1 = w + k - 1;
-    if (tid == 0) S.ticket[0] = (int)atomicAdd(scan_state, 1ULL);
+    if (tid == 0) S.ticket[0] = tile_begin + (int)atomicAdd(ticket, 1ULL);
     // the deferred tile
     bool have_prev = false;
     int p_tile = 0, p_seq = 0, p_t0 = 0, p_c = 0, p_e0 = 0, p_e1 = 0, p_buf = 0;
@@ -572,8 +574,8 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
         const int buf = it & 1;
         __syncthreads();
         const int tile = S.ticket[buf];
-        const bool valid = tile < n_tiles;
-        if (tid == 0 && valid) S.ticket[buf ^ 1] = (int)atomicAdd(scan_state, 1ULL);     // in flight while this tile is computed
+        const bool valid = tile < tile_end;
+        if (tid == 0 && valid) S.ticket[buf ^ 1] = tile_begin + (int)atomicAdd(ticket, 1ULL);     // in flight while this tile is computed
         int s = 0, t0 = 0, c = 0, e0 = 0, e1 = 0, i = 0, jj = 0, l = 0, mode = 0, mprev_j = -1, mp_j = -1, len = 0;
         u32 cur = NONE, mprev_x = NONE, mx = NONE, v = 0, tot = 0;
         bool dup1 = false, dup0 = false, in_range = false;
