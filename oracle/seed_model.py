@@ -421,3 +421,70 @@ def check_dest_forms():
 
 if __name__ == "__main__":
     check_dest_forms()
+
+
+# ---- third formulation: the walk with run jumps (tried in k_seed_sort, measured 2.5x SLOWER than the one-lane walk: kept as a model) ----
+# An arrival into bucket d lands at cur[d] and pushes the run of d-residents behind it one slot up, until the next slot of d's
+# region that holds a foreign element (which is evicted and carries on).  The run is a RANGE (dest[x] = x + 1 for all of it, found
+# by scanning the digits 32 at a time on the device); the serial work is one step per foreign element only.  In the home phase of a
+# bucket its in-place residents are passed over without moving.
+
+def pass_dest_runs(dig):
+    n = len(dig)
+    cnt = [0] * 256
+    for d in dig:
+        cnt[d] += 1
+    cur, en, run = [0] * 256, [0] * 256, 0
+    for d in range(256):
+        cur[d] = run
+        run += cnt[d]
+        en[d] = run
+    dest = list(range(n))
+    for kk in range(256):
+        kb, ke = cur[kk], en[kk]
+        while kb < ke:
+            while kb < ke and dig[kb] == kk:      # home scan: residents in place
+                kb += 1
+            if kb >= ke:
+                break
+            frm, d = kb, dig[kb]
+            while True:
+                pos = cur[d]
+                nm = pos
+                while dig[nm] == d:               # the run of residents behind the landing slot moves up by one
+                    dest[nm] = nm + 1
+                    nm += 1
+                    assert nm < en[d]
+                dest[frm] = pos
+                cur[d] = nm + 1
+                frm, d = nm, dig[nm]
+                if d == kk:
+                    break
+            dest[frm] = kb
+            kb += 1
+        cur[kk] = kb
+    return dest
+
+
+def check_runs_form():
+    rng = np.random.default_rng(9)
+    bad = 0
+    for n in (2, 5, 40, 300, 2000):
+        for nb in (2, 3, 6, 40, 256):
+            for skew in (0, 1):
+                for _ in range(10):
+                    pool = rng.choice(256, nb, replace=False)
+                    if skew:          # one dominant bucket: long runs of residents
+                        p = np.full(nb, 0.1 / max(nb - 1, 1)); p[0] = 0.9 if nb > 1 else 1.0; p /= p.sum()
+                        dig = [int(v) for v in rng.choice(pool, n, p=p)]
+                    else:
+                        dig = [int(v) for v in rng.choice(pool, n)]
+                    a, _ = pass_dest_walk(dig)
+                    b = pass_dest_runs(dig)
+                    if a != b:
+                        bad += 1
+    print("run-jump form mismatches:", bad)
+
+
+if __name__ == "__main__":
+    check_runs_form()

@@ -76,6 +76,25 @@ def test_sort_replay_model_vs_reference():
             assert np.array_equal(ref[:, 1], np.array(seed_model.flag_sort_model([int(v) for v in x]), dtype=np.uint64)), (n, spread)
 
 
+def test_pass_forms_agree():
+    """one flag pass: the step-by-step replay on (digit, index) words, the replay on the original digits alone (destinations), its closed
+    form for two buckets, and the walk with run jumps all give the same permutation"""
+    import seed_model
+    rng = np.random.default_rng(12)
+    for n in (2, 7, 100, 1500):
+        for nb in (2, 3, 9, 256):
+            for skew in (False, True):
+                pool = rng.choice(256, nb, replace=False)
+                p = None
+                if skew and nb > 1:
+                    p = np.full(nb, 0.1 / (nb - 1)); p[0] = 0.9
+                dig = [int(v) for v in rng.choice(pool, n, p=p)]
+                a, _ = seed_model.pass_dest_walk(dig)
+                assert seed_model.pass_dest_runs(dig) == a, (n, nb, skew)
+                if len(set(dig)) == 2:
+                    assert seed_model.pass_dest_two(dig) == a, (n, nb, skew)
+
+
 @needs_ref
 def test_seed_model_vs_reference(cases):
     """Closed forms of mm_seed_mz_flt / mm_seed_select / rep_len + the sort replay = mm_map_seed."""
