@@ -238,9 +238,7 @@ def seed_chain_leg(pkg, torch, dist, w, rank, local_rank, world, host_threads, n
     for _ in range(2):
         res = sd.seed_chain(ctx, prm, buf, off, copy=False)
     pairs = int(res.stats.n_pairs)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
+    torch.cuda.synchronize()     # (no barrier here: a rank whose leg fails must not leave the others waiting; the job figure takes the max time)
     t0 = time.perf_counter()
     for _ in range(steps):
         res = sd.seed_chain(ctx, prm, buf, off, copy=False)     # pageable host sequences in, chains + compacted anchors in host memory out
@@ -538,14 +536,19 @@ def main():
 
     # ---- row N2: device seeding + chaining fused (sequences in, chains out) ------------------------------------------------
     seed_leg = None
-    if args.workload in ("ont", "mini") and not os.environ.get("MM2GB_BENCH_NO_SEED"):
-        seed_leg, (s_reads, s_pairs), s_sec = seed_chain_leg(pkg, torch, dist, w, rank, local_rank, world, host_threads,
-                                                            n_reads=min(3000, w["n_reads"]))
     from mm2gb_b200 import sharding
-    if seed_leg is not None:
-        (j_reads, j_pairs), (j_sec,) = sharding.reduce_job(dist, [s_reads, s_pairs], [s_sec], device="cuda")
-        seed_leg["job"] = {"n_gpus": world, "reads_per_s": j_reads / j_sec, "pairs_per_s": j_pairs / j_sec,
-                           "note": "every rank seeds + chains its own reads; sum of work / max over ranks of the end-to-end time"}
+    if args.workload in ("ont", "mini") and not os.environ.get("MM2GB_BENCH_NO_SEED"):
+        try:
+            seed_leg, (s_reads, s_pairs), s_sec = seed_chain_leg(pkg, torch, dist, w, rank, local_rank, world, host_threads,
+                                                                n_reads=min(3000, w["n_reads"]))
+        except Exception as e:  # noqa: BLE001 -- the leg must not take the headline line down with it; the failure is reported in the line
+            sys.stderr.write("bench.py: seed_chain leg failed: %r\n" % (e,))
+            seed_leg, s_reads, s_pairs, s_sec = {"error": repr(e)}, 0, 0, 0.0
+        # every rank takes part in the reduction, whether its leg worked or not
+        (j_reads, j_pairs, j_ok), (j_sec,) = sharding.reduce_job(dist, [s_reads, s_pairs, 0 if "error" in seed_leg else 1], [s_sec], device="cuda")
+        if "error" not in seed_leg and int(j_ok) == world and j_sec > 0:
+            seed_leg["job"] = {"n_gpus": world, "reads_per_s": j_reads / j_sec, "pairs_per_s": j_pairs / j_sec,
+                               "note": "every rank seeds + chains its own reads; sum of work / max over ranks of the end-to-end time"}
 
     # ---- reduce over ranks: max time, sum of work -------------------------------------------------------------------
     (tot_pairs, tot_anchors, tot_reads), (ms_max, e2e_max) = sharding.reduce_job(dist, [pairs, n, n_reads], [ms, e2e_s], device="cuda")
