@@ -603,14 +603,50 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
             const long long base = seq_off[s];
             len = (int)(seq_off[s + 1] - base);
             t0 = (tile - tile_first[s]) * kTile;
-            for (int j = tid; j < kHalo + kTile; j += kTile) {
-                const int pos = t0 - kHalo + j;
-                const int cc = (pos >= 0 && pos < len) ? nt4_fast(__ldg(seqs + base + pos)) : 4;
-                const u32 b0 = __ballot_sync(0xffffffffu, cc & 1), b1 = __ballot_sync(0xffffffffu, cc & 2), bn = __ballot_sync(0xffffffffu, cc == 4);
-                if (lane == 0) {
-                    S.pk[j >> 5] = spread32(__brev(b1)) << 1 | spread32(__brev(b0));
-                    S.nmask[j >> 5] = bn;
+            // staging: thread t < (kHalo + kTile) / 4 packs four consecutive bases (SWAR: all four are letters of ACGTU in the common
+            // case), eight neighbouring lanes assemble a 32-base word
+            if (wid < (kHalo + kTile + 127) / 128) {
+                const int j4 = 4 * tid;
+                u32 pk8 = 0, n4 = 0;
+                if (j4 < kHalo + kTile) {
+                    const int pos0 = t0 - kHalo + j4;
+                    u32 wv = 0x4E4E4E4Eu;                                   // "NNNN"
+                    if (pos0 >= 0 && pos0 + 3 < len) {
+                        const unsigned char *p = seqs + base + pos0;
+                        wv = (u32)__ldg(p) | (u32)__ldg(p + 1) << 8 | (u32)__ldg(p + 2) << 16 | (u32)__ldg(p + 3) << 24;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (pos0 + q >= 0 && pos0 + q < len) wv = (wv & ~(0xffu << (8 * q))) | (u32)__ldg(seqs + base + pos0 + q) << (8 * q);
+                    }
+                    const u32 up = wv & 0xDFDFDFDFu;
+                    u32 ok = 0;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const u32 cc = (q == 0 ? 0x41u : q == 1 ? 0x43u : q == 2 ? 0x47u : q == 3 ? 0x54u : 0x55u) * 0x01010101u;
+                        const u32 v = up ^ cc;
+                        ok |= ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;   // bit 7 of every byte that is zero
+                    }
+                    u32 code;
+                    if (ok == 0x80808080u) {
+                        const u32 x = (wv >> 1) & 0x03030303u;
+                        code = x ^ ((x >> 1) & 0x01010101u);
+                    } else {                                                // an ambiguous base (or the table's 0..3 bytes): one by one
+                        code = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int c1 = nt4_fast((wv >> (8 * q)) & 0xffu);
+                            code |= (u32)(c1 & 3) << (8 * q);
+                            n4 |= (c1 == 4 ? 1u : 0u) << q;
+                        }
+                    }
+                    pk8 = (code * 0x40100401u) >> 24;                       // b0 << 6 | b1 << 4 | b2 << 2 | b3
                 }
+                u64 v64 = (u64)pk8 << (8 * (7 - (lane & 7)));
+                u32 nm = n4 << (4 * (lane & 7));
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) { v64 |= __shfl_xor_sync(0xffffffffu, v64, o); nm |= __shfl_xor_sync(0xffffffffu, nm, o); }
+                if ((lane & 7) == 0 && j4 < kHalo + kTile) { S.pk[j4 >> 5] = v64; S.nmask[j4 >> 5] = nm; }
             }
             __syncthreads();
             for (int j = tid; j < nloc; j += kTile) {
