@@ -394,7 +394,11 @@ int check_params(const mm2gb_seed_params_t *p)
 int run_sort(mm2gb_seeder *sd, int n_reads)
 {
     struct Cls { int cap, warps; };
-    static const Cls base[] = {{2048, 4}, {4096, 4}, {8192, 2}, {16384, 1}, {32768, 1}, {65536, 1}, {131072, 1}};
+    // small reads: several warps (= reads) per CTA; above that one warp per CTA with caps chosen so that exactly 16, 12, 10, 8, 6, 5, 4, 3, 2
+    // CTAs fit the shared memory of an SM (227 KB; digits + SortShared + the 1 KB the runtime reserves per CTA) -- what matters for
+    // these latency-bound single warps is how many reads are resident
+    static const Cls base[] = {{2048, 4}, {4096, 4}, {8192, 2}, {11200, 1}, {16032, 1}, {19904, 1}, {25728, 1}, {35408, 1}, {43152, 1},
+                               {54784, 1}, {74144, 1}, {112896, 1}};
     std::vector<Cls> cls;
     for (const Cls &c : base) if (c.cap < sd->sort_max_cap) cls.push_back(c);
     cls.push_back({sd->sort_max_cap, 1});
