@@ -71,6 +71,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--reads", type=int, default=150)
+    ap.add_argument("--chain", action="store_true", help="also run the fused seed + chain step and compare chains / compacted anchors with mm_map_seed + mg_lchain_dp")
     args = ap.parse_args()
     pkg = entry.load_package()
     from mm2gb_b200 import seed
@@ -91,6 +92,25 @@ def main():
         with seed.Index(refs, w=w, k=k) as ix, seed.Seeder(ix, max_bases=int(off[-1]) + 1024, max_reads=len(reads) + 8, max_anchors=1 << 26) as sd:
             prm = seed.map_ont_seed_params(mid, occ_dist=dist, q_occ_frac=frac, max_max_occ=mmo)
             a, a_off, rep, mp, mp_off = sd.seed(prm, buf, off)
+        if args.chain:
+            rix.field("max_chain_skip", 2147483647)
+            n_a, n_u, dig, _ = rix.seed_batch(buf, off, chain=True, threads=8)
+            misc = pkg.Misc.from_buffer_copy(rix.misc())
+            cap = int(n_a.sum()) + 1024
+            with seed.Index(refs, w=w, k=k) as ix, pkg.ChainContext(misc, device=0, max_anchors=cap, max_reads=len(reads) + 8, n_slots=1,
+                                                                    flags=pkg.ChainContext.DEVICE_ONLY) as ctx, \
+                    seed.Seeder(ix, max_bases=int(off[-1]) + 1024, max_reads=len(reads) + 8, max_anchors=cap) as sd:
+                res = sd.seed_chain(ctx, prm, buf, off)
+            for r in range(len(reads)):
+                u = res["u"][res["u_pos"][r]:res["u_pos"][r] + res["n_u"][r]]
+                b = res["b"][res["b_pos"][r]:res["b_pos"][r] + res["n_b"][r]]
+                ok = int(res["n_u"][r]) == int(n_u[r]) and int(res["a_off"][r + 1] - res["a_off"][r]) == int(n_a[r]) and rs.chain_digest(u, b) == int(dig[r])
+                total += 1
+                if not ok:
+                    bad += 1
+                    if len(detail) < 10:
+                        detail.append({"round": rnd, "read": r, "len": len(reads[r]), "w": w, "k": k, "mid_occ": mid, "chain": True,
+                                       "n_u": [int(res["n_u"][r]), int(n_u[r])], "n_a": [int(res["a_off"][r + 1] - res["a_off"][r]), int(n_a[r])]})
         for r, read in enumerate(reads):
             ea, erep, emp = rix.seed(read)
             ga, gmp = a[a_off[r]:a_off[r + 1]], mp[mp_off[r]:mp_off[r + 1]]
