@@ -488,3 +488,71 @@ def check_runs_form():
 
 if __name__ == "__main__":
     check_runs_form()
+
+
+# ---- fourth formulation: foreign elements only + one boundary per bucket (tried in k_seed_sort: bit-exact, slower; kept as a model) ---
+# Arrivals into bucket l during the phases of earlier buckets consume l's foreign slots in order; when l's own phase starts its cursor
+# stands right behind the last consumed one (B_l).  Every resident of l below B_l has been pushed up by exactly one slot, every
+# resident at or above B_l stays: the shifts need no serial work at all.  The serial part visits foreign elements only (landing slot =
+# the bucket's cursor, evicted element = the next foreign slot at or after it).
+
+def pass_dest_foreign(dig):
+    n = len(dig)
+    cnt = [0] * 256
+    for d in dig:
+        cnt[d] += 1
+    cur, st, en, run = [0] * 256, [0] * 256, [0] * 256, 0
+    for d in range(256):
+        cur[d] = st[d] = run
+        run += cnt[d]
+        en[d] = run
+    def next_foreign(d, p):
+        while p < en[d] and dig[p] == d:
+            p += 1
+        return p
+    dest = list(range(n))
+    bound = [0] * 256
+    for kk in range(256):
+        bound[kk] = cur[kk]                       # B_kk: where the home phase starts
+        kb = next_foreign(kk, cur[kk])
+        while kb < en[kk]:
+            frm, d = kb, dig[kb]
+            while True:
+                pos = cur[d]
+                nm = next_foreign(d, pos)
+                assert nm < en[d]
+                dest[frm] = pos
+                cur[d] = nm + 1
+                frm, d = nm, dig[nm]
+                if d == kk:
+                    break
+            dest[frm] = kb
+            kb = next_foreign(kk, kb + 1)
+    for d in range(256):                          # the shifts, in parallel on the device
+        for x in range(st[d], en[d]):
+            if dig[x] == d and x < bound[d]:
+                dest[x] = x + 1
+    return dest
+
+
+def check_foreign_form():
+    rng = np.random.default_rng(19)
+    bad = 0
+    for n in (2, 5, 40, 300, 2000):
+        for nb in (2, 3, 6, 40, 256):
+            for skew in (0, 1):
+                for _ in range(10):
+                    pool = rng.choice(256, nb, replace=False)
+                    if skew and nb > 1:
+                        p = np.full(nb, 0.1 / (nb - 1)); p[0] = 0.9
+                        dig = [int(v) for v in rng.choice(pool, n, p=p)]
+                    else:
+                        dig = [int(v) for v in rng.choice(pool, n)]
+                    a, _ = pass_dest_walk(dig)
+                    if pass_dest_foreign(dig) != a:
+                        bad += 1
+    print("foreign-only form mismatches:", bad)
+
+
+if __name__ == "__main__":
+    check_foreign_form()

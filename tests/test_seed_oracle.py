@@ -91,6 +91,7 @@ def test_pass_forms_agree():
                 dig = [int(v) for v in rng.choice(pool, n, p=p)]
                 a, _ = seed_model.pass_dest_walk(dig)
                 assert seed_model.pass_dest_runs(dig) == a, (n, nb, skew)
+                assert seed_model.pass_dest_foreign(dig) == a, (n, nb, skew)
                 if len(set(dig)) == 2:
                     assert seed_model.pass_dest_two(dig) == a, (n, nb, skew)
 
