@@ -969,17 +969,23 @@ __global__ void k_select(Seeds m, const u64 *__restrict__ m_idx, const u64 *__re
         // seed.c:65-69: nothing happens with fewer than two seeds or without a high-occurrence seed; the second test is
         // implied for a seed that is not high itself (its flt stays 0 either way)
         if (n0 >= 2 && ni > (u32)max_occ) {
-            long long st = i, en = i + 1;
-            int rank = 0;
-            while (st > b && m.n[st - 1] > (u32)max_occ) { --st; if (m.n[st] <= ni) ++rank; }          // (n, j) < (ni, i) with j < i
-            while (en < e && m.n[en] > (u32)max_occ) { if (m.n[en] < ni) ++rank; ++en; }               // j > i: strictly smaller n
-            const int len = (int)(seq_off[s + 1] - seq_off[s]);
-            const int ps = st > b ? (int)(m.q_pos[st - 1] >> 1) : 0;
-            const int pe = en < e ? (int)(m.q_pos[en] >> 1) : len;
-            int max_high_occ = (int)((double)(pe - ps) / dist + .499);
-            if (max_high_occ > 128) max_high_occ = 128;
-            flt = (max_high_occ > 0 && rank < max_high_occ) ? 0 : 1;
-            if (ni > (u32)max_max_occ) flt = 1;
+            flt = 1;
+            if (ni <= (u32)max_max_occ) {          // seed.c:91-93: above max_max_occ the seed is filtered whatever its rank
+                long long st = i, en = i + 1;
+                int rank = 0;
+                // a seed with 128 (MAX_MAX_HIGH_OCC, seed.c:55) smaller ones in its streak is filtered whatever the streak's bounds
+                // are: stop scanning there (a read that is one long repeat is one long streak)
+                while (rank < 128 && st > b && m.n[st - 1] > (u32)max_occ) { --st; if (m.n[st] <= ni) ++rank; }      // (n, j) < (ni, i) with j < i
+                while (rank < 128 && en < e && m.n[en] > (u32)max_occ) { if (m.n[en] < ni) ++rank; ++en; }           // j > i: strictly smaller n
+                if (rank < 128) {
+                    const int len = (int)(seq_off[s + 1] - seq_off[s]);
+                    const int ps = st > b ? (int)(m.q_pos[st - 1] >> 1) : 0;
+                    const int pe = en < e ? (int)(m.q_pos[en] >> 1) : len;
+                    int max_high_occ = (int)((double)(pe - ps) / dist + .499);
+                    if (max_high_occ > 128) max_high_occ = 128;
+                    flt = (max_high_occ > 0 && rank < max_high_occ) ? 0 : 1;
+                }
+            }
         }
     } else if (ni > (u32)max_occ) flt = 1;
     m.flt[i] = flt;
