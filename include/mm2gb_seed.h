@@ -9,8 +9,8 @@
  * reference's unstable in-place radix sort leaves among anchors of equal x) are computed there, and the anchors go straight
  * into the chaining kernels without crossing PCIe.  Results are identical to the reference's arrays (tests/test_seed*.py).
  *
- * Scope: single-segment reads, non-HPC minimizers with odd k <= 28 and w <= 32 (map-ont, map-hifi, asm* index settings), no
- * sdust masking, and none of the flags that change seed collection (MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_FOR_ONLY, MM_F_REV_ONLY,
+ * Scope: single-segment reads, minimizers with odd k <= 28 and w <= 32, plain or homopolymer-compressed (map-ont, map-hifi, map-pb,
+ * asm* index settings), no sdust masking, and none of the flags that change seed collection (MM_F_NO_DIAG, MM_F_NO_DUAL, MM_F_FOR_ONLY, MM_F_REV_ONLY,
  * MM_F_QSTRAND, MM_F_HEAP_SORT).  Anything else is refused with MM2GB_EARG -- never approximated, never sent to a CPU path.
  *
  * Every function returns 0 on success and a negative MM2GB_E* code (mm2gb_chain.h) on failure; mm2gb_last_error() has the text.

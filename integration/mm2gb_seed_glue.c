@@ -12,7 +12,7 @@
  * mm_map_align (map.c:566-635) continues unchanged.  Switched on with MM2GB_GPU_SEED=1; the two-line change of map.c that calls
  * it is integration/map_gpu_seed.sed (applied to a scratch copy by oracle/Makefile for the test binary minimap2_b200_seed).
  *
- * Batches the device cannot take (HPC index, even k, sdust, multi-segment reads, all-vs-all flags) end the run with a message:
+ * Batches the device cannot take (even k, sdust, multi-segment reads, all-vs-all flags) end the run with a message:
  * leave MM2GB_GPU_SEED unset for those.
  */
 #include <pthread.h>

@@ -59,6 +59,7 @@ template <class T> int dalloc(T *&p, size_t n)
 
 struct mm2gb_index {
     int device = 0, w = 0, k = 0;
+    bool hpc = false;          // MM_I_HPC: minimizers of the homopolymer-compressed sequences
     // host copy: keys ascending, occurrences of keys[i] at occ[off[i] .. off[i+1]) ascending
     std::vector<uint64_t> keys, off, occ;
     bool keys_sorted = true;               // false: built from an enumerated hash table (mm2gb_index_from_lists); lookups go through hk / hv
@@ -94,6 +95,11 @@ struct mm2gb_seeder {
     int *d_tile_first = nullptr;
     u32 *d_tile_cnt = nullptr;
     u64 *d_tile_base = nullptr, *d_part = nullptr, *d_scan_state = nullptr;
+    // homopolymer compression (HPC indices only): element-end flags, element index of every base, element codes / end positions / offsets
+    unsigned char *d_hflag = nullptr, *d_ecode = nullptr;
+    u64 *d_eidx = nullptr;
+    u32 *d_epos = nullptr;
+    long long *d_eoff = nullptr;
     // minimizers
     u64 *d_mv_x = nullptr, *d_mv_y = nullptr, *d_mv_off = nullptr;
     u32 *d_mv_seq = nullptr;
@@ -131,7 +137,7 @@ struct mm2gb_seeder {
     std::vector<int> tile_first;
     std::vector<int64_t> a_off_copy;
     // last batch
-    long long n_mv = 0, n_m = 0, n_a = 0, n_mp = 0;
+    long long n_mv = 0, n_m = 0, n_a = 0, n_mp = 0, n_bases = 0;
     int n_tiles = 0;
     float ms[MM2GB_SEED_NTIMERS] = {0};
     bool timed = false;
@@ -139,16 +145,18 @@ struct mm2gb_seeder {
 
 namespace {
 
-int scan_u32(cudaStream_t st, const u32 *in, long long n, u64 *out, u64 *part)
+template <typename TI>
+int scan_any(cudaStream_t st, const TI *in, long long n, u64 *out, u64 *part)
 {
     if (n <= 0) { CK(cudaMemsetAsync(out, 0, sizeof(u64), st)); return MM2GB_OK; }
     const int nb = (int)((n + kScanChunk - 1) / kScanChunk);
-    k_scan_reduce<<<nb, kScanThreads, 0, st>>>(in, n, part);
+    k_scan_reduce<TI><<<nb, kScanThreads, 0, st>>>(in, n, part);
     k_scan_top<<<1, 1024, 0, st>>>(part, nb);
-    k_scan_apply<<<nb, kScanThreads, 0, st>>>(in, n, part, out);
+    k_scan_apply<TI><<<nb, kScanThreads, 0, st>>>(in, n, part, out);
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
+int scan_u32(cudaStream_t st, const u32 *in, long long n, u64 *out, u64 *part) { return scan_any<u32>(st, in, n, out, part); }
 
 inline unsigned grid_for(long long n, int threads) { return (unsigned)std::max<long long>(1, (n + threads - 1) / threads); }
 
@@ -192,15 +200,26 @@ int sketch_launch(mm2gb_seeder *sd, int n_seq, int rid_is_seq, int c, int t0, in
     const int nt = sd->n_tiles, n = t1 - t0;
     u64 *ticket = sd->d_scan_state + c, *status = sd->d_scan_state + 16;
     const int *tile_seq = (const int *)sd->d_tile_cnt;
-    if (ix->k <= 15 && sd->sketch_persistent)
+    if (ix->hpc) {
+        // elements of the homopolymer-compressed sequences first (flags, scan, write), then the generic kernel on them; the tiles are
+        // planned on the original lengths (an upper bound of the element counts: surplus tiles publish a count of zero)
+        const long long nb = sd->n_bases;
+        k_hpc_flags<<<nt, 256, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, nt, sd->d_hflag);
+        int rc = scan_any<unsigned char>(st, sd->d_hflag, nb, sd->d_eidx, sd->d_part);
+        if (rc) return rc;
+        k_hpc_write<<<nt, 256, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, nt, sd->d_hflag, sd->d_eidx, sd->d_ecode, sd->d_epos);
+        k_hpc_offsets<<<grid_for(n_seq + 1, 256), 256, 0, st>>>(sd->d_seq_off, sd->d_eidx, n_seq, sd->d_eoff);
+        k_sketch<u64, true><<<n, kTile, 0, st>>>(sd->d_ecode, sd->d_eoff, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket, t0, t1, status,
+                                                 (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base, sd->d_epos);
+    } else if (ix->k <= 15 && sd->sketch_persistent)
         k_sketch32p<<<std::min(n, sd->sketch_grid), kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket,
                                                                    t0, t1, status, (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     else if (ix->k <= 15)
         k_sketch32<<<n, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket, t0, t1, status,
                                         (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
     else
-        k_sketch<u64><<<n, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket, t0, t1, status,
-                                           (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base);
+        k_sketch<u64, false><<<n, kTile, 0, st>>>(sd->d_seq, sd->d_seq_off, sd->d_tile_first, tile_seq, n_seq, nt, ix->w, ix->k, rid_is_seq, ticket, t0, t1, status,
+                                           (long long)sd->max_mv, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_tile_base, nullptr);
     CK(cudaGetLastError());
     return MM2GB_OK;
 }
@@ -240,6 +259,7 @@ int upload_offsets(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
     const int nt = plan_tiles(sd, seq_off, n_seq);
     if (nt < 0) return fail(MM2GB_ECAP, "batch does not fit the seeder (tiles)");
     sd->n_tiles = nt;
+    sd->n_bases = seq_off[n_seq];
     CK(cudaMemcpyAsync(sd->d_seq_off, seq_off, ((size_t)n_seq + 1) * sizeof(long long), cudaMemcpyHostToDevice, sd->stream));
     CK(cudaMemcpyAsync(sd->d_tile_first, sd->tile_first.data(), ((size_t)n_seq + 1) * sizeof(int), cudaMemcpyHostToDevice, sd->stream));
     return MM2GB_OK;
@@ -351,7 +371,12 @@ int upload_and_sketch(mm2gb_seeder *sd, const char *seqs, const int64_t *seq_off
     int rc = sketch_prepare(sd, n_seq);
     if (rc) return rc;
     const int64_t total = seq_off[n_seq];
-    if (total > 0) {
+    if (total > 0 && sd->idx->hpc) {      // the homopolymer compression runs over the whole batch: upload first, one launch
+        rc = upload_seqs(sd, seqs, total);
+        if (rc) return rc;
+        rc = sketch_launch(sd, n_seq, rid_is_seq, 0, 0, sd->n_tiles);
+        if (rc) return rc;
+    } else if (total > 0) {
         const bool pinned = is_pinned_host(seqs);
         rc = stage_begin(sd);
         if (rc) return rc;
@@ -485,7 +510,7 @@ int run_seed(mm2gb_seeder *sd, const mm2gb_seed_params_t *prm, const int64_t *se
     CK(cudaStreamSynchronize(st));
     const long long n_m = sd->n_m = (long long)sd->h_tot[0];
     if (n_m) {
-        k_compact_seeds<<<grid_for(n_mv, T), T, 0, st>>>(sd->d_mv_y, sd->d_mv_seq, sd->d_occ_n, sd->d_occ_off, sd->d_tandem, sd->d_m_idx, n_mv, sd->m);
+        k_compact_seeds<<<grid_for(n_mv, T), T, 0, st>>>(sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq, sd->d_occ_n, sd->d_occ_off, sd->d_tandem, sd->d_m_idx, n_mv, sd->m);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(sd->ev[3], st));
@@ -559,13 +584,17 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
     TRY(dalloc(sd->d_seq, (size_t)max_bases + 16));
     TRY(dalloc(sd->d_seq_off, R)); TRY(dalloc(sd->d_tile_first, R));
     TRY(dalloc(sd->d_tile_cnt, NT)); TRY(dalloc(sd->d_tile_base, NT)); TRY(dalloc(sd->d_scan_state, NT + 18));
-    TRY(dalloc(sd->d_part, std::max(M, NT) / kScanChunk + 4));
+    TRY(dalloc(sd->d_part, std::max(std::max(M, NT), (size_t)max_bases) / kScanChunk + 4));
+    if (idx->hpc) {
+        TRY(dalloc(sd->d_hflag, (size_t)max_bases + 16)); TRY(dalloc(sd->d_ecode, (size_t)max_bases + 16)); TRY(dalloc(sd->d_eidx, (size_t)max_bases + 2));
+        TRY(dalloc(sd->d_epos, (size_t)max_bases + 16)); TRY(dalloc(sd->d_eoff, R));
+    }
     TRY(dalloc(sd->d_mv_x, M)); TRY(dalloc(sd->d_mv_y, M)); TRY(dalloc(sd->d_mv_seq, M)); TRY(dalloc(sd->d_mv_off, R));
     TRY(dalloc(sd->d_keep, M)); TRY(dalloc(sd->d_tandem, M));
     TRY(dalloc(sd->d_tab_key, 2 * M)); TRY(dalloc(sd->d_tab_cnt, 2 * M));
     TRY(dalloc(sd->d_occ_n, M)); TRY(dalloc(sd->d_has, M)); TRY(dalloc(sd->d_occ_off, M)); TRY(dalloc(sd->d_m_idx, M + 1));
     TRY(dalloc(sd->m.n, M)); TRY(dalloc(sd->m.q_pos, M)); TRY(dalloc(sd->m.off, M)); TRY(dalloc(sd->m.seq, M));
-    TRY(dalloc(sd->m.tandem, M)); TRY(dalloc(sd->m.flt, M));
+    TRY(dalloc(sd->m.tandem, M)); TRY(dalloc(sd->m.flt, M)); TRY(dalloc(sd->m.span, M));
     TRY(dalloc(sd->d_cnt_a, M)); TRY(dalloc(sd->d_kept, M)); TRY(dalloc(sd->d_a_pos, M + 1)); TRY(dalloc(sd->d_mp_pos, M + 1));
     TRY(dalloc(sd->d_mini_pos, M));
     TRY(dalloc(sd->d_a_off, R)); TRY(dalloc(sd->d_mp_off, R)); TRY(dalloc(sd->d_rep_len, R));
@@ -607,7 +636,7 @@ extern "C" void mm2gb_seeder_destroy(mm2gb_seeder_t *sd)
     if (sd->stream) cudaStreamSynchronize(sd->stream);
     void *dev[] = {sd->d_seq, sd->d_seq_off, sd->d_tile_first, sd->d_tile_cnt, sd->d_tile_base, sd->d_scan_state, sd->d_part, sd->d_mv_x, sd->d_mv_y, sd->d_mv_seq,
                    sd->d_mv_off, sd->d_keep, sd->d_tandem, sd->d_tab_key, sd->d_tab_cnt, sd->d_occ_n, sd->d_has, sd->d_occ_off, sd->d_m_idx,
-                   sd->m.n, sd->m.q_pos, sd->m.off, sd->m.seq, sd->m.tandem, sd->m.flt, sd->d_cnt_a, sd->d_kept, sd->d_a_pos, sd->d_mp_pos,
+                   sd->m.n, sd->m.q_pos, sd->m.off, sd->m.seq, sd->m.tandem, sd->m.flt, sd->m.span, sd->d_hflag, sd->d_ecode, sd->d_eidx, sd->d_epos, sd->d_eoff, sd->d_cnt_a, sd->d_kept, sd->d_a_pos, sd->d_mp_pos,
                    sd->d_mini_pos, sd->d_a_off, sd->d_mp_off, sd->d_rep_len, sd->d_a_tmp, sd->d_a, sd->d_dest, sd->d_lst, sd->d_dig, sd->d_stack, sd->d_sort_list, sd->d_f, sd->d_p};
     for (void *p : dev) if (p) cudaFree(p);
     void *pin[] = {sd->h_a_off, sd->h_mp_off, sd->h_rep_len, sd->h_tot, sd->h_b, sd->h_u, sd->h_seq, sd->h_sort_list};
@@ -814,7 +843,6 @@ extern "C" int mm2gb_index_build(mm2gb_index_t **out, int device, const char *se
     (void)bucket_bits;
     if (!out || !seqs || !seq_off || n_seq <= 0) return fail(MM2GB_EARG, "bad argument");
     *out = nullptr;
-    if (is_hpc) return fail(MM2GB_EARG, "homopolymer-compressed minimizers (MM_I_HPC) are not supported by the device seeding path");
     if (k < 1 || k > 28 || !(k & 1)) return fail(MM2GB_EARG, "device seeding needs an odd k <= 28 (got %d)", k);
     if (w < 1 || w > kMaxW) return fail(MM2GB_EARG, "device seeding needs 1 <= w <= %d (got %d)", kMaxW, w);
     int ndev = 0;
@@ -822,7 +850,7 @@ extern "C" int mm2gb_index_build(mm2gb_index_t **out, int device, const char *se
     if (device < 0 || device >= ndev) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
     CK(cudaSetDevice(device));
     mm2gb_index *ix = new mm2gb_index();
-    ix->device = device; ix->w = w; ix->k = k;
+    ix->device = device; ix->w = w; ix->k = k; ix->hpc = is_hpc != 0;
     // sketch every sequence with the read kernel (rid = sequence number), in pieces of at most 256 M bases
     std::vector<std::pair<u64, u64>> mz;     // (minimizer = x >> 8, y)
     {
@@ -889,7 +917,6 @@ extern "C" int mm2gb_index_from_lists(mm2gb_index_t **out, int device, int w, in
 {
     if (!out || n_keys < 0 || (n_keys && (!keys || !off || !occ))) return fail(MM2GB_EARG, "bad argument");
     *out = nullptr;
-    if (is_hpc) return fail(MM2GB_EARG, "homopolymer-compressed minimizers (MM_I_HPC) are not supported by the device seeding path");
     if (k < 1 || k > 28 || !(k & 1)) return fail(MM2GB_EARG, "device seeding needs an odd k <= 28 (got %d)", k);
     if (w < 1 || w > kMaxW) return fail(MM2GB_EARG, "device seeding needs 1 <= w <= %d (got %d)", kMaxW, w);
     int ndev = 0;
@@ -897,7 +924,7 @@ extern "C" int mm2gb_index_from_lists(mm2gb_index_t **out, int device, int w, in
     if (device < 0 || device >= ndev) return fail(MM2GB_EARG, "no CUDA device %d (have %d)", device, ndev);
     CK(cudaSetDevice(device));
     mm2gb_index *ix = new mm2gb_index();
-    ix->device = device; ix->w = w; ix->k = k;
+    ix->device = device; ix->w = w; ix->k = k; ix->hpc = is_hpc != 0;
     // keys arrive in the enumeration order of the host hash tables and stay in it: the device side is a hash table anyway, and the
     // host-side lookups (mm2gb_index_get: tests) go through the host copy of that table
     ix->keys.assign(keys, keys + n_keys);

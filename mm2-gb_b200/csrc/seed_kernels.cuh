@@ -14,6 +14,9 @@
 //                     are replayed step for step on 4-byte (digit, index) words in shared memory; buckets of <= 64 elements
 //                     (stable insertion sort in the reference) are ranked by a warp.
 //
+//   k_hpc_*           homopolymer compression (MM_I_HPC, sketch.c:92-101) as a stream compaction: one element per run of equal bases;
+//                     k_sketch<u64, true> then runs the same rules on the elements, every record carrying its own span.
+//
 // Integer / byte work, HBM- and latency-bound: no tensor cores here.
 #pragma once
 
@@ -115,13 +118,18 @@ __device__ __forceinline__ u32 hash32(u32 key, u32 mask)    // hash64 (sketch.c:
 // A launch covers the tiles [tile_begin, tile_end) (a batch is sketched in a few launches so that the upload of its later reads
 // overlaps the sketch of its earlier ones; launches of a batch run in stream order, so every predecessor tile of an earlier launch
 // is complete); *ticket = that launch's ticket counter, scan_state[tile] = status word; all zero before the first launch
-template <typename HT>
+// HPC (MM_I_HPC, sketch.c:92-101): the kernel then runs on the ELEMENTS of the homopolymer-compressed sequence (k_hpc_* below: one
+// element per run of equal unambiguous bases, one per ambiguous base; `seqs` holds their codes, `seq_off` their offsets, `epos` the
+// position of every element's last base) -- the loop does on elements exactly what it does on positions without HPC, with the
+// k-mer span = distance between the ends of the k-th previous element and this one, and only spans below 256 are valid.
+template <typename HT, bool HPC>
 __global__ void __launch_bounds__(kTile)
 k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq, int n_seq,
          int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ ticket, int tile_begin, int tile_end, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x, u64 *__restrict__ mv_y,
-         u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl)
+         u32 *__restrict__ mv_seq, u64 *__restrict__ tile_excl, const u32 *__restrict__ epos)
 {
     __shared__ SketchTile<HT> S;
+    __shared__ u32 s_epos[HPC ? kHalo + kTile : 1];
     constexpr HT NONE = (HT)~(HT)0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -143,6 +151,7 @@ k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ s
             S.pk[j >> 5] = spread32(__brev(b1)) << 1 | spread32(__brev(b0));
             S.nmask[j >> 5] = bn;
         }
+        if (HPC) s_epos[j] = (pos >= 0 && pos < len) ? __ldg(epos + base + pos) : 0xffffffffu;   // before the first element: -1
     }
     __syncthreads();
     const u64 mask = (1ULL << (2 * k)) - 1;
@@ -167,6 +176,10 @@ k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ s
                     z = f < rc ? 0 : 1;
                     const u64 km = z ? rc : f;
                     h = sizeof(HT) == 4 ? (HT)hash32((u32)km, (u32)mask) : (HT)hash64(km, mask);
+                    if (HPC) {       // the record compared by the loop is hash << 8 | span (sketch.c:109), and spans of 256 or more are no records
+                        const u32 span = s_epos[sj] - s_epos[sj - k];
+                        h = span < 256u ? (HT)((u64)h << 8 | span) : NONE;
+                    }
                 }
             }
         }
@@ -215,8 +228,8 @@ k_sketch(const unsigned char *__restrict__ seqs, const long long *__restrict__ s
         auto emit = [&](int p) {
             if (pass == 1 && (long long)(wpos + c) < cap) {
                 const int q = w + (p - t0);
-                mv_x[wpos + c] = (u64)S.ih[q] << 8 | (u64)k;
-                mv_y[wpos + c] = (rid_is_seq ? (u64)s << 32 : 0ULL) | (u64)(u32)p << 1 | (u64)S.iz[q];
+                mv_x[wpos + c] = HPC ? (u64)S.ih[q] : ((u64)S.ih[q] << 8 | (u64)k);
+                mv_y[wpos + c] = (rid_is_seq ? (u64)s << 32 : 0ULL) | (u64)(HPC ? s_epos[kHalo + (p - t0)] : (u32)p) << 1 | (u64)S.iz[q];
                 mv_seq[wpos + c] = (u32)s;
             }
             ++c;
@@ -753,6 +766,52 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
     }
 }
 
+// ---- homopolymer compression of a batch (sketch.c:92-101 as a stream compaction) ------------------------------------------------
+// flag[g] = 1 if an element ends at global base g: the last base of a run of equal unambiguous bases, or an ambiguous base.
+__global__ void __launch_bounds__(256)
+k_hpc_flags(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first,
+            const int *__restrict__ tile_seq, int n_tiles, unsigned char *__restrict__ flag)
+{
+    const int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const int s = tile_seq[tile];
+    const long long base = seq_off[s];
+    const int len = (int)(seq_off[s + 1] - base);
+    const int t0 = (tile - tile_first[s]) * kTile;
+    for (int i = t0 + threadIdx.x; i < min(len, t0 + kTile); i += blockDim.x) {
+        const int c = nt4(__ldg(seqs + base + i));
+        const int cn = i + 1 < len ? nt4(__ldg(seqs + base + i + 1)) : 5;
+        flag[base + i] = (c == 4 || cn != c) ? 1 : 0;
+    }
+}
+
+// element e = eidx[g] of every flagged base g: its code and the position (inside its sequence) of its last base
+__global__ void __launch_bounds__(256)
+k_hpc_write(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first,
+            const int *__restrict__ tile_seq, int n_tiles, const unsigned char *__restrict__ flag, const u64 *__restrict__ eidx,
+            unsigned char *__restrict__ ecode, u32 *__restrict__ epos)
+{
+    const int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const int s = tile_seq[tile];
+    const long long base = seq_off[s];
+    const int len = (int)(seq_off[s + 1] - base);
+    const int t0 = (tile - tile_first[s]) * kTile;
+    for (int i = t0 + threadIdx.x; i < min(len, t0 + kTile); i += blockDim.x) {
+        if (!flag[base + i]) continue;
+        const u64 e = eidx[base + i];
+        ecode[e] = (unsigned char)nt4(__ldg(seqs + base + i));
+        epos[e] = (u32)i;
+    }
+}
+
+// element offsets per sequence
+__global__ void k_hpc_offsets(const long long *__restrict__ seq_off, const u64 *__restrict__ eidx, int n_seq, long long *__restrict__ eoff)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= n_seq) eoff[s] = (long long)eidx[seq_off[s]];
+}
+
 // ---- exclusive scan of a u32 array into u64 (three kernels; n up to 2^40) -------------------------------------------------
 constexpr int kScanThreads = 256, kScanItems = 16, kScanChunk = kScanThreads * kScanItems;
 
@@ -777,7 +836,8 @@ __device__ __forceinline__ u64 block_scan_excl(u64 v, u64 *warp_sum, u64 *total)
     return excl;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const u32 *__restrict__ in, long long n, u64 *__restrict__ part)
+template <typename TI>
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const TI *__restrict__ in, long long n, u64 *__restrict__ part)
 {
     __shared__ u64 ws[32];
     const long long b0 = (long long)blockIdx.x * kScanChunk;
@@ -811,7 +871,8 @@ __global__ void __launch_bounds__(1024) k_scan_top(u64 *__restrict__ part, int n
     if (threadIdx.x == 0) part[n_part] = carry;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const u32 *__restrict__ in, long long n, const u64 *__restrict__ part,
+template <typename TI>
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const TI *__restrict__ in, long long n, const u64 *__restrict__ part,
                                                              u64 *__restrict__ out)
 {
     __shared__ u64 ws[32];
@@ -941,9 +1002,10 @@ struct Seeds {
     u32 *seq;        // read
     unsigned char *tandem;
     unsigned char *flt;
+    unsigned char *span;     // q_span = the low byte of the minimizer record (k unless the index is homopolymer-compressed)
 };
 
-__global__ void k_compact_seeds(const u64 *__restrict__ mv_y, const u32 *__restrict__ mv_seq, const u32 *__restrict__ occ_n,
+__global__ void k_compact_seeds(const u64 *__restrict__ mv_x, const u64 *__restrict__ mv_y, const u32 *__restrict__ mv_seq, const u32 *__restrict__ occ_n,
                                 const u64 *__restrict__ occ_off, const unsigned char *__restrict__ tandem, const u64 *__restrict__ m_idx,
                                 long long n_mv, Seeds m)
 {
@@ -951,6 +1013,7 @@ __global__ void k_compact_seeds(const u64 *__restrict__ mv_y, const u32 *__restr
     if (i >= n_mv || occ_n[i] == 0) return;
     const u64 q = m_idx[i];
     m.n[q] = occ_n[i]; m.q_pos[q] = (u32)mv_y[i]; m.off[q] = occ_off[i]; m.seq[q] = mv_seq[i]; m.tandem[q] = tandem[i];
+    m.span[q] = (unsigned char)(mv_x[i] & 0xffu);
 }
 
 // ---- mm_seed_select + the filter / rep_len part of mm_collect_matches -----------------------------------------------------
@@ -1002,7 +1065,8 @@ __global__ void k_rep_len(Seeds m, const u64 *__restrict__ m_idx, const u64 *__r
     if (i >= n_m || !m.flt[i]) return;
     const u32 s = m.seq[i];
     const long long b = (long long)m_idx[mv_off[s]];
-    const int en = (int)(m.q_pos[i] >> 1) + 1, st = en - q_span;
+    (void)q_span;
+    const int en = (int)(m.q_pos[i] >> 1) + 1, st = en - (int)m.span[i];
     long long j = i - 1;
     while (j >= b && !m.flt[j]) --j;
     const int prev_en = j >= b ? (int)(m.q_pos[j] >> 1) + 1 : 0;
@@ -1033,8 +1097,10 @@ __global__ void k_expand(Seeds m, const u64 *__restrict__ occ, const u64 *__rest
     const int qlen = (int)(seq_off[s + 1] - seq_off[s]);
     const u64 *r = occ + m.off[i];
     const u64 fl = m.tandem[i] ? kSeedTandem : 0ULL;
-    const u64 yf = (u64)q_span << 32 | (u64)(qp >> 1) | fl;
-    const u64 yr = (u64)q_span << 32 | (u64)(u32)(qlen - ((int)(qp >> 1) + 1 - q_span) - 1) | fl;
+    (void)q_span;
+    const int sp = (int)m.span[i];
+    const u64 yf = (u64)sp << 32 | (u64)(qp >> 1) | fl;
+    const u64 yr = (u64)sp << 32 | (u64)(u32)(qlen - ((int)(qp >> 1) + 1 - sp) - 1) | fl;
     uint4 *o = a + a_pos[i];
     for (u32 t = 0; t < n; ++t) {
         const u64 rr = __ldg(r + t);
@@ -1044,7 +1110,7 @@ __global__ void k_expand(Seeds m, const u64 *__restrict__ occ, const u64 *__rest
         else { x = 1ULL << 63 | (rr & 0xffffffff00000000ULL) | rpos; y = yr; }
         o[t] = make_uint4((u32)x, (u32)(x >> 32), (u32)y, (u32)(y >> 32));
     }
-    if (mini_pos) mini_pos[mp_pos[i]] = (u64)q_span << 32 | (u64)(qp >> 1);
+    if (mini_pos) mini_pos[mp_pos[i]] = (u64)sp << 32 | (u64)(qp >> 1);
 }
 
 // ---- radix_sort_128x (ksort.h:98-151) replayed per read --------------------------------------------------------------------

@@ -50,6 +50,17 @@ def main():
     a = [ix2.seed(r)[0] for r in reads]
     out["a_k19"] = np.concatenate(a)
     out["a_off_k19"] = np.cumsum([0] + [len(x) for x in a]).astype(np.int64)
+    # homopolymer-compressed minimizers (map-pb: MM_I_HPC, k = 19, w = 10): minimizers and anchors carry their own spans
+    ix3 = rs.RefIndex(refs, w=10, k=19, hpc=True, preset="map-pb")
+    ix3.field("mid_occ", 10)
+    mv3 = [rs.sketch(r, 10, 19, hpc=True) for r in reads]
+    out["mv_hpc"] = np.concatenate(mv3)
+    out["mv_off_hpc"] = np.cumsum([0] + [len(m) for m in mv3]).astype(np.int64)
+    res3 = [ix3.seed(r) for r in reads]
+    out["a_hpc"] = np.concatenate([x[0] for x in res3])
+    out["a_off_hpc"] = np.cumsum([0] + [len(x[0]) for x in res3]).astype(np.int64)
+    out["rep_hpc"] = np.array([x[1] for x in res3], dtype=np.int32)
+    out["mp_hpc"] = np.concatenate([x[2] for x in res3])
     path = os.path.join(HERE, "..", "tests", "golden", "seed_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes;", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})

@@ -556,3 +556,126 @@ def check_foreign_form():
 
 if __name__ == "__main__":
     check_foreign_form()
+
+
+# ---- homopolymer-compressed minimizers (MM_I_HPC, sketch.c:92-101) ---------------------------------------------------------------
+# Every run of equal unambiguous bases is ONE element (code, position of its last base); every ambiguous base is an element of its own.
+# mm_sketch's loop then does on the elements exactly what it does on positions without HPC, with the k-mer span = distance between the
+# ends of the k-th previous element and this one (the sum of the last k run lengths, sketch.c:98-100), valid only below 256.
+
+def hpc_elements(seq: bytes):
+    code = [NT4.get(c, 4) for c in seq]
+    n = len(code)
+    el = []          # (code, end position)
+    i = 0
+    while i < n:
+        c = code[i]
+        if c < 4:
+            j = i
+            while j + 1 < n and code[j + 1] == c:
+                j += 1
+            el.append((c, j))
+            i = j + 1
+        else:
+            el.append((4, i))
+            i += 1
+    return el
+
+
+def sketch_model_hpc(seq: bytes, w: int, k: int, rid: int = 0):
+    el = hpc_elements(seq)
+    n = len(el)
+    mask = (1 << (2 * k)) - 1
+    ix = [NONE] * n
+    iz = [0] * n
+    l = [0] * n
+    run = 0
+    for e in range(n):
+        run = run + 1 if el[e][0] < 4 else 0
+        l[e] = run
+        if run >= k:
+            f = r = 0
+            for t in range(k - 1, -1, -1):
+                c = el[e - t][0]
+                f = (f << 2 | c) & mask
+                r = (r >> 2) | (3 ^ c) << (2 * (k - 1))
+            span = el[e][1] - (el[e - k][1] if e - k >= 0 else -1)
+            if f != r and span < 256:
+                z = 0 if f < r else 1
+                ix[e] = hash64(r if z else f, mask) << 8 | span
+                iz[e] = z
+    def X(p):
+        return ix[p] if p >= 0 else NONE
+    out = []
+    T1 = w + k - 1
+    for i in range(n):
+        cur = ix[i]
+        mprev_x, mprev_p = NONE, -1
+        for d in range(w, 0, -1):
+            x = X(i - d)
+            if x <= mprev_x:
+                mprev_x, mprev_p = x, i - d
+        mode = 0
+        mx, mp = NONE, -1
+        if cur <= mprev_x:
+            mode = 2
+        elif mprev_p == i - w:
+            mode = 3
+            for d in range(w - 1, -1, -1):
+                x = X(i - d)
+                if x <= mx:
+                    mx, mp = x, i - d
+        def emit(p):
+            out.append((ix[p], rid << 32 | el[p][1] << 1 | iz[p]))
+        if l[i] == T1 and mprev_x != NONE:
+            for d in range(w - 1, 0, -1):
+                if X(i - d) == mprev_x and i - d != mprev_p:
+                    emit(i - d)
+        if mode == 2:
+            if l[i] >= T1 + 1 and mprev_x != NONE:
+                emit(mprev_p)
+        elif mode == 3:
+            if l[i] >= T1:
+                emit(mprev_p)
+            if l[i] >= T1 and mx != NONE:
+                for d in range(w - 1, -1, -1):
+                    if X(i - d) == mx and i - d != mp:
+                        emit(i - d)
+        if i == n - 1:
+            fx, fp = (cur, i) if mode == 2 else (mx, mp) if mode == 3 else (mprev_x, mprev_p)
+            if fx != NONE:
+                emit(fp)
+    return np.array(out, dtype=np.uint64).reshape(-1, 2)
+
+
+def check_hpc():
+    import pyrefseed as rs
+    rng = np.random.default_rng(23)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    cases = [acgt[rng.integers(0, 4, n)].tobytes() for n in (1, 5, 19, 20, 40, 300, 3000)]
+    # homopolymer-rich sequences
+    def hp(n):
+        out = bytearray()
+        while len(out) < n:
+            out += bytes([acgt[rng.integers(0, 4)]]) * int(rng.geometric(0.4))
+        return bytes(out[:n])
+    cases += [hp(n) for n in (50, 500, 4000)]
+    s = bytearray(hp(3000))
+    for p in (10, 11, 500, 1500, 1501, 2999):
+        s[p] = ord("N")
+    cases.append(bytes(s))
+    cases.append(b"A" * 400 + hp(300) + b"C" * 300 + hp(500))      # runs longer than 255: span >= 256 invalidates k-mers
+    cases.append(b"AC" * 300)
+    bad = 0
+    for w, k in ((10, 19), (5, 19), (10, 15), (19, 19)):
+        for c in cases:
+            a = rs.sketch(c, w, k, hpc=True)
+            b = sketch_model_hpc(c, w, k)
+            if a.shape != b.shape or not np.array_equal(a, b):
+                bad += 1
+                print("HPC MISMATCH w", w, "k", k, "len", len(c), a.shape, b.shape)
+    print("hpc sketch model mismatches:", bad)
+
+
+if __name__ == "__main__":
+    check_hpc()

@@ -123,3 +123,14 @@ def test_gpu_seed_driver_threads_spread_over_gpus(pkg, synth, tmp_path):
     cpu = run(CPU, ["-t", "4", "-x", "map-ont", "--max-chain-skip=2147483647", ref, reads], tmp_path)
     assert gpu == cpu
     assert err.count("seed+chain thread") >= 2
+
+
+@needs_seed_driver
+def test_gpu_seed_driver_map_pb_hpc_paf(synth, tmp_path):
+    """-x map-pb: homopolymer-compressed minimizers (k = 19) seeded and chained on the device inside the driver"""
+    ref, reads = _synth_fasta(synth, tmp_path, 3_000_000, 200, 5000, 40000, repeats=150, seed=13)
+    gpu, err = run_env(SEED, ["-t", "3", "-x", "map-pb", "--max-chain-skip=2147483647", ref, reads], tmp_path, MM2GB_GPU_SEED="1", MM2GB_VERBOSE="1")
+    cpu = run(CPU, ["-t", "4", "-x", "map-pb", "--max-chain-skip=2147483647", ref, reads], tmp_path)
+    assert len(cpu.splitlines()) >= 200
+    assert gpu == cpu
+    assert "seed+chain thread" in err

@@ -125,6 +125,58 @@ def test_seed_golden_k19(sd, cases, golden):
         assert np.array_equal(a_off, golden["a_off_k19"]) and np.array_equal(a, golden["a_k19"])
 
 
+def test_hpc_golden(sd, cases, golden):
+    """homopolymer-compressed minimizers (MM_I_HPC; map-pb: k = 19, w = 10): minimizers with their spans, anchors, rep_len, mini_pos"""
+    with sd.Index(cases[0], w=10, k=19, hpc=True) as ix, sd.Seeder(ix, max_bases=1 << 19, max_reads=256, max_anchors=1 << 16) as s:
+        buf, off = sd.pack_seqs(cases[1])
+        mv, mvo = s.sketch(buf, off)
+        assert np.array_equal(mvo, golden["mv_off_hpc"]) and np.array_equal(mv, golden["mv_hpc"])
+        a, a_off, rep, mp, _ = s.seed(sd.map_ont_seed_params(10), buf, off)
+        assert np.array_equal(a_off, golden["a_off_hpc"]) and np.array_equal(a, golden["a_hpc"])
+        assert np.array_equal(rep, golden["rep_hpc"]) and np.array_equal(mp, golden["mp_hpc"])
+
+
+@needs_ref
+@pytest.mark.parametrize("w,k", [(10, 19), (5, 15), (19, 19)])
+def test_hpc_sketch_vs_reference(sd, cases, w, k):
+    refs, reads = cases
+    rng = np.random.default_rng(k)
+    def hp(n):      # homopolymer-rich
+        out = bytearray()
+        while len(out) < n:
+            out += bytes([seed_cases.ACGT[rng.integers(0, 4)]]) * int(rng.geometric(0.35))
+        return bytes(out[:n])
+    seqs = list(reads) + [hp(n) for n in (1, 30, 600, 5000, 40000)] + [b"A" * 400 + hp(300) + b"C" * 300 + hp(2500), refs[0][59000:62000], refs[0][:30000]]
+    s2 = bytearray(hp(3000))
+    for p in (10, 11, 500, 1500, 1501, 2999):
+        s2[p] = ord("N")
+    seqs.append(bytes(s2))
+    with sd.Index([refs[0][:5000]], w=w, k=k, hpc=True) as ix, sd.Seeder(ix, max_bases=1 << 19, max_reads=256, max_anchors=1024) as s:
+        buf, off = sd.pack_seqs(seqs)
+        mv, mvo = s.sketch(buf, off, rid_is_seq=True)
+    for i, q in enumerate(seqs):
+        exp = rs.sketch(q, w, k, rid=i, hpc=True)
+        got = mv[mvo[i]:mvo[i + 1]]
+        assert got.shape == exp.shape and np.array_equal(got, exp), (w, k, i, len(q), got.shape, exp.shape)
+
+
+@needs_ref
+def test_hpc_seed_batch_vs_reference(sd, cases):
+    refs, _ = cases
+    reads = make_batch(refs, 120, seed=77)
+    buf, off = sd.pack_seqs(reads)
+    ix = rs.RefIndex(refs, w=10, k=19, hpc=True, preset="map-pb")
+    mid = int(ix.field("mid_occ"))
+    n_a, _, dig, _ = ix.seed_batch(buf, off, chain=False, threads=4)
+    with sd.Index(refs, w=10, k=19, hpc=True) as dix:
+        assert dix.mid_occ() == mid
+        with sd.Seeder(dix, max_bases=int(off[-1]) + 1024, max_reads=256, max_anchors=int(n_a.sum()) + 1024) as s:
+            a, a_off, _, _, _ = s.seed(sd.map_ont_seed_params(mid), buf, off, want_mini_pos=False)
+    assert np.array_equal(np.diff(a_off), n_a)
+    for r in range(len(reads)):
+        assert rs.word_digest(a[a_off[r]:a_off[r + 1]]) == int(dig[r]), r
+
+
 def test_sort_words_in_hbm(sd, index, cases, golden, monkeypatch):
     """Reads whose digit bytes do not fit shared memory keep them in HBM (same replay)."""
     monkeypatch.setenv("MM2GB_SEED_SORT_CAP", "64")
@@ -209,8 +261,6 @@ def test_refused_settings(pkg, sd, index, seeder, cases):
             seeder.seed(sd.map_ont_seed_params(10, **kw), buf, off)
     with pytest.raises(pkg.Mm2gbError):
         sd.Index(cases[0], w=10, k=16)
-    with pytest.raises(pkg.Mm2gbError):
-        sd.Index(cases[0], w=10, k=19, hpc=True)
     with pytest.raises(pkg.Mm2gbError):     # capacity: fails loudly, no partial result
         with sd.Seeder(index, max_bases=1 << 20, max_reads=64, max_anchors=100) as s:
             s.seed(sd.map_ont_seed_params(10), *sd.pack_seqs(cases[1][:4]))

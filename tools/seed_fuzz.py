@@ -86,10 +86,11 @@ def main():
         dist = int(rng.choice([0, 50, 100, 500, 2000]))
         frac = float(rng.choice([0.0, 0.002, 0.01, 0.05]))
         mmo = int(rng.choice([mid, mid + 3, 100, 4095]))
-        rix = rs.RefIndex(refs, w=w, k=k)
+        hpc = bool(rng.random() < 0.3)
+        rix = rs.RefIndex(refs, w=w, k=k, hpc=hpc)
         rix.field("mid_occ", mid); rix.field("occ_dist", dist); rix.field("q_occ_frac", frac); rix.field("max_max_occ", mmo)
         buf, off = seed.pack_seqs(reads)
-        with seed.Index(refs, w=w, k=k) as ix, seed.Seeder(ix, max_bases=int(off[-1]) + 1024, max_reads=len(reads) + 8, max_anchors=1 << 26) as sd:
+        with seed.Index(refs, w=w, k=k, hpc=hpc) as ix, seed.Seeder(ix, max_bases=int(off[-1]) + 1024, max_reads=len(reads) + 8, max_anchors=1 << 26) as sd:
             prm = seed.map_ont_seed_params(mid, occ_dist=dist, q_occ_frac=frac, max_max_occ=mmo)
             a, a_off, rep, mp, mp_off = sd.seed(prm, buf, off)
         if args.chain:
@@ -97,7 +98,7 @@ def main():
             n_a, n_u, dig, _ = rix.seed_batch(buf, off, chain=True, threads=8)
             misc = pkg.Misc.from_buffer_copy(rix.misc())
             cap = int(n_a.sum()) + 1024
-            with seed.Index(refs, w=w, k=k) as ix, pkg.ChainContext(misc, device=0, max_anchors=cap, max_reads=len(reads) + 8, n_slots=1,
+            with seed.Index(refs, w=w, k=k, hpc=hpc) as ix, pkg.ChainContext(misc, device=0, max_anchors=cap, max_reads=len(reads) + 8, n_slots=1,
                                                                     flags=pkg.ChainContext.DEVICE_ONLY) as ctx, \
                     seed.Seeder(ix, max_bases=int(off[-1]) + 1024, max_reads=len(reads) + 8, max_anchors=cap) as sd:
                 res = sd.seed_chain(ctx, prm, buf, off)
@@ -119,7 +120,7 @@ def main():
                 bad += 1
                 if len(detail) < 10:
                     same_set = ga.shape == ea.shape and np.array_equal(ga[np.lexsort((ga[:, 1], ga[:, 0]))], ea[np.lexsort((ea[:, 1], ea[:, 0]))])
-                    detail.append({"round": rnd, "read": r, "len": len(read), "w": w, "k": k, "mid_occ": mid, "occ_dist": dist, "q_occ_frac": frac,
+                    detail.append({"round": rnd, "read": r, "len": len(read), "w": w, "k": k, "hpc": hpc, "mid_occ": mid, "occ_dist": dist, "q_occ_frac": frac,
                                    "max_max_occ": mmo, "anchors": [int(len(ga)), int(len(ea))], "rep": [int(rep[r]), erep],
                                    "mini_pos": [int(len(gmp)), int(len(emp))], "same_anchor_set": bool(same_set)})
         rix.close()
