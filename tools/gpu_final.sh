@@ -2,7 +2,7 @@
 # final validation of round 2 / session 3: smoke, all GPU tests, the contract bench, the seeding bench at full size
 set +e
 mkdir -p gpurun_out
-T=r6y
+T=r7k
 python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -2
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/${T}_tests.log
 SECONDS=0; timeout 1200 python bench.py > gpurun_out/${T}_bench_ont.json 2> gpurun_out/${T}_bench_ont.err; echo "ont rc=$? wall ${SECONDS}s"; tail -2 gpurun_out/${T}_bench_ont.err
