@@ -214,6 +214,7 @@ def seed_chain_leg(pkg, torch, dist, w, rank, local_rank, world, host_threads, n
     """Device seeding + chaining (include/mm2gb_seed.h) on `n_reads` reads of the workload's reference: end to end from host
     sequences, device-resident, stage timers; the reference's mm_map_seed + mg_lchain_dp on the host threads beside it."""
     from mm2gb_b200 import seed, synth
+    os.environ.setdefault("MM2GB_STAGE_THREADS", str(max(1, min(8, host_threads))))   # the ranks share the host's cores
     ref = synth.simulate_reference(w["ref_len"], seed=1, n_repeat_copies=w.get("n_repeat_copies", 0), repeat_unit=w.get("repeat_unit", 3000))
     reads = synth.simulate_reads(ref, n_reads, w["lo"], w["hi"], seed=100 + rank, err=w["err"])
     off = np.zeros(len(reads) + 1, dtype=np.int64)

@@ -327,7 +327,9 @@ int stage_range(mm2gb_seeder *sd, const char *seqs, size_t b0, size_t b1)
     if (b1 <= b0) return MM2GB_OK;
     const size_t n_bases = b1 - b0;
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int nt = n_bases < 2 * kStageWindow ? 1 : std::max(1, std::min(kStageThreads, hw / 2));
+    int want = hw / 2;      // MM2GB_STAGE_THREADS: host threads per seeder for staging (several ranks / driver threads share the cores)
+    if (const char *e = getenv("MM2GB_STAGE_THREADS")) want = atoi(e);
+    const int nt = n_bases < 2 * kStageWindow ? 1 : std::max(1, std::min(kStageThreads, want));
     if (nt > 1 && sd->pool.empty())
         for (int t = 1; t < kStageThreads; ++t) sd->pool.emplace_back(stage_worker, sd, t);
     sd->job_seqs = seqs; sd->job_b0 = b0; sd->job_b1 = b1;
