@@ -76,7 +76,10 @@ int mm2gb_glue_enabled(void)
     if (g_enabled < 0) {
         const char *e = getenv("MM2GB_GPU_SEED");
         g_enabled = (e && atoi(e)) ? 1 : 0;
-        if (g_enabled) atexit(glue_atexit);
+        if (g_enabled) {
+            atexit(glue_atexit);
+            setenv("MM2GB_STAGE_THREADS", "2", 0);     /* several worker threads share the cores: two staging threads per seeder */
+        }
     }
     return g_enabled;
 }
