@@ -352,6 +352,12 @@ def main():
         return
 
     # ---- our arm ----------------------------------------------------------------------------------------------------
+    # a rank runs next to its GPU: on a box with several NUMA nodes the process is confined to the CPUs of the GPU's node before
+    # anything is allocated (mm2-gb_b200/sharding.py: place_rank); a no-op for one rank or without exposed topology
+    from mm2gb_b200 import sharding as _sharding
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    placement = {"pinned": False, "why": "MM2GB_BENCH_NO_PIN"} if os.environ.get("MM2GB_BENCH_NO_PIN") else _sharding.place_rank(local_rank, local_world)
+    cfg["host_placement"] = placement
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the chaining path has no CPU fallback")
@@ -438,7 +444,7 @@ def main():
     #      D2H of chains + chain-anchor indices, and on the calling threads kmalloc of u / a', compact_a's gather, kfree of the
     #      input arrays, post_chaining_helper.  The seeded reads of every step are built before the clock starts.
     import ctypes as C
-    host_threads = max(1, cpu_threads() // max(1, world))
+    host_threads = max(1, cpu_threads() // max(1, placement["ranks_sharing"] if placement.get("pinned") else world))
     drv_threads = int(os.environ.get("MM2GB_BENCH_THREADS", "0")) or host_threads
     e2e_steps = max(1, min(args.steps, 8))
     D = C.CDLL(os.path.join(ROOT, "tests", "_build", "libdropin_test.so"))

@@ -60,6 +60,10 @@ int mm2gb_device_count(void);
 int mm2gb_device_memory(int device, size_t *free_bytes, size_t *total_bytes);
 /* total memory only, without creating a context on the device (bringing a GPU up can take seconds) */
 int mm2gb_device_total_memory(int device, size_t *total_bytes);
+/* Confines the CALLING thread to the CPUs Linux lists as local to `device` (the NUMA node of its PCI function), so that the
+ * host passes of that thread and the pages it touches stay on the GPU's node.  Returns 1 if the affinity was changed, 0 where
+ * the box exposes no topology or with MM2GB_NUMA=0.  The staging of a context is placed that way regardless of the caller. */
+int mm2gb_bind_thread_near_device(int device);
 
 /* One context per (host thread, GPU).  `max_anchors` / `max_reads` bound one batch; `n_slots` (1..8) is the
  * number of batches that may be in flight (each slot owns a stream, pinned staging and device buffers).

@@ -14,6 +14,7 @@
 #include "chain_kernels.cuh"
 #include "backtrack_kernels.cuh"
 #include "wire.h"
+#include "host_place.h"
 #include "../../include/mm2gb_chain.h"
 
 #include <sys/mman.h>
@@ -70,6 +71,13 @@ extern "C" int mm2gb_device_total_memory(int device, size_t *total_bytes)
     CK(cudaGetDeviceProperties(&prop, device));
     if (total_bytes) *total_bytes = prop.totalGlobalMem;
     return MM2GB_OK;
+}
+
+extern "C" int mm2gb_bind_thread_near_device(int device)
+{
+    cpu_set_t near;
+    if (!mm2gb::gpu_local_cpus(device, &near)) return 0;
+    return sched_setaffinity(0, sizeof(near), &near) == 0 ? 1 : 0;
 }
 
 extern "C" int mm2gb_device_memory(int device, size_t *free_bytes, size_t *total_bytes)
@@ -804,6 +812,8 @@ extern "C" int mm2gb_ctx_create_ex(mm2gb_ctx_t **out, int device, size_t max_anc
             // The staging block: transparent-huge-page backed memory of our own, registered with CUDA.  Pinning is paid per page,
             // so 2 MB pages make this ~10x cheaper than cudaMallocHost's 4 KB pages (which took ~100 ms per 230 MB and serialised
             // the driver threads), and the host pass over the staging area takes fewer TLB misses.  MM2GB_PIN=alloc: cudaMallocHost.
+            // The pages are first touched / pinned on the NUMA node of the GPU (host_place.h).
+            mm2gb::NearGpu near_gpu(device);
             const char *pm = getenv("MM2GB_PIN");
             bool done = false;
             if (!pm || strcmp(pm, "alloc") != 0) {

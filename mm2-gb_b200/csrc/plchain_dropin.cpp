@@ -522,7 +522,16 @@ extern "C" void init_stream_gpu(size_t *max_total_n, int *max_reads, int *min_n,
 extern "C" void chain_stream_gpu(const mm2gb_idx_t *mi, const mm2gb_mapopt_t *opt, mm2gb_chain_read_t **in_arr_, int *n_read_, int thread_id, void *km)
 {
     ThreadState &S = state_of(thread_id);
-    if (S.n_batches == 0) VLOG(2, "thread %d: first chain_stream_gpu", thread_id);
+    if (S.n_batches == 0) {
+        VLOG(2, "thread %d: first chain_stream_gpu", thread_id);
+        // MM2GB_PIN_THREADS=1: the driver thread moves next to its GPU (several GPUs on a multi-socket box: every gather / publish
+        // pass stays on the GPU's node).  Off by default: with fewer GPUs than sockets it would take the far cores away from the
+        // driver's own stages (seeding, alignment), which run on the same threads.
+        if (getenv("MM2GB_PIN_THREADS") && atoi(getenv("MM2GB_PIN_THREADS")) != 0) {
+            const int moved = mm2gb_bind_thread_near_device(S.device);
+            VLOG(1, "thread %d: %s the CPUs of GPU %d", thread_id, moved ? "moved to" : "no topology, not moved to", S.device);
+        }
+    }
     const Misc_abi misc = batch_misc(mi, opt);
     mm2gb_chain_read_t *in = in_arr_ ? *in_arr_ : nullptr;
     const int n_in = (n_read_ && in) ? *n_read_ : 0;

@@ -8,6 +8,7 @@
 // as an open-addressing table in HBM.
 #include "seed_kernels.cuh"
 #include "../../include/mm2gb_seed.h"
+#include "host_place.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -573,6 +574,7 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
     sd->max_mv = std::max<int64_t>(1024, (int64_t)((double)max_bases * 3.0 / (idx->w + 1)) + 64 * (int64_t)max_reads);
     const size_t M = (size_t)sd->max_mv, A = (size_t)max_anchors, R = (size_t)max_reads + 2, NT = (size_t)sd->max_tiles + 2;
     int rc = MM2GB_OK;
+    mm2gb::NearGpu near_gpu(sd->device);   // the pinned staging windows and counters below land on the GPU's NUMA node
 #define TRY(x) do { if ((rc = (x)) != MM2GB_OK) { mm2gb_seeder_destroy(sd); return rc; } } while (0)
 #define TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(MM2GB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); mm2gb_seeder_destroy(sd); return rc; } } while (0)
     TRYC(cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking));
@@ -734,6 +736,7 @@ extern "C" int mm2gb_seed_chain(mm2gb_seeder_t *sd, mm2gb_ctx_t *ctx, const mm2g
     rc = upload_offsets(sd, seq_off, n_reads);
     if (rc) return rc;
     if (!sd->h_b) {   // result landing buffers (pinned, mapped): allocated on first use, the parity / device-resident entries never need them
+        mm2gb::NearGpu near_gpu(sd->device);   // pinned on the GPU's NUMA node
         CK(cudaHostAlloc((void **)&sd->h_b, (size_t)sd->max_anchors * sizeof(mm2gb_anchor_t), cudaHostAllocMapped));
         CK(cudaHostAlloc((void **)&sd->h_u, (size_t)sd->max_anchors * sizeof(uint64_t), cudaHostAllocMapped));
     }

@@ -44,3 +44,67 @@ def reduce_job(dist, sums, maxes, device="cpu"):
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
     return [float(x) for x in s.tolist()], [float(x) for x in m.tolist()]
+
+
+# ---- host placement of a rank: the CPUs next to its GPU ----------------------------------------------------------------
+# The end-to-end path of a rank is bound by host memory passes (gather into pinned staging, compact_a's gather).
+# On a box with more than one NUMA node a rank whose worker threads or staging pages sit on the far node pays the socket
+# interconnect for every one of those passes, so a rank is confined to the CPUs of its GPU's node BEFORE it allocates
+# anything (first touch then places its buffers there too).  Where the box exposes a single node nothing is changed.
+
+def plan_rank_cpus(gpu_cpus, local_rank: int, all_cpus):
+    """CPUs this rank should run on and the number of ranks sharing them: (cpus, sharers), or (None, local_world) when there
+    is nothing to gain -- no topology (a GPU's set is empty or covers every CPU), or a GPU whose node has no usable CPU.
+    `gpu_cpus[r]` = CPUs NVML reports as local to the GPU of local rank r; `all_cpus` = the CPUs the process may use."""
+    allc = frozenset(all_cpus)
+    sets = [frozenset(c) & allc for c in gpu_cpus]
+    world = len(sets)
+    if not 0 <= local_rank < world:
+        raise ValueError("local_rank outside the box")
+    if any(len(s) == 0 for s in sets) or all(s == allc for s in sets):
+        return None, world
+    mine = sets[local_rank]
+    sharers = sum(1 for s in sets if s == mine)
+    return sorted(mine), sharers
+
+
+def gpu_local_cpus(n_gpus: int):
+    """NVML's ideal CPU set of each of the first `n_gpus` GPUs (honouring a numeric CUDA_VISIBLE_DEVICES); [] for a GPU NVML
+    cannot describe."""
+    import os
+    out = []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+    except Exception:
+        return [[] for _ in range(n_gpus)]
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    n_words = (max(os.cpu_count() or 1, 1) + 63) // 64
+    for r in range(n_gpus):
+        try:
+            idx = int(vis[r]) if r < len(vis) and vis[r].isdigit() else r
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+            out.append([64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1])
+        except Exception:
+            out.append([])
+    return out
+
+
+def place_rank(local_rank: int, local_world: int):
+    """Confine this process to the CPUs of its GPU's NUMA node (see above).  Returns a small report for the bench line."""
+    import os
+    try:
+        allc = sorted(os.sched_getaffinity(0))
+    except Exception:
+        return {"pinned": False, "why": "no sched_getaffinity"}
+    if local_world <= 1:
+        return {"pinned": False, "why": "one rank", "cpus": len(allc)}
+    cpus, sharers = plan_rank_cpus(gpu_local_cpus(local_world), local_rank, allc)
+    if cpus is None:
+        return {"pinned": False, "why": "no NUMA topology exposed for the GPUs", "cpus": len(allc), "ranks_sharing": local_world}
+    try:
+        os.sched_setaffinity(0, cpus)
+    except Exception as e:                                   # keep running unpinned
+        return {"pinned": False, "why": "sched_setaffinity: %s" % e, "cpus": len(allc), "ranks_sharing": local_world}
+    return {"pinned": True, "cpus": len(cpus), "first_cpu": cpus[0], "last_cpu": cpus[-1], "ranks_sharing": sharers}

@@ -76,3 +76,64 @@ def test_two_ranks_gloo_sum_of_work_max_of_time(tmp_path):
     assert res["maxes"] == [11.0]
     (a0, a1), (b0, b1) = res["ranges"]
     assert a0 == 0 and a1 == b0 and b1 == res["reads"]
+
+
+def test_rank_placement_plan(pkg):
+    """host placement of a rank (bench under torchrun): CPUs of the GPU's NUMA node, or nothing where no topology shows"""
+    from mm2gb_b200 import sharding
+    allc = list(range(64))
+    node0, node1 = list(range(0, 32)), list(range(32, 64))
+    gpus = [node0] * 4 + [node1] * 4
+    for r in range(8):
+        cpus, sharers = sharding.plan_rank_cpus(gpus, r, allc)
+        assert cpus == (node0 if r < 4 else node1) and sharers == 4
+    # affinity mask of the process narrower than the node
+    cpus, sharers = sharding.plan_rank_cpus(gpus, 5, list(range(16, 48)))
+    assert cpus == list(range(32, 48)) and sharers == 4
+    # flat box: every GPU reports every CPU -> leave the scheduler alone
+    assert sharding.plan_rank_cpus([allc] * 8, 3, allc) == (None, 8)
+    # NVML silent for one GPU, or a node without usable CPUs -> no pinning either
+    assert sharding.plan_rank_cpus([node0, []], 0, allc) == (None, 2)
+    assert sharding.plan_rank_cpus([node0, node1], 1, node0) == (None, 2)
+    # uneven: 3 GPUs on one node, 1 on the other
+    cpus, sharers = sharding.plan_rank_cpus([node0, node0, node0, node1], 3, allc)
+    assert cpus == node1 and sharers == 1
+    # one rank / no NVML in this container: a report, never an exception, and the affinity is untouched
+    import os
+    before = os.sched_getaffinity(0)
+    rep = sharding.place_rank(0, 1)
+    assert rep["pinned"] is False
+    rep = sharding.place_rank(1, 2)
+    assert rep["pinned"] is False and os.sched_getaffinity(0) == before
+
+
+def test_cpulist_parser_of_the_staging_placement(tmp_path):
+    """csrc/host_place.h: the sysfs local_cpulist format ("0-31,64-95") -> cpu set (host-only code, compiled with g++)"""
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "host_place.h"
+#include <cstring>
+int main(int argc, char **argv) {
+    cpu_set_t s;
+    int n = mm2gb::parse_cpulist(argv[1], &s);
+    printf("%d", n);
+    for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &s)) printf(" %d", c);
+    printf("\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "mm2-gb_b200", "csrc"), "-I", cuda_inc, "-o", str(exe), str(src)],
+                   check=True)
+
+    def parse(s):
+        out = subprocess.run([str(exe), s], check=True, capture_output=True, text=True).stdout.split()
+        return int(out[0]), [int(x) for x in out[1:]]
+    assert parse("0-3,8-9\n") == (6, [0, 1, 2, 3, 8, 9])
+    assert parse("5") == (1, [5])
+    assert parse("0-1,1-2") == (3, [0, 1, 2])
+    assert parse("") == (0, [])
+    assert parse("\n") == (0, [])
+    assert parse("7-3") == (0, [])          # malformed range: nothing
+    assert parse("2,x") == (1, [2])
