@@ -561,6 +561,9 @@ __device__ __forceinline__ u64 cta_lookback(volatile u64 *st, int tile, u64 tot,
 #ifndef MM2GB_SKETCHP_MIN_CTAS
 #define MM2GB_SKETCHP_MIN_CTAS 3
 #endif
+#ifndef MM2GB_SKETCHP_V2
+#define MM2GB_SKETCHP_V2 1     // 0: the r7 form of the two phases marked below (A/B: profiles/r8d_sketch_ab.txt)
+#endif
 __global__ void __launch_bounds__(kTile, MM2GB_SKETCHP_MIN_CTAS)
 k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict__ seq_off, const int *__restrict__ tile_first, const int *__restrict__ tile_seq,
             int n_seq, int n_tiles, int w, int k, int rid_is_seq, u64 *__restrict__ ticket, int tile_begin, int tile_end, u64 *__restrict__ scan_state, long long cap, u64 *__restrict__ mv_x,
@@ -686,6 +689,35 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
                 S.iz[buf][j] = z;
             }
             __syncthreads();
+#if MM2GB_SKETCHP_V2
+            {   // the four running minima (prefix / suffix x rightmost / leftmost key) of a chunk on four different warps: the CTA waits
+                // for w dependent steps instead of 2 w steps of twice the work (ncu r8c: 18 % of the stall samples behind this barrier)
+                const int nch = (nloc + w - 1) / w, R = (nch + 31) & ~31;
+                for (int idx = tid; idx < 4 * R; idx += kTile) {
+                    const int role = idx / R, cidx = idx - role * R;       // warp-uniform: R and kTile are multiples of 32
+                    if (cidx >= nch) continue;
+                    const int c0 = cidx * w, c1 = min(c0 + w, nloc);
+                    u64 *dst = role == 0 ? S.pre_r : role == 1 ? S.pre_l : role == 2 ? S.suf_r : S.suf_l;
+                    const bool right = (role & 1) == 0;
+                    u64 m = ~0ULL;
+                    if (role < 2) {
+                        for (int j = c0; j < c1; ++j) {
+                            const u32 h = S.ih[buf][j];
+                            const u64 key = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)(right ? 2047 - j : j));
+                            m = min(m, key);
+                            dst[j] = m;
+                        }
+                    } else {
+                        for (int j = c1 - 1; j >= c0; --j) {
+                            const u32 h = S.ih[buf][j];
+                            const u64 key = h == NONE ? ~0ULL : ((u64)h << 11 | (u64)(right ? 2047 - j : j));
+                            m = min(m, key);
+                            dst[j] = m;
+                        }
+                    }
+                }
+            }
+#else
             for (int cidx = tid; cidx * w < nloc; cidx += kTile) {
                 const int c0 = cidx * w, c1 = min(c0 + w, nloc);
                 u64 mr = ~0ULL, ml = ~0ULL;
@@ -703,6 +735,7 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
                     S.suf_r[j] = mr; S.suf_l[j] = ml;
                 }
             }
+#endif
             __syncthreads();
             i = t0 + tid; jj = w + tid;
             in_range = i < len;
@@ -733,6 +766,19 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
             if (lane == 31) S.warp_sum[buf][wid] = v;
         }
         const bool many = __syncthreads_or(valid && c > 2);
+#if MM2GB_SKETCHP_V2
+        if (valid) {
+            // every warp scans the kTile / 32 warp totals itself (they are final after the barrier above): no second barrier, no
+            // round trip through shared memory (ncu r8c: 10 % of the stall samples sat behind it); warp 0 publishes the aggregate
+            u32 t = lane < kTile / 32 ? S.warp_sum[buf][lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            tot = __shfl_sync(0xffffffffu, t, 31);
+            const u32 before = __shfl_sync(0xffffffffu, t, (wid + 31) & 31);
+            if (wid == 0 && lane == 31) { __threadfence(); st[tile] = (tile == 0 ? MM2GB_FLAG_PREFIX : MM2GB_FLAG_AGG) | (u64)tot; }
+            v = v - (u32)c + (wid ? before : 0u);                        // exclusive offset of this thread inside the tile
+        }
+#else
         if (valid) {
             if (wid == 0) {
                 u32 t = lane < kTile / 32 ? S.warp_sum[buf][lane] : 0u;
@@ -745,6 +791,7 @@ k_sketch32p(const unsigned char *__restrict__ seqs, const long long *__restrict_
             tot = S.warp_sum[buf][kTile / 32 - 1];
             v = v - (u32)c + (wid ? S.warp_sum[buf][wid - 1] : 0u);      // exclusive offset of this thread inside the tile
         }
+#endif
         // finish the deferred tile: its predecessors have had a whole tile's time to publish
         if (have_prev) {
             const u64 excl = p_tile ? cta_lookback(st, p_tile, p_tot, S) : 0ULL;

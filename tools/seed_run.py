@@ -31,4 +31,5 @@ prm = seed.map_ont_seed_params(ix.mid_occ())
 sd = seed.Seeder(ix, max_bases=int(off[-1]) + 4096, max_reads=len(reads) + 8, max_anchors=int(off[-1]))
 for _ in range(args.iters):
     a, a_off, rep, _, _ = sd.seed(prm, buf, off, want_mini_pos=False)
-print("anchors", int(a_off[-1]), sd.profile())
+import hashlib
+print("anchors", int(a_off[-1]), "sha1", hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16], "bases", int(off[-1]), sd.profile())
