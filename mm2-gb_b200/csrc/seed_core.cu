@@ -79,7 +79,8 @@ struct mm2gb_seeder {
     cudaEvent_t ev[MM2GB_SEED_NTIMERS + 1] = {nullptr};
     cudaEvent_t ev_join = nullptr;
     cudaStream_t stage_stream[8] = {nullptr};
-    cudaEvent_t stage_ev[8][2] = {{nullptr}}, stage_done[8] = {nullptr};
+    cudaEvent_t stage_ev[8][4] = {{nullptr}}, stage_done[8] = {nullptr};
+    int stage_pos[8] = {0};            // next window of a staging thread's ring (persists across jobs, see stage_slice)
     // staging workers (pageable sources): created on first use, parked on a condition variable between jobs
     std::vector<std::thread> pool;
     std::mutex pool_mu;
@@ -269,8 +270,12 @@ int upload_offsets(mm2gb_seeder *sd, const int64_t *seq_off, int n_seq)
 // Sequences -> device.  Pinned sources are DMA'd as they are.  Pageable ones are staged through pinned windows by kStageThreads
 // host threads, each with its own stream and two windows (the copy into one overlaps the DMA of the other): a single thread's
 // memcpy (~10 GB/s) would be five times slower than the link.
+// A thread's windows form a ring that carries over from one job (chunk) to the next: a chunk's slice is smaller than a window or
+// two, and a thread that started every job at window 0 would first wait for the DMA of its previous slice -- copy and DMA in
+// lockstep, ~19 GB/s from pageable memory (profiles/r8d_sketch_ab.txt: the sketch stage was bound by this, not by the kernel).
 constexpr int kStageThreads = 8;
-constexpr size_t kStageWindow = (size_t)2 << 20;
+constexpr int kStageRing = 4;
+constexpr size_t kStageWindow = (size_t)1 << 20;
 
 static bool is_pinned_host(const void *p)
 {
@@ -287,10 +292,10 @@ static void stage_slice(mm2gb_seeder *sd, int t, int nt)
     err = cudaSetDevice(sd->device);
     const size_t n_bases = sd->job_b1 - sd->job_b0;
     const size_t lo = sd->job_b0 + n_bases * (size_t)t / (size_t)nt, hi = sd->job_b0 + n_bases * (size_t)(t + 1) / (size_t)nt;
-    int which = 0;
-    for (size_t done = lo; done < hi && err == cudaSuccess; which ^= 1) {
+    int which = sd->stage_pos[t];
+    for (size_t done = lo; done < hi && err == cudaSuccess; which = (which + 1) % kStageRing) {
         const size_t n = std::min(kStageWindow, hi - done);
-        unsigned char *stg = sd->h_seq + ((size_t)t * 2 + (size_t)which) * kStageWindow;
+        unsigned char *stg = sd->h_seq + ((size_t)t * kStageRing + (size_t)which) * kStageWindow;
         cudaEvent_t ev = sd->stage_ev[t][which];
         if ((err = cudaEventSynchronize(ev)) != cudaSuccess) break;     // the window's previous DMA (a never-recorded event is complete)
         memcpy(stg, sd->job_seqs + done, n);
@@ -298,6 +303,7 @@ static void stage_slice(mm2gb_seeder *sd, int t, int nt)
         err = cudaEventRecord(ev, sd->stage_stream[t]);
         done += n;
     }
+    sd->stage_pos[t] = which;
     if (err == cudaSuccess) err = cudaEventRecord(sd->stage_done[t], sd->stage_stream[t]);
 }
 
@@ -613,7 +619,7 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
     TRYC(cudaHostAlloc((void **)&sd->h_mp_off, R * sizeof(long long), cudaHostAllocDefault));
     TRYC(cudaHostAlloc((void **)&sd->h_rep_len, R * sizeof(int), cudaHostAllocDefault));
     TRYC(cudaHostAlloc((void **)&sd->h_tot, 64, cudaHostAllocDefault));
-    TRYC(cudaHostAlloc((void **)&sd->h_seq, (size_t)kStageThreads * 2 * kStageWindow, cudaHostAllocDefault));
+    TRYC(cudaHostAlloc((void **)&sd->h_seq, (size_t)kStageThreads * kStageRing * kStageWindow, cudaHostAllocDefault));
     {
         // the x-sort keeps one digit byte per anchor of a read in shared memory; reads above the largest class use HBM for them
         int dev_smem = 0;

@@ -18,6 +18,7 @@ ap.add_argument("--lo", type=int, default=10000)
 ap.add_argument("--hi", type=int, default=100000)
 ap.add_argument("--err", type=float, default=0.10)
 ap.add_argument("--repeats", type=int, default=-1)
+ap.add_argument("--pinned", action="store_true", help="sequences in pinned host memory (DMA as they are): the sketch stage is then bound by the kernel, not by staging")
 args = ap.parse_args()
 pkg = entry.load_package()
 from mm2gb_b200 import seed, synth  # noqa: E402
@@ -26,6 +27,9 @@ reads = synth.simulate_reads(ref, args.reads, args.lo, args.hi, seed=2, err=args
 off = np.zeros(len(reads) + 1, dtype=np.int64)
 off[1:] = np.cumsum([len(r) for r in reads])
 buf = synth._NT[np.concatenate(reads)]
+if args.pinned:
+    import torch
+    buf = torch.from_numpy(buf).pin_memory().numpy()
 ix = seed.Index((synth._NT[ref], np.array([0, len(ref)], dtype=np.int64)), w=10, k=15)
 prm = seed.map_ont_seed_params(ix.mid_occ())
 sd = seed.Seeder(ix, max_bases=int(off[-1]) + 4096, max_reads=len(reads) + 8, max_anchors=int(off[-1]))
