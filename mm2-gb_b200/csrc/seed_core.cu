@@ -70,6 +70,10 @@ struct mm2gb_index {
     uint64_t mask = 0;
 };
 
+// streams the size classes of the x-sort are spread over (run_sort): one per class, so that every class is on the GPU at once -- a
+// class of long reads is a few dozen single-warp CTAs, and classes queued behind each other on a shared stream leave most SMs idle
+constexpr int kSortStreams = 14;
+
 struct mm2gb_seeder {
     const mm2gb_index *idx = nullptr;
     int device = 0;
@@ -123,8 +127,8 @@ struct mm2gb_seeder {
     unsigned char *d_dig = nullptr;                // digits of reads too long for shared memory
     int4 *d_stack = nullptr;
     int *d_sort_list = nullptr, *h_sort_list = nullptr;
-    cudaStream_t sort_stream[4] = {nullptr};
-    cudaEvent_t sort_fork = nullptr, sort_join[4] = {nullptr};
+    cudaStream_t sort_stream[kSortStreams] = {nullptr};
+    cudaEvent_t sort_fork = nullptr, sort_join[kSortStreams] = {nullptr};
     int *d_f = nullptr, *d_p = nullptr;
     int sort_max_cap = 0;
     bool sketch_persistent = true;     // k_sketch32p (MM2GB_SKETCH_PERSISTENT=0: one CTA per tile, k_sketch32)
@@ -458,12 +462,16 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
     cudaStream_t st = sd->stream;
     CK(cudaMemcpyAsync(sd->d_sort_list, sd->h_sort_list, (size_t)pos * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(sd->sort_fork, st));
+    static const int n_streams = [] {       // MM2GB_SORT_STREAMS: A/B against the four streams of r7 (profiles/r8f_sort_streams.txt)
+        const char *e = getenv("MM2GB_SORT_STREAMS");
+        return std::max(1, std::min(kSortStreams, e ? atoi(e) : kSortStreams));
+    }();
     int used = 0;
     for (int k = nc; k >= 0; --k) {
         const int cnt = (int)bin[(size_t)k].size();
         if (!cnt) continue;
         const int cap = k < nc ? cls[(size_t)k].cap : 0, warps = k < nc ? cls[(size_t)k].warps : 1;
-        cudaStream_t ss = sd->sort_stream[used & 3];
+        cudaStream_t ss = sd->sort_stream[used % n_streams];
         CK(cudaStreamWaitEvent(ss, sd->sort_fork, 0));
         const size_t smem = (size_t)warps * ((size_t)cap + sizeof(SortShared));
         if (k < nc)
@@ -475,7 +483,7 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
         CK(cudaGetLastError());
         ++used;
     }
-    for (int i = 0; i < std::min(used, 4); ++i) {
+    for (int i = 0; i < std::min(used, n_streams); ++i) {
         CK(cudaEventRecord(sd->sort_join[i], sd->sort_stream[i]));
         CK(cudaStreamWaitEvent(st, sd->sort_join[i], 0));
     }
