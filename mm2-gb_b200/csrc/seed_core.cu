@@ -466,10 +466,13 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
         const char *e = getenv("MM2GB_SORT_STREAMS");
         return std::max(1, std::min(kSortStreams, e ? atoi(e) : kSortStreams));
     }();
+    // experiment switch: the HBM class after all others, alone on the GPU (145-148 ms on the workload above: steadier, slower)
+    static const bool hbm_alone = getenv("MM2GB_SORT_HBM_ALONE") && atoi(getenv("MM2GB_SORT_HBM_ALONE")) != 0;
     int used = 0;
     for (int k = nc; k >= 0; --k) {
         const int cnt = (int)bin[(size_t)k].size();
         if (!cnt) continue;
+        if (hbm_alone && k == nc) continue;
         const int cap = k < nc ? cls[(size_t)k].cap : 0, warps = k < nc ? cls[(size_t)k].warps : 1;
         cudaStream_t ss = sd->sort_stream[used % n_streams];
         CK(cudaStreamWaitEvent(ss, sd->sort_fork, 0));
@@ -486,6 +489,11 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
     for (int i = 0; i < std::min(used, n_streams); ++i) {
         CK(cudaEventRecord(sd->sort_join[i], sd->sort_stream[i]));
         CK(cudaStreamWaitEvent(st, sd->sort_join[i], 0));
+    }
+    if (hbm_alone && !bin[(size_t)nc].empty()) {      // after every other class has left the GPU
+        k_seed_sort<false><<<(int)bin[(size_t)nc].size(), 32, sizeof(SortShared), st>>>(sd->d_a_tmp, sd->d_a, sd->d_a_off, sd->d_sort_list + start[(size_t)nc],
+                                                                                       (int)bin[(size_t)nc].size(), 0, sd->d_dig, sd->d_dest, sd->d_lst, sd->d_stack);
+        CK(cudaGetLastError());
     }
     return MM2GB_OK;
 }
@@ -635,6 +643,14 @@ extern "C" int mm2gb_seeder_create(mm2gb_seeder_t **out, const mm2gb_index_t *id
         sd->sort_max_cap = ((dev_smem - (int)sizeof(SortShared) - 1024) / 16) * 16;
         if (const char *e = getenv("MM2GB_SEED_SORT_CAP")) sd->sort_max_cap = std::max(64, std::min(sd->sort_max_cap, atoi(e) / 16 * 16));
         TRYC(cudaFuncSetAttribute(k_seed_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sd->sort_max_cap + (int)sizeof(SortShared)));
+        // The class whose digits stay in HBM (reads above sort_max_cap anchors) is one serial chain of dependent loads per read and
+        // needs next to no shared memory: it asks for the largest L1.  Without the preference its CTAs ran with whatever carve-out
+        // the SM had (usually the near-full shared memory of the other classes): 214-219 ms against 123 ms for the x-sort of 300
+        // reads of 190 k anchors, with both figures (and 94 ms, an SM of its own) appearing from launch to launch
+        // (profiles/r8g_sort_probe.txt, r8h_sort_probe.txt; MM2GB_SORT_L1=0 switches the preference off)
+        if (!(getenv("MM2GB_SORT_L1") && atoi(getenv("MM2GB_SORT_L1")) == 0))
+            if (cudaFuncSetAttribute(k_seed_sort<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1) != cudaSuccess)
+                cudaGetLastError();      // a preference only
         int n_sm = 0, per_sm = 0;
         TRYC(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, sd->device));
         TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sketch32p, kTile, 0));
