@@ -356,7 +356,10 @@ def main():
     # anything is allocated (mm2-gb_b200/sharding.py: place_rank); a no-op for one rank or without exposed topology
     from mm2gb_b200 import sharding as _sharding
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    placement = {"pinned": False, "why": "MM2GB_BENCH_NO_PIN"} if os.environ.get("MM2GB_BENCH_NO_PIN") else _sharding.place_rank(local_rank, local_world)
+    try:
+        placement = {"pinned": False, "why": "MM2GB_BENCH_NO_PIN"} if os.environ.get("MM2GB_BENCH_NO_PIN") else _sharding.place_rank(local_rank, local_world)
+    except Exception as e:      # placement is an optimisation: never the reason a run fails
+        placement = {"pinned": False, "why": "place_rank failed: %s" % e}
     cfg["host_placement"] = placement
     import torch
     if not torch.cuda.is_available():
