@@ -70,9 +70,13 @@ struct mm2gb_index {
     uint64_t mask = 0;
 };
 
-// streams the size classes of the x-sort are spread over (run_sort): one per class, so that every class is on the GPU at once -- a
-// class of long reads is a few dozen single-warp CTAs, and classes queued behind each other on a shared stream leave most SMs idle
+// Streams the size classes of the x-sort are spread over (run_sort), round robin.  kSortStreams is what a seeder owns, the default in
+// use is four (MM2GB_SORT_STREAMS).  One stream per class is faster for the sort on its own (2.91 -> 2.6 ms on 3000 reads of 10-100 kb,
+// profiles/r8f_sort_streams.txt) but slower for the fused step on batches that use many classes (10 k reads with repeat-rich
+// outliers: 62.8 ms with four streams, 67.8 ms with fourteen, profiles/r8j-r8l_seed_full*.json): the chain-extraction classes that
+// follow on the context's own streams then share hardware queues with them.
 constexpr int kSortStreams = 14;
+constexpr int kSortStreamsDefault = 4;
 
 struct mm2gb_seeder {
     const mm2gb_index *idx = nullptr;
@@ -462,9 +466,9 @@ int run_sort(mm2gb_seeder *sd, int n_reads)
     cudaStream_t st = sd->stream;
     CK(cudaMemcpyAsync(sd->d_sort_list, sd->h_sort_list, (size_t)pos * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(sd->sort_fork, st));
-    static const int n_streams = [] {       // MM2GB_SORT_STREAMS: A/B against the four streams of r7 (profiles/r8f_sort_streams.txt)
+    static const int n_streams = [] {       // MM2GB_SORT_STREAMS: see kSortStreams
         const char *e = getenv("MM2GB_SORT_STREAMS");
-        return std::max(1, std::min(kSortStreams, e ? atoi(e) : kSortStreams));
+        return std::max(1, std::min(kSortStreams, e ? atoi(e) : kSortStreamsDefault));
     }();
     // experiment switch: the HBM class after all others, alone on the GPU (145-148 ms on the workload above: steadier, slower)
     static const bool hbm_alone = getenv("MM2GB_SORT_HBM_ALONE") && atoi(getenv("MM2GB_SORT_HBM_ALONE")) != 0;
