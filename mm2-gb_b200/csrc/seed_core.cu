@@ -73,8 +73,8 @@ struct mm2gb_index {
 // Streams the size classes of the x-sort are spread over (run_sort), round robin.  kSortStreams is what a seeder owns, the default in
 // use is four (MM2GB_SORT_STREAMS).  One stream per class is faster for the sort on its own (2.91 -> 2.6 ms on 3000 reads of 10-100 kb,
 // profiles/r8f_sort_streams.txt) but slower for the fused step on batches that use many classes (10 k reads with repeat-rich
-// outliers: 62.8 ms with four streams, 67.8 ms with fourteen, profiles/r8j-r8l_seed_full*.json): the chain-extraction classes that
-// follow on the context's own streams then share hardware queues with them.
+// outliers: 62.8 ms with four streams, 67.8 ms with fourteen, profiles/r8j-r8l_seed_full*.json): most likely the chain-extraction
+// classes that follow on the context's own streams then share hardware queues with them (not isolated further).
 constexpr int kSortStreams = 14;
 constexpr int kSortStreamsDefault = 4;
 
