@@ -353,14 +353,14 @@ def main():
 
     # ---- our arm ----------------------------------------------------------------------------------------------------
     # a rank runs next to its GPU: on a box with several NUMA nodes the process is confined to the CPUs of the GPU's node before
-    # anything is allocated (mm2-gb_b200/sharding.py: place_rank); a no-op for one rank or without exposed topology
+    # anything is allocated (mm2-gb_b200/sharding.py: place_rank); a no-op for one rank or without exposed topology.  Reported as
+    # the line's "host_placement" (not inside "config": both arms print the same config)
     from mm2gb_b200 import sharding as _sharding
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     try:
         placement = {"pinned": False, "why": "MM2GB_BENCH_NO_PIN"} if os.environ.get("MM2GB_BENCH_NO_PIN") else _sharding.place_rank(local_rank, local_world)
     except Exception as e:      # placement is an optimisation: never the reason a run fails
         placement = {"pinned": False, "why": "place_rank failed: %s" % e}
-    cfg["host_placement"] = placement
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the chaining path has no CPU fallback")
@@ -637,7 +637,7 @@ def main():
             "one_batch_at_a_time": {"ms_per_step": ms_seq / args.steps, "value": pairs * args.steps / (ms_seq / 1e3), "unit": "pairs/s",
                                     "note": "the same steps strictly one after the other on one stream (latency of a step; the per-kernel timers and the roofline come from this run)"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": cfg, "reads_per_s": tot_reads * args.steps / sec, "anchors_per_s": tot_anchors * args.steps / sec,
+            "data": "synthetic", "config": cfg, "host_placement": placement, "reads_per_s": tot_reads * args.steps / sec, "anchors_per_s": tot_anchors * args.steps / sec,
             "batch": {"reads": n_reads, "anchors": n, "pairs": pairs, "pairs_per_anchor": pairs / max(1, n), "units": int(st.n_units),
                       "units_exact": int(st.n_units_exact), "units_long_kernel": int(st.n_long), "chains": n_chains, **workload_shape(a, off)},
             "kernel_ms_per_step": {k: v[0] / max(1, v[1]) for k, v in prof.items() if v[1]},
